@@ -1,0 +1,209 @@
+/*
+ * sgmcmc_b200 -- C ABI of the B200-native sgmcmc sampler hot path.
+ *
+ * This is the drop-in boundary.  The reference (STOR-i/sgmcmc,
+ * an R package) has no FFI of its own: below its exported R API every numeric
+ * operation is a TensorFlow op reached through reticulate (R/update.R:44,127-129).
+ * The functions declared here are what the replacement R files bind with .Call
+ * (see INTEGRATION.md and r-package/src/rshim.c); each one names the reference
+ * interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no exceptions / longjmp across the boundary; every function returns
+ *     SGM_OK (0) or a negative sgm_status, and sgm_last_error() holds the message
+ *     (thread-local);
+ *   - host arrays are R-native: column-major doubles.  The library copies inputs in
+ *     sgm_create (the caller may free them at once) and writes outputs into
+ *     caller-allocated buffers;
+ *   - a handle owns all of its device memory; distinct handles are independent, one
+ *     handle is not thread-safe;
+ *   - "flat parameter order" = tensors in names(params) order, each in column-major
+ *     element order; P = total number of scalars;
+ *   - n_chains > 1 runs that many independent replicas of the reference's single
+ *     chain (extension; n_chains = 1 reproduces the reference's behaviour).
+ */
+#ifndef SGMCMC_B200_H
+#define SGMCMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGM_ABI_VERSION 1
+
+typedef enum sgm_status {
+    SGM_OK = 0,
+    SGM_EINVAL = -1,    /* bad argument / unsupported shape                         */
+    SGM_ECUDA = -2,     /* CUDA runtime failure, or no CUDA device (no CPU fallback) */
+    SGM_ENOMODEL = -3,  /* logLik/logPrior is not one of the routed model families    */
+    SGM_EDIVERGED = -4, /* "Chain diverged, try decreasing stepsize" (R/update.R:202) */
+    SGM_ENOMEM = -5,
+    SGM_ESTATE = -6,    /* call order violated (e.g. step before init)                */
+    SGM_ECOMM = -7      /* NCCL failure                                               */
+} sgm_status;
+
+/* Model families routed to hand-written gradient kernels. */
+typedef enum sgm_model {
+    SGM_MODEL_GAUSS_MEAN = 1,  /* vignettes/mvGauss.Rmd:37-54, tests/testthat/test{1d,3d}Gauss.R */
+    SGM_MODEL_MIXTURE2 = 2,    /* vignettes/gaussMixture.Rmd:48-76                               */
+    SGM_MODEL_LOGISTIC = 3,    /* vignettes/logisticRegression.Rmd:45-57                         */
+    SGM_MODEL_SOFTMAX_NET = 4  /* vignettes/nn.Rmd:58-79                                         */
+} sgm_model;
+
+/* Dynamics (R/dynamics.R:7-31, 35-69, 73-120). */
+typedef enum sgm_algo { SGM_ALGO_SGLD = 1, SGM_ALGO_SGHMC = 2, SGM_ALGO_SGNHT = 3 } sgm_algo;
+
+/* One entry of the reference's `dataset` list (R/setup.R:105-113): sliced on dim 0. */
+typedef struct sgm_array {
+    const char* name;
+    const double* data; /* column-major; may be NULL iff sgm_config.synth_rows > 0 */
+    int32_t ndim;       /* 1 or 2 */
+    int64_t dims[4];
+} sgm_array;
+
+/* One entry of the reference's `params` list plus its tuning constants
+ * (convertList, R/setup.R:160-170). */
+typedef struct sgm_param {
+    const char* name;
+    const double* init; /* column-major start value, replicated to every chain */
+    int32_t ndim;       /* 0 = R scalar, 1 = vector, 2 = matrix */
+    int64_t dims[4];
+    double stepsize;    /* epsilon (sgld) / eta (sghmc, sgnht) */
+    double alpha;       /* sghmc friction; ignored otherwise   */
+    double a;           /* sgnht diffusion; ignored otherwise  */
+} sgm_param;
+
+#define SGM_FLAG_SHARED_MODE 1u /* *cv with n_chains > 1: find ONE mode (chain 0's stream) and share it */
+
+/* Everything createSGMCMC / createSGMCMCCV / *Setup take (R/setup.R:2-28,
+ * R/controlVariates.R:2-25, R/sgld.R:114-123 ...). */
+typedef struct sgm_config {
+    int32_t abi_version; /* SGM_ABI_VERSION */
+    int32_t model;       /* sgm_model */
+    int32_t algo;        /* sgm_algo  */
+    int32_t cv;          /* 0: sgld/sghmc/sgnht, 1: *cv */
+    int32_t n_data;
+    const sgm_array* data; /* model's dataset entries, in the order the family documents */
+    int32_t n_params;
+    const sgm_param* params; /* names(params) order = update order (Gauss-Seidel, R/update.R:43-45) */
+    double minibatch_size;   /* < 1: proportion of N (convertProp, R/setup.R:128-140) */
+    int32_t L;               /* sghmc sub-steps (R/sghmc.R:40-41)          */
+    double opt_stepsize;     /* *cv: SGD step of the mode finder (cV.R:87) */
+    int64_t n_iters_opt;     /* *cv: mode-finder iterations (cV.R:42)      */
+    int32_t seeded;          /* 0 = seed=NULL (library draws one from the clock) */
+    uint64_t seed;
+    int32_t n_chains;        /* >= 1 */
+    int32_t device;          /* CUDA device ordinal */
+    uint32_t flags;
+    /* model constants (what the user's closures hard-code) */
+    int32_t use_prior;       /* 0 = logPrior = NULL (flat, R/setup.R:119-123)              */
+    double prior_sd;         /* Gaussian families: Normal(0, prior_sd) on every mean entry   */
+    const double* precision; /* GAUSS_MEAN: d x d Sigma^{-1} (column-major), NULL = identity */
+    /* synthetic dataset generated on the device (too large to ship from the host) */
+    int64_t synth_rows;      /* > 0: ignore data[].data, generate N = synth_rows rows        */
+    int64_t synth_dim;       /* LOGISTIC: d                                                   */
+    uint64_t synth_seed;
+} sgm_config;
+
+typedef struct sgm_handle sgm_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+
+/* *Setup (R/sgld.R:114-123 etc.): validates, uploads the dataset (column-major double
+ * -> row-major float32, 16-byte-aligned row stride), allocates chain state. */
+int sgm_create(const sgm_config* cfg, sgm_handle** out);
+
+/* initSess (R/update.R:126-140): draws the initial momenta (R/dynamics.R:47,84); for
+ * *cv runs getMode + calcFullGrads and sets theta := theta_hat (cV.R:37-52,105-111).
+ * Returns SGM_EDIVERGED with "Chain diverged" if the optimiser produced NaN (cV.R:119). */
+int sgm_init(sgm_handle* h);
+
+/* Deterministic validation mode of initSess: caller supplies standard normals for the
+ * initial momenta ([n_chains][P], may be NULL = zeros) and, for *cv, the 0-based
+ * minibatch rows of every optimiser iteration ([n_chains][n_iters_opt][n]). */
+int sgm_init_deterministic(sgm_handle* h, const float* momentum_noise, const int32_t* opt_idx);
+
+void sgm_destroy(sgm_handle* h);
+
+/* ---- stepping -------------------------------------------------------------------- */
+
+/* sgmcmcStep (R/update.R:40-81) with device-side minibatch sampling and noise. */
+int sgm_step(sgm_handle* h);
+
+/* sgmcmcStep in the deterministic validation mode: idx = 0-based rows
+ * [n_chains][n_sub][n] (n_sub = L for sghmc, else 1); noise = standard normals
+ * [n_chains][noise_len] in flat parameter order, noise_len = P (sgld, sgnht) or
+ * (L+1)*P (sghmc: refresh block, then one block per sub-step).  Scale factors
+ * (sqrt(2 eps) etc., R/dynamics.R) are applied on the device. */
+int sgm_step_deterministic(sgm_handle* h, const int32_t* idx, const float* noise);
+
+/* runSGMCMC's loop (R/update.R:154-161) on the device: n_iters steps in one launch;
+ * store != 0 appends every post-update state to the device-resident chain
+ * (storeState, R/storage.R:54-60).  Returns SGM_EDIVERGED if a state went non-finite.
+ * Callers loop in chunks (<= 100) to print progress at the reference's cadence. */
+int sgm_run(sgm_handle* h, int64_t n_iters, int store);
+
+/* ---- reading results ------------------------------------------------------------- */
+
+/* getParams (R/storage.R:37-39): [n_chains][P] doubles, flat parameter order. */
+int sgm_get_params(sgm_handle* h, double* out);
+/* Momenta [n_chains][P] and thermostats [n_chains][n_params] (validation). */
+int sgm_get_state(sgm_handle* h, double* momentum, double* thermostat);
+/* *cv: mode estimate and full-data gradient at it, each [n_chains][P]. */
+int sgm_get_mode(sgm_handle* h, double* theta_hat, double* grad_hat);
+
+int64_t sgm_chain_length(const sgm_handle* h);
+/* One copy-out of the stored chain (replaces initStorage/updateStorage,
+ * R/storage.R:42-80).  Layout: for chain c, for parameter p: a column-major
+ * (iters, dims_p...) double array; arrays are concatenated p-major inside c. */
+int sgm_copy_chain(sgm_handle* h, double* out);
+int sgm_reset_chain(sgm_handle* h);
+/* Pre-allocates device storage for n_iters more stored states (initStorage, R/storage.R:42-51). */
+int sgm_reserve_chain(sgm_handle* h, int64_t n_iters);
+
+/* estLogPost on a fresh device-drawn minibatch, one value per chain
+ * (checkDivergence, R/update.R:197-207). */
+int sgm_est_logpost(sgm_handle* h, double* out);
+int sgm_est_logpost_deterministic(sgm_handle* h, const int32_t* idx, double* out);
+
+/* Validation: the gradient estimate getGradients.{sgmcmc,sgmcmccv} would produce at the
+ * current state on the given rows (R/setup.R:36-62): [n_chains][P]. */
+int sgm_grad_estimate(sgm_handle* h, const int32_t* idx, double* out);
+
+/* Held-out log-likelihood of the current state on caller data (replaces the user-built
+ * TF tensors of vignettes/nn.Rmd:113-123): data as in sgm_config.data, out[n_chains]. */
+int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t n_data, double* out);
+
+/* ---- introspection / measurement -------------------------------------------------- */
+
+int64_t sgm_num_rows(const sgm_handle* h);      /* N */
+int32_t sgm_minibatch(const sgm_handle* h);     /* n after convertProp */
+int32_t sgm_num_scalars(const sgm_handle* h);   /* P */
+int32_t sgm_noise_len(const sgm_handle* h);
+/* Device time (CUDA events on the launch stream) and launch count of the last
+ * sgm_init / sgm_step* / sgm_run call's kernels. */
+int sgm_last_timing(const sgm_handle* h, float* kernel_ms, int32_t* launches);
+/* Device time of the last control-variate full-data gradient pass and the bytes it read. */
+int sgm_last_fullgrad_timing(const sgm_handle* h, float* kernel_ms, int64_t* bytes);
+/* Copies rows [row0, row0+rows) of the device dataset back as column-major doubles
+ * (entry k of sgm_config.data); lets tests feed device-generated data to the oracle. */
+int sgm_copy_dataset(sgm_handle* h, int32_t entry, int64_t row0, int64_t rows, double* out);
+
+/* ---- multi-GPU (row-sharded control-variate pass) -------------------- */
+
+#define SGM_NCCL_ID_BYTES 128
+/* Rank 0 fills id (an ncclUniqueId); every rank then calls sgm_comm_init with the same id. */
+int sgm_comm_unique_id(void* id_out, int32_t id_bytes);
+/* After this, sgm_init computes the full-data gradient on rows [rank*N/world, (rank+1)*N/world)
+ * and all-reduces (sum, float32) the [n_chains][P] result with NCCL. */
+int sgm_comm_init(sgm_handle* h, const void* id, int32_t id_bytes, int32_t rank, int32_t world);
+
+const char* sgm_last_error(void);
+const char* sgm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGMCMC_B200_H */

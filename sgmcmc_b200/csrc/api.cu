@@ -1,0 +1,1098 @@
+// C-ABI implementation (include/sgmcmc_b200.h): handle lifecycle, dataset upload,
+// kernel dispatch, chain storage, NCCL row-sharded control-variate pass.
+// No CPU fallback: every entry point needs a CUDA device and fails with SGM_ECUDA
+// otherwise.
+#include <cmath>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+#include <cuda_runtime.h>
+
+#include "../../include/sgmcmc_b200.h"
+#include "common.cuh"
+#include "small_models.cuh"
+#include "logistic.cuh"
+#include "softmax_net.cuh"
+
+using namespace sgm;
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(SGM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* sgm_last_error(void) { return g_err.c_str(); }
+extern "C" const char* sgm_version(void) { return "sgmcmc_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------
+// NCCL through dlopen (the library must load on hosts without NCCL)
+// ------------------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+struct NcclId { char internal[SGM_NCCL_ID_BYTES]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, /*ncclUniqueId by value*/ NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.lib) return SGM_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return fail(SGM_ECOMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(SGM_ECOMM, "libnccl lacks required symbols");
+    g_nccl.lib = lib;
+    return SGM_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------
+struct TensorInfo {
+    std::string name;
+    int ndim;
+    int64_t dims[4];
+    int64_t size;
+    int64_t offset;  // flat
+};
+
+struct sgm_handle {
+    int model = 0, algo = 0, cv = 0;
+    int64_t N = 0;
+    int n = 0, d = 0, ld = 0, P = 0, Pst = 0, T = 0, C = 1, L = 1;
+    int device = 0;
+    uint32_t flags = 0;
+    int use_prior = 0;
+    double prior_sd = 0;
+    double opt_stepsize = 0;
+    int64_t n_iters_opt = 0;
+    uint64_t seed = 0;
+    std::vector<TensorInfo> tensors;
+    std::vector<double> eps, alpha, a;
+    // device
+    float* X = nullptr;
+    float *theta = nullptr, *mom = nullptr, *thermo = nullptr, *theta_hat = nullptr, *g_hat = nullptr, *scratch = nullptr;
+    double* gsum = nullptr;
+    double* dout = nullptr;   // [C] logpost values
+    int* d_flag = nullptr;
+    int32_t* d_idx = nullptr; size_t d_idx_cap = 0;
+    float* d_noise = nullptr; size_t d_noise_cap = 0;
+    float* store = nullptr; int64_t store_cap = 0, store_len = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0; int last_launches = 0;
+    float fullgrad_ms = 0; int64_t fullgrad_bytes = 0;
+    uint64_t step = 0, check_ctr = 0;
+    bool inited = false;
+    ChainArgs base;  // template of kernel arguments
+    SoftmaxNetWork* nn = nullptr;
+    // comm
+    ncclComm_t comm = nullptr; int rank = 0, world = 1;
+};
+
+static int hat_count(const sgm_handle* h) { return (h->flags & SGM_FLAG_SHARED_MODE) ? 1 : h->C; }
+
+// ------------------------------------------------------------------------------------
+// small kernels used by the host layer
+// ------------------------------------------------------------------------------------
+// column-major double [N, cols] -> row-major float rows with stride ld at column offset col0
+__global__ void pack_rows_kernel(const double* __restrict__ src, int64_t N, int cols, float* __restrict__ dst, int ld, int col0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * cols) return;
+    const int64_t r = i % N; const int c = (int)(i / N);
+    dst[r * ld + col0 + c] = (float)src[i];
+}
+
+__global__ void unpack_rows_kernel(const float* __restrict__ src, int64_t row0, int64_t rows, int cols, int ld, int col0, double* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i % rows; const int c = (int)(i / rows);
+    dst[i] = (double)src[(row0 + r) * ld + col0 + c];
+}
+
+// synthetic logistic dataset: x ~ N(0,1) from Philox(TAG_DATA), planted beta* ~ N(0, 1/d),
+// y ~ Bernoulli(sigmoid(x . beta*)).  One warp per row.
+__global__ void synth_logistic_kernel(float* __restrict__ X, int64_t N, int d, int ld, uint32_t k0, uint32_t k1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= N) return;
+    const float inv_sqrt_d = rsqrtf((float)d);
+    float z = 0.f;
+    float* xr = X + row * ld;
+    for (int b = lane; 4 * b < ld; b += 32) {
+        float v[4], bs[4];
+        normal4_at((uint32_t)b, (uint32_t)(row & 0xffffffffu), (uint32_t)(row >> 32), TAG_DATA, k0, k1, v);
+        normal4_at((uint32_t)b, 0xffffffffu, 0xffffffffu, TAG_DATA, k0 ^ 0x5bd1e995u, k1, bs);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = 4 * b + k;
+            if (col < d) { z += v[k] * bs[k] * inv_sqrt_d; } else v[k] = 0.f;
+        }
+        *reinterpret_cast<float4*>(xr + 4 * b) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    z = warp_sum(z);
+    if (lane == 0) {
+        const U4 r = philox4x32(0xfffffffeu, (uint32_t)(row & 0xffffffffu), (uint32_t)(row >> 32), TAG_DATA, k0, k1);
+        const float u = (float)(r.x >> 8) * 5.9604644775390625e-8f;
+        xr[d] = (u < 1.0f / (1.0f + expf(-z))) ? 1.0f : 0.0f;
+    }
+}
+
+__global__ void fill_kernel(float* p, float v, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = v;
+}
+
+// momentum init: sqrt(eta_t) * N(0,1) (R/dynamics.R:47,84); internal index e -> (flat f, tensor t) via tables
+__global__ void momentum_init_kernel(float* __restrict__ mom, int C, int Pst, int P, const int* __restrict__ flat_of,
+                                     const int* __restrict__ tensor_of, TensorConsts tc, const float* __restrict__ noise,
+                                     uint32_t k0, uint32_t k1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)C * Pst) return;
+    const int c = (int)(i / Pst), e = (int)(i % Pst);
+    const int f = flat_of[e];
+    if (f < 0) { mom[i] = 0.f; return; }
+    const float z = noise ? noise[(size_t)c * P + f] : normal_at((uint32_t)f, (uint32_t)c, 0u, TAG_MOMENTUM, k0, k1);
+    mom[i] = tc.sqrt_eps[tensor_of[e]] * z;
+}
+
+// [iter][C][P] float -> [C][P][iter] double (R layout: every tensor a column-major (iters, dims...) array)
+__global__ void chain_transpose_kernel(const float* __restrict__ store, int64_t iters, int C, int P, int c0, int cn,
+                                       double* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int c = c0 + blockIdx.z;
+    const int64_t it0 = (int64_t)blockIdx.x * 32; const int f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t it = it0 + r; const int f = f0 + threadIdx.x;
+        tile[r][threadIdx.x] = (it < iters && f < P) ? store[((size_t)it * C + c) * P + f] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int f = f0 + r; const int64_t it = it0 + threadIdx.x;
+        if (f < P && it < iters) out[((size_t)blockIdx.z * P + f) * iters + it] = (double)tile[threadIdx.x][r];
+    }
+    (void)cn;
+}
+
+__global__ void state_to_double_kernel(const float* __restrict__ src, int C, int Pst, int P, const int* __restrict__ flat_of, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)C * Pst) return;
+    const int c = (int)(i / Pst), e = (int)(i % Pst);
+    const int f = flat_of[e];
+    if (f >= 0) out[(size_t)c * P + f] = (double)src[i];
+}
+
+__global__ void broadcast_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int C, int Pst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)C * Pst) dst[i] = src[i % Pst];
+}
+
+// Gaussian families: full-data sums at the mode(s), double atomics into gsum[m][Pst]
+template <int MODEL>
+__global__ void small_fullsum_kernel(ChainArgs a, int64_t row0, int64_t row1, double* __restrict__ gsum) {
+    const int m = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    float hat[SMALL_MAXP], s[SMALL_MAXP];
+#pragma unroll
+    for (int k = 0; k < SMALL_MAXP; ++k) {
+        const int f = small_flat_of_slot<MODEL>(k, a.d);
+        hat[k] = f >= 0 ? a.theta_hat[(size_t)m * a.Pst + f] : 0.f;
+        s[k] = 0.f;
+    }
+    const int d = a.d;
+    for (int64_t j = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row1; j += (int64_t)gridDim.x * blockDim.x) {
+        const float* xr = a.X + (size_t)j * a.ld;
+        float x[SMALL_MAXD];
+#pragma unroll
+        for (int k = 0; k < SMALL_MAXD; ++k) x[k] = (k < d) ? __ldg(xr + k) : 0.f;
+        if (MODEL == SMALL_MODEL_GAUSS) {
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXD; ++k) if (k < d) s[k] += x[k] - hat[k];
+        } else {
+            float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXD; ++k)
+                if (k < d) { const float e1 = x[k] - hat[k], e2 = x[k] - hat[SMALL_MAXD + k]; q1 += e1 * e1; q2 += e2 * e2; }
+            const float p1 = 1.0f / (1.0f + expf(0.5f * (q1 - q2))), p2 = 1.0f - p1;
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXD; ++k)
+                if (k < d) { s[k] += p1 * (x[k] - hat[k]); s[SMALL_MAXD + k] += p2 * (x[k] - hat[SMALL_MAXD + k]); }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SMALL_MAXP; ++k) {
+        const int f = small_flat_of_slot<MODEL>(k, d);
+        if (f < 0) continue;
+        const float t = warp_sum(s[k]);
+        if (lane == 0) atomicAdd(gsum + (size_t)m * a.Pst + f, (double)t);
+    }
+}
+
+template <int MODEL>
+__global__ void small_fullgrad_finish(ChainArgs a, int M, const double* __restrict__ gsum, float* __restrict__ g_hat,
+                                      float* __restrict__ theta) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int d = a.d;
+    for (int f = 0; f < a.P; ++f) {
+        const int kk = f % d;
+        float ll;
+        if (MODEL == SMALL_MODEL_GAUSS) {
+            ll = 0.f;
+            for (int q = 0; q < d; ++q) ll += a.prec[kk * SMALL_MAXD + q] * (float)gsum[(size_t)m * a.Pst + q];
+        } else {
+            ll = (float)gsum[(size_t)m * a.Pst + f];
+        }
+        const float th = a.theta_hat[(size_t)m * a.Pst + f];
+        g_hat[(size_t)m * a.Pst + f] = (a.use_prior ? -th * a.prior_inv_var : 0.f) + ll;
+        theta[(size_t)m * a.Pst + f] = th;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+static int set_device(const sgm_handle* h) {
+    CU(cudaSetDevice(h->device));
+    return SGM_OK;
+}
+
+static void host_tables(const sgm_handle* h, std::vector<int>& flat_of, std::vector<int>& tensor_of) {
+    flat_of.assign(h->Pst, -1);
+    tensor_of.assign(h->Pst, 0);
+    if (h->model == SGM_MODEL_LOGISTIC) {
+        for (int e = 0; e < h->d; ++e) { flat_of[e] = e + 1; tensor_of[e] = 1; }
+        flat_of[h->d] = 0; tensor_of[h->d] = 0;
+    } else {
+        for (int t = 0; t < h->T; ++t)
+            for (int64_t k = 0; k < h->tensors[t].size; ++k) {
+                flat_of[h->tensors[t].offset + k] = (int)(h->tensors[t].offset + k);
+                tensor_of[h->tensors[t].offset + k] = t;
+            }
+    }
+}
+
+struct LogiShape { int G, V; };
+static bool logi_shape(int ld, LogiShape* s) {
+    const int q = ld / 4;
+    const int Gs[] = {1, 2, 4, 8, 16, 32};
+    for (int G : Gs) if (G >= q) { s->G = G; s->V = 1; return true; }
+    const int Vs[] = {2, 3, 4, 5, 6, 8, 9, 12, 16};
+    for (int V : Vs) if (32 * V >= q) { s->G = 32; s->V = V; return true; }
+    return false;
+}
+
+static int logi_threads(const sgm_handle* h, const LogiShape& s) {
+    // rows in flight per CTA = threads / G; keep it <= minibatch, and keep register use in mind
+    int thr = (s.V >= 5) ? 512 : 256;
+    while (thr > 32 && thr / s.G > h->n) thr >>= 1;
+    return thr;
+}
+
+static size_t logi_smem_bytes(int threads, const LogiShape& s, int n) {
+    const int ldp = s.V * s.G * 4;
+    return sizeof(float) * ((size_t)(5 + threads / 32) * ldp + 32 + 3 * (size_t)n);
+}
+
+template <int G, int V>
+static int launch_logistic_gv(sgm_handle* h, const ChainArgs& a, int threads, size_t smem) {
+    auto k = logistic_chain_kernel<G, V>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    int grid = a.C < sms * (per_sm > 0 ? per_sm : 1) ? a.C : sms * (per_sm > 0 ? per_sm : 1);
+    k<<<grid, threads, smem, h->stream>>>(a);
+    CU(cudaGetLastError());
+    return SGM_OK;
+}
+
+template <int G, int V>
+static int launch_logistic_fullgrad_gv(sgm_handle* h, int64_t row0, int64_t row1, int M, const float* theta_hat) {
+    auto k = logistic_fullgrad_kernel<G, V>;
+    const int threads = (V >= 5) ? 512 : 256;
+    const int ldp = V * G * 4;
+    const size_t smem = sizeof(float) * (size_t)(1 + threads / 32) * ldp;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const int64_t rows = row1 - row0;
+    // >= 4 CTAs per SM worth of chunks, each at least one sweep of the CTA's row groups
+    int64_t chunks = (int64_t)sms * 8;
+    int64_t rows_per_cta = cdiv(rows, chunks);
+    const int64_t min_rows = 4 * (threads / G);
+    if (rows_per_cta < min_rows) rows_per_cta = min_rows;
+    chunks = cdiv(rows, rows_per_cta);
+    if (chunks < 1) chunks = 1;
+    dim3 grid((unsigned)chunks, (unsigned)M);
+    k<<<grid, threads, smem, h->stream>>>(h->X, h->ld, h->d, row0, row1, (int)rows_per_cta, theta_hat, h->Pst, h->gsum);
+    CU(cudaGetLastError());
+    return SGM_OK;
+}
+
+#define LOGI_DISPATCH(FN, ...)                                                                 \
+    do {                                                                                       \
+        LogiShape s_;                                                                          \
+        if (!logi_shape(h->ld, &s_)) return fail(SGM_EINVAL, "logistic: d = %d too large", h->d); \
+        switch (s_.G * 100 + s_.V) {                                                           \
+            case 101: return FN<1, 1>(__VA_ARGS__);                                            \
+            case 201: return FN<2, 1>(__VA_ARGS__);                                            \
+            case 401: return FN<4, 1>(__VA_ARGS__);                                            \
+            case 801: return FN<8, 1>(__VA_ARGS__);                                            \
+            case 1601: return FN<16, 1>(__VA_ARGS__);                                          \
+            case 3201: return FN<32, 1>(__VA_ARGS__);                                          \
+            case 3202: return FN<32, 2>(__VA_ARGS__);                                          \
+            case 3203: return FN<32, 3>(__VA_ARGS__);                                          \
+            case 3204: return FN<32, 4>(__VA_ARGS__);                                          \
+            case 3205: return FN<32, 5>(__VA_ARGS__);                                          \
+            case 3206: return FN<32, 6>(__VA_ARGS__);                                          \
+            case 3208: return FN<32, 8>(__VA_ARGS__);                                          \
+            case 3209: return FN<32, 9>(__VA_ARGS__);                                          \
+            case 3212: return FN<32, 12>(__VA_ARGS__);                                         \
+            case 3216: return FN<32, 16>(__VA_ARGS__);                                         \
+        }                                                                                      \
+        return fail(SGM_EINVAL, "logistic: no kernel for ld = %d", h->ld);                     \
+    } while (0)
+
+static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
+    LogiShape s;
+    if (!logi_shape(h->ld, &s)) return fail(SGM_EINVAL, "logistic: d = %d too large", h->d);
+    const int threads = logi_threads(h, s);
+    const size_t smem = logi_smem_bytes(threads, s, a.n);
+    if (smem > 227 * 1024) return fail(SGM_EINVAL, "logistic: minibatch %d needs %zu B of shared memory", a.n, smem);
+    LOGI_DISPATCH(launch_logistic_gv, h, a, threads, smem);
+}
+
+static int launch_logistic_fullgrad(sgm_handle* h, int64_t row0, int64_t row1, int M, const float* theta_hat) {
+    LOGI_DISPATCH(launch_logistic_fullgrad_gv, h, row0, row1, M, theta_hat);
+}
+
+// one launch of the family's chain kernel
+static int launch_chain(sgm_handle* h, const ChainArgs& a) {
+    h->last_launches += 1;
+    switch (h->model) {
+        case SGM_MODEL_GAUSS_MEAN:
+        case SGM_MODEL_MIXTURE2: {
+            const int threads = 128;
+            int sms = 0;
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            int64_t grid = cdiv((int64_t)a.C * 32, threads);
+            if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
+            if (h->model == SGM_MODEL_GAUSS_MEAN) small_chain_kernel<SMALL_MODEL_GAUSS><<<(unsigned)grid, threads, 0, h->stream>>>(a);
+            else small_chain_kernel<SMALL_MODEL_MIX2><<<(unsigned)grid, threads, 0, h->stream>>>(a);
+            CU(cudaGetLastError());
+            return SGM_OK;
+        }
+        case SGM_MODEL_LOGISTIC:
+            return launch_logistic(h, a);
+        case SGM_MODEL_SOFTMAX_NET: {
+            int launches = 0;
+            const int rc = softmax_net_launch(h->nn, a, h->stream, &launches);
+            h->last_launches += launches - 1;
+            if (rc != 0) return fail(SGM_ECUDA, "softmax net launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            return SGM_OK;
+        }
+    }
+    return fail(SGM_ENOMODEL, "unknown model %d", h->model);
+}
+
+static int ensure_buf(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return SGM_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CU(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return SGM_OK;
+}
+
+static int check_diverged(sgm_handle* h, const char* msg) {
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (flag) {
+        CU(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+        return fail(SGM_EDIVERGED, "%s", msg);
+    }
+    return SGM_OK;
+}
+
+struct Timer {
+    sgm_handle* h;
+    explicit Timer(sgm_handle* hh) : h(hh) { h->last_launches = 0; cudaEventRecord(h->ev0, h->stream); }
+    int stop() {
+        CU(cudaEventRecord(h->ev1, h->stream));
+        CU(cudaEventSynchronize(h->ev1));
+        CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+        return SGM_OK;
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// create
+// ------------------------------------------------------------------------------------
+static int64_t tensor_size(const sgm_param& p) {
+    int64_t s = 1;
+    for (int i = 0; i < p.ndim; ++i) s *= p.dims[i];
+    return s;
+}
+
+extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
+    if (!cfg || !out) return fail(SGM_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SGM_ABI_VERSION) return fail(SGM_EINVAL, "ABI version mismatch (%d != %d)", cfg->abi_version, SGM_ABI_VERSION);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SGM_ECUDA, "no CUDA device available: sgmcmc_b200 has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SGM_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+    if (cfg->algo < SGM_ALGO_SGLD || cfg->algo > SGM_ALGO_SGNHT) return fail(SGM_EINVAL, "unknown algorithm %d", cfg->algo);
+    if (cfg->n_chains < 1) return fail(SGM_EINVAL, "n_chains must be >= 1");
+    if (cfg->n_params < 1 || cfg->n_params > MAX_TENSORS || !cfg->params) return fail(SGM_EINVAL, "bad params list");
+    if (cfg->model < SGM_MODEL_GAUSS_MEAN || cfg->model > SGM_MODEL_SOFTMAX_NET)
+        return fail(SGM_ENOMODEL, "logLik/logPrior must be one of the routed model families "
+                                  "(gaussMean, mixture2, logistic, softmaxNet); arbitrary closures cannot run on the device");
+
+    sgm_handle* h = new sgm_handle();
+    auto bail = [&](int rc) { sgm_destroy(h); return rc; };
+    h->model = cfg->model; h->algo = cfg->algo; h->cv = cfg->cv ? 1 : 0; h->C = cfg->n_chains;
+    h->device = cfg->device; h->flags = cfg->flags; h->use_prior = cfg->use_prior ? 1 : 0;
+    h->prior_sd = cfg->prior_sd; h->opt_stepsize = cfg->opt_stepsize; h->n_iters_opt = cfg->n_iters_opt;
+    h->L = (cfg->algo == SGM_ALGO_SGHMC) ? cfg->L : 1;
+    if (h->L < 1) return bail(fail(SGM_EINVAL, "L must be >= 1"));
+    if (cfg->seeded) h->seed = cfg->seed;
+    else h->seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count() * 0x9E3779B97F4A7C15ull;
+    if (int rc = set_device(h)) return bail(rc);
+
+    // ---- parameter tensors
+    int64_t off = 0;
+    for (int t = 0; t < cfg->n_params; ++t) {
+        const sgm_param& p = cfg->params[t];
+        if (p.ndim < 0 || p.ndim > 4 || !p.init) return bail(fail(SGM_EINVAL, "parameter %d: bad shape or null init", t));
+        TensorInfo ti; ti.name = p.name ? p.name : ""; ti.ndim = p.ndim;
+        for (int i = 0; i < 4; ++i) ti.dims[i] = i < p.ndim ? p.dims[i] : 1;
+        ti.size = tensor_size(p); ti.offset = off; off += ti.size;
+        if (!(p.stepsize > 0)) return bail(fail(SGM_EINVAL, "parameter %s: stepsize must be > 0", ti.name.c_str()));
+        h->tensors.push_back(ti);
+        h->eps.push_back(p.stepsize); h->alpha.push_back(p.alpha); h->a.push_back(p.a);
+    }
+    h->T = cfg->n_params; h->P = (int)off;
+
+    // ---- dataset shape per family
+    const bool synth = cfg->synth_rows > 0;
+    auto need_data = [&](int k) -> bool { return cfg->n_data >= k && cfg->data && (synth || [&] { for (int i = 0; i < k; ++i) if (!cfg->data[i].data) return false; return true; }()); };
+    int ycols = 0;
+    switch (h->model) {
+        case SGM_MODEL_GAUSS_MEAN:
+        case SGM_MODEL_MIXTURE2: {
+            if (synth || !need_data(1)) return bail(fail(SGM_EINVAL, "Gaussian families need dataset entry X"));
+            const sgm_array& X = cfg->data[0];
+            h->N = X.dims[0]; h->d = X.ndim >= 2 ? (int)X.dims[1] : 1;
+            if (h->d < 1 || h->d > SMALL_MAXD) return bail(fail(SGM_EINVAL, "Gaussian families support 1 <= d <= %d (got %d)", SMALL_MAXD, h->d));
+            const int want_T = h->model == SGM_MODEL_GAUSS_MEAN ? 1 : 2;
+            if (h->T != want_T) return bail(fail(SGM_EINVAL, "model expects %d parameter tensor(s), got %d", want_T, h->T));
+            for (auto& ti : h->tensors) if (ti.size != h->d) return bail(fail(SGM_EINVAL, "parameter %s must have %d entries", ti.name.c_str(), h->d));
+            h->ld = h->d; h->Pst = h->P;
+            break;
+        }
+        case SGM_MODEL_LOGISTIC: {
+            if (synth) { h->N = cfg->synth_rows; h->d = (int)cfg->synth_dim; }
+            else {
+                if (!need_data(2)) return bail(fail(SGM_EINVAL, "logistic needs dataset entries X, y"));
+                h->N = cfg->data[0].dims[0]; h->d = cfg->data[0].ndim >= 2 ? (int)cfg->data[0].dims[1] : 1;
+                if (cfg->data[1].dims[0] != h->N) return bail(fail(SGM_EINVAL, "X and y disagree on the number of rows"));
+            }
+            if (h->T != 2 || h->tensors[0].size != 1 || h->tensors[1].size != h->d)
+                return bail(fail(SGM_EINVAL, "logistic expects params (bias: scalar, beta: [%d,1])", h->d));
+            h->ld = 4 * (h->d / 4 + 1);
+            LogiShape s; if (!logi_shape(h->ld, &s)) return bail(fail(SGM_EINVAL, "logistic: d = %d too large", h->d));
+            h->Pst = s.G * s.V * 4;
+            break;
+        }
+        case SGM_MODEL_SOFTMAX_NET: {
+            if (synth || !need_data(2)) return bail(fail(SGM_EINVAL, "softmax net needs dataset entries X, y"));
+            h->N = cfg->data[0].dims[0]; h->d = (int)cfg->data[0].dims[1];
+            ycols = (int)cfg->data[1].dims[1];
+            if (cfg->data[1].dims[0] != h->N) return bail(fail(SGM_EINVAL, "X and y disagree on the number of rows"));
+            if (h->T != 8) return bail(fail(SGM_EINVAL, "softmax net expects params A, B, a, b, lambdaA, lambdaB, lambdaa, lambdab"));
+            const int64_t hid = h->tensors[3].size, outc = h->tensors[2].size;
+            if (h->tensors[0].size != hid * outc || h->tensors[1].size != (int64_t)h->d * hid || outc != ycols ||
+                h->tensors[4].size != 1 || h->tensors[5].size != 1 || h->tensors[6].size != 1 || h->tensors[7].size != 1)
+                return bail(fail(SGM_EINVAL, "softmax net: inconsistent parameter shapes"));
+            h->ld = 4 * (int)cdiv(h->d + ycols, 4);
+            h->Pst = 4 * (int)cdiv(h->P, 4);
+            break;
+        }
+    }
+    if (h->N < 1 || h->N >= (1ll << 31)) return bail(fail(SGM_EINVAL, "dataset rows must be in [1, 2^31)"));
+
+    // ---- convertProp (R/setup.R:128-140)
+    if (!(cfg->minibatch_size > 0)) return bail(fail(SGM_EINVAL, "minibatchSize must be > 0"));
+    if (cfg->minibatch_size < 1) {
+        const double r = std::nearbyint(cfg->minibatch_size * (double)h->N);
+        if (r == 0) return bail(fail(SGM_EINVAL, "minibatchSize proportion (%g) too small for dataset size (%lld).", cfg->minibatch_size, (long long)h->N));
+        h->n = (int)r;
+    } else h->n = (int)cfg->minibatch_size;
+    if (h->n > h->N) return bail(fail(SGM_EINVAL, "minibatchSize (%d) exceeds dataset size (%lld)", h->n, (long long)h->N));
+
+    // ---- device allocations
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
+    const size_t xbytes = (size_t)h->N * h->ld * sizeof(float);
+    if (cudaMalloc(&h->X, xbytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(SGM_ENOMEM, "cannot allocate %zu bytes for the dataset", xbytes)); }
+    const uint32_t sk0 = (uint32_t)(cfg->synth_seed & 0xffffffffu), sk1 = (uint32_t)(cfg->synth_seed >> 32);
+    if (synth) {
+        const int64_t warps = h->N;
+        synth_logistic_kernel<<<(unsigned)cdiv(warps * 32, 256), 256, 0, h->stream>>>(h->X, h->N, h->d, h->ld, sk0, sk1);
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMemsetAsync(h->X, 0, xbytes, h->stream));
+        int col0 = 0;
+        const int entries = (h->model == SGM_MODEL_GAUSS_MEAN || h->model == SGM_MODEL_MIXTURE2) ? 1 : 2;
+        // upload in row slabs to bound the double staging buffer
+        for (int k = 0; k < entries; ++k) {
+            const sgm_array& A = cfg->data[k];
+            const int cols = A.ndim >= 2 ? (int)A.dims[1] : 1;
+            double* stage = nullptr;
+            const size_t bytes = (size_t)h->N * cols * sizeof(double);
+            if (cudaMalloc(&stage, bytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(SGM_ENOMEM, "cannot allocate %zu staging bytes", bytes)); }
+            CU(cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream));
+            pack_rows_kernel<<<(unsigned)cdiv(h->N * cols, 256), 256, 0, h->stream>>>(stage, h->N, cols, h->X, h->ld, col0);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(h->stream));
+            cudaFree(stage);
+            col0 += cols;
+        }
+    }
+    const size_t sbytes = (size_t)h->C * h->Pst * sizeof(float);
+    CU(cudaMalloc(&h->theta, sbytes)); CU(cudaMalloc(&h->mom, sbytes)); CU(cudaMalloc(&h->scratch, sbytes));
+    CU(cudaMalloc(&h->thermo, (size_t)h->C * MAX_TENSORS * sizeof(float)));
+    CU(cudaMalloc(&h->d_flag, sizeof(int))); CU(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+    CU(cudaMalloc(&h->dout, (size_t)h->C * sizeof(double)));
+    CU(cudaMemsetAsync(h->mom, 0, sbytes, h->stream));
+    if (h->cv) {
+        const size_t hb = (size_t)hat_count(h) * h->Pst * sizeof(float);
+        CU(cudaMalloc(&h->theta_hat, sbytes)); CU(cudaMalloc(&h->g_hat, sbytes));
+        CU(cudaMalloc(&h->gsum, (size_t)h->C * h->Pst * sizeof(double)));
+        CU(cudaMemsetAsync(h->g_hat, 0, sbytes, h->stream));
+        (void)hb;
+    }
+    // initial state: every chain starts at params (internal layout)
+    {
+        std::vector<int> flat_of, tensor_of;
+        host_tables(h, flat_of, tensor_of);
+        std::vector<float> init((size_t)h->Pst, 0.f), flat((size_t)h->P);
+        for (int t = 0; t < h->T; ++t)
+            for (int64_t k = 0; k < h->tensors[t].size; ++k) flat[h->tensors[t].offset + k] = (float)cfg->params[t].init[k];
+        for (int e = 0; e < h->Pst; ++e) if (flat_of[e] >= 0) init[e] = flat[flat_of[e]];
+        std::vector<float> all((size_t)h->C * h->Pst);
+        for (int c = 0; c < h->C; ++c) std::memcpy(all.data() + (size_t)c * h->Pst, init.data(), h->Pst * sizeof(float));
+        CU(cudaMemcpyAsync(h->theta, all.data(), sbytes, cudaMemcpyHostToDevice, h->stream));
+        if (h->cv) CU(cudaMemcpyAsync(h->theta_hat, all.data(), sbytes, cudaMemcpyHostToDevice, h->stream));
+        std::vector<float> th((size_t)h->C * MAX_TENSORS, 0.f);
+        for (int c = 0; c < h->C; ++c) for (int t = 0; t < h->T; ++t) th[(size_t)c * MAX_TENSORS + t] = (float)h->a[t];
+        CU(cudaMemcpyAsync(h->thermo, th.data(), th.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+
+    // ---- kernel argument template
+    ChainArgs& a = h->base;
+    std::memset(&a, 0, sizeof a);
+    a.X = h->X; a.N = (uint32_t)h->N; a.perm_bits = perm_bits((uint32_t)h->N); a.ld = h->ld; a.d = h->d; a.n = h->n;
+    a.corr = (float)((double)h->N / (double)h->n);
+    a.C = h->C; a.Pst = h->Pst; a.P = h->P; a.T = h->T;
+    a.theta = h->theta; a.mom = h->mom; a.thermo = h->thermo; a.theta_hat = h->theta_hat; a.g_hat = h->g_hat;
+    a.hat_stride = h->Pst;
+    a.algo = h->algo; a.cv = h->cv; a.L = h->L; a.use_prior = h->use_prior;
+    a.prior_inv_var = (h->prior_sd > 0) ? (float)(1.0 / (h->prior_sd * h->prior_sd)) : 0.f;
+    if ((h->model == SGM_MODEL_GAUSS_MEAN || h->model == SGM_MODEL_MIXTURE2) && h->use_prior && !(h->prior_sd > 0))
+        return bail(fail(SGM_EINVAL, "prior_sd must be > 0 when use_prior is set"));
+    for (int i = 0; i < SMALL_MAXD; ++i) a.prec[i * SMALL_MAXD + i] = 1.f;
+    if (h->model == SGM_MODEL_GAUSS_MEAN && cfg->precision) {
+        // column-major d x d; symmetric, so the transpose is immaterial, but index it properly
+        std::vector<double> Pm((size_t)h->d * h->d);
+        for (int i = 0; i < h->d; ++i) for (int j = 0; j < h->d; ++j) { a.prec[i * SMALL_MAXD + j] = (float)cfg->precision[i + (size_t)j * h->d]; Pm[i * h->d + j] = cfg->precision[i + (size_t)j * h->d]; }
+        // log det by Cholesky (precision must be SPD)
+        double logdet = 0;
+        for (int i = 0; i < h->d; ++i) {
+            for (int j = 0; j <= i; ++j) {
+                double s = Pm[i * h->d + j];
+                for (int k = 0; k < j; ++k) s -= Pm[i * h->d + k] * Pm[j * h->d + k];
+                if (i == j) { if (!(s > 0)) return bail(fail(SGM_EINVAL, "precision matrix is not positive definite")); Pm[i * h->d + i] = std::sqrt(s); logdet += 2 * std::log(Pm[i * h->d + i]); }
+                else Pm[i * h->d + j] = s / Pm[j * h->d + j];
+            }
+        }
+        a.logdet_prec = (float)logdet;
+    }
+    a.opt_lr = (float)h->opt_stepsize;
+    for (int t = 0; t < h->T; ++t) {
+        const double e = h->eps[t];
+        a.tc.half_eps[t] = (float)(0.5 * e); a.tc.eps[t] = (float)e; a.tc.sqrt_2eps[t] = (float)std::sqrt(2 * e);
+        a.tc.alpha[t] = (float)h->alpha[t]; a.tc.sqrt_alpha[t] = (float)std::sqrt(h->alpha[t] > 0 ? h->alpha[t] : 0);
+        a.tc.sqrt_a[t] = (float)std::sqrt(h->a[t] > 0 ? h->a[t] : 0); a.tc.sqrt_eps[t] = (float)std::sqrt(e);
+        a.tc.offset[t] = (int)h->tensors[t].offset;
+    }
+    a.tc.offset[h->T] = h->P;
+    a.k0 = (uint32_t)(h->seed & 0xffffffffu); a.k1 = (uint32_t)(h->seed >> 32);
+    a.index_tag = TAG_INDEX;
+    a.noise_len = (h->algo == SGM_ALGO_SGHMC) ? (h->L + 1) * h->P : h->P;
+    a.diverged = h->d_flag;
+
+    if (h->model == SGM_MODEL_SOFTMAX_NET) {
+        const int hid = (int)h->tensors[3].size, outc = (int)h->tensors[2].size;
+        int rc = softmax_net_create(&h->nn, h->d, hid, outc, h->n, h->C, h->device);
+        if (rc != 0) return bail(fail(SGM_ECUDA, "softmax net workspace: %s", cudaGetErrorString((cudaError_t)rc)));
+    }
+    *out = h;
+    return SGM_OK;
+}
+
+extern "C" void sgm_destroy(sgm_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->nn) softmax_net_destroy(h->nn);
+    void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,
+                    h->d_flag, h->d_idx, h->d_noise, h->store};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------
+// init (initSess)
+// ------------------------------------------------------------------------------------
+static int full_gradient(sgm_handle* h) {
+    const int M = hat_count(h);
+    const int64_t row0 = h->N * h->rank / h->world, row1 = h->N * (h->rank + 1) / h->world;
+    CU(cudaMemsetAsync(h->gsum, 0, (size_t)M * h->Pst * sizeof(double), h->stream));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, h->stream));
+    switch (h->model) {
+        case SGM_MODEL_GAUSS_MEAN:
+        case SGM_MODEL_MIXTURE2: {
+            ChainArgs a = h->base;
+            int sms = 0; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            int64_t gx = cdiv(row1 - row0, 256 * 4); if (gx > sms * 8) gx = sms * 8; if (gx < 1) gx = 1;
+            dim3 grid((unsigned)gx, (unsigned)M);
+            if (h->model == SGM_MODEL_GAUSS_MEAN) small_fullsum_kernel<SMALL_MODEL_GAUSS><<<grid, 256, 0, h->stream>>>(a, row0, row1, h->gsum);
+            else small_fullsum_kernel<SMALL_MODEL_MIX2><<<grid, 256, 0, h->stream>>>(a, row0, row1, h->gsum);
+            CU(cudaGetLastError());
+            break;
+        }
+        case SGM_MODEL_LOGISTIC:
+            if (int rc = launch_logistic_fullgrad(h, row0, row1, M, h->theta_hat)) return rc;
+            break;
+        case SGM_MODEL_SOFTMAX_NET: {
+            const int rc = softmax_net_fullgrad(h->nn, h->base, row0, row1, M, h->theta_hat, h->gsum, h->stream);
+            if (rc != 0) return fail(SGM_ECUDA, "softmax net full gradient: %s", cudaGetErrorString((cudaError_t)rc));
+            break;
+        }
+    }
+    CU(cudaEventRecord(e1, h->stream));
+    h->last_launches += 1;
+    if (h->comm) {
+        // ncclDouble = 8, ncclSum = 0
+        const int rc = g_nccl.AllReduce(h->gsum, h->gsum, (size_t)M * h->Pst, 8, 0, h->comm, h->stream);
+        if (rc != 0) return fail(SGM_ECOMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    }
+    const int total = M * h->Pst;
+    switch (h->model) {
+        case SGM_MODEL_GAUSS_MEAN:
+            small_fullgrad_finish<SMALL_MODEL_GAUSS><<<(unsigned)cdiv(M, 128), 128, 0, h->stream>>>(h->base, M, h->gsum, h->g_hat, h->theta); break;
+        case SGM_MODEL_MIXTURE2:
+            small_fullgrad_finish<SMALL_MODEL_MIX2><<<(unsigned)cdiv(M, 128), 128, 0, h->stream>>>(h->base, M, h->gsum, h->g_hat, h->theta); break;
+        case SGM_MODEL_LOGISTIC:
+            logistic_fullgrad_finish<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(h->gsum, h->theta_hat, h->g_hat, h->theta, h->Pst, h->d, h->use_prior, total); break;
+        case SGM_MODEL_SOFTMAX_NET: {
+            const int rc = softmax_net_fullgrad_finish(h->nn, h->base, M, h->gsum, h->theta_hat, h->g_hat, h->theta, h->stream);
+            if (rc != 0) return fail(SGM_ECUDA, "softmax net finish: %s", cudaGetErrorString((cudaError_t)rc));
+            break;
+        }
+    }
+    CU(cudaGetLastError());
+    if (M == 1 && h->C > 1) {  // shared mode: every chain starts at the one mode (cV.R:98-99)
+        broadcast_rows_kernel<<<(unsigned)cdiv((int64_t)h->C * h->Pst, 256), 256, 0, h->stream>>>(h->theta, h->theta_hat, h->C, h->Pst);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventElapsedTime(&h->fullgrad_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    h->fullgrad_bytes = (row1 - row0) * (int64_t)h->ld * 4 * (h->model == SGM_MODEL_LOGISTIC ? 1 : 1);
+    return SGM_OK;
+}
+
+static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t* opt_idx, bool det) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    if (int rc = set_device(h)) return rc;
+    Timer tm(h);
+    // momenta (sghmc's is overwritten by the first refresh; sgnht's persists) -- R/dynamics.R:47,84
+    std::vector<int> flat_of, tensor_of;
+    host_tables(h, flat_of, tensor_of);
+    int *d_flat = nullptr, *d_tens = nullptr;
+    CU(cudaMalloc(&d_flat, h->Pst * sizeof(int))); CU(cudaMalloc(&d_tens, h->Pst * sizeof(int)));
+    CU(cudaMemcpyAsync(d_flat, flat_of.data(), h->Pst * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_tens, tensor_of.data(), h->Pst * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (h->algo != SGM_ALGO_SGLD) {
+        const float* dn = nullptr;
+        if (det && momentum_noise) {
+            const size_t bytes = (size_t)h->C * h->P * sizeof(float);
+            if (int rc = ensure_buf((void**)&h->d_noise, &h->d_noise_cap, bytes)) return rc;
+            CU(cudaMemcpyAsync(h->d_noise, momentum_noise, bytes, cudaMemcpyHostToDevice, h->stream));
+            dn = h->d_noise;
+        }
+        if (det && !momentum_noise) CU(cudaMemsetAsync(h->mom, 0, (size_t)h->C * h->Pst * sizeof(float), h->stream));
+        else {
+            momentum_init_kernel<<<(unsigned)cdiv((int64_t)h->C * h->Pst, 256), 256, 0, h->stream>>>(
+                h->mom, h->C, h->Pst, h->P, d_flat, d_tens, h->base.tc, dn, h->base.k0, h->base.k1);
+            CU(cudaGetLastError());
+        }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_flat); cudaFree(d_tens);
+
+    if (h->cv) {
+        // getMode (R/controlVariates.R:37-52): n_iters_opt plain SGD ascent steps on theta_hat
+        const int M = hat_count(h);
+        ChainArgs a = h->base;
+        a.C = M; a.theta = h->theta_hat; a.mom = h->scratch; a.algo = ALGO_OPT; a.cv = 0; a.L = 1;
+        a.index_tag = TAG_OPT_INDEX; a.step0 = 0; a.iters = (int)h->n_iters_opt; a.store = nullptr;
+        a.noise_len = 0;
+        if (det) {
+            if (h->n_iters_opt > 0 && !opt_idx) return fail(SGM_EINVAL, "opt_idx required for a deterministic *cv init");
+            const size_t bytes = (size_t)M * h->n_iters_opt * h->n * sizeof(int32_t);
+            if (bytes) {
+                if (int rc = ensure_buf((void**)&h->d_idx, &h->d_idx_cap, bytes)) return rc;
+                CU(cudaMemcpyAsync(h->d_idx, opt_idx, bytes, cudaMemcpyHostToDevice, h->stream));
+            }
+            a.det = 1; a.idx = h->d_idx;
+        }
+        if (h->n_iters_opt > 0) {
+            if (int rc = launch_chain(h, a)) return rc;
+            if (int rc = check_diverged(h, "Chain diverged")) return rc;   // cV.R:119
+        }
+        if (int rc = full_gradient(h)) return rc;
+        h->base.hat_stride = (M == 1 && h->C > 1) ? 0 : h->Pst;
+    }
+    h->inited = true;
+    h->step = 0;
+    return tm.stop();
+}
+
+extern "C" int sgm_init(sgm_handle* h) { return init_common(h, nullptr, nullptr, false); }
+extern "C" int sgm_init_deterministic(sgm_handle* h, const float* momentum_noise, const int32_t* opt_idx) {
+    return init_common(h, momentum_noise, opt_idx, true);
+}
+
+// ------------------------------------------------------------------------------------
+// stepping
+// ------------------------------------------------------------------------------------
+extern "C" int sgm_step_deterministic(sgm_handle* h, const int32_t* idx, const float* noise) {
+    if (!h || !idx || !noise) return fail(SGM_EINVAL, "null argument");
+    if (!h->inited) return fail(SGM_ESTATE, "sgm_init has not been called");
+    if (int rc = set_device(h)) return rc;
+    const size_t ib = (size_t)h->C * h->L * h->n * sizeof(int32_t);
+    const size_t nb = (size_t)h->C * h->base.noise_len * sizeof(float);
+    if (int rc = ensure_buf((void**)&h->d_idx, &h->d_idx_cap, ib)) return rc;
+    if (int rc = ensure_buf((void**)&h->d_noise, &h->d_noise_cap, nb)) return rc;
+    CU(cudaMemcpyAsync(h->d_idx, idx, ib, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_noise, noise, nb, cudaMemcpyHostToDevice, h->stream));
+    Timer tm(h);
+    ChainArgs a = h->base;
+    a.det = 1; a.idx = h->d_idx; a.noise = h->d_noise; a.iters = 1; a.step0 = h->step; a.store = nullptr;
+    if (int rc = launch_chain(h, a)) return rc;
+    h->step += 1;
+    if (int rc = tm.stop()) return rc;
+    return SGM_OK;
+}
+
+static int ensure_store(sgm_handle* h, int64_t extra) {
+    const int64_t need = h->store_len + extra;
+    if (need <= h->store_cap) return SGM_OK;
+    int64_t cap = h->store_cap * 2 > need ? h->store_cap * 2 : need;
+    float* nb = nullptr;
+    const size_t row = (size_t)h->C * h->P * sizeof(float);
+    if (cudaMalloc(&nb, cap * row) != cudaSuccess) {
+        cudaGetLastError();
+        cap = need;
+        if (cudaMalloc(&nb, cap * row) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate %zu bytes of chain storage", cap * row); }
+    }
+    if (h->store) {
+        CU(cudaMemcpyAsync(nb, h->store, h->store_len * row, cudaMemcpyDeviceToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(h->store);
+    }
+    h->store = nb; h->store_cap = cap;
+    return SGM_OK;
+}
+
+extern "C" int sgm_reserve_chain(sgm_handle* h, int64_t n_iters) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    if (int rc = set_device(h)) return rc;
+    return ensure_store(h, n_iters);
+}
+
+extern "C" int sgm_run(sgm_handle* h, int64_t n_iters, int store) {
+    if (!h || n_iters < 0) return fail(SGM_EINVAL, "bad argument");
+    if (!h->inited) return fail(SGM_ESTATE, "sgm_init has not been called");
+    if (n_iters == 0) return SGM_OK;
+    if (int rc = set_device(h)) return rc;
+    if (store) if (int rc = ensure_store(h, n_iters)) return rc;
+    Timer tm(h);
+    ChainArgs a = h->base;
+    a.det = 0; a.iters = (int)n_iters; a.step0 = h->step;
+    a.store = store ? h->store : nullptr; a.store_pos = h->store_len;
+    if (int rc = launch_chain(h, a)) return rc;
+    h->step += (uint64_t)n_iters;
+    if (store) h->store_len += n_iters;
+    if (int rc = tm.stop()) return rc;
+    return check_diverged(h, "Chain diverged, try decreasing stepsize");  // R/update.R:202
+}
+
+extern "C" int sgm_step(sgm_handle* h) { return sgm_run(h, 1, 0); }
+
+// ------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------
+static int state_out(sgm_handle* h, const float* src, int count, double* out) {
+    if (int rc = set_device(h)) return rc;
+    std::vector<int> flat_of, tensor_of;
+    host_tables(h, flat_of, tensor_of);
+    int* d_flat = nullptr; double* d_out = nullptr;
+    CU(cudaMalloc(&d_flat, h->Pst * sizeof(int)));
+    CU(cudaMalloc(&d_out, (size_t)count * h->P * sizeof(double)));
+    CU(cudaMemcpyAsync(d_flat, flat_of.data(), h->Pst * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    state_to_double_kernel<<<(unsigned)cdiv((int64_t)count * h->Pst, 256), 256, 0, h->stream>>>(src, count, h->Pst, h->P, d_flat, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, (size_t)count * h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_flat); cudaFree(d_out);
+    return SGM_OK;
+}
+
+extern "C" int sgm_get_params(sgm_handle* h, double* out) {
+    if (!h || !out) return fail(SGM_EINVAL, "null argument");
+    return state_out(h, h->theta, h->C, out);
+}
+
+extern "C" int sgm_get_state(sgm_handle* h, double* momentum, double* thermostat) {
+    if (!h) return fail(SGM_EINVAL, "null argument");
+    if (momentum) if (int rc = state_out(h, h->mom, h->C, momentum)) return rc;
+    if (thermostat) {
+        if (int rc = set_device(h)) return rc;
+        std::vector<float> th((size_t)h->C * MAX_TENSORS);
+        CU(cudaMemcpyAsync(th.data(), h->thermo, th.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int c = 0; c < h->C; ++c) for (int t = 0; t < h->T; ++t) thermostat[(size_t)c * h->T + t] = th[(size_t)c * MAX_TENSORS + t];
+    }
+    return SGM_OK;
+}
+
+extern "C" int sgm_get_mode(sgm_handle* h, double* theta_hat, double* grad_hat) {
+    if (!h) return fail(SGM_EINVAL, "null argument");
+    if (!h->cv) return fail(SGM_ESTATE, "not a control-variate sampler");
+    const int M = hat_count(h);
+    std::vector<double> tmp((size_t)M * h->P);
+    for (int which = 0; which < 2; ++which) {
+        double* dst = which ? grad_hat : theta_hat;
+        if (!dst) continue;
+        if (int rc = state_out(h, which ? h->g_hat : h->theta_hat, M, tmp.data())) return rc;
+        for (int c = 0; c < h->C; ++c) std::memcpy(dst + (size_t)c * h->P, tmp.data() + (size_t)(M == 1 ? 0 : c) * h->P, h->P * sizeof(double));
+    }
+    return SGM_OK;
+}
+
+extern "C" int64_t sgm_chain_length(const sgm_handle* h) { return h ? h->store_len : 0; }
+extern "C" int sgm_reset_chain(sgm_handle* h) { if (!h) return fail(SGM_EINVAL, "null handle"); h->store_len = 0; return SGM_OK; }
+
+extern "C" int sgm_copy_chain(sgm_handle* h, double* out) {
+    if (!h || !out) return fail(SGM_EINVAL, "null argument");
+    if (h->store_len == 0) return SGM_OK;
+    if (int rc = set_device(h)) return rc;
+    const int64_t iters = h->store_len;
+    // chains per slab so that the double staging buffer stays <= 256 MiB
+    const size_t per_chain = (size_t)iters * h->P * sizeof(double);
+    int slab = (int)((256ull << 20) / (per_chain ? per_chain : 1));
+    if (slab < 1) slab = 1;
+    if (slab > h->C) slab = h->C;
+    if (slab > 65535) slab = 65535;
+    double* stage = nullptr;
+    if (cudaMalloc(&stage, (size_t)slab * per_chain) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate chain staging buffer"); }
+    for (int c0 = 0; c0 < h->C; c0 += slab) {
+        const int cn = (h->C - c0 < slab) ? h->C - c0 : slab;
+        dim3 grid((unsigned)cdiv(iters, 32), (unsigned)cdiv(h->P, 32), (unsigned)cn), block(32, 8);
+        chain_transpose_kernel<<<grid, block, 0, h->stream>>>(h->store, iters, h->C, h->P, c0, cn, stage);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out + (size_t)c0 * iters * h->P, stage, (size_t)cn * per_chain, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(stage);
+    return SGM_OK;
+}
+
+static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta, double* out) {
+    if (int rc = set_device(h)) return rc;
+    ChainArgs a = h->base;
+    a.theta = const_cast<float*>(theta);
+    if (idx) {
+        const size_t ib = (size_t)h->C * h->n * sizeof(int32_t);
+        if (int rc = ensure_buf((void**)&h->d_idx, &h->d_idx_cap, ib)) return rc;
+        CU(cudaMemcpyAsync(h->d_idx, idx, ib, cudaMemcpyHostToDevice, h->stream));
+        a.det = 1; a.idx = h->d_idx;
+    }
+    const uint32_t word2 = (uint32_t)h->check_ctr;
+    switch (h->model) {
+        case SGM_MODEL_GAUSS_MEAN:
+            small_logpost_kernel<SMALL_MODEL_GAUSS><<<(unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream>>>(a, word2, h->dout); break;
+        case SGM_MODEL_MIXTURE2:
+            small_logpost_kernel<SMALL_MODEL_MIX2><<<(unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream>>>(a, word2, h->dout); break;
+        case SGM_MODEL_LOGISTIC:
+            logistic_logpost_kernel<<<h->C, 256, 0, h->stream>>>(a, word2, theta, h->dout); break;
+        case SGM_MODEL_SOFTMAX_NET: {
+            const int rc = softmax_net_logpost(h->nn, a, word2, theta, h->dout, h->stream);
+            if (rc != 0) return fail(SGM_ECUDA, "softmax net logpost: %s", cudaGetErrorString((cudaError_t)rc));
+            break;
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, h->dout, (size_t)h->C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SGM_OK;
+}
+
+extern "C" int sgm_est_logpost(sgm_handle* h, double* out) {
+    if (!h || !out) return fail(SGM_EINVAL, "null argument");
+    h->check_ctr += 1;
+    return logpost_common(h, nullptr, h->theta, out);
+}
+
+extern "C" int sgm_est_logpost_deterministic(sgm_handle* h, const int32_t* idx, double* out) {
+    if (!h || !out || !idx) return fail(SGM_EINVAL, "null argument");
+    return logpost_common(h, idx, h->theta, out);
+}
+
+extern "C" int sgm_grad_estimate(sgm_handle* h, const int32_t* idx, double* out) {
+    if (!h || !idx || !out) return fail(SGM_EINVAL, "null argument");
+    if (!h->inited) return fail(SGM_ESTATE, "sgm_init has not been called");
+    if (int rc = set_device(h)) return rc;
+    const size_t ib = (size_t)h->C * h->n * sizeof(int32_t);
+    if (int rc = ensure_buf((void**)&h->d_idx, &h->d_idx_cap, ib)) return rc;
+    CU(cudaMemcpyAsync(h->d_idx, idx, ib, cudaMemcpyHostToDevice, h->stream));
+    // plain-SGD kernel with unit step on a scratch copy: g = theta' - theta would lose bits, so the
+    // kernels' ALGO_GRAD path writes the estimate into the momentum slot of a scratch state instead
+    CU(cudaMemcpyAsync(h->scratch, h->theta, (size_t)h->C * h->Pst * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    float* gbuf = nullptr;
+    CU(cudaMalloc(&gbuf, (size_t)h->C * h->Pst * sizeof(float)));
+    CU(cudaMemsetAsync(gbuf, 0, (size_t)h->C * h->Pst * sizeof(float), h->stream));
+    ChainArgs a = h->base;
+    a.theta = h->scratch; a.mom = gbuf; a.algo = ALGO_GRAD; a.L = 1; a.det = 1; a.idx = h->d_idx; a.noise = nullptr;
+    a.iters = 1; a.store = nullptr; a.noise_len = 0;
+    int rc = launch_chain(h, a);
+    if (rc == SGM_OK) rc = state_out(h, gbuf, h->C, out);
+    cudaFree(gbuf);
+    return rc;
+}
+
+extern "C" int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t n_data, double* out) {
+    (void)h; (void)data; (void)n_data; (void)out;
+    return fail(SGM_EINVAL, "sgm_heldout_loglik: not implemented in this build");
+}
+
+extern "C" int64_t sgm_num_rows(const sgm_handle* h) { return h ? h->N : 0; }
+extern "C" int32_t sgm_minibatch(const sgm_handle* h) { return h ? h->n : 0; }
+extern "C" int32_t sgm_num_scalars(const sgm_handle* h) { return h ? h->P : 0; }
+extern "C" int32_t sgm_noise_len(const sgm_handle* h) { return h ? h->base.noise_len : 0; }
+
+extern "C" int sgm_last_timing(const sgm_handle* h, float* kernel_ms, int32_t* launches) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    if (kernel_ms) *kernel_ms = h->last_ms;
+    if (launches) *launches = h->last_launches;
+    return SGM_OK;
+}
+
+extern "C" int sgm_last_fullgrad_timing(const sgm_handle* h, float* kernel_ms, int64_t* bytes) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    if (kernel_ms) *kernel_ms = h->fullgrad_ms;
+    if (bytes) *bytes = h->fullgrad_bytes;
+    return SGM_OK;
+}
+
+extern "C" int sgm_copy_dataset(sgm_handle* h, int32_t entry, int64_t row0, int64_t rows, double* out) {
+    if (!h || !out || row0 < 0 || rows < 0 || row0 + rows > h->N) return fail(SGM_EINVAL, "bad argument");
+    if (int rc = set_device(h)) return rc;
+    int col0 = 0, cols = h->d;
+    if (entry == 1) {
+        if (h->model == SGM_MODEL_LOGISTIC) { col0 = h->d; cols = 1; }
+        else if (h->model == SGM_MODEL_SOFTMAX_NET) { col0 = h->d; cols = (int)h->tensors[2].size; }
+        else return fail(SGM_EINVAL, "model has no dataset entry %d", entry);
+    } else if (entry != 0) return fail(SGM_EINVAL, "model has no dataset entry %d", entry);
+    double* stage = nullptr;
+    CU(cudaMalloc(&stage, (size_t)rows * cols * sizeof(double)));
+    unpack_rows_kernel<<<(unsigned)cdiv(rows * cols, 256), 256, 0, h->stream>>>(h->X, row0, rows, cols, h->ld, col0, stage);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, stage, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(stage);
+    return SGM_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// multi-GPU
+// ------------------------------------------------------------------------------------
+extern "C" int sgm_comm_unique_id(void* id_out, int32_t id_bytes) {
+    if (!id_out || id_bytes < SGM_NCCL_ID_BYTES) return fail(SGM_EINVAL, "id buffer must hold %d bytes", SGM_NCCL_ID_BYTES);
+    if (int rc = load_nccl()) return rc;
+    const int rc = g_nccl.GetUniqueId(id_out);
+    if (rc != 0) return fail(SGM_ECOMM, "ncclGetUniqueId failed (%d)", rc);
+    return SGM_OK;
+}
+
+extern "C" int sgm_comm_init(sgm_handle* h, const void* id, int32_t id_bytes, int32_t rank, int32_t world) {
+    if (!h || !id || id_bytes < SGM_NCCL_ID_BYTES || world < 1 || rank < 0 || rank >= world) return fail(SGM_EINVAL, "bad argument");
+    if (int rc = load_nccl()) return rc;
+    if (int rc = set_device(h)) return rc;
+    NcclId nid;
+    std::memcpy(nid.internal, id, SGM_NCCL_ID_BYTES);
+    const int rc = g_nccl.CommInitRank(&h->comm, world, nid, rank);
+    if (rc != 0) return fail(SGM_ECOMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    h->rank = rank; h->world = world;
+    return SGM_OK;
+}

@@ -1,0 +1,268 @@
+// Gaussian-mean and two-component-mixture families: one warp per chain, state in
+// registers, the whole sgmcmcStep loop (sample -> gather -> per-datum gradient ->
+// warp-shuffle reduce -> x N/n -> fused SGLD/SGHMC/SGNHT update with Philox noise)
+// inside one persistent kernel.
+//
+// Replaces, for these families, dataFeed/dataSelect (R/update.R:166-194),
+// tf$gradients of estLogPost (R/setup.R:36-62,116-125), declareDynamics.*
+// (R/dynamics.R:7-120) and the per-tensor Session.run loops of sgmcmcStep.*
+// (R/update.R:40-81).  Models: vignettes/mvGauss.Rmd:37-54,
+// tests/testthat/test{1d,3d}Gauss.R, vignettes/gaussMixture.Rmd:48-76.
+#pragma once
+#include "common.cuh"
+
+namespace sgm {
+
+constexpr int SMALL_MODEL_GAUSS = 1;
+constexpr int SMALL_MODEL_MIX2 = 2;
+
+// Sum over the minibatch of the per-datum log-likelihood gradients at `th`
+// (and at `hat` when cv), all-reduced over the warp.  Rows are either the first n
+// images of the keyed permutation (device sampling) or caller-supplied.
+template <int MODEL>
+__device__ __forceinline__ void small_minibatch_sums(const ChainArgs& a, int lane, const Perm& perm,
+                                                     const int32_t* __restrict__ idx,
+                                                     const float (&th)[SMALL_MAXP], const float (&hat)[SMALL_MAXP],
+                                                     float (&s)[SMALL_MAXP], float (&sh)[SMALL_MAXP]) {
+    const int d = a.d;
+#pragma unroll
+    for (int k = 0; k < SMALL_MAXP; ++k) { s[k] = 0.f; sh[k] = 0.f; }
+    for (int j = lane; j < a.n; j += 32) {
+        const uint32_t row = idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j);
+        const float* __restrict__ xr = a.X + (size_t)row * a.ld;
+        float x[SMALL_MAXD];
+#pragma unroll
+        for (int k = 0; k < SMALL_MAXD; ++k) x[k] = (k < d) ? __ldg(xr + k) : 0.f;
+        if (MODEL == SMALL_MODEL_GAUSS) {
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXD; ++k)
+                if (k < d) { s[k] += x[k] - th[k]; if (a.cv) sh[k] += x[k] - hat[k]; }
+        } else {
+            // responsibilities r_k = softmax_k(-0.5 |x - theta_k|^2) (equal weights cancel)
+            float q1 = 0.f, q2 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXD; ++k)
+                if (k < d) {
+                    const float e1 = x[k] - th[k], e2 = x[k] - th[SMALL_MAXD + k];
+                    q1 += e1 * e1; q2 += e2 * e2;
+                    if (a.cv) {
+                        const float f1 = x[k] - hat[k], f2 = x[k] - hat[SMALL_MAXD + k];
+                        h1 += f1 * f1; h2 += f2 * f2;
+                    }
+                }
+            // p1 = w1 / (w1 + w2), w_k = exp(-q_k / 2)
+            const float p1 = 1.0f / (1.0f + expf(0.5f * (q1 - q2)));
+            const float p2 = 1.0f - p1;
+            float g1 = 0.f, g2 = 0.f;
+            if (a.cv) { g1 = 1.0f / (1.0f + expf(0.5f * (h1 - h2))); g2 = 1.0f - g1; }
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXD; ++k)
+                if (k < d) {
+                    s[k] += p1 * (x[k] - th[k]);
+                    s[SMALL_MAXD + k] += p2 * (x[k] - th[SMALL_MAXD + k]);
+                    if (a.cv) {
+                        sh[k] += g1 * (x[k] - hat[k]);
+                        sh[SMALL_MAXD + k] += g2 * (x[k] - hat[SMALL_MAXD + k]);
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SMALL_MAXP; ++k) {
+        const bool live = (k % SMALL_MAXD) < d && (MODEL == SMALL_MODEL_MIX2 || k < SMALL_MAXD);
+        if (live) { s[k] = warp_sum(s[k]); if (a.cv) sh[k] = warp_sum(sh[k]); }
+    }
+}
+
+// d estLogPost / d theta (R/setup.R:116-125) from the minibatch sums.
+template <int MODEL>
+__device__ __forceinline__ void small_grad_from_sums(const ChainArgs& a, const float (&th)[SMALL_MAXP],
+                                                     const float (&s)[SMALL_MAXP], float (&g)[SMALL_MAXP]) {
+    const int d = a.d;
+#pragma unroll
+    for (int k = 0; k < SMALL_MAXP; ++k) {
+        const int kk = k % SMALL_MAXD;
+        g[k] = 0.f;
+        if (kk >= d || (MODEL == SMALL_MODEL_GAUSS && k >= SMALL_MAXD)) continue;
+        float ll = s[k];
+        if (MODEL == SMALL_MODEL_GAUSS) {
+            ll = 0.f;
+#pragma unroll
+            for (int m = 0; m < SMALL_MAXD; ++m)
+                if (m < d) ll += a.prec[kk * SMALL_MAXD + m] * s[m];
+        }
+        const float pr = a.use_prior ? -th[k] * a.prior_inv_var : 0.f;
+        g[k] = pr + a.corr * ll;
+    }
+}
+
+// Register slot k <-> flat parameter index (mixture: two tensors of d entries each).
+template <int MODEL>
+__device__ __forceinline__ int small_flat_of_slot(int k, int d) {
+    if (MODEL == SMALL_MODEL_GAUSS) return k < d ? k : -1;
+    const int t = k / SMALL_MAXD, kk = k % SMALL_MAXD;
+    return kk < d ? t * d + kk : -1;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    const int T = (MODEL == SMALL_MODEL_GAUSS) ? 1 : 2;
+    const float SQRT_HALF = 0.70710678118654752440f;
+    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < a.C; c += warps_per_grid) {
+        float th[SMALL_MAXP], mo[SMALL_MAXP], hat[SMALL_MAXP], gh0[SMALL_MAXP];
+        float zeta[2];
+#pragma unroll
+        for (int k = 0; k < SMALL_MAXP; ++k) {
+            const int f = small_flat_of_slot<MODEL>(k, a.d);
+            th[k] = f >= 0 ? a.theta[(size_t)c * a.Pst + f] : 0.f;
+            mo[k] = f >= 0 ? a.mom[(size_t)c * a.Pst + f] : 0.f;
+            hat[k] = (f >= 0 && a.cv) ? a.theta_hat[(size_t)c * a.hat_stride + f] : 0.f;
+            gh0[k] = (f >= 0 && a.cv) ? a.g_hat[(size_t)c * a.hat_stride + f] : 0.f;
+        }
+        zeta[0] = a.thermo[c * MAX_TENSORS + 0];
+        zeta[1] = a.thermo[c * MAX_TENSORS + 1];
+        bool bad = false;
+
+        for (int it = 0; it < a.iters; ++it) {
+            const uint64_t step = a.step0 + (uint64_t)it;
+            auto noise_at = [&](int f, int sub) -> float {
+                if (a.det) return a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + f];
+                return normal_at((uint32_t)f, (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1);
+            };
+            if (a.algo == ALGO_SGHMC) {  // momentum refresh, R/dynamics.R:62, R/update.R:52-57
+#pragma unroll
+                for (int k = 0; k < SMALL_MAXP; ++k) {
+                    const int f = small_flat_of_slot<MODEL>(k, a.d);
+                    if (f >= 0) mo[k] = 0.5f * (a.tc.sqrt_2eps[k / SMALL_MAXD] * noise_at(f, 0));
+                }
+            }
+            for (int l = 0; l < a.L; ++l) {
+                const int sub = l + 1;
+                Perm perm = make_perm(a.N, a.perm_bits, (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
+                const int32_t* idx = a.det ? a.idx + (((size_t)c * a.iters + it) * a.L + l) * a.n : nullptr;
+                // sgld / sghmc: one gradient evaluation per tensor (Gauss-Seidel, R/update.R:43-45,60-64);
+                // sgnht / optimiser: all tensors from one evaluation (R/update.R:72-80, cV.R:87-88).
+                const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
+                const int passes = seidel ? T : 1;
+                for (int pass = 0; pass < passes; ++pass) {
+                    float s[SMALL_MAXP], sh[SMALL_MAXP], g[SMALL_MAXP], gh[SMALL_MAXP];
+                    small_minibatch_sums<MODEL>(a, lane, perm, idx, th, hat, s, sh);
+                    small_grad_from_sums<MODEL>(a, th, s, g);
+                    if (a.cv) {
+                        small_grad_from_sums<MODEL>(a, hat, sh, gh);
+#pragma unroll
+                        for (int k = 0; k < SMALL_MAXP; ++k) g[k] = (gh0[k] - gh[k]) + g[k];  // R/setup.R:58
+                    }
+#pragma unroll
+                    for (int k = 0; k < SMALL_MAXP; ++k) {
+                        const int t = k / SMALL_MAXD;
+                        const int f = small_flat_of_slot<MODEL>(k, a.d);
+                        if (f < 0 || (seidel && t != pass)) continue;
+                        if (a.algo == ALGO_SGLD) {
+                            const float z = noise_at(f, sub);
+                            th[k] += a.tc.half_eps[t] * g[k] + SQRT_HALF * (a.tc.sqrt_2eps[t] * z);
+                        } else if (a.algo == ALGO_SGHMC) {
+                            const float z = noise_at(f, sub);
+                            mo[k] += a.tc.eps[t] * g[k] - a.tc.alpha[t] * mo[k] + a.tc.sqrt_alpha[t] * (a.tc.sqrt_2eps[t] * z);
+                            th[k] += mo[k];
+                        } else if (a.algo == ALGO_SGNHT) {
+                            const float z = noise_at(f, sub);
+                            mo[k] += a.tc.eps[t] * g[k] - mo[k] * zeta[t] + a.tc.sqrt_a[t] * (a.tc.sqrt_2eps[t] * z);
+                        } else if (a.algo == ALGO_OPT) {
+                            th[k] += a.opt_lr * g[k];
+                        } else {  // ALGO_GRAD
+                            mo[k] = g[k];
+                        }
+                    }
+                    if (a.algo == ALGO_SGNHT) {  // theta pass then thermostat pass, R/update.R:75-80
+                        float uu[2] = {0.f, 0.f};
+#pragma unroll
+                        for (int k = 0; k < SMALL_MAXP; ++k) {
+                            if (small_flat_of_slot<MODEL>(k, a.d) < 0) continue;
+                            th[k] += mo[k];
+                            uu[k / SMALL_MAXD] += mo[k] * mo[k];
+                        }
+#pragma unroll
+                        for (int t = 0; t < T; ++t) zeta[t] += uu[t] / (float)a.d - a.tc.eps[t];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXP; ++k) {
+                const int f = small_flat_of_slot<MODEL>(k, a.d);
+                if (f < 0) continue;
+                bad |= !isfinite(th[k]);
+                if (a.store && lane == (f & 31))
+                    a.store[((size_t)(a.store_pos + it) * a.C + c) * a.P + f] = th[k];
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXP; ++k) {
+                const int f = small_flat_of_slot<MODEL>(k, a.d);
+                if (f < 0) continue;
+                a.theta[(size_t)c * a.Pst + f] = th[k];
+                a.mom[(size_t)c * a.Pst + f] = mo[k];
+            }
+            a.thermo[c * MAX_TENSORS + 0] = zeta[0];
+            a.thermo[c * MAX_TENSORS + 1] = zeta[1];
+            if (bad) *a.diverged = 1;
+        }
+    }
+}
+
+// estLogPost value (R/setup.R:116-125) incl. the densities' constants, one warp per chain.
+template <int MODEL>
+__global__ void small_logpost_kernel(const ChainArgs a, uint32_t word2, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= a.C) return;
+    const int d = a.d;
+    const float LOG_2PI = 1.8378770664093453f;
+    float th[SMALL_MAXP];
+#pragma unroll
+    for (int k = 0; k < SMALL_MAXP; ++k) {
+        const int f = small_flat_of_slot<MODEL>(k, d);
+        th[k] = f >= 0 ? a.theta[(size_t)c * a.Pst + f] : 0.f;
+    }
+    Perm perm = make_perm(a.N, a.perm_bits, (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
+    const int32_t* idx = a.det ? a.idx + (size_t)c * a.n : nullptr;
+    float ll = 0.f;
+    for (int j = lane; j < a.n; j += 32) {
+        const uint32_t row = idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j);
+        const float* xr = a.X + (size_t)row * a.ld;
+        if (MODEL == SMALL_MODEL_GAUSS) {
+            float q = 0.f;
+            for (int k = 0; k < d; ++k)
+                for (int m = 0; m < d; ++m) q += (xr[k] - th[k]) * a.prec[k * SMALL_MAXD + m] * (xr[m] - th[m]);
+            ll += -0.5f * q;
+        } else {
+            float q1 = 0.f, q2 = 0.f;
+            for (int k = 0; k < d; ++k) {
+                const float e1 = xr[k] - th[k], e2 = xr[k] - th[SMALL_MAXD + k];
+                q1 += e1 * e1; q2 += e2 * e2;
+            }
+            const float l1 = -0.5f * q1, l2 = -0.5f * q2, m = fmaxf(l1, l2);
+            ll += m + logf(expf(l1 - m) + expf(l2 - m)) + logf(0.5f) - 0.5f * d * LOG_2PI;
+        }
+    }
+    ll = warp_sum(ll);
+    if (lane == 0) {
+        float lp = 0.f;
+        if (MODEL == SMALL_MODEL_GAUSS) {
+            ll += (float)a.n * (0.5f * a.logdet_prec - 0.5f * d * LOG_2PI);
+        }
+        if (a.use_prior) {
+            const float sd = rsqrtf(a.prior_inv_var);
+#pragma unroll
+            for (int k = 0; k < SMALL_MAXP; ++k)
+                if (small_flat_of_slot<MODEL>(k, d) >= 0)
+                    lp += -0.5f * th[k] * th[k] * a.prior_inv_var - logf(sd) - 0.5f * LOG_2PI;
+        }
+        out[c] = (double)(lp + a.corr * ll);
+    }
+}
+
+}  // namespace sgm

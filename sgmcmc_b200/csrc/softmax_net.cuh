@@ -1,0 +1,16 @@
+// 784-100-10 softmax-softmax network family (vignettes/nn.Rmd:58-79) -- interface used by api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace sgm {
+struct SoftmaxNetWork;
+int softmax_net_create(SoftmaxNetWork** out, int d_in, int d_hidden, int d_out, int n, int chains, int device);
+void softmax_net_destroy(SoftmaxNetWork* w);
+int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t stream, int* launches);
+int softmax_net_fullgrad(SoftmaxNetWork* w, const ChainArgs& a, int64_t row0, int64_t row1, int M,
+                         const float* theta_hat, double* gsum, cudaStream_t stream);
+int softmax_net_fullgrad_finish(SoftmaxNetWork* w, const ChainArgs& a, int M, const double* gsum,
+                                const float* theta_hat, float* g_hat, float* theta, cudaStream_t stream);
+int softmax_net_logpost(SoftmaxNetWork* w, const ChainArgs& a, uint32_t word2, const float* theta, double* out,
+                        cudaStream_t stream);
+}  // namespace sgm

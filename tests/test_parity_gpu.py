@@ -1,0 +1,208 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Deterministic validation mode: identical minibatch rows and standard normals go to
+the device kernels and to oracle/samplers.py.  Tolerance: the north star's rel. tol
+1e-5 (fp32), applied per tensor as |ours - ref| <= 1e-5 * max|ref| + 1e-7 (elementwise
+relative error is undefined where an entry crosses zero), against BOTH the float32
+op-by-op graph replica (what the reference computes) and the float64 closed form
+(where we additionally allow the float32 replica's own distance from float64).
+"""
+import numpy as np
+import pytest
+
+from oracle import samplers as OS
+from tests.cases import ALGOS, device_setup, make_case, oracle_chain
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+CASES = ["gauss1d", "gauss2d", "gauss3d_fullcov", "gauss2d_flat", "mixture", "logistic5", "logistic54", "logistic130"]
+
+
+def close(ours, ref, scale=None, rtol=RTOL, what=""):
+    ours, ref = np.asarray(ours, np.float64), np.asarray(ref, np.float64)
+    s = np.abs(ref).max() if scale is None else scale
+    err = np.abs(ours - ref).max()
+    assert err <= rtol * s + 1e-7, f"{what}: max err {err:.3e} vs scale {s:.3e} (rel {err / max(s, 1e-30):.2e})"
+
+
+def tensor_close(ours_flat, ref_params, what, rtol=RTOL):
+    o = 0
+    for k, v in ref_params.items():
+        sz = int(np.size(v))
+        close(ours_flat[o:o + sz], np.asarray(v).reshape(-1, order="F"), what=f"{what}[{k}]", rtol=rtol)
+        o += sz
+
+
+def draw_inputs(rs, chain: OS.Chain, N, n, C):
+    idx = np.stack([np.stack([rs.choice(N, n, replace=False) for _ in range(chain.n_sub())]) for _ in range(C)])
+    noise = rs.randn(C, chain.noise_len()).astype(np.float32)
+    return idx.astype(np.int32), noise
+
+
+@pytest.mark.parametrize("case_name", CASES)
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("cv", [False, True])
+def test_deterministic_steps_match_oracle(lib, case_name, algo, cv):
+    from sgmcmc_b200 import validation as V
+    case = make_case(case_name)
+    C, steps, n_opt = 3, 4, 25
+    rs = np.random.RandomState(5)
+    dev = device_setup(case, algo, cv, n_chains=C, n_iters_opt=n_opt)
+    chains32 = [oracle_chain(case, algo, cv, np.float32, graph=True) for _ in range(C)]
+    chains64 = [oracle_chain(case, algo, cv, np.float64) for _ in range(C)]
+    P = sum(int(np.size(v)) for v in case["params"].values())
+    mom_noise = rs.randn(C, P).astype(np.float32)
+    opt_idx = np.stack([np.stack([rs.choice(case["N"], case["n"], replace=False) for _ in range(n_opt)]) for _ in range(C)]).astype(np.int32)
+    V.initSessDeterministic(dev, mom_noise, opt_idx if cv else None)
+    for c in range(C):
+        for ch in (chains32[c], chains64[c]):
+            if algo != "sgld":
+                ch.init_momentum(mom_noise[c])
+            if cv:
+                ch.find_mode(opt_idx[c])
+    if cv:
+        th_hat, g_hat = V.getMode(dev)
+        for c in range(C):
+            tensor_close(th_hat[c], chains32[c].theta_hat, "theta_hat")
+            # full-data gradient: scale by the per-datum gradient mass, not by the (near-zero at the mode) total
+            gl = case["om"].grad_loglik(chains64[c].theta_hat, case["data"], np.float64)
+            o = 0
+            for k, v in chains64[c].g_hat.items():
+                sz = int(np.size(v))
+                scale = max(np.abs(v).max(), np.abs(gl[k]).max(), 1.0) * 10
+                close(g_hat[c][o:o + sz], np.asarray(v).reshape(-1, order="F"), scale=scale, what=f"g_hat[{k}]")
+                o += sz
+    # gradient estimate at the start state
+    gidx = np.stack([rs.choice(case["N"], case["n"], replace=False) for _ in range(C)]).astype(np.int32)
+    g_dev = V.gradEstimate(dev, gidx)
+    for c in range(C):
+        g32 = chains32[c].grad_estimate(OS.take(case["data"], gidx[c]))
+        g64 = chains64[c].grad_estimate(OS.take(case["data"], gidx[c]))
+        if not cv:
+            tensor_close(g_dev[c], g32, "grad vs f32 graph")
+            tensor_close(g_dev[c], g64, "grad vs f64")
+        else:
+            # control-variate estimate: tolerance scaled by the summand magnitude
+            plain = chains64[c].grad_fn(chains64[c].theta, OS.take(case["data"], gidx[c]))
+            o = 0
+            for k, v in g64.items():
+                sz = int(np.size(v))
+                ref = np.asarray(v).reshape(-1, order="F")
+                scale = np.abs(plain[k]).max()
+                close(g_dev[c][o:o + sz], ref, scale=scale, what=f"cv grad[{k}] vs f64")
+                e32 = np.abs(np.asarray(g32[k]).reshape(-1, order="F") - ref).max()
+                eours = np.abs(g_dev[c][o:o + sz] - ref).max()
+                assert eours <= e32 + RTOL * scale, f"cv grad[{k}]: ours {eours:.2e} worse than f32 replica {e32:.2e}"
+                o += sz
+    # a few full steps
+    for s in range(steps):
+        idx, noise = draw_inputs(rs, chains32[0], case["N"], case["n"], C)
+        V.stepDeterministic(dev, idx, noise)
+        for c in range(C):
+            chains32[c].step(idx[c], noise[c])
+            chains64[c].step(idx[c], noise[c])
+    th = V.flatParams(dev)
+    mom, thermo = V.getState(dev)
+    for c in range(C):
+        tensor_close(th[c], chains32[c].theta, f"theta after {steps} steps vs f32 graph")
+        tensor_close(th[c], chains64[c].theta, f"theta after {steps} steps vs f64", rtol=2e-5)
+        if algo != "sgld":
+            o = 0
+            for k, v in chains64[c].mom.items():
+                sz = int(np.size(v))
+                scale = max(np.abs(v).max(), np.abs(chains64[c].theta[k]).max() * 1e-2)
+                close(mom[c][o:o + sz], np.asarray(v).reshape(-1, order="F"), scale=scale, rtol=1e-4, what=f"momentum[{k}]")
+                o += sz
+        if algo == "sgnht":
+            ref = np.array([chains64[c].thermo[k] for k in chains64[c].theta])
+            close(thermo[c], ref, rtol=1e-5, what="thermostat")
+
+
+@pytest.mark.parametrize("case_name", ["gauss2d", "mixture", "logistic54"])
+def test_est_logpost_matches_oracle(lib, case_name):
+    from sgmcmc_b200 import validation as V
+    case = make_case(case_name)
+    dev = device_setup(case, "sgld", False, n_chains=2)
+    V.initSessDeterministic(dev)
+    rs = np.random.RandomState(3)
+    idx = np.stack([rs.choice(case["N"], case["n"], replace=False) for _ in range(2)]).astype(np.int32)
+    got = V.estLogPostDeterministic(dev, idx)
+    post = OS.Posterior(case["om"], case["N"], case["n"], np.float64, use_prior=case["logprior"] is not None)
+    for c in range(2):
+        want = post.est_logpost(case["params"], OS.take(case["data"], idx[c]))
+        assert abs(got[c] - want) <= 1e-5 * abs(want) + 1e-3, (got[c], want)
+
+
+@pytest.mark.parametrize("case_name,algo,cv", [("gauss2d", "sgld", False), ("mixture", "sghmc", False),
+                                               ("logistic54", "sgld", True), ("logistic130", "sgnht", True),
+                                               ("gauss3d_fullcov", "sgnht", False), ("logistic5", "sghmc", True)])
+def test_device_rng_streams_match_oracle(lib, case_name, algo, cv):
+    """Device-side sampling: the oracle regenerates the Philox index / noise streams
+    (indices bit-exact by construction) and must land on the same state."""
+    import sgmcmc_b200 as S
+    from oracle import rng
+    from sgmcmc_b200 import validation as V
+    case = make_case(case_name)
+    seed, C, steps, L, n_opt = 1234567, 2, 3, 3, 10
+    dev = device_setup(case, algo, cv, n_chains=C, seed=seed, L=L, n_iters_opt=n_opt)
+    sess = S.initSess(dev, verbose=False)
+    for _ in range(steps):
+        S.sgmcmcStep(dev, sess)
+    th = V.flatParams(dev)
+    P = th.shape[1]
+    Leff = L if algo == "sghmc" else 1
+    for c in range(C):
+        ch = oracle_chain(case, algo, cv, np.float32, L=L)
+        if algo != "sgld":
+            ch.init_momentum(rng.normals(seed, c, 0, rng.TAG_MOMENTUM, P))
+        if cv:
+            ch.find_mode([rng.minibatch_indices(seed, c, it, rng.TAG_OPT_INDEX, case["N"], case["n"]) for it in range(n_opt)])
+        for s in range(steps):
+            w2 = lambda sub: s * (Leff + 1) + sub
+            idx = np.stack([rng.minibatch_indices(seed, c, w2(l + 1), rng.TAG_INDEX, case["N"], case["n"]) for l in range(Leff)])
+            if algo == "sghmc":
+                noise = np.concatenate([rng.normals(seed, c, w2(sub), rng.TAG_NOISE, P) for sub in range(Leff + 1)])
+            else:
+                noise = rng.normals(seed, c, w2(1), rng.TAG_NOISE, P)
+            ch.step(idx, noise)
+        tensor_close(th[c], ch.theta, "theta (device RNG)", rtol=5e-5)
+
+
+def test_chain_storage_layout_and_shapes(lib):
+    """storage.R quirks: scalar -> (nIters, 1); beta[d,1] -> (nIters, d, 1); last row == getParams."""
+    import sgmcmc_b200 as S
+    case = make_case("logistic5")
+    out = S.sgldcv(case["loglik"], case["data"], case["params"], case["eps"], case["opt_eps"], logPrior=case["logprior"],
+                   minibatchSize=case["n"], nIters=130, nItersOpt=20, verbose=False, seed=3)
+    assert out["bias"].shape == (130, 1) and out["beta"].shape == (130, 5, 1)
+    assert np.isfinite(out["beta"]).all()
+    case = make_case("gauss3d_fullcov")
+    sg = S.sgnhtSetup(case["loglik"], case["data"], case["params"], 5e-6, logPrior=case["logprior"], minibatchSize=100, seed=1, nChains=4)
+    sess = S.initSess(sg, verbose=False)
+    from sgmcmc_b200 import _lib
+    L = _lib.load()
+    _lib.check(L.sgm_run(sg.handle, 17, 1))
+    ch = S.getChains(sg)
+    assert ch["theta"].shape == (4, 17, 3)
+    np.testing.assert_allclose(ch["theta"][:, -1, :], S.getParams(sg, sess)["theta"], rtol=0, atol=0)
+
+
+def test_same_seed_reproduces(lib):
+    """tests/testthat/testSeeds.R: same seed twice => identical chains (all six samplers)."""
+    import sgmcmc_b200 as S
+    rs = np.random.RandomState(0)
+    data = {"X": rs.randn(10 ** 4)}
+    params = {"theta": np.array(0.0)}
+    std = dict(nIters=10, minibatchSize=5, verbose=False, seed=1)
+    for f in (S.sgld, S.sghmc, S.sgnht):
+        o1 = f(S.gaussMeanLogLik(), data, params, 1e-6, **std)["theta"]
+        o2 = f(S.gaussMeanLogLik(), data, params, 1e-6, **std)["theta"]
+        assert abs((o1 - o2).sum()) <= 1e-8
+    for f in (S.sgldcv, S.sghmccv, S.sgnhtcv):
+        o1 = f(S.gaussMeanLogLik(), data, params, 1e-6, 1e-5, nItersOpt=10, **std)["theta"]
+        o2 = f(S.gaussMeanLogLik(), data, params, 1e-6, 1e-5, nItersOpt=10, **std)["theta"]
+        assert abs((o1 - o2).sum()) <= 1e-8
+    o3 = S.sgld(S.gaussMeanLogLik(), data, params, 1e-6, nIters=10, minibatchSize=5, verbose=False, seed=2)["theta"]
+    o1 = S.sgld(S.gaussMeanLogLik(), data, params, 1e-6, **std)["theta"]
+    assert np.abs(o1 - o3).max() > 0
