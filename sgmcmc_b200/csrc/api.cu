@@ -475,12 +475,6 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     if (!cfg || !out) return fail(SGM_EINVAL, "null argument");
     *out = nullptr;
     if (cfg->abi_version != SGM_ABI_VERSION) return fail(SGM_EINVAL, "ABI version mismatch (%d != %d)", cfg->abi_version, SGM_ABI_VERSION);
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(SGM_ECUDA, "no CUDA device available: sgmcmc_b200 has no CPU fallback");
-    }
-    if (cfg->device < 0 || cfg->device >= ndev) return fail(SGM_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
     if (cfg->algo < SGM_ALGO_SGLD || cfg->algo > SGM_ALGO_SGNHT) return fail(SGM_EINVAL, "unknown algorithm %d", cfg->algo);
     if (cfg->n_chains < 1) return fail(SGM_EINVAL, "n_chains must be >= 1");
     if (cfg->n_params < 1 || cfg->n_params > MAX_TENSORS || !cfg->params) return fail(SGM_EINVAL, "bad params list");
@@ -497,7 +491,6 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     if (h->L < 1) return bail(fail(SGM_EINVAL, "L must be >= 1"));
     if (cfg->seeded) h->seed = cfg->seed;
     else h->seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count() * 0x9E3779B97F4A7C15ull;
-    if (int rc = set_device(h)) return bail(rc);
 
     // ---- parameter tensors
     int64_t off = 0;
@@ -570,6 +563,22 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     } else h->n = (int)cfg->minibatch_size;
     if (h->n > h->N) return bail(fail(SGM_EINVAL, "minibatchSize (%d) exceeds dataset size (%lld)", h->n, (long long)h->N));
 
+    if ((h->model == SGM_MODEL_GAUSS_MEAN || h->model == SGM_MODEL_MIXTURE2) && h->use_prior && !(h->prior_sd > 0))
+        return bail(fail(SGM_EINVAL, "prior_sd must be > 0 when use_prior is set"));
+    if (h->cv && (!(h->opt_stepsize > 0) || h->n_iters_opt < 0))
+        return bail(fail(SGM_EINVAL, "*cv samplers need optStepsize > 0 and nItersOpt >= 0"));
+
+    // ---- everything above is host logic; from here on a CUDA device is mandatory (no CPU fallback)
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            return bail(fail(SGM_ECUDA, "no CUDA device available: sgmcmc_b200 has no CPU fallback"));
+        }
+        if (cfg->device < 0 || cfg->device >= ndev) return bail(fail(SGM_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev));
+    }
+    if (int rc = set_device(h)) return bail(rc);
+
     // ---- device allocations
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
@@ -640,8 +649,6 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     a.hat_stride = h->Pst;
     a.algo = h->algo; a.cv = h->cv; a.L = h->L; a.use_prior = h->use_prior;
     a.prior_inv_var = (h->prior_sd > 0) ? (float)(1.0 / (h->prior_sd * h->prior_sd)) : 0.f;
-    if ((h->model == SGM_MODEL_GAUSS_MEAN || h->model == SGM_MODEL_MIXTURE2) && h->use_prior && !(h->prior_sd > 0))
-        return bail(fail(SGM_EINVAL, "prior_sd must be > 0 when use_prior is set"));
     for (int i = 0; i < SMALL_MAXD; ++i) a.prec[i * SMALL_MAXD + i] = 1.f;
     if (h->model == SGM_MODEL_GAUSS_MEAN && cfg->precision) {
         // column-major d x d; symmetric, so the transpose is immaterial, but index it properly
@@ -684,7 +691,7 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
 
 extern "C" void sgm_destroy(sgm_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->stream) cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->nn) softmax_net_destroy(h->nn);
     void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,

@@ -1,0 +1,64 @@
+"""CPU suite, world_size 2 over gloo: the host-side sharding logic of the N>1 path.
+
+Chains are partitioned with no communication; the control-variate full-data gradient is
+summed over per-rank row ranges and all-reduced.  Here the per-rank partial sums come from
+the oracle (no GPU), the reduction from torch.distributed/gloo -- the same plumbing bench.py
+uses with NCCL."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import samplers as OS
+from sgmcmc_b200.partition import chain_range, row_range
+from tests.cases import make_case
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = make_case("logistic5")
+    lo, hi = row_range(rank, world, case["N"])
+    shard = {k: v[lo:hi] for k, v in case["data"].items()}
+    part = case["om"].grad_loglik(case["params"], shard, np.float64)
+    t = torch.from_numpy(OS.flat(part).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    # max-over-ranks timing reduction used by bench.py
+    ms = torch.tensor([10.0 + rank])
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        out["sum"] = t.numpy().copy()
+        out["ms"] = float(ms)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_full_gradient_allreduce_equals_single_rank():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    case = make_case("logistic5")
+    full = OS.flat(case["om"].grad_loglik(case["params"], case["data"], np.float64))
+    np.testing.assert_allclose(out["sum"], full, rtol=1e-12, atol=1e-10)
+    assert out["ms"] == 11.0
+
+
+def test_partitions_cover_everything_once():
+    for world in (1, 2, 3, 4, 8):
+        for total in (1, 7, 128, 1024, 581012):
+            chains = [chain_range(r, world, total) for r in range(world)]
+            rows = [row_range(r, world, total) for r in range(world)]
+            for parts in (chains, rows):
+                assert parts[0][0] == 0 and parts[-1][1] == total
+                assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+                sizes = [b - a for a, b in parts]
+                assert max(sizes) - min(sizes) <= 1
