@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the sgmcmc sampler hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3]
+
+One "step" = one launch of the persistent chain kernel: ``--iters-per-step``
+sgmcmcSteps for every chain of this rank (minibatch sampling + gather + gradient +
+fused update + device-side chain storage).  The metric is BASELINE.json's: SGMCMC
+iterations/s counted as chains x iters (whole job, all ranks), plus the
+control-variate full-data gradient GB/s, each against the HBM roofline.
+
+Workloads (BASELINE.json configs; synthetic data of the named shapes):
+    c1  mvGauss SGLD            N=1e4  d=2   n=100
+    c2  gaussMixture SGHMC L=5  N=1e4  d=2   n=100
+    c3  logistic SGLDCV         N=581012 d=54 n=500      <- default (metric names both halves on it)
+    c4  nn 784-100-10 SGHMC L=5 N=60000 n=100
+    c5  SGNHTCV logistic        N=1.25e7/GPU d=1024 n=1024, 128 chains/GPU (1024 at 8 GPUs), data generated on device
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sgmcmc_iterations_per_s_chains_x_iters"
+UNIT = "chain-iterations/s"
+
+
+# --------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------
+def workload(name: str, chains: int | None):
+    """Returns dict(desc, setup_kwargs..., bytes_per_chain_iter, ...). Host data is synthetic, seed 13."""
+    rs = np.random.RandomState(13)
+    if name == "c1":
+        X = rs.randn(10 ** 4, 2)
+        return dict(desc="mvGauss vignette: SGLD, 2-d Gaussian mean, N=1e4, n=100", algo="sgld", cv=False, family="gauss",
+                    data={"X": X}, params={"theta": np.zeros(2)}, stepsize=1e-5, n=100, chains=chains or 148 * 64,
+                    bytes_per_chain_iter=824, bound_note="dataset (80 KB) is L1/L2 resident: not HBM-bound")
+    if name == "c2":
+        z = rs.rand(10 ** 4) < 0.5
+        X = rs.randn(10 ** 4, 2) + np.where(z[:, None], 0.0, 0.1)
+        return dict(desc="gaussMixture vignette: SGHMC L=5, 2-component 2-d mixture, N=1e4, n=100", algo="sghmc", cv=False,
+                    family="mixture", data={"X": X}, params={"theta1": np.zeros(2), "theta2": np.full(2, 0.1)},
+                    stepsize=2e-5, n=100, chains=chains or 148 * 64, L=5, alpha=0.01,
+                    bytes_per_chain_iter=4352, bound_note="dataset (80 KB) is L1/L2 resident: not HBM-bound")
+    if name == "c3":
+        N, d = 581012, 54
+        X = rs.randn(N, d)
+        beta = rs.randn(d) * 0.5
+        y = (rs.rand(N) < 1.0 / (1.0 + np.exp(-(0.1 + X @ beta / np.sqrt(d))))).astype(np.float64)
+        return dict(desc="logisticRegression: SGLDCV, covertype-shaped N=581012 d=54, n=500, CV full gradient at mode",
+                    algo="sgld", cv=True, family="logistic", data={"X": X, "y": y},
+                    params={"bias": np.array(0.0), "beta": np.zeros((d, 1))}, stepsize=5e-6, opt_stepsize=5e-6,
+                    n_iters_opt=10 ** 4, n=500, chains=chains or 148 * 8,
+                    bytes_per_chain_iter=111100, fullgrad_bytes=N * 55 * 4,
+                    bound_note="dataset is 130 MB (~L2 size): gathers are served partly from L2")
+    if name == "c5":
+        d = 1024
+        return dict(desc="scale-out: SGNHTCV logistic, d=1024, n=1024, 128 chains/GPU, N=1.25e7 rows/GPU generated on device",
+                    algo="sgnht", cv=True, family="logistic", data=None, synth=dict(rows=int(os.environ.get("SGM_C5_ROWS", 12500000)), dim=d, seed=13),
+                    params={"bias": np.array(0.0), "beta": np.zeros((d, 1))}, stepsize=1e-8, opt_stepsize=1e-7,
+                    n_iters_opt=200, n=1024, chains=chains or 128, a=0.01,
+                    bytes_per_chain_iter=1024 * 1025 * 4 + (4 * 1025 + 4) * 4 + 2 * 1025 * 4,
+                    fullgrad_bytes=int(os.environ.get("SGM_C5_ROWS", 12500000)) * 1025 * 4,
+                    bound_note="51 GB dataset >> L2: HBM-bound gather")
+    if name == "c4":
+        N = 60000
+        X = rs.rand(N, 784)
+        Y = np.eye(10)[rs.randint(0, 10, N)]
+        p = {"A": rs.randn(100, 10), "B": rs.randn(784, 100), "a": rs.randn(10), "b": rs.randn(100),
+             "lambdaA": np.array(rs.gamma(1.0)), "lambdaB": np.array(rs.gamma(1.0)),
+             "lambdaa": np.array(rs.gamma(1.0)), "lambdab": np.array(rs.gamma(1.0))}
+        return dict(desc="nn vignette: SGHMC L=5, 784-100-10 softmax net, N=60000, n=100", algo="sghmc", cv=False, family="nn",
+                    data={"X": X, "y": Y}, params=p, stepsize=1e-6, n=100, chains=chains or 64, L=5, alpha=0.01,
+                    bytes_per_chain_iter=int(8.59e6), bound_note="per-chain weights (318 KB) stream from L2/HBM")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def model_objects(family):
+    import sgmcmc_b200 as S
+    return {"gauss": (S.gaussMeanLogLik(), S.normalPrior(10.0)), "mixture": (S.mixture2LogLik(), S.normalPrior(10.0)),
+            "logistic": (S.logisticLogLik(), S.laplacePrior()), "nn": (S.softmaxNetLogLik(), S.gammaPrecisionPrior())}[family]
+
+
+def oracle_model(w):
+    from oracle import models as OM
+    if w["family"] == "gauss":
+        return OM.GaussMean(2, prior_sd=10.0)
+    if w["family"] == "mixture":
+        return OM.Mixture2(2, 10.0)
+    if w["family"] == "logistic":
+        return OM.Logistic(w["params"]["beta"].shape[0])
+    return OM.SoftmaxNet()
+
+
+def make_sampler(w, rank, world, chains_local, seed=13):
+    import sgmcmc_b200 as S
+    ll, lp = model_objects(w["family"])
+    kw = dict(logPrior=lp, minibatchSize=w["n"], seed=seed, nChains=chains_local, chainOffset=rank * chains_local,
+              sharedMode=True, device=int(os.environ.get("LOCAL_RANK", 0)))
+    if w.get("synth"):
+        kw["synth"] = w["synth"]
+    data = w["data"] if w["data"] is not None else {}
+    algo, cv = w["algo"], w["cv"]
+    if algo == "sghmc":
+        kw.update(alpha=w.get("alpha", 0.01), L=w.get("L", 5))
+    if algo == "sgnht":
+        kw.update(a=w.get("a", 0.01))
+    if cv:
+        fn = {"sgld": S.sgldcvSetup, "sghmc": S.sghmccvSetup, "sgnht": S.sgnhtcvSetup}[algo]
+        return fn(ll, data, w["params"], w["stepsize"], w["opt_stepsize"], nItersOpt=w["n_iters_opt"], verbose=False, **kw)
+    fn = {"sgld": S.sgldSetup, "sghmc": S.sghmcSetup, "sgnht": S.sgnhtSetup}[algo]
+    return fn(ll, data, w["params"], w["stepsize"], **kw)
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_ev, self.thread = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.05)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_ev.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm (reference-structured proxy; see oracle/cpu_baseline.py)
+# --------------------------------------------------------------------------------------
+def cpu_proxy(w, budget_s, threads):
+    import torch
+    from oracle.cpu_baseline import ReferenceStructuredSampler, time_full_gradient, time_iterations
+    torch.set_num_threads(threads)
+    if w["data"] is None:  # c5: bounded host sample of the device-generated shape
+        rs = np.random.RandomState(13)
+        d = w["synth"]["dim"]
+        N = 20000
+        X = rs.randn(N, d)
+        y = (rs.rand(N) < 1 / (1 + np.exp(-(X @ (rs.randn(d) / np.sqrt(d)))))).astype(np.float64)
+        data, sample_note = {"X": X, "y": y}, f"N reduced to {N} rows on the host (the 51 GB device dataset cannot be held by the CPU arm); "
+    else:
+        data, sample_note = w["data"], ""
+    s = ReferenceStructuredSampler(oracle_model(w), data, w["params"], w["algo"], w["stepsize"], cv=w["cv"],
+                                   alpha=w.get("alpha", 0.01), a=w.get("a", 0.01), L=w.get("L", 5),
+                                   opt_stepsize=w.get("opt_stepsize", 0.0), n=w["n"])
+    fg = None
+    if w["cv"]:
+        s.find_mode(50)  # enough to exercise the path; the timed part is the sampling loop + the full gradient
+        fg = time_full_gradient(oracle_model(w), data, w["params"])
+    ips, iters, dt = time_iterations(s, budget_s)
+    return ips, f"{sample_note}1 chain, {iters} sgmcmcSteps in {dt:.1f} s, torch CPU float32 graph replica, {threads} thread(s)", fg, data
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's own structure on the host cores (the real R+TF stack is absent)."""
+    import torch
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    times, iters_tot = [], 0
+    ips_all = []
+    for i in range(args.warmup + args.steps):
+        ips, note, fg, _ = cpu_proxy(w, budget if i >= args.warmup else 1.0, threads)
+        if i >= args.warmup:
+            ips_all.append(ips)
+    val = float(np.mean(ips_all))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * budget, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": w["desc"], "chains": 1},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": note},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "TF-proxy (torch CPU) -- not the reference binary: R and TensorFlow are absent from this image"}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__
+    if local == 0:
+        __graft_entry__.build()   # no-op when the in-tree .so is current
+    if world > 1:
+        dist.barrier()
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib
+    from sgmcmc_b200 import validation as V
+    lib = _lib.load()
+    chains_local = w["chains"]
+    I = args.iters_per_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- end-to-end leg (public API, host buffers): Setup (dataset H2D) + initSess + K x [run + copy-out (D2H)]
+    barrier()
+    t_e2e0 = time.perf_counter()
+    sg = make_sampler(w, rank, world, chains_local)
+    if world > 1 and w["cv"]:
+        idbuf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_char * _lib.NCCL_ID_BYTES)()
+            _lib.check(lib.sgm_comm_unique_id(raw, _lib.NCCL_ID_BYTES))
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = idbuf.cpu().numpy().tobytes()
+        _lib.check(lib.sgm_comm_init(sg.handle, raw, _lib.NCCL_ID_BYTES, rank, world))
+    sess = S.initSess(sg, verbose=False)
+    init_ms, init_launches = V.lastTiming(sg)
+    fg_ms, fg_bytes = V.lastFullGradTiming(sg) if w["cv"] else (0.0, 0)
+    _lib.check(lib.sgm_reserve_chain(sg.handle, I))
+    d2h_bytes = 0
+    for _ in range(args.steps):
+        _lib.check(lib.sgm_reset_chain(sg.handle))
+        _lib.check(lib.sgm_run(sg.handle, I, 1))
+        ch = S.getChains(sg)
+        d2h_bytes = sum(v.nbytes for v in ch.values())
+        del ch
+    barrier()
+    t_e2e = time.perf_counter() - t_e2e0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t)
+    h2d_total = sum(np.asarray(v).size * 8 for v in (w["data"] or {}).values())
+
+    # ---- device-resident leg: W warm-up steps, then exactly K timed steps
+    for _ in range(max(3, args.warmup)):
+        _lib.check(lib.sgm_reset_chain(sg.handle))
+        _lib.check(lib.sgm_run(sg.handle, I, 1))
+    kernel_ms, launches = [], 0
+    with ClockSampler(local) as clk:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            lib.sgm_reset_chain(sg.handle)
+            _lib.check(lib.sgm_run(sg.handle, I, 1))
+            ms, nl = V.lastTiming(sg)
+            kernel_ms.append(ms)
+            launches += nl
+        barrier()
+        dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt, max(kernel_ms)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+    clocks = clk.summary()
+
+    total_chains = chains_local * world
+    value = total_chains * I * args.steps / dt
+    peak, peak_src = measured_peaks()
+    k_ms = float(np.mean(kernel_ms))
+    achieved = chains_local * I * w["bytes_per_chain_iter"] / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "chains_per_gpu": chains_local, "chains_total": total_chains,
+                   "iters_per_step": I, "minibatch": w["n"], "store": "device-resident chain, every iteration",
+                   "l2": "inputs larger than L2" if args.workload in ("c3", "c4", "c5") else "dataset smaller than L2 (stated; not an HBM-bound case)",
+                   "sampling": "device Philox, without replacement", "shared_mode": bool(w["cv"])},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "persistent chain kernel (gather + gradient + update + store)",
+                     "kernel_ms_per_launch": k_ms, "bytes_per_chain_iter": w["bytes_per_chain_iter"], "peak_source": peak_src,
+                     "note": w["bound_note"]},
+        "clocks": clocks,
+        "e2e": {"value": total_chains * I * args.steps / t_e2e, "unit": UNIT,
+                "h2d_bytes_per_step": h2d_total / args.steps, "d2h_bytes_per_step": d2h_bytes,
+                "seconds": t_e2e, "includes": "Setup (dataset upload) + initSess (mode finder, full gradient) + K x [run + chain copy-out as doubles]"},
+        "gpu_launches": launches,
+    }
+    if w["cv"]:
+        line["cv_full_gradient"] = {"ms": fg_ms, "bytes": fg_bytes, "GBps": (fg_bytes / (fg_ms * 1e-3) / 1e9) if fg_ms > 0 else None,
+                                    "frac_of_hbm_peak": (fg_bytes / (fg_ms * 1e-3) / 1e9 / peak) if fg_ms > 0 else None,
+                                    "rows_per_rank": fg_bytes // (4 * 55) if args.workload == "c3" else None,
+                                    "init_ms_total": init_ms}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ips, note, fg, _ = cpu_proxy(w, args.cpu_budget, 1)
+        line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": 1, "kind": "port", "sample": note,
+                                "full_gradient_s": fg, "label": "TF-proxy (torch CPU) -- not the reference binary"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SGM_WORKLOAD", "c3"))
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
+    ap.add_argument("--iters-per-step", type=int, default=550)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    w = workload(args.workload, args.chains)
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

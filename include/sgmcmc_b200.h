@@ -95,6 +95,7 @@ typedef struct sgm_config {
     int32_t seeded;          /* 0 = seed=NULL (library draws one from the clock) */
     uint64_t seed;
     int32_t n_chains;        /* >= 1 */
+    int64_t chain_offset;    /* global index of this handle's first chain (multi-GPU chain groups); 0 otherwise */
     int32_t device;          /* CUDA device ordinal */
     uint32_t flags;
     /* model constants (what the user's closures hard-code) */

@@ -34,7 +34,7 @@ class SgmConfig(C.Structure):
         ("n_data", C.c_int32), ("data", C.POINTER(SgmArray)),
         ("n_params", C.c_int32), ("params", C.POINTER(SgmParam)),
         ("minibatch_size", C.c_double), ("L", C.c_int32), ("opt_stepsize", C.c_double), ("n_iters_opt", C.c_int64),
-        ("seeded", C.c_int32), ("seed", C.c_uint64), ("n_chains", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
+        ("seeded", C.c_int32), ("seed", C.c_uint64), ("n_chains", C.c_int32), ("chain_offset", C.c_int64), ("device", C.c_int32), ("flags", C.c_uint32),
         ("use_prior", C.c_int32), ("prior_sd", C.c_double), ("precision", C.POINTER(C.c_double)),
         ("synth_rows", C.c_int64), ("synth_dim", C.c_int64), ("synth_seed", C.c_uint64),
     ]

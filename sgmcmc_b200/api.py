@@ -74,7 +74,7 @@ class Session:
 
 def _create(logLik, logPrior, dataset, params, stepsize, minibatchSize, seed, algo, cv, *,
             optStepsize=0.0, nItersOpt=0, alpha=0.01, L=5, a=0.01, nChains=1, device=0, sharedMode=False,
-            synth=None) -> Sgmcmc:
+            synth=None, chainOffset=0) -> Sgmcmc:
     """createSGMCMC / createSGMCMCCV (R/setup.R:2-28, R/controlVariates.R:2-25)."""
     lib = _lib.load()
     model_id, use_prior, prior_sd, precision = models.resolve(logLik, logPrior)
@@ -124,6 +124,7 @@ def _create(logLik, logPrior, dataset, params, stepsize, minibatchSize, seed, al
     cfg.seeded = int(seed is not None)
     cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF if seed is not None else 0
     cfg.n_chains = int(nChains)
+    cfg.chain_offset = int(chainOffset)
     cfg.device = int(device)
     cfg.flags = _lib.FLAG_SHARED_MODE if sharedMode else 0
     cfg.use_prior = use_prior

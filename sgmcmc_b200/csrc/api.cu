@@ -99,6 +99,7 @@ struct sgm_handle {
     double opt_stepsize = 0;
     int64_t n_iters_opt = 0;
     uint64_t seed = 0;
+    int64_t chain_offset = 0;
     std::vector<TensorInfo> tensors;
     std::vector<double> eps, alpha, a;
     // device
@@ -178,13 +179,13 @@ __global__ void fill_kernel(float* p, float v, int64_t count) {
 // momentum init: sqrt(eta_t) * N(0,1) (R/dynamics.R:47,84); internal index e -> (flat f, tensor t) via tables
 __global__ void momentum_init_kernel(float* __restrict__ mom, int C, int Pst, int P, const int* __restrict__ flat_of,
                                      const int* __restrict__ tensor_of, TensorConsts tc, const float* __restrict__ noise,
-                                     uint32_t k0, uint32_t k1) {
+                                     uint32_t k0, uint32_t k1, uint32_t chain0) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)C * Pst) return;
     const int c = (int)(i / Pst), e = (int)(i % Pst);
     const int f = flat_of[e];
     if (f < 0) { mom[i] = 0.f; return; }
-    const float z = noise ? noise[(size_t)c * P + f] : normal_at((uint32_t)f, (uint32_t)c, 0u, TAG_MOMENTUM, k0, k1);
+    const float z = noise ? noise[(size_t)c * P + f] : normal_at((uint32_t)f, chain0 + (uint32_t)c, 0u, TAG_MOMENTUM, k0, k1);
     mom[i] = tc.sqrt_eps[tensor_of[e]] * z;
 }
 
@@ -485,7 +486,7 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     sgm_handle* h = new sgm_handle();
     auto bail = [&](int rc) { sgm_destroy(h); return rc; };
     h->model = cfg->model; h->algo = cfg->algo; h->cv = cfg->cv ? 1 : 0; h->C = cfg->n_chains;
-    h->device = cfg->device; h->flags = cfg->flags; h->use_prior = cfg->use_prior ? 1 : 0;
+    h->device = cfg->device; h->flags = cfg->flags; h->chain_offset = cfg->chain_offset; h->use_prior = cfg->use_prior ? 1 : 0;
     h->prior_sd = cfg->prior_sd; h->opt_stepsize = cfg->opt_stepsize; h->n_iters_opt = cfg->n_iters_opt;
     h->L = (cfg->algo == SGM_ALGO_SGHMC) ? cfg->L : 1;
     if (h->L < 1) return bail(fail(SGM_EINVAL, "L must be >= 1"));
@@ -677,6 +678,7 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     a.tc.offset[h->T] = h->P;
     a.k0 = (uint32_t)(h->seed & 0xffffffffu); a.k1 = (uint32_t)(h->seed >> 32);
     a.index_tag = TAG_INDEX;
+    a.chain0 = (uint32_t)h->chain_offset;
     a.noise_len = (h->algo == SGM_ALGO_SGHMC) ? (h->L + 1) * h->P : h->P;
     a.diverged = h->d_flag;
 
@@ -789,7 +791,7 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
         if (det && !momentum_noise) CU(cudaMemsetAsync(h->mom, 0, (size_t)h->C * h->Pst * sizeof(float), h->stream));
         else {
             momentum_init_kernel<<<(unsigned)cdiv((int64_t)h->C * h->Pst, 256), 256, 0, h->stream>>>(
-                h->mom, h->C, h->Pst, h->P, d_flat, d_tens, h->base.tc, dn, h->base.k0, h->base.k1);
+                h->mom, h->C, h->Pst, h->P, d_flat, d_tens, h->base.tc, dn, h->base.k0, h->base.k1, h->base.chain0);
             CU(cudaGetLastError());
         }
     }
@@ -801,6 +803,7 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
         const int M = hat_count(h);
         ChainArgs a = h->base;
         a.C = M; a.theta = h->theta_hat; a.mom = h->scratch; a.algo = ALGO_OPT; a.cv = 0; a.L = 1;
+        if (M == 1 && (h->flags & SGM_FLAG_SHARED_MODE)) a.chain0 = 0;  // one mode for the whole job, identical on every rank
         a.index_tag = TAG_OPT_INDEX; a.step0 = 0; a.iters = (int)h->n_iters_opt; a.store = nullptr;
         a.noise_len = 0;
         if (det) {
@@ -1094,6 +1097,8 @@ extern "C" int sgm_comm_unique_id(void* id_out, int32_t id_bytes) {
 
 extern "C" int sgm_comm_init(sgm_handle* h, const void* id, int32_t id_bytes, int32_t rank, int32_t world) {
     if (!h || !id || id_bytes < SGM_NCCL_ID_BYTES || world < 1 || rank < 0 || rank >= world) return fail(SGM_EINVAL, "bad argument");
+    if (h->cv && h->C > 1 && !(h->flags & SGM_FLAG_SHARED_MODE))
+        return fail(SGM_EINVAL, "a row-sharded control-variate pass needs SGM_FLAG_SHARED_MODE (every rank must hold the same mode)");
     if (int rc = load_nccl()) return rc;
     if (int rc = set_device(h)) return rc;
     NcclId nid;

@@ -58,6 +58,7 @@ struct ChainArgs {
     TensorConsts tc;
     // rng
     uint32_t k0, k1;
+    uint32_t chain0;     // global index of chain 0 of this launch (RNG stream id = chain0 + c)
     uint32_t index_tag;  // TAG_INDEX or TAG_OPT_INDEX
     uint64_t step0;   // step counter of the first iteration of this launch
     int iters;

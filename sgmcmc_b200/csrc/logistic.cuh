@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(512) logistic_chain_kernel(const ChainArgs a) 
             // internal element e: tensor 0 = bias (e == d), tensor 1 = beta; flat index f
             auto noise_at = [&](int f, int sub) -> float {
                 if (a.det) return a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + f];
-                return normal_at((uint32_t)f, (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1);
+                return normal_at((uint32_t)f, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1);
             };
             if (a.algo == ALGO_SGHMC) {  // refresh, R/dynamics.R:62
                 for (int e = tid; e <= d; e += blockDim.x) {
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(512) logistic_chain_kernel(const ChainArgs a) 
             }
             for (int l = 0; l < a.L; ++l) {
                 const int sub = l + 1;
-                const Perm perm = make_perm(a.N, a.perm_bits, (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
+                const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
                 const int32_t* idx = a.det ? a.idx + (((size_t)c * a.iters + it) * a.L + l) * a.n : nullptr;
                 const int passes = seidel ? 2 : 1;
                 for (int pass = 0; pass < passes; ++pass) {
@@ -370,7 +370,7 @@ __global__ void logistic_logpost_kernel(const ChainArgs a, uint32_t word2, const
     __shared__ float scratch[32];
     const int c = blockIdx.x, tid = threadIdx.x;
     const float* th = theta + (size_t)c * a.Pst;
-    const Perm perm = make_perm(a.N, a.perm_bits, (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
+    const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
     const int32_t* idx = a.det ? a.idx + (size_t)c * a.n : nullptr;
     float ll = 0.f;
     for (int j = tid; j < a.n; j += blockDim.x) {

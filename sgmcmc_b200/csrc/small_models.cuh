@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
             const uint64_t step = a.step0 + (uint64_t)it;
             auto noise_at = [&](int f, int sub) -> float {
                 if (a.det) return a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + f];
-                return normal_at((uint32_t)f, (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1);
+                return normal_at((uint32_t)f, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1);
             };
             if (a.algo == ALGO_SGHMC) {  // momentum refresh, R/dynamics.R:62, R/update.R:52-57
 #pragma unroll
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
             }
             for (int l = 0; l < a.L; ++l) {
                 const int sub = l + 1;
-                Perm perm = make_perm(a.N, a.perm_bits, (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
+                Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
                 const int32_t* idx = a.det ? a.idx + (((size_t)c * a.iters + it) * a.L + l) * a.n : nullptr;
                 // sgld / sghmc: one gradient evaluation per tensor (Gauss-Seidel, R/update.R:43-45,60-64);
                 // sgnht / optimiser: all tensors from one evaluation (R/update.R:72-80, cV.R:87-88).
@@ -227,7 +227,7 @@ __global__ void small_logpost_kernel(const ChainArgs a, uint32_t word2, double* 
         const int f = small_flat_of_slot<MODEL>(k, d);
         th[k] = f >= 0 ? a.theta[(size_t)c * a.Pst + f] : 0.f;
     }
-    Perm perm = make_perm(a.N, a.perm_bits, (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
+    Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
     const int32_t* idx = a.det ? a.idx + (size_t)c * a.n : nullptr;
     float ll = 0.f;
     for (int j = lane; j < a.n; j += 32) {
