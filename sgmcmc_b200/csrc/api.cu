@@ -298,6 +298,8 @@ static void host_tables(const sgm_handle* h, std::vector<int>& flat_of, std::vec
     if (h->model == SGM_MODEL_LOGISTIC) {
         for (int e = 0; e < h->d; ++e) { flat_of[e] = e + 1; tensor_of[e] = 1; }
         flat_of[h->d] = 0; tensor_of[h->d] = 0;
+    } else if (h->model == SGM_MODEL_SOFTMAX_NET && h->nn) {
+        softmax_net_tables(h->nn, flat_of.data(), tensor_of.data(), h->Pst);
     } else {
         for (int t = 0; t < h->T; ++t)
             for (int64_t k = 0; k < h->tensors[t].size; ++k) {
@@ -622,6 +624,11 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
         CU(cudaMemsetAsync(h->g_hat, 0, sbytes, h->stream));
         (void)hb;
     }
+    if (h->model == SGM_MODEL_SOFTMAX_NET) {
+        const int hid = (int)h->tensors[3].size, outc = (int)h->tensors[2].size;
+        int rc = softmax_net_create(&h->nn, h->d, hid, outc, h->n, h->C, h->device);
+        if (rc != 0) return bail(fail(SGM_ECUDA, "softmax net workspace: %s", cudaGetErrorString((cudaError_t)rc)));
+    }
     // initial state: every chain starts at params (internal layout)
     {
         std::vector<int> flat_of, tensor_of;
@@ -682,11 +689,6 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     a.noise_len = (h->algo == SGM_ALGO_SGHMC) ? (h->L + 1) * h->P : h->P;
     a.diverged = h->d_flag;
 
-    if (h->model == SGM_MODEL_SOFTMAX_NET) {
-        const int hid = (int)h->tensors[3].size, outc = (int)h->tensors[2].size;
-        int rc = softmax_net_create(&h->nn, h->d, hid, outc, h->n, h->C, h->device);
-        if (rc != 0) return bail(fail(SGM_ECUDA, "softmax net workspace: %s", cudaGetErrorString((cudaError_t)rc)));
-    }
     *out = h;
     return SGM_OK;
 }

@@ -1,10 +1,714 @@
+// 784-100-10 softmax-softmax network family (vignettes/nn.Rmd:58-79): one CTA per chain,
+// one persistent launch for `iters` sgmcmcSteps.
+//
+// Replaces, for this family, dataFeed/dataSelect (R/update.R:166-194), tf$gradients of
+// estLogPost (R/setup.R:36-62,116-125), declareDynamics.* (R/dynamics.R:7-120) and the
+// per-tensor Session.run loops of sgmcmcStep.* (R/update.R:40-81).
+//
+// Forward / backward, per minibatch row block (<= 128 rows):
+//   S1  Z1 = X B + b,  H = softmax_row(Z1)                       [n x 784] x [784 x 100]
+//   S2  Z2 = H A + a,  Pr = softmax_row(Z2),  dZ2 = Y - Pr * rowsum(Y)
+//   S3  grad A = H^T dZ2,  grad a = colsum(dZ2)
+//   S4  dH = dZ2 A^T,  dZ1 = H * (dH - rowsum(dH * H)),  grad b = colsum(dZ1)
+//   S5  grad B = X^T dZ1                                          [784 x n] x [n x 100]
+// The reference updates the 8 parameter tensors one Session.run at a time (Gauss-Seidel,
+// R/update.R:43-45,60-64): A, B, a, b, lambdaA, lambdaB, lambdaa, lambdab.  Because Z1/H
+// depend only on (B, b), the exact sequence needs S1 twice and S5 once per sub-step:
+//   S1 S2 S3 -> A;  S2 S4 S5 -> B;  S1 S2 S3 -> a;  S2 S4 -> b;  lambdas (prior only).
+//
+// Internal parameter layout per chain (float32, stride Pst): A[k][l] row-major, B[j][k]
+// row-major, a, b, 4 lambdas; the flat (ABI) order keeps R's column-major element order
+// inside A and B.  Dynamics noise is indexed by INTERNAL element (Philox block = 4
+// consecutive internal elements) when drawn on the device, by flat index when supplied.
 #include "softmax_net.cuh"
+#include <cstdio>
+
 namespace sgm {
-struct SoftmaxNetWork { int dummy; };
-int softmax_net_create(SoftmaxNetWork**, int, int, int, int, int, int) { return (int)cudaErrorNotSupported; }
-void softmax_net_destroy(SoftmaxNetWork*) {}
-int softmax_net_launch(SoftmaxNetWork*, const ChainArgs&, cudaStream_t, int*) { return (int)cudaErrorNotSupported; }
-int softmax_net_fullgrad(SoftmaxNetWork*, const ChainArgs&, int64_t, int64_t, int, const float*, double*, cudaStream_t) { return (int)cudaErrorNotSupported; }
-int softmax_net_fullgrad_finish(SoftmaxNetWork*, const ChainArgs&, int, const double*, const float*, float*, float*, cudaStream_t) { return (int)cudaErrorNotSupported; }
-int softmax_net_logpost(SoftmaxNetWork*, const ChainArgs&, uint32_t, const float*, double*, cudaStream_t) { return (int)cudaErrorNotSupported; }
+
+constexpr int NN_THREADS = 512;
+constexpr int NN_WARPS = NN_THREADS / 32;
+constexpr int NN_RB = 128;      // rows per block
+constexpr int NN_KC = 32;       // K chunk of S1
+constexpr int NN_JT = 64;       // j tile of S5
+constexpr int NN_MAXH = 128;    // hidden width limit (lanes x 4)
+constexpr int NN_MAXO = 16;     // output width limit
+
+struct NNDims {
+    int din, dh, dop;  // dop = output width padded to a multiple of 4
+    int dout;
+    int offA, offB, offa, offb, offl;  // internal == flat tensor offsets
+    int P;
+};
+
+struct SoftmaxNetWork {
+    NNDims dm;
+    int n, chains, device;
+    float* G = nullptr;      // [chains][Pst] gradient sums at theta
+    float* Ghat = nullptr;   // [chains][Pst] gradient sums at theta_hat (cv)
+    float* part = nullptr;   // full-gradient partials
+    size_t part_cap = 0;
+    size_t smem = 0;
+};
+
+__device__ __forceinline__ int nn_flat_of_internal(const NNDims& dm, int e) {
+    if (e < dm.offB) { const int k = e / dm.dout, l = e % dm.dout; return dm.offA + k + dm.dh * l; }
+    if (e < dm.offa) { const int r = e - dm.offB; const int j = r / dm.dh, k = r % dm.dh; return dm.offB + j + dm.din * k; }
+    return e;
 }
+__device__ __forceinline__ int nn_tensor_of(const NNDims& dm, int e) {
+    if (e < dm.offB) return 0;
+    if (e < dm.offa) return 1;
+    if (e < dm.offb) return 2;
+    if (e < dm.offl) return 3;
+    return 4 + (e - dm.offl);
+}
+
+struct NNSmem {
+    float* H;     // [NN_RB][dh]
+    float* dZ1;   // [NN_RB][dh]
+    float* dZ2;   // [NN_RB][dop]
+    float* A;     // [dh][dop] (zero padded)
+    float* a;     // [dop]
+    float* b;     // [dh]
+    float* tile;  // max(S1 tiles, S5 tile)
+    float* gb;    // [NN_WARPS][dh] partial column sums
+    float* gA;    // [dh*dop] gradient of A (row block accumulation)
+    float* ga;    // [dop]
+    float* red;   // [64]
+    int* rows;    // [NN_RB]
+};
+
+__device__ __forceinline__ float nn_block_sum(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = (threadIdx.x < NN_WARPS) ? red[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) { t = warp_sum(t); if (threadIdx.x == 0) red[32] = t; }
+    __syncthreads();
+    return red[32];
+}
+
+// load A (padded), a, b of one parameter vector into shared memory
+__device__ void nn_load_small(const NNDims& dm, const NNSmem& sm, const float* __restrict__ th) {
+    for (int i = threadIdx.x; i < dm.dh * dm.dop; i += NN_THREADS) {
+        const int k = i / dm.dop, l = i % dm.dop;
+        sm.A[i] = (l < dm.dout) ? th[dm.offA + k * dm.dout + l] : 0.f;
+    }
+    for (int i = threadIdx.x; i < dm.dop; i += NN_THREADS) sm.a[i] = (i < dm.dout) ? th[dm.offa + i] : 0.f;
+    for (int i = threadIdx.x; i < dm.dh; i += NN_THREADS) sm.b[i] = th[dm.offb + i];
+    __syncthreads();
+}
+
+// S1: H[r][k] = softmax_k( sum_j X[row_r][j] B[j][k] + b[k] ) for the nb rows listed in sm.rows
+__device__ void nn_stage1(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb,
+                          const float* __restrict__ th) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncg = dm.dh >> 2;           // column groups of 4
+    const bool live = lane < ncg;
+    float* Xt = sm.tile;                  // [NN_KC][NN_RB + 4]
+    float* Bt = sm.tile + NN_KC * (NN_RB + 4);   // [NN_KC][dh]
+    const float* __restrict__ B = th + dm.offB;
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+    for (int j0 = 0; j0 < dm.din; j0 += NN_KC) {
+        const int kc = (dm.din - j0 < NN_KC) ? dm.din - j0 : NN_KC;
+        __syncthreads();
+        // X tile, transposed: lanes walk rows so the shared-memory stores are conflict free
+        for (int t = tid; t < NN_RB * (NN_KC / 4); t += NN_THREADS) {
+            const int r = t % NN_RB, q = t / NN_RB;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nb && 4 * q < kc) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)sm.rows[r] * ld + j0 + 4 * q));
+            Xt[(4 * q + 0) * (NN_RB + 4) + r] = v.x; Xt[(4 * q + 1) * (NN_RB + 4) + r] = v.y;
+            Xt[(4 * q + 2) * (NN_RB + 4) + r] = v.z; Xt[(4 * q + 3) * (NN_RB + 4) + r] = v.w;
+        }
+        for (int t = tid; t < NN_KC * ncg; t += NN_THREADS) {
+            const int jj = t / ncg, cg = t % ncg;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (jj < kc) v = *reinterpret_cast<const float4*>(B + (size_t)(j0 + jj) * dm.dh + 4 * cg);
+            *reinterpret_cast<float4*>(Bt + jj * dm.dh + 4 * cg) = v;
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (int jj = 0; jj < NN_KC; ++jj) {
+                const float4 bv = *reinterpret_cast<const float4*>(Bt + jj * dm.dh + 4 * lane);
+                const float4 x0 = *reinterpret_cast<const float4*>(Xt + jj * (NN_RB + 4) + 8 * warp);
+                const float4 x1 = *reinterpret_cast<const float4*>(Xt + jj * (NN_RB + 4) + 8 * warp + 4);
+                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    acc[r][0] += xs[r] * bv.x; acc[r][1] += xs[r] * bv.y;
+                    acc[r][2] += xs[r] * bv.z; acc[r][3] += xs[r] * bv.w;
+                }
+            }
+        }
+    }
+    // bias + row softmax: a row's dh entries live in the lanes of one warp
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) bb = *reinterpret_cast<const float4*>(sm.b + 4 * lane);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int row = 8 * warp + r;
+        float v0 = acc[r][0] + bb.x, v1 = acc[r][1] + bb.y, v2 = acc[r][2] + bb.z, v3 = acc[r][3] + bb.w;
+        float m = live ? fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+        if (live) { e0 = expf(v0 - m); e1 = expf(v1 - m); e2 = expf(v2 - m); e3 = expf(v3 - m); }
+        const float s = warp_sum(e0 + e1 + e2 + e3);
+        if (live && row < nb)
+            *reinterpret_cast<float4*>(sm.H + row * dm.dh + 4 * lane) = make_float4(e0 / s, e1 / s, e2 / s, e3 / s);
+    }
+    __syncthreads();
+}
+
+// S2: dZ2[r][l] = Y[r][l] - Pr[r][l] * rowsum(Y[r]);  returns (via loglik) sum_r sum_l Y log Pr when asked
+__device__ float nn_stage2(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb, bool want_ll) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 2, lq = tid & 3;   // 128 rows x 4 quads of outputs
+    float ll = 0.f;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool qlive = 4 * lq < dm.dop;
+    if (r < nb && qlive) {
+        const float* h = sm.H + r * dm.dh;
+        for (int k = 0; k < dm.dh; ++k) {
+            const float hv = h[k];
+            const float4 av = *reinterpret_cast<const float4*>(sm.A + k * dm.dop + 4 * lq);
+            z[0] += hv * av.x; z[1] += hv * av.y; z[2] += hv * av.z; z[3] += hv * av.w;
+        }
+    }
+    float y[4] = {0.f, 0.f, 0.f, 0.f};
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int l = 4 * lq + c;
+        const bool ok = r < nb && l < dm.dout;
+        z[c] = ok ? z[c] + sm.a[l] : -INFINITY;
+        if (ok) y[c] = __ldg(X + (size_t)sm.rows[r] * ld + dm.din + l);
+        m = fmaxf(m, z[c]);
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float e[4], s = 0.f, ys = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { e[c] = (z[c] > -INFINITY) ? expf(z[c] - m) : 0.f; s += e[c]; ys += y[c]; }
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+    ys += __shfl_xor_sync(0xffffffffu, ys, 1); ys += __shfl_xor_sync(0xffffffffu, ys, 2);
+    if (r < nb && qlive) {
+        float4 o;
+        float* op = &o.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int l = 4 * lq + c;
+            const float pr = e[c] / s;
+            op[c] = (l < dm.dout) ? y[c] - pr * ys : 0.f;
+            if (want_ll && l < dm.dout && y[c] != 0.f) ll += y[c] * logf(pr);
+        }
+        *reinterpret_cast<float4*>(sm.dZ2 + r * dm.dop + 4 * lq) = o;
+    }
+    __syncthreads();
+    return ll;
+}
+
+// S3: gA[k][l] (+)= sum_r H[r][k] dZ2[r][l];  ga[l] (+)= sum_r dZ2[r][l]
+__device__ void nn_stage3(const NNDims& dm, const NNSmem& sm, int nb, bool first) {
+    for (int i = threadIdx.x; i < dm.dh * dm.dop; i += NN_THREADS) {
+        const int k = i / dm.dop, l = i % dm.dop;
+        float s = 0.f;
+        for (int r = 0; r < nb; ++r) s += sm.H[r * dm.dh + k] * sm.dZ2[r * dm.dop + l];
+        sm.gA[i] = first ? s : sm.gA[i] + s;
+    }
+    for (int l = threadIdx.x; l < dm.dop; l += NN_THREADS) {
+        float s = 0.f;
+        for (int r = 0; r < nb; ++r) s += sm.dZ2[r * dm.dop + l];
+        sm.ga[l] = first ? s : sm.ga[l] + s;
+    }
+    __syncthreads();
+}
+
+// S4: dZ1[r][k] = H (dH - rowsum(dH H)), dH = dZ2 A^T;  gb[k] (+)= sum_r dZ1[r][k]  (warp per row)
+__device__ void nn_stage4(const NNDims& dm, const NNSmem& sm, int nb, bool first, float* __restrict__ gb_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncg = dm.dh >> 2;
+    const bool live = lane < ncg;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = warp; r < nb; r += NN_WARPS) {
+        float dh[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            h = *reinterpret_cast<const float4*>(sm.H + r * dm.dh + 4 * lane);
+            for (int l = 0; l < dm.dout; ++l) {
+                const float dz = sm.dZ2[r * dm.dop + l];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dh[c] += dz * sm.A[(4 * lane + c) * dm.dop + l];
+            }
+        }
+        const float s = warp_sum(dh[0] * h.x + dh[1] * h.y + dh[2] * h.z + dh[3] * h.w);
+        if (live) {
+            const float4 o = make_float4(h.x * (dh[0] - s), h.y * (dh[1] - s), h.z * (dh[2] - s), h.w * (dh[3] - s));
+            *reinterpret_cast<float4*>(sm.dZ1 + r * dm.dh + 4 * lane) = o;
+            cs[0] += o.x; cs[1] += o.y; cs[2] += o.z; cs[3] += o.w;
+        }
+    }
+    if (live) *reinterpret_cast<float4*>(sm.gb + warp * dm.dh + 4 * lane) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+    __syncthreads();
+    for (int k = threadIdx.x; k < dm.dh; k += NN_THREADS) {
+        float s = 0.f;
+        for (int w = 0; w < NN_WARPS; ++w) s += sm.gb[w * dm.dh + k];
+        gb_out[k] = first ? s : gb_out[k] + s;
+    }
+    __syncthreads();
+}
+
+// S5: GB[j][k] (+)= sum_r X[row_r][j] dZ1[r][k]
+__device__ void nn_stage5(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb, bool first,
+                          float* __restrict__ GB) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncg = dm.dh >> 2;
+    const bool live = lane < ncg;
+    float* Xs = sm.tile;   // [NN_RB][NN_JT]
+    for (int j0 = 0; j0 < dm.din; j0 += NN_JT) {
+        const int jt = (dm.din - j0 < NN_JT) ? dm.din - j0 : NN_JT;
+        __syncthreads();
+        for (int t = tid; t < NN_RB * (NN_JT / 4); t += NN_THREADS) {
+            const int r = t / (NN_JT / 4), q = t % (NN_JT / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nb && 4 * q < jt) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)sm.rows[r] * ld + j0 + 4 * q));
+            *reinterpret_cast<float4*>(Xs + r * NN_JT + 4 * q) = v;
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+        if (live) {
+#pragma unroll 4
+            for (int r = 0; r < nb; ++r) {
+                const float4 xv = *reinterpret_cast<const float4*>(Xs + r * NN_JT + 4 * warp);
+                const float4 dz = *reinterpret_cast<const float4*>(sm.dZ1 + r * dm.dh + 4 * lane);
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    acc[a][0] += xs[a] * dz.x; acc[a][1] += xs[a] * dz.y;
+                    acc[a][2] += xs[a] * dz.z; acc[a][3] += xs[a] * dz.w;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int j = j0 + 4 * warp + a;
+                if (j < dm.din) {
+                    float4* dst = reinterpret_cast<float4*>(GB + (size_t)j * dm.dh + 4 * lane);
+                    float4 o = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                    if (!first) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                    *dst = o;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+enum : int { NEED_A = 1, NEED_B = 2, NEED_a = 4, NEED_b = 8, NEED_ALL = 15 };
+
+// One gradient evaluation of the log-likelihood SUM over the minibatch at `th`, for the tensors in
+// `need`, written to Gout (internal layout).  h_valid: sm.H already holds softmax(X B + b) for th.
+// Rows come from idx (deterministic), the keyed permutation, or the contiguous range [row0, row0+n).
+__device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int n,
+                         const Perm* perm, const int32_t* __restrict__ idx, int64_t row0,
+                         const float* __restrict__ th, int need, bool h_valid, bool want_ll, float* __restrict__ Gout) {
+    nn_load_small(dm, sm, th);
+    float ll = 0.f;
+    const int nblocks = (n + NN_RB - 1) / NN_RB;
+    for (int rb = 0; rb < nblocks; ++rb) {
+        const int r0 = rb * NN_RB;
+        const int nb = (n - r0 < NN_RB) ? n - r0 : NN_RB;
+        const bool first = rb == 0;
+        if (!(h_valid && nblocks == 1)) {
+            __syncthreads();
+            for (int r = threadIdx.x; r < NN_RB; r += NN_THREADS)
+                sm.rows[r] = (r < nb) ? (idx ? idx[r0 + r] : (perm ? (int)perm_at(*perm, (uint32_t)(r0 + r)) : (int)(row0 + r0 + r))) : 0;
+            __syncthreads();
+            nn_stage1(dm, sm, X, ld, nb, th);
+        }
+        ll += nn_stage2(dm, sm, X, ld, nb, want_ll);
+        if (need & (NEED_A | NEED_a)) nn_stage3(dm, sm, nb, first);
+        if (need & (NEED_b | NEED_B)) nn_stage4(dm, sm, nb, first, Gout + dm.offb);
+        if (need & NEED_B) nn_stage5(dm, sm, X, ld, nb, first, Gout + dm.offB);
+    }
+    if (need & (NEED_A | NEED_a)) {
+        for (int i = threadIdx.x; i < dm.dh * dm.dout; i += NN_THREADS) {
+            const int k = i / dm.dout, l = i % dm.dout;
+            Gout[dm.offA + i] = sm.gA[k * dm.dop + l];
+        }
+        for (int l = threadIdx.x; l < dm.dout; l += NN_THREADS) Gout[dm.offa + l] = sm.ga[l];
+    }
+    __syncthreads();
+    return ll;
+}
+
+// sum of squares of one weight tensor (for the lambda gradients / prior value)
+__device__ float nn_sumsq(const float* __restrict__ w, int count, float* red) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < count; i += NN_THREADS) { const float v = w[i]; s += v * v; }
+    return nn_block_sum(s, red);
+}
+
+__device__ __forceinline__ void nn_tensor_range(const NNDims& dm, int t, int& lo, int& hi) {
+    const int offs[9] = {dm.offA, dm.offB, dm.offa, dm.offb, dm.offl, dm.offl + 1, dm.offl + 2, dm.offl + 3, dm.offl + 4};
+    lo = offs[t]; hi = offs[t + 1];
+}
+
+// prior gradient of internal element e at th; ssq = ||W||^2 for a lambda element
+__device__ __forceinline__ float nn_prior_grad(const NNDims& dm, const float* __restrict__ th, int e, int t, float ssq) {
+    if (t < 4) return -th[dm.offl + t] * th[e];
+    int lo, hi;
+    nn_tensor_range(dm, t - 4, lo, hi);
+    return (float)(hi - lo) / (2.0f * th[e]) - 0.5f * ssq - 1.0f;
+}
+
+struct NNChainState {
+    float* th; float* mo; const float* hat; const float* ghat; float* G; float* Ghat;
+    float zeta[MAX_TENSORS];
+};
+
+// fused dynamics update of tensor t (R/dynamics.R) from the gradient sums in G (and Ghat for cv)
+__device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNSmem& sm, NNChainState& st, int t, int c,
+                                 uint64_t step, int sub, float* uu_out) {
+    const float SQRT_HALF = 0.70710678118654752440f;
+    int lo, hi;
+    nn_tensor_range(dm, t, lo, hi);
+    float ssq = 0.f, ssq_hat = 0.f;
+    if (t >= 4 && a.use_prior) {
+        int wlo, whi;
+        nn_tensor_range(dm, t - 4, wlo, whi);
+        ssq = nn_sumsq(st.th + wlo, whi - wlo, sm.red);
+        if (a.cv) ssq_hat = nn_sumsq(st.hat + wlo, whi - wlo, sm.red);
+    }
+    float uu = 0.f;
+    for (int e0 = lo + 4 * threadIdx.x; e0 < hi; e0 += 4 * NN_THREADS) {
+        float z4[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool noisy = a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT;
+        if (noisy && !a.det) {
+            // Philox block = 4 consecutive INTERNAL elements (tensor ranges need not be 4-aligned)
+            float zz[4];
+            normal4_at((uint32_t)(e0 >> 2), a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1, zz);
+            if ((e0 & 3) == 0) { z4[0] = zz[0]; z4[1] = zz[1]; z4[2] = zz[2]; z4[3] = zz[3]; }
+            else {
+                float z2[4];
+                normal4_at((uint32_t)(e0 >> 2) + 1u, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1, z2);
+                for (int q = 0; q < 4; ++q) { const int ee = (e0 & 3) + q; z4[q] = ee < 4 ? zz[ee] : z2[ee - 4]; }
+            }
+        }
+        for (int q = 0; q < 4; ++q) {
+            const int e = e0 + q;
+            if (e >= hi) break;
+            const float th = st.th[e];
+            float g = (t < 4) ? a.corr * st.G[e] : 0.f;
+            if (a.use_prior) g += nn_prior_grad(dm, st.th, e, t, ssq);
+            if (a.cv) {
+                float gh = (t < 4) ? a.corr * st.Ghat[e] : 0.f;
+                if (a.use_prior) gh += nn_prior_grad(dm, st.hat, e, t, ssq_hat);
+                g = (st.ghat[e] - gh) + g;   // R/setup.R:58
+            }
+            float z = z4[q];
+            if (noisy && a.det)
+                z = a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + nn_flat_of_internal(dm, e)];
+            if (a.algo == ALGO_SGLD) {
+                st.th[e] = th + (a.tc.half_eps[t] * g + SQRT_HALF * (a.tc.sqrt_2eps[t] * z));
+            } else if (a.algo == ALGO_SGHMC) {
+                float nu = st.mo[e];
+                nu += a.tc.eps[t] * g - a.tc.alpha[t] * nu + a.tc.sqrt_alpha[t] * (a.tc.sqrt_2eps[t] * z);
+                st.mo[e] = nu;
+                st.th[e] = th + nu;
+            } else if (a.algo == ALGO_SGNHT) {
+                float u = st.mo[e];
+                u += a.tc.eps[t] * g - u * st.zeta[t] + a.tc.sqrt_a[t] * (a.tc.sqrt_2eps[t] * z);
+                st.mo[e] = u;
+                uu += u * u;
+            } else if (a.algo == ALGO_OPT) {
+                st.th[e] = th + a.opt_lr * g;
+            } else {
+                st.mo[e] = g;
+            }
+        }
+    }
+    if (uu_out) *uu_out = nn_block_sum(uu, sm.red);
+    __syncthreads();
+}
+
+__device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
+    float* p = base;
+    sm.H = p; p += NN_RB * dm.dh;
+    sm.dZ1 = p; p += NN_RB * dm.dh;
+    sm.dZ2 = p; p += NN_RB * dm.dop;
+    sm.A = p; p += dm.dh * dm.dop;
+    sm.a = p; p += NN_MAXO;
+    sm.b = p; p += NN_MAXH;
+    const int t1 = NN_KC * (NN_RB + 4) + NN_KC * dm.dh, t5 = NN_RB * NN_JT;
+    sm.tile = p; p += (t1 > t5 ? t1 : t5);
+    sm.gb = p; p += NN_WARPS * dm.dh;
+    sm.gA = p; p += dm.dh * dm.dop;
+    sm.ga = p; p += NN_MAXO;
+    sm.red = p; p += 64;
+    sm.rows = reinterpret_cast<int*>(p);
+}
+
+static size_t nn_smem_bytes(const NNDims& dm) {
+    const int t1 = NN_KC * (NN_RB + 4) + NN_KC * dm.dh, t5 = NN_RB * NN_JT;
+    size_t f = (size_t)2 * NN_RB * dm.dh + NN_RB * dm.dop + dm.dh * dm.dop + NN_MAXO + NN_MAXH + (t1 > t5 ? t1 : t5) +
+               NN_WARPS * dm.dh + dm.dh * dm.dop + NN_MAXO + 64 + NN_RB;
+    return f * sizeof(float);
+}
+
+__global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const ChainArgs a, const NNDims dm, float* Gall, float* Ghatall) {
+    extern __shared__ __align__(16) float smem_f[];
+    NNSmem sm;
+    nn_carve(dm, smem_f, sm);
+    const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
+    for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
+        NNChainState st;
+        st.th = a.theta + (size_t)c * a.Pst; st.mo = a.mom + (size_t)c * a.Pst;
+        st.hat = a.cv ? a.theta_hat + (size_t)c * a.hat_stride : nullptr;
+        st.ghat = a.cv ? a.g_hat + (size_t)c * a.hat_stride : nullptr;
+        st.G = Gall + (size_t)c * a.Pst; st.Ghat = Ghatall ? Ghatall + (size_t)c * a.Pst : nullptr;
+        for (int t = 0; t < MAX_TENSORS; ++t) st.zeta[t] = a.thermo[c * MAX_TENSORS + t];
+        for (int it = 0; it < a.iters; ++it) {
+            const uint64_t step = a.step0 + (uint64_t)it;
+            if (a.algo == ALGO_SGHMC) {  // refresh (R/dynamics.R:62)
+                for (int e = threadIdx.x; e < a.P; e += NN_THREADS) {
+                    const int t = nn_tensor_of(dm, e);
+                    const float z = a.det ? a.noise[(size_t)c * a.noise_len + nn_flat_of_internal(dm, e)]
+                                          : normal_at((uint32_t)e, a.chain0 + (uint32_t)c, word2_of(step, a.L, 0), TAG_NOISE, a.k0, a.k1);
+                    st.mo[e] = 0.5f * (a.tc.sqrt_2eps[t] * z);
+                }
+                __syncthreads();
+            }
+            for (int l = 0; l < a.L; ++l) {
+                const int sub = l + 1;
+                const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
+                const int32_t* idx = a.det ? a.idx + (((size_t)c * a.iters + it) * a.L + l) * a.n : nullptr;
+                const Perm* pp = a.det ? nullptr : &perm;
+                if (a.cv) nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.hat, NEED_ALL, false, false, st.Ghat);
+                if (seidel) {
+                    // A
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_A, false, false, st.G);
+                    nn_update_tensor(a, dm, sm, st, 0, c, step, sub, nullptr);
+                    // B: H still valid (depends on B, b only)
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_B, true, false, st.G);
+                    nn_update_tensor(a, dm, sm, st, 1, c, step, sub, nullptr);
+                    // a: B changed -> recompute H
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_a, false, false, st.G);
+                    nn_update_tensor(a, dm, sm, st, 2, c, step, sub, nullptr);
+                    // b
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_b, true, false, st.G);
+                    nn_update_tensor(a, dm, sm, st, 3, c, step, sub, nullptr);
+                    for (int t = 4; t < 8; ++t) nn_update_tensor(a, dm, sm, st, t, c, step, sub, nullptr);
+                } else {
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_ALL, false, false, st.G);
+                    float uu[MAX_TENSORS];
+                    // All tensors move from ONE evaluation.  The mode finder writes theta in place, so the
+                    // precisions (whose gradient reads ||W||^2) go first and the weights see the OLD precisions.
+                    float lam_old[4], lam_new[4];
+                    for (int t = 0; t < 4; ++t) lam_old[t] = st.th[dm.offl + t];
+                    for (int t = 7; t >= 4; --t) nn_update_tensor(a, dm, sm, st, t, c, step, sub, &uu[t]);
+                    if (a.algo == ALGO_OPT) {
+                        for (int t = 0; t < 4; ++t) lam_new[t] = st.th[dm.offl + t];
+                        __syncthreads();
+                        if (threadIdx.x == 0) for (int t = 0; t < 4; ++t) st.th[dm.offl + t] = lam_old[t];
+                        __syncthreads();
+                    }
+                    for (int t = 3; t >= 0; --t) nn_update_tensor(a, dm, sm, st, t, c, step, sub, &uu[t]);
+                    if (a.algo == ALGO_OPT) {
+                        if (threadIdx.x == 0) for (int t = 0; t < 4; ++t) st.th[dm.offl + t] = lam_new[t];
+                        __syncthreads();
+                    }
+                    if (a.algo == ALGO_SGNHT) {  // theta += u, then thermostats (R/update.R:75-80)
+                        for (int e = threadIdx.x; e < a.P; e += NN_THREADS) st.th[e] += st.mo[e];
+                        for (int t = 0; t < 8; ++t) {
+                            int lo, hi;
+                            nn_tensor_range(dm, t, lo, hi);
+                            st.zeta[t] += uu[t] / (float)(hi - lo) - a.tc.eps[t];
+                        }
+                        __syncthreads();
+                    }
+                }
+            }
+            bool bad = false;
+            for (int e = threadIdx.x; e < a.P; e += NN_THREADS) {
+                const float v = st.th[e];
+                bad |= !isfinite(v);
+                if (a.store) a.store[((size_t)(a.store_pos + it) * a.C + c) * a.P + nn_flat_of_internal(dm, e)] = v;
+            }
+            if (bad) *a.diverged = 1;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0)
+            for (int t = 0; t < MAX_TENSORS; ++t) a.thermo[c * MAX_TENSORS + t] = st.zeta[t];
+    }
+}
+
+// full-data gradient partials: CTA (x, m) sums rows [row0 + x*rows_per, ...) at theta_hat[m] into part[(m*gx + x)][Pst]
+__global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_fullgrad_kernel(const ChainArgs a, const NNDims dm, int64_t row0, int64_t row1,
+                                                                             int rows_per, const float* __restrict__ theta_hat, float* __restrict__ part) {
+    extern __shared__ __align__(16) float smem_f[];
+    NNSmem sm;
+    nn_carve(dm, smem_f, sm);
+    const int m = blockIdx.y;
+    const int64_t lo = row0 + (int64_t)blockIdx.x * rows_per;
+    int64_t hi = lo + rows_per; if (hi > row1) hi = row1;
+    float* G = part + ((size_t)m * gridDim.x + blockIdx.x) * a.Pst;
+    if (lo >= hi) { for (int e = threadIdx.x; e < a.Pst; e += NN_THREADS) G[e] = 0.f; return; }
+    nn_eval(dm, sm, a.X, a.ld, (int)(hi - lo), nullptr, nullptr, lo, theta_hat + (size_t)m * a.Pst, NEED_ALL, false, false, G);
+    for (int e = dm.offl + threadIdx.x; e < a.Pst; e += NN_THREADS) G[e] = 0.f;
+}
+
+__global__ void softmax_net_part_reduce(const float* __restrict__ part, int gx, int Pst, double* __restrict__ gsum, int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int m = i / Pst, e = i % Pst;
+    double s = 0.0;
+    for (int x = 0; x < gx; ++x) s += (double)part[((size_t)m * gx + x) * Pst + e];
+    gsum[i] = s;
+}
+
+__global__ void __launch_bounds__(NN_THREADS) softmax_net_finish_kernel(const ChainArgs a, const NNDims dm, const double* __restrict__ gsum,
+                                                                        const float* __restrict__ theta_hat, float* __restrict__ g_hat,
+                                                                        float* __restrict__ theta) {
+    __shared__ float red[64];
+    const int m = blockIdx.x;
+    const float* th = theta_hat + (size_t)m * a.Pst;
+    float ssq[4];
+    for (int t = 0; t < 4; ++t) {
+        int lo, hi;
+        nn_tensor_range(dm, t, lo, hi);
+        ssq[t] = nn_sumsq(th + lo, hi - lo, red);
+    }
+    for (int e = threadIdx.x; e < a.P; e += NN_THREADS) {
+        const int t = nn_tensor_of(dm, e);
+        float g = (t < 4) ? (float)gsum[(size_t)m * a.Pst + e] : 0.f;
+        if (a.use_prior) g += nn_prior_grad(dm, th, e, t, t >= 4 ? ssq[t - 4] : 0.f);
+        g_hat[(size_t)m * a.Pst + e] = g;
+        theta[(size_t)m * a.Pst + e] = th[e];
+    }
+}
+
+__global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_logpost_kernel(const ChainArgs a, const NNDims dm, uint32_t word2,
+                                                                            const float* __restrict__ theta, float* Gscratch,
+                                                                            double* __restrict__ out) {
+    extern __shared__ __align__(16) float smem_f[];
+    NNSmem sm;
+    nn_carve(dm, smem_f, sm);
+    const int c = blockIdx.x;
+    const float* th = theta + (size_t)c * a.Pst;
+    const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
+    const int32_t* idx = a.det ? a.idx + (size_t)c * a.n : nullptr;
+    float ll = nn_eval(dm, sm, a.X, a.ld, a.n, a.det ? nullptr : &perm, idx, 0, th, 0, false, true, Gscratch + (size_t)c * a.Pst);
+    ll = nn_block_sum(ll, sm.red);
+    float lp = 0.f;
+    if (a.use_prior) {
+        const float LOG_2PI = 1.8378770664093453f;
+        for (int t = 0; t < 4; ++t) {
+            int lo, hi;
+            nn_tensor_range(dm, t, lo, hi);
+            const float ssq = nn_sumsq(th + lo, hi - lo, sm.red);
+            const float lam = th[dm.offl + t];
+            lp += (float)(hi - lo) * (0.5f * logf(lam) - 0.5f * LOG_2PI) - 0.5f * lam * ssq - lam;
+        }
+    }
+    if (threadIdx.x == 0) out[c] = (double)(lp + a.corr * ll);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int softmax_net_create(SoftmaxNetWork** out, int d_in, int d_hidden, int d_out, int n, int chains, int device) {
+    if (d_in % 4 || d_hidden % 4 || d_hidden > NN_MAXH || d_out > NN_MAXO || d_out < 1 || (d_hidden * d_out) % 4) return (int)cudaErrorInvalidValue;
+    SoftmaxNetWork* w = new SoftmaxNetWork();
+    NNDims& dm = w->dm;
+    dm.din = d_in; dm.dh = d_hidden; dm.dout = d_out; dm.dop = 4 * ((d_out + 3) / 4);
+    dm.offA = 0; dm.offB = d_hidden * d_out; dm.offa = dm.offB + d_in * d_hidden; dm.offb = dm.offa + d_out; dm.offl = dm.offb + d_hidden;
+    dm.P = dm.offl + 4;
+    w->n = n; w->chains = chains; w->device = device;
+    w->smem = nn_smem_bytes(dm);
+    const int Pst = 4 * ((dm.P + 3) / 4);
+    cudaError_t e = cudaMalloc(&w->G, (size_t)chains * Pst * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&w->Ghat, (size_t)chains * Pst * sizeof(float));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(softmax_net_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(softmax_net_fullgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(softmax_net_logpost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem);
+    if (e != cudaSuccess) { softmax_net_destroy(w); return (int)e; }
+    *out = w;
+    return 0;
+}
+
+void softmax_net_destroy(SoftmaxNetWork* w) {
+    if (!w) return;
+    if (w->G) cudaFree(w->G);
+    if (w->Ghat) cudaFree(w->Ghat);
+    if (w->part) cudaFree(w->part);
+    delete w;
+}
+
+void softmax_net_tables(const SoftmaxNetWork* w, int* flat_of, int* tensor_of, int Pst) {
+    const NNDims& dm = w->dm;
+    for (int e = 0; e < Pst; ++e) {
+        if (e >= dm.P) { flat_of[e] = -1; tensor_of[e] = 0; continue; }
+        int f = e, t;
+        if (e < dm.offB) { const int k = e / dm.dout, l = e % dm.dout; f = dm.offA + k + dm.dh * l; t = 0; }
+        else if (e < dm.offa) { const int r = e - dm.offB; const int j = r / dm.dh, k = r % dm.dh; f = dm.offB + j + dm.din * k; t = 1; }
+        else if (e < dm.offb) t = 2;
+        else if (e < dm.offl) t = 3;
+        else t = 4 + (e - dm.offl);
+        flat_of[e] = f; tensor_of[e] = t;
+    }
+}
+
+int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t stream, int* launches) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+    const int grid = a.C < sms ? a.C : sms;
+    softmax_net_chain_kernel<<<grid, NN_THREADS, w->smem, stream>>>(a, w->dm, w->G, a.cv ? w->Ghat : nullptr);
+    *launches = 1;
+    return (int)cudaGetLastError();
+}
+
+int softmax_net_fullgrad(SoftmaxNetWork* w, const ChainArgs& a, int64_t row0, int64_t row1, int M, const float* theta_hat,
+                         double* gsum, cudaStream_t stream) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+    const int64_t rows = row1 - row0;
+    int gx = (int)((sms + M - 1) / M);
+    if (gx < 1) gx = 1;
+    int64_t rows_per = (rows + gx - 1) / gx;
+    if (rows_per < NN_RB) rows_per = NN_RB;
+    rows_per = ((rows_per + NN_RB - 1) / NN_RB) * NN_RB;
+    gx = (int)((rows + rows_per - 1) / rows_per);
+    if (gx < 1) gx = 1;
+    const size_t need = (size_t)M * gx * a.Pst * sizeof(float);
+    if (need > w->part_cap) {
+        if (w->part) cudaFree(w->part);
+        w->part = nullptr; w->part_cap = 0;
+        cudaError_t e = cudaMalloc(&w->part, need);
+        if (e != cudaSuccess) return (int)e;
+        w->part_cap = need;
+    }
+    dim3 grid((unsigned)gx, (unsigned)M);
+    softmax_net_fullgrad_kernel<<<grid, NN_THREADS, w->smem, stream>>>(a, w->dm, row0, row1, (int)rows_per, theta_hat, w->part);
+    const int total = M * a.Pst;
+    softmax_net_part_reduce<<<(total + 255) / 256, 256, 0, stream>>>(w->part, gx, a.Pst, gsum, total);
+    return (int)cudaGetLastError();
+}
+
+int softmax_net_fullgrad_finish(SoftmaxNetWork* w, const ChainArgs& a, int M, const double* gsum, const float* theta_hat,
+                                float* g_hat, float* theta, cudaStream_t stream) {
+    softmax_net_finish_kernel<<<M, NN_THREADS, 0, stream>>>(a, w->dm, gsum, theta_hat, g_hat, theta);
+    return (int)cudaGetLastError();
+}
+
+int softmax_net_logpost(SoftmaxNetWork* w, const ChainArgs& a, uint32_t word2, const float* theta, double* out, cudaStream_t stream) {
+    softmax_net_logpost_kernel<<<a.C, NN_THREADS, w->smem, stream>>>(a, w->dm, word2, theta, w->G, out);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sgm

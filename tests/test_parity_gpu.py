@@ -16,7 +16,8 @@ from tests.cases import ALGOS, device_setup, make_case, oracle_chain
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
-CASES = ["gauss1d", "gauss2d", "gauss3d_fullcov", "gauss2d_flat", "mixture", "logistic5", "logistic54", "logistic130"]
+CASES = ["gauss1d", "gauss2d", "gauss3d_fullcov", "gauss2d_flat", "mixture", "logistic5", "logistic54", "logistic130",
+         "softmaxnet_small", "softmaxnet"]
 
 
 def close(ours, ref, scale=None, rtol=RTOL, what=""):
@@ -47,6 +48,8 @@ def test_deterministic_steps_match_oracle(lib, case_name, algo, cv):
     from sgmcmc_b200 import validation as V
     case = make_case(case_name)
     C, steps, n_opt = 3, 4, 25
+    if case_name == "softmaxnet":  # full 784-100-10: keep the CPU oracle's share of the test short
+        C, steps, n_opt = 2, 2, 3
     rs = np.random.RandomState(5)
     dev = device_setup(case, algo, cv, n_chains=C, n_iters_opt=n_opt)
     chains32 = [oracle_chain(case, algo, cv, np.float32, graph=True) for _ in range(C)]
@@ -119,7 +122,7 @@ def test_deterministic_steps_match_oracle(lib, case_name, algo, cv):
             close(thermo[c], ref, rtol=1e-5, what="thermostat")
 
 
-@pytest.mark.parametrize("case_name", ["gauss2d", "mixture", "logistic54"])
+@pytest.mark.parametrize("case_name", ["gauss2d", "mixture", "logistic54", "softmaxnet_small", "softmaxnet"])
 def test_est_logpost_matches_oracle(lib, case_name):
     from sgmcmc_b200 import validation as V
     case = make_case(case_name)
@@ -136,7 +139,8 @@ def test_est_logpost_matches_oracle(lib, case_name):
 
 @pytest.mark.parametrize("case_name,algo,cv", [("gauss2d", "sgld", False), ("mixture", "sghmc", False),
                                                ("logistic54", "sgld", True), ("logistic130", "sgnht", True),
-                                               ("gauss3d_fullcov", "sgnht", False), ("logistic5", "sghmc", True)])
+                                               ("gauss3d_fullcov", "sgnht", False), ("logistic5", "sghmc", True),
+                                               ("softmaxnet_small", "sghmc", False), ("softmaxnet_small", "sgnht", True)])
 def test_device_rng_streams_match_oracle(lib, case_name, algo, cv):
     """Device-side sampling: the oracle regenerates the Philox index / noise streams
     (indices bit-exact by construction) and must land on the same state."""
@@ -152,19 +156,29 @@ def test_device_rng_streams_match_oracle(lib, case_name, algo, cv):
     th = V.flatParams(dev)
     P = th.shape[1]
     Leff = L if algo == "sghmc" else 1
+    # the softmax-net kernels index device-drawn dynamics noise by INTERNAL element (A, B row-major)
+    to_internal = np.arange(P)
+    if case_name.startswith("softmaxnet"):
+        dh, do = case["params"]["A"].shape
+        din = case["params"]["B"].shape[0]
+        offB = dh * do
+        fA = np.arange(dh * do)
+        to_internal[fA] = (fA % dh) * do + fA // dh
+        fB = np.arange(din * dh)
+        to_internal[offB + fB] = offB + (fB % din) * dh + fB // din
     for c in range(C):
         ch = oracle_chain(case, algo, cv, np.float32, L=L)
         if algo != "sgld":
             ch.init_momentum(rng.normals(seed, c, 0, rng.TAG_MOMENTUM, P))
         if cv:
-            ch.find_mode([rng.minibatch_indices(seed, c, it, rng.TAG_OPT_INDEX, case["N"], case["n"]) for it in range(n_opt)])
+            ch.find_mode([rng.minibatch_indices(seed, c, 2 * it + 1, rng.TAG_OPT_INDEX, case["N"], case["n"]) for it in range(n_opt)])  # word2 = it*(L+1)+sub, L = 1
         for s in range(steps):
             w2 = lambda sub: s * (Leff + 1) + sub
             idx = np.stack([rng.minibatch_indices(seed, c, w2(l + 1), rng.TAG_INDEX, case["N"], case["n"]) for l in range(Leff)])
             if algo == "sghmc":
-                noise = np.concatenate([rng.normals(seed, c, w2(sub), rng.TAG_NOISE, P) for sub in range(Leff + 1)])
+                noise = np.concatenate([rng.normals(seed, c, w2(sub), rng.TAG_NOISE, P)[to_internal] for sub in range(Leff + 1)])
             else:
-                noise = rng.normals(seed, c, w2(1), rng.TAG_NOISE, P)
+                noise = rng.normals(seed, c, w2(1), rng.TAG_NOISE, P)[to_internal]
             ch.step(idx, noise)
         tensor_close(th[c], ch.theta, "theta (device RNG)", rtol=5e-5)
 
