@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <dlfcn.h>
@@ -16,6 +17,7 @@
 #include "common.cuh"
 #include "small_models.cuh"
 #include "logistic.cuh"
+#include "logistic_staged.cuh"
 #include "softmax_net.cuh"
 
 using namespace sgm;
@@ -392,7 +394,28 @@ static int launch_logistic_fullgrad_gv(sgm_handle* h, int64_t row0, int64_t row1
         return fail(SGM_EINVAL, "logistic: no kernel for ld = %d", h->ld);                     \
     } while (0)
 
+// short rows: whole minibatch staged in shared memory by TMA bulk copies (logistic_staged.cuh)
+static bool logistic_use_staged(const sgm_handle* h, const ChainArgs& a) {
+    const char* force = getenv("SGM_LOGISTIC_KERNEL");
+    if (force && !strcmp(force, "generic")) return false;
+    return h->ld <= 128 && a.n <= 4 * LS_THREADS && ls_smem_bytes(h->ld, a.n) <= 227 * 1024;
+}
+
+static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
+    const size_t smem = ls_smem_bytes(h->ld, a.n);
+    CU(cudaFuncSetAttribute(logistic_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0, per_sm = 1;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, logistic_staged_kernel, LS_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = a.C < sms * per_sm ? a.C : sms * per_sm;
+    logistic_staged_kernel<<<grid, LS_THREADS, smem, h->stream>>>(a);
+    CU(cudaGetLastError());
+    return SGM_OK;
+}
+
 static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
+    if (logistic_use_staged(h, a)) return launch_logistic_staged(h, a);
     LogiShape s;
     if (!logi_shape(h->ld, &s)) return fail(SGM_EINVAL, "logistic: d = %d too large", h->d);
     const int threads = logi_threads(h, s);

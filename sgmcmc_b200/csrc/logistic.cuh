@@ -24,7 +24,10 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret
 __device__ __forceinline__ float dot4(const float4 a, const float4 b) {
     return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
 }
-__device__ __forceinline__ float& comp4(float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float get4(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void set4(float4& v, int k, float s) {
+    v.x = (k == 0) ? s : v.x; v.y = (k == 1) ? s : v.y; v.z = (k == 2) ? s : v.z; v.w = (k == 3) ? s : v.w;
+}
 __device__ __forceinline__ float signf(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
 template <int G>
@@ -100,7 +103,7 @@ __device__ __forceinline__ void logi_pass(const ChainArgs& a, const LogiSmem& sm
         if (lg == lg_t) {
 #pragma unroll
             for (int v = 0; v < V; ++v)
-                if (v == v_t) { y = comp4(x[v], ct); comp4(x[v], ct) = 0.f; }
+                if (v == v_t) { y = get4(x[v], ct); set4(x[v], ct, 0.f); }
         }
         float coef;
         if (pass == PASS_BETA) {
@@ -131,7 +134,7 @@ __device__ __forceinline__ void logi_pass(const ChainArgs& a, const LogiSmem& sm
             if (lg == lg_t) {
 #pragma unroll
                 for (int v = 0; v < V; ++v)
-                    if (v == v_t) comp4(x[v], ct) = 1.0f;   // the bias "feature"
+                    if (v == v_t) set4(x[v], ct, 1.0f);   // the bias "feature"
             }
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(512) logistic_fullgrad_kernel(const float* __r
         if (lg == lg_t) {
 #pragma unroll
             for (int v = 0; v < V; ++v)
-                if (v == v_t) { y = comp4(x[v], ct); comp4(x[v], ct) = 0.f; }
+                if (v == v_t) { y = get4(x[v], ct); set4(x[v], ct, 0.f); }
         }
         y = __shfl_sync(0xffffffffu, y, lg_t, G);
         float dz = 0.f;
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(512) logistic_fullgrad_kernel(const float* __r
         if (lg == lg_t) {
 #pragma unroll
             for (int v = 0; v < V; ++v)
-                if (v == v_t) comp4(x[v], ct) = 1.0f;
+                if (v == v_t) set4(x[v], ct, 1.0f);
         }
 #pragma unroll
         for (int v = 0; v < V; ++v) {
