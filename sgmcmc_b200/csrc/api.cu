@@ -119,6 +119,7 @@ struct sgm_handle {
     float fullgrad_ms = 0; int64_t fullgrad_bytes = 0;
     uint64_t step = 0, check_ctr = 0;
     bool inited = false;
+    bool rhat_cached = false;   // logistic *cv, shared mode: y - s(x.beta_hat) stored in the rows' spare slot
     ChainArgs base;  // template of kernel arguments
     SoftmaxNetWork* nn = nullptr;
     // comm
@@ -398,20 +399,28 @@ static int launch_logistic_fullgrad_gv(sgm_handle* h, int64_t row0, int64_t row1
 static bool logistic_use_staged(const sgm_handle* h, const ChainArgs& a) {
     const char* force = getenv("SGM_LOGISTIC_KERNEL");
     if (force && !strcmp(force, "generic")) return false;
-    return h->ld <= 128 && a.n <= 4 * LS_THREADS && ls_smem_bytes(h->ld, a.n) <= 227 * 1024;
+    return h->ld <= 128 && a.n <= LS_MAX_R * LS_THREADS && ls_smem_bytes(h->ld, a.n) <= 227 * 1024;
+}
+
+template <bool HAT_DOT>
+static int launch_logistic_staged_t(sgm_handle* h, const ChainArgs& a) {
+    auto k = logistic_staged_kernel<HAT_DOT>;
+    const size_t smem = ls_smem_bytes(h->ld, a.n);
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0, per_sm = 1;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LS_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = a.C < sms * per_sm ? a.C : sms * per_sm;
+    k<<<grid, LS_THREADS, smem, h->stream>>>(a);
+    CU(cudaGetLastError());
+    return SGM_OK;
 }
 
 static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
-    const size_t smem = ls_smem_bytes(h->ld, a.n);
-    CU(cudaFuncSetAttribute(logistic_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int sms = 0, per_sm = 1;
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, logistic_staged_kernel, LS_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int grid = a.C < sms * per_sm ? a.C : sms * per_sm;
-    logistic_staged_kernel<<<grid, LS_THREADS, smem, h->stream>>>(a);
-    CU(cudaGetLastError());
-    return SGM_OK;
+    // control variates need x.beta_hat per row unless the residual at the (shared) mode is cached in the rows
+    if (a.cv && !h->rhat_cached) return launch_logistic_staged_t<true>(h, a);
+    return launch_logistic_staged_t<false>(h, a);
 }
 
 static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
@@ -846,6 +855,14 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
         }
         if (int rc = full_gradient(h)) return rc;
         h->base.hat_stride = (M == 1 && h->C > 1) ? 0 : h->Pst;
+        // one mode for every chain: cache the per-datum residual at the mode next to y (logistic_staged.cuh)
+        h->rhat_cached = false;
+        if (h->model == SGM_MODEL_LOGISTIC && M == 1 && (h->d & 3) != 3 && logistic_use_staged(h, h->base)) {
+            logistic_cache_rhat_kernel<<<(unsigned)cdiv(h->N * 32, 256), 256, 0, h->stream>>>(h->X, h->N, h->ld, h->d, h->theta_hat);
+            CU(cudaGetLastError());
+            h->rhat_cached = true;
+            h->last_launches += 1;
+        }
     }
     h->inited = true;
     h->step = 0;

@@ -45,13 +45,25 @@ def draw_inputs(rs, chain: OS.Chain, N, n, C):
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("cv", [False, True])
 def test_deterministic_steps_match_oracle(lib, case_name, algo, cv):
+    _deterministic_steps(case_name, algo, cv, shared=False)
+
+
+@pytest.mark.parametrize("case_name", ["gauss2d", "mixture", "logistic5", "logistic54", "logistic130", "softmaxnet_small"])
+@pytest.mark.parametrize("algo", ALGOS)
+def test_deterministic_steps_shared_mode(lib, case_name, algo):
+    """*cv with ONE mode shared by all chains (SGM_FLAG_SHARED_MODE): the logistic short-row kernel then
+    reads the residual at the mode from the rows (cached once) instead of recomputing x.beta_hat."""
+    _deterministic_steps(case_name, algo, True, shared=True)
+
+
+def _deterministic_steps(case_name, algo, cv, shared):
     from sgmcmc_b200 import validation as V
     case = make_case(case_name)
     C, steps, n_opt = 3, 4, 25
     if case_name == "softmaxnet":  # full 784-100-10: keep the CPU oracle's share of the test short
         C, steps, n_opt = 2, 2, 3
     rs = np.random.RandomState(5)
-    dev = device_setup(case, algo, cv, n_chains=C, n_iters_opt=n_opt)
+    dev = device_setup(case, algo, cv, n_chains=C, n_iters_opt=n_opt, sharedMode=shared)
     chains32 = [oracle_chain(case, algo, cv, np.float32, graph=True) for _ in range(C)]
     chains64 = [oracle_chain(case, algo, cv, np.float64) for _ in range(C)]
     P = sum(int(np.size(v)) for v in case["params"].values())
@@ -63,7 +75,7 @@ def test_deterministic_steps_match_oracle(lib, case_name, algo, cv):
             if algo != "sgld":
                 ch.init_momentum(mom_noise[c])
             if cv:
-                ch.find_mode(opt_idx[c])
+                ch.find_mode(opt_idx[0 if shared else c])
     if cv:
         th_hat, g_hat = V.getMode(dev)
         for c in range(C):
