@@ -402,9 +402,9 @@ static bool logistic_use_staged(const sgm_handle* h, const ChainArgs& a) {
     return h->ld <= 128 && a.n <= LS_MAX_R * LS_THREADS && ls_smem_bytes(h->ld, a.n) <= 227 * 1024;
 }
 
-template <bool HAT_DOT>
+template <bool HAT_DOT, int R>
 static int launch_logistic_staged_t(sgm_handle* h, const ChainArgs& a) {
-    auto k = logistic_staged_kernel<HAT_DOT>;
+    auto k = logistic_staged_kernel<HAT_DOT, R>;
     const size_t smem = ls_smem_bytes(h->ld, a.n);
     CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 0, per_sm = 1;
@@ -419,8 +419,20 @@ static int launch_logistic_staged_t(sgm_handle* h, const ChainArgs& a) {
 
 static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
     // control variates need x.beta_hat per row unless the residual at the (shared) mode is cached in the rows
-    if (a.cv && !h->rhat_cached) return launch_logistic_staged_t<true>(h, a);
-    return launch_logistic_staged_t<false>(h, a);
+    const bool hat_dot = a.cv && !h->rhat_cached;
+    { const char* g = getenv("SGM_GATHER"); const_cast<ChainArgs&>(a).gather_tma = !g ? 1 : (!strcmp(g, "ldgsts") ? 0 : (!strcmp(g, "mixed") ? 2 : 1)); }   // default: one TMA bulk copy per row
+    const int R = (a.n + LS_THREADS - 1) / LS_THREADS;
+    switch ((hat_dot ? 10 : 0) + R) {
+        case 1: return launch_logistic_staged_t<false, 1>(h, a);
+        case 2: return launch_logistic_staged_t<false, 2>(h, a);
+        case 3: return launch_logistic_staged_t<false, 3>(h, a);
+        case 4: return launch_logistic_staged_t<false, 4>(h, a);
+        case 11: return launch_logistic_staged_t<true, 1>(h, a);
+        case 12: return launch_logistic_staged_t<true, 2>(h, a);
+        case 13: return launch_logistic_staged_t<true, 3>(h, a);
+        case 14: return launch_logistic_staged_t<true, 4>(h, a);
+    }
+    return fail(SGM_EINVAL, "logistic staged kernel: minibatch %d too large", a.n);
 }
 
 static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
@@ -940,6 +952,17 @@ extern "C" int sgm_run(sgm_handle* h, int64_t n_iters, int store) {
 }
 
 extern "C" int sgm_step(sgm_handle* h) { return sgm_run(h, 1, 0); }
+
+// debug: per-phase clock64() totals of thread 0 of every CTA (see LS_TICK in logistic_staged.cuh); n slots of uint64
+extern "C" int sgm_debug_phase_cycles(sgm_handle* h, int enable, unsigned long long* out, int n) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    if (int rc = set_device(h)) return rc;
+    if (enable && !h->base.prof) { CU(cudaMalloc(&h->base.prof, 64 * sizeof(unsigned long long))); }
+    if (h->base.prof && out) { CU(cudaMemcpy(out, h->base.prof, (n > 64 ? 64 : n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost)); }
+    if (h->base.prof) CU(cudaMemset(h->base.prof, 0, 64 * sizeof(unsigned long long)));
+    if (!enable && h->base.prof) { cudaFree(h->base.prof); h->base.prof = nullptr; }
+    return SGM_OK;
+}
 
 // ------------------------------------------------------------------------------------
 // results

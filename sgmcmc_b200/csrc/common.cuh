@@ -72,6 +72,9 @@ struct ChainArgs {
     int64_t store_pos;
     // divergence flag (set to 1 if any state element is non-finite)
     int* diverged;
+    // optional phase timing (debug): thread 0 of every CTA adds clock64() deltas, [phase] slots
+    unsigned long long* prof;
+    int gather_tma;   // logistic short-row kernel: 1 = one TMA bulk copy per row, 0 = 16-byte cp.async
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

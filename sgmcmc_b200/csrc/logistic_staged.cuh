@@ -54,7 +54,7 @@ static inline size_t ls_smem_bytes(int ld, int n) {
 }
 
 // scratch slots
-constexpr int LS_BIAS = 40, LS_BIAS_HAT = 41, LS_UBIAS = 42, LS_PERM = 48;   // [48..54] = Perm words
+constexpr int LS_BIAS = 40, LS_BIAS_HAT = 41, LS_UBIAS = 42, LS_PERM = 48;   // [48..51] and [56..59]: permutation keys of sub-steps s with s & 1 = 0 / 1
 
 struct LogiStagedSmem {
     float* rows;     // [n][4*S]
@@ -88,7 +88,44 @@ __global__ void logistic_cache_rhat_kernel(float* __restrict__ X, int64_t N, int
 }
 
 // HAT_DOT: control variates whose residual at the mode is NOT cached in the rows (per-chain modes)
-template <bool HAT_DOT>
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared::cta, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+#define LS_TICK(slot)                                                                      \
+    if (a.prof && tid == 0) { const long long t_ = clock64(); atomicAdd(a.prof + (slot), (unsigned long long)(t_ - t_prev)); t_prev = t_; }
+
+// explicit shared-space accessors: generic pointers into shared memory cost an address-window conversion per
+// access and keep ptxas from batching the loads (profiles/r01_c3_staged_v4.txt)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+// HAT_DOT: control variates whose residual at the mode is NOT cached in the rows (per-chain modes)
+// R: rows per lane = ceil(n / 256)
+template <bool HAT_DOT, int R>
 __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const ChainArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -96,17 +133,30 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
     const int Q = ld >> 2, S = ls_row_stride4(ld);
     const bool paired = (S & 1) == 0;      // unpadded rows: skewed lanes
     const int qt = d >> 2, ct = d & 3;     // float4 / slot holding y (and, for the parameters, the bias)
-    const int R = (n + LS_THREADS - 1) / LS_THREADS;
     const float SQRT_HALF = 0.70710678118654752440f;
     LogiStagedSmem sm;
     sm.rows = reinterpret_cast<float*>(smem_raw);
     sm.th = sm.rows + (size_t)n * 4 * S; sm.hat = sm.th + ld; sm.grad = sm.hat + ld; sm.coef = sm.grad + ld; sm.scratch = sm.coef + n;
-    const float4* rows4 = reinterpret_cast<const float4*>(sm.rows);
+    const uint32_t rows_s = smem_u32(sm.rows), th_s = smem_u32(sm.th), hat_s = smem_u32(sm.hat), coef_s = smem_u32(sm.coef);
     const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
+    const bool noisy = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT);
     const bool cached = a.cv && !HAT_DOT;   // r_hat rides in the row
     const int e = tid;                      // the parameter element this thread owns in the update (e <= d)
     const bool owner = e <= d;
     const int t_own = (e == d) ? 0 : 1, f_own = (e == d) ? 0 : e + 1;
+    // gather mapping: one LDGSTS instruction covers rpi whole rows (lane = row-in-instruction * Q + float4 column)
+    const int rpi = 32 / Q, g_row = lane / Q, g_q = lane - g_row * Q;
+    const bool g_live = g_row < rpi;
+    // phase-1 skew (unpadded rows only): row quads 4..7 (mod 8) start one float4 later, so the 8 lanes of a
+    // shared-memory phase hit 8 different 16-byte bank groups although the row stride is even
+    const int skew = paired ? ((tid >> 2) & 1) : 0;
+    const uint32_t bar_s = smem_u32(sm.scratch + 16) + (uint32_t)warp * 8u;   // one mbarrier per warp (TMA gather mode)
+    uint32_t bar_uses = 0;
+    if (a.gather_tma) {
+        if (lane == 0) mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    long long t_prev = clock64();
 
     for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
         __syncthreads();
@@ -122,6 +172,34 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
         if (e == d) { sm.scratch[LS_BIAS] = th_e; sm.scratch[LS_BIAS_HAT] = hat_e; }
         float zeta_bias = a.thermo[c * MAX_TENSORS + 0], zeta_beta = a.thermo[c * MAX_TENSORS + 1];
         bool bad = false;
+        // Row indices are always computed one sub-step ahead (they do not depend on theta): the first ones here,
+        // later ones while the previous minibatch is in flight.  Sub-step s of this launch = (it, l) = (s / L, s % L);
+        // its permutation keys are published by the last warp in scratch slot s & 1, two sub-steps ahead.
+        const int n_sub = a.iters * a.L;
+        auto keys_of = [&](int s_) -> Perm {
+            return make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2_of(a.step0 + (uint64_t)(s_ / a.L), a.L, s_ % a.L + 1),
+                             a.index_tag, a.k0, a.k1);
+        };
+        auto rows_of = [&](const Perm& p_, int s_, uint32_t (&out)[R]) {
+            const int32_t* idx_ = a.det ? a.idx + ((size_t)c * n_sub + s_) * n : nullptr;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int j = r * LS_THREADS + tid;
+                out[r] = 0;
+                if (j < n && s_ < n_sub) out[r] = idx_ ? (uint32_t)idx_[j] : perm_at(p_, (uint32_t)j);
+            }
+        };
+        uint32_t next_row[R];
+        {
+            Perm p0;
+            if (!a.det) p0 = keys_of(0);
+            rows_of(p0, 0, next_row);
+            if (!a.det && warp == LS_WARPS - 1) {
+                const Perm p1 = keys_of(1);
+                if (lane < 4) reinterpret_cast<uint32_t*>(sm.scratch + LS_PERM + 8)[lane] = p1.key[lane];
+            }
+        }
+        int s_cur = 0;
 
         for (int it = 0; it < a.iters; ++it) {
             const uint64_t step = a.step0 + (uint64_t)it;
@@ -132,138 +210,169 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
             if (a.algo == ALGO_SGHMC && owner) mo_e = 0.5f * (a.tc.sqrt_2eps[t_own] * noise_own(0));   // refresh, R/dynamics.R:62
             for (int l = 0; l < a.L; ++l) {
                 const int sub = l + 1;
-                const int32_t* idx = a.det ? a.idx + (((size_t)c * a.iters + it) * a.L + l) * n : nullptr;
-                // the permutation keys cost one Philox call: warp 0 computes, everybody reads
-                if (!a.det && warp == 0) {
-                    const Perm p = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
-                    if (lane < 4) reinterpret_cast<uint32_t*>(sm.scratch + LS_PERM)[lane] = p.key[lane];
-                }
+                LS_TICK(0)   // store / loop overhead
                 __syncthreads();   // previous minibatch fully consumed; th/hat/bias/keys published
-                Perm perm;
-                perm.N = a.N; perm.mask = (a.perm_bits >= 32) ? 0xFFFFFFFFu : ((1u << a.perm_bits) - 1u);
-                perm.shift = a.perm_bits / 2 > 0 ? a.perm_bits / 2 : 1;
+                LS_TICK(1)   // sync before gather
+                // ---- gather: each warp fetches the rows its lanes own (R x 32), everything in flight at once.
+                // gather_tma: 1 = every round by TMA bulk copies, 0 = every round by 16-byte cp.async,
+                //             2 = even rounds TMA / odd rounds cp.async (both engines busy at the same time)
+                auto via_tma = [&](int r) -> bool { return a.gather_tma == 1 || (a.gather_tma == 2 && (r & 1) == 0); };
+                int tma_rows = 0;
+                if (a.gather_tma) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < 4; ++k) perm.key[k] = reinterpret_cast<const uint32_t*>(sm.scratch + LS_PERM)[k];
-                // ---- gather: each warp fetches the rows its lanes own (R x 32), everything in flight at once
-                const int sub16 = lane & 1, rl = lane >> 1;
-#pragma unroll 1
+                    for (int r = 0; r < R; ++r)
+                        if (via_tma(r)) { int cnt = n - (r * LS_THREADS + warp * 32); tma_rows += cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt); }
+                    if (lane == 0 && tma_rows > 0) mbar_expect_tx(bar_s, (uint32_t)tma_rows * (uint32_t)ld * 4u);
+                    __syncwarp();
+                }
+#pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int j = r * LS_THREADS + tid;
-                    const int j0 = r * LS_THREADS + warp * 32;
-                    uint32_t my_row = 0;
-                    if (j < n) my_row = idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int jr = h * 16 + rl;
-                        const uint32_t row = __shfl_sync(0xffffffffu, my_row, jr);
-                        if (j0 + jr < n) {
-                            const float* src = a.X + ((size_t)row * ld + 4 * sub16);
-                            uint32_t dst = smem_u32(sm.rows) + (uint32_t)((j0 + jr) * S + sub16) * 16u;
-#pragma unroll 2
-                            for (int q = sub16; q < Q; q += 2) {
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                                src += 8; dst += 32u;
+                    if (via_tma(r)) {
+                        if (j < n) bulk_g2s(rows_s + (uint32_t)(j * S) * 16u, a.X + (size_t)next_row[r] * ld, (uint32_t)ld * 4u, bar_s);
+                    } else {
+                        const int j0 = r * LS_THREADS + warp * 32;
+                        const uint32_t my_row = next_row[r];
+                        const uint32_t dst0 = rows_s + (uint32_t)((j0 + g_row) * S + g_q) * 16u;
+                        for (int i = 0; i * rpi < 32; ++i) {
+                            const int jr = i * rpi + g_row;
+                            const uint32_t row = __shfl_sync(0xffffffffu, my_row, jr & 31);
+                            if (g_live && jr < 32 && j0 + jr < n) {
+                                const float* src = a.X + ((size_t)row * ld + 4 * g_q);
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(i * rpi * S) * 16u), "l"(src) : "memory");
                             }
                         }
                     }
                 }
                 cp_async_commit();
+                LS_TICK(2)   // index computation + issue of the copies
+                // ---- while the rows are in flight: this sub-step's noise and the next sub-step's permutation keys
+                float z_own = 0.f;
+                if (owner && noisy) z_own = noise_own(sub);
+                if (!a.det && warp == LS_WARPS - 1 && s_cur + 2 < n_sub) {
+                    const Perm p2 = keys_of(s_cur + 2);
+                    if (lane < 4) reinterpret_cast<uint32_t*>(sm.scratch + LS_PERM + 8 * (s_cur & 1))[lane] = p2.key[lane];
+                }
+                {
+                    Perm pn;
+                    pn.N = a.N; pn.mask = (a.perm_bits >= 32) ? 0xFFFFFFFFu : ((1u << a.perm_bits) - 1u);
+                    pn.shift = a.perm_bits / 2 > 0 ? a.perm_bits / 2 : 1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pn.key[k] = reinterpret_cast<const uint32_t*>(sm.scratch + LS_PERM + 8 * ((s_cur + 1) & 1))[k];
+                    rows_of(pn, s_cur + 1, next_row);
+                }
+                ++s_cur;
+                if (tma_rows > 0) { mbar_wait(bar_s, bar_uses & 1u); ++bar_uses; }
                 cp_async_wait_all();
                 __syncwarp();
-                // ---- phase 1: lane-per-row dots, R rows per lane walked together (one beta load serves R rows)
-                const float4* t4 = reinterpret_cast<const float4*>(sm.th);
-                const float4* h4 = reinterpret_cast<const float4*>(sm.hat);
-                // skew (unpadded rows only): row quads 4..7 (mod 8) start one float4 later, so the 8 lanes of a
-                // shared-memory phase hit 8 different 16-byte bank groups although the row stride is even
-                const int skew = paired ? ((tid >> 2) & 1) : 0;
-                float dz[LS_MAX_R], dh[LS_MAX_R];
-                const float4* xr[LS_MAX_R];
+                LS_TICK(3)   // wait for the rows
+                // ---- phase 1: lane-per-row dots, R rows per lane walked together, two float4 columns per iteration
+                uint32_t xa[R];
+                float dz0[R], dz1[R], dh0[R], dh1[R];
 #pragma unroll
-                for (int r = 0; r < LS_MAX_R; ++r) {
-                    dz[r] = 0.f; dh[r] = 0.f;
+                for (int r = 0; r < R; ++r) {
                     const int j = r * LS_THREADS + tid;
-                    xr[r] = rows4 + (size_t)((r < R && j < n) ? j : 0) * S;   // out-of-range lanes recompute row 0 (discarded)
+                    xa[r] = rows_s + (uint32_t)((j < n ? j : 0) * S) * 16u;   // out-of-range lanes recompute row 0 (discarded)
+                    dz0[r] = dz1[r] = dh0[r] = dh1[r] = 0.f;
                 }
-                for (int k = 0; k < Q; ++k) {
-                    int q = k + skew; q = (q >= Q) ? q - Q : q;
-                    const float4 tv = t4[q];
-                    float4 hv;
-                    if (HAT_DOT) hv = h4[q];
+                for (int k = 0; k + 1 < Q; k += 2) {
+                    const int q0 = k + skew;
+                    const int q1 = (q0 + 1 == Q) ? 0 : q0 + 1;
+                    const float4 t0 = lds128(th_s + q0 * 16), t1 = lds128(th_s + q1 * 16);
+                    float4 h0, h1;
+                    if (HAT_DOT) { h0 = lds128(hat_s + q0 * 16); h1 = lds128(hat_s + q1 * 16); }
+                    float4 x0[R], x1[R];
 #pragma unroll
-                    for (int r = 0; r < LS_MAX_R; ++r) {
-                        if (r < R) {
-                            const float4 x = xr[r][q];
-                            dz[r] = fdot4(x, tv, dz[r]);
-                            if (HAT_DOT) dh[r] = fdot4(x, hv, dh[r]);
-                        }
+                    for (int r = 0; r < R; ++r) { x0[r] = lds128(xa[r] + q0 * 16); x1[r] = lds128(xa[r] + q1 * 16); }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        dz0[r] = fdot4(x0[r], t0, dz0[r]); dz1[r] = fdot4(x1[r], t1, dz1[r]);
+                        if (HAT_DOT) { dh0[r] = fdot4(x0[r], h0, dh0[r]); dh1[r] = fdot4(x1[r], h1, dh1[r]); }
                     }
                 }
-                float yv[LS_MAX_R], rhat[LS_MAX_R];
+                if (Q & 1) {   // odd column count (padded stride, no skew): last column
+                    const int q0 = Q - 1;
+                    const float4 t0 = lds128(th_s + q0 * 16);
+                    float4 h0;
+                    if (HAT_DOT) h0 = lds128(hat_s + q0 * 16);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const float4 x0 = lds128(xa[r] + q0 * 16);
+                        dz0[r] = fdot4(x0, t0, dz0[r]);
+                        if (HAT_DOT) dh0[r] = fdot4(x0, h0, dh0[r]);
+                    }
+                }
+                float dz[R], yv[R], rhat[R];
                 const float bias_hat = sm.scratch[LS_BIAS_HAT];
 #pragma unroll
-                for (int r = 0; r < LS_MAX_R; ++r) {
-                    yv[r] = 0.f; rhat[r] = 0.f;
-                    if (r < R) {
-                        const float4 tail = xr[r][qt];
-                        yv[r] = get4(tail, ct);
-                        if (cached) rhat[r] = get4(tail, ct + 1);
-                        else if (HAT_DOT) rhat[r] = yv[r] - sigmoid_fast(bias_hat + dh[r]);
-                        if (cached) {
-                            // the cached residual sits in a slot where beta is zero-padded, so it never enters dz
-                        }
-                    }
+                for (int r = 0; r < R; ++r) {
+                    dz[r] = dz0[r] + dz1[r];
+                    const float4 tail = lds128(xa[r] + qt * 16);
+                    yv[r] = get4(tail, ct);
+                    rhat[r] = 0.f;
+                    if (cached) rhat[r] = get4(tail, ct + 1);   // sits where beta is zero-padded: never enters dz
+                    else if (HAT_DOT) rhat[r] = yv[r] - sigmoid_fast(bias_hat + (dh0[r] + dh1[r]));
                 }
+                LS_TICK(4)   // phase 1 dots
                 const int passes = seidel ? 2 : 1;
                 for (int pass = 0; pass < passes; ++pass) {
                     const float bias = sm.scratch[LS_BIAS];
                     float csum = 0.f;
 #pragma unroll
-                    for (int r = 0; r < LS_MAX_R; ++r) {
+                    for (int r = 0; r < R; ++r) {
                         const int j = r * LS_THREADS + tid;
-                        if (r < R && j < n) {
+                        if (j < n) {
                             const float rr = yv[r] - sigmoid_fast(bias + dz[r]);
                             const float cf = a.cv ? rr - rhat[r] : rr;
                             csum += cf;
-                            sm.coef[j] = cf;
+                            sts32(coef_s + j * 4, cf);
                         }
                     }
+                    LS_TICK(5)   // sigmoid + coef
                     const float cs_tot = ls_block_sum(csum, sm.scratch);   // = gradient sum of the bias; also publishes coef
+                    LS_TICK(6)   // block sum (barrier)
                     if (!(seidel && pass == 0)) {
-                        // ---- phase 2: column sums of c_i * x_i
-                        if (paired) {
-                            const int cpar = lane & 1;
-                            for (int q0 = 2 * warp; q0 < Q; q0 += 2 * LS_WARPS) {
-                                const float4* col = rows4 + q0 + cpar;
-                                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-                                for (int j = rl; j < n; j += 16) {
-                                    const float4 x = col[(size_t)j * S];
-                                    const float cf = sm.coef[j];
-                                    acc.x = fmaf(cf, x.x, acc.x); acc.y = fmaf(cf, x.y, acc.y); acc.z = fmaf(cf, x.z, acc.z); acc.w = fmaf(cf, x.w, acc.w);
-                                }
+                        // ---- phase 2: column sums of c_i * x_i (4 independent accumulators per lane)
+                        const int rstep = paired ? 16 : 32;                 // rows between a lane's consecutive rows
+                        const int rl = paired ? (lane >> 1) : lane;
+                        const int cpar = paired ? (lane & 1) : 0;
+                        const int cstep = paired ? 2 : 1;
+                        for (int q0 = cstep * warp; q0 < Q; q0 += cstep * LS_WARPS) {
+                            const uint32_t col = rows_s + (uint32_t)(q0 + cpar) * 16u;
+                            float4 acc[4];
 #pragma unroll
-                                for (int o = 2; o < 32; o <<= 1) {
-                                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                            for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            int j = rl;
+                            for (; j + 3 * rstep < n; j += 4 * rstep) {
+                                float4 x[4]; float cf[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) { x[u] = lds128(col + (uint32_t)((j + u * rstep) * S) * 16u); cf[u] = lds32(coef_s + (j + u * rstep) * 4); }
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    acc[u].x = fmaf(cf[u], x[u].x, acc[u].x); acc[u].y = fmaf(cf[u], x[u].y, acc[u].y);
+                                    acc[u].z = fmaf(cf[u], x[u].z, acc[u].z); acc[u].w = fmaf(cf[u], x[u].w, acc[u].w);
                                 }
-                                if (lane < 2) *reinterpret_cast<float4*>(sm.grad + 4 * (q0 + cpar)) = acc;
                             }
-                        } else {
-                            for (int q = warp; q < Q; q += LS_WARPS) {
-                                const float4* col = rows4 + q;
-                                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-                                for (int j = lane; j < n; j += 32) {
-                                    const float4 x = col[(size_t)j * S];
-                                    const float cf = sm.coef[j];
-                                    acc.x = fmaf(cf, x.x, acc.x); acc.y = fmaf(cf, x.y, acc.y); acc.z = fmaf(cf, x.z, acc.z); acc.w = fmaf(cf, x.w, acc.w);
-                                }
-                                acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
-                                if (lane == 0) *reinterpret_cast<float4*>(sm.grad + 4 * q) = acc;
+                            for (; j < n; j += rstep) {
+                                const float4 x = lds128(col + (uint32_t)(j * S) * 16u);
+                                const float cf = lds32(coef_s + j * 4);
+                                acc[0].x = fmaf(cf, x.x, acc[0].x); acc[0].y = fmaf(cf, x.y, acc[0].y);
+                                acc[0].z = fmaf(cf, x.z, acc[0].z); acc[0].w = fmaf(cf, x.w, acc[0].w);
                             }
+                            float4 t;
+                            t.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x); t.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+                            t.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z); t.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
+#pragma unroll
+                            for (int o = cstep; o < 32; o <<= 1) {
+                                t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+                                t.z += __shfl_xor_sync(0xffffffffu, t.z, o); t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
+                            }
+                            if (lane < cstep) *reinterpret_cast<float4*>(sm.grad + 4 * (q0 + cpar)) = t;
                         }
                         __syncthreads();
                     }
+                    LS_TICK(7)   // phase 2 column sums (+ barrier)
                     // ---- fused update: thread e owns element e; the y slot of grad is garbage, the bias uses cs_tot
                     float uu = 0.f;
                     if (owner && !(seidel && t_own != pass)) {
@@ -275,12 +384,12 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
                         }
                         const int t = t_own;
                         if (a.algo == ALGO_SGLD) {
-                            th_e = th_e + (a.tc.half_eps[t] * g + SQRT_HALF * (a.tc.sqrt_2eps[t] * noise_own(sub)));
+                            th_e = th_e + (a.tc.half_eps[t] * g + SQRT_HALF * (a.tc.sqrt_2eps[t] * z_own));
                         } else if (a.algo == ALGO_SGHMC) {
-                            mo_e += a.tc.eps[t] * g - a.tc.alpha[t] * mo_e + a.tc.sqrt_alpha[t] * (a.tc.sqrt_2eps[t] * noise_own(sub));
+                            mo_e += a.tc.eps[t] * g - a.tc.alpha[t] * mo_e + a.tc.sqrt_alpha[t] * (a.tc.sqrt_2eps[t] * z_own);
                             th_e = th_e + mo_e;
                         } else if (a.algo == ALGO_SGNHT) {
-                            mo_e += a.tc.eps[t] * g - mo_e * (t == 0 ? zeta_bias : zeta_beta) + a.tc.sqrt_a[t] * (a.tc.sqrt_2eps[t] * noise_own(sub));
+                            mo_e += a.tc.eps[t] * g - mo_e * (t == 0 ? zeta_bias : zeta_beta) + a.tc.sqrt_a[t] * (a.tc.sqrt_2eps[t] * z_own);
                             th_e = th_e + mo_e;
                             if (t == 1) uu = mo_e * mo_e;
                         } else if (a.algo == ALGO_OPT) {
@@ -298,7 +407,9 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
                         zeta_beta += tot / (float)d - a.tc.eps[1];
                         zeta_bias += ub * ub - a.tc.eps[0];
                     }
+                    LS_TICK(8)   // update
                     __syncthreads();
+                    LS_TICK(9)   // sync after update
                 }
             }
             if (owner) {
