@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <dlfcn.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/sgmcmc_b200.h"
@@ -119,6 +120,8 @@ struct sgm_handle {
     float fullgrad_ms = 0; int64_t fullgrad_bytes = 0;
     uint64_t step = 0, check_ctr = 0;
     bool inited = false;
+    CUtensorMap tmap;           // 2-D map of the dataset (box = one row) for TMA tile::gather4
+    bool tmap_ok = false;
     bool rhat_cached = false;   // logistic *cv, shared mode: y - s(x.beta_hat) stored in the rows' spare slot
     ChainArgs base;  // template of kernel arguments
     SoftmaxNetWork* nn = nullptr;
@@ -402,6 +405,24 @@ static bool logistic_use_staged(const sgm_handle* h, const ChainArgs& a) {
     return h->ld <= 128 && a.n <= LS_MAX_R * LS_THREADS && ls_smem_bytes(h->ld, a.n) <= 227 * 1024;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+static int make_row_tensor_map(sgm_handle* h) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { cudaGetLastError(); return -1; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)h->ld, (cuuint64_t)h->N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)h->ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)h->ld, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = ((EncodeFn)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->X, gdim, gstride, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS ? 0 : -1;
+}
+
 template <bool HAT_DOT, int R>
 static int launch_logistic_staged_t(sgm_handle* h, const ChainArgs& a) {
     auto k = logistic_staged_kernel<HAT_DOT, R>;
@@ -412,7 +433,7 @@ static int launch_logistic_staged_t(sgm_handle* h, const ChainArgs& a) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LS_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const int grid = a.C < sms * per_sm ? a.C : sms * per_sm;
-    k<<<grid, LS_THREADS, smem, h->stream>>>(a);
+    k<<<grid, LS_THREADS, smem, h->stream>>>(a, h->tmap);
     CU(cudaGetLastError());
     return SGM_OK;
 }
@@ -420,7 +441,12 @@ static int launch_logistic_staged_t(sgm_handle* h, const ChainArgs& a) {
 static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
     // control variates need x.beta_hat per row unless the residual at the (shared) mode is cached in the rows
     const bool hat_dot = a.cv && !h->rhat_cached;
-    { const char* g = getenv("SGM_GATHER"); const_cast<ChainArgs&>(a).gather_tma = !g ? 1 : (!strcmp(g, "ldgsts") ? 0 : (!strcmp(g, "mixed") ? 2 : 1)); }   // default: one TMA bulk copy per row
+    {   // gather engine: TMA tile::gather4 when the shared-memory rows are unpadded, else one TMA bulk copy per row
+        const char* g = getenv("SGM_GATHER");
+        int mode = (h->tmap_ok && (ls_row_stride4(h->ld) == h->ld / 4) && h->ld <= 256) ? 3 : 1;
+        if (g) mode = !strcmp(g, "ldgsts") ? 0 : (!strcmp(g, "mixed") ? 2 : (!strcmp(g, "bulk") ? 1 : mode));
+        const_cast<ChainArgs&>(a).gather_tma = mode;
+    }
     const int R = (a.n + LS_THREADS - 1) / LS_THREADS;
     switch ((hat_dot ? 10 : 0) + R) {
         case 1: return launch_logistic_staged_t<false, 1>(h, a);
@@ -673,6 +699,7 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
         int rc = softmax_net_create(&h->nn, h->d, hid, outc, h->n, h->C, h->device);
         if (rc != 0) return bail(fail(SGM_ECUDA, "softmax net workspace: %s", cudaGetErrorString((cudaError_t)rc)));
     }
+    if (h->model == SGM_MODEL_LOGISTIC && h->ld <= 128) h->tmap_ok = (make_row_tensor_map(h) == 0);
     // initial state: every chain starts at params (internal layout)
     {
         std::vector<int> flat_of, tensor_of;

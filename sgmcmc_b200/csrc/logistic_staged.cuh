@@ -29,6 +29,7 @@
 // Replaces the same reference code as logistic.cuh (dataFeed/dataSelect R/update.R:166-194,
 // tf$gradients R/setup.R:36-62, declareDynamics.* R/dynamics.R:7-120, sgmcmcStep.* R/update.R:40-81).
 #pragma once
+#include <cuda.h>   // CUtensorMap
 #include "common.cuh"
 #include "logistic.cuh"
 
@@ -106,6 +107,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// TMA tile::gather4: FOUR rows of a 2-D tensor (box = ld x 1) per instruction, landing contiguously in shared
+// memory (SASS: UTMALDG.2D.GATHER4).  Quarter the TMA requests and issue loops of one-bulk-copy-per-row.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+                 : "memory");
+}
+
 #define LS_TICK(slot)                                                                      \
     if (a.prof && tid == 0) { const long long t_ = clock64(); atomicAdd(a.prof + (slot), (unsigned long long)(t_ - t_prev)); t_prev = t_; }
 
@@ -126,7 +135,7 @@ __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st
 // HAT_DOT: control variates whose residual at the mode is NOT cached in the rows (per-chain modes)
 // R: rows per lane = ceil(n / 256)
 template <bool HAT_DOT, int R>
-__global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const ChainArgs a) {
+__global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const ChainArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = a.d, ld = a.ld, n = a.n;
@@ -215,8 +224,8 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
                 LS_TICK(1)   // sync before gather
                 // ---- gather: each warp fetches the rows its lanes own (R x 32), everything in flight at once.
                 // gather_tma: 1 = every round by TMA bulk copies, 0 = every round by 16-byte cp.async,
-                //             2 = even rounds TMA / odd rounds cp.async (both engines busy at the same time)
-                auto via_tma = [&](int r) -> bool { return a.gather_tma == 1 || (a.gather_tma == 2 && (r & 1) == 0); };
+                //             2 = even rounds TMA / odd rounds cp.async, 3 = TMA tile::gather4 (4 rows per request; unpadded rows)
+                auto via_tma = [&](int r) -> bool { return a.gather_tma == 1 || a.gather_tma == 3 || (a.gather_tma == 2 && (r & 1) == 0); };
                 int tma_rows = 0;
                 if (a.gather_tma) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -229,7 +238,17 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int j = r * LS_THREADS + tid;
-                    if (via_tma(r)) {
+                    if (a.gather_tma == 3) {
+                        // rows j..j+3 of a full group by one gather4 (issued by the lane with j % 4 == 0), leftovers singly
+                        const int r1 = __shfl_down_sync(0xffffffffu, (int)next_row[r], 1);
+                        const int r2 = __shfl_down_sync(0xffffffffu, (int)next_row[r], 2);
+                        const int r3 = __shfl_down_sync(0xffffffffu, (int)next_row[r], 3);
+                        if ((j | 3) < n) {
+                            if ((lane & 3) == 0) tma_gather4(rows_s + (uint32_t)(j * S) * 16u, &tmap, (int)next_row[r], r1, r2, r3, bar_s);
+                        } else if (j < n) {
+                            bulk_g2s(rows_s + (uint32_t)(j * S) * 16u, a.X + (size_t)next_row[r] * ld, (uint32_t)ld * 4u, bar_s);
+                        }
+                    } else if (via_tma(r)) {
                         if (j < n) bulk_g2s(rows_s + (uint32_t)(j * S) * 16u, a.X + (size_t)next_row[r] * ld, (uint32_t)ld * 4u, bar_s);
                     } else {
                         const int j0 = r * LS_THREADS + warp * 32;
