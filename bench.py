@@ -338,10 +338,13 @@ def run_ours(args, w):
         "gpu_launches": launches,
     }
     if w["cv"]:
+        if w["family"] == "logistic":   # steady-state figure: 20 launches back to back (the one inside initSess sits between launch gaps)
+            fg_ms, fg_bytes = V.benchFullGradient(sg, 20)
         line["cv_full_gradient"] = {"ms": fg_ms, "bytes": fg_bytes, "GBps": (fg_bytes / (fg_ms * 1e-3) / 1e9) if fg_ms > 0 else None,
                                     "frac_of_hbm_peak": (fg_bytes / (fg_ms * 1e-3) / 1e9 / peak) if fg_ms > 0 else None,
-                                    "rows_per_rank": fg_bytes // (4 * 55) if args.workload == "c3" else None,
-                                    "init_ms_total": init_ms}
+                                    "rows_per_rank": fg_bytes // (16 * (w["params"]["beta"].shape[0] // 4 + 1)) if w["family"] == "logistic" else None,
+                                    "init_ms_total": init_ms,
+                                    "note": "one mode (shared by all chains): HBM-bound stream, not a GEMM; bytes = rows x row stride"}
     if rank == 0 and world == 1 and not args.no_cpu:
         ips, note, fg, _ = cpu_proxy(w, args.cpu_budget, 1)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": 1, "kind": "port", "sample": note,

@@ -188,6 +188,11 @@ int32_t sgm_noise_len(const sgm_handle* h);
 int sgm_last_timing(const sgm_handle* h, float* kernel_ms, int32_t* launches);
 /* Device time of the last control-variate full-data gradient pass and the bytes it read. */
 int sgm_last_fullgrad_timing(const sgm_handle* h, float* kernel_ms, int64_t* bytes);
+/* Re-runs the full-data gradient kernel of an initialised logistic *cv handle `reps` times between two CUDA events
+ * (measurement only; sampler state is untouched). */
+int sgm_bench_full_gradient(sgm_handle* h, int reps, float* ms_per_rep, int64_t* bytes);
+/* Debug: per-phase clock64() totals of the logistic short-row kernel (thread 0 of every CTA). */
+int sgm_debug_phase_cycles(sgm_handle* h, int enable, unsigned long long* out, int n);
 /* Copies rows [row0, row0+rows) of the device dataset back as column-major doubles
  * (entry k of sgm_config.data); lets tests feed device-generated data to the oracle. */
 int sgm_copy_dataset(sgm_handle* h, int32_t entry, int64_t row0, int64_t rows, double* out);

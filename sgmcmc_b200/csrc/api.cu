@@ -19,6 +19,7 @@
 #include "small_models.cuh"
 #include "logistic.cuh"
 #include "logistic_staged.cuh"
+#include "logistic_fullgrad_stream.cuh"
 #include "softmax_net.cuh"
 
 using namespace sgm;
@@ -471,7 +472,47 @@ static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
     LOGI_DISPATCH(launch_logistic_gv, h, a, threads, smem);
 }
 
+template <bool LONG, int V>
+static int launch_fullgrad_stream_t(sgm_handle* h, int64_t row0, int64_t row1, const float* theta_hat) {
+    auto k = logistic_fullgrad_stream_kernel<LONG, V>;
+    const int tile_rows = LONG ? FG_LONG_ROWS : FG_SHORT_ROWS;
+    const size_t smem = fg_smem_bytes(h->ld, tile_rows);
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0, per_sm = 1;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FG_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_tiles = cdiv(row1 - row0, tile_rows);
+    const int grid = (int)(n_tiles < (int64_t)sms * per_sm ? n_tiles : (int64_t)sms * per_sm);
+    if (grid < 1) return SGM_OK;
+    k<<<grid, FG_THREADS, smem, h->stream>>>(h->X, h->ld, h->d, row0, row1, tile_rows, (int)n_tiles, theta_hat, h->gsum);
+    CU(cudaGetLastError());
+    return SGM_OK;
+}
+
+// one mode: streaming kernel (TMA bulk tile ring); per-chain modes: row-chunk x mode grid
 static int launch_logistic_fullgrad(sgm_handle* h, int64_t row0, int64_t row1, int M, const float* theta_hat) {
+    const char* force = getenv("SGM_FULLGRAD");
+    const int Q = h->ld / 4;
+    if (M == 1 && !(force && !strcmp(force, "generic")) && cdiv(row1 - row0, FG_SHORT_ROWS) < (1ll << 31)) {
+        if (h->ld <= 128) {
+            // lane-per-row needs conflict-free shared rows: odd float4 stride, or 2 (mod 4) with skewed lanes; <= 4 column slots per warp
+            if (((Q & 1) || (Q % 4 == 2)) && fg_smem_bytes(h->ld, FG_SHORT_ROWS) <= 113 * 1024)
+                return launch_fullgrad_stream_t<false, 1>(h, row0, row1, theta_hat);
+        } else if (fg_smem_bytes(h->ld, FG_LONG_ROWS) <= 113 * 1024) {
+            const int V = (Q + 31) / 32;
+            switch (V) {
+                case 2: return launch_fullgrad_stream_t<true, 2>(h, row0, row1, theta_hat);
+                case 3: return launch_fullgrad_stream_t<true, 3>(h, row0, row1, theta_hat);
+                case 4: return launch_fullgrad_stream_t<true, 4>(h, row0, row1, theta_hat);
+                case 5: return launch_fullgrad_stream_t<true, 5>(h, row0, row1, theta_hat);
+                case 6: return launch_fullgrad_stream_t<true, 6>(h, row0, row1, theta_hat);
+                case 7: return launch_fullgrad_stream_t<true, 7>(h, row0, row1, theta_hat);
+                case 8: return launch_fullgrad_stream_t<true, 8>(h, row0, row1, theta_hat);
+                case 9: return launch_fullgrad_stream_t<true, 9>(h, row0, row1, theta_hat);
+            }
+        }
+    }
     LOGI_DISPATCH(launch_logistic_fullgrad_gv, h, row0, row1, M, theta_hat);
 }
 
@@ -1173,6 +1214,28 @@ extern "C" int sgm_copy_dataset(sgm_handle* h, int32_t entry, int64_t row0, int6
     CU(cudaMemcpyAsync(out, stage, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(stage);
+    return SGM_OK;
+}
+
+// measurement: the full-data gradient kernel of a *cv handle, `reps` back-to-back launches between two CUDA events
+// (a single launch inside sgm_init is bracketed by launch gaps that matter for a 20-70 us kernel); state is untouched
+extern "C" int sgm_bench_full_gradient(sgm_handle* h, int reps, float* ms_per_rep, int64_t* bytes) {
+    if (!h || reps < 1) return fail(SGM_EINVAL, "bad argument");
+    if (!h->cv || !h->inited) return fail(SGM_ESTATE, "needs an initialised *cv sampler");
+    if (h->model != SGM_MODEL_LOGISTIC) return fail(SGM_EINVAL, "only the logistic family is instrumented");
+    if (int rc = set_device(h)) return rc;
+    const int M = hat_count(h);
+    const int64_t row0 = h->N * h->rank / h->world, row1 = h->N * (h->rank + 1) / h->world;
+    for (int warm = 0; warm < 2; ++warm) if (int rc = launch_logistic_fullgrad(h, row0, row1, M, h->theta_hat)) return rc;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    for (int r = 0; r < reps; ++r) if (int rc = launch_logistic_fullgrad(h, row0, row1, M, h->theta_hat)) return rc;
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (ms_per_rep) *ms_per_rep = ms / reps;
+    if (bytes) *bytes = (row1 - row0) * (int64_t)h->ld * 4;
+    CU(cudaMemsetAsync(h->gsum, 0, (size_t)M * h->Pst * sizeof(double), h->stream));
     return SGM_OK;
 }
 

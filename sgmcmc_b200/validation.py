@@ -102,3 +102,10 @@ def lastFullGradTiming(sgmcmc: Sgmcmc):
     ms, b = C.c_float(), C.c_int64()
     _lib.check(_lib.load().sgm_last_fullgrad_timing(sgmcmc.handle, C.byref(ms), C.byref(b)))
     return ms.value, b.value
+
+
+def benchFullGradient(sgmcmc: Sgmcmc, reps: int = 20):
+    """(ms per launch, bytes read) of the control-variate full-data gradient kernel, `reps` launches back to back."""
+    ms, b = C.c_float(), C.c_int64()
+    _lib.check(_lib.load().sgm_bench_full_gradient(sgmcmc.handle, reps, C.byref(ms), C.byref(b)))
+    return ms.value, b.value
