@@ -81,7 +81,7 @@ def workload(name: str, chains: int | None):
              "lambdaA": np.array(rs.gamma(1.0)), "lambdaB": np.array(rs.gamma(1.0)),
              "lambdaa": np.array(rs.gamma(1.0)), "lambdab": np.array(rs.gamma(1.0))}
         return dict(desc="nn vignette: SGHMC L=5, 784-100-10 softmax net, N=60000, n=100", algo="sghmc", cv=False, family="nn",
-                    data={"X": X, "y": Y}, params=p, stepsize=1e-6, n=100, chains=chains or 64, L=5, alpha=0.01,
+                    data={"X": X, "y": Y}, params=p, stepsize=1e-6, n=100, chains=chains or 148, L=5, alpha=0.01,
                     bytes_per_chain_iter=int(8.59e6), bound_note="per-chain weights (318 KB) stream from L2/HBM")
     raise SystemExit(f"unknown workload {name}")
 

@@ -43,10 +43,10 @@ __host__ __device__ __forceinline__ U4 philox4x32(uint32_t c0, uint32_t c1, uint
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
     const float u1 = ((float)(a >> 8) + 1.0f) * 5.9604644775390625e-8f;  // (0,1]
     const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;           // [0,1)
-    const float r = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    z0 = r * c; z1 = r * s;
+    // fast intrinsics: |error| <~ 1e-6 in a unit-variance variate (the noise is then scaled by sqrt(2 eps))
+    const float r = sqrtf(-2.0f * __logf(u1));
+    const float ang = 6.283185307179586f * u2 - (u2 >= 0.5f ? 6.283185307179586f : 0.f);   // in [-pi, pi)
+    z0 = r * __cosf(ang); z1 = r * __sinf(ang);
 }
 
 // N(0,1) for flat element e of stream (chain, word2, tag): Philox block e/4, lane e%4.

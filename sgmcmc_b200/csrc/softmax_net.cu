@@ -33,6 +33,12 @@ constexpr int NN_JT = 64;       // j tile of S5
 constexpr int NN_MAXH = 128;    // hidden width limit (lanes x 4)
 constexpr int NN_MAXO = 16;     // output width limit
 
+// optional phase timing (debug, ChainArgs::prof): thread 0 of every CTA adds clock64() deltas per stage
+__device__ unsigned long long* nn_prof = nullptr;
+__device__ long long nn_t_prev[1024];
+#define NN_TICK(slot)                                                                                   \
+    if (nn_prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(nn_prof + (slot), (unsigned long long)(t_ - nn_t_prev[blockIdx.x & 1023])); nn_t_prev[blockIdx.x & 1023] = t_; }
+
 struct NNDims {
     int din, dh, dop;  // dop = output width padded to a multiple of 4
     int dout;
@@ -100,37 +106,59 @@ __device__ void nn_load_small(const NNDims& dm, const NNSmem& sm, const float* _
     __syncthreads();
 }
 
-// S1: H[r][k] = softmax_k( sum_j X[row_r][j] B[j][k] + b[k] ) for the nb rows listed in sm.rows
+// S1: H[r][k] = softmax_k( sum_j X[row_r][j] B[j][k] + b[k] ) for the nb rows listed in sm.rows.
+// K is walked in chunks of NN_KC through a double-buffered pair of shared tiles: the next chunk's X rows are
+// prefetched into registers and its B rows by cp.async while the current chunk is multiplied (one barrier per chunk).
 __device__ void nn_stage1(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb,
                           const float* __restrict__ th) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncg = dm.dh >> 2;           // column groups of 4
     const bool live = lane < ncg;
-    float* Xt = sm.tile;                  // [NN_KC][NN_RB + 4]
-    float* Bt = sm.tile + NN_KC * (NN_RB + 4);   // [NN_KC][dh]
+    const int XT = NN_KC * (NN_RB + 4), BT = NN_KC * dm.dh, TILE = XT + BT;   // per buffer: Xt [NN_KC][NN_RB + 4], Bt [NN_KC][dh]
     const float* __restrict__ B = th + dm.offB;
+    const int xr = tid % NN_RB, xq = tid / NN_RB;      // this thread's X row and first float4 column (second: xq + 4)
+    const float* xrow = X + (size_t)sm.rows[xr < nb ? xr : 0] * ld;
     float acc[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
-    for (int j0 = 0; j0 < dm.din; j0 += NN_KC) {
+    float4 xv0, xv1;
+    auto fetch = [&](int j0, float* buf) {   // global -> registers (X) / cp.async -> shared (B)
         const int kc = (dm.din - j0 < NN_KC) ? dm.din - j0 : NN_KC;
-        __syncthreads();
-        // X tile, transposed: lanes walk rows so the shared-memory stores are conflict free
-        for (int t = tid; t < NN_RB * (NN_KC / 4); t += NN_THREADS) {
-            const int r = t % NN_RB, q = t / NN_RB;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nb && 4 * q < kc) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)sm.rows[r] * ld + j0 + 4 * q));
-            Xt[(4 * q + 0) * (NN_RB + 4) + r] = v.x; Xt[(4 * q + 1) * (NN_RB + 4) + r] = v.y;
-            Xt[(4 * q + 2) * (NN_RB + 4) + r] = v.z; Xt[(4 * q + 3) * (NN_RB + 4) + r] = v.w;
-        }
+        xv0 = (xr < nb && 4 * xq < kc) ? __ldg(reinterpret_cast<const float4*>(xrow + j0 + 4 * xq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv1 = (xr < nb && 4 * (xq + 4) < kc) ? __ldg(reinterpret_cast<const float4*>(xrow + j0 + 4 * (xq + 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* Bt = buf + XT;
         for (int t = tid; t < NN_KC * ncg; t += NN_THREADS) {
             const int jj = t / ncg, cg = t % ncg;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jj < kc) v = *reinterpret_cast<const float4*>(B + (size_t)(j0 + jj) * dm.dh + 4 * cg);
-            *reinterpret_cast<float4*>(Bt + jj * dm.dh + 4 * cg) = v;
+            if (jj < kc) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Bt + jj * dm.dh + 4 * cg);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(B + (size_t)(j0 + jj) * dm.dh + 4 * cg) : "memory");
+            } else {
+                *reinterpret_cast<float4*>(Bt + jj * dm.dh + 4 * cg) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto stash = [&](float* buf) {           // registers -> transposed shared X tile (lanes walk rows: conflict free)
+        float* Xt = buf;
+        Xt[(4 * xq + 0) * (NN_RB + 4) + xr] = xv0.x; Xt[(4 * xq + 1) * (NN_RB + 4) + xr] = xv0.y;
+        Xt[(4 * xq + 2) * (NN_RB + 4) + xr] = xv0.z; Xt[(4 * xq + 3) * (NN_RB + 4) + xr] = xv0.w;
+        Xt[(4 * xq + 16) * (NN_RB + 4) + xr] = xv1.x; Xt[(4 * xq + 17) * (NN_RB + 4) + xr] = xv1.y;
+        Xt[(4 * xq + 18) * (NN_RB + 4) + xr] = xv1.z; Xt[(4 * xq + 19) * (NN_RB + 4) + xr] = xv1.w;
+    };
+    __syncthreads();
+    fetch(0, sm.tile);
+    stash(sm.tile);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    int cur = 0;
+    for (int j0 = 0; j0 < dm.din; j0 += NN_KC, cur ^= 1) {
+        float* buf = sm.tile + cur * TILE;
+        float* nxt = sm.tile + (cur ^ 1) * TILE;
+        const bool more = j0 + NN_KC < dm.din;
+        if (more) fetch(j0 + NN_KC, nxt);
         if (live) {
+            const float* Xt = buf;
+            const float* Bt = buf + XT;
 #pragma unroll 4
             for (int jj = 0; jj < NN_KC; ++jj) {
                 const float4 bv = *reinterpret_cast<const float4*>(Bt + jj * dm.dh + 4 * lane);
@@ -139,11 +167,13 @@ __device__ void nn_stage1(const NNDims& dm, const NNSmem& sm, const float* __res
                 const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    acc[r][0] += xs[r] * bv.x; acc[r][1] += xs[r] * bv.y;
-                    acc[r][2] += xs[r] * bv.z; acc[r][3] += xs[r] * bv.w;
+                    acc[r][0] = fmaf(xs[r], bv.x, acc[r][0]); acc[r][1] = fmaf(xs[r], bv.y, acc[r][1]);
+                    acc[r][2] = fmaf(xs[r], bv.z, acc[r][2]); acc[r][3] = fmaf(xs[r], bv.w, acc[r][3]);
                 }
             }
         }
+        if (more) { stash(nxt); asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+        __syncthreads();
     }
     // bias + row softmax: a row's dh entries live in the lanes of one warp
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -262,23 +292,35 @@ __device__ void nn_stage4(const NNDims& dm, const NNSmem& sm, int nb, bool first
     __syncthreads();
 }
 
-// S5: GB[j][k] (+)= sum_r X[row_r][j] dZ1[r][k]
+// S5: GB[j][k] (+)= sum_r X[row_r][j] dZ1[r][k]; the X tiles (128 rows x 64 columns) are double-buffered by cp.async
 __device__ void nn_stage5(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb, bool first,
                           float* __restrict__ GB) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncg = dm.dh >> 2;
     const bool live = lane < ncg;
-    float* Xs = sm.tile;   // [NN_RB][NN_JT]
-    for (int j0 = 0; j0 < dm.din; j0 += NN_JT) {
+    const int TILE = NN_RB * NN_JT;
+    auto fetch = [&](int j0, float* Xs) {
         const int jt = (dm.din - j0 < NN_JT) ? dm.din - j0 : NN_JT;
-        __syncthreads();
         for (int t = tid; t < NN_RB * (NN_JT / 4); t += NN_THREADS) {
             const int r = t / (NN_JT / 4), q = t % (NN_JT / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nb && 4 * q < jt) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)sm.rows[r] * ld + j0 + 4 * q));
-            *reinterpret_cast<float4*>(Xs + r * NN_JT + 4 * q) = v;
+            if (r < nb && 4 * q < jt) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Xs + r * NN_JT + 4 * q);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(X + (size_t)sm.rows[r] * ld + j0 + 4 * q) : "memory");
+            } else {
+                *reinterpret_cast<float4*>(Xs + r * NN_JT + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    __syncthreads();
+    fetch(0, sm.tile);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    int cur = 0;
+    for (int j0 = 0; j0 < dm.din; j0 += NN_JT, cur ^= 1) {
+        const float* Xs = sm.tile + cur * TILE;
+        const bool more = j0 + NN_JT < dm.din;
+        if (more) fetch(j0 + NN_JT, sm.tile + (cur ^ 1) * TILE);
         float acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
@@ -290,8 +332,8 @@ __device__ void nn_stage5(const NNDims& dm, const NNSmem& sm, const float* __res
                 const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    acc[a][0] += xs[a] * dz.x; acc[a][1] += xs[a] * dz.y;
-                    acc[a][2] += xs[a] * dz.z; acc[a][3] += xs[a] * dz.w;
+                    acc[a][0] = fmaf(xs[a], dz.x, acc[a][0]); acc[a][1] = fmaf(xs[a], dz.y, acc[a][1]);
+                    acc[a][2] = fmaf(xs[a], dz.z, acc[a][2]); acc[a][3] = fmaf(xs[a], dz.w, acc[a][3]);
                 }
             }
 #pragma unroll
@@ -305,8 +347,9 @@ __device__ void nn_stage5(const NNDims& dm, const NNSmem& sm, const float* __res
                 }
             }
         }
+        if (more) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 enum : int { NEED_A = 1, NEED_B = 2, NEED_a = 4, NEED_b = 8, NEED_ALL = 15 };
@@ -329,12 +372,18 @@ __device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __rest
             for (int r = threadIdx.x; r < NN_RB; r += NN_THREADS)
                 sm.rows[r] = (r < nb) ? (idx ? idx[r0 + r] : (perm ? (int)perm_at(*perm, (uint32_t)(r0 + r)) : (int)(row0 + r0 + r))) : 0;
             __syncthreads();
+            NN_TICK(6)
             nn_stage1(dm, sm, X, ld, nb, th);
+            NN_TICK(0)
         }
         ll += nn_stage2(dm, sm, X, ld, nb, want_ll);
+        NN_TICK(1)
         if (need & (NEED_A | NEED_a)) nn_stage3(dm, sm, nb, first);
+        NN_TICK(2)
         if (need & (NEED_b | NEED_B)) nn_stage4(dm, sm, nb, first, Gout + dm.offb);
+        NN_TICK(3)
         if (need & NEED_B) nn_stage5(dm, sm, X, ld, nb, first, Gout + dm.offB);
+        NN_TICK(4)
     }
     if (need & (NEED_A | NEED_a)) {
         for (int i = threadIdx.x; i < dm.dh * dm.dout; i += NN_THREADS) {
@@ -379,16 +428,22 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
     int lo, hi;
     nn_tensor_range(dm, t, lo, hi);
     float ssq = 0.f, ssq_hat = 0.f;
+    int ssq_count = 0;
     if (t >= 4 && a.use_prior) {
         int wlo, whi;
         nn_tensor_range(dm, t - 4, wlo, whi);
+        ssq_count = whi - wlo;
         ssq = nn_sumsq(st.th + wlo, whi - wlo, sm.red);
         if (a.cv) ssq_hat = nn_sumsq(st.hat + wlo, whi - wlo, sm.red);
     }
     float uu = 0.f;
+    const bool noisy = a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT;
+    // hoisted uniforms: the precision this weight tensor's prior uses (t < 4) at theta and at the mode
+    const float lam_t = (t < 4 && a.use_prior) ? st.th[dm.offl + t] : 0.f;
+    const float lam_h = (t < 4 && a.use_prior && a.cv) ? st.hat[dm.offl + t] : 0.f;
+    const bool vec = (lo & 3) == 0;   // 16-byte aligned tensor: whole float4 groups are loaded before any store
     for (int e0 = lo + 4 * threadIdx.x; e0 < hi; e0 += 4 * NN_THREADS) {
         float z4[4] = {0.f, 0.f, 0.f, 0.f};
-        const bool noisy = a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT;
         if (noisy && !a.det) {
             // Philox block = 4 consecutive INTERNAL elements (tensor ranges need not be 4-aligned)
             float zz[4];
@@ -400,41 +455,71 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
                 for (int q = 0; q < 4; ++q) { const int ee = (e0 & 3) + q; z4[q] = ee < 4 ? zz[ee] : z2[ee - 4]; }
             }
         }
-        for (int q = 0; q < 4; ++q) {
-            const int e = e0 + q;
-            if (e >= hi) break;
-            const float th = st.th[e];
-            float g = (t < 4) ? a.corr * st.G[e] : 0.f;
-            if (a.use_prior) g += nn_prior_grad(dm, st.th, e, t, ssq);
+        const int cnt = (hi - e0 < 4) ? hi - e0 : 4;
+        // ---- all loads of the group first (theta / momentum / gradient buffers may alias for the compiler)
+        float th4[4] = {0.f, 0.f, 0.f, 0.f}, mo4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {0.f, 0.f, 0.f, 0.f};
+        float gh4[4] = {0.f, 0.f, 0.f, 0.f}, hat4[4] = {0.f, 0.f, 0.f, 0.f}, ghat4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec && cnt == 4) {
+            const float4 tv = *reinterpret_cast<const float4*>(st.th + e0), mv = *reinterpret_cast<const float4*>(st.mo + e0);
+            th4[0] = tv.x; th4[1] = tv.y; th4[2] = tv.z; th4[3] = tv.w; mo4[0] = mv.x; mo4[1] = mv.y; mo4[2] = mv.z; mo4[3] = mv.w;
+            if (t < 4) { const float4 gv = *reinterpret_cast<const float4*>(st.G + e0); g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w; }
             if (a.cv) {
-                float gh = (t < 4) ? a.corr * st.Ghat[e] : 0.f;
-                if (a.use_prior) gh += nn_prior_grad(dm, st.hat, e, t, ssq_hat);
-                g = (st.ghat[e] - gh) + g;   // R/setup.R:58
+                const float4 hv = *reinterpret_cast<const float4*>(st.hat + e0), qv = *reinterpret_cast<const float4*>(st.ghat + e0);
+                hat4[0] = hv.x; hat4[1] = hv.y; hat4[2] = hv.z; hat4[3] = hv.w; ghat4[0] = qv.x; ghat4[1] = qv.y; ghat4[2] = qv.z; ghat4[3] = qv.w;
+                if (t < 4) { const float4 gv = *reinterpret_cast<const float4*>(st.Ghat + e0); gh4[0] = gv.x; gh4[1] = gv.y; gh4[2] = gv.z; gh4[3] = gv.w; }
             }
-            float z = z4[q];
-            if (noisy && a.det)
-                z = a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + nn_flat_of_internal(dm, e)];
+        } else {
+            for (int q = 0; q < cnt; ++q) {
+                th4[q] = st.th[e0 + q]; mo4[q] = st.mo[e0 + q];
+                if (t < 4) g4[q] = st.G[e0 + q];
+                if (a.cv) { hat4[q] = st.hat[e0 + q]; ghat4[q] = st.ghat[e0 + q]; if (t < 4) gh4[q] = st.Ghat[e0 + q]; }
+            }
+        }
+        if (noisy && a.det)
+            for (int q = 0; q < cnt; ++q)
+                z4[q] = a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + nn_flat_of_internal(dm, e0 + q)];
+        // ---- arithmetic
+        for (int q = 0; q < cnt; ++q) {
+            const float th = th4[q];
+            float g = (t < 4) ? a.corr * g4[q] : 0.f;
+            if (a.use_prior) g += (t < 4) ? -lam_t * th : ((float)(ssq_count) / (2.0f * th) - 0.5f * ssq - 1.0f);
+            if (a.cv) {
+                float gh = (t < 4) ? a.corr * gh4[q] : 0.f;
+                if (a.use_prior) gh += (t < 4) ? -lam_h * hat4[q] : ((float)(ssq_count) / (2.0f * hat4[q]) - 0.5f * ssq_hat - 1.0f);
+                g = (ghat4[q] - gh) + g;   // R/setup.R:58
+            }
+            const float z = z4[q];
             if (a.algo == ALGO_SGLD) {
-                st.th[e] = th + (a.tc.half_eps[t] * g + SQRT_HALF * (a.tc.sqrt_2eps[t] * z));
+                th4[q] = th + (a.tc.half_eps[t] * g + SQRT_HALF * (a.tc.sqrt_2eps[t] * z));
             } else if (a.algo == ALGO_SGHMC) {
-                float nu = st.mo[e];
+                float nu = mo4[q];
                 nu += a.tc.eps[t] * g - a.tc.alpha[t] * nu + a.tc.sqrt_alpha[t] * (a.tc.sqrt_2eps[t] * z);
-                st.mo[e] = nu;
-                st.th[e] = th + nu;
+                mo4[q] = nu;
+                th4[q] = th + nu;
             } else if (a.algo == ALGO_SGNHT) {
-                float u = st.mo[e];
+                float u = mo4[q];
                 u += a.tc.eps[t] * g - u * st.zeta[t] + a.tc.sqrt_a[t] * (a.tc.sqrt_2eps[t] * z);
-                st.mo[e] = u;
+                mo4[q] = u;
                 uu += u * u;
             } else if (a.algo == ALGO_OPT) {
-                st.th[e] = th + a.opt_lr * g;
+                th4[q] = th + a.opt_lr * g;
             } else {
-                st.mo[e] = g;
+                mo4[q] = g;
             }
+        }
+        // ---- stores
+        const bool wr_th = a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_OPT;
+        const bool wr_mo = a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT || a.algo == ALGO_GRAD;
+        if (vec && cnt == 4) {
+            if (wr_th) *reinterpret_cast<float4*>(st.th + e0) = make_float4(th4[0], th4[1], th4[2], th4[3]);
+            if (wr_mo) *reinterpret_cast<float4*>(st.mo + e0) = make_float4(mo4[0], mo4[1], mo4[2], mo4[3]);
+        } else {
+            for (int q = 0; q < cnt; ++q) { if (wr_th) st.th[e0 + q] = th4[q]; if (wr_mo) st.mo[e0 + q] = mo4[q]; }
         }
     }
     if (uu_out) *uu_out = nn_block_sum(uu, sm.red);
     __syncthreads();
+    NN_TICK(5)
 }
 
 __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
@@ -445,7 +530,7 @@ __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
     sm.A = p; p += dm.dh * dm.dop;
     sm.a = p; p += NN_MAXO;
     sm.b = p; p += NN_MAXH;
-    const int t1 = NN_KC * (NN_RB + 4) + NN_KC * dm.dh, t5 = NN_RB * NN_JT;
+    const int t1 = 2 * (NN_KC * (NN_RB + 4) + NN_KC * dm.dh), t5 = 2 * NN_RB * NN_JT;   // double-buffered
     sm.tile = p; p += (t1 > t5 ? t1 : t5);
     sm.gb = p; p += NN_WARPS * dm.dh;
     sm.gA = p; p += dm.dh * dm.dop;
@@ -455,7 +540,7 @@ __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
 }
 
 static size_t nn_smem_bytes(const NNDims& dm) {
-    const int t1 = NN_KC * (NN_RB + 4) + NN_KC * dm.dh, t5 = NN_RB * NN_JT;
+    const int t1 = 2 * (NN_KC * (NN_RB + 4) + NN_KC * dm.dh), t5 = 2 * NN_RB * NN_JT;
     size_t f = (size_t)2 * NN_RB * dm.dh + NN_RB * dm.dop + dm.dh * dm.dop + NN_MAXO + NN_MAXH + (t1 > t5 ? t1 : t5) +
                NN_WARPS * dm.dh + dm.dh * dm.dop + NN_MAXO + 64 + NN_RB;
     return f * sizeof(float);
@@ -466,6 +551,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
     NNSmem sm;
     nn_carve(dm, smem_f, sm);
     const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
+    if (threadIdx.x == 0) nn_t_prev[blockIdx.x & 1023] = clock64();
     for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
         NNChainState st;
         st.th = a.theta + (size_t)c * a.Pst; st.mo = a.mom + (size_t)c * a.Pst;
@@ -542,6 +628,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
             }
             if (bad) *a.diverged = 1;
             __syncthreads();
+            NN_TICK(7)
         }
         if (threadIdx.x == 0)
             for (int t = 0; t < MAX_TENSORS; ++t) a.thermo[c * MAX_TENSORS + t] = st.zeta[t];
@@ -665,6 +752,7 @@ void softmax_net_tables(const SoftmaxNetWork* w, int* flat_of, int* tensor_of, i
 }
 
 int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t stream, int* launches) {
+    cudaMemcpyToSymbolAsync(nn_prof, &a.prof, sizeof(a.prof), 0, cudaMemcpyHostToDevice, stream);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
     const int grid = a.C < sms ? a.C : sms;
