@@ -66,10 +66,10 @@ def workload(name: str, chains: int | None):
                     bound_note="dataset is 130 MB (~L2 size): gathers are served partly from L2")
     if name == "c5":
         d = 1024
-        return dict(desc="scale-out: SGNHTCV logistic, d=1024, n=1024, 128 chains/GPU, N=1.25e7 rows/GPU generated on device",
+        return dict(desc="scale-out: SGNHTCV logistic, d=1024, n=1024, 148 chains/GPU (one per SM; 8 GPUs = 1184 >= the config's 1024), N=1.25e7 rows/GPU generated on device",
                     algo="sgnht", cv=True, family="logistic", data=None, synth=dict(rows=int(os.environ.get("SGM_C5_ROWS", 12500000)), dim=d, seed=13),
                     params={"bias": np.array(0.0), "beta": np.zeros((d, 1))}, stepsize=1e-8, opt_stepsize=1e-7,
-                    n_iters_opt=200, n=1024, chains=chains or 128, a=0.01,
+                    n_iters_opt=200, n=1024, chains=chains or 148, a=0.01,
                     bytes_per_chain_iter=1024 * 1025 * 4 + (4 * 1025 + 4) * 4 + 2 * 1025 * 4,
                     fullgrad_bytes=int(os.environ.get("SGM_C5_ROWS", 12500000)) * 1025 * 4,
                     bound_note="51 GB dataset >> L2: HBM-bound gather")

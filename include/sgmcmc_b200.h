@@ -161,6 +161,9 @@ int64_t sgm_chain_length(const sgm_handle* h);
  * (iters, dims_p...) double array; arrays are concatenated p-major inside c. */
 int sgm_copy_chain(sgm_handle* h, double* out);
 int sgm_reset_chain(sgm_handle* h);
+/* Optional page-locked host buffers for sgm_copy_chain / sgm_get_params outputs (faster device-to-host copies). */
+void* sgm_host_alloc(size_t bytes);
+void sgm_host_free(void* p);
 /* Pre-allocates device storage for n_iters more stored states (initStorage, R/storage.R:42-51). */
 int sgm_reserve_chain(sgm_handle* h, int64_t n_iters);
 

@@ -59,6 +59,8 @@ SYMBOLS = {
     "sgm_chain_length": (C.c_int64, [_H]),
     "sgm_copy_chain": (C.c_int, [_H, _PD]),
     "sgm_reset_chain": (C.c_int, [_H]),
+    "sgm_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "sgm_host_free": (None, [C.c_void_p]),
     "sgm_reserve_chain": (C.c_int, [_H, C.c_int64]),
     "sgm_est_logpost": (C.c_int, [_H, _PD]),
     "sgm_est_logpost_deterministic": (C.c_int, [_H, _PI, _PD]),

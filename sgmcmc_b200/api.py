@@ -264,17 +264,39 @@ def checkDivergence(sess: Session, sgmcmc: Sgmcmc, iter_: int, verbose: bool):
         _message(f"Iteration: {iter_}\t\tLog posterior estimate: {est[0] if est.size == 1 else est.mean()}")
 
 
+def _pinned_doubles(count: int) -> np.ndarray:
+    """A float64 array in page-locked host memory (freed when the array is collected)."""
+    import weakref
+    lib = _lib.load()
+    ptr = lib.sgm_host_alloc(count * 8)
+    if not ptr:
+        return np.empty(count, dtype=np.float64)
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(count,))
+    weakref.finalize(arr, lib.sgm_host_free, ptr)
+    return arr
+
+
 def getChains(sgmcmc: Sgmcmc) -> Dict[str, np.ndarray]:
     """One copy-out of the device-resident chain as the reference's storage list
-    (R/storage.R:42-51): per parameter an array (nIters, dims...); scalars give (nIters, 1)."""
+    (R/storage.R:42-51): per parameter an array (nIters, dims...); scalars give (nIters, 1).
+    The arrays are zero-copy views of the single buffer the library fills in R's column-major layout."""
     lib = _lib.load()
     iters = int(lib.sgm_chain_length(sgmcmc.handle))
-    buf = np.empty((sgmcmc.nChains, sgmcmc.P, iters), dtype=np.float64)
+    C_, P = sgmcmc.nChains, sgmcmc.P
+    buf = _pinned_doubles(C_ * P * iters)
     _lib.check(lib.sgm_copy_chain(sgmcmc.handle, _dptr(buf)))
-    flat = np.ascontiguousarray(buf.transpose(0, 2, 1))  # [C][iter][P]
-    if sgmcmc.nChains == 1:
-        return _split_flat(sgmcmc, flat[0], (iters,), scalar_as_1=True)
-    return _split_flat(sgmcmc, flat, (sgmcmc.nChains, iters), scalar_as_1=True)
+    out, o = {}, 0
+    for k, shp in sgmcmc.paramShapes.items():
+        shp = tuple(shp) if len(shp) else (1,)
+        sz = int(np.prod(shp))
+        # chain c, this parameter: a column-major (iters, dims...) block at offset (c * P + o) * iters
+        strides = [8]
+        for dim in (iters,) + shp[:-1]:
+            strides.append(strides[-1] * dim)
+        view = np.lib.stride_tricks.as_strided(buf[o * iters:], shape=(C_, iters) + shp, strides=(P * iters * 8,) + tuple(strides))
+        out[k] = view[0] if C_ == 1 else view
+        o += sz
+    return out
 
 
 def runSGMCMC(sgmcmc: Sgmcmc, paramsRaw, options) -> Dict[str, np.ndarray]:

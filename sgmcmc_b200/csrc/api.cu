@@ -20,6 +20,7 @@
 #include "logistic.cuh"
 #include "logistic_staged.cuh"
 #include "logistic_fullgrad_stream.cuh"
+#include "logistic_ring.cuh"
 #include "softmax_net.cuh"
 
 using namespace sgm;
@@ -462,8 +463,40 @@ static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
     return fail(SGM_EINVAL, "logistic staged kernel: minibatch %d too large", a.n);
 }
 
+template <int V, bool HAT_DOT>
+static int launch_logistic_ring_t(sgm_handle* h, const ChainArgs& a) {
+    auto k = logistic_ring_kernel<V, HAT_DOT>;
+    const size_t smem = lr_smem_bytes(h->ld, a.n);
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const int grid = a.C < sms ? a.C : sms;
+    k<<<grid, LR_THREADS, smem, h->stream>>>(a);
+    CU(cudaGetLastError());
+    return SGM_OK;
+}
+
+// long rows: warp-specialised TMA ring (logistic_ring.cuh)
+static bool logistic_use_ring(const sgm_handle* h, const ChainArgs& a) {
+    const char* force = getenv("SGM_LOGISTIC_KERNEL");
+    if (!(force && !strcmp(force, "ring"))) return false;   // opt-in: measured slower than the register-staged kernel (profiles/r01_c5_ring_vs_generic.txt)
+    const int V = (h->ld / 4 + 31) / 32;
+    return h->ld > 128 && V >= 2 && V <= 9 && lr_smem_bytes(h->ld, a.n) <= 227 * 1024;
+}
+
+static int launch_logistic_ring(sgm_handle* h, const ChainArgs& a) {
+    const bool hat_dot = a.cv && !h->rhat_cached;
+    const int V = (h->ld / 4 + 31) / 32;
+#define LR_CASE(v) case v: return hat_dot ? launch_logistic_ring_t<v, true>(h, a) : launch_logistic_ring_t<v, false>(h, a);
+    switch (V) { LR_CASE(2) LR_CASE(3) LR_CASE(4) LR_CASE(5) LR_CASE(6) LR_CASE(7) LR_CASE(8) LR_CASE(9) }
+#undef LR_CASE
+    return fail(SGM_EINVAL, "logistic ring kernel: unsupported row length %d", h->ld);
+}
+
 static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
+    const_cast<ChainArgs&>(a).rhat_cached = h->rhat_cached ? 1 : 0;
     if (logistic_use_staged(h, a)) return launch_logistic_staged(h, a);
+    if (logistic_use_ring(h, a)) return launch_logistic_ring(h, a);
     LogiShape s;
     if (!logi_shape(h->ld, &s)) return fail(SGM_EINVAL, "logistic: d = %d too large", h->d);
     const int threads = logi_threads(h, s);
@@ -937,7 +970,7 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
         h->base.hat_stride = (M == 1 && h->C > 1) ? 0 : h->Pst;
         // one mode for every chain: cache the per-datum residual at the mode next to y (logistic_staged.cuh)
         h->rhat_cached = false;
-        if (h->model == SGM_MODEL_LOGISTIC && M == 1 && (h->d & 3) != 3 && logistic_use_staged(h, h->base)) {
+        if (h->model == SGM_MODEL_LOGISTIC && M == 1 && (h->d & 3) != 3) {
             logistic_cache_rhat_kernel<<<(unsigned)cdiv(h->N * 32, 256), 256, 0, h->stream>>>(h->X, h->N, h->ld, h->d, h->theta_hat);
             CU(cudaGetLastError());
             h->rhat_cached = true;
@@ -1238,6 +1271,14 @@ extern "C" int sgm_bench_full_gradient(sgm_handle* h, int reps, float* ms_per_re
     CU(cudaMemsetAsync(h->gsum, 0, (size_t)M * h->Pst * sizeof(double), h->stream));
     return SGM_OK;
 }
+
+// pinned host buffers for result copy-out (optional: any caller-allocated buffer works, pinned ones copy faster)
+extern "C" void* sgm_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void sgm_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------
 // multi-GPU

@@ -74,6 +74,7 @@ struct ChainArgs {
     int* diverged;
     // optional phase timing (debug): thread 0 of every CTA adds clock64() deltas, [phase] slots
     unsigned long long* prof;
+    int rhat_cached;  // logistic *cv with one shared mode: y - s(x.beta_hat + bias_hat) is stored at column d + 1 of every row
     int gather_tma;   // logistic short-row kernel: 1 = one TMA bulk copy per row, 0 = 16-byte cp.async
 };
 

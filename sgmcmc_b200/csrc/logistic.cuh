@@ -99,11 +99,12 @@ __device__ __forceinline__ void logi_pass(const ChainArgs& a, const LogiSmem& sm
             for (int v = 0; v < V; ++v) x[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         // extract y from the tail float4 and blank its slot
-        float y = 0.f;
+        float y = 0.f, rc = 0.f;
+        const bool hat_dot = a.cv && !a.rhat_cached;   // the residual at a shared mode rides in the row (column d + 1)
         if (lg == lg_t) {
 #pragma unroll
             for (int v = 0; v < V; ++v)
-                if (v == v_t) { y = get4(x[v], ct); set4(x[v], ct, 0.f); }
+                if (v == v_t) { y = get4(x[v], ct); rc = get4(x[v], ct + 1); set4(x[v], ct, 0.f); }
         }
         float coef;
         if (pass == PASS_BETA) {
@@ -117,13 +118,14 @@ __device__ __forceinline__ void logi_pass(const ChainArgs& a, const LogiSmem& sm
             for (int v = 0; v < V; ++v) {
                 const int col = 4 * (lg + G * v);
                 dz += dot4(x[v], *reinterpret_cast<const float4*>(sm.th + col));
-                if (a.cv) dh += dot4(x[v], *reinterpret_cast<const float4*>(sm.hat + col));
+                if (hat_dot) dh += dot4(x[v], *reinterpret_cast<const float4*>(sm.hat + col));
             }
             // the bias slot of th/hat meets a blanked x slot, so dz/dh are pure x.beta
             dz = group_sum<G>(dz);
             const float r = y - sigmoidf(bias + dz);
             float rh = 0.f;
-            if (a.cv) { dh = group_sum<G>(dh); rh = y - sigmoidf(bias_hat + dh); }
+            if (hat_dot) { dh = group_sum<G>(dh); rh = y - sigmoidf(bias_hat + dh); }
+            else if (a.cv) rh = __shfl_sync(0xffffffffu, rc, lg_t, G);
             coef = a.cv ? r - rh : r;
             if (pass == PASS_BIAS && valid && lg == 0) { sm.dots[j] = dz; sm.rhat[j] = rh; sm.ys[j] = y; }
         }
