@@ -276,14 +276,21 @@ def _pinned_doubles(count: int) -> np.ndarray:
     return arr
 
 
-def getChains(sgmcmc: Sgmcmc) -> Dict[str, np.ndarray]:
+def getChains(sgmcmc: Sgmcmc, reuse_buffer: bool = False) -> Dict[str, np.ndarray]:
     """One copy-out of the device-resident chain as the reference's storage list
     (R/storage.R:42-51): per parameter an array (nIters, dims...); scalars give (nIters, 1).
     The arrays are zero-copy views of the single buffer the library fills in R's column-major layout."""
     lib = _lib.load()
     iters = int(lib.sgm_chain_length(sgmcmc.handle))
     C_, P = sgmcmc.nChains, sgmcmc.P
-    buf = _pinned_doubles(C_ * P * iters)
+    # reuse_buffer: streaming consumers (chunked runs) may let successive calls overwrite one page-locked buffer
+    # instead of paying a page-locked allocation per call; the default hands out independent arrays
+    if reuse_buffer and getattr(sgmcmc, "_chain_buf", None) is not None and sgmcmc._chain_buf.size == C_ * P * iters:
+        buf = sgmcmc._chain_buf
+    else:
+        buf = _pinned_doubles(C_ * P * iters)
+        if reuse_buffer:
+            sgmcmc._chain_buf = buf
     _lib.check(lib.sgm_copy_chain(sgmcmc.handle, _dptr(buf)))
     out, o = {}, 0
     for k, shp in sgmcmc.paramShapes.items():
