@@ -146,6 +146,7 @@ def _create(logLik, logPrior, dataset, params, stepsize, minibatchSize, seed, al
     obj.params = params
     obj.paramShapes = {k: v.shape for k, v in params.items()}
     obj.nChains = int(nChains)
+    obj.dataNames = tuple(names)
     obj.P = int(lib.sgm_num_scalars(h))
     if algo == _lib.ALGO_SGHMC:
         obj.alpha, obj.L = alpha, int(L)
@@ -252,6 +253,25 @@ def estLogPost(sgmcmc: Sgmcmc, sess: Session) -> np.ndarray:
     """sess$run(sgmcmc$estLogPost, fresh minibatch) -- R/update.R:198-199."""
     out = np.empty(sgmcmc.nChains, dtype=np.float64)
     _lib.check(_lib.load().sgm_est_logpost(sgmcmc.handle, _dptr(out)))
+    return out
+
+
+def heldoutLogLik(sgmcmc: Sgmcmc, sess: Session, testset) -> np.ndarray:
+    """logLik(current params, testset) per chain, on the device.  Replaces the user-built TensorFlow tensors that
+    referenced ``sgld$params`` in the reference's vignettes (nn.Rmd:113-123: logLoss = -logLik / Ntest;
+    logisticRegression.Rmd:89-115)."""
+    lib = _lib.load()
+    names = list(sgmcmc.dataNames)
+    arrs = (_lib.SgmArray * len(names))()
+    keep = []
+    for i, nm in enumerate(names):
+        v = np.asfortranarray(np.asarray(testset[nm], dtype=np.float64))
+        keep.append(v)
+        arrs[i].name = nm.encode(); arrs[i].data = _dptr(v); arrs[i].ndim = v.ndim
+        for j, s_ in enumerate(v.shape):
+            arrs[i].dims[j] = s_
+    out = np.empty(sgmcmc.nChains, dtype=np.float64)
+    _lib.check(lib.sgm_heldout_loglik(sgmcmc.handle, arrs, len(names), _dptr(out)))
     return out
 
 

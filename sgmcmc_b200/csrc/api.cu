@@ -1207,9 +1207,58 @@ extern "C" int sgm_grad_estimate(sgm_handle* h, const int32_t* idx, double* out)
     return rc;
 }
 
+// log-likelihood of the current state of every chain on caller data (no prior, no N/n factor); replaces the
+// user-built TensorFlow tensors of vignettes/nn.Rmd:113-123 and the R loop of logisticRegression.Rmd:89-115
 extern "C" int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t n_data, double* out) {
-    (void)h; (void)data; (void)n_data; (void)out;
-    return fail(SGM_EINVAL, "sgm_heldout_loglik: not implemented in this build");
+    if (!h || !data || !out) return fail(SGM_EINVAL, "null argument");
+    const int entries = (h->model == SGM_MODEL_GAUSS_MEAN || h->model == SGM_MODEL_MIXTURE2) ? 1 : 2;
+    if (n_data < entries) return fail(SGM_EINVAL, "held-out data needs %d entries", entries);
+    const int64_t Nh = data[0].dims[0];
+    if (Nh < 1 || Nh >= (1ll << 31)) return fail(SGM_EINVAL, "held-out rows must be in [1, 2^31)");
+    if (int rc = set_device(h)) return rc;
+    float* Xh = nullptr;
+    const size_t xbytes = (size_t)Nh * h->ld * sizeof(float);
+    if (cudaMalloc(&Xh, xbytes) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate %zu bytes for the held-out set", xbytes); }
+    CU(cudaMemsetAsync(Xh, 0, xbytes, h->stream));
+    int col0 = 0;
+    for (int k = 0; k < entries; ++k) {
+        const sgm_array& A = data[k];
+        const int cols = A.ndim >= 2 ? (int)A.dims[1] : 1;
+        const int want = (k == 0) ? h->d : (h->ld >= h->d + cols ? cols : -1);
+        if (!A.data || A.dims[0] != Nh || (k == 0 && cols != want)) { cudaFree(Xh); return fail(SGM_EINVAL, "held-out entry %d has the wrong shape", k); }
+        double* stage = nullptr;
+        const size_t bytes = (size_t)Nh * cols * sizeof(double);
+        if (cudaMalloc(&stage, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(Xh); return fail(SGM_ENOMEM, "cannot allocate staging"); }
+        CU(cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream));
+        pack_rows_kernel<<<(unsigned)cdiv(Nh * cols, 256), 256, 0, h->stream>>>(stage, Nh, cols, Xh, h->ld, col0);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(stage);
+        col0 += cols;
+    }
+    ChainArgs a = h->base;
+    a.X = Xh; a.N = (uint32_t)Nh; a.n = (int)Nh; a.corr = 1.0f; a.use_prior = 0; a.det = 2; a.idx = nullptr;
+    int rc = SGM_OK;
+    switch (h->model) {
+        case SGM_MODEL_GAUSS_MEAN:
+            small_logpost_kernel<SMALL_MODEL_GAUSS><<<(unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream>>>(a, 0u, h->dout); break;
+        case SGM_MODEL_MIXTURE2:
+            small_logpost_kernel<SMALL_MODEL_MIX2><<<(unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream>>>(a, 0u, h->dout); break;
+        case SGM_MODEL_LOGISTIC:
+            logistic_logpost_kernel<<<h->C, 256, 0, h->stream>>>(a, 0u, h->theta, h->dout); break;
+        case SGM_MODEL_SOFTMAX_NET: {
+            const int e = softmax_net_logpost(h->nn, a, 0u, h->theta, h->dout, h->stream);
+            if (e != 0) rc = fail(SGM_ECUDA, "softmax net held-out: %s", cudaGetErrorString((cudaError_t)e));
+            break;
+        }
+    }
+    if (rc == SGM_OK && cudaGetLastError() != cudaSuccess) rc = fail(SGM_ECUDA, "held-out kernel launch failed");
+    if (rc == SGM_OK) {
+        cudaMemcpyAsync(out, h->dout, (size_t)h->C * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(SGM_ECUDA, "held-out evaluation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(Xh);
+    return rc;
 }
 
 extern "C" int64_t sgm_num_rows(const sgm_handle* h) { return h ? h->N : 0; }

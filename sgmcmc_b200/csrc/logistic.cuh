@@ -376,10 +376,10 @@ __global__ void logistic_logpost_kernel(const ChainArgs a, uint32_t word2, const
     const int c = blockIdx.x, tid = threadIdx.x;
     const float* th = theta + (size_t)c * a.Pst;
     const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
-    const int32_t* idx = a.det ? a.idx + (size_t)c * a.n : nullptr;
+    const int32_t* idx = (a.det == 1) ? a.idx + (size_t)c * a.n : nullptr;
     float ll = 0.f;
     for (int j = tid; j < a.n; j += blockDim.x) {
-        const uint32_t row = idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j);
+        const uint32_t row = (a.det == 2) ? (uint32_t)j : (idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j));   // det == 2: rows 0..n-1
         const float* xr = a.X + (size_t)row * a.ld;
         float z = 0.f;
         for (int k = 0; k < a.d; ++k) z += xr[k] * th[k];

@@ -228,10 +228,10 @@ __global__ void small_logpost_kernel(const ChainArgs a, uint32_t word2, double* 
         th[k] = f >= 0 ? a.theta[(size_t)c * a.Pst + f] : 0.f;
     }
     Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
-    const int32_t* idx = a.det ? a.idx + (size_t)c * a.n : nullptr;
+    const int32_t* idx = (a.det == 1) ? a.idx + (size_t)c * a.n : nullptr;
     float ll = 0.f;
     for (int j = lane; j < a.n; j += 32) {
-        const uint32_t row = idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j);
+        const uint32_t row = (a.det == 2) ? (uint32_t)j : (idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j));   // det == 2: rows 0..n-1 (held-out set)
         const float* xr = a.X + (size_t)row * a.ld;
         if (MODEL == SMALL_MODEL_GAUSS) {
             float q = 0.f;

@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_logpost_kernel(cons
     const int c = blockIdx.x;
     const float* th = theta + (size_t)c * a.Pst;
     const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
-    const int32_t* idx = a.det ? a.idx + (size_t)c * a.n : nullptr;
+    const int32_t* idx = (a.det == 1) ? a.idx + (size_t)c * a.n : nullptr;   // det == 2: contiguous rows 0..n-1 (held-out set)
     float ll = nn_eval(dm, sm, a.X, a.ld, a.n, a.det ? nullptr : &perm, idx, 0, th, 0, false, true, Gscratch + (size_t)c * a.Pst);
     ll = nn_block_sum(ll, sm.red);
     float lp = 0.f;

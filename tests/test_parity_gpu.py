@@ -232,3 +232,21 @@ def test_same_seed_reproduces(lib):
     o3 = S.sgld(S.gaussMeanLogLik(), data, params, 1e-6, nIters=10, minibatchSize=5, verbose=False, seed=2)["theta"]
     o1 = S.sgld(S.gaussMeanLogLik(), data, params, 1e-6, **std)["theta"]
     assert np.abs(o1 - o3).max() > 0
+
+
+@pytest.mark.parametrize("case_name", ["gauss2d", "mixture", "logistic54", "softmaxnet_small"])
+def test_heldout_loglik_matches_oracle(lib, case_name):
+    """Held-out log-likelihood on the device (replaces the user-built TF tensors of vignettes/nn.Rmd:113-123)."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import validation as V
+    case = make_case(case_name)
+    dev = device_setup(case, "sgld", False, n_chains=2)
+    sess = V.initSessDeterministic(dev)
+    rs = np.random.RandomState(11)
+    pick = rs.choice(case["N"], 333, replace=False)
+    test = {k: np.asarray(v)[pick] for k, v in case["data"].items()}
+    got = S.heldoutLogLik(dev, sess, test)
+    want = float(case["om"].loglik(case["params"], test, np.float64))
+    assert got.shape == (2,)
+    for c in range(2):
+        assert abs(got[c] - want) <= 2e-5 * abs(want) + 1e-3, (got[c], want)
