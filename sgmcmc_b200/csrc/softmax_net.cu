@@ -56,11 +56,8 @@ struct SoftmaxNetWork {
     size_t smem = 0;
 };
 
-__device__ __forceinline__ int nn_flat_of_internal(const NNDims& dm, int e) {
-    if (e < dm.offB) { const int k = e / dm.dout, l = e % dm.dout; return dm.offA + k + dm.dh * l; }
-    if (e < dm.offa) { const int r = e - dm.offB; const int j = r / dm.dh, k = r % dm.dh; return dm.offB + j + dm.din * k; }
-    return e;
-}
+// internal element order == flat (ABI) order: every tensor in R's column-major element order (A[k + dh*l], B[j + din*n])
+__device__ __forceinline__ int nn_flat_of_internal(const NNDims&, int e) { return e; }
 __device__ __forceinline__ int nn_tensor_of(const NNDims& dm, int e) {
     if (e < dm.offB) return 0;
     if (e < dm.offa) return 1;
@@ -68,6 +65,13 @@ __device__ __forceinline__ int nn_tensor_of(const NNDims& dm, int e) {
     if (e < dm.offl) return 3;
     return 4 + (e - dm.offl);
 }
+
+// tcgen05 state of one CTA: TMEM base, two stage barriers (operand buffers) and their commit counts
+struct TcCtx {
+    uint32_t tmem;      // TMEM base address (512 columns allocated for the kernel's lifetime)
+    uint32_t bar[2];    // shared-space addresses of the stage mbarriers
+    uint32_t commits[2];
+};
 
 struct NNSmem {
     float* H;     // [NN_RB][dh]
@@ -82,6 +86,8 @@ struct NNSmem {
     float* ga;    // [dop]
     float* red;   // [64]
     int* rows;    // [NN_RB]
+    uint32_t* tc_slot;  // [4]: TMEM base written by tcgen05.alloc; 16-byte aligned
+    uint64_t* tc_bars;  // [2]
 };
 
 __device__ __forceinline__ float nn_block_sum(float v, float* red) {
@@ -99,7 +105,7 @@ __device__ __forceinline__ float nn_block_sum(float v, float* red) {
 __device__ void nn_load_small(const NNDims& dm, const NNSmem& sm, const float* __restrict__ th) {
     for (int i = threadIdx.x; i < dm.dh * dm.dop; i += NN_THREADS) {
         const int k = i / dm.dop, l = i % dm.dop;
-        sm.A[i] = (l < dm.dout) ? th[dm.offA + k * dm.dout + l] : 0.f;
+        sm.A[i] = (l < dm.dout) ? th[dm.offA + k + dm.dh * l] : 0.f;
     }
     for (int i = threadIdx.x; i < dm.dop; i += NN_THREADS) sm.a[i] = (i < dm.dout) ? th[dm.offa + i] : 0.f;
     for (int i = threadIdx.x; i < dm.dh; i += NN_THREADS) sm.b[i] = th[dm.offb + i];
@@ -191,6 +197,213 @@ __device__ void nn_stage1(const NNDims& dm, const NNSmem& sm, const float* __res
         if (live && row < nb)
             *reinterpret_cast<float4*>(sm.H + row * dm.dh + 4 * lane) = make_float4(e0 / s, e1 / s, e2 / s, e3 / s);
     }
+    __syncthreads();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05 helpers (5th-generation tensor cores: operands in shared memory, accumulator in tensor memory)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Shared-memory operand descriptor, K-major, no swizzle: the operand is a grid of 8-row x 16-byte core matrices;
+// the 16-byte chunk (kg, row) lives at kg * lbo + row * 16, so LBO = distance between the two K chunks of one MMA,
+// SBO = distance between 8-row groups = 128 B.  (Bit layout: cute/arch/mma_sm100_desc.hpp, descriptor version 1.)
+__device__ __forceinline__ uint64_t nn_umma_desc(uint32_t addr, uint32_t lbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
+}
+// Instruction descriptor for kind::tf32, float32 accumulate, both operands K-major
+__device__ __forceinline__ uint32_t nn_umma_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void nn_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void nn_umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void nn_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void nn_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// float32 -> (hi, lo), both rounded to nearest TF32 (cvt.rna): hi*hi' + hi*lo' + lo*hi' recovers float32-level
+// products with unbiased errors (a truncating split leaves same-signed residuals that add up coherently over K)
+__device__ __forceinline__ float nn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void nn_split4(const float4 x, float4& hi, float4& lo) {
+    hi.x = nn_tf32(x.x); hi.y = nn_tf32(x.y); hi.z = nn_tf32(x.z); hi.w = nn_tf32(x.w);
+    lo.x = nn_tf32(x.x - hi.x); lo.y = nn_tf32(x.y - hi.y); lo.z = nn_tf32(x.z - hi.z); lo.w = nn_tf32(x.w - hi.w);
+}
+
+// kernel prologue / epilogue: TMEM allocation (all 512 columns: one CTA per SM), stage barriers
+__device__ void nn_tc_init(const NNSmem& sm, TcCtx& tc) {
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(nn_smem_u32(sm.tc_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(nn_smem_u32(sm.tc_bars)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(nn_smem_u32(sm.tc_bars + 1)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc.tmem = *sm.tc_slot;
+    tc.bar[0] = nn_smem_u32(sm.tc_bars); tc.bar[1] = nn_smem_u32(sm.tc_bars + 1);
+    tc.commits[0] = tc.commits[1] = 0;
+}
+__device__ void nn_tc_fini(const TcCtx& tc) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "n"(512));
+}
+
+constexpr int TC_KC = 16;   // K per operand stage of S1 (two k8 MMAs x three split terms)
+constexpr int TC_SEG = 4;   // K is cut into TC_SEG segments with separate TMEM accumulators, summed in registers: the tensor
+                            // core's float32 accumulation truncates, and the bias grows with the number of accumulation steps
+
+// S1 on the tensor cores: Z1[128 x Npad] = X[128 x din] * B^T (B stored [hidden][input] = K-major) as 3xTF32 tcgen05.mma
+// with the accumulator in TMEM; operand stages are written by all threads (float4 global loads -> hi/lo split -> 16-byte
+// shared stores in the core-matrix layout), double-buffered against the asynchronous MMAs; the epilogue (bias, row
+// softmax) reads TMEM with tcgen05.ld, one row per thread, and writes H to shared memory.
+__device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb,
+                             const float* __restrict__ th, TcCtx& tc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Npad = (dm.dh + 15) & ~15;
+    const int LBOA = NN_RB * 16;                   // bytes between K chunks of the A operand (128 rows x 16 B)
+    const int rowsB = Npad + 2;                    // +2 rows: K chunks land 8 banks apart (conflict-free 16-byte stores)
+    const int LBOB = rowsB * 16;
+    const int KG = TC_KC / 4;                      // 16-byte K chunks per stage
+    const int A_FLOATS = KG * NN_RB * 4, B_FLOATS = KG * rowsB * 4, STAGE = 2 * A_FLOATS + 2 * B_FLOATS;
+    const float* __restrict__ B = th + dm.offB;    // [dh][din]
+    const uint32_t idesc = nn_umma_idesc(NN_RB, Npad);
+    // zero the padding rows of the B operand (hidden units dh..Npad-1) in both stages once per call
+    __syncthreads();
+    for (int t = tid; t < 2 * 2 * KG * (rowsB - dm.dh); t += NN_THREADS) {
+        const int st = t / (2 * KG * (rowsB - dm.dh)), r0 = t % (2 * KG * (rowsB - dm.dh));
+        const int half = r0 / (KG * (rowsB - dm.dh)), r1 = r0 % (KG * (rowsB - dm.dh));
+        const int kg = r1 / (rowsB - dm.dh), n = dm.dh + r1 % (rowsB - dm.dh);
+        *reinterpret_cast<float4*>(sm.tile + st * STAGE + 2 * A_FLOATS + half * B_FLOATS + (kg * rowsB + n) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int xr = tid % NN_RB, xkg = tid / NN_RB;   // 512 threads = 128 rows x 4 chunks: one float4 of X per thread per stage
+    const float* xrow = X + (size_t)sm.rows[xr < nb ? xr : 0] * ld;
+    const int nchunks = (dm.din + TC_KC - 1) / TC_KC;
+    const int seg_chunks = (nchunks + TC_SEG - 1) / TC_SEG;
+    const int nseg = (nchunks + seg_chunks - 1) / seg_chunks;
+    // software pipeline: the global loads of chunk c + 1 are issued before chunk c's barrier / MMAs
+    const int bt0 = tid, bt1 = tid + NN_THREADS;                 // this thread's (up to two) B float4 slots per stage
+    const bool b0_live = bt0 < dm.dh * KG, b1_live = bt1 < dm.dh * KG;
+    const float* b0_ptr = B + (size_t)(bt0 / KG) * dm.din + 4 * (bt0 % KG);
+    const float* b1_ptr = B + (size_t)(bt1 / KG) * dm.din + 4 * (bt1 % KG);
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), bv0 = xv, bv1 = xv;
+    auto prefetch = [&](int j0) {
+        xv = make_float4(0.f, 0.f, 0.f, 0.f); bv0 = xv; bv1 = xv;
+        if (xkg < KG && xr < nb && j0 + 4 * xkg < dm.din) xv = __ldg(reinterpret_cast<const float4*>(xrow + j0 + 4 * xkg));
+        if (b0_live && j0 + 4 * (bt0 % KG) < dm.din) bv0 = *reinterpret_cast<const float4*>(b0_ptr + j0);
+        if (b1_live && j0 + 4 * (bt1 % KG) < dm.din) bv1 = *reinterpret_cast<const float4*>(b1_ptr + j0);
+    };
+    prefetch(0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        float* stage = sm.tile + buf * STAGE;
+        // the MMAs that read this buffer two chunks ago must have completed
+        if (tc.commits[buf] > 0) nn_mbar_wait(tc.bar[buf], (tc.commits[buf] - 1u) & 1u);
+        {
+            float4 hi, lo;
+            if (xkg < KG) {   // A operand: X rows
+                nn_split4(xv, hi, lo);
+                *reinterpret_cast<float4*>(stage + (xkg * NN_RB + xr) * 4) = hi;
+                *reinterpret_cast<float4*>(stage + A_FLOATS + (xkg * NN_RB + xr) * 4) = lo;
+            }
+            if (b0_live) {    // B operand: hidden unit n, chunk kg
+                nn_split4(bv0, hi, lo);
+                *reinterpret_cast<float4*>(stage + 2 * A_FLOATS + ((bt0 % KG) * rowsB + bt0 / KG) * 4) = hi;
+                *reinterpret_cast<float4*>(stage + 2 * A_FLOATS + B_FLOATS + ((bt0 % KG) * rowsB + bt0 / KG) * 4) = lo;
+            }
+            if (b1_live) {
+                nn_split4(bv1, hi, lo);
+                *reinterpret_cast<float4*>(stage + 2 * A_FLOATS + ((bt1 % KG) * rowsB + bt1 / KG) * 4) = hi;
+                *reinterpret_cast<float4*>(stage + 2 * A_FLOATS + B_FLOATS + ((bt1 % KG) * rowsB + bt1 / KG) * 4) = lo;
+            }
+        }
+        if (c + 1 < nchunks) prefetch((c + 1) * TC_KC);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = nn_smem_u32(stage), a_lo = a_hi + A_FLOATS * 4, b_hi = a_hi + 2 * A_FLOATS * 4, b_lo = b_hi + B_FLOATS * 4;
+#pragma unroll
+            const int seg = c / seg_chunks;
+            const uint32_t td = tc.tmem + (uint32_t)(seg * Npad);
+            for (int k8 = 0; k8 < TC_KC / 8; ++k8) {
+                const uint32_t ao = (uint32_t)(2 * k8) * LBOA, bo = (uint32_t)(2 * k8) * LBOB;
+                const bool acc0 = (c % seg_chunks > 0) || (k8 > 0);
+                nn_umma_tf32(td, nn_umma_desc(a_hi + ao, LBOA), nn_umma_desc(b_hi + bo, LBOB), idesc, acc0);
+                nn_umma_tf32(td, nn_umma_desc(a_hi + ao, LBOA), nn_umma_desc(b_lo + bo, LBOB), idesc, true);
+                nn_umma_tf32(td, nn_umma_desc(a_lo + ao, LBOA), nn_umma_desc(b_hi + bo, LBOB), idesc, true);
+            }
+            nn_umma_commit(tc.bar[buf]);
+        }
+        tc.commits[buf] += 1;
+    }
+    // all MMAs complete in order: wait for the last commit of each buffer
+#pragma unroll
+    for (int b2 = 0; b2 < 2; ++b2)
+        if (tc.commits[b2] > 0) nn_mbar_wait(tc.bar[b2], (tc.commits[b2] - 1u) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warps 0..3 own TMEM lanes 32w..32w+31 = rows; one row per thread
+    if (warp < 4) {
+        const int row = 32 * warp + lane;
+        const uint32_t tbase = tc.tmem + ((uint32_t)(32 * warp) << 16);
+        auto load16 = [&](int c0, float (&v)[16]) {   // sum of the K segments' accumulators, in registers
+            nn_tmem_ld16(tbase + (uint32_t)c0, v);
+            for (int sg = 1; sg < nseg; ++sg) {
+                float w[16];
+                nn_tmem_ld16(tbase + (uint32_t)(sg * Npad + c0), w);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += w[i];
+            }
+        };
+        float m = -INFINITY;
+        for (int c0 = 0; c0 < Npad; c0 += 16) {
+            float v[16];
+            load16(c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c0 + i < dm.dh) m = fmaxf(m, v[i] + sm.b[c0 + i]);
+        }
+        float ssum = 0.f;
+        for (int c0 = 0; c0 < Npad; c0 += 16) {
+            float v[16];
+            load16(c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (c0 + i < dm.dh) {
+                    const float e = expf(v[i] + sm.b[c0 + i] - m);
+                    ssum += e;
+                    if (row < nb) sm.H[row * dm.dh + c0 + i] = e;
+                }
+            }
+        }
+        const float inv = 1.0f / ssum;
+        if (row < nb) for (int k = 0; k < dm.dh; ++k) sm.H[row * dm.dh + k] *= inv;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
 }
 
@@ -340,10 +553,11 @@ __device__ void nn_stage5(const NNDims& dm, const NNSmem& sm, const float* __res
             for (int a = 0; a < 4; ++a) {
                 const int j = j0 + 4 * warp + a;
                 if (j < dm.din) {
-                    float4* dst = reinterpret_cast<float4*>(GB + (size_t)j * dm.dh + 4 * lane);
-                    float4 o = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-                    if (!first) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-                    *dst = o;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {   // GB is stored like B: [hidden unit][input], R's column-major order
+                        float* dst = GB + (size_t)(4 * lane + c4) * dm.din + j;
+                        *dst = first ? acc[a][c4] : *dst + acc[a][c4];
+                    }
                 }
             }
         }
@@ -359,7 +573,7 @@ enum : int { NEED_A = 1, NEED_B = 2, NEED_a = 4, NEED_b = 8, NEED_ALL = 15 };
 // Rows come from idx (deterministic), the keyed permutation, or the contiguous range [row0, row0+n).
 __device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int n,
                          const Perm* perm, const int32_t* __restrict__ idx, int64_t row0,
-                         const float* __restrict__ th, int need, bool h_valid, bool want_ll, float* __restrict__ Gout) {
+                         const float* __restrict__ th, int need, bool h_valid, bool want_ll, float* __restrict__ Gout, TcCtx& tc) {
     nn_load_small(dm, sm, th);
     float ll = 0.f;
     const int nblocks = (n + NN_RB - 1) / NN_RB;
@@ -373,7 +587,7 @@ __device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __rest
                 sm.rows[r] = (r < nb) ? (idx ? idx[r0 + r] : (perm ? (int)perm_at(*perm, (uint32_t)(r0 + r)) : (int)(row0 + r0 + r))) : 0;
             __syncthreads();
             NN_TICK(6)
-            nn_stage1(dm, sm, X, ld, nb, th);
+            nn_stage1_tc(dm, sm, X, ld, nb, th, tc);
             NN_TICK(0)
         }
         ll += nn_stage2(dm, sm, X, ld, nb, want_ll);
@@ -388,7 +602,7 @@ __device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __rest
     if (need & (NEED_A | NEED_a)) {
         for (int i = threadIdx.x; i < dm.dh * dm.dout; i += NN_THREADS) {
             const int k = i / dm.dout, l = i % dm.dout;
-            Gout[dm.offA + i] = sm.gA[k * dm.dop + l];
+            Gout[dm.offA + k + dm.dh * l] = sm.gA[k * dm.dop + l];
         }
         for (int l = threadIdx.x; l < dm.dout; l += NN_THREADS) Gout[dm.offa + l] = sm.ga[l];
     }
@@ -536,13 +750,15 @@ __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
     sm.gA = p; p += dm.dh * dm.dop;
     sm.ga = p; p += NN_MAXO;
     sm.red = p; p += 64;
-    sm.rows = reinterpret_cast<int*>(p);
+    sm.rows = reinterpret_cast<int*>(p); p += NN_RB;
+    sm.tc_slot = reinterpret_cast<uint32_t*>(p); p += 4;
+    sm.tc_bars = reinterpret_cast<uint64_t*>(p);
 }
 
 static size_t nn_smem_bytes(const NNDims& dm) {
     const int t1 = 2 * (NN_KC * (NN_RB + 4) + NN_KC * dm.dh), t5 = 2 * NN_RB * NN_JT;
     size_t f = (size_t)2 * NN_RB * dm.dh + NN_RB * dm.dop + dm.dh * dm.dop + NN_MAXO + NN_MAXH + (t1 > t5 ? t1 : t5) +
-               NN_WARPS * dm.dh + dm.dh * dm.dop + NN_MAXO + 64 + NN_RB;
+               NN_WARPS * dm.dh + dm.dh * dm.dop + NN_MAXO + 64 + NN_RB + 4 + 4;
     return f * sizeof(float);
 }
 
@@ -551,6 +767,8 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
     NNSmem sm;
     nn_carve(dm, smem_f, sm);
     const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
+    TcCtx tc;
+    nn_tc_init(sm, tc);
     if (threadIdx.x == 0) nn_t_prev[blockIdx.x & 1023] = clock64();
     for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
         NNChainState st;
@@ -575,23 +793,23 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
                 const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
                 const int32_t* idx = a.det ? a.idx + (((size_t)c * a.iters + it) * a.L + l) * a.n : nullptr;
                 const Perm* pp = a.det ? nullptr : &perm;
-                if (a.cv) nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.hat, NEED_ALL, false, false, st.Ghat);
+                if (a.cv) nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.hat, NEED_ALL, false, false, st.Ghat, tc);
                 if (seidel) {
                     // A
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_A, false, false, st.G);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_A, false, false, st.G, tc);
                     nn_update_tensor(a, dm, sm, st, 0, c, step, sub, nullptr);
                     // B: H still valid (depends on B, b only)
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_B, true, false, st.G);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_B, true, false, st.G, tc);
                     nn_update_tensor(a, dm, sm, st, 1, c, step, sub, nullptr);
                     // a: B changed -> recompute H
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_a, false, false, st.G);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_a, false, false, st.G, tc);
                     nn_update_tensor(a, dm, sm, st, 2, c, step, sub, nullptr);
                     // b
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_b, true, false, st.G);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_b, true, false, st.G, tc);
                     nn_update_tensor(a, dm, sm, st, 3, c, step, sub, nullptr);
                     for (int t = 4; t < 8; ++t) nn_update_tensor(a, dm, sm, st, t, c, step, sub, nullptr);
                 } else {
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_ALL, false, false, st.G);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_ALL, false, false, st.G, tc);
                     float uu[MAX_TENSORS];
                     // All tensors move from ONE evaluation.  The mode finder writes theta in place, so the
                     // precisions (whose gradient reads ||W||^2) go first and the weights see the OLD precisions.
@@ -633,6 +851,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
         if (threadIdx.x == 0)
             for (int t = 0; t < MAX_TENSORS; ++t) a.thermo[c * MAX_TENSORS + t] = st.zeta[t];
     }
+    nn_tc_fini(tc);
 }
 
 // full-data gradient partials: CTA (x, m) sums rows [row0 + x*rows_per, ...) at theta_hat[m] into part[(m*gx + x)][Pst]
@@ -646,8 +865,11 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_fullgrad_kernel(con
     int64_t hi = lo + rows_per; if (hi > row1) hi = row1;
     float* G = part + ((size_t)m * gridDim.x + blockIdx.x) * a.Pst;
     if (lo >= hi) { for (int e = threadIdx.x; e < a.Pst; e += NN_THREADS) G[e] = 0.f; return; }
-    nn_eval(dm, sm, a.X, a.ld, (int)(hi - lo), nullptr, nullptr, lo, theta_hat + (size_t)m * a.Pst, NEED_ALL, false, false, G);
+    TcCtx tc;
+    nn_tc_init(sm, tc);
+    nn_eval(dm, sm, a.X, a.ld, (int)(hi - lo), nullptr, nullptr, lo, theta_hat + (size_t)m * a.Pst, NEED_ALL, false, false, G, tc);
     for (int e = dm.offl + threadIdx.x; e < a.Pst; e += NN_THREADS) G[e] = 0.f;
+    nn_tc_fini(tc);
 }
 
 __global__ void softmax_net_part_reduce(const float* __restrict__ part, int gx, int Pst, double* __restrict__ gsum, int total) {
@@ -690,7 +912,9 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_logpost_kernel(cons
     const float* th = theta + (size_t)c * a.Pst;
     const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2, TAG_CHECK_INDEX, a.k0, a.k1);
     const int32_t* idx = (a.det == 1) ? a.idx + (size_t)c * a.n : nullptr;   // det == 2: contiguous rows 0..n-1 (held-out set)
-    float ll = nn_eval(dm, sm, a.X, a.ld, a.n, a.det ? nullptr : &perm, idx, 0, th, 0, false, true, Gscratch + (size_t)c * a.Pst);
+    TcCtx tc;
+    nn_tc_init(sm, tc);
+    float ll = nn_eval(dm, sm, a.X, a.ld, a.n, a.det ? nullptr : &perm, idx, 0, th, 0, false, true, Gscratch + (size_t)c * a.Pst, tc);
     ll = nn_block_sum(ll, sm.red);
     float lp = 0.f;
     if (a.use_prior) {
@@ -704,6 +928,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_logpost_kernel(cons
         }
     }
     if (threadIdx.x == 0) out[c] = (double)(lp + a.corr * ll);
+    nn_tc_fini(tc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -741,13 +966,8 @@ void softmax_net_tables(const SoftmaxNetWork* w, int* flat_of, int* tensor_of, i
     const NNDims& dm = w->dm;
     for (int e = 0; e < Pst; ++e) {
         if (e >= dm.P) { flat_of[e] = -1; tensor_of[e] = 0; continue; }
-        int f = e, t;
-        if (e < dm.offB) { const int k = e / dm.dout, l = e % dm.dout; f = dm.offA + k + dm.dh * l; t = 0; }
-        else if (e < dm.offa) { const int r = e - dm.offB; const int j = r / dm.dh, k = r % dm.dh; f = dm.offB + j + dm.din * k; t = 1; }
-        else if (e < dm.offb) t = 2;
-        else if (e < dm.offl) t = 3;
-        else t = 4 + (e - dm.offl);
-        flat_of[e] = f; tensor_of[e] = t;
+        flat_of[e] = e;
+        tensor_of[e] = e < dm.offB ? 0 : (e < dm.offa ? 1 : (e < dm.offb ? 2 : (e < dm.offl ? 3 : 4 + (e - dm.offl))));
     }
 }
 

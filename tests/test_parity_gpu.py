@@ -168,16 +168,7 @@ def test_device_rng_streams_match_oracle(lib, case_name, algo, cv):
     th = V.flatParams(dev)
     P = th.shape[1]
     Leff = L if algo == "sghmc" else 1
-    # the softmax-net kernels index device-drawn dynamics noise by INTERNAL element (A, B row-major)
-    to_internal = np.arange(P)
-    if case_name.startswith("softmaxnet"):
-        dh, do = case["params"]["A"].shape
-        din = case["params"]["B"].shape[0]
-        offB = dh * do
-        fA = np.arange(dh * do)
-        to_internal[fA] = (fA % dh) * do + fA // dh
-        fB = np.arange(din * dh)
-        to_internal[offB + fB] = offB + (fB % din) * dh + fB // din
+    to_internal = np.arange(P)   # every family indexes device-drawn noise by flat parameter position
     for c in range(C):
         ch = oracle_chain(case, algo, cv, np.float32, L=L)
         if algo != "sgld":
