@@ -310,14 +310,20 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
     const bool b0_live = bt0 < dm.dh * KG, b1_live = bt1 < dm.dh * KG;
     const float* b0_ptr = B + (size_t)(bt0 / KG) * dm.din + 4 * (bt0 % KG);
     const float* b1_ptr = B + (size_t)(bt1 / KG) * dm.din + 4 * (bt1 % KG);
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), bv0 = xv, bv1 = xv;
-    auto prefetch = [&](int j0) {
-        xv = make_float4(0.f, 0.f, 0.f, 0.f); bv0 = xv; bv1 = xv;
-        if (xkg < KG && xr < nb && j0 + 4 * xkg < dm.din) xv = __ldg(reinterpret_cast<const float4*>(xrow + j0 + 4 * xkg));
-        if (b0_live && j0 + 4 * (bt0 % KG) < dm.din) bv0 = *reinterpret_cast<const float4*>(b0_ptr + j0);
-        if (b1_live && j0 + 4 * (bt1 % KG) < dm.din) bv1 = *reinterpret_cast<const float4*>(b1_ptr + j0);
+    // register pipeline three chunks deep: p0 is the chunk about to be staged, p1 / p2 the following two
+    struct Pre { float4 x, b0, b1; };
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int cc) -> Pre {
+        Pre pr{z4, z4, z4};
+        if (cc < nchunks) {
+            const int j0 = cc * TC_KC;
+            if (xkg < KG && xr < nb && j0 + 4 * xkg < dm.din) pr.x = __ldg(reinterpret_cast<const float4*>(xrow + j0 + 4 * xkg));
+            if (b0_live && j0 + 4 * (bt0 % KG) < dm.din) pr.b0 = *reinterpret_cast<const float4*>(b0_ptr + j0);
+            if (b1_live && j0 + 4 * (bt1 % KG) < dm.din) pr.b1 = *reinterpret_cast<const float4*>(b1_ptr + j0);
+        }
+        return pr;
     };
-    prefetch(0);
+    Pre p0 = fetch(0), p1 = fetch(1), p2 = fetch(2);
     for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1;
         float* stage = sm.tile + buf * STAGE;
@@ -325,6 +331,7 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
         if (tc.commits[buf] > 0) nn_mbar_wait(tc.bar[buf], (tc.commits[buf] - 1u) & 1u);
         {
             float4 hi, lo;
+            const float4 xv = p0.x, bv0 = p0.b0, bv1 = p0.b1;
             if (xkg < KG) {   // A operand: X rows
                 nn_split4(xv, hi, lo);
                 *reinterpret_cast<float4*>(stage + (xkg * NN_RB + xr) * 4) = hi;
@@ -341,7 +348,7 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
                 *reinterpret_cast<float4*>(stage + 2 * A_FLOATS + B_FLOATS + ((bt1 % KG) * rowsB + bt1 / KG) * 4) = lo;
             }
         }
-        if (c + 1 < nchunks) prefetch((c + 1) * TC_KC);
+        p0 = p1; p1 = p2; p2 = fetch(c + 3);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -367,11 +374,13 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
     for (int b2 = 0; b2 < 2; ++b2)
         if (tc.commits[b2] > 0) nn_mbar_wait(tc.bar[b2], (tc.commits[b2] - 1u) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // epilogue: warps 0..3 own TMEM lanes 32w..32w+31 = rows; one row per thread
-    if (warp < 4) {
-        const int row = 32 * warp + lane;
-        const uint32_t tbase = tc.tmem + ((uint32_t)(32 * warp) << 16);
-        auto load16 = [&](int c0, float (&v)[16]) {   // sum of the K segments' accumulators, in registers
+    // epilogue, all 16 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (= rows) for the 16-column groups w / 4, w / 4 + 4, ...,
+    // sums the K segments in registers, adds the bias and parks Z1 in sm.H; then one warp per row does the softmax in place
+    {
+        const int q = warp & 3, row = 32 * q + lane;
+        const uint32_t tbase = tc.tmem + ((uint32_t)(32 * q) << 16);
+        for (int c0 = 16 * (warp >> 2); c0 < Npad; c0 += 64) {
+            float v[16];
             nn_tmem_ld16(tbase + (uint32_t)c0, v);
             for (int sg = 1; sg < nseg; ++sg) {
                 float w[16];
@@ -379,31 +388,32 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] += w[i];
             }
-        };
-        float m = -INFINITY;
-        for (int c0 = 0; c0 < Npad; c0 += 16) {
-            float v[16];
-            load16(c0, v);
+            if (row < nb) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (c0 + i < dm.dh) m = fmaxf(m, v[i] + sm.b[c0 + i]);
-        }
-        float ssum = 0.f;
-        for (int c0 = 0; c0 < Npad; c0 += 16) {
-            float v[16];
-            load16(c0, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (c0 + i < dm.dh) {
-                    const float e = expf(v[i] + sm.b[c0 + i] - m);
-                    ssum += e;
-                    if (row < nb) sm.H[row * dm.dh + c0 + i] = e;
-                }
+                for (int i = 0; i < 16; i += 4)
+                    if (c0 + i < dm.dh)
+                        *reinterpret_cast<float4*>(sm.H + row * dm.dh + c0 + i) =
+                            make_float4(v[i] + sm.b[c0 + i], v[i + 1] + sm.b[c0 + i + 1], v[i + 2] + sm.b[c0 + i + 2], v[i + 3] + sm.b[c0 + i + 3]);
             }
         }
-        const float inv = 1.0f / ssum;
-        if (row < nb) for (int k = 0; k < dm.dh; ++k) sm.H[row * dm.dh + k] *= inv;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    {
+        const int ncg = dm.dh >> 2;
+        const bool live = lane < ncg;
+        for (int row = warp; row < nb; row += NN_WARPS) {
+            float4 z = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (live) z = *reinterpret_cast<const float4*>(sm.H + row * dm.dh + 4 * lane);
+            float m = fmaxf(fmaxf(z.x, z.y), fmaxf(z.z, z.w));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) { e.x = expf(z.x - m); e.y = expf(z.y - m); e.z = expf(z.z - m); e.w = expf(z.w - m); }
+            const float inv = 1.0f / warp_sum(e.x + e.y + e.z + e.w);
+            if (live) *reinterpret_cast<float4*>(sm.H + row * dm.dh + 4 * lane) = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
+        }
+    }
     __syncthreads();
 }
 
@@ -566,6 +576,121 @@ __device__ void nn_stage5(const NNDims& dm, const NNSmem& sm, const float* __res
     }
 }
 
+
+constexpr int TC5_NT = 64;    // input columns (j) per S5 tile = MMA N
+constexpr int TC5_KH = 64;    // minibatch rows (K) per staging step
+
+// S5 on the tensor cores: GB[n][j] (+)= sum_r dZ1[r][n] X[row_r][j]  as  D[128 x 64] = dZ1^T[128 x K] * (X^T)[64 x K]^T per
+// tile of 64 inputs, K = minibatch rows in halves of 64, 3xTF32.  Up to 8 tiles (512 TMEM columns) accumulate before one
+// epilogue pass writes them out with 16-byte stores.  The A operand (dZ1^T, hi/lo) is re-staged from shared memory per
+// (tile group, K half); the B operand (X^T tile) is gathered from global memory with register prefetch.
+__device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb, bool first,
+                             float* __restrict__ GB, TcCtx& tc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int KG = TC5_KH / 4;                          // 16-byte K chunks per staging step
+    const int LBOA = NN_RB * 16;                        // A operand: 128 rows (hidden units, zero padded)
+    const int rowsB = TC5_NT + 1, LBOB = rowsB * 16;    // +1 row: the 4-byte scatter below is bank-conflict free
+    const int A_FLOATS = KG * NN_RB * 4, B_FLOATS = KG * rowsB * 4;
+    float* Ahi = sm.tile; float* Alo = Ahi + A_FLOATS; float* Bhi = Alo + A_FLOATS; float* Blo = Bhi + B_FLOATS;
+    const uint32_t idesc = nn_umma_idesc(NN_RB, TC5_NT);
+    const int ntiles = (dm.din + TC5_NT - 1) / TC5_NT;
+    const int halves = (nb + TC5_KH - 1) / TC5_KH;
+    // B staging: thread -> (row r of the half, float4 column jq): 64 x 16 = 1024 float4 = 2 per thread
+    const int sr = tid % TC5_KH, sq0 = tid / TC5_KH;     // jq = sq0 and sq0 + 8
+    float4 xv0, xv1;
+    auto prefetch = [&](int t, int h) {
+        const int r = h * TC5_KH + sr, j0 = t * TC5_NT;
+        xv0 = make_float4(0.f, 0.f, 0.f, 0.f); xv1 = xv0;
+        if (r < nb) {
+            const float* xrow = X + (size_t)sm.rows[r] * ld + j0;
+            if (j0 + 4 * sq0 < dm.din) xv0 = __ldg(reinterpret_cast<const float4*>(xrow + 4 * sq0));
+            if (j0 + 4 * (sq0 + 8) < dm.din) xv1 = __ldg(reinterpret_cast<const float4*>(xrow + 4 * (sq0 + 8)));
+        }
+    };
+    auto scatter = [&](const float4 v, int jq) {          // X[r][4jq..4jq+3] -> operand rows j = 4jq + i, chunk sr/4, slot sr%4
+        float4 hi, lo;
+        nn_split4(v, hi, lo);
+        const int base = ((sr >> 2) * rowsB + 4 * jq) * 4 + (sr & 3);
+        Bhi[base] = hi.x; Bhi[base + 4] = hi.y; Bhi[base + 8] = hi.z; Bhi[base + 12] = hi.w;
+        Blo[base] = lo.x; Blo[base + 4] = lo.y; Blo[base + 8] = lo.z; Blo[base + 12] = lo.w;
+    };
+    for (int t0 = 0; t0 < ntiles; t0 += 8) {
+        const int t1 = (t0 + 8 < ntiles) ? t0 + 8 : ntiles;
+        for (int h = 0; h < halves; ++h) {
+            prefetch(t0, h);
+            // every MMA issued so far has completed before the A operand is overwritten
+            if (tc.commits[0] > 0) nn_mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
+            __syncthreads();
+            for (int u = tid; u < NN_RB * KG; u += NN_THREADS) {   // A: (hidden unit n, chunk kg) <- dZ1[64h + 4kg .. +3][n]
+                const int n = u % NN_RB, kg = u / NN_RB;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+                if (n < dm.dh) {
+                    const int r = h * TC5_KH + 4 * kg;
+                    v.x = (r + 0 < nb) ? sm.dZ1[(r + 0) * dm.dh + n] : 0.f; v.y = (r + 1 < nb) ? sm.dZ1[(r + 1) * dm.dh + n] : 0.f;
+                    v.z = (r + 2 < nb) ? sm.dZ1[(r + 2) * dm.dh + n] : 0.f; v.w = (r + 3 < nb) ? sm.dZ1[(r + 3) * dm.dh + n] : 0.f;
+                }
+                nn_split4(v, hi, lo);
+                *reinterpret_cast<float4*>(Ahi + (kg * NN_RB + n) * 4) = hi;
+                *reinterpret_cast<float4*>(Alo + (kg * NN_RB + n) * 4) = lo;
+            }
+            for (int t = t0; t < t1; ++t) {
+                // the MMAs of the previous tile read the B buffer
+                if (t > t0 && tc.commits[0] > 0) nn_mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
+                scatter(xv0, sq0);
+                scatter(xv1, sq0 + 8);
+                if (t + 1 < t1) prefetch(t + 1, h);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = nn_smem_u32(Ahi), a_lo = nn_smem_u32(Alo), b_hi = nn_smem_u32(Bhi), b_lo = nn_smem_u32(Blo);
+                    const uint32_t td = tc.tmem + (uint32_t)((t - t0) * TC5_NT);
+#pragma unroll
+                    for (int k8 = 0; k8 < TC5_KH / 8; ++k8) {
+                        const uint32_t ao = (uint32_t)(2 * k8) * LBOA, bo = (uint32_t)(2 * k8) * LBOB;
+                        const bool acc0 = (h > 0) || (k8 > 0);
+                        nn_umma_tf32(td, nn_umma_desc(a_hi + ao, LBOA), nn_umma_desc(b_hi + bo, LBOB), idesc, acc0);
+                        nn_umma_tf32(td, nn_umma_desc(a_hi + ao, LBOA), nn_umma_desc(b_lo + bo, LBOB), idesc, true);
+                        nn_umma_tf32(td, nn_umma_desc(a_lo + ao, LBOA), nn_umma_desc(b_hi + bo, LBOB), idesc, true);
+                    }
+                    nn_umma_commit(tc.bar[0]);
+                }
+                tc.commits[0] += 1;
+            }
+        }
+        // ---- epilogue of the group: TMEM lane = hidden unit n, columns = inputs of the group's tiles; all 16 warps
+        // (warp w reads lanes 32 (w % 4) .. +31, the tiles w / 4, w / 4 + 4 of the group)
+        nn_mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const int q = warp & 3, n = 32 * q + lane;
+            const uint32_t tbase = tc.tmem + ((uint32_t)(32 * q) << 16);
+            for (int t = t0 + (warp >> 2); t < t1; t += 4) {
+                for (int c0 = 0; c0 < TC5_NT; c0 += 16) {
+                    float v[16];
+                    nn_tmem_ld16(tbase + (uint32_t)((t - t0) * TC5_NT + c0), v);
+                    const int j = t * TC5_NT + c0;
+                    if (n < dm.dh && j < dm.din) {   // din is a multiple of 4, so float4 groups are all-or-nothing
+                        float* dst = GB + (size_t)n * dm.din + j;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            if (j + 4 * q4 < dm.din) {
+                                float4 o = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                                float4* d4 = reinterpret_cast<float4*>(dst + 4 * q4);
+                                if (!first) { const float4 pv = *d4; o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w; }
+                                *d4 = o;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+}
+
 enum : int { NEED_A = 1, NEED_B = 2, NEED_a = 4, NEED_b = 8, NEED_ALL = 15 };
 
 // One gradient evaluation of the log-likelihood SUM over the minibatch at `th`, for the tensors in
@@ -596,7 +721,7 @@ __device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __rest
         NN_TICK(2)
         if (need & (NEED_b | NEED_B)) nn_stage4(dm, sm, nb, first, Gout + dm.offb);
         NN_TICK(3)
-        if (need & NEED_B) nn_stage5(dm, sm, X, ld, nb, first, Gout + dm.offB);
+        if (need & NEED_B) nn_stage5_tc(dm, sm, X, ld, nb, first, Gout + dm.offB, tc);
         NN_TICK(4)
     }
     if (need & (NEED_A | NEED_a)) {
@@ -628,6 +753,14 @@ __device__ __forceinline__ float nn_prior_grad(const NNDims& dm, const float* __
     int lo, hi;
     nn_tensor_range(dm, t - 4, lo, hi);
     return (float)(hi - lo) / (2.0f * th[e]) - 0.5f * ssq - 1.0f;
+}
+
+// operand staging region: max(S1: two stages of A hi/lo [4][128] + B hi/lo [4][Npad+2] chunks, S5: A hi/lo [16][128] + B hi/lo [16][65])
+__host__ __device__ inline int nn_tile_floats(const NNDims& dm) {
+    const int Npad = (dm.dh + 15) & ~15;
+    const int s1 = 2 * (2 * (16 / 4) * NN_RB * 4 + 2 * (16 / 4) * (Npad + 2) * 4);
+    const int s5 = 2 * (64 / 4) * NN_RB * 4 + 2 * (64 / 4) * 65 * 4;
+    return s1 > s5 ? s1 : s5;
 }
 
 struct NNChainState {
@@ -744,8 +877,8 @@ __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
     sm.A = p; p += dm.dh * dm.dop;
     sm.a = p; p += NN_MAXO;
     sm.b = p; p += NN_MAXH;
-    const int t1 = 2 * (NN_KC * (NN_RB + 4) + NN_KC * dm.dh), t5 = 2 * NN_RB * NN_JT;   // double-buffered
-    sm.tile = p; p += (t1 > t5 ? t1 : t5);
+    const int t1 = nn_tile_floats(dm);
+    sm.tile = p; p += t1;
     sm.gb = p; p += NN_WARPS * dm.dh;
     sm.gA = p; p += dm.dh * dm.dop;
     sm.ga = p; p += NN_MAXO;
@@ -756,8 +889,8 @@ __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
 }
 
 static size_t nn_smem_bytes(const NNDims& dm) {
-    const int t1 = 2 * (NN_KC * (NN_RB + 4) + NN_KC * dm.dh), t5 = 2 * NN_RB * NN_JT;
-    size_t f = (size_t)2 * NN_RB * dm.dh + NN_RB * dm.dop + dm.dh * dm.dop + NN_MAXO + NN_MAXH + (t1 > t5 ? t1 : t5) +
+    const int t1 = nn_tile_floats(dm);
+    size_t f = (size_t)2 * NN_RB * dm.dh + NN_RB * dm.dop + dm.dh * dm.dop + NN_MAXO + NN_MAXH + t1 +
                NN_WARPS * dm.dh + dm.dh * dm.dop + NN_MAXO + 64 + NN_RB + 4 + 4;
     return f * sizeof(float);
 }
