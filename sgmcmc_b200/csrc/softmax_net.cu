@@ -78,6 +78,7 @@ struct NNSmem {
     float* dZ1;   // [NN_RB][dh]
     float* dZ2;   // [NN_RB][dop]
     float* A;     // [dh][dop] (zero padded)
+    float* At;    // [dop][dh] transposed copy (stage 4 reads it with conflict-free float4 loads)
     float* a;     // [dop]
     float* b;     // [dh]
     float* tile;  // max(S1 tiles, S5 tile)
@@ -105,7 +106,9 @@ __device__ __forceinline__ float nn_block_sum(float v, float* red) {
 __device__ void nn_load_small(const NNDims& dm, const NNSmem& sm, const float* __restrict__ th) {
     for (int i = threadIdx.x; i < dm.dh * dm.dop; i += NN_THREADS) {
         const int k = i / dm.dop, l = i % dm.dop;
-        sm.A[i] = (l < dm.dout) ? th[dm.offA + k + dm.dh * l] : 0.f;
+        const float av = (l < dm.dout) ? th[dm.offA + k + dm.dh * l] : 0.f;
+        sm.A[i] = av;
+        sm.At[l * dm.dh + k] = av;
     }
     for (int i = threadIdx.x; i < dm.dop; i += NN_THREADS) sm.a[i] = (i < dm.dout) ? th[dm.offa + i] : 0.f;
     for (int i = threadIdx.x; i < dm.dh; i += NN_THREADS) sm.b[i] = th[dm.offb + i];
@@ -220,6 +223,12 @@ __device__ __forceinline__ void nn_umma_tf32(uint32_t tmem_d, uint64_t adesc, ui
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
 }
+// one lane of a fully converged warp (the MMA issuer): ptxas keeps warp-uniform operands in uniform registers around elect.sync
+__device__ __forceinline__ bool nn_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void nn_umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -240,9 +249,9 @@ __device__ __forceinline__ void nn_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // float32 -> (hi, lo), both rounded to nearest TF32 (cvt.rna): hi*hi' + hi*lo' + lo*hi' recovers float32-level
 // products with unbiased errors (a truncating split leaves same-signed residuals that add up coherently over K)
 __device__ __forceinline__ float nn_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    // round to nearest (ties away) on the 13 dropped mantissa bits == cvt.rna.tf32.f32, but on the integer pipe
+    // (the conversion instruction issues at a fraction of the ALU rate and the split runs once per staged element)
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void nn_split4(const float4 x, float4& hi, float4& lo) {
     hi.x = nn_tf32(x.x); hi.y = nn_tf32(x.y); hi.z = nn_tf32(x.z); hi.w = nn_tf32(x.w);
@@ -324,14 +333,25 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
         return pr;
     };
     Pre p0 = fetch(0), p1 = fetch(1), p2 = fetch(2);
-    for (int c = 0; c < nchunks; ++c) {
+    // shared-memory descriptors of stage 0 (stage 1 = + STAGE bytes in the address field, which counts 16-byte units)
+    uint64_t d_ahi[TC_KC / 8], d_alo[TC_KC / 8], d_bhi[TC_KC / 8], d_blo[TC_KC / 8];
+    {
+        const uint32_t a_hi = nn_smem_u32(sm.tile), a_lo = a_hi + A_FLOATS * 4, b_hi = a_hi + 2 * A_FLOATS * 4, b_lo = b_hi + B_FLOATS * 4;
+#pragma unroll
+        for (int k8 = 0; k8 < TC_KC / 8; ++k8) {
+            d_ahi[k8] = nn_umma_desc(a_hi + (uint32_t)(2 * k8) * LBOA, LBOA); d_alo[k8] = nn_umma_desc(a_lo + (uint32_t)(2 * k8) * LBOA, LBOA);
+            d_bhi[k8] = nn_umma_desc(b_hi + (uint32_t)(2 * k8) * LBOB, LBOB); d_blo[k8] = nn_umma_desc(b_lo + (uint32_t)(2 * k8) * LBOB, LBOB);
+        }
+    }
+    const uint32_t stage_step = (uint32_t)(STAGE * 4) >> 4;
+    auto do_chunk = [&](int c, Pre& pr) {
         const int buf = c & 1;
         float* stage = sm.tile + buf * STAGE;
         // the MMAs that read this buffer two chunks ago must have completed
         if (tc.commits[buf] > 0) nn_mbar_wait(tc.bar[buf], (tc.commits[buf] - 1u) & 1u);
         {
             float4 hi, lo;
-            const float4 xv = p0.x, bv0 = p0.b0, bv1 = p0.b1;
+            const float4 xv = pr.x, bv0 = pr.b0, bv1 = pr.b1;
             if (xkg < KG) {   // A operand: X rows
                 nn_split4(xv, hi, lo);
                 *reinterpret_cast<float4*>(stage + (xkg * NN_RB + xr) * 4) = hi;
@@ -348,32 +368,39 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
                 *reinterpret_cast<float4*>(stage + 2 * A_FLOATS + B_FLOATS + ((bt1 % KG) * rowsB + bt1 / KG) * 4) = lo;
             }
         }
-        p0 = p1; p1 = p2; p2 = fetch(c + 3);
+        pr = fetch(c + 3);   // refill the SAME registers (no rotation moves: a move of an in-flight load result would stall on it)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && nn_elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = nn_smem_u32(stage), a_lo = a_hi + A_FLOATS * 4, b_hi = a_hi + 2 * A_FLOATS * 4, b_lo = b_hi + B_FLOATS * 4;
-#pragma unroll
             const int seg = c / seg_chunks;
             const uint32_t td = tc.tmem + (uint32_t)(seg * Npad);
+            const bool fresh = (c % seg_chunks) == 0;
+#pragma unroll
             for (int k8 = 0; k8 < TC_KC / 8; ++k8) {
-                const uint32_t ao = (uint32_t)(2 * k8) * LBOA, bo = (uint32_t)(2 * k8) * LBOB;
-                const bool acc0 = (c % seg_chunks > 0) || (k8 > 0);
-                nn_umma_tf32(td, nn_umma_desc(a_hi + ao, LBOA), nn_umma_desc(b_hi + bo, LBOB), idesc, acc0);
-                nn_umma_tf32(td, nn_umma_desc(a_hi + ao, LBOA), nn_umma_desc(b_lo + bo, LBOB), idesc, true);
-                nn_umma_tf32(td, nn_umma_desc(a_lo + ao, LBOA), nn_umma_desc(b_hi + bo, LBOB), idesc, true);
+                // descriptors were built once before the loop: only the buffer's base differs (added to the 14-bit address field)
+                const uint64_t bo = (uint64_t)(buf ? stage_step : 0u);
+                nn_umma_tf32(td, d_ahi[k8] + bo, d_bhi[k8] + bo, idesc, !(fresh && k8 == 0));
+                nn_umma_tf32(td, d_ahi[k8] + bo, d_blo[k8] + bo, idesc, true);
+                nn_umma_tf32(td, d_alo[k8] + bo, d_bhi[k8] + bo, idesc, true);
             }
             nn_umma_commit(tc.bar[buf]);
         }
         tc.commits[buf] += 1;
+    };
+    for (int c = 0; c < nchunks; c += 3) {
+        do_chunk(c, p0);
+        if (c + 1 < nchunks) do_chunk(c + 1, p1);
+        if (c + 2 < nchunks) do_chunk(c + 2, p2);
     }
+    NN_TICK(8)    // S1: staging loop
     // all MMAs complete in order: wait for the last commit of each buffer
 #pragma unroll
     for (int b2 = 0; b2 < 2; ++b2)
         if (tc.commits[b2] > 0) nn_mbar_wait(tc.bar[b2], (tc.commits[b2] - 1u) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    NN_TICK(9)    // S1: drain
     // epilogue, all 16 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (= rows) for the 16-column groups w / 4, w / 4 + 4, ...,
     // sums the K segments in registers, adds the bias and parks Z1 in sm.H; then one warp per row does the softmax in place
     {
@@ -494,8 +521,8 @@ __device__ void nn_stage4(const NNDims& dm, const NNSmem& sm, int nb, bool first
             h = *reinterpret_cast<const float4*>(sm.H + r * dm.dh + 4 * lane);
             for (int l = 0; l < dm.dout; ++l) {
                 const float dz = sm.dZ2[r * dm.dop + l];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) dh[c] += dz * sm.A[(4 * lane + c) * dm.dop + l];
+                const float4 av = *reinterpret_cast<const float4*>(sm.At + l * dm.dh + 4 * lane);
+                dh[0] = fmaf(dz, av.x, dh[0]); dh[1] = fmaf(dz, av.y, dh[1]); dh[2] = fmaf(dz, av.z, dh[2]); dh[3] = fmaf(dz, av.w, dh[3]);
             }
         }
         const float s = warp_sum(dh[0] * h.x + dh[1] * h.y + dh[2] * h.z + dh[3] * h.w);
@@ -614,6 +641,12 @@ __device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __
         Bhi[base] = hi.x; Bhi[base + 4] = hi.y; Bhi[base + 8] = hi.z; Bhi[base + 12] = hi.w;
         Blo[base] = lo.x; Blo[base + 4] = lo.y; Blo[base + 8] = lo.z; Blo[base + 12] = lo.w;
     };
+    uint64_t e_ahi[TC5_KH / 8], e_alo[TC5_KH / 8], e_bhi[TC5_KH / 8], e_blo[TC5_KH / 8];
+#pragma unroll
+    for (int k8 = 0; k8 < TC5_KH / 8; ++k8) {
+        e_ahi[k8] = nn_umma_desc(nn_smem_u32(Ahi) + (uint32_t)(2 * k8) * LBOA, LBOA); e_alo[k8] = nn_umma_desc(nn_smem_u32(Alo) + (uint32_t)(2 * k8) * LBOA, LBOA);
+        e_bhi[k8] = nn_umma_desc(nn_smem_u32(Bhi) + (uint32_t)(2 * k8) * LBOB, LBOB); e_blo[k8] = nn_umma_desc(nn_smem_u32(Blo) + (uint32_t)(2 * k8) * LBOB, LBOB);
+    }
     for (int t0 = 0; t0 < ntiles; t0 += 8) {
         const int t1 = (t0 + 8 < ntiles) ? t0 + 8 : ntiles;
         for (int h = 0; h < halves; ++h) {
@@ -642,17 +675,14 @@ __device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
-                if (tid == 0) {
+                if (warp == 0 && nn_elect_one()) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi = nn_smem_u32(Ahi), a_lo = nn_smem_u32(Alo), b_hi = nn_smem_u32(Bhi), b_lo = nn_smem_u32(Blo);
                     const uint32_t td = tc.tmem + (uint32_t)((t - t0) * TC5_NT);
 #pragma unroll
                     for (int k8 = 0; k8 < TC5_KH / 8; ++k8) {
-                        const uint32_t ao = (uint32_t)(2 * k8) * LBOA, bo = (uint32_t)(2 * k8) * LBOB;
-                        const bool acc0 = (h > 0) || (k8 > 0);
-                        nn_umma_tf32(td, nn_umma_desc(a_hi + ao, LBOA), nn_umma_desc(b_hi + bo, LBOB), idesc, acc0);
-                        nn_umma_tf32(td, nn_umma_desc(a_hi + ao, LBOA), nn_umma_desc(b_lo + bo, LBOB), idesc, true);
-                        nn_umma_tf32(td, nn_umma_desc(a_lo + ao, LBOA), nn_umma_desc(b_hi + bo, LBOB), idesc, true);
+                        nn_umma_tf32(td, e_ahi[k8], e_bhi[k8], idesc, (h > 0) || (k8 > 0));
+                        nn_umma_tf32(td, e_ahi[k8], e_blo[k8], idesc, true);
+                        nn_umma_tf32(td, e_alo[k8], e_bhi[k8], idesc, true);
                     }
                     nn_umma_commit(tc.bar[0]);
                 }
@@ -875,6 +905,7 @@ __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
     sm.dZ1 = p; p += NN_RB * dm.dh;
     sm.dZ2 = p; p += NN_RB * dm.dop;
     sm.A = p; p += dm.dh * dm.dop;
+    sm.At = p; p += dm.dop * dm.dh;
     sm.a = p; p += NN_MAXO;
     sm.b = p; p += NN_MAXH;
     const int t1 = nn_tile_floats(dm);
@@ -890,7 +921,7 @@ __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
 
 static size_t nn_smem_bytes(const NNDims& dm) {
     const int t1 = nn_tile_floats(dm);
-    size_t f = (size_t)2 * NN_RB * dm.dh + NN_RB * dm.dop + dm.dh * dm.dop + NN_MAXO + NN_MAXH + t1 +
+    size_t f = (size_t)2 * NN_RB * dm.dh + NN_RB * dm.dop + 2 * dm.dh * dm.dop + NN_MAXO + NN_MAXH + t1 +
                NN_WARPS * dm.dh + dm.dh * dm.dop + NN_MAXO + 64 + NN_RB + 4 + 4;
     return f * sizeof(float);
 }

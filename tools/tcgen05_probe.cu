@@ -23,7 +23,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t rows) {
     return d;
 }
 
-__global__ void __launch_bounds__(128, 1) probe(const float* A, const float* B, float* D, int split) {
+__global__ void __launch_bounds__(128, 1) probe(const float* A, const float* B, float* D, int split, int reps, long long* cycles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* Ahi = reinterpret_cast<float*>(smem);        // [K/4][M][4]
     float* Alo = Ahi + M * K;
@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(128, 1) probe(const float* A, const float* B, 
     if (tid == 0) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
         int first = 1;
+        const long long t_start = clock64();
+        for (int rep = 0; rep < reps; ++rep)
         for (int k8 = 0; k8 < K / 8; ++k8) {
             const uint32_t aoff = (uint32_t)(2 * k8) * (M * 16), boff = (uint32_t)(2 * k8) * (N * 16);
             const uint64_t ahi = make_desc(smem_u32(Ahi) + aoff, M), alo = make_desc(smem_u32(Alo) + aoff, M);
@@ -77,6 +79,10 @@ __global__ void __launch_bounds__(128, 1) probe(const float* A, const float* B, 
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        const long long t_issued = clock64();
+        asm volatile("{\n\t.reg .pred p;\n\tW2_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D2_%=;\n\tbra W2_%=;\n\tD2_%=:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
+        const long long t_done = clock64();
+        if (cycles) { cycles[0] = t_issued - t_start; cycles[1] = t_done - t_start; }
     }
     // everybody waits for the MMAs
     asm volatile(
@@ -112,7 +118,7 @@ int main() {
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int split = 0; split < 2; ++split) {
         cudaMemset(dD, 0, D.size() * 4);
-        probe<<<1, 128, smem>>>(dA, dB, dD, split);
+        probe<<<1, 128, smem>>>(dA, dB, dD, split, 1, nullptr);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
         cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
@@ -124,6 +130,14 @@ int main() {
                 maxerr = fmax(maxerr, fabs(r - D[m * N + n])); maxref = fmax(maxref, fabs(r));
             }
         printf("split=%d  max|err|=%.3e  max|ref|=%.3e  rel=%.3e\n", split, maxerr, maxref, maxerr / maxref);
+    }
+    long long* dc; cudaMalloc(&dc, 16);
+    for (int reps : {1, 8, 64}) {
+        probe<<<1, 128, smem>>>(dA, dB, dD, 1, reps, dc);
+        cudaDeviceSynchronize();
+        long long hc[2]; cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost);
+        const int mmas = reps * (K / 8) * 3;
+        printf("reps=%d: %d MMAs (128x%dx8 tf32): issue %lld cycles (%.1f / MMA), done %lld cycles (%.1f / MMA)\n", reps, mmas, N, hc[0], (double)hc[0] / mmas, hc[1], (double)hc[1] / mmas);
     }
     return 0;
 }
