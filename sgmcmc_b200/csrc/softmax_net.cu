@@ -22,6 +22,9 @@
 // consecutive internal elements) when drawn on the device, by flat index when supplied.
 #include "softmax_net.cuh"
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda.h>   // CUtensorMap
 
 namespace sgm {
 
@@ -54,6 +57,18 @@ struct SoftmaxNetWork {
     float* part = nullptr;   // full-gradient partials
     size_t part_cap = 0;
     size_t smem = 0;
+    // TMA descriptors, encoded on first use and cached by (base pointer, extent, stride)
+    struct MapEntry { const void* base; long long rows; long long stride; CUtensorMap map; };
+    MapEntry maps[8];
+    int n_maps = 0;
+};
+
+// TMA descriptors of one gradient evaluation: the dataset (rows gathered four at a time) and the parameter array that
+// holds this evaluation's B (3-D: input, hidden unit, chain); x == nullptr selects the register-staged path
+struct NNMaps {
+    const CUtensorMap* x;
+    const CUtensorMap* b;
+    int bcoord;
 };
 
 // internal element order == flat (ABI) order: every tensor in R's column-major element order (A[k + dh*l], B[j + din*n])
@@ -82,6 +97,9 @@ struct NNSmem {
     float* a;     // [dop]
     float* b;     // [dh]
     float* tile;  // max(S1 tiles, S5 tile)
+    uint32_t ring;      // shared-space address (1024-byte aligned) of the H | dZ1 | tile region = the S1 operand ring
+    uint32_t ring_bytes;
+    uint64_t* s1_bars;  // [16] barriers of the S1 pipeline
     float* gb;    // [NN_WARPS][dh] partial column sums
     float* gA;    // [dh*dop] gradient of A (row block accumulation)
     float* ga;    // [dop]
@@ -102,16 +120,21 @@ __device__ __forceinline__ float nn_block_sum(float v, float* red) {
     return red[32];
 }
 
-// load A (padded), a, b of one parameter vector into shared memory
-__device__ void nn_load_small(const NNDims& dm, const NNSmem& sm, const float* __restrict__ th) {
-    for (int i = threadIdx.x; i < dm.dh * dm.dop; i += NN_THREADS) {
-        const int k = i / dm.dop, l = i % dm.dop;
-        const float av = (l < dm.dout) ? th[dm.offA + k + dm.dh * l] : 0.f;
-        sm.A[i] = av;
-        sm.At[l * dm.dh + k] = av;
-    }
-    for (int i = threadIdx.x; i < dm.dop; i += NN_THREADS) sm.a[i] = (i < dm.dout) ? th[dm.offa + i] : 0.f;
-    for (int i = threadIdx.x; i < dm.dh; i += NN_THREADS) sm.b[i] = th[dm.offb + i];
+// load A (padded), a, b of one parameter vector into shared memory; `which` selects the tensors that changed since the last
+// load (bit 0: A, bit 1: a, bit 2: b) -- inside a Gauss-Seidel sub-step only one small tensor moves between evaluations
+enum : int { LOAD_A = 1, LOAD_a = 2, LOAD_b = 4, LOAD_ALL = 7 };
+__device__ void nn_load_small(const NNDims& dm, const NNSmem& sm, const float* __restrict__ th, int which = LOAD_ALL) {
+    if (which & LOAD_A)
+        for (int i = threadIdx.x; i < dm.dh * dm.dop; i += NN_THREADS) {
+            const int l = i / dm.dh, k = i % dm.dh;   // coalesced over k (A is stored [k + dh * l])
+            const float av = (l < dm.dout) ? th[dm.offA + k + dm.dh * l] : 0.f;
+            sm.A[k * dm.dop + l] = av;
+            sm.At[l * dm.dh + k] = av;
+        }
+    if (which & LOAD_a)
+        for (int i = threadIdx.x; i < dm.dop; i += NN_THREADS) sm.a[i] = (i < dm.dout) ? th[dm.offa + i] : 0.f;
+    if (which & LOAD_b)
+        for (int i = threadIdx.x; i < dm.dh; i += NN_THREADS) sm.b[i] = th[dm.offb + i];
     __syncthreads();
 }
 
@@ -282,6 +305,53 @@ __device__ void nn_tc_fini(const TcCtx& tc) {
     if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "n"(512));
 }
 
+// S1 epilogue, shared by the register-staged and the TMA-fed pipelines: TMEM -> registers (K segments summed), + bias -> sm.H,
+// then the row softmax in place
+__device__ void nn_stage1_epilogue(const NNDims& dm, const NNSmem& sm, int nb, const TcCtx& tc, int nseg, int Npad) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // epilogue, all 16 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (= rows) for the 16-column groups w / 4, w / 4 + 4, ...,
+    // sums the K segments in registers, adds the bias and parks Z1 in sm.H; then one warp per row does the softmax in place
+    {
+        const int q = warp & 3, row = 32 * q + lane;
+        const uint32_t tbase = tc.tmem + ((uint32_t)(32 * q) << 16);
+        for (int c0 = 16 * (warp >> 2); c0 < Npad; c0 += 64) {
+            float v[16];
+            nn_tmem_ld16(tbase + (uint32_t)c0, v);
+            for (int sg = 1; sg < nseg; ++sg) {
+                float w[16];
+                nn_tmem_ld16(tbase + (uint32_t)(sg * Npad + c0), w);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += w[i];
+            }
+            if (row < nb) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    if (c0 + i < dm.dh)
+                        *reinterpret_cast<float4*>(sm.H + row * dm.dh + c0 + i) =
+                            make_float4(v[i] + sm.b[c0 + i], v[i + 1] + sm.b[c0 + i + 1], v[i + 2] + sm.b[c0 + i + 2], v[i + 3] + sm.b[c0 + i + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    {
+        const int ncg = dm.dh >> 2;
+        const bool live = lane < ncg;
+        for (int row = warp; row < nb; row += NN_WARPS) {
+            float4 z = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (live) z = *reinterpret_cast<const float4*>(sm.H + row * dm.dh + 4 * lane);
+            float m = fmaxf(fmaxf(z.x, z.y), fmaxf(z.z, z.w));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) { e.x = expf(z.x - m); e.y = expf(z.y - m); e.z = expf(z.z - m); e.w = expf(z.w - m); }
+            const float inv = 1.0f / warp_sum(e.x + e.y + e.z + e.w);
+            if (live) *reinterpret_cast<float4*>(sm.H + row * dm.dh + 4 * lane) = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
+        }
+    }
+    __syncthreads();
+}
+
 constexpr int TC_KC = 16;   // K per operand stage of S1 (two k8 MMAs x three split terms)
 constexpr int TC_SEG = 4;   // K is cut into TC_SEG segments with separate TMEM accumulators, summed in registers: the tensor
                             // core's float32 accumulation truncates, and the bias grows with the number of accumulation steps
@@ -401,47 +471,148 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
         if (tc.commits[b2] > 0) nn_mbar_wait(tc.bar[b2], (tc.commits[b2] - 1u) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     NN_TICK(9)    // S1: drain
-    // epilogue, all 16 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (= rows) for the 16-column groups w / 4, w / 4 + 4, ...,
-    // sums the K segments in registers, adds the bias and parks Z1 in sm.H; then one warp per row does the softmax in place
-    {
-        const int q = warp & 3, row = 32 * q + lane;
-        const uint32_t tbase = tc.tmem + ((uint32_t)(32 * q) << 16);
-        for (int c0 = 16 * (warp >> 2); c0 < Npad; c0 += 64) {
-            float v[16];
-            nn_tmem_ld16(tbase + (uint32_t)c0, v);
-            for (int sg = 1; sg < nseg; ++sg) {
-                float w[16];
-                nn_tmem_ld16(tbase + (uint32_t)(sg * Npad + c0), w);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += w[i];
+    nn_stage1_epilogue(dm, sm, nb, tc, nseg, Npad);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// S1, TMA-fed: no operand byte passes through a register before it is in shared memory.
+//   warp 14 (producer): per K chunk of 32 inputs, TMA tile::gather4 requests bring the minibatch rows' 128-byte segments (four rows
+//            per request) and one 3-D box brings B[0..dh)[j0..j0+32) of this chain, both written with the 128-byte swizzle the
+//            tensor core reads (K-major SW128), completion counted on the stage's mbarrier;
+//   warps 0..13 (converters): round the raw stage to TF32 in place (= hi operands) and write the residuals to a lo stage of the
+//            same layout (element-wise, so the swizzle never has to be computed), then fence to the async proxy;
+//   warp 15 (issuer): 4 x (hi*hi + hi*lo + lo*hi) tcgen05.mma per stage, commits release the raw and the lo stage.
+// The register-staged version of this loop paid one global-memory latency per chunk: ptxas drains every outstanding load at
+// fence.proxy.async (profiles/r01_c4_s1_scoreboard.txt).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nn_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void nn_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nn_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void nn_tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+                 : "memory");
+}
+__device__ __forceinline__ void nn_tma_box3(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// K-major operand descriptor, 128-byte swizzle: rows are 128 bytes, 8-row groups 1024 bytes apart (SBO); a K step of 8 TF32
+// advances the start address by 32 bytes inside the swizzle span
+__device__ __forceinline__ uint64_t nn_umma_desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ float4 nn_lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void nn_sts128(uint32_t addr, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// S1 operand ring (TMA path): raw stages (X 128 rows x 128 B | B round8(dh) rows x 128 B, 128-byte swizzle) and lo stages of the
+// same shape; the tensor core reads Npad = round16(dh) rows of B, i.e. up to 1 KB past a stage (garbage in, ignored columns out)
+constexpr int S1_KC = 32;       // floats per operand row per stage = one 128-byte swizzle span
+constexpr int S1_NRAW = 4;      // raw stages in flight (TMA destinations; rounded to TF32 in place = the hi operands)
+constexpr int S1_NLO = 2;       // lo stages
+__host__ __device__ inline int nn_s1_stage_bytes(const NNDims& dm) { return NN_RB * 128 + ((dm.dh + 7) / 8) * 1024; }
+__host__ __device__ inline int nn_s1_ring_bytes(const NNDims& dm) { return (S1_NRAW + S1_NLO) * nn_s1_stage_bytes(dm) + 2048; }
+
+constexpr int S1_CONV_WARPS = NN_WARPS - 2;
+
+__device__ void nn_stage1_tma(const NNDims& dm, const NNSmem& sm, const NNMaps& mp, int nb, TcCtx& tc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Npad = (dm.dh + 15) & ~15;
+    const uint32_t XB = NN_RB * 128u, BB = (uint32_t)((dm.dh + 7) / 8) * 1024u, STG = XB + BB;
+    const int nchunks = (dm.din + S1_KC - 1) / S1_KC;
+    const int seg_chunks = (nchunks + TC_SEG - 1) / TC_SEG;
+    const int nseg = (nchunks + seg_chunks - 1) / seg_chunks;
+    const uint32_t raw0 = sm.ring, lo0 = sm.ring + S1_NRAW * STG;
+    // barriers: full[S1_NRAW] | rawfree[S1_NRAW] | conv[S1_NLO] | lofree[S1_NLO] | done
+    const uint32_t bars = nn_smem_u32(sm.s1_bars);
+    const uint32_t b_full = bars, b_rawfree = bars + 8 * S1_NRAW, b_conv = bars + 16 * S1_NRAW, b_lofree = b_conv + 8 * S1_NLO, b_done = b_lofree + 8 * S1_NLO;
+    asm volatile("fence.proxy.async.global;" ::: "memory");   // this CTA's parameter updates (generic proxy) -> the TMA reads below
+    __syncthreads();   // the previous users of H | dZ1 | tile are done
+    if (tid == 0) {
+        for (int s = 0; s < S1_NRAW; ++s) { nn_mbar_init(b_full + 8 * s, 1); nn_mbar_init(b_rawfree + 8 * s, 1); }
+        for (int l = 0; l < S1_NLO; ++l) { nn_mbar_init(b_conv + 8 * l, S1_CONV_WARPS); nn_mbar_init(b_lofree + 8 * l, 1); }
+        nn_mbar_init(b_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == NN_WARPS - 2) {
+        // ---- producer
+        const int ngroups = (nb + 3) >> 2;
+        const uint32_t tx = (uint32_t)ngroups * 512u + (uint32_t)dm.dh * 128u;
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % S1_NRAW;
+            if (c >= S1_NRAW) nn_mbar_wait(b_rawfree + 8 * s, (uint32_t)((c / S1_NRAW) - 1) & 1u);
+            const uint32_t dst = raw0 + (uint32_t)s * STG, bar = b_full + 8 * s;
+            if (lane == 0) nn_mbar_expect_tx(bar, tx);
+            __syncwarp();
+            for (int g = lane; g < ngroups; g += 32) {
+                const int r = 4 * g;
+                nn_tma_gather4(dst + (uint32_t)g * 512u, mp.x, c * S1_KC, sm.rows[r], sm.rows[r + 1 < nb ? r + 1 : 0], sm.rows[r + 2 < nb ? r + 2 : 0],
+                               sm.rows[r + 3 < nb ? r + 3 : 0], bar);
             }
-            if (row < nb) {
+            if (lane == 31) nn_tma_box3(dst + XB, mp.b, c * S1_KC, 0, mp.bcoord, bar);
+        }
+    } else if (warp == NN_WARPS - 1) {
+        // ---- MMA issuer
+        const uint32_t idesc = nn_umma_idesc(NN_RB, Npad);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % S1_NRAW, l = c % S1_NLO;
+            nn_mbar_wait(b_conv + 8 * l, (uint32_t)(c / S1_NLO) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (nn_elect_one()) {
+                const uint32_t td = tc.tmem + (uint32_t)((c / seg_chunks) * Npad);
+                const bool fresh = (c % seg_chunks) == 0;
+                const uint64_t ahi = nn_umma_desc_sw128(raw0 + (uint32_t)s * STG), bhi = nn_umma_desc_sw128(raw0 + (uint32_t)s * STG + XB);
+                const uint64_t alo = nn_umma_desc_sw128(lo0 + (uint32_t)l * STG), blo = nn_umma_desc_sw128(lo0 + (uint32_t)l * STG + XB);
 #pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                    if (c0 + i < dm.dh)
-                        *reinterpret_cast<float4*>(sm.H + row * dm.dh + c0 + i) =
-                            make_float4(v[i] + sm.b[c0 + i], v[i + 1] + sm.b[c0 + i + 1], v[i + 2] + sm.b[c0 + i + 2], v[i + 3] + sm.b[c0 + i + 3]);
+                for (int k8 = 0; k8 < S1_KC / 8; ++k8) {
+                    const uint64_t ko = (uint64_t)(2 * k8);   // 32 bytes per K step, in 16-byte units
+                    nn_umma_tf32(td, ahi + ko, bhi + ko, idesc, !(fresh && k8 == 0));
+                    nn_umma_tf32(td, ahi + ko, blo + ko, idesc, true);
+                    nn_umma_tf32(td, alo + ko, bhi + ko, idesc, true);
+                }
+                nn_umma_commit(b_rawfree + 8 * s);
+                nn_umma_commit(b_lofree + 8 * l);
+                if (c == nchunks - 1) nn_umma_commit(b_done);
             }
+            __syncwarp();
+        }
+    } else {
+        // ---- converters: hi = rna_tf32(x) in place, lo = rna_tf32(x - hi) at the same offset of the lo stage
+        const int nvec = (int)(STG >> 4);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % S1_NRAW, l = c % S1_NLO;
+            const uint32_t raw = raw0 + (uint32_t)s * STG, lo = lo0 + (uint32_t)l * STG;
+            const bool prof = nn_prof && tid == 0;   // sub-counters of the S1 slot: wait for the lo stage (MMA pace) / for the loads
+            long long t0 = prof ? clock64() : 0;
+            if (c >= S1_NLO) nn_mbar_wait(b_lofree + 8 * l, (uint32_t)((c / S1_NLO) - 1) & 1u);
+            if (prof) { const long long t1 = clock64(); atomicAdd(nn_prof + 9, (unsigned long long)(t1 - t0)); t0 = t1; }
+            nn_mbar_wait(b_full + 8 * s, (uint32_t)(c / S1_NRAW) & 1u);
+            if (prof) atomicAdd(nn_prof + 8, (unsigned long long)(clock64() - t0));
+            for (int i = tid; i < nvec; i += 32 * S1_CONV_WARPS) {
+                const float4 x = nn_lds128(raw + 16u * (uint32_t)i);
+                float4 hi, lw;
+                nn_split4(x, hi, lw);
+                nn_sts128(raw + 16u * (uint32_t)i, hi);
+                nn_sts128(lo + 16u * (uint32_t)i, lw);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) nn_mbar_arrive(b_conv + 8 * l);
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    {
-        const int ncg = dm.dh >> 2;
-        const bool live = lane < ncg;
-        for (int row = warp; row < nb; row += NN_WARPS) {
-            float4 z = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            if (live) z = *reinterpret_cast<const float4*>(sm.H + row * dm.dh + 4 * lane);
-            float m = fmaxf(fmaxf(z.x, z.y), fmaxf(z.z, z.w));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) { e.x = expf(z.x - m); e.y = expf(z.y - m); e.z = expf(z.z - m); e.w = expf(z.w - m); }
-            const float inv = 1.0f / warp_sum(e.x + e.y + e.z + e.w);
-            if (live) *reinterpret_cast<float4*>(sm.H + row * dm.dh + 4 * lane) = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
-        }
-    }
-    __syncthreads();
+    nn_mbar_wait(b_done, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    nn_stage1_epilogue(dm, sm, nb, tc, nseg, Npad);
 }
 
 // S2: dZ2[r][l] = Y[r][l] - Pr[r][l] * rowsum(Y[r]);  returns (via loglik) sum_r sum_l Y log Pr when asked
@@ -453,10 +624,16 @@ __device__ float nn_stage2(const NNDims& dm, const NNSmem& sm, const float* __re
     const bool qlive = 4 * lq < dm.dop;
     if (r < nb && qlive) {
         const float* h = sm.H + r * dm.dh;
-        for (int k = 0; k < dm.dh; ++k) {
-            const float hv = h[k];
-            const float4 av = *reinterpret_cast<const float4*>(sm.A + k * dm.dop + 4 * lq);
-            z[0] += hv * av.x; z[1] += hv * av.y; z[2] += hv * av.z; z[3] += hv * av.w;
+        const float* Ap = sm.A + 4 * lq;
+#pragma unroll 2
+        for (int k = 0; k < dm.dh; k += 4) {   // dh % 4 == 0; same summation order as the scalar loop
+            const float4 hv = *reinterpret_cast<const float4*>(h + k);
+            const float4 a0 = *reinterpret_cast<const float4*>(Ap + (k + 0) * dm.dop), a1 = *reinterpret_cast<const float4*>(Ap + (k + 1) * dm.dop);
+            const float4 a2 = *reinterpret_cast<const float4*>(Ap + (k + 2) * dm.dop), a3 = *reinterpret_cast<const float4*>(Ap + (k + 3) * dm.dop);
+            z[0] += hv.x * a0.x; z[1] += hv.x * a0.y; z[2] += hv.x * a0.z; z[3] += hv.x * a0.w;
+            z[0] += hv.y * a1.x; z[1] += hv.y * a1.y; z[2] += hv.y * a1.z; z[3] += hv.y * a1.w;
+            z[0] += hv.z * a2.x; z[1] += hv.z * a2.y; z[2] += hv.z * a2.z; z[3] += hv.z * a2.w;
+            z[0] += hv.w * a3.x; z[1] += hv.w * a3.y; z[2] += hv.w * a3.z; z[3] += hv.w * a3.w;
         }
     }
     float y[4] = {0.f, 0.f, 0.f, 0.f};
@@ -494,13 +671,24 @@ __device__ float nn_stage2(const NNDims& dm, const NNSmem& sm, const float* __re
 
 // S3: gA[k][l] (+)= sum_r H[r][k] dZ2[r][l];  ga[l] (+)= sum_r dZ2[r][l]
 __device__ void nn_stage3(const NNDims& dm, const NNSmem& sm, int nb, bool first) {
-    for (int i = threadIdx.x; i < dm.dh * dm.dop; i += NN_THREADS) {
-        const int k = i / dm.dop, l = i % dm.dop;
-        float s = 0.f;
-        for (int r = 0; r < nb; ++r) s += sm.H[r * dm.dh + k] * sm.dZ2[r * dm.dop + l];
-        sm.gA[i] = first ? s : sm.gA[i] + s;
+    // one (hidden unit k, output quad) per thread: 4 independent accumulators, rows walked in order (same sums as a scalar loop)
+    const int nq = dm.dop >> 2;
+    for (int i = threadIdx.x; i < dm.dh * nq; i += NN_THREADS) {
+        const int k = i / nq, lq = i % nq;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const float* hp = sm.H + k;
+        const float* zp = sm.dZ2 + 4 * lq;
+#pragma unroll 4
+        for (int r = 0; r < nb; ++r) {
+            const float hv = hp[r * dm.dh];
+            const float4 dz = *reinterpret_cast<const float4*>(zp + r * dm.dop);
+            s0 += hv * dz.x; s1 += hv * dz.y; s2 += hv * dz.z; s3 += hv * dz.w;
+        }
+        float4* o = reinterpret_cast<float4*>(sm.gA + k * dm.dop + 4 * lq);
+        if (first) *o = make_float4(s0, s1, s2, s3);
+        else { const float4 pv = *o; *o = make_float4(pv.x + s0, pv.y + s1, pv.z + s2, pv.w + s3); }
     }
-    for (int l = threadIdx.x; l < dm.dop; l += NN_THREADS) {
+    for (int l = NN_THREADS - 1 - threadIdx.x; l < dm.dop; l += NN_THREADS) {   // the last threads (idle above)
         float s = 0.f;
         for (int r = 0; r < nb; ++r) s += sm.dZ2[r * dm.dop + l];
         sm.ga[l] = first ? s : sm.ga[l] + s;
@@ -728,8 +916,9 @@ enum : int { NEED_A = 1, NEED_B = 2, NEED_a = 4, NEED_b = 8, NEED_ALL = 15 };
 // Rows come from idx (deterministic), the keyed permutation, or the contiguous range [row0, row0+n).
 __device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int n,
                          const Perm* perm, const int32_t* __restrict__ idx, int64_t row0,
-                         const float* __restrict__ th, int need, bool h_valid, bool want_ll, float* __restrict__ Gout, TcCtx& tc) {
-    nn_load_small(dm, sm, th);
+                         const float* __restrict__ th, int need, bool h_valid, bool want_ll, float* __restrict__ Gout, TcCtx& tc,
+                         const NNMaps& mp, int reload = LOAD_ALL) {
+    nn_load_small(dm, sm, th, reload);
     float ll = 0.f;
     const int nblocks = (n + NN_RB - 1) / NN_RB;
     for (int rb = 0; rb < nblocks; ++rb) {
@@ -742,7 +931,8 @@ __device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __rest
                 sm.rows[r] = (r < nb) ? (idx ? idx[r0 + r] : (perm ? (int)perm_at(*perm, (uint32_t)(r0 + r)) : (int)(row0 + r0 + r))) : 0;
             __syncthreads();
             NN_TICK(6)
-            nn_stage1_tc(dm, sm, X, ld, nb, th, tc);
+            if (mp.x) nn_stage1_tma(dm, sm, mp, nb, tc);
+            else nn_stage1_tc(dm, sm, X, ld, nb, th, tc);
             NN_TICK(0)
         }
         ll += nn_stage2(dm, sm, X, ld, nb, want_ll);
@@ -819,7 +1009,33 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
     const float lam_t = (t < 4 && a.use_prior) ? st.th[dm.offl + t] : 0.f;
     const float lam_h = (t < 4 && a.use_prior && a.cv) ? st.hat[dm.offl + t] : 0.f;
     const bool vec = (lo & 3) == 0;   // 16-byte aligned tensor: whole float4 groups are loaded before any store
-    for (int e0 = lo + 4 * threadIdx.x; e0 < hi; e0 += 4 * NN_THREADS) {
+    // software pipeline: the loads of the NEXT group of four elements are issued before the current group's noise / arithmetic /
+    // stores (one group at a time left ~24 KB in flight per SM and the pass latency-bound, profiles/r01_c4_phases.txt)
+    struct Grp { float th4[4], mo4[4], g4[4], gh4[4], hat4[4], ghat4[4]; };
+    auto load_group = [&](int e0, Grp& q) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { q.th4[i] = q.mo4[i] = q.g4[i] = q.gh4[i] = q.hat4[i] = q.ghat4[i] = 0.f; }
+        if (e0 >= hi) return;
+        const int cnt = (hi - e0 < 4) ? hi - e0 : 4;
+        if (vec && cnt == 4) {
+            const float4 tv = *reinterpret_cast<const float4*>(st.th + e0), mv = *reinterpret_cast<const float4*>(st.mo + e0);
+            q.th4[0] = tv.x; q.th4[1] = tv.y; q.th4[2] = tv.z; q.th4[3] = tv.w; q.mo4[0] = mv.x; q.mo4[1] = mv.y; q.mo4[2] = mv.z; q.mo4[3] = mv.w;
+            if (t < 4) { const float4 gv = *reinterpret_cast<const float4*>(st.G + e0); q.g4[0] = gv.x; q.g4[1] = gv.y; q.g4[2] = gv.z; q.g4[3] = gv.w; }
+            if (a.cv) {
+                const float4 hv = *reinterpret_cast<const float4*>(st.hat + e0), qv = *reinterpret_cast<const float4*>(st.ghat + e0);
+                q.hat4[0] = hv.x; q.hat4[1] = hv.y; q.hat4[2] = hv.z; q.hat4[3] = hv.w; q.ghat4[0] = qv.x; q.ghat4[1] = qv.y; q.ghat4[2] = qv.z; q.ghat4[3] = qv.w;
+                if (t < 4) { const float4 gv = *reinterpret_cast<const float4*>(st.Ghat + e0); q.gh4[0] = gv.x; q.gh4[1] = gv.y; q.gh4[2] = gv.z; q.gh4[3] = gv.w; }
+            }
+        } else {
+            for (int i = 0; i < cnt; ++i) {
+                q.th4[i] = st.th[e0 + i]; q.mo4[i] = st.mo[e0 + i];
+                if (t < 4) q.g4[i] = st.G[e0 + i];
+                if (a.cv) { q.hat4[i] = st.hat[e0 + i]; q.ghat4[i] = st.ghat[e0 + i]; if (t < 4) q.gh4[i] = st.Ghat[e0 + i]; }
+            }
+        }
+    };
+    auto process = [&](int e0, Grp& cur) {
+        if (e0 >= hi) return;
         float z4[4] = {0.f, 0.f, 0.f, 0.f};
         if (noisy && !a.det) {
             // Philox block = 4 consecutive INTERNAL elements (tensor ranges need not be 4-aligned)
@@ -833,25 +1049,8 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
             }
         }
         const int cnt = (hi - e0 < 4) ? hi - e0 : 4;
-        // ---- all loads of the group first (theta / momentum / gradient buffers may alias for the compiler)
-        float th4[4] = {0.f, 0.f, 0.f, 0.f}, mo4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {0.f, 0.f, 0.f, 0.f};
-        float gh4[4] = {0.f, 0.f, 0.f, 0.f}, hat4[4] = {0.f, 0.f, 0.f, 0.f}, ghat4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (vec && cnt == 4) {
-            const float4 tv = *reinterpret_cast<const float4*>(st.th + e0), mv = *reinterpret_cast<const float4*>(st.mo + e0);
-            th4[0] = tv.x; th4[1] = tv.y; th4[2] = tv.z; th4[3] = tv.w; mo4[0] = mv.x; mo4[1] = mv.y; mo4[2] = mv.z; mo4[3] = mv.w;
-            if (t < 4) { const float4 gv = *reinterpret_cast<const float4*>(st.G + e0); g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w; }
-            if (a.cv) {
-                const float4 hv = *reinterpret_cast<const float4*>(st.hat + e0), qv = *reinterpret_cast<const float4*>(st.ghat + e0);
-                hat4[0] = hv.x; hat4[1] = hv.y; hat4[2] = hv.z; hat4[3] = hv.w; ghat4[0] = qv.x; ghat4[1] = qv.y; ghat4[2] = qv.z; ghat4[3] = qv.w;
-                if (t < 4) { const float4 gv = *reinterpret_cast<const float4*>(st.Ghat + e0); gh4[0] = gv.x; gh4[1] = gv.y; gh4[2] = gv.z; gh4[3] = gv.w; }
-            }
-        } else {
-            for (int q = 0; q < cnt; ++q) {
-                th4[q] = st.th[e0 + q]; mo4[q] = st.mo[e0 + q];
-                if (t < 4) g4[q] = st.G[e0 + q];
-                if (a.cv) { hat4[q] = st.hat[e0 + q]; ghat4[q] = st.ghat[e0 + q]; if (t < 4) gh4[q] = st.Ghat[e0 + q]; }
-            }
-        }
+        float (&th4)[4] = cur.th4; float (&mo4)[4] = cur.mo4; float (&g4)[4] = cur.g4;
+        float (&gh4)[4] = cur.gh4; float (&hat4)[4] = cur.hat4; float (&ghat4)[4] = cur.ghat4;
         if (noisy && a.det)
             for (int q = 0; q < cnt; ++q)
                 z4[q] = a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + nn_flat_of_internal(dm, e0 + q)];
@@ -893,40 +1092,64 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
         } else {
             for (int q = 0; q < cnt; ++q) { if (wr_th) st.th[e0 + q] = th4[q]; if (wr_mo) st.mo[e0 + q] = mo4[q]; }
         }
+    };
+    {   // two register sets in ping-pong (no moves of in-flight load results)
+        Grp ga, gb;
+        const int stride = 4 * NN_THREADS;
+        load_group(lo + 4 * (int)threadIdx.x, ga);
+        for (int e0 = lo + 4 * (int)threadIdx.x; e0 < hi; e0 += 2 * stride) {
+            load_group(e0 + stride, gb);
+            process(e0, ga);
+            load_group(e0 + 2 * stride, ga);
+            process(e0 + stride, gb);
+        }
     }
     if (uu_out) *uu_out = nn_block_sum(uu, sm.red);
     __syncthreads();
     NN_TICK(5)
 }
 
+__host__ __device__ inline int nn_tile_floats_all(const NNDims& dm) {
+    const int t1 = nn_tile_floats(dm);
+    const int need = nn_s1_ring_bytes(dm) / 4 - 2 * NN_RB * dm.dh;   // the ring spans H | dZ1 | tile
+    return t1 > need ? t1 : need;
+}
+
 __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
-    float* p = base;
+    // 1024-byte aligned start: the swizzled operand tiles need it (the launch reserves the slack)
+    const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(base);
+    float* p = base + (((1024u - (b0 & 1023u)) & 1023u) >> 2);
+    const int t1 = nn_tile_floats_all(dm);
+    sm.ring = (uint32_t)__cvta_generic_to_shared(p);
+    sm.ring_bytes = (uint32_t)(2 * NN_RB * dm.dh + t1) * 4u;
     sm.H = p; p += NN_RB * dm.dh;
     sm.dZ1 = p; p += NN_RB * dm.dh;
+    sm.tile = p; p += t1;
     sm.dZ2 = p; p += NN_RB * dm.dop;
     sm.A = p; p += dm.dh * dm.dop;
     sm.At = p; p += dm.dop * dm.dh;
     sm.a = p; p += NN_MAXO;
     sm.b = p; p += NN_MAXH;
-    const int t1 = nn_tile_floats(dm);
-    sm.tile = p; p += t1;
     sm.gb = p; p += NN_WARPS * dm.dh;
     sm.gA = p; p += dm.dh * dm.dop;
     sm.ga = p; p += NN_MAXO;
     sm.red = p; p += 64;
     sm.rows = reinterpret_cast<int*>(p); p += NN_RB;
     sm.tc_slot = reinterpret_cast<uint32_t*>(p); p += 4;
-    sm.tc_bars = reinterpret_cast<uint64_t*>(p);
+    sm.tc_bars = reinterpret_cast<uint64_t*>(p); p += 4;
+    sm.s1_bars = reinterpret_cast<uint64_t*>(p);
 }
 
 static size_t nn_smem_bytes(const NNDims& dm) {
-    const int t1 = nn_tile_floats(dm);
+    const int t1 = nn_tile_floats_all(dm);
     size_t f = (size_t)2 * NN_RB * dm.dh + NN_RB * dm.dop + 2 * dm.dh * dm.dop + NN_MAXO + NN_MAXH + t1 +
-               NN_WARPS * dm.dh + dm.dh * dm.dop + NN_MAXO + 64 + NN_RB + 4 + 4;
-    return f * sizeof(float);
+               NN_WARPS * dm.dh + dm.dh * dm.dop + NN_MAXO + 64 + NN_RB + 4 + 4 + 32;
+    return f * sizeof(float) + 1024;
 }
 
-__global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const ChainArgs a, const NNDims dm, float* Gall, float* Ghatall) {
+__global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const ChainArgs a, const NNDims dm, float* Gall, float* Ghatall,
+                                                                          const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmTh,
+                                                                          const __grid_constant__ CUtensorMap tmHat, int use_tma) {
     extern __shared__ __align__(16) float smem_f[];
     NNSmem sm;
     nn_carve(dm, smem_f, sm);
@@ -941,6 +1164,8 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
         st.ghat = a.cv ? a.g_hat + (size_t)c * a.hat_stride : nullptr;
         st.G = Gall + (size_t)c * a.Pst; st.Ghat = Ghatall ? Ghatall + (size_t)c * a.Pst : nullptr;
         for (int t = 0; t < MAX_TENSORS; ++t) st.zeta[t] = a.thermo[c * MAX_TENSORS + t];
+        bool small_valid = false;   // shared copies of A / a / b belong to this chain's theta
+        const NNMaps mpT{use_tma ? &tmX : nullptr, &tmTh, c}, mpH{use_tma ? &tmX : nullptr, &tmHat, a.hat_stride ? c : 0};
         for (int it = 0; it < a.iters; ++it) {
             const uint64_t step = a.step0 + (uint64_t)it;
             if (a.algo == ALGO_SGHMC) {  // refresh (R/dynamics.R:62)
@@ -957,23 +1182,24 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
                 const Perm perm = make_perm(a.N, a.perm_bits, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), a.index_tag, a.k0, a.k1);
                 const int32_t* idx = a.det ? a.idx + (((size_t)c * a.iters + it) * a.L + l) * a.n : nullptr;
                 const Perm* pp = a.det ? nullptr : &perm;
-                if (a.cv) nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.hat, NEED_ALL, false, false, st.Ghat, tc);
+                if (a.cv) nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.hat, NEED_ALL, false, false, st.Ghat, tc, mpH);
                 if (seidel) {
-                    // A
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_A, false, false, st.G, tc);
+                    // A   (shared A / a / b are current from the previous sub-step except b, unless the mode's were loaded)
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_A, false, false, st.G, tc, mpT, (a.cv || !small_valid) ? LOAD_ALL : LOAD_b);
+                    small_valid = true;
                     nn_update_tensor(a, dm, sm, st, 0, c, step, sub, nullptr);
                     // B: H still valid (depends on B, b only)
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_B, true, false, st.G, tc);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_B, true, false, st.G, tc, mpT, LOAD_A);
                     nn_update_tensor(a, dm, sm, st, 1, c, step, sub, nullptr);
                     // a: B changed -> recompute H
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_a, false, false, st.G, tc);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_a, false, false, st.G, tc, mpT, 0);
                     nn_update_tensor(a, dm, sm, st, 2, c, step, sub, nullptr);
                     // b
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_b, true, false, st.G, tc);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_b, true, false, st.G, tc, mpT, LOAD_a);
                     nn_update_tensor(a, dm, sm, st, 3, c, step, sub, nullptr);
                     for (int t = 4; t < 8; ++t) nn_update_tensor(a, dm, sm, st, t, c, step, sub, nullptr);
                 } else {
-                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_ALL, false, false, st.G, tc);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_ALL, false, false, st.G, tc, mpT);
                     float uu[MAX_TENSORS];
                     // All tensors move from ONE evaluation.  The mode finder writes theta in place, so the
                     // precisions (whose gradient reads ||W||^2) go first and the weights see the OLD precisions.
@@ -1020,7 +1246,8 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
 
 // full-data gradient partials: CTA (x, m) sums rows [row0 + x*rows_per, ...) at theta_hat[m] into part[(m*gx + x)][Pst]
 __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_fullgrad_kernel(const ChainArgs a, const NNDims dm, int64_t row0, int64_t row1,
-                                                                             int rows_per, const float* __restrict__ theta_hat, float* __restrict__ part) {
+                                                                             int rows_per, const float* __restrict__ theta_hat, float* __restrict__ part,
+                                                                             const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmHat, int use_tma) {
     extern __shared__ __align__(16) float smem_f[];
     NNSmem sm;
     nn_carve(dm, smem_f, sm);
@@ -1031,7 +1258,8 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_fullgrad_kernel(con
     if (lo >= hi) { for (int e = threadIdx.x; e < a.Pst; e += NN_THREADS) G[e] = 0.f; return; }
     TcCtx tc;
     nn_tc_init(sm, tc);
-    nn_eval(dm, sm, a.X, a.ld, (int)(hi - lo), nullptr, nullptr, lo, theta_hat + (size_t)m * a.Pst, NEED_ALL, false, false, G, tc);
+    nn_eval(dm, sm, a.X, a.ld, (int)(hi - lo), nullptr, nullptr, lo, theta_hat + (size_t)m * a.Pst, NEED_ALL, false, false, G, tc,
+            NNMaps{use_tma ? &tmX : nullptr, &tmHat, m});
     for (int e = dm.offl + threadIdx.x; e < a.Pst; e += NN_THREADS) G[e] = 0.f;
     nn_tc_fini(tc);
 }
@@ -1068,7 +1296,8 @@ __global__ void __launch_bounds__(NN_THREADS) softmax_net_finish_kernel(const Ch
 
 __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_logpost_kernel(const ChainArgs a, const NNDims dm, uint32_t word2,
                                                                             const float* __restrict__ theta, float* Gscratch,
-                                                                            double* __restrict__ out) {
+                                                                            double* __restrict__ out, const __grid_constant__ CUtensorMap tmX,
+                                                                            const __grid_constant__ CUtensorMap tmTh, int use_tma) {
     extern __shared__ __align__(16) float smem_f[];
     NNSmem sm;
     nn_carve(dm, smem_f, sm);
@@ -1078,7 +1307,8 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_logpost_kernel(cons
     const int32_t* idx = (a.det == 1) ? a.idx + (size_t)c * a.n : nullptr;   // det == 2: contiguous rows 0..n-1 (held-out set)
     TcCtx tc;
     nn_tc_init(sm, tc);
-    float ll = nn_eval(dm, sm, a.X, a.ld, a.n, a.det ? nullptr : &perm, idx, 0, th, 0, false, true, Gscratch + (size_t)c * a.Pst, tc);
+    float ll = nn_eval(dm, sm, a.X, a.ld, a.n, a.det ? nullptr : &perm, idx, 0, th, 0, false, true, Gscratch + (size_t)c * a.Pst, tc,
+                       NNMaps{use_tma ? &tmX : nullptr, &tmTh, c});
     ll = nn_block_sum(ll, sm.red);
     float lp = 0.f;
     if (a.use_prior) {
@@ -1098,6 +1328,67 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_logpost_kernel(cons
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*NNEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static NNEncodeFn nn_encode_fn() {
+    static NNEncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) { cudaGetLastError(); return nullptr; }
+        fn = (NNEncodeFn)p;
+    }
+    return fn;
+}
+
+// dataset map: 2-D (input column, row), box = 32 columns x 1 row (tile::gather4 fetches four such rows), 128-byte swizzle;
+// the column extent is din, so the K tail past the last input (labels, padding) reads as zeros
+static const CUtensorMap* nn_x_map(SoftmaxNetWork* w, const float* X, long long N, int ld) {
+    for (int i = 0; i < w->n_maps; ++i)
+        if (w->maps[i].base == X && w->maps[i].rows == N && w->maps[i].stride == ld) return &w->maps[i].map;
+    NNEncodeFn fn = nn_encode_fn();
+    if (!fn || !X) return nullptr;
+    if (w->n_maps == 8) w->n_maps = 0;
+    SoftmaxNetWork::MapEntry& e = w->maps[w->n_maps];
+    const cuuint64_t gdim[2] = {(cuuint64_t)w->dm.din, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)S1_KC, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    if (fn(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return nullptr;
+    e.base = X; e.rows = N; e.stride = ld;
+    ++w->n_maps;
+    return &e.map;
+}
+
+// parameter map: 3-D (input j, hidden unit k, chain) over the B block of a [count][stride] state array, box = 32 x dh x 1
+static const CUtensorMap* nn_b_map(SoftmaxNetWork* w, const float* state, long long count, long long stride) {
+    if (stride == 0 || count < 1) { count = 1; stride = 4 * ((w->dm.P + 3) / 4); }
+    for (int i = 0; i < w->n_maps; ++i)
+        if (w->maps[i].base == state && w->maps[i].rows == -count && w->maps[i].stride == stride) return &w->maps[i].map;
+    NNEncodeFn fn = nn_encode_fn();
+    if (!fn || !state) return nullptr;
+    if (w->n_maps == 8) w->n_maps = 0;
+    SoftmaxNetWork::MapEntry& e = w->maps[w->n_maps];
+    const cuuint64_t gdim[3] = {(cuuint64_t)w->dm.din, (cuuint64_t)w->dm.dh, (cuuint64_t)count};
+    const cuuint64_t gstride[2] = {(cuuint64_t)w->dm.din * 4, (cuuint64_t)stride * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)S1_KC, (cuuint32_t)w->dm.dh, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (fn(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(state) + w->dm.offB, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return nullptr;
+    e.base = state; e.rows = -count; e.stride = stride;
+    ++w->n_maps;
+    return &e.map;
+}
+
+static bool nn_tma_enabled(const SoftmaxNetWork* w) {
+    const char* f = getenv("SGM_NN_S1");
+    if (f && !strcmp(f, "regs")) return false;
+    return (w->dm.offB % 4) == 0 && (size_t)nn_s1_ring_bytes(w->dm) <= (size_t)(2 * NN_RB * w->dm.dh + nn_tile_floats_all(w->dm)) * 4;
+}
+
 int softmax_net_create(SoftmaxNetWork** out, int d_in, int d_hidden, int d_out, int n, int chains, int device) {
     if (d_in % 4 || d_hidden % 4 || d_hidden > NN_MAXH || d_out > NN_MAXO || d_out < 1 || (d_hidden * d_out) % 4) return (int)cudaErrorInvalidValue;
     SoftmaxNetWork* w = new SoftmaxNetWork();
@@ -1140,7 +1431,13 @@ int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t strea
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
     const int grid = a.C < sms ? a.C : sms;
-    softmax_net_chain_kernel<<<grid, NN_THREADS, w->smem, stream>>>(a, w->dm, w->G, a.cv ? w->Ghat : nullptr);
+    static const CUtensorMap zero_map{};
+    const CUtensorMap* mx = nn_tma_enabled(w) ? nn_x_map(w, a.X, a.N, a.ld) : nullptr;
+    const CUtensorMap* mt = mx ? nn_b_map(w, a.theta, a.C, a.Pst) : nullptr;
+    const CUtensorMap* mh = (mx && a.cv) ? nn_b_map(w, a.theta_hat, a.hat_stride ? a.C : 1, a.hat_stride) : mt;
+    const int use_tma = (mx && mt && mh) ? 1 : 0;
+    softmax_net_chain_kernel<<<grid, NN_THREADS, w->smem, stream>>>(a, w->dm, w->G, a.cv ? w->Ghat : nullptr, use_tma ? *mx : zero_map,
+                                                                   use_tma ? *mt : zero_map, use_tma ? *mh : zero_map, use_tma);
     *launches = 1;
     return (int)cudaGetLastError();
 }
@@ -1166,7 +1463,12 @@ int softmax_net_fullgrad(SoftmaxNetWork* w, const ChainArgs& a, int64_t row0, in
         w->part_cap = need;
     }
     dim3 grid((unsigned)gx, (unsigned)M);
-    softmax_net_fullgrad_kernel<<<grid, NN_THREADS, w->smem, stream>>>(a, w->dm, row0, row1, (int)rows_per, theta_hat, w->part);
+    static const CUtensorMap zero_map{};
+    const CUtensorMap* mx = nn_tma_enabled(w) ? nn_x_map(w, a.X, a.N, a.ld) : nullptr;
+    const CUtensorMap* mh = mx ? nn_b_map(w, theta_hat, M, a.Pst) : nullptr;
+    const int use_tma = (mx && mh) ? 1 : 0;
+    softmax_net_fullgrad_kernel<<<grid, NN_THREADS, w->smem, stream>>>(a, w->dm, row0, row1, (int)rows_per, theta_hat, w->part,
+                                                                      use_tma ? *mx : zero_map, use_tma ? *mh : zero_map, use_tma);
     const int total = M * a.Pst;
     softmax_net_part_reduce<<<(total + 255) / 256, 256, 0, stream>>>(w->part, gx, a.Pst, gsum, total);
     return (int)cudaGetLastError();
@@ -1179,7 +1481,12 @@ int softmax_net_fullgrad_finish(SoftmaxNetWork* w, const ChainArgs& a, int M, co
 }
 
 int softmax_net_logpost(SoftmaxNetWork* w, const ChainArgs& a, uint32_t word2, const float* theta, double* out, cudaStream_t stream) {
-    softmax_net_logpost_kernel<<<a.C, NN_THREADS, w->smem, stream>>>(a, w->dm, word2, theta, w->G, out);
+    static const CUtensorMap zero_map{};
+    const CUtensorMap* mx = nn_tma_enabled(w) ? nn_x_map(w, a.X, a.N, a.ld) : nullptr;
+    const CUtensorMap* mt = mx ? nn_b_map(w, theta, a.C, a.Pst) : nullptr;
+    const int use_tma = (mx && mt) ? 1 : 0;
+    softmax_net_logpost_kernel<<<a.C, NN_THREADS, w->smem, stream>>>(a, w->dm, word2, theta, w->G, out, use_tma ? *mx : zero_map,
+                                                                    use_tma ? *mt : zero_map, use_tma);
     return (int)cudaGetLastError();
 }
 
