@@ -103,13 +103,13 @@ def oracle_model(w):
     return OM.SoftmaxNet()
 
 
-def make_sampler(w, rank, world, chains_local, seed=13):
+def make_sampler(w, rank, world, chains_local, seed=13, shared=True, synth=None, n_iters_opt=None):
     import sgmcmc_b200 as S
     ll, lp = model_objects(w["family"])
     kw = dict(logPrior=lp, minibatchSize=w["n"], seed=seed, nChains=chains_local, chainOffset=rank * chains_local,
-              sharedMode=True, device=int(os.environ.get("LOCAL_RANK", 0)))
-    if w.get("synth"):
-        kw["synth"] = w["synth"]
+              sharedMode=shared, device=int(os.environ.get("LOCAL_RANK", 0)))
+    if synth or w.get("synth"):
+        kw["synth"] = synth or w["synth"]
     data = w["data"] if w["data"] is not None else {}
     algo, cv = w["algo"], w["cv"]
     if algo == "sghmc":
@@ -118,7 +118,7 @@ def make_sampler(w, rank, world, chains_local, seed=13):
         kw.update(a=w.get("a", 0.01))
     if cv:
         fn = {"sgld": S.sgldcvSetup, "sghmc": S.sghmccvSetup, "sgnht": S.sgnhtcvSetup}[algo]
-        return fn(ll, data, w["params"], w["stepsize"], w["opt_stepsize"], nItersOpt=w["n_iters_opt"], verbose=False, **kw)
+        return fn(ll, data, w["params"], w["stepsize"], w["opt_stepsize"], nItersOpt=n_iters_opt or w["n_iters_opt"], verbose=False, **kw)
     fn = {"sgld": S.sgldSetup, "sghmc": S.sghmcSetup, "sgnht": S.sgnhtSetup}[algo]
     return fn(ll, data, w["params"], w["stepsize"], **kw)
 
@@ -172,6 +172,40 @@ def measured_peaks():
         j = json.load(open(p))
         return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1500.0, "fallback (B200_PROFILING.md dense bf16)"
+
+
+def many_mode_full_gradient(w, rank, world, modes):
+    """Control-variate full-data gradient with one mode per chain: two tensor-core contractions (csrc/logistic_cv_gemm.cuh).
+    A separate sampler (sharedMode=False) on a bounded row count; returns the cv_full_gradient_modes object."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import validation as V
+    synth = None
+    if w.get("synth"):   # c5: the rank's whole row shard unless SGM_MODES_ROWS bounds it
+        synth = dict(w["synth"], rows=int(os.environ.get("SGM_MODES_ROWS", w["synth"]["rows"])))
+    sg = make_sampler(w, rank, world, modes, shared=False, synth=synth, n_iters_opt=20)
+    S.initSess(sg, verbose=False)
+    flops = V.lastFullGradFlops(sg)
+    reps = 3 if flops > 2e14 else 20
+    ms, _ = V.benchFullGradient(sg, reps)
+    peak, src = measured_tensor_peak()
+    rows = synth["rows"] if synth else np.asarray(w["data"]["X"]).shape[0]
+    d = w["params"]["beta"].shape[0]
+    tf = flops / (ms * 1e-3) / 1e12 if ms > 0 and flops > 0 else None
+    del sg
+    return {"modes": modes, "rows_per_rank": rows, "d": d, "ms": ms, "flops": flops, "TFLOPs": tf, "bound": "tensor",
+            "peak": peak, "peak_source": src, "frac": (tf / peak) if tf else None,
+            "arithmetic": "3xTF32 (hi*hi + hi*lo + lo*hi) on tcgen05, float32-level accuracy: three TF32 MMAs per float32 product, "
+                          "so the ceiling of this arithmetic is about TF32 peak / 3 = bf16 peak / 6",
+            "passes": "R = y - sigmoid(X theta_hat^T + bias); G = X^T R (K split over row ranges), per row block",
+            "sample": "whole dataset" if not synth or synth["rows"] == w["synth"]["rows"] else "bounded row sample of the c5 shape"}
 
 
 # --------------------------------------------------------------------------------------
@@ -345,6 +379,9 @@ def run_ours(args, w):
                                     "rows_per_rank": fg_bytes // (16 * (w["params"]["beta"].shape[0] // 4 + 1)) if w["family"] == "logistic" else None,
                                     "init_ms_total": init_ms,
                                     "note": "one mode (shared by all chains): HBM-bound stream, not a GEMM; bytes = rows x row stride"}
+    if w["cv"] and w["family"] == "logistic" and not args.no_modes:
+        del sg, sess
+        line["cv_full_gradient_modes"] = many_mode_full_gradient(w, rank, world, args.modes)
     if rank == 0 and world == 1 and not args.no_cpu:
         ips, note, fg, _ = cpu_proxy(w, args.cpu_budget, 1)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": 1, "kind": "port", "sample": note,
@@ -366,6 +403,8 @@ def main():
     ap.add_argument("--iters-per-step", type=int, default=550)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--modes", type=int, default=1024, help="modes of the many-mode control-variate full gradient leg (logistic *cv workloads)")
+    ap.add_argument("--no-modes", action="store_true")
     args = ap.parse_args()
     w = workload(args.workload, args.chains)
     if args.impl == "reference":

@@ -194,6 +194,9 @@ int sgm_last_fullgrad_timing(const sgm_handle* h, float* kernel_ms, int64_t* byt
 /* Re-runs the full-data gradient kernel of an initialised logistic *cv handle `reps` times between two CUDA events
  * (measurement only; sampler state is untouched). */
 int sgm_bench_full_gradient(sgm_handle* h, int reps, float* ms_per_rep, int64_t* bytes);
+/* 4 N d M flops of the last full-data gradient when it ran as tensor-core contractions (logistic family, one mode per
+ * chain: calcFullGrads of R/controlVariates.R:105-111 for M independent chains at once); 0 when the streaming path ran. */
+int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops);
 /* Debug: per-phase clock64() totals of the logistic short-row kernel (thread 0 of every CTA). */
 int sgm_debug_phase_cycles(sgm_handle* h, int enable, unsigned long long* out, int n);
 /* Copies rows [row0, row0+rows) of the device dataset back as column-major doubles

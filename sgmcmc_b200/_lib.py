@@ -74,6 +74,7 @@ SYMBOLS = {
     "sgm_last_timing": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "sgm_last_fullgrad_timing": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "sgm_bench_full_gradient": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "sgm_last_fullgrad_flops": (C.c_int, [_H, _PD]),
     "sgm_debug_phase_cycles": (C.c_int, [_H, C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),
     "sgm_copy_dataset": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, _PD]),
     "sgm_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),

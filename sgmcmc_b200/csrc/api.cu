@@ -21,6 +21,7 @@
 #include "logistic_staged.cuh"
 #include "logistic_fullgrad_stream.cuh"
 #include "logistic_ring.cuh"
+#include "logistic_cv_gemm.cuh"
 #include "softmax_net.cuh"
 
 using namespace sgm;
@@ -124,6 +125,9 @@ struct sgm_handle {
     bool inited = false;
     CUtensorMap tmap;           // 2-D map of the dataset (box = one row) for TMA tile::gather4
     bool tmap_ok = false;
+    float* Xt = nullptr; int64_t xt_pitch = 0;      // logistic, many modes: transposed copy of the features [d][xt_pitch] (tensor-core pass 2)
+    float* Rt = nullptr; size_t rt_cap = 0;         // residuals of one row block, transposed [M][rt_pitch]
+    double fullgrad_flops = 0;                      // 4 N d M of the last tensor-core full gradient (0: not used)
     bool rhat_cached = false;   // logistic *cv, shared mode: y - s(x.beta_hat) stored in the rows' spare slot
     ChainArgs base;  // template of kernel arguments
     SoftmaxNetWork* nn = nullptr;
@@ -523,10 +527,111 @@ static int launch_fullgrad_stream_t(sgm_handle* h, int64_t row0, int64_t row1, c
     return SGM_OK;
 }
 
+// ---- many modes: two tensor-core contractions per row block (logistic_cv_gemm.cuh)
+static int cvg_encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t pitch_floats) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) { cudaGetLastError(); return -1; }
+        fn = (EncodeFn)p;
+    }
+    const cuuint64_t gdim[2] = {inner, rows};
+    const cuuint64_t gstride[1] = {pitch_floats * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)CVG_KC, (cuuint32_t)CVG_TILE};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
+}
+
+static bool logistic_fullgrad_use_tc(const sgm_handle* h, int M) {
+    const char* force = getenv("SGM_FULLGRAD");
+    if (force && !strcmp(force, "tc")) return M >= 1;
+    if (force) return false;
+    return M >= 16 && (h->Pst % 4) == 0 && (h->ld % 4) == 0;   // below that the SIMT row-chunk x mode grid is HBM-bound anyway
+}
+
+static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1, int M, const float* theta_hat) {
+    const int d = h->d;
+    const int64_t rows_all = row1 - row0;
+    if (rows_all <= 0) return SGM_OK;
+    CU(cudaFuncSetAttribute(cvg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CVG_SMEM));
+    if (!h->Xt) {   // one-time transposed copy of the features (pass 2 reads it K-major); 16-byte aligned rows
+        h->xt_pitch = (h->N + 3) / 4 * 4;
+        CU(cudaMalloc(&h->Xt, (size_t)d * h->xt_pitch * sizeof(float)));
+        dim3 tb(32, 8), tg((unsigned)cdiv(h->N, 32), (unsigned)cdiv(d, 32));
+        cvg_transpose_kernel<<<tg, tb, 0, h->stream>>>(h->X, h->N, h->ld, d, h->Xt, h->xt_pitch);
+        CU(cudaGetLastError());
+    }
+    // row blocks: R^T of one block stays <= ~2 GB
+    const int Mpad = (int)cdiv(M, CVG_TILE) * CVG_TILE;
+    int64_t blk = ((int64_t)1 << 29) / Mpad;
+    blk = blk / 256 * 256; if (blk < 256) blk = 256;
+    if (blk > rows_all) blk = cdiv(rows_all, 256) * 256;
+    const size_t rt_need = (size_t)M * blk * sizeof(float);
+    if (rt_need > h->rt_cap) {
+        if (h->Rt) cudaFree(h->Rt);
+        h->Rt = nullptr; h->rt_cap = 0;
+        CU(cudaMalloc(&h->Rt, rt_need));
+        h->rt_cap = rt_need;
+    }
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    CUtensorMap mX, mTh, mXt, mRt;
+    if (cvg_encode_2d(&mX, h->X, (uint64_t)d, (uint64_t)h->N, (uint64_t)h->ld) || cvg_encode_2d(&mTh, theta_hat, (uint64_t)d, (uint64_t)M, (uint64_t)h->Pst) ||
+        cvg_encode_2d(&mXt, h->Xt, (uint64_t)h->N, (uint64_t)d, (uint64_t)h->xt_pitch))
+        return fail(SGM_ECUDA, "logistic full gradient: cuTensorMapEncodeTiled failed");
+    const int tiles_m = (int)cdiv(M, CVG_TILE);
+    for (int64_t b0 = row0; b0 < row1; b0 += blk) {
+        const int64_t b1 = (b0 + blk < row1) ? b0 + blk : row1;
+        const int64_t rows = b1 - b0;
+        if (cvg_encode_2d(&mRt, h->Rt, (uint64_t)rows, (uint64_t)M, (uint64_t)blk)) return fail(SGM_ECUDA, "logistic full gradient: tensor map (R^T)");
+        CvgArgs a{};
+        a.X = h->X; a.ld = h->ld; a.d = d; a.theta_hat = theta_hat; a.Pst = h->Pst; a.M = M; a.Rt = h->Rt; a.rt_pitch = blk; a.gsum = h->gsum;
+        a.row_base = b0; a.row_end = b1; a.tiles_b = tiles_m;
+        // pass 1: R^T = y - sigmoid(X theta_hat^T + bias)
+        a.epi = 0; a.k_chunks = (int)cdiv(d, CVG_KC); a.a_row0 = (int)b0; a.a_k0 = 0; a.b_k0 = 0; a.k_per_split = 0; a.k_end_a = d;
+        {
+            a.tiles_a = (int)cdiv(rows, CVG_TILE);
+            a.n_items = a.tiles_a * tiles_m;
+            const int grid = a.n_items < sms ? a.n_items : sms;
+            cvg_kernel<<<grid, CVG_THREADS, CVG_SMEM, h->stream>>>(a, mX, mTh);
+            CU(cudaGetLastError());
+            const int64_t warps = (int64_t)M * cdiv(rows, 4096);
+            cvg_rowsum_kernel<<<(unsigned)cdiv(warps * 32, 256), 256, 0, h->stream>>>(h->Rt, blk, rows, M, h->Pst, d, h->gsum);
+            CU(cudaGetLastError());
+        }
+        // pass 2: gsum[m][k] += sum_i R^T[m][i] X^T[k][i], K (= rows) split over CTAs
+        a.epi = 1; a.a_row0 = 0;
+        const int tiles_k = (int)cdiv(d, CVG_TILE);
+        // ~8 work items per CTA (static round-robin: the tail is at most one item), each at least 2 K segments long
+        int64_t splits = cdiv((int64_t)sms * 8, (int64_t)tiles_k * tiles_m);
+        int64_t kps = cdiv(cdiv(rows, splits), CVG_KC * CVG_SEG) * (CVG_KC * CVG_SEG);
+        if (kps < 2 * CVG_KC * CVG_SEG) kps = 2 * CVG_KC * CVG_SEG;
+        splits = cdiv(rows, kps);
+        a.k_per_split = (int)kps; a.k_chunks = (int)(kps / CVG_KC); a.a_k0 = (int)b0; a.b_k0 = 0; a.k_end_a = (int)b1;
+        {
+            a.tiles_a = tiles_k;
+            a.n_items = (int)(tiles_k * tiles_m * splits);
+            const int grid = a.n_items < sms ? a.n_items : sms;
+            cvg_kernel<<<grid, CVG_THREADS, CVG_SMEM, h->stream>>>(a, mXt, mRt);
+            CU(cudaGetLastError());
+        }
+        h->last_launches += 3;
+    }
+    h->fullgrad_flops = 4.0 * (double)rows_all * (double)d * (double)M;
+    return SGM_OK;
+}
+
 // one mode: streaming kernel (TMA bulk tile ring); per-chain modes: row-chunk x mode grid
 static int launch_logistic_fullgrad(sgm_handle* h, int64_t row0, int64_t row1, int M, const float* theta_hat) {
     const char* force = getenv("SGM_FULLGRAD");
     const int Q = h->ld / 4;
+    h->fullgrad_flops = 0;
+    if (logistic_fullgrad_use_tc(h, M)) return launch_logistic_fullgrad_tc(h, row0, row1, M, theta_hat);
     if (M == 1 && !(force && !strcmp(force, "generic")) && cdiv(row1 - row0, FG_SHORT_ROWS) < (1ll << 31)) {
         if (h->ld <= 128) {
             // lane-per-row needs conflict-free shared rows: odd float4 stride, or 2 (mod 4) with skewed lanes; <= 4 column slots per warp
@@ -844,7 +949,7 @@ extern "C" void sgm_destroy(sgm_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->nn) softmax_net_destroy(h->nn);
     void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,
-                    h->d_flag, h->d_idx, h->d_noise, h->store};
+                    h->d_flag, h->d_idx, h->d_noise, h->store, h->Xt, h->Rt};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1296,6 +1401,12 @@ extern "C" int sgm_copy_dataset(sgm_handle* h, int32_t entry, int64_t row0, int6
     CU(cudaMemcpyAsync(out, stage, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(stage);
+    return SGM_OK;
+}
+
+extern "C" int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    if (flops) *flops = h->fullgrad_flops;
     return SGM_OK;
 }
 

@@ -1,0 +1,308 @@
+// Control-variate full-data gradient at MANY modes (one per chain) on the 5th-generation tensor cores.
+//
+// Replaces calcFullGrads / fullCalc (R/controlVariates.R:96-97,105-111) for the logistic family when every chain
+// carries its own mode (the reference's independent runs each call getMode, cV.R:37-52).  With M modes the pass is
+// two dense contractions over the N x d data matrix ("CV full gradient, C modes"):
+//     Z[i][m] = x_i . beta_m + bias_m            [N x d] x [d x M]          (pass 1, epilogue: R = y - sigmoid(Z))
+//     G[m][k] = sum_i R[i][m] X[i][k]            [d x N] x [N x M]          (pass 2, split over row ranges)
+// 4 N d M flops against N d 4 bytes: tensor-bound from a few dozen modes on.
+//
+// Both passes are ONE kernel, C[128 x 128] = A[128 x K] B[128 x K]^T with both operands K-major:
+//     pass 1: A = X (rows i), B = theta_hat (rows m), K = features;
+//     pass 2: A = X^T (rows k; a transposed copy of the data kept in HBM), B = R^T (rows m; written by pass 1), K = data rows.
+// float32 accuracy on TF32 tensor cores by the 3-term split hi*hi + hi*lo + lo*hi (tcgen05.mma kind::tf32, accumulators in
+// TMEM).  Pipeline per 32-wide K stage: warp 0 issues two TMA boxes (128-byte swizzle) into a raw stage; warps 2..15 round the
+// raw stage to TF32 in place (hi) and write the residual (lo) into a lo stage; warp 1 issues 12 MMAs.  The tensor core's
+// float32 accumulation truncates, so K is cut into segments of 8 stages (96 accumulation steps) that alternate between two
+// TMEM buffers; warps 8..15 drain a finished segment into float32 registers (round-to-nearest adds) while the next one runs.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace sgm {
+
+constexpr int CVG_THREADS = 512;
+constexpr int CVG_WARPS = CVG_THREADS / 32;
+constexpr int CVG_TILE = 128;          // C tile: 128 A rows x 128 B rows
+constexpr int CVG_KC = 32;             // K per stage (one 128-byte swizzle span of float32)
+constexpr int CVG_NRAW = 4;            // raw stages (TMA destinations)
+constexpr int CVG_NLO = 2;             // lo stages
+constexpr int CVG_SEG = 8;             // stages per TMEM segment
+constexpr int CVG_CONV_WARPS = CVG_WARPS - 2;
+constexpr int CVG_DRAIN_WARP0 = 8;     // warps 8..15 also drain TMEM (two per lane quarter, 64 columns each)
+constexpr uint32_t CVG_OP_BYTES = CVG_TILE * 128u;          // one operand tile: 128 rows x 128 bytes
+constexpr uint32_t CVG_STAGE_BYTES = 2u * CVG_OP_BYTES;     // A | B
+constexpr size_t CVG_SMEM = (size_t)(CVG_NRAW + CVG_NLO) * CVG_STAGE_BYTES + 1024 /* alignment */ + 256 /* barriers, tmem slot */;
+
+struct CvgArgs {
+    int epi;               // 0: residual pass, 1: gradient pass
+    int k_chunks;          // stages per CTA (K extent of this CTA / 32, rounded up)
+    int tiles_a, tiles_b;  // C tiles along the A rows / the B rows (modes); a work item = (tile_a, tile_b, K split)
+    int n_items;           // tiles_a * tiles_b * splits; CTA b takes items b, b + gridDim.x, ...
+    int a_row0;            // row coordinate of A-tile 0 in the A tensor (pass 1: first row of the block)
+    int a_k0, b_k0;        // K coordinate offsets of split 0 into the A and B tensors (pass 2: global row / block-relative row)
+    int k_per_split;       // K elements per split (multiple of 32 x 8)
+    int k_end_a;           // exclusive K bound of the A tensor coordinates (pass 2: row1)
+    // pass 1 epilogue
+    const float* X; int ld; int d;
+    int64_t row_base;      // global row of A-tile 0 (this launch's row block)
+    int64_t row_end;       // rows >= row_end write r = 0
+    const float* theta_hat; int Pst; int M;
+    float* Rt; int64_t rt_pitch;   // R^T [M][rt_pitch], column = row - row_base
+    double* gsum;          // [M][Pst]: pass 1 adds the bias component (column d), pass 2 the feature components
+};
+
+__device__ __forceinline__ uint32_t cvg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cvg_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void cvg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cvg_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void cvg_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cvg_tma_box2(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128-byte swizzle: 128-byte rows, 8-row groups 1024 bytes apart; a K step of 8 TF32 = +32 bytes in the start address
+__device__ __forceinline__ uint64_t cvg_desc(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void cvg_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void cvg_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool cvg_elect() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ float cvg_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }   // round to nearest, ties away
+
+// work item -> (A tile, B tile, K split); consecutive items share the A tile (and run on different CTAs at the same time: L2 reuse)
+struct CvgItem { int tile_a, tile_b, ka0, kb0, nchunks; };
+__device__ __forceinline__ CvgItem cvg_item(const CvgArgs& a, int item) {
+    CvgItem w;
+    const int tiles = a.tiles_a * a.tiles_b;
+    const int split = item / tiles, t = item % tiles;
+    w.tile_a = t / a.tiles_b; w.tile_b = t % a.tiles_b;
+    w.ka0 = a.a_k0 + split * a.k_per_split; w.kb0 = a.b_k0 + split * a.k_per_split;
+    w.nchunks = a.k_chunks;
+    if (a.epi == 1) {   // the last split may be short
+        const int left = a.k_end_a - w.ka0;
+        const int c = left > 0 ? (left + CVG_KC - 1) / CVG_KC : 0;
+        if (c < w.nchunks) w.nchunks = c;
+    }
+    return w;
+}
+
+__global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+    extern __shared__ __align__(16) unsigned char cvg_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t base = (cvg_smem_u32(cvg_smem) + 1023u) & ~1023u;
+    const uint32_t raw0 = base, lo0 = base + CVG_NRAW * CVG_STAGE_BYTES;
+    const uint32_t bars = lo0 + CVG_NLO * CVG_STAGE_BYTES;
+    // barriers: full[NRAW] | rawfree[NRAW] | conv[NLO] | lofree[NLO] | tfull[2] | tfree[2]; then the TMEM slot
+    const uint32_t b_full = bars, b_rawfree = b_full + 8 * CVG_NRAW, b_conv = b_rawfree + 8 * CVG_NRAW, b_lofree = b_conv + 8 * CVG_NLO,
+                   b_tfull = b_lofree + 8 * CVG_NLO, b_tfree = b_tfull + 16, slot = b_tfree + 16;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < CVG_NRAW; ++s) { cvg_mbar_init(b_full + 8 * s, 1); cvg_mbar_init(b_rawfree + 8 * s, 1); }
+        for (int l = 0; l < CVG_NLO; ++l) { cvg_mbar_init(b_conv + 8 * l, CVG_CONV_WARPS); cvg_mbar_init(b_lofree + 8 * l, 1); }
+        for (int t = 0; t < 2; ++t) { cvg_mbar_init(b_tfull + 8 * t, 1); cvg_mbar_init(b_tfree + 8 * t, CVG_WARPS - CVG_DRAIN_WARP0); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+
+    // every role walks the same item sequence; g = running stage counter, sg = running segment counter (barrier phases never reset)
+    if (warp == 0) {
+        // ---- producer
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+                const CvgItem w = cvg_item(a, item);
+                for (int c = 0; c < w.nchunks; ++c, ++g) {
+                    const uint32_t s = g % CVG_NRAW;
+                    if (g >= CVG_NRAW) cvg_mbar_wait(b_rawfree + 8 * s, ((g / CVG_NRAW) - 1u) & 1u);
+                    const uint32_t dst = raw0 + s * CVG_STAGE_BYTES, bar = b_full + 8 * s;
+                    cvg_mbar_expect_tx(bar, CVG_STAGE_BYTES);
+                    cvg_tma_box2(dst, &tmA, w.ka0 + c * CVG_KC, a.a_row0 + w.tile_a * CVG_TILE, bar);
+                    cvg_tma_box2(dst + CVG_OP_BYTES, &tmB, w.kb0 + c * CVG_KC, w.tile_b * CVG_TILE, bar);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CVG_TILE >> 3) << 17) | ((uint32_t)(CVG_TILE >> 4) << 24);
+        uint32_t g = 0, sg = 0;
+        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+            const CvgItem w = cvg_item(a, item);
+            for (int c = 0; c < w.nchunks; ++c, ++g) {
+                const uint32_t s = g % CVG_NRAW, l = g % CVG_NLO, tb = sg & 1u;
+                const bool seg_first = (c % CVG_SEG) == 0, seg_last = (c % CVG_SEG) == CVG_SEG - 1 || c == w.nchunks - 1;
+                if (seg_first && sg >= 2) cvg_mbar_wait(b_tfree + 8 * tb, ((sg >> 1) - 1u) & 1u);   // buffer drained
+                cvg_mbar_wait(b_conv + 8 * l, (g / CVG_NLO) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (cvg_elect()) {
+                    const uint32_t td = tmem + tb * CVG_TILE;
+                    const uint64_t ahi = cvg_desc(raw0 + s * CVG_STAGE_BYTES), bhi = cvg_desc(raw0 + s * CVG_STAGE_BYTES + CVG_OP_BYTES);
+                    const uint64_t alo = cvg_desc(lo0 + l * CVG_STAGE_BYTES), blo = cvg_desc(lo0 + l * CVG_STAGE_BYTES + CVG_OP_BYTES);
+#pragma unroll
+                    for (int k8 = 0; k8 < CVG_KC / 8; ++k8) {
+                        const uint64_t ko = (uint64_t)(2 * k8);
+                        cvg_mma(td, ahi + ko, bhi + ko, idesc, !(seg_first && k8 == 0));
+                        cvg_mma(td, ahi + ko, blo + ko, idesc, true);
+                        cvg_mma(td, alo + ko, bhi + ko, idesc, true);
+                    }
+                    cvg_commit(b_rawfree + 8 * s);
+                    cvg_commit(b_lofree + 8 * l);
+                    if (seg_last) cvg_commit(b_tfull + 8 * tb);
+                }
+                __syncwarp();
+                if (seg_last) ++sg;
+            }
+        }
+    } else {
+        // ---- converters (warps 2..15); warps 8..15 drain finished segments between stages and run the epilogue
+        const int ctid = tid - 64;
+        constexpr int NVEC = (int)(CVG_STAGE_BYTES >> 4), CT = 32 * CVG_CONV_WARPS, ROUNDS = (NVEC + CT - 1) / CT;
+        const bool drainer = warp >= CVG_DRAIN_WARP0;
+        const int q = warp & 3, hb = (warp - CVG_DRAIN_WARP0) >> 2;
+        const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * hb);
+        float acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+        auto drain = [&](uint32_t seg) {
+            const uint32_t tb = seg & 1u;
+            cvg_mbar_wait(b_tfull + 8 * tb, (seg >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+                uint32_t r[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                               "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(tq + tb * CVG_TILE + 16u * gq));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[16 * gq + j] += __uint_as_float(r[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) cvg_mbar_arrive(b_tfree + 8 * tb);
+        };
+        uint32_t g = 0, sg0 = 0;
+        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+            const CvgItem w = cvg_item(a, item);
+            const int nseg = (w.nchunks + CVG_SEG - 1) / CVG_SEG;
+            int dl = 0;   // segments of this item drained so far
+            for (int c = 0; c < w.nchunks; ++c, ++g) {
+                const uint32_t s = g % CVG_NRAW, l = g % CVG_NLO;
+                const uint32_t raw = raw0 + s * CVG_STAGE_BYTES, lo = lo0 + l * CVG_STAGE_BYTES;
+                if (g >= CVG_NLO) cvg_mbar_wait(b_lofree + 8 * l, ((g / CVG_NLO) - 1u) & 1u);
+                cvg_mbar_wait(b_full + 8 * s, (g / CVG_NRAW) & 1u);
+                // all loads of this thread's slice first, then the splits and stores (one latency per stage, not per float4)
+                float4 x[ROUNDS];
+#pragma unroll
+                for (int u = 0; u < ROUNDS; ++u) {
+                    const int i = ctid + u * CT;
+                    if (i < NVEC) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "r"(raw + 16u * (uint32_t)i));
+                }
+#pragma unroll
+                for (int u = 0; u < ROUNDS; ++u) {
+                    const int i = ctid + u * CT;
+                    if (i < NVEC) {
+                        const float hx = cvg_tf32(x[u].x), hy = cvg_tf32(x[u].y), hz = cvg_tf32(x[u].z), hw = cvg_tf32(x[u].w);
+                        const float lx = cvg_tf32(x[u].x - hx), ly = cvg_tf32(x[u].y - hy), lz = cvg_tf32(x[u].z - hz), lw = cvg_tf32(x[u].w - hw);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raw + 16u * (uint32_t)i), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + 16u * (uint32_t)i), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) cvg_mbar_arrive(b_conv + 8 * l);
+                // a segment whose last stage was converted two stages ago has (almost surely) finished: drain it now
+                if (drainer && dl < nseg && c >= (dl + 1) * CVG_SEG + 1) { drain(sg0 + (uint32_t)dl); ++dl; }
+            }
+            if (drainer) {
+                while (dl < nseg) { drain(sg0 + (uint32_t)dl); ++dl; }
+                // ---- epilogue: this thread owns C row 32 q + lane, columns 64 hb .. 64 hb + 63 of the tile
+                const int arow = w.tile_a * CVG_TILE + 32 * q + lane;
+                const int bcol0 = w.tile_b * CVG_TILE + 64 * hb;
+                if (a.epi == 0) {
+                    const int64_t row = a.row_base + arow;
+                    const bool live = row < a.row_end;
+                    const float y = live ? __ldg(a.X + (size_t)row * a.ld + a.d) : 0.f;
+                    const float bias_l = (bcol0 + lane < a.M) ? __ldg(a.theta_hat + (size_t)(bcol0 + lane) * a.Pst + a.d) : 0.f;
+                    const float bias_h = (bcol0 + 32 + lane < a.M) ? __ldg(a.theta_hat + (size_t)(bcol0 + 32 + lane) * a.Pst + a.d) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {   // fully unrolled: acc[] stays in registers
+                        const int m = bcol0 + j;
+                        const float bias = __shfl_sync(0xffffffffu, j < 32 ? bias_l : bias_h, j & 31);
+                        if (m < a.M) {   // warp-uniform
+                            const float r = live ? y - sigmoidf(acc[j] + bias) : 0.f;
+                            if (arow < a.rt_pitch) a.Rt[(size_t)m * a.rt_pitch + arow] = r;
+                        }
+                        acc[j] = 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        const int m = bcol0 + j;
+                        if (arow < a.d && m < a.M) atomicAdd(a.gsum + (size_t)m * a.Pst + arow, (double)acc[j]);
+                        acc[j] = 0.f;
+                    }
+                }
+            }
+            sg0 += (uint32_t)nseg;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+}
+
+// bias component of the gradient: gsum[m][d] += sum_i R^T[m][i]   (one warp per 4096-column slice of a row of R^T)
+__global__ void cvg_rowsum_kernel(const float* __restrict__ Rt, int64_t pitch, int64_t rows, int M, int Pst, int d, double* __restrict__ gsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t slices = (rows + 4095) / 4096;
+    if (wid >= (int64_t)M * slices) return;
+    const int m = (int)(wid / slices);
+    const int64_t i0 = (wid % slices) * 4096, i1 = (i0 + 4096 < rows) ? i0 + 4096 : rows;
+    float s = 0.f;
+    for (int64_t i = i0 + lane; i < i1; i += 32) s += Rt[(size_t)m * pitch + i];
+    s = warp_sum(s);
+    if (lane == 0) atomicAdd(gsum + (size_t)m * Pst + d, (double)s);
+}
+
+// X [rows][ld] (features in the first d columns) -> X^T [d][pitch], tiled through shared memory
+__global__ void cvg_transpose_kernel(const float* __restrict__ X, int64_t N, int ld, int d, float* __restrict__ Xt, int64_t pitch) {
+    __shared__ float tile[32][33];
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t i = i0 + r; const int k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < N && k < d) ? X[(size_t)i * ld + k] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r; const int64_t i = i0 + threadIdx.x;
+        if (k < d && i < N) Xt[(size_t)k * pitch + i] = tile[threadIdx.x][r];
+    }
+}
+
+}  // namespace sgm

@@ -104,6 +104,13 @@ def lastFullGradTiming(sgmcmc: Sgmcmc):
     return ms.value, b.value
 
 
+def lastFullGradFlops(sgmcmc: Sgmcmc) -> float:
+    """4 N d M of the last full-data gradient if it ran as tensor-core contractions (one mode per chain), else 0."""
+    f = C.c_double()
+    _lib.check(_lib.load().sgm_last_fullgrad_flops(sgmcmc.handle, C.byref(f)))
+    return f.value
+
+
 def benchFullGradient(sgmcmc: Sgmcmc, reps: int = 20):
     """(ms per launch, bytes read) of the control-variate full-data gradient kernel, `reps` launches back to back."""
     ms, b = C.c_float(), C.c_int64()

@@ -1,0 +1,71 @@
+"""-m gpu: control-variate full-data gradient at MANY modes on the tensor cores (csrc/logistic_cv_gemm.cuh, 3xTF32
+tcgen05 contractions) against the float64 oracle and against the SIMT row-chunk x mode kernel, through the C ABI.
+
+Reference path: calcFullGrads (R/controlVariates.R:105-111) once per independent chain.  Tolerance: 1e-5 relative to the
+per-datum gradient mass (the total is near zero at a mode), the same scale tests/test_parity_gpu.py uses for g_hat.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import samplers as OS
+from tests.cases import device_setup, make_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _mode_and_grad(case, chains, path, n_opt=30):
+    from sgmcmc_b200 import validation as V
+    import sgmcmc_b200 as S
+    old = os.environ.get("SGM_FULLGRAD")
+    os.environ["SGM_FULLGRAD"] = path
+    try:
+        dev = device_setup(case, "sgld", True, n_chains=chains, n_iters_opt=n_opt)
+        S.initSess(dev, verbose=False)
+        return V.getMode(dev)
+    finally:
+        if old is None:
+            os.environ.pop("SGM_FULLGRAD", None)
+        else:
+            os.environ["SGM_FULLGRAD"] = old
+
+
+@pytest.mark.parametrize("case_name,chains", [("logistic54", 20), ("logistic54", 150), ("logistic130", 40), ("logistic5", 16)])
+def test_many_mode_full_gradient_matches_oracle(lib, case_name, chains):
+    case = make_case(case_name)
+    th_tc, g_tc = _mode_and_grad(case, chains, "tc")
+    th_sm, g_sm = _mode_and_grad(case, chains, "generic")
+    # same seed, same device RNG streams: the modes are identical, so the two gradient paths see the same input
+    assert np.array_equal(th_tc, th_sm)
+    assert len({tuple(t) for t in th_tc}) == chains, "every chain finds its own mode"
+    post = OS.Posterior(case["om"], case["N"], case["n"], np.float64, use_prior=True)
+    worst = 0.0
+    for c in range(chains):
+        th = OS.unflat(th_tc[c], case["params"])
+        ref = OS.flat(post.full_grad(th, case["data"]))
+        gl = OS.flat(case["om"].grad_loglik(th, case["data"], np.float64))
+        # mass of the per-datum summands: sum_i |y_i - s_i| |x_ik| >= |sum|; use the data scale N * mean|x| as in test_parity_gpu
+        scale = max(np.abs(ref).max(), np.abs(gl).max(), 1.0) * 10
+        err = np.abs(g_tc[c] - ref).max()
+        worst = max(worst, err / scale)
+        assert err <= 1e-5 * scale + 1e-7, f"chain {c}: tensor-core g_hat err {err:.3e} vs scale {scale:.3e}"
+        err_sm = np.abs(g_sm[c] - ref).max()
+        assert err <= err_sm + 1e-5 * scale, f"chain {c}: tensor-core path ({err:.2e}) worse than the SIMT path ({err_sm:.2e})"
+    print(f"{case_name} x {chains} modes: worst scaled error {worst:.2e}")
+
+
+def test_many_mode_full_gradient_row_tail_and_blocks(lib):
+    """N not a multiple of the 128-row tile or of the 256-row K segment; more than one K split."""
+    case = make_case("logistic54")
+    keep = 3877
+    case["data"] = {k: v[:keep] for k, v in case["data"].items()}
+    case["N"] = keep
+    th_tc, g_tc = _mode_and_grad(case, 24, "tc", n_opt=10)
+    post = OS.Posterior(case["om"], case["N"], case["n"], np.float64, use_prior=True)
+    for c in range(24):
+        th = OS.unflat(th_tc[c], case["params"])
+        ref = OS.flat(post.full_grad(th, case["data"]))
+        gl = OS.flat(case["om"].grad_loglik(th, case["data"], np.float64))
+        scale = max(np.abs(ref).max(), np.abs(gl).max(), 1.0) * 10
+        assert np.abs(g_tc[c] - ref).max() <= 1e-5 * scale + 1e-7
