@@ -11,8 +11,9 @@
 //     pass 1: A = X (rows i), B = theta_hat (rows m), K = features;
 //     pass 2: A = X^T (rows k; a transposed copy of the data kept in HBM), B = R^T (rows m; written by pass 1), K = data rows.
 // float32 accuracy on TF32 tensor cores by the 3-term split hi*hi + hi*lo + lo*hi (tcgen05.mma kind::tf32, accumulators in
-// TMEM).  Pipeline per 32-wide K stage: warp 0 issues two TMA boxes (128-byte swizzle) into a raw stage; warps 2..15 round the
-// raw stage to TF32 in place (hi) and write the residual (lo) into a lo stage; warp 1 issues 12 MMAs.  The tensor core's
+// TMEM).  Pipeline per 32-wide K stage: warp 0 issues two TMA boxes (128-byte swizzle) into a raw stage; warps 2..7 round the
+// raw B tile to TF32 in place (hi) and write the residual (lo) into a lo stage; warps 8..15 split the raw A tile into TENSOR
+// MEMORY (tcgen05.st; A-from-TMEM MMAs fetch only B from shared memory, whose bandwidth bounds the SS form); warp 1 issues 12 MMAs.  The tensor core's
 // float32 accumulation truncates, so K is cut into segments of 8 stages (96 accumulation steps) that alternate between two
 // TMEM buffers; warps 8..15 drain a finished segment into float32 registers (round-to-nearest adds) while the next one runs.
 #pragma once
@@ -32,7 +33,9 @@ constexpr int CVG_CONV_WARPS = CVG_WARPS - 2;
 constexpr int CVG_DRAIN_WARP0 = 8;     // warps 8..15 also drain TMEM (two per lane quarter, 64 columns each)
 constexpr uint32_t CVG_OP_BYTES = CVG_TILE * 128u;          // one operand tile: 128 rows x 128 bytes
 constexpr uint32_t CVG_STAGE_BYTES = 2u * CVG_OP_BYTES;     // A | B
-constexpr size_t CVG_SMEM = (size_t)(CVG_NRAW + CVG_NLO) * CVG_STAGE_BYTES + 1024 /* alignment */ + 256 /* barriers, tmem slot */;
+constexpr int CVG_BCONV_WARPS = CVG_DRAIN_WARP0 - 2;   // warps 2..7 split the B operand in shared memory; warps 8..15 move A into TMEM
+constexpr uint32_t CVG_TMEM_A = 256;                   // TMEM columns: [0, 256) two accumulator buffers, [256, 384) two A buffers (hi 32 | lo 32)
+constexpr size_t CVG_SMEM = (size_t)CVG_NRAW * CVG_STAGE_BYTES + (size_t)CVG_NLO * CVG_OP_BYTES + 1024 /* alignment */ + 256 /* barriers, tmem slot */;
 
 struct CvgArgs {
     int epi;               // 0: residual pass, 1: gradient pass
@@ -74,6 +77,19 @@ __device__ __forceinline__ void cvg_mma(uint32_t tmem_d, uint64_t adesc, uint64_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
 }
+// A operand read from tensor memory (lane = row, one TF32 element per 32-bit column), B from shared memory
+__device__ __forceinline__ void cvg_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void cvg_tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
 __device__ __forceinline__ void cvg_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -105,14 +121,14 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
     extern __shared__ __align__(16) unsigned char cvg_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t base = (cvg_smem_u32(cvg_smem) + 1023u) & ~1023u;
-    const uint32_t raw0 = base, lo0 = base + CVG_NRAW * CVG_STAGE_BYTES;
-    const uint32_t bars = lo0 + CVG_NLO * CVG_STAGE_BYTES;
+    const uint32_t raw0 = base, lo0 = base + CVG_NRAW * CVG_STAGE_BYTES;   // lo stages hold only the B residuals
+    const uint32_t bars = lo0 + CVG_NLO * CVG_OP_BYTES;
     // barriers: full[NRAW] | rawfree[NRAW] | conv[NLO] | lofree[NLO] | tfull[2] | tfree[2]; then the TMEM slot
     const uint32_t b_full = bars, b_rawfree = b_full + 8 * CVG_NRAW, b_conv = b_rawfree + 8 * CVG_NRAW, b_lofree = b_conv + 8 * CVG_NLO,
                    b_tfull = b_lofree + 8 * CVG_NLO, b_tfree = b_tfull + 16, slot = b_tfree + 16;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "n"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
@@ -158,14 +174,14 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (cvg_elect()) {
                     const uint32_t td = tmem + tb * CVG_TILE;
-                    const uint64_t ahi = cvg_desc(raw0 + s * CVG_STAGE_BYTES), bhi = cvg_desc(raw0 + s * CVG_STAGE_BYTES + CVG_OP_BYTES);
-                    const uint64_t alo = cvg_desc(lo0 + l * CVG_STAGE_BYTES), blo = cvg_desc(lo0 + l * CVG_STAGE_BYTES + CVG_OP_BYTES);
+                    const uint64_t bhi = cvg_desc(raw0 + s * CVG_STAGE_BYTES + CVG_OP_BYTES), blo = cvg_desc(lo0 + l * CVG_OP_BYTES);
+                    const uint32_t ahi = tmem + CVG_TMEM_A + l * 64u, alo = ahi + 32u;
 #pragma unroll
                     for (int k8 = 0; k8 < CVG_KC / 8; ++k8) {
                         const uint64_t ko = (uint64_t)(2 * k8);
-                        cvg_mma(td, ahi + ko, bhi + ko, idesc, !(seg_first && k8 == 0));
-                        cvg_mma(td, ahi + ko, blo + ko, idesc, true);
-                        cvg_mma(td, alo + ko, bhi + ko, idesc, true);
+                        cvg_mma_ts(td, ahi + 8u * k8, bhi + ko, idesc, !(seg_first && k8 == 0));
+                        cvg_mma_ts(td, ahi + 8u * k8, blo + ko, idesc, true);
+                        cvg_mma_ts(td, alo + 8u * k8, bhi + ko, idesc, true);
                     }
                     cvg_commit(b_rawfree + 8 * s);
                     cvg_commit(b_lofree + 8 * l);
@@ -178,7 +194,7 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
     } else {
         // ---- converters (warps 2..15); warps 8..15 drain finished segments between stages and run the epilogue
         const int ctid = tid - 64;
-        constexpr int NVEC = (int)(CVG_STAGE_BYTES >> 4), CT = 32 * CVG_CONV_WARPS, ROUNDS = (NVEC + CT - 1) / CT;
+        constexpr int NVEC = (int)(CVG_OP_BYTES >> 4), CT = 32 * CVG_BCONV_WARPS, ROUNDS = (NVEC + CT - 1) / CT;
         const bool drainer = warp >= CVG_DRAIN_WARP0;
         const int q = warp & 3, hb = (warp - CVG_DRAIN_WARP0) >> 2;
         const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * hb);
@@ -211,25 +227,48 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
             int dl = 0;   // segments of this item drained so far
             for (int c = 0; c < w.nchunks; ++c, ++g) {
                 const uint32_t s = g % CVG_NRAW, l = g % CVG_NLO;
-                const uint32_t raw = raw0 + s * CVG_STAGE_BYTES, lo = lo0 + l * CVG_STAGE_BYTES;
+                const uint32_t raw = raw0 + s * CVG_STAGE_BYTES, lo = lo0 + l * CVG_OP_BYTES;
                 if (g >= CVG_NLO) cvg_mbar_wait(b_lofree + 8 * l, ((g / CVG_NLO) - 1u) & 1u);
                 cvg_mbar_wait(b_full + 8 * s, (g / CVG_NRAW) & 1u);
-                // all loads of this thread's slice first, then the splits and stores (one latency per stage, not per float4)
-                float4 x[ROUNDS];
+                if (!drainer) {
+                    // ---- B operand (warps 2..7): hi = rna_tf32(x) in place, lo = rna_tf32(x - hi) into the lo stage; loads first
+                    const uint32_t braw = raw + CVG_OP_BYTES;
+                    float4 x[ROUNDS];
 #pragma unroll
-                for (int u = 0; u < ROUNDS; ++u) {
-                    const int i = ctid + u * CT;
-                    if (i < NVEC) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "r"(raw + 16u * (uint32_t)i));
-                }
-#pragma unroll
-                for (int u = 0; u < ROUNDS; ++u) {
-                    const int i = ctid + u * CT;
-                    if (i < NVEC) {
-                        const float hx = cvg_tf32(x[u].x), hy = cvg_tf32(x[u].y), hz = cvg_tf32(x[u].z), hw = cvg_tf32(x[u].w);
-                        const float lx = cvg_tf32(x[u].x - hx), ly = cvg_tf32(x[u].y - hy), lz = cvg_tf32(x[u].z - hz), lw = cvg_tf32(x[u].w - hw);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raw + 16u * (uint32_t)i), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + 16u * (uint32_t)i), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+                    for (int u = 0; u < ROUNDS; ++u) {
+                        const int i = ctid + u * CT;
+                        if (i < NVEC) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "r"(braw + 16u * (uint32_t)i));
                     }
+#pragma unroll
+                    for (int u = 0; u < ROUNDS; ++u) {
+                        const int i = ctid + u * CT;
+                        if (i < NVEC) {
+                            const float hx = cvg_tf32(x[u].x), hy = cvg_tf32(x[u].y), hz = cvg_tf32(x[u].z), hw = cvg_tf32(x[u].w);
+                            const float lx = cvg_tf32(x[u].x - hx), ly = cvg_tf32(x[u].y - hy), lz = cvg_tf32(x[u].z - hz), lw = cvg_tf32(x[u].w - hw);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(braw + 16u * (uint32_t)i), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + 16u * (uint32_t)i), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+                        }
+                    }
+                } else {
+                    // ---- A operand (warps 8..15): row 32 q + lane, K columns 16 hb .. 16 hb + 15 of the swizzled raw tile -> hi / lo
+                    // straight into tensor memory (tcgen05.st): the MMAs then fetch only B from shared memory
+                    const int r = 32 * q + lane;
+                    const uint32_t rowp = raw + (uint32_t)r * 128u;
+                    float hi[16], lw[16];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const uint32_t chunk = (uint32_t)((4 * hb + cc) ^ (r & 7));
+                        float4 x;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(rowp + 16u * chunk));
+                        hi[4 * cc + 0] = cvg_tf32(x.x); hi[4 * cc + 1] = cvg_tf32(x.y); hi[4 * cc + 2] = cvg_tf32(x.z); hi[4 * cc + 3] = cvg_tf32(x.w);
+                        lw[4 * cc + 0] = cvg_tf32(x.x - hi[4 * cc + 0]); lw[4 * cc + 1] = cvg_tf32(x.y - hi[4 * cc + 1]);
+                        lw[4 * cc + 2] = cvg_tf32(x.z - hi[4 * cc + 2]); lw[4 * cc + 3] = cvg_tf32(x.w - hi[4 * cc + 3]);
+                    }
+                    const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + CVG_TMEM_A + l * 64u + 16u * (uint32_t)hb;
+                    cvg_tmem_st16(ta, hi);
+                    cvg_tmem_st16(ta + 32u, lw);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -272,7 +311,7 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 // bias component of the gradient: gsum[m][d] += sum_i R^T[m][i]   (one warp per 4096-column slice of a row of R^T)
