@@ -12,10 +12,11 @@
 //     pass 2: A = X^T (rows k; a transposed copy of the data kept in HBM), B = R^T (rows m; written by pass 1), K = data rows.
 // float32 accuracy on TF32 tensor cores by the 3-term split hi*hi + hi*lo + lo*hi (tcgen05.mma kind::tf32, accumulators in
 // TMEM).  Pipeline per 32-wide K stage: warp 0 issues two TMA boxes (128-byte swizzle) into a raw stage; warps 2..7 round the
-// raw B tile to TF32 in place (hi) and write the residual (lo) into a lo stage; warps 8..15 split the raw A tile into TENSOR
-// MEMORY (tcgen05.st; A-from-TMEM MMAs fetch only B from shared memory, whose bandwidth bounds the SS form); warp 1 issues 12 MMAs.  The tensor core's
+// raw B tile to TF32 in place (hi), write the residual (lo) into a lo stage and split the raw A tile into TENSOR MEMORY
+// (tcgen05.st; A-from-TMEM MMAs fetch only B from shared memory, whose bandwidth bounds the SS form); warp 1 issues 12 MMAs.  The tensor core's
 // float32 accumulation truncates, so K is cut into segments of 8 stages (96 accumulation steps) that alternate between two
-// TMEM buffers; warps 8..15 drain a finished segment into float32 registers (round-to-nearest adds) while the next one runs.
+// TMEM buffers; warps 8..15 drain a finished segment into float32 registers (round-to-nearest adds) while the next one runs,
+// and write the item's output (pass 1: R^T; pass 2: double-precision atomics into the gradient sums).
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
     }
     if (tid == 0) {
         for (int s = 0; s < CVG_NRAW; ++s) { cvg_mbar_init(b_full + 8 * s, 1); cvg_mbar_init(b_rawfree + 8 * s, 1); }
-        for (int l = 0; l < CVG_NLO; ++l) { cvg_mbar_init(b_conv + 8 * l, CVG_CONV_WARPS); cvg_mbar_init(b_lofree + 8 * l, 1); }
+        for (int l = 0; l < CVG_NLO; ++l) { cvg_mbar_init(b_conv + 8 * l, CVG_BCONV_WARPS); cvg_mbar_init(b_lofree + 8 * l, 1); }
         for (int t = 0; t < 2; ++t) { cvg_mbar_init(b_tfull + 8 * t, 1); cvg_mbar_init(b_tfree + 8 * t, CVG_WARPS - CVG_DRAIN_WARP0); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -191,122 +192,128 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                 if (seg_last) ++sg;
             }
         }
+    } else if (warp < CVG_DRAIN_WARP0) {
+        // ---- converters (warps 2..7).  B operand: hi = rna_tf32(x) in place, lo = rna_tf32(x - hi) into the lo stage.
+        // A operand: the swizzled raw tile -> hi / lo straight into TENSOR MEMORY (tcgen05.st), so the MMAs fetch only B from
+        // shared memory.  A warp may touch only the TMEM lanes 32 (warp % 4) .. +31: quarters 2 and 3 have two converter warps
+        // (16 K columns each), quarters 0 and 1 one (all 32 columns); the B slices are sized to even the load out (10 vs 12 float4).
+        const int q = warp & 3;
+        const bool heavy = (warp == 4 || warp == 5);              // both column halves of its quarter
+        const int hb0 = heavy ? 0 : (warp >= 6 ? 1 : 0);
+        const int nhalf = heavy ? 2 : 1;
+        const int lw = heavy ? warp - 4 : (warp < 4 ? warp - 2 : warp - 4);   // light warps 2,3,6,7 -> 0..3; heavy 4,5 -> 0,1
+        const int b_first = heavy ? 768 + lw * 32 + lane : lw * 32 + lane;
+        const int b_step = heavy ? 64 : 128, b_rounds = heavy ? 4 : 6;
+        const int r = 32 * q + lane;
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+            const CvgItem w = cvg_item(a, item);
+            for (int c = 0; c < w.nchunks; ++c, ++g) {
+                const uint32_t s = g % CVG_NRAW, l = g % CVG_NLO;
+                const uint32_t raw = raw0 + s * CVG_STAGE_BYTES, braw = raw + CVG_OP_BYTES, lo = lo0 + l * CVG_OP_BYTES;
+                if (g >= CVG_NLO) cvg_mbar_wait(b_lofree + 8 * l, ((g / CVG_NLO) - 1u) & 1u);
+                cvg_mbar_wait(b_full + 8 * s, (g / CVG_NRAW) & 1u);
+                // all shared loads of this thread first (one latency per stage), then the splits and the stores
+                float4 xb[6], xa[8];
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+                    if (u < b_rounds) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xb[u].x), "=f"(xb[u].y), "=f"(xb[u].z), "=f"(xb[u].w) : "r"(braw + 16u * (uint32_t)(b_first + u * b_step)));
+                const uint32_t rowp = raw + (uint32_t)r * 128u;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                    if (cc < 4 * nhalf) {
+                        const uint32_t chunk = (uint32_t)((4 * hb0 + cc) ^ (r & 7));
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xa[cc].x), "=f"(xa[cc].y), "=f"(xa[cc].z), "=f"(xa[cc].w) : "r"(rowp + 16u * chunk));
+                    }
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+                    if (u < b_rounds) {
+                        const uint32_t off = 16u * (uint32_t)(b_first + u * b_step);
+                        const float hx = cvg_tf32(xb[u].x), hy = cvg_tf32(xb[u].y), hz = cvg_tf32(xb[u].z), hw = cvg_tf32(xb[u].w);
+                        const float lx = cvg_tf32(xb[u].x - hx), ly = cvg_tf32(xb[u].y - hy), lz = cvg_tf32(xb[u].z - hz), lq = cvg_tf32(xb[u].w - hw);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(braw + off), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + off), "f"(lx), "f"(ly), "f"(lz), "f"(lq) : "memory");
+                    }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+                    if (hh < nhalf) {
+                        float hi[16], lv[16];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const float4 x = xa[4 * hh + cc];
+                            hi[4 * cc + 0] = cvg_tf32(x.x); hi[4 * cc + 1] = cvg_tf32(x.y); hi[4 * cc + 2] = cvg_tf32(x.z); hi[4 * cc + 3] = cvg_tf32(x.w);
+                            lv[4 * cc + 0] = cvg_tf32(x.x - hi[4 * cc + 0]); lv[4 * cc + 1] = cvg_tf32(x.y - hi[4 * cc + 1]);
+                            lv[4 * cc + 2] = cvg_tf32(x.z - hi[4 * cc + 2]); lv[4 * cc + 3] = cvg_tf32(x.w - hi[4 * cc + 3]);
+                        }
+                        const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + CVG_TMEM_A + l * 64u + 16u * (uint32_t)(hb0 + hh);
+                        cvg_tmem_st16(ta, hi);
+                        cvg_tmem_st16(ta + 32u, lv);
+                    }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) cvg_mbar_arrive(b_conv + 8 * l);
+            }
+        }
     } else {
-        // ---- converters (warps 2..15); warps 8..15 drain finished segments between stages and run the epilogue
-        const int ctid = tid - 64;
-        constexpr int NVEC = (int)(CVG_OP_BYTES >> 4), CT = 32 * CVG_BCONV_WARPS, ROUNDS = (NVEC + CT - 1) / CT;
-        const bool drainer = warp >= CVG_DRAIN_WARP0;
+        // ---- drain + epilogue warps (8..15): finished K segments TMEM -> float32 registers, then the item's output; never on the
+        // converters' path, so the next item's stages keep flowing during an epilogue
         const int q = warp & 3, hb = (warp - CVG_DRAIN_WARP0) >> 2;
         const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * hb);
         float acc[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-        auto drain = [&](uint32_t seg) {
-            const uint32_t tb = seg & 1u;
-            cvg_mbar_wait(b_tfull + 8 * tb, (seg >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-                uint32_t r[16];
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                               "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                             : "r"(tq + tb * CVG_TILE + 16u * gq));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[16 * gq + j] += __uint_as_float(r[j]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) cvg_mbar_arrive(b_tfree + 8 * tb);
-        };
-        uint32_t g = 0, sg0 = 0;
+        uint32_t sg = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
             const CvgItem w = cvg_item(a, item);
             const int nseg = (w.nchunks + CVG_SEG - 1) / CVG_SEG;
-            int dl = 0;   // segments of this item drained so far
-            for (int c = 0; c < w.nchunks; ++c, ++g) {
-                const uint32_t s = g % CVG_NRAW, l = g % CVG_NLO;
-                const uint32_t raw = raw0 + s * CVG_STAGE_BYTES, lo = lo0 + l * CVG_OP_BYTES;
-                if (g >= CVG_NLO) cvg_mbar_wait(b_lofree + 8 * l, ((g / CVG_NLO) - 1u) & 1u);
-                cvg_mbar_wait(b_full + 8 * s, (g / CVG_NRAW) & 1u);
-                if (!drainer) {
-                    // ---- B operand (warps 2..7): hi = rna_tf32(x) in place, lo = rna_tf32(x - hi) into the lo stage; loads first
-                    const uint32_t braw = raw + CVG_OP_BYTES;
-                    float4 x[ROUNDS];
+            for (int sl = 0; sl < nseg; ++sl, ++sg) {
+                const uint32_t tb = sg & 1u;
+                cvg_mbar_wait(b_tfull + 8 * tb, (sg >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                    for (int u = 0; u < ROUNDS; ++u) {
-                        const int i = ctid + u * CT;
-                        if (i < NVEC) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "r"(braw + 16u * (uint32_t)i));
-                    }
+                for (int gq = 0; gq < 4; ++gq) {
+                    uint32_t rr[16];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]), "=r"(rr[9]),
+                                   "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+                                 : "r"(tq + tb * CVG_TILE + 16u * gq));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int u = 0; u < ROUNDS; ++u) {
-                        const int i = ctid + u * CT;
-                        if (i < NVEC) {
-                            const float hx = cvg_tf32(x[u].x), hy = cvg_tf32(x[u].y), hz = cvg_tf32(x[u].z), hw = cvg_tf32(x[u].w);
-                            const float lx = cvg_tf32(x[u].x - hx), ly = cvg_tf32(x[u].y - hy), lz = cvg_tf32(x[u].z - hz), lw = cvg_tf32(x[u].w - hw);
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(braw + 16u * (uint32_t)i), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + 16u * (uint32_t)i), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
-                        }
-                    }
-                } else {
-                    // ---- A operand (warps 8..15): row 32 q + lane, K columns 16 hb .. 16 hb + 15 of the swizzled raw tile -> hi / lo
-                    // straight into tensor memory (tcgen05.st): the MMAs then fetch only B from shared memory
-                    const int r = 32 * q + lane;
-                    const uint32_t rowp = raw + (uint32_t)r * 128u;
-                    float hi[16], lw[16];
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const uint32_t chunk = (uint32_t)((4 * hb + cc) ^ (r & 7));
-                        float4 x;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(rowp + 16u * chunk));
-                        hi[4 * cc + 0] = cvg_tf32(x.x); hi[4 * cc + 1] = cvg_tf32(x.y); hi[4 * cc + 2] = cvg_tf32(x.z); hi[4 * cc + 3] = cvg_tf32(x.w);
-                        lw[4 * cc + 0] = cvg_tf32(x.x - hi[4 * cc + 0]); lw[4 * cc + 1] = cvg_tf32(x.y - hi[4 * cc + 1]);
-                        lw[4 * cc + 2] = cvg_tf32(x.z - hi[4 * cc + 2]); lw[4 * cc + 3] = cvg_tf32(x.w - hi[4 * cc + 3]);
-                    }
-                    const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + CVG_TMEM_A + l * 64u + 16u * (uint32_t)hb;
-                    cvg_tmem_st16(ta, hi);
-                    cvg_tmem_st16(ta + 32u, lw);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    for (int j = 0; j < 16; ++j) acc[16 * gq + j] += __uint_as_float(rr[j]);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) cvg_mbar_arrive(b_conv + 8 * l);
-                // a segment whose last stage was converted two stages ago has (almost surely) finished: drain it now
-                if (drainer && dl < nseg && c >= (dl + 1) * CVG_SEG + 1) { drain(sg0 + (uint32_t)dl); ++dl; }
+                if (lane == 0) cvg_mbar_arrive(b_tfree + 8 * tb);
             }
-            if (drainer) {
-                while (dl < nseg) { drain(sg0 + (uint32_t)dl); ++dl; }
-                // ---- epilogue: this thread owns C row 32 q + lane, columns 64 hb .. 64 hb + 63 of the tile
-                const int arow = w.tile_a * CVG_TILE + 32 * q + lane;
-                const int bcol0 = w.tile_b * CVG_TILE + 64 * hb;
-                if (a.epi == 0) {
-                    const int64_t row = a.row_base + arow;
-                    const bool live = row < a.row_end;
-                    const float y = live ? __ldg(a.X + (size_t)row * a.ld + a.d) : 0.f;
-                    const float bias_l = (bcol0 + lane < a.M) ? __ldg(a.theta_hat + (size_t)(bcol0 + lane) * a.Pst + a.d) : 0.f;
-                    const float bias_h = (bcol0 + 32 + lane < a.M) ? __ldg(a.theta_hat + (size_t)(bcol0 + 32 + lane) * a.Pst + a.d) : 0.f;
+            // ---- epilogue: this thread owns C row 32 q + lane, columns 64 hb .. 64 hb + 63 of the tile
+            const int arow = w.tile_a * CVG_TILE + 32 * q + lane;
+            const int bcol0 = w.tile_b * CVG_TILE + 64 * hb;
+            if (a.epi == 0) {
+                const int64_t row = a.row_base + arow;
+                const bool live = row < a.row_end;
+                const float y = live ? __ldg(a.X + (size_t)row * a.ld + a.d) : 0.f;
+                const float bias_l = (bcol0 + lane < a.M) ? __ldg(a.theta_hat + (size_t)(bcol0 + lane) * a.Pst + a.d) : 0.f;
+                const float bias_h = (bcol0 + 32 + lane < a.M) ? __ldg(a.theta_hat + (size_t)(bcol0 + 32 + lane) * a.Pst + a.d) : 0.f;
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) {   // fully unrolled: acc[] stays in registers
-                        const int m = bcol0 + j;
-                        const float bias = __shfl_sync(0xffffffffu, j < 32 ? bias_l : bias_h, j & 31);
-                        if (m < a.M) {   // warp-uniform
-                            const float r = live ? y - sigmoidf(acc[j] + bias) : 0.f;
-                            if (arow < a.rt_pitch) a.Rt[(size_t)m * a.rt_pitch + arow] = r;
-                        }
-                        acc[j] = 0.f;
+                for (int j = 0; j < 64; ++j) {   // fully unrolled: acc[] stays in registers
+                    const int m = bcol0 + j;
+                    const float bias = __shfl_sync(0xffffffffu, j < 32 ? bias_l : bias_h, j & 31);
+                    if (m < a.M) {   // warp-uniform
+                        const float rv = live ? y - sigmoidf(acc[j] + bias) : 0.f;
+                        if (arow < a.rt_pitch) a.Rt[(size_t)m * a.rt_pitch + arow] = rv;
                     }
-                } else {
+                    acc[j] = 0.f;
+                }
+            } else {
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) {
-                        const int m = bcol0 + j;
-                        if (arow < a.d && m < a.M) atomicAdd(a.gsum + (size_t)m * a.Pst + arow, (double)acc[j]);
-                        acc[j] = 0.f;
-                    }
+                for (int j = 0; j < 64; ++j) {
+                    const int m = bcol0 + j;
+                    if (arow < a.d && m < a.M) atomicAdd(a.gsum + (size_t)m * a.Pst + arow, (double)acc[j]);
+                    acc[j] = 0.f;
                 }
             }
-            sg0 += (uint32_t)nseg;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
