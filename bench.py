@@ -182,6 +182,23 @@ def measured_tensor_peak():
     return 1500.0, "fallback (B200_PROFILING.md dense bf16)"
 
 
+def comm_init(sg, rank, world):
+    """Gives the handle an NCCL communicator over all ranks (id broadcast through torch.distributed)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from sgmcmc_b200 import _lib
+    lib = _lib.load()
+    idbuf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        raw = (C.c_char * _lib.NCCL_ID_BYTES)()
+        _lib.check(lib.sgm_comm_unique_id(raw, _lib.NCCL_ID_BYTES))
+        idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+    idbuf = idbuf.cuda()
+    dist.broadcast(idbuf, 0)
+    _lib.check(lib.sgm_comm_init(sg.handle, idbuf.cpu().numpy().tobytes(), _lib.NCCL_ID_BYTES, rank, world))
+
+
 def many_mode_full_gradient(w, rank, world, modes):
     """Control-variate full-data gradient with one mode per chain: two tensor-core contractions (csrc/logistic_cv_gemm.cuh).
     A separate sampler (sharedMode=False) on a bounded row count; returns the cv_full_gradient_modes object."""
@@ -190,17 +207,21 @@ def many_mode_full_gradient(w, rank, world, modes):
     synth = None
     if w.get("synth"):   # c5: the rank's whole row shard unless SGM_MODES_ROWS bounds it
         synth = dict(w["synth"], rows=int(os.environ.get("SGM_MODES_ROWS", w["synth"]["rows"])))
-    sg = make_sampler(w, rank, world, modes, shared=False, synth=synth, n_iters_opt=20)
+    # N > 1: the chains (and their modes) are split over the ranks, every rank contracts its 1/N of the rows against ALL modes
+    # (all-gather of the modes, reduce-scatter of the sums): strong scaling of a fixed 4 N d M
+    sg = make_sampler(w, rank, world, max(1, modes // world), shared=False, synth=synth, n_iters_opt=20)
+    if world > 1:
+        comm_init(sg, rank, world)
     S.initSess(sg, verbose=False)
     flops = V.lastFullGradFlops(sg)
     reps = 3 if flops > 2e14 else 20
     ms, _ = V.benchFullGradient(sg, reps)
     peak, src = measured_tensor_peak()
-    rows = synth["rows"] if synth else np.asarray(w["data"]["X"]).shape[0]
+    rows = (synth["rows"] if synth else np.asarray(w["data"]["X"]).shape[0]) // world
     d = w["params"]["beta"].shape[0]
     tf = flops / (ms * 1e-3) / 1e12 if ms > 0 and flops > 0 else None
     del sg
-    return {"modes": modes, "rows_per_rank": rows, "d": d, "ms": ms, "flops": flops, "TFLOPs": tf, "bound": "tensor",
+    return {"modes": max(1, modes // world) * world, "rows_per_rank": rows, "d": d, "ms": ms, "flops": flops, "TFLOPs": tf, "TFLOPs_all_ranks": (tf * world) if tf else None, "bound": "tensor",
             "peak": peak, "peak_source": src, "frac": (tf / peak) if tf else None,
             "arithmetic": "3xTF32 (hi*hi + hi*lo + lo*hi) on tcgen05, float32-level accuracy: three TF32 MMAs per float32 product, "
                           "so the ceiling of this arithmetic is about TF32 peak / 3 = bf16 peak / 6",
@@ -298,15 +319,7 @@ def run_ours(args, w):
     t_e2e0 = time.perf_counter()
     sg = make_sampler(w, rank, world, chains_local)
     if world > 1 and w["cv"]:
-        idbuf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8)
-        if rank == 0:
-            raw = (C.c_char * _lib.NCCL_ID_BYTES)()
-            _lib.check(lib.sgm_comm_unique_id(raw, _lib.NCCL_ID_BYTES))
-            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
-        idbuf = idbuf.cuda()
-        dist.broadcast(idbuf, 0)
-        raw = idbuf.cpu().numpy().tobytes()
-        _lib.check(lib.sgm_comm_init(sg.handle, raw, _lib.NCCL_ID_BYTES, rank, world))
+        comm_init(sg, rank, world)
     sess = S.initSess(sg, verbose=False)
     init_ms, init_launches = V.lastTiming(sg)
     fg_ms, fg_bytes = V.lastFullGradTiming(sg) if w["cv"] else (0.0, 0)

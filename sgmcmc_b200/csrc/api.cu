@@ -61,6 +61,8 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(ncclComm_t*, int, /*ncclUniqueId by value*/ NcclId, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -75,9 +77,11 @@ static int load_nccl() {
     g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
+    g_nccl.ReduceScatter = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclReduceScatter");
     g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.ReduceScatter || !g_nccl.CommDestroy)
         return fail(SGM_ECOMM, "libnccl lacks required symbols");
     g_nccl.lib = lib;
     return SGM_OK;
@@ -127,6 +131,7 @@ struct sgm_handle {
     bool tmap_ok = false;
     float* Xt = nullptr; int64_t xt_pitch = 0;      // logistic, many modes: transposed copy of the features [d][xt_pitch] (tensor-core pass 2)
     float* Rt = nullptr; size_t rt_cap = 0;         // residuals of one row block, transposed [M][rt_pitch]
+    float* hat_all = nullptr; double* gsum_all = nullptr;   // row-sharded pass with one mode per chain: the modes of ALL ranks / their sums
     double fullgrad_flops = 0;                      // 4 N d M of the last tensor-core full gradient (0: not used)
     bool rhat_cached = false;   // logistic *cv, shared mode: y - s(x.beta_hat) stored in the rows' spare slot
     ChainArgs base;  // template of kernel arguments
@@ -949,7 +954,7 @@ extern "C" void sgm_destroy(sgm_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->nn) softmax_net_destroy(h->nn);
     void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,
-                    h->d_flag, h->d_idx, h->d_noise, h->store, h->Xt, h->Rt};
+                    h->d_flag, h->d_idx, h->d_noise, h->store, h->Xt, h->Rt, h->hat_all, h->gsum_all};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -960,9 +965,28 @@ extern "C" void sgm_destroy(sgm_handle* h) {
 // ------------------------------------------------------------------------------------
 // init (initSess)
 // ------------------------------------------------------------------------------------
+// Row-sharded pass with one mode per chain (logistic): every rank needs the sums of ITS chains' modes over ALL rows, so the modes
+// are all-gathered, each rank contracts its row range against the modes of every rank (the tensor-core pass, M = world x C), and a
+// reduce-scatter returns each rank the totals of its own chains.
+static bool fullgrad_gathered(const sgm_handle* h) {
+    return h->comm && h->world > 1 && h->model == SGM_MODEL_LOGISTIC && !(h->flags & SGM_FLAG_SHARED_MODE);
+}
+static int fullgrad_gather_modes(sgm_handle* h) {
+    const size_t per = (size_t)h->C * h->Pst, all = per * h->world;
+    if (!h->hat_all) { CU(cudaMalloc(&h->hat_all, all * sizeof(float))); CU(cudaMalloc(&h->gsum_all, all * sizeof(double))); }
+    const int rc = g_nccl.AllGather(h->theta_hat, h->hat_all, per, 7 /* ncclFloat32 */, h->comm, h->stream);
+    if (rc != 0) return fail(SGM_ECOMM, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return SGM_OK;
+}
+
 static int full_gradient(sgm_handle* h) {
     const int M = hat_count(h);
     const int64_t row0 = h->N * h->rank / h->world, row1 = h->N * (h->rank + 1) / h->world;
+    const bool gathered = fullgrad_gathered(h);
+    if (gathered) {
+        if (int rc = fullgrad_gather_modes(h)) return rc;
+        CU(cudaMemsetAsync(h->gsum_all, 0, (size_t)M * h->world * h->Pst * sizeof(double), h->stream));
+    }
     CU(cudaMemsetAsync(h->gsum, 0, (size_t)M * h->Pst * sizeof(double), h->stream));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
@@ -980,7 +1004,13 @@ static int full_gradient(sgm_handle* h) {
             break;
         }
         case SGM_MODEL_LOGISTIC:
-            if (int rc = launch_logistic_fullgrad(h, row0, row1, M, h->theta_hat)) return rc;
+            if (gathered) {
+                double* own = h->gsum;
+                h->gsum = h->gsum_all;
+                const int rc = launch_logistic_fullgrad(h, row0, row1, M * h->world, h->hat_all);
+                h->gsum = own;
+                if (rc) return rc;
+            } else if (int rc = launch_logistic_fullgrad(h, row0, row1, M, h->theta_hat)) return rc;
             break;
         case SGM_MODEL_SOFTMAX_NET: {
             const int rc = softmax_net_fullgrad(h->nn, h->base, row0, row1, M, h->theta_hat, h->gsum, h->stream);
@@ -990,7 +1020,10 @@ static int full_gradient(sgm_handle* h) {
     }
     CU(cudaEventRecord(e1, h->stream));
     h->last_launches += 1;
-    if (h->comm) {
+    if (gathered) {
+        const int rc = g_nccl.ReduceScatter(h->gsum_all, h->gsum, (size_t)M * h->Pst, 8 /* ncclFloat64 */, 0 /* ncclSum */, h->comm, h->stream);
+        if (rc != 0) return fail(SGM_ECOMM, "ncclReduceScatter failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    } else if (h->comm) {
         // ncclDouble = 8, ncclSum = 0
         const int rc = g_nccl.AllReduce(h->gsum, h->gsum, (size_t)M * h->Pst, 8, 0, h->comm, h->stream);
         if (rc != 0) return fail(SGM_ECOMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
@@ -1417,18 +1450,26 @@ extern "C" int sgm_bench_full_gradient(sgm_handle* h, int reps, float* ms_per_re
     if (!h->cv || !h->inited) return fail(SGM_ESTATE, "needs an initialised *cv sampler");
     if (h->model != SGM_MODEL_LOGISTIC) return fail(SGM_EINVAL, "only the logistic family is instrumented");
     if (int rc = set_device(h)) return rc;
-    const int M = hat_count(h);
+    int M = hat_count(h);
     const int64_t row0 = h->N * h->rank / h->world, row1 = h->N * (h->rank + 1) / h->world;
-    for (int warm = 0; warm < 2; ++warm) if (int rc = launch_logistic_fullgrad(h, row0, row1, M, h->theta_hat)) return rc;
-    CU(cudaEventRecord(h->ev0, h->stream));
-    for (int r = 0; r < reps; ++r) if (int rc = launch_logistic_fullgrad(h, row0, row1, M, h->theta_hat)) return rc;
+    const float* hat = h->theta_hat;
+    double* own = h->gsum;
+    if (fullgrad_gathered(h)) {   // kernels only: the modes of all ranks were gathered by sgm_init
+        if (!h->hat_all) return fail(SGM_ESTATE, "modes not gathered yet");
+        M *= h->world; hat = h->hat_all; h->gsum = h->gsum_all;
+    }
+    int rc = SGM_OK;
+    for (int warm = 0; warm < 2 && !rc; ++warm) rc = launch_logistic_fullgrad(h, row0, row1, M, hat);
+    if (!rc) CU(cudaEventRecord(h->ev0, h->stream));
+    for (int r = 0; r < reps && !rc; ++r) rc = launch_logistic_fullgrad(h, row0, row1, M, hat);
+    h->gsum = own;
+    if (rc) return rc;
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     if (ms_per_rep) *ms_per_rep = ms / reps;
     if (bytes) *bytes = (row1 - row0) * (int64_t)h->ld * 4;
-    CU(cudaMemsetAsync(h->gsum, 0, (size_t)M * h->Pst * sizeof(double), h->stream));
     return SGM_OK;
 }
 
@@ -1453,8 +1494,9 @@ extern "C" int sgm_comm_unique_id(void* id_out, int32_t id_bytes) {
 
 extern "C" int sgm_comm_init(sgm_handle* h, const void* id, int32_t id_bytes, int32_t rank, int32_t world) {
     if (!h || !id || id_bytes < SGM_NCCL_ID_BYTES || world < 1 || rank < 0 || rank >= world) return fail(SGM_EINVAL, "bad argument");
-    if (h->cv && h->C > 1 && !(h->flags & SGM_FLAG_SHARED_MODE))
-        return fail(SGM_EINVAL, "a row-sharded control-variate pass needs SGM_FLAG_SHARED_MODE (every rank must hold the same mode)");
+    if (h->cv && h->C > 1 && !(h->flags & SGM_FLAG_SHARED_MODE) && h->model != SGM_MODEL_LOGISTIC)
+        return fail(SGM_EINVAL, "a row-sharded control-variate pass needs SGM_FLAG_SHARED_MODE (every rank must hold the same mode); "
+                                "one mode per chain across ranks is implemented for the logistic family");
     if (int rc = load_nccl()) return rc;
     if (int rc = set_device(h)) return rc;
     NcclId nid;

@@ -38,6 +38,7 @@ constexpr int NN_MAXO = 16;     // output width limit
 
 // optional phase timing (debug, ChainArgs::prof): thread 0 of every CTA adds clock64() deltas per stage
 __device__ unsigned long long* nn_prof = nullptr;
+__device__ int nn_stream_updates = 1;   // 0: register-staged update of every tensor (SGM_NN_UPDATE=regs)
 __device__ long long nn_t_prev[1024];
 #define NN_TICK(slot)                                                                                   \
     if (nn_prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(nn_prof + (slot), (unsigned long long)(t_ - nn_t_prev[blockIdx.x & 1023])); nn_t_prev[blockIdx.x & 1023] = t_; }
@@ -986,6 +987,10 @@ __host__ __device__ inline int nn_tile_floats(const NNDims& dm) {
 struct NNChainState {
     float* th; float* mo; const float* hat; const float* ghat; float* G; float* Ghat;
     float zeta[MAX_TENSORS];
+    // ||W||^2 of the weight tensors: at theta when the last update of tensor t produced it (bit t of ssq_valid), at the mode
+    // once per launch (theta_hat never moves while sampling)
+    float ssq[4], ssq_hat[4];
+    unsigned ssq_valid, ssq_hat_valid;
 };
 
 // fused dynamics update of tensor t (R/dynamics.R) from the gradient sums in G (and Ghat for cv)
@@ -1000,15 +1005,130 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
         int wlo, whi;
         nn_tensor_range(dm, t - 4, wlo, whi);
         ssq_count = whi - wlo;
-        ssq = nn_sumsq(st.th + wlo, whi - wlo, sm.red);
-        if (a.cv) ssq_hat = nn_sumsq(st.hat + wlo, whi - wlo, sm.red);
+        ssq = (st.ssq_valid >> (t - 4)) & 1u ? st.ssq[t - 4] : nn_sumsq(st.th + wlo, whi - wlo, sm.red);
+        if (a.cv) {
+            if (!((st.ssq_hat_valid >> (t - 4)) & 1u)) { st.ssq_hat[t - 4] = nn_sumsq(st.hat + wlo, whi - wlo, sm.red); st.ssq_hat_valid |= 1u << (t - 4); }
+            ssq_hat = st.ssq_hat[t - 4];
+        }
     }
+    if (t < 4) st.ssq_valid &= ~(1u << t);   // this tensor moves now
     float uu = 0.f;
     const bool noisy = a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT;
     // hoisted uniforms: the precision this weight tensor's prior uses (t < 4) at theta and at the mode
     const float lam_t = (t < 4 && a.use_prior) ? st.th[dm.offl + t] : 0.f;
     const float lam_h = (t < 4 && a.use_prior && a.cv) ? st.hat[dm.offl + t] : 0.f;
     const bool vec = (lo & 3) == 0;   // 16-byte aligned tensor: whole float4 groups are loaded before any store
+    // ---- large 16-byte aligned tensors (B): stream theta / momentum / gradient sums through shared memory with TMA bulk copies
+    // (a deep ring of 2048-element chunks: ~100 KB in flight per SM without holding a register), update in shared memory,
+    // bulk-store theta / momentum back.  The ring is the H | dZ1 | tile region, dead between a gradient evaluation and the next S1.
+    const bool wr_th_ = a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_OPT;
+    const bool wr_mo_ = a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT || a.algo == ALGO_GRAD;
+    const int narr = a.cv ? 6 : 3;
+    constexpr int UCH = 4 * NN_THREADS;                         // elements per chunk: one float4 group per thread
+    const uint32_t ustage = (uint32_t)narr * UCH * 4u;
+    const int ustages = (int)((sm.ring_bytes) / ustage) < 8 ? (int)(sm.ring_bytes / ustage) : 8;
+    if (t < 4 && (lo & 3) == 0 && ((hi - lo) & 3) == 0 && (hi - lo) >= 8 * UCH && ustages >= 3 && nn_stream_updates) {
+        const int count = hi - lo, nchunks = (count + UCH - 1) / UCH;
+        const uint32_t bars = nn_smem_u32(sm.s1_bars);
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // this CTA's generic stores (gradient sums, state) -> the bulk reads
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int s2 = 0; s2 < ustages; ++s2) nn_mbar_init(bars + 8 * s2, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        const float* src[6] = {st.th + lo, st.mo + lo, st.G + lo, a.cv ? st.hat + lo : nullptr, a.cv ? st.ghat + lo : nullptr, a.cv ? st.Ghat + lo : nullptr};
+        auto issue = [&](int k) {
+            const int s2 = k % ustages;
+            const int n_el = (count - k * UCH < UCH) ? count - k * UCH : UCH;
+            const uint32_t bytes = (uint32_t)n_el * 4u, bar = bars + 8 * s2, dst = sm.ring + (uint32_t)s2 * ustage;
+            nn_mbar_expect_tx(bar, bytes * (uint32_t)narr);
+            for (int q = 0; q < narr; ++q)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + (uint32_t)q * UCH * 4u), "l"(src[q] + (size_t)k * UCH), "r"(bytes), "r"(bar) : "memory");
+        };
+        if (threadIdx.x == 0) for (int k = 0; k < ustages - 1 && k < nchunks; ++k) issue(k);
+        float ssq_new = 0.f;
+        for (int k = 0; k < nchunks; ++k) {
+            const int s2 = k % ustages;
+            const uint32_t stg = sm.ring + (uint32_t)s2 * ustage + 16u * threadIdx.x;
+            const int e0 = lo + k * UCH + 4 * (int)threadIdx.x;
+            nn_mbar_wait(bars + 8 * s2, (uint32_t)(k / ustages) & 1u);
+            if (e0 < hi) {
+                float z4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (noisy && !a.det) normal4_at((uint32_t)(e0 >> 2), a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1, z4);
+                if (noisy && a.det)
+                    for (int q = 0; q < 4; ++q)
+                        z4[q] = a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + nn_flat_of_internal(dm, e0 + q)];
+                const float4 tv = nn_lds128(stg), mv = nn_lds128(stg + UCH * 4u), gv = nn_lds128(stg + 2u * UCH * 4u);
+                float th4[4] = {tv.x, tv.y, tv.z, tv.w}, mo4[4] = {mv.x, mv.y, mv.z, mv.w};
+                const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
+                float hat4[4] = {0.f, 0.f, 0.f, 0.f}, ghat4[4] = {0.f, 0.f, 0.f, 0.f}, gh4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (a.cv) {
+                    const float4 hv = nn_lds128(stg + 3u * UCH * 4u), qv = nn_lds128(stg + 4u * UCH * 4u), pv = nn_lds128(stg + 5u * UCH * 4u);
+                    hat4[0] = hv.x; hat4[1] = hv.y; hat4[2] = hv.z; hat4[3] = hv.w; ghat4[0] = qv.x; ghat4[1] = qv.y; ghat4[2] = qv.z; ghat4[3] = qv.w;
+                    gh4[0] = pv.x; gh4[1] = pv.y; gh4[2] = pv.z; gh4[3] = pv.w;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {   // the same arithmetic, in the same order, as the register path below
+                    const float th = th4[q];
+                    float g = a.corr * g4[q];
+                    if (a.use_prior) g += -lam_t * th;
+                    if (a.cv) {
+                        float gh = a.corr * gh4[q];
+                        if (a.use_prior) gh += -lam_h * hat4[q];
+                        g = (ghat4[q] - gh) + g;   // R/setup.R:58
+                    }
+                    const float z = z4[q];
+                    if (a.algo == ALGO_SGLD) {
+                        th4[q] = th + (a.tc.half_eps[t] * g + SQRT_HALF * (a.tc.sqrt_2eps[t] * z));
+                    } else if (a.algo == ALGO_SGHMC) {
+                        float nu = mo4[q];
+                        nu += a.tc.eps[t] * g - a.tc.alpha[t] * nu + a.tc.sqrt_alpha[t] * (a.tc.sqrt_2eps[t] * z);
+                        mo4[q] = nu;
+                        th4[q] = th + nu;
+                    } else if (a.algo == ALGO_SGNHT) {
+                        float u = mo4[q];
+                        u += a.tc.eps[t] * g - u * st.zeta[t] + a.tc.sqrt_a[t] * (a.tc.sqrt_2eps[t] * z);
+                        mo4[q] = u;
+                        uu += u * u;
+                    } else if (a.algo == ALGO_OPT) {
+                        th4[q] = th + a.opt_lr * g;
+                    } else {
+                        mo4[q] = g;
+                    }
+                    ssq_new += th4[q] * th4[q];
+                }
+                if (wr_th_) nn_sts128(stg, make_float4(th4[0], th4[1], th4[2], th4[3]));
+                if (wr_mo_) nn_sts128(stg + UCH * 4u, make_float4(mo4[0], mo4[1], mo4[2], mo4[3]));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> the bulk store's reads
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int n_el = (count - k * UCH < UCH) ? count - k * UCH : UCH;
+                const uint32_t bytes = (uint32_t)n_el * 4u, srcs = sm.ring + (uint32_t)s2 * ustage;
+                if (wr_th_) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.th + lo + (size_t)k * UCH), "r"(srcs), "r"(bytes) : "memory");
+                if (wr_mo_) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.mo + lo + (size_t)k * UCH), "r"(srcs + UCH * 4u), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                // the stage of chunk k - 1 is free once ITS store has read shared memory: refill it with chunk k - 1 + ustages
+                if (k >= 1 && k - 1 + ustages < nchunks) {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    issue(k - 1 + ustages);
+                } else if (k == 0 && ustages - 1 < nchunks) {
+                    issue(ustages - 1);   // the last stage was never used
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // bulk stores (async proxy) -> later generic loads of the state
+        }
+        __syncthreads();
+        if (wr_th_) {   // (SGNHT moves theta in a later pass: its ||W||^2 is not the one accumulated here)
+            st.ssq[t] = nn_block_sum(ssq_new, sm.red);
+            st.ssq_valid |= 1u << t;
+        }
+    } else {
     // software pipeline: the loads of the NEXT group of four elements are issued before the current group's noise / arithmetic /
     // stores (one group at a time left ~24 KB in flight per SM and the pass latency-bound, profiles/r01_c4_phases.txt)
     struct Grp { float th4[4], mo4[4], g4[4], gh4[4], hat4[4], ghat4[4]; };
@@ -1104,9 +1224,10 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
             process(e0 + stride, gb);
         }
     }
+    }
     if (uu_out) *uu_out = nn_block_sum(uu, sm.red);
     __syncthreads();
-    NN_TICK(5)
+    NN_TICK(t == 1 ? 10 : (t >= 4 ? 11 : 5))
 }
 
 __host__ __device__ inline int nn_tile_floats_all(const NNDims& dm) {
@@ -1164,6 +1285,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
         st.ghat = a.cv ? a.g_hat + (size_t)c * a.hat_stride : nullptr;
         st.G = Gall + (size_t)c * a.Pst; st.Ghat = Ghatall ? Ghatall + (size_t)c * a.Pst : nullptr;
         for (int t = 0; t < MAX_TENSORS; ++t) st.zeta[t] = a.thermo[c * MAX_TENSORS + t];
+        st.ssq_valid = 0u; st.ssq_hat_valid = 0u;
         bool small_valid = false;   // shared copies of A / a / b belong to this chain's theta
         const NNMaps mpT{use_tma ? &tmX : nullptr, &tmTh, c}, mpH{use_tma ? &tmX : nullptr, &tmHat, a.hat_stride ? c : 0};
         for (int it = 0; it < a.iters; ++it) {
@@ -1428,6 +1550,11 @@ void softmax_net_tables(const SoftmaxNetWork* w, int* flat_of, int* tensor_of, i
 
 int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t stream, int* launches) {
     cudaMemcpyToSymbolAsync(nn_prof, &a.prof, sizeof(a.prof), 0, cudaMemcpyHostToDevice, stream);
+    {
+        const char* u = getenv("SGM_NN_UPDATE");
+        const int on = (u && !strcmp(u, "regs")) ? 0 : 1;
+        cudaMemcpyToSymbolAsync(nn_stream_updates, &on, sizeof(on), 0, cudaMemcpyHostToDevice, stream);
+    }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
     const int grid = a.C < sms ? a.C : sms;

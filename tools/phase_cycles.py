@@ -16,7 +16,7 @@ _lib.check(lib.sgm_run(sg.handle,NIT,0))
 lib.sgm_debug_phase_cycles(sg.handle,1,buf,16)
 v=np.array(list(buf),dtype=np.float64)
 names=['store/loop','sync pre-gather','idx+issue','wait rows','phase1','sigmoid/coef','block sum','phase2','update','sync post']
-if w['family']=='nn': names=['S1 epilogue','S2','S3 gradA','S4','S5 gradB GEMM','update','eval prologue','store','  (S1: wait loads)','  (S1: wait lo stage)']
+if w['family']=='nn': names=['S1 (total)','S2','S3 gradA','S4','S5 gradB GEMM','update A,a,b','eval prologue','store','  (S1: wait loads)','  (S1: wait lo stage)','update B','update lambdas']
 steps=w['chains']*NIT
 for n,x in zip(names,v): print(f"{n:18s} {x/steps:10.0f} cycles/chain-step {100*x/v.sum():5.1f}%")
-print('total', v.sum()/steps)
+print('total (S1 sub-counters excluded)', (v.sum()-v[8]-v[9])/steps)
