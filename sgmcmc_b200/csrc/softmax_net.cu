@@ -726,7 +726,9 @@ __device__ void nn_stage4(const NNDims& dm, const NNSmem& sm, int nb, bool first
     for (int k = threadIdx.x; k < dm.dh; k += NN_THREADS) {
         float s = 0.f;
         for (int w = 0; w < NN_WARPS; ++w) s += sm.gb[w * dm.dh + k];
-        gb_out[k] = first ? s : gb_out[k] + s;
+        const float tot = first ? s : gb_out[k] + s;
+        gb_out[k] = tot;
+        sm.gb[k] = tot;   // column k of the partials is read by this thread only: the total stays in shared memory for the fused small update
     }
     __syncthreads();
 }
@@ -991,7 +993,17 @@ struct NNChainState {
     // once per launch (theta_hat never moves while sampling)
     float ssq[4], ssq_hat[4];
     unsigned ssq_valid, ssq_hat_valid;
+    // Gauss-Seidel fast path without control variates: the small tensors never round-trip through global memory on the critical
+    // path.  theta of A / a / b lives in sm.A / sm.At / sm.a / sm.b (the copies S2 and S4 read), their momenta in registers
+    // (small index si = tid + 512 slot), the four precisions and their momenta in every thread; all writes go through to global.
+    bool fast;
+    float mo_reg[3];
+    float lam_th[4], lam_mo[4];
 };
+
+// small index <-> internal element: A first (e < offB), then a, b, lambdas (e >= offa)
+__device__ __forceinline__ int nn_small_elem(const NNDims& dm, int si) { return si < dm.offB ? si : si + (dm.offa - dm.offB); }
+__device__ __forceinline__ int nn_small_count(const NNDims& dm) { return dm.offB + (dm.P - dm.offa); }
 
 // fused dynamics update of tensor t (R/dynamics.R) from the gradient sums in G (and Ghat for cv)
 __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNSmem& sm, NNChainState& st, int t, int c,
@@ -1015,7 +1027,7 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
     float uu = 0.f;
     const bool noisy = a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT;
     // hoisted uniforms: the precision this weight tensor's prior uses (t < 4) at theta and at the mode
-    const float lam_t = (t < 4 && a.use_prior) ? st.th[dm.offl + t] : 0.f;
+    const float lam_t = (t < 4 && a.use_prior) ? (st.fast ? st.lam_th[t] : st.th[dm.offl + t]) : 0.f;
     const float lam_h = (t < 4 && a.use_prior && a.cv) ? st.hat[dm.offl + t] : 0.f;
     const bool vec = (lo & 3) == 0;   // 16-byte aligned tensor: whole float4 groups are loaded before any store
     // ---- large 16-byte aligned tensors (B): stream theta / momentum / gradient sums through shared memory with TMA bulk copies
@@ -1230,6 +1242,75 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
     NN_TICK(t == 1 ? 10 : (t >= 4 ? 11 : 5))
 }
 
+// ---- fused updates of the small tensors (fast path, see NNChainState): tensor t in {A = 0, a = 2, b = 3}
+__device__ void nn_update_small(const ChainArgs& a, const NNDims& dm, const NNSmem& sm, NNChainState& st, int t, int c, uint64_t step, int sub) {
+    const float SQRT_HALF = 0.70710678118654752440f;
+    int lo, hi;
+    nn_tensor_range(dm, t, lo, hi);
+    const float lam = a.use_prior ? st.lam_th[t] : 0.f;
+    float ssq_new = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int si = (int)threadIdx.x + NN_THREADS * k;
+        const int e = nn_small_elem(dm, si);
+        if (si < nn_small_count(dm) && e >= lo && e < hi) {
+            float th, g;
+            int ia = 0;
+            if (t == 0) { ia = (e % dm.dh) * dm.dop + e / dm.dh; th = sm.A[ia]; g = sm.gA[ia]; }
+            else if (t == 2) { th = sm.a[e - dm.offa]; g = sm.ga[e - dm.offa]; }
+            else { th = sm.b[e - dm.offb]; g = sm.gb[e - dm.offb]; }
+            g = a.corr * g;
+            if (a.use_prior) g += -lam * th;
+            const float z = a.det ? a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + nn_flat_of_internal(dm, e)]
+                                  : normal_at((uint32_t)e, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1);
+            if (a.algo == ALGO_SGLD) {
+                th = th + (a.tc.half_eps[t] * g + SQRT_HALF * (a.tc.sqrt_2eps[t] * z));
+            } else {   // ALGO_SGHMC
+                float nu = st.mo_reg[k];
+                nu += a.tc.eps[t] * g - a.tc.alpha[t] * nu + a.tc.sqrt_alpha[t] * (a.tc.sqrt_2eps[t] * z);
+                st.mo_reg[k] = nu;
+                st.mo[e] = nu;
+                th = th + nu;
+            }
+            st.th[e] = th;
+            if (t == 0) { sm.A[ia] = th; sm.At[(e / dm.dh) * dm.dh + e % dm.dh] = th; }
+            else if (t == 2) sm.a[e - dm.offa] = th;
+            else sm.b[e - dm.offb] = th;
+            ssq_new += th * th;
+        }
+    }
+    st.ssq[t] = nn_block_sum(ssq_new, sm.red);   // (its barriers also publish the new values in shared memory)
+    st.ssq_valid |= 1u << t;
+    NN_TICK(5)
+}
+
+// precision t - 4 (scalar): every thread keeps the value and its momentum; thread 0 writes them through
+__device__ void nn_update_lambda(const ChainArgs& a, const NNDims& dm, const NNSmem& sm, NNChainState& st, int t, int c, uint64_t step, int sub) {
+    const float SQRT_HALF = 0.70710678118654752440f;
+    const int w = t - 4, e = dm.offl + w;
+    int wlo, whi;
+    nn_tensor_range(dm, w, wlo, whi);
+    float th = st.lam_th[w], g = 0.f;
+    if (a.use_prior) {
+        const float ssq = (st.ssq_valid >> w) & 1u ? st.ssq[w] : nn_sumsq(st.th + wlo, whi - wlo, sm.red);
+        g = (float)(whi - wlo) / (2.0f * th) - 0.5f * ssq - 1.0f;
+    }
+    const float z = a.det ? a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + nn_flat_of_internal(dm, e)]
+                          : normal_at((uint32_t)e, a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1);
+    if (a.algo == ALGO_SGLD) {
+        th = th + (a.tc.half_eps[t] * g + SQRT_HALF * (a.tc.sqrt_2eps[t] * z));
+    } else {
+        float nu = st.lam_mo[w];
+        nu += a.tc.eps[t] * g - a.tc.alpha[t] * nu + a.tc.sqrt_alpha[t] * (a.tc.sqrt_2eps[t] * z);
+        st.lam_mo[w] = nu;
+        if (threadIdx.x == 0) st.mo[e] = nu;
+        th = th + nu;
+    }
+    st.lam_th[w] = th;
+    if (threadIdx.x == 0) st.th[e] = th;
+    NN_TICK(11)
+}
+
 __host__ __device__ inline int nn_tile_floats_all(const NNDims& dm) {
     const int t1 = nn_tile_floats(dm);
     const int need = nn_s1_ring_bytes(dm) / 4 - 2 * NN_RB * dm.dh;   // the ring spans H | dZ1 | tile
@@ -1286,6 +1367,15 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
         st.G = Gall + (size_t)c * a.Pst; st.Ghat = Ghatall ? Ghatall + (size_t)c * a.Pst : nullptr;
         for (int t = 0; t < MAX_TENSORS; ++t) st.zeta[t] = a.thermo[c * MAX_TENSORS + t];
         st.ssq_valid = 0u; st.ssq_hat_valid = 0u;
+        st.fast = seidel && !a.cv && nn_stream_updates;
+        if (st.fast) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int si = (int)threadIdx.x + NN_THREADS * k;
+                st.mo_reg[k] = si < nn_small_count(dm) ? st.mo[nn_small_elem(dm, si)] : 0.f;
+            }
+            for (int w4 = 0; w4 < 4; ++w4) { st.lam_th[w4] = st.th[dm.offl + w4]; st.lam_mo[w4] = st.mo[dm.offl + w4]; }
+        }
         bool small_valid = false;   // shared copies of A / a / b belong to this chain's theta
         const NNMaps mpT{use_tma ? &tmX : nullptr, &tmTh, c}, mpH{use_tma ? &tmX : nullptr, &tmHat, a.hat_stride ? c : 0};
         for (int it = 0; it < a.iters; ++it) {
@@ -1297,6 +1387,24 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
                                           : normal_at((uint32_t)e, a.chain0 + (uint32_t)c, word2_of(step, a.L, 0), TAG_NOISE, a.k0, a.k1);
                     st.mo[e] = 0.5f * (a.tc.sqrt_2eps[t] * z);
                 }
+                if (st.fast) {   // the register copies of the small momenta take the same refreshed values
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int si = (int)threadIdx.x + NN_THREADS * k;
+                        if (si < nn_small_count(dm)) {
+                            const int e = nn_small_elem(dm, si), t = nn_tensor_of(dm, e);
+                            const float z = a.det ? a.noise[(size_t)c * a.noise_len + nn_flat_of_internal(dm, e)]
+                                                  : normal_at((uint32_t)e, a.chain0 + (uint32_t)c, word2_of(step, a.L, 0), TAG_NOISE, a.k0, a.k1);
+                            st.mo_reg[k] = 0.5f * (a.tc.sqrt_2eps[t] * z);
+                        }
+                    }
+                    for (int w4 = 0; w4 < 4; ++w4) {
+                        const int e = dm.offl + w4;
+                        const float z = a.det ? a.noise[(size_t)c * a.noise_len + nn_flat_of_internal(dm, e)]
+                                              : normal_at((uint32_t)e, a.chain0 + (uint32_t)c, word2_of(step, a.L, 0), TAG_NOISE, a.k0, a.k1);
+                        st.lam_mo[w4] = 0.5f * (a.tc.sqrt_2eps[4 + w4] * z);
+                    }
+                }
                 __syncthreads();
             }
             for (int l = 0; l < a.L; ++l) {
@@ -1305,7 +1413,19 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
                 const int32_t* idx = a.det ? a.idx + (((size_t)c * a.iters + it) * a.L + l) * a.n : nullptr;
                 const Perm* pp = a.det ? nullptr : &perm;
                 if (a.cv) nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.hat, NEED_ALL, false, false, st.Ghat, tc, mpH);
-                if (seidel) {
+                if (seidel && st.fast) {
+                    // the small tensors are updated in shared memory / registers (written through): nothing to reload between evaluations
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_A, false, false, st.G, tc, mpT, small_valid ? 0 : LOAD_ALL);
+                    small_valid = true;
+                    nn_update_small(a, dm, sm, st, 0, c, step, sub);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_B, true, false, st.G, tc, mpT, 0);
+                    nn_update_tensor(a, dm, sm, st, 1, c, step, sub, nullptr);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_a, false, false, st.G, tc, mpT, 0);
+                    nn_update_small(a, dm, sm, st, 2, c, step, sub);
+                    nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_b, true, false, st.G, tc, mpT, 0);
+                    nn_update_small(a, dm, sm, st, 3, c, step, sub);
+                    for (int t = 4; t < 8; ++t) nn_update_lambda(a, dm, sm, st, t, c, step, sub);
+                } else if (seidel) {
                     // A   (shared A / a / b are current from the previous sub-step except b, unless the mode's were loaded)
                     nn_eval(dm, sm, a.X, a.ld, a.n, pp, idx, 0, st.th, NEED_A, false, false, st.G, tc, mpT, (a.cv || !small_valid) ? LOAD_ALL : LOAD_b);
                     small_valid = true;
