@@ -576,7 +576,9 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
     int64_t blk = ((int64_t)1 << 29) / Mpad;
     blk = blk / 256 * 256; if (blk < 256) blk = 256;
     if (blk > rows_all) blk = cdiv(rows_all, 256) * 256;
-    const size_t rt_need = (size_t)M * blk * sizeof(float);
+    const int shift = (int)(row0 & 31);            // pass 2 walks K from the 32-row aligned global row row0 - shift (TMA box starts are 16-byte aligned)
+    const int64_t pitch = blk + 32;
+    const size_t rt_need = (size_t)M * pitch * sizeof(float);
     if (rt_need > h->rt_cap) {
         if (h->Rt) cudaFree(h->Rt);
         h->Rt = nullptr; h->rt_cap = 0;
@@ -593,9 +595,13 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
     for (int64_t b0 = row0; b0 < row1; b0 += blk) {
         const int64_t b1 = (b0 + blk < row1) ? b0 + blk : row1;
         const int64_t rows = b1 - b0;
-        if (cvg_encode_2d(&mRt, h->Rt, (uint64_t)rows, (uint64_t)M, (uint64_t)blk)) return fail(SGM_ECUDA, "logistic full gradient: tensor map (R^T)");
+        if (cvg_encode_2d(&mRt, h->Rt, (uint64_t)(rows + shift), (uint64_t)M, (uint64_t)pitch)) return fail(SGM_ECUDA, "logistic full gradient: tensor map (R^T)");
+        if (shift) {
+            cvg_zero_cols_kernel<<<(unsigned)cdiv((int64_t)M * shift, 256), 256, 0, h->stream>>>(h->Rt, pitch, shift, M);
+            CU(cudaGetLastError());
+        }
         CvgArgs a{};
-        a.X = h->X; a.ld = h->ld; a.d = d; a.theta_hat = theta_hat; a.Pst = h->Pst; a.M = M; a.Rt = h->Rt; a.rt_pitch = blk; a.gsum = h->gsum;
+        a.X = h->X; a.ld = h->ld; a.d = d; a.theta_hat = theta_hat; a.Pst = h->Pst; a.M = M; a.Rt = h->Rt; a.rt_pitch = pitch; a.rt_col0 = shift; a.gsum = h->gsum;
         a.row_base = b0; a.row_end = b1; a.tiles_b = tiles_m;
         // pass 1: R^T = y - sigmoid(X theta_hat^T + bias)
         a.epi = 0; a.k_chunks = (int)cdiv(d, CVG_KC); a.a_row0 = (int)b0; a.a_k0 = 0; a.b_k0 = 0; a.k_per_split = 0; a.k_end_a = d;
@@ -605,8 +611,8 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
             const int grid = a.n_items < sms ? a.n_items : sms;
             cvg_kernel<<<grid, CVG_THREADS, CVG_SMEM, h->stream>>>(a, mX, mTh);
             CU(cudaGetLastError());
-            const int64_t warps = (int64_t)M * cdiv(rows, 4096);
-            cvg_rowsum_kernel<<<(unsigned)cdiv(warps * 32, 256), 256, 0, h->stream>>>(h->Rt, blk, rows, M, h->Pst, d, h->gsum);
+            const int64_t warps = (int64_t)M * cdiv(rows + shift, 4096);
+            cvg_rowsum_kernel<<<(unsigned)cdiv(warps * 32, 256), 256, 0, h->stream>>>(h->Rt, pitch, rows + shift, M, h->Pst, d, h->gsum);
             CU(cudaGetLastError());
         }
         // pass 2: gsum[m][k] += sum_i R^T[m][i] X^T[k][i], K (= rows) split over CTAs
@@ -614,10 +620,11 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
         const int tiles_k = (int)cdiv(d, CVG_TILE);
         // ~8 work items per CTA (static round-robin: the tail is at most one item), each at least 2 K segments long
         int64_t splits = cdiv((int64_t)sms * 8, (int64_t)tiles_k * tiles_m);
-        int64_t kps = cdiv(cdiv(rows, splits), CVG_KC * CVG_SEG) * (CVG_KC * CVG_SEG);
+        const int64_t kext = rows + shift;
+        int64_t kps = cdiv(cdiv(kext, splits), CVG_KC * CVG_SEG) * (CVG_KC * CVG_SEG);
         if (kps < 2 * CVG_KC * CVG_SEG) kps = 2 * CVG_KC * CVG_SEG;
-        splits = cdiv(rows, kps);
-        a.k_per_split = (int)kps; a.k_chunks = (int)(kps / CVG_KC); a.a_k0 = (int)b0; a.b_k0 = 0; a.k_end_a = (int)b1;
+        splits = cdiv(kext, kps);
+        a.k_per_split = (int)kps; a.k_chunks = (int)(kps / CVG_KC); a.a_k0 = (int)(b0 - shift); a.b_k0 = 0; a.k_end_a = (int)b1;
         {
             a.tiles_a = tiles_k;
             a.n_items = (int)(tiles_k * tiles_m * splits);

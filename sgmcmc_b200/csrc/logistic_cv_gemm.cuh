@@ -52,7 +52,9 @@ struct CvgArgs {
     int64_t row_base;      // global row of A-tile 0 (this launch's row block)
     int64_t row_end;       // rows >= row_end write r = 0
     const float* theta_hat; int Pst; int M;
-    float* Rt; int64_t rt_pitch;   // R^T [M][rt_pitch], column = row - row_base
+    float* Rt; int64_t rt_pitch;   // R^T [M][rt_pitch], column = rt_col0 + row - row_base
+    int rt_col0;           // (TMA box starts must be 16-byte aligned: pass 2 walks K from a 32-row aligned global row, so the
+                           //  block's first row sits at column row_base % 32 and the columns before it are zero)
     double* gsum;          // [M][Pst]: pass 1 adds the bias component (column d), pass 2 the feature components
 };
 
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                     const float bias = __shfl_sync(0xffffffffu, j < 32 ? bias_l : bias_h, j & 31);
                     if (m < a.M) {   // warp-uniform
                         const float rv = live ? y - sigmoidf(acc[j] + bias) : 0.f;
-                        if (arow < a.rt_pitch) a.Rt[(size_t)m * a.rt_pitch + arow] = rv;
+                        if (a.rt_col0 + arow < a.rt_pitch) a.Rt[(size_t)m * a.rt_pitch + a.rt_col0 + arow] = rv;
                     }
                     acc[j] = 0.f;
                 }
@@ -319,6 +321,12 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// zero the alignment columns [0, cols) of every row of R^T
+__global__ void cvg_zero_cols_kernel(float* __restrict__ Rt, int64_t pitch, int cols, int M) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M * cols) Rt[(size_t)(i / cols) * pitch + (i % cols)] = 0.f;
 }
 
 // bias component of the gradient: gsum[m][d] += sum_i R^T[m][i]   (one warp per 4096-column slice of a row of R^T)
