@@ -363,6 +363,14 @@ def run_ours(args, w):
 
     total_chains = chains_local * world
     value = total_chains * I * args.steps / dt
+    traffic, traffic_src = None, None
+    try:   # measured DRAM bytes per chain-iteration of the dominant kernel (one ncu --set full capture), scaled to this launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+        if tj:
+            traffic = tj["dram_bytes_per_chain_iter"] * chains_local * I
+            traffic_src = f"{tj['capture']}: {tj['dram_bytes_per_chain_iter']:.0f} B per chain-iteration ({tj['note']})"
+    except Exception:
+        pass
     peak, peak_src = measured_peaks()
     k_ms = float(np.mean(kernel_ms))
     achieved = chains_local * I * w["bytes_per_chain_iter"] / (k_ms * 1e-3) / 1e9
@@ -375,7 +383,8 @@ def run_ours(args, w):
                    "l2": "inputs larger than L2" if args.workload in ("c3", "c4", "c5") else "dataset smaller than L2 (stated; not an HBM-bound case)",
                    "sampling": "device Philox, without replacement", "shared_mode": bool(w["cv"])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "persistent chain kernel (gather + gradient + update + store)",
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": chains_local * I * w["bytes_per_chain_iter"],
+                     "kernel": "persistent chain kernel (gather + gradient + update + store)",
                      "kernel_ms_per_launch": k_ms, "bytes_per_chain_iter": w["bytes_per_chain_iter"], "peak_source": peak_src,
                      "note": w["bound_note"]},
         "clocks": clocks,
