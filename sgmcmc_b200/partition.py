@@ -15,3 +15,18 @@ def chain_range(rank: int, world: int, n_chains: int):
 def row_range(rank: int, world: int, n_rows: int):
     """Dataset rows [lo, hi) whose gradient ``rank`` sums (matches api.cu: N*rank/world)."""
     return n_rows * rank // world, n_rows * (rank + 1) // world
+
+
+def aligned_k_walk(row0: int, rows: int, block: int, align: int = 32):
+    """Pass 2 of the many-mode control-variate gradient (csrc/api.cu launch_logistic_fullgrad_tc): the K walk over this rank's
+    data rows starts at the ``align``-row aligned global row below ``row0`` (a TMA box start must be 16-byte aligned), so the
+    first row of every block sits at column ``shift`` of the transposed residual buffer and the columns before it are zero.
+    Returns [(k_start_global, shift, rows_in_block)] per row block."""
+    shift = row0 % align
+    out = []
+    b0 = row0
+    while b0 < row0 + rows:
+        n = min(block, row0 + rows - b0)
+        out.append((b0 - shift, shift, n))
+        b0 += block
+    return out
