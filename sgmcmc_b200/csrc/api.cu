@@ -625,6 +625,10 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
         if (kps < 2 * CVG_KC * CVG_SEG) kps = 2 * CVG_KC * CVG_SEG;
         splits = cdiv(kext, kps);
         a.k_per_split = (int)kps; a.k_chunks = (int)(kps / CVG_KC); a.a_k0 = (int)(b0 - shift); a.b_k0 = 0; a.k_end_a = (int)b1;
+        // a TMA box whose inner start coordinate is not 16-byte aligned is an illegal instruction on the device: refuse on the host
+        if ((a.a_k0 & 3) || (a.k_per_split & 3) || (h->xt_pitch & 3) || (pitch & 3) || (h->ld & 3) || (h->Pst & 3))
+            return fail(SGM_EINVAL, "logistic full gradient: unaligned TMA coordinates (k0 %d, split %d, pitches %lld / %lld)", a.a_k0, a.k_per_split,
+                        (long long)h->xt_pitch, (long long)pitch);
         {
             a.tiles_a = tiles_k;
             a.n_items = (int)(tiles_k * tiles_m * splits);
