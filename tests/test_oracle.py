@@ -128,3 +128,56 @@ def test_sghmc_refresh_and_substeps_consume_expected_inputs():
     case = make_case("mixture")
     ch = OS.Chain(OS.Posterior(case["om"], case["N"], case["n"]), case["data"], case["params"], "sghmc", 2e-5, L=5)
     assert ch.n_sub() == 5 and ch.noise_len() == 6 * 4
+
+
+@pytest.mark.parametrize("case_name", ["gauss1d", "gauss3d_fullcov", "mixture", "logistic5", "softmaxnet_small"])
+def test_closed_form_gradients_match_finite_differences(case_name):
+    """The closed-form gradients (what the CUDA kernels hard-wire) are the derivatives of the oracle's own
+    log-densities: central differences in float64 on a minibatch, every parameter tensor, a handful of coordinates each."""
+    case = make_case(case_name)
+    rs = np.random.RandomState(3)
+    om = case["om"]
+    batch = OS.take(case["data"], rs.choice(case["N"], 25, replace=False))
+    params = {k: np.array(v, dtype=np.float64) for k, v in case["params"].items()}
+    g_ll, g_lp = om.grad_loglik(params, batch, np.float64), om.grad_logprior(params, np.float64)
+
+    def f(p):
+        return float(om.loglik(p, batch, np.float64)) + float(om.logprior(p, np.float64))
+
+    for k, v in params.items():
+        flat = v.reshape(-1)
+        for i in rs.choice(flat.size, min(5, flat.size), replace=False):
+            h = 1e-5 * max(1.0, abs(flat[i]))
+            pp = {q: np.array(w, dtype=np.float64) for q, w in params.items()}
+            pm = {q: np.array(w, dtype=np.float64) for q, w in params.items()}
+            pp[k].reshape(-1)[i] += h
+            pm[k].reshape(-1)[i] -= h
+            num = (f(pp) - f(pm)) / (2 * h)
+            ana = float(np.asarray(g_ll[k]).reshape(-1)[i] + np.asarray(g_lp[k]).reshape(-1)[i])
+            assert abs(num - ana) <= 1e-5 * max(1.0, abs(ana)), (case_name, k, int(i), num, ana)
+
+
+def test_three_term_tf32_split_keeps_float32_accuracy():
+    """Arithmetic of the tensor-core contractions (csrc/logistic_cv_gemm.cuh, csrc/softmax_net.cu): x = hi + lo with both halves
+    rounded to nearest TF32 (ties away: (bits + 0x1000) & 0xFFFFE000), products hi*hi' + hi*lo' + lo*hi'.  Emulated here in
+    numpy: the dropped lo*lo' term and the roundings leave a relative error of a few 1e-7 of sum|x x'| -- float32 level, against
+    ~5e-4 for a single TF32 product."""
+    def rna_tf32(x):
+        b = x.astype(np.float32).view(np.uint32)
+        return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    rs = np.random.RandomState(7)
+    A = rs.randn(64, 512).astype(np.float32)
+    B = rs.randn(48, 512).astype(np.float32)
+    a_hi = rna_tf32(A); a_lo = rna_tf32(A - a_hi)
+    b_hi = rna_tf32(B); b_lo = rna_tf32(B - b_hi)
+    # every operand is exactly representable in TF32 (13 low mantissa bits clear)
+    for t in (a_hi, a_lo, b_hi, b_lo):
+        assert not np.any(t.view(np.uint32) & np.uint32(0x1FFF))
+    exact = A.astype(np.float64) @ B.astype(np.float64).T
+    mass = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    d = np.float64
+    split = a_hi.astype(d) @ b_hi.astype(d).T + a_hi.astype(d) @ b_lo.astype(d).T + a_lo.astype(d) @ b_hi.astype(d).T
+    single = a_hi.astype(d) @ b_hi.astype(d).T
+    assert (np.abs(split - exact) / mass).max() < 1e-6
+    assert (np.abs(single - exact) / mass).max() > 1e-5      # why one TF32 pass is not enough for the 1e-5 parity bound
