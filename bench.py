@@ -199,6 +199,21 @@ def comm_init(sg, rank, world):
     _lib.check(lib.sgm_comm_init(sg.handle, idbuf.cpu().numpy().tobytes(), _lib.NCCL_ID_BYTES, rank, world))
 
 
+def attach_peer_shards(sg, rank, world):
+    """Every rank keeps its own N rows; the peers' shards are mapped through CUDA IPC so the chains sample from world x N rows."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from sgmcmc_b200 import _lib
+    lib = _lib.load()
+    mine = (C.c_char * _lib.IPC_HANDLE_BYTES)()
+    _lib.check(lib.sgm_dataset_ipc_handle(sg.handle, mine, _lib.IPC_HANDLE_BYTES))
+    t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone().cuda()
+    allh = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allh, t)
+    _lib.check(lib.sgm_attach_peer_shards(sg.handle, b"".join(x.cpu().numpy().tobytes() for x in allh), world, rank))
+
+
 def many_mode_full_gradient(w, rank, world, modes):
     """Control-variate full-data gradient with one mode per chain: two tensor-core contractions (csrc/logistic_cv_gemm.cuh).
     A separate sampler (sharedMode=False) on a bounded row count; returns the cv_full_gradient_modes object."""
@@ -317,7 +332,11 @@ def run_ours(args, w):
     # ---- end-to-end leg (public API, host buffers): Setup (dataset H2D) + initSess + K x [run + copy-out (D2H)]
     barrier()
     t_e2e0 = time.perf_counter()
-    sg = make_sampler(w, rank, world, chains_local)
+    sharded = bool(args.peer_shards and world > 1 and w["family"] == "logistic")
+    synth_main = dict(w["synth"], seed=w["synth"].get("seed", 13) + rank) if (sharded and w.get("synth")) else None   # different rows per rank
+    sg = make_sampler(w, rank, world, chains_local, synth=synth_main)
+    if sharded:
+        attach_peer_shards(sg, rank, world)
     if world > 1 and w["cv"]:
         comm_init(sg, rank, world)
     sess = S.initSess(sg, verbose=False)
@@ -381,7 +400,9 @@ def run_ours(args, w):
         "config": {"workload": args.workload, "desc": w["desc"], "chains_per_gpu": chains_local, "chains_total": total_chains,
                    "iters_per_step": I, "minibatch": w["n"], "store": "device-resident chain, every iteration",
                    "l2": "inputs larger than L2" if args.workload in ("c3", "c4", "c5") else "dataset smaller than L2 (stated; not an HBM-bound case)",
-                   "sampling": "device Philox, without replacement", "shared_mode": bool(w["cv"])},
+                   "sampling": "device Philox, without replacement", "shared_mode": bool(w["cv"]),
+                   "dataset": (f"sharded over {world} ranks, peers mapped by CUDA IPC: chains sample from {world}x the rows, "
+                               f"{world - 1}/{world} of the gathered bytes arrive over NVLink") if sharded else "replicated per GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": chains_local * I * w["bytes_per_chain_iter"],
                      "kernel": "persistent chain kernel (gather + gradient + update + store)",
@@ -401,6 +422,9 @@ def run_ours(args, w):
                                     "rows_per_rank": fg_bytes // (16 * (w["params"]["beta"].shape[0] // 4 + 1)) if w["family"] == "logistic" else None,
                                     "init_ms_total": init_ms,
                                     "note": "one mode (shared by all chains): HBM-bound stream, not a GEMM; bytes = rows x row stride"}
+    if sharded:   # unmap on every rank before any owner frees its shard
+        _lib.check(lib.sgm_detach_peer_shards(sg.handle))
+        barrier()
     if w["cv"] and w["family"] == "logistic" and not args.no_modes:
         del sg, sess
         line["cv_full_gradient_modes"] = many_mode_full_gradient(w, rank, world, args.modes)
@@ -427,6 +451,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--modes", type=int, default=1024, help="modes of the many-mode control-variate full gradient leg (logistic *cv workloads)")
     ap.add_argument("--no-modes", action="store_true")
+    ap.add_argument("--peer-shards", action="store_true",
+                    help="N > 1, logistic workloads: every rank keeps its own rows and maps the peers' (the c5 config at N = world x rows/GPU)")
     args = ap.parse_args()
     w = workload(args.workload, args.chains)
     if args.impl == "reference":

@@ -211,6 +211,16 @@ int sgm_comm_unique_id(void* id_out, int32_t id_bytes);
 /* After this, sgm_init computes the full-data gradient on rows [rank*N/world, (rank+1)*N/world)
  * and all-reduces (sum, float32) the [n_chains][P] result with NCCL. */
 int sgm_comm_init(sgm_handle* h, const void* id, int32_t id_bytes, int32_t rank, int32_t world);
+/* Dataset sharded over ranks (one process per GPU, equal shards of N rows each; new: the reference is single-process).
+ * sgm_dataset_ipc_handle writes the CUDA IPC handle (64 bytes) of this rank's device dataset; after an all-gather of the
+ * handles, sgm_attach_peer_shards maps the peers' shards: the chains then sample minibatches from all world x N rows
+ * (remote rows are loaded over NVLink / NVSwitch), N / n is the global ratio, and the control-variate pass sums this rank's
+ * shard (needs sgm_comm_init for the reduction).  Logistic family, before sgm_init. */
+#define SGM_IPC_HANDLE_BYTES 64
+int sgm_dataset_ipc_handle(sgm_handle* h, void* out, int32_t out_bytes);
+int sgm_attach_peer_shards(sgm_handle* h, const void* handles, int32_t world, int32_t rank);
+/* Unmaps the peers' shards: every rank calls it, then a barrier, then the handles may be destroyed in any order. */
+int sgm_detach_peer_shards(sgm_handle* h);
 
 const char* sgm_last_error(void);
 const char* sgm_version(void);

@@ -18,6 +18,7 @@ MODEL_GAUSS_MEAN, MODEL_MIXTURE2, MODEL_LOGISTIC, MODEL_SOFTMAX_NET = 1, 2, 3, 4
 ALGO_SGLD, ALGO_SGHMC, ALGO_SGNHT = 1, 2, 3
 FLAG_SHARED_MODE = 1
 NCCL_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 class SgmArray(C.Structure):
@@ -75,6 +76,9 @@ SYMBOLS = {
     "sgm_last_fullgrad_timing": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "sgm_bench_full_gradient": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "sgm_last_fullgrad_flops": (C.c_int, [_H, _PD]),
+    "sgm_dataset_ipc_handle": (C.c_int, [_H, C.c_void_p, C.c_int32]),
+    "sgm_attach_peer_shards": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "sgm_detach_peer_shards": (C.c_int, [_H]),
     "sgm_debug_phase_cycles": (C.c_int, [_H, C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),
     "sgm_copy_dataset": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, _PD]),
     "sgm_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -131,6 +131,11 @@ struct sgm_handle {
     bool tmap_ok = false;
     float* Xt = nullptr; int64_t xt_pitch = 0;      // logistic, many modes: transposed copy of the features [d][xt_pitch] (tensor-core pass 2)
     float* Rt = nullptr; size_t rt_cap = 0;         // residuals of one row block, transposed [M][rt_pitch]
+    // dataset row-sharded over the ranks, peers mapped through CUDA IPC (sgm_attach_peer_shards): every rank holds N rows, the
+    // chains sample from world x N rows and gather remote rows over NVLink; the control-variate pass sums the local shard
+    int n_shards = 1;
+    void* peer_base[16] = {nullptr};
+    const float** d_shard_ptr = nullptr;
     float* hat_all = nullptr; double* gsum_all = nullptr;   // row-sharded pass with one mode per chain: the modes of ALL ranks / their sums
     double fullgrad_flops = 0;                      // 4 N d M of the last tensor-core full gradient (0: not used)
     bool rhat_cached = false;   // logistic *cv, shared mode: y - s(x.beta_hat) stored in the rows' spare slot
@@ -413,6 +418,7 @@ static int launch_logistic_fullgrad_gv(sgm_handle* h, int64_t row0, int64_t row1
 static bool logistic_use_staged(const sgm_handle* h, const ChainArgs& a) {
     const char* force = getenv("SGM_LOGISTIC_KERNEL");
     if (force && !strcmp(force, "generic")) return false;
+    if (h->n_shards > 1) return false;   // the TMA row map covers the local shard only
     return h->ld <= 128 && a.n <= LS_MAX_R * LS_THREADS && ls_smem_bytes(h->ld, a.n) <= 227 * 1024;
 }
 
@@ -488,6 +494,7 @@ static int launch_logistic_ring_t(sgm_handle* h, const ChainArgs& a) {
 // long rows: warp-specialised TMA ring (logistic_ring.cuh)
 static bool logistic_use_ring(const sgm_handle* h, const ChainArgs& a) {
     const char* force = getenv("SGM_LOGISTIC_KERNEL");
+    if (h->n_shards > 1) return false;
     if (!(force && !strcmp(force, "ring"))) return false;   // opt-in: measured slower than the register-staged kernel (profiles/r01_c5_ring_vs_generic.txt)
     const int V = (h->ld / 4 + 31) / 32;
     return h->ld > 128 && V >= 2 && V <= 9 && lr_smem_bytes(h->ld, a.n) <= 227 * 1024;
@@ -964,6 +971,8 @@ extern "C" void sgm_destroy(sgm_handle* h) {
     if (h->stream) cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->nn) softmax_net_destroy(h->nn);
+    for (int r = 0; r < 16; ++r) if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    if (h->d_shard_ptr) cudaFree((void*)h->d_shard_ptr);
     void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,
                     h->d_flag, h->d_idx, h->d_noise, h->store, h->Xt, h->Rt, h->hat_all, h->gsum_all};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -992,7 +1001,8 @@ static int fullgrad_gather_modes(sgm_handle* h) {
 
 static int full_gradient(sgm_handle* h) {
     const int M = hat_count(h);
-    const int64_t row0 = h->N * h->rank / h->world, row1 = h->N * (h->rank + 1) / h->world;
+    // replicated dataset: this rank sums its 1/world slice; sharded dataset: its whole local shard
+    const int64_t row0 = h->n_shards > 1 ? 0 : h->N * h->rank / h->world, row1 = h->n_shards > 1 ? h->N : h->N * (h->rank + 1) / h->world;
     const bool gathered = fullgrad_gathered(h);
     if (gathered) {
         if (int rc = fullgrad_gather_modes(h)) return rc;
@@ -1124,6 +1134,14 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
             CU(cudaGetLastError());
             h->rhat_cached = true;
             h->last_launches += 1;
+        }
+        if (h->n_shards > 1) {
+            // peers read the residuals cached in OUR rows: nobody may sample before every rank has written its shard.  A one-double
+            // all-reduce enqueued after the cache kernel completes only when all ranks have reached it (stream-ordered rendezvous).
+            if (!h->comm) return fail(SGM_ESTATE, "a sharded dataset with control variates needs sgm_comm_init (reduction of the shard sums)");
+            const int rc = g_nccl.AllReduce(h->gsum, h->gsum, 1, 8, 0, h->comm, h->stream);
+            if (rc != 0) return fail(SGM_ECOMM, "ncclAllReduce (rendezvous) failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+            CU(cudaStreamSynchronize(h->stream));
         }
     }
     h->inited = true;
@@ -1462,7 +1480,7 @@ extern "C" int sgm_bench_full_gradient(sgm_handle* h, int reps, float* ms_per_re
     if (h->model != SGM_MODEL_LOGISTIC) return fail(SGM_EINVAL, "only the logistic family is instrumented");
     if (int rc = set_device(h)) return rc;
     int M = hat_count(h);
-    const int64_t row0 = h->N * h->rank / h->world, row1 = h->N * (h->rank + 1) / h->world;
+    const int64_t row0 = h->n_shards > 1 ? 0 : h->N * h->rank / h->world, row1 = h->n_shards > 1 ? h->N : h->N * (h->rank + 1) / h->world;
     const float* hat = h->theta_hat;
     double* own = h->gsum;
     if (fullgrad_gathered(h)) {   // kernels only: the modes of all ranks were gathered by sgm_init
@@ -1500,6 +1518,54 @@ extern "C" int sgm_comm_unique_id(void* id_out, int32_t id_bytes) {
     if (int rc = load_nccl()) return rc;
     const int rc = g_nccl.GetUniqueId(id_out);
     if (rc != 0) return fail(SGM_ECOMM, "ncclGetUniqueId failed (%d)", rc);
+    return SGM_OK;
+}
+
+// ---- dataset sharded over ranks, peers mapped through CUDA IPC ------------------------------------------------------------
+extern "C" int sgm_dataset_ipc_handle(sgm_handle* h, void* out, int32_t out_bytes) {
+    if (!h || !out || out_bytes < (int32_t)sizeof(cudaIpcMemHandle_t)) return fail(SGM_EINVAL, "bad argument");
+    if (int rc = set_device(h)) return rc;
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, h->X));
+    memcpy(out, &mh, sizeof mh);
+    return SGM_OK;
+}
+
+extern "C" int sgm_attach_peer_shards(sgm_handle* h, const void* handles, int32_t world, int32_t rank) {
+    if (!h || !handles || world < 1 || world > 16 || rank < 0 || rank >= world) return fail(SGM_EINVAL, "bad argument");
+    if (h->model != SGM_MODEL_LOGISTIC) return fail(SGM_EINVAL, "a dataset sharded over ranks is implemented for the logistic family");
+    if (h->inited) return fail(SGM_ESTATE, "attach the peer shards before sgm_init");
+    if ((uint64_t)h->N * (uint64_t)world > 0xFFFFFFFFull) return fail(SGM_EINVAL, "more than 2^32 rows in total");
+    if (int rc = set_device(h)) return rc;
+    std::vector<const float*> table((size_t)world, nullptr);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { table[r] = h->X; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char*)handles + (size_t)r * sizeof mh, sizeof mh);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_base[r] = p;
+        table[r] = (const float*)p;
+    }
+    CU(cudaMalloc((void**)&h->d_shard_ptr, sizeof(const float*) * (size_t)world));
+    CU(cudaMemcpy((void*)h->d_shard_ptr, table.data(), sizeof(const float*) * (size_t)world, cudaMemcpyHostToDevice));
+    h->n_shards = world;
+    // every rank holds h->N rows (equal shards); the chains sample from all of them, N / n is the global ratio (R/setup.R:117)
+    const uint64_t n_global = (uint64_t)h->N * (uint64_t)world;
+    h->base.N = (uint32_t)n_global; h->base.perm_bits = perm_bits((uint32_t)n_global);
+    h->base.corr = (float)((double)n_global / (double)h->n);
+    h->base.shard_ptr = h->d_shard_ptr; h->base.shard_rows = (uint32_t)h->N; h->base.n_shards = world;
+    return SGM_OK;
+}
+
+// unmap the peers' shards (every rank calls this, THEN a barrier, THEN the owners may free their datasets)
+extern "C" int sgm_detach_peer_shards(sgm_handle* h) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    if (int rc = set_device(h)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < 16; ++r) if (h->peer_base[r]) { cudaIpcCloseMemHandle(h->peer_base[r]); h->peer_base[r] = nullptr; }
+    h->n_shards = 1; h->base.n_shards = 0; h->base.shard_ptr = nullptr;
+    h->inited = false;   // the sampler state referred to the global row space
     return SGM_OK;
 }
 

@@ -74,9 +74,23 @@ struct ChainArgs {
     int* diverged;
     // optional phase timing (debug): thread 0 of every CTA adds clock64() deltas, [phase] slots
     unsigned long long* prof;
+    // dataset row-sharded over ranks and peer-mapped (loads over NVLink / NVSwitch): global row r lives in shard r / shard_rows.
+    // n_shards <= 1: the whole dataset is X (every path except the logistic long-row kernel ignores these fields)
+    const float* const* shard_ptr;   // device table [n_shards] of the shards' base pointers (own shard = X)
+    uint32_t shard_rows;
+    int n_shards;
     int rhat_cached;  // logistic *cv with one shared mode: y - s(x.beta_hat + bias_hat) is stored at column d + 1 of every row
     int gather_tma;   // logistic short-row kernel: 1 = one TMA bulk copy per row, 0 = 16-byte cp.async
 };
+
+// base pointer of dataset row `row` (global index when the dataset is sharded over ranks)
+__device__ __forceinline__ const float* row_ptr(const ChainArgs& a, uint32_t row) {
+    if (a.n_shards > 1) {
+        const uint32_t s = row / a.shard_rows;
+        return a.shard_ptr[s] + (size_t)(row - s * a.shard_rows) * a.ld;
+    }
+    return a.X + (size_t)row * a.ld;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -88,7 +88,7 @@ __device__ __forceinline__ void logi_pass(const ChainArgs& a, const LogiSmem& sm
         float4 x[V];
         if (valid) {
             const uint32_t row = idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j);
-            const float* __restrict__ xr = a.X + (size_t)row * a.ld;
+            const float* __restrict__ xr = row_ptr(a, row);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const int col = 4 * (lg + G * v);
@@ -380,7 +380,7 @@ __global__ void logistic_logpost_kernel(const ChainArgs a, uint32_t word2, const
     float ll = 0.f;
     for (int j = tid; j < a.n; j += blockDim.x) {
         const uint32_t row = (a.det == 2) ? (uint32_t)j : (idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j));   // det == 2: rows 0..n-1
-        const float* xr = a.X + (size_t)row * a.ld;
+        const float* xr = (a.det == 2) ? a.X + (size_t)row * a.ld : row_ptr(a, row);   // det == 2: a held-out set of this rank
         float z = 0.f;
         for (int k = 0; k < a.d; ++k) z += xr[k] * th[k];
         z += th[a.d];

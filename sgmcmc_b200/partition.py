@@ -30,3 +30,9 @@ def aligned_k_walk(row0: int, rows: int, block: int, align: int = 32):
         out.append((b0 - shift, shift, n))
         b0 += block
     return out
+
+
+def shard_of_row(row: int, shard_rows: int):
+    """Dataset sharded over ranks in equal shards (csrc/common.cuh row_ptr, sgm_attach_peer_shards): global row -> (owning rank,
+    local row).  The chains sample global rows; rows of other ranks are loaded through the peer mapping."""
+    return row // shard_rows, row % shard_rows

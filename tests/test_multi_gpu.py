@@ -17,3 +17,14 @@ def test_row_sharded_pass_with_one_mode_per_chain(lib):
            "--master-port", "29511", os.path.join(ROOT, "tools", "check_sharded_modes.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.xfail(reason="written after gpurun was closed for this round: not yet run on a GPU box", strict=False)
+def test_dataset_sharded_over_ranks_and_peer_mapped(lib):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29513", os.path.join(ROOT, "tools", "check_peer_shards.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]

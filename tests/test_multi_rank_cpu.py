@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import samplers as OS
-from sgmcmc_b200.partition import aligned_k_walk, chain_range, row_range
+from sgmcmc_b200.partition import aligned_k_walk, chain_range, row_range, shard_of_row
 from tests.cases import make_case
 
 
@@ -109,3 +109,12 @@ def test_pass2_k_walk_is_aligned_and_covers_the_shard():
                     assert k0 + shift == lo + covered            # first data row of the block
                     covered += n
                 assert covered == hi - lo
+
+
+def test_global_rows_map_onto_equal_shards():
+    for world, per in ((2, 2000), (8, 12500000)):
+        rows = np.array([0, 1, per - 1, per, world * per - 1])
+        for r in rows:
+            rank, local = shard_of_row(int(r), per)
+            assert 0 <= rank < world and 0 <= local < per and rank * per + local == r
+        assert world * per < 2 ** 32          # the kernels carry global rows as uint32
