@@ -39,6 +39,7 @@ constexpr int NN_MAXO = 16;     // output width limit
 // optional phase timing (debug, ChainArgs::prof): thread 0 of every CTA adds clock64() deltas per stage
 __device__ unsigned long long* nn_prof = nullptr;
 __device__ int nn_stream_updates = 1;   // 0: register-staged update of every tensor (SGM_NN_UPDATE=regs)
+__device__ int nn_s5_tmem = 0;          // 1: S5 with the X tile on the tensor-memory side (SGM_NN_S5=tmem; NOT YET RUN ON A GPU)
 __device__ long long nn_t_prev[1024];
 #define NN_TICK(slot)                                                                                   \
     if (nn_prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(nn_prof + (slot), (unsigned long long)(t_ - nn_t_prev[blockIdx.x & 1023])); nn_t_prev[blockIdx.x & 1023] = t_; }
@@ -912,6 +913,154 @@ __device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __
     }
 }
 
+#ifdef NN_ENABLE_S5_TMEM
+// ---------------------------------------------------------------------------------------------------------
+// S5, TMA-fed, X on the tensor-memory side -- written at the end of round 1, NOT YET RUN ON A GPU.  Compiled only with
+// -DNN_ENABLE_S5_TMEM (SGM_BUILD_DEFS=-DNN_ENABLE_S5_TMEM python __graft_entry__.py --force), then selected by SGM_NN_S5=tmem.
+//   GB^T[j][n] = sum_r X[row_r][j] dZ1[r][n]      M = 128 inputs j per tile, N = Npad hidden units, K = Kp = round8(nb) rows
+//   * B operand: dZ1^T staged ONCE per call, K-major no-swizzle core matrices, hi / lo (same layout the register-staged S5 uses for A);
+//   * A operand: the X tile arrives as four gather4 blocks [Kp rows][32 inputs] (the SW128 tiles S1 loads); block q belongs to the
+//     warps of lane quarter q, each thread transposes its lane's column (one ld.shared.32 per row: a row of a block is one
+//     128-byte line, so a warp reads 32 distinct banks) into TMEM columns r (hi) / 128 + r (lo) with tcgen05.st;
+//   * 3 x Kp / 8 A-from-TMEM MMAs per tile into one of two TMEM accumulators; the epilogue of tile t - 1 (lane = input j: coalesced
+//     stores to GB[n][j]) runs while the MMAs of tile t execute; the TMA requests of tile t + 2 go out as soon as tile t is in TMEM.
+// TMEM: accumulators [0, 2 Npad), A hi [256, 384), A lo [384, 512).  Shared memory (inside the H | dZ1 | tile ring; dZ1 is read
+// before anything overwrites it): two raw X stages of 4 x Kp x 128 B at the start, dZ1^T hi / lo behind them.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nn_umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void nn_tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+
+// the two raw stages must end behind dZ1 (H | dZ1 come first in the ring; dZ1 is read while the B operand is written behind the stages)
+__device__ __forceinline__ bool nn_s5_tmem_fits(const NNDims& dm, int nb, uint32_t ring_bytes) {
+    const int Kp = (nb + 7) & ~7, Npad = (dm.dh + 15) & ~15;
+    const long stages = 2L * 4 * Kp * 128, need = stages + 2L * (Kp / 4) * Npad * 16;
+    return Kp <= 128 && Npad <= 112 && need <= (long)ring_bytes && stages >= 2L * NN_RB * dm.dh * 4;
+}
+
+__device__ __noinline__ void nn_stage5_tmem(const NNDims& dm, const NNSmem& sm, const CUtensorMap* xmap, int nb, bool first,
+                                            float* __restrict__ GB, TcCtx& tc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = warp & 3, cg = warp >> 2;
+    const int Kp = (nb + 7) & ~7, Npad = (dm.dh + 15) & ~15, KG = Kp >> 2;
+    const uint32_t BLK = (uint32_t)Kp * 128u, STG = 4u * BLK;
+    const uint32_t x0 = sm.ring, bop = sm.ring + 2u * STG;            // raw X stages | dZ1^T hi | dZ1^T lo
+    const uint32_t LBOB = (uint32_t)Npad * 16u, PLANE = (uint32_t)KG * LBOB;
+    const int ntiles = (dm.din + 127) >> 7;
+    const uint32_t bars = nn_smem_u32(sm.s1_bars);
+    const uint32_t b_full = bars, b_dfull = bars + 16;               // full[2] | dfull[2]
+    const uint32_t idesc = nn_umma_idesc(NN_RB, Npad);
+    // ---- B operand from dZ1 (shared, [r][dh]); rows >= nb and hidden units >= dh are zero
+    __syncthreads();
+    for (int u = tid; u < Npad * KG; u += NN_THREADS) {
+        const int n = u % Npad, kg = u / Npad, r = 4 * kg;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+        if (n < dm.dh) {
+            v.x = (r + 0 < nb) ? sm.dZ1[(r + 0) * dm.dh + n] : 0.f; v.y = (r + 1 < nb) ? sm.dZ1[(r + 1) * dm.dh + n] : 0.f;
+            v.z = (r + 2 < nb) ? sm.dZ1[(r + 2) * dm.dh + n] : 0.f; v.w = (r + 3 < nb) ? sm.dZ1[(r + 3) * dm.dh + n] : 0.f;
+        }
+        nn_split4(v, hi, lo);
+        nn_sts128(bop + (uint32_t)(kg * Npad + n) * 16u, hi);
+        nn_sts128(bop + PLANE + (uint32_t)(kg * Npad + n) * 16u, lo);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) nn_mbar_init(bars + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // operand stores -> the tensor core
+    __syncthreads();                                                   // ... and dZ1 may now be overwritten by the X stages
+    auto issue_tile = [&](int t) {   // warp 0: 4 blocks x Kp / 4 gather4 requests
+        const uint32_t dst = x0 + (uint32_t)(t & 1) * STG, bar = b_full + 8 * (t & 1);
+        if (lane == 0) nn_mbar_expect_tx(bar, STG);
+        __syncwarp();
+        for (int i = lane; i < 4 * KG; i += 32) {
+            const int b = i / KG, g = i % KG, r = 4 * g;
+            nn_tma_gather4(dst + (uint32_t)b * BLK + (uint32_t)g * 512u, xmap, 128 * t + 32 * b, sm.rows[r < nb ? r : 0], sm.rows[r + 1 < nb ? r + 1 : 0],
+                           sm.rows[r + 2 < nb ? r + 2 : 0], sm.rows[r + 3 < nb ? r + 3 : 0], bar);
+        }
+    };
+    if (warp == 0) { issue_tile(0); if (ntiles > 1) issue_tile(1); }
+    auto epilogue = [&](int t) {     // TMEM lane = input j of tile t, columns = hidden units
+        nn_mbar_wait(b_dfull + 8 * (t & 1), (uint32_t)(t >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int j = 128 * t + 32 * q + lane;
+        const uint32_t tb = tc.tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((t & 1) * Npad);
+        for (int c0 = 32 * cg; c0 < 32 * cg + 32 && c0 < Npad; c0 += 16) {
+            float v[16];
+            nn_tmem_ld16(tb + (uint32_t)c0, v);
+            if (j < dm.din) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = c0 + i;
+                    if (n < dm.dh) {
+                        float* dst = GB + (size_t)n * dm.din + j;
+                        *dst = first ? v[i] : *dst + v[i];
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+    for (int t = 0; t < ntiles; ++t) {
+        const uint32_t xs = x0 + (uint32_t)(t & 1) * STG + (uint32_t)q * BLK;
+        nn_mbar_wait(b_full + 8 * (t & 1), (uint32_t)(t >> 1) & 1u);
+        // the MMAs of tile t - 1 read the TMEM A buffer: they must be done before it is rewritten
+        if (t > 0) { nn_mbar_wait(b_dfull + 8 * ((t - 1) & 1), (uint32_t)((t - 1) >> 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        // transpose: this thread's input column (lane) of block q, rows 32 cg .. 32 cg + 31 -> TMEM columns
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int r0 = 32 * cg + 16 * h2;
+            if (r0 < Kp) {   // warp-uniform
+                float hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int r = r0 + i;
+                    float x = 0.f;
+                    if (r < Kp) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xs + (uint32_t)r * 128u + ((uint32_t)((lane >> 2) ^ (r & 7)) << 4) + ((uint32_t)(lane & 3) << 2)));
+                    hi[i] = nn_tf32(x);
+                    lo[i] = nn_tf32(x - hi[i]);
+                }
+                const uint32_t ta = tc.tmem + ((uint32_t)(32 * q) << 16) + 256u + (uint32_t)r0;
+                nn_tmem_st16(ta, hi);
+                nn_tmem_st16(ta + 128u, lo);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            if (t + 2 < ntiles) issue_tile(t + 2);     // stage t & 1 is free: its tile lives in TMEM now
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (nn_elect_one()) {
+                const uint32_t td = tc.tmem + (uint32_t)((t & 1) * Npad);
+                for (int k8 = 0; k8 < (Kp >> 3); ++k8) {
+                    const uint64_t bhi = nn_umma_desc(bop + (uint32_t)(2 * k8) * LBOB, LBOB), blo = nn_umma_desc(bop + PLANE + (uint32_t)(2 * k8) * LBOB, LBOB);
+                    const uint32_t ahi = tc.tmem + 256u + 8u * (uint32_t)k8, alo = ahi + 128u;
+                    nn_umma_tf32_ts(td, ahi, bhi, idesc, k8 > 0);
+                    nn_umma_tf32_ts(td, ahi, blo, idesc, true);
+                    nn_umma_tf32_ts(td, alo, bhi, idesc, true);
+                }
+                nn_umma_commit(b_dfull + 8 * (t & 1));
+            }
+            __syncwarp();
+        }
+        if (t > 0) epilogue(t - 1);                      // overlaps the MMAs of tile t
+    }
+    epilogue(ntiles - 1);
+    __syncthreads();
+}
+
+#endif  // NN_ENABLE_S5_TMEM
+
 enum : int { NEED_A = 1, NEED_B = 2, NEED_a = 4, NEED_b = 8, NEED_ALL = 15 };
 
 // One gradient evaluation of the log-likelihood SUM over the minibatch at `th`, for the tensors in
@@ -944,6 +1093,10 @@ __device__ float nn_eval(const NNDims& dm, const NNSmem& sm, const float* __rest
         NN_TICK(2)
         if (need & (NEED_b | NEED_B)) nn_stage4(dm, sm, nb, first, Gout + dm.offb);
         NN_TICK(3)
+#ifdef NN_ENABLE_S5_TMEM   // compiled out by default: even an untaken call changes the register allocation of the default kernels
+        if ((need & NEED_B) && mp.x && nn_s5_tmem && nn_s5_tmem_fits(dm, nb, sm.ring_bytes)) nn_stage5_tmem(dm, sm, mp.x, nb, first, Gout + dm.offB, tc);
+        else
+#endif
         if (need & NEED_B) nn_stage5_tc(dm, sm, X, ld, nb, first, Gout + dm.offB, tc);
         NN_TICK(4)
     }
@@ -1674,6 +1827,9 @@ int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t strea
         const char* u = getenv("SGM_NN_UPDATE");
         const int on = (u && !strcmp(u, "regs")) ? 0 : 1;
         cudaMemcpyToSymbolAsync(nn_stream_updates, &on, sizeof(on), 0, cudaMemcpyHostToDevice, stream);
+        const char* s5 = getenv("SGM_NN_S5");
+        const int s5on = (s5 && !strcmp(s5, "tmem")) ? 1 : 0;   // opt-in until it has run on a GPU
+        cudaMemcpyToSymbolAsync(nn_s5_tmem, &s5on, sizeof(s5on), 0, cudaMemcpyHostToDevice, stream);
     }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
