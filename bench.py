@@ -238,6 +238,7 @@ def many_mode_full_gradient(w, rank, world, modes):
     del sg
     return {"modes": max(1, modes // world) * world, "rows_per_rank": rows, "d": d, "ms": ms, "flops": flops, "TFLOPs": tf, "TFLOPs_all_ranks": (tf * world) if tf else None, "bound": "tensor",
             "peak": peak, "peak_source": src, "frac": (tf / peak) if tf else None,
+            "frac_of_3xtf32_ceiling": (tf / (peak / 6.0)) if tf else None,   # TF32 = bf16 / 2 (B200 datasheet ratio), three MMAs per fp32 product
             "arithmetic": "3xTF32 (hi*hi + hi*lo + lo*hi) on tcgen05, float32-level accuracy: three TF32 MMAs per float32 product, "
                           "so the ceiling of this arithmetic is about TF32 peak / 3 = bf16 peak / 6",
             "passes": "R = y - sigmoid(X theta_hat^T + bias); G = X^T R (K split over row ranges), per row block",
