@@ -197,6 +197,14 @@ int sgm_bench_full_gradient(sgm_handle* h, int reps, float* ms_per_rep, int64_t*
 /* 4 N d M flops of the last full-data gradient when it ran as tensor-core contractions (logistic family, one mode per
  * chain: calcFullGrads of R/controlVariates.R:105-111 for M independent chains at once); 0 when the streaming path ran. */
 int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops);
+/* Pins a kernel path of this handle (tests, A/B measurements); value 0 restores the default dispatch.  Keys:
+ *   "logistic_kernel"  1 = generic warp-group kernel also for short rows
+ *   "gather"           short-row kernel: 1 = 16-byte cp.async, 2 = one TMA bulk copy per row, 3 = mixed, 4 = TMA tile::gather4
+ *   "fullgrad"         logistic full-data gradient: 1 = tensor-core contractions, 2 = SIMT row-chunk x mode grid
+ *   "nn_update"        softmax net: 1 = register-staged update of every tensor (default: streamed through shared memory)
+ *   "nn_stage1"        softmax net: 1 = register-staged forward GEMM operands (default: TMA-fed)
+ * The library never reads environment variables on the dispatch path. */
+int sgm_set_option(sgm_handle* h, const char* key, int32_t value);
 /* Debug: per-phase clock64() totals of the logistic short-row kernel (thread 0 of every CTA). */
 int sgm_debug_phase_cycles(sgm_handle* h, int enable, unsigned long long* out, int n);
 /* Copies rows [row0, row0+rows) of the device dataset back as column-major doubles

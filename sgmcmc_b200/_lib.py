@@ -79,6 +79,7 @@ SYMBOLS = {
     "sgm_dataset_ipc_handle": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "sgm_attach_peer_shards": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "sgm_detach_peer_shards": (C.c_int, [_H]),
+    "sgm_set_option": (C.c_int, [_H, C.c_char_p, C.c_int32]),
     "sgm_debug_phase_cycles": (C.c_int, [_H, C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),
     "sgm_copy_dataset": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, _PD]),
     "sgm_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),

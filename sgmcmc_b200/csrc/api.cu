@@ -20,7 +20,6 @@
 #include "logistic.cuh"
 #include "logistic_staged.cuh"
 #include "logistic_fullgrad_stream.cuh"
-#include "logistic_ring.cuh"
 #include "logistic_cv_gemm.cuh"
 #include "softmax_net.cuh"
 
@@ -112,6 +111,7 @@ struct sgm_handle {
     int64_t chain_offset = 0;
     std::vector<TensorInfo> tensors;
     std::vector<double> eps, alpha, a;
+    std::vector<float> init_state;   // [Pst] start values in the internal layout (restored by every sgm_init)
     // device
     float* X = nullptr;
     float *theta = nullptr, *mom = nullptr, *thermo = nullptr, *theta_hat = nullptr, *g_hat = nullptr, *scratch = nullptr;
@@ -140,6 +140,11 @@ struct sgm_handle {
     double fullgrad_flops = 0;                      // 4 N d M of the last tensor-core full gradient (0: not used)
     bool rhat_cached = false;   // logistic *cv, shared mode: y - s(x.beta_hat) stored in the rows' spare slot
     ChainArgs base;  // template of kernel arguments
+    // kernel selectors (sgm_set_option; 0 = the default dispatch).  They exist so that tests can pin a path through the ABI;
+    // nothing on the dispatch path reads the environment.
+    int opt_logistic_kernel = 0;   // 1: generic warp-group kernel even for short rows
+    int opt_gather = 0;            // short-row kernel: 1 cp.async, 2 TMA bulk copy per row, 3 mixed, 4 TMA tile::gather4
+    int opt_fullgrad = 0;          // logistic full-data gradient: 1 tensor-core contractions, 2 SIMT row-chunk x mode grid
     SoftmaxNetWork* nn = nullptr;
     // comm
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
@@ -309,6 +314,18 @@ __global__ void small_fullgrad_finish(ChainArgs a, int M, const double* __restri
 // ------------------------------------------------------------------------------------
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// scratch device buffers / events of one ABI call: released on every return path
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
+};
+struct EventPair {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+
 static int set_device(const sgm_handle* h) {
     CU(cudaSetDevice(h->device));
     return SGM_OK;
@@ -362,7 +379,7 @@ static int launch_logistic_gv(sgm_handle* h, const ChainArgs& a, int threads, si
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
     int grid = a.C < sms * (per_sm > 0 ? per_sm : 1) ? a.C : sms * (per_sm > 0 ? per_sm : 1);
-    k<<<grid, threads, smem, h->stream>>>(a);
+    SGM_LAUNCH(k, grid, threads, smem, h->stream, a);
     CU(cudaGetLastError());
     return SGM_OK;
 }
@@ -385,7 +402,7 @@ static int launch_logistic_fullgrad_gv(sgm_handle* h, int64_t row0, int64_t row1
     chunks = cdiv(rows, rows_per_cta);
     if (chunks < 1) chunks = 1;
     dim3 grid((unsigned)chunks, (unsigned)M);
-    k<<<grid, threads, smem, h->stream>>>(h->X, h->ld, h->d, row0, row1, (int)rows_per_cta, theta_hat, h->Pst, h->gsum);
+    SGM_LAUNCH(k, grid, threads, smem, h->stream, h->X, h->ld, h->d, row0, row1, (int)rows_per_cta, theta_hat, h->Pst, h->gsum);
     CU(cudaGetLastError());
     return SGM_OK;
 }
@@ -416,8 +433,7 @@ static int launch_logistic_fullgrad_gv(sgm_handle* h, int64_t row0, int64_t row1
 
 // short rows: whole minibatch staged in shared memory by TMA bulk copies (logistic_staged.cuh)
 static bool logistic_use_staged(const sgm_handle* h, const ChainArgs& a) {
-    const char* force = getenv("SGM_LOGISTIC_KERNEL");
-    if (force && !strcmp(force, "generic")) return false;
+    if (h->opt_logistic_kernel == 1) return false;
     if (h->n_shards > 1) return false;   // the TMA row map covers the local shard only
     return h->ld <= 128 && a.n <= LS_MAX_R * LS_THREADS && ls_smem_bytes(h->ld, a.n) <= 227 * 1024;
 }
@@ -450,7 +466,7 @@ static int launch_logistic_staged_t(sgm_handle* h, const ChainArgs& a) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LS_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const int grid = a.C < sms * per_sm ? a.C : sms * per_sm;
-    k<<<grid, LS_THREADS, smem, h->stream>>>(a, h->tmap);
+    SGM_LAUNCH(k, grid, LS_THREADS, smem, h->stream, a, h->tmap);
     CU(cudaGetLastError());
     return SGM_OK;
 }
@@ -459,9 +475,14 @@ static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
     // control variates need x.beta_hat per row unless the residual at the (shared) mode is cached in the rows
     const bool hat_dot = a.cv && !h->rhat_cached;
     {   // gather engine: TMA tile::gather4 when the shared-memory rows are unpadded, else one TMA bulk copy per row
-        const char* g = getenv("SGM_GATHER");
-        int mode = (h->tmap_ok && (ls_row_stride4(h->ld) == h->ld / 4) && h->ld <= 256) ? 3 : 1;
-        if (g) mode = !strcmp(g, "ldgsts") ? 0 : (!strcmp(g, "mixed") ? 2 : (!strcmp(g, "bulk") ? 1 : mode));
+        const bool can_gather4 = h->tmap_ok && (ls_row_stride4(h->ld) == h->ld / 4) && h->ld <= 256;
+        int mode = can_gather4 ? 3 : 1;
+        switch (h->opt_gather) {
+            case 1: mode = 0; break;
+            case 2: mode = 1; break;
+            case 3: mode = 2; break;
+            case 4: if (!can_gather4) return fail(SGM_EINVAL, "gather = tile::gather4 needs unpadded shared-memory rows and a tensor map (ld = %d)", h->ld); mode = 3; break;
+        }
         const_cast<ChainArgs&>(a).gather_tma = mode;
     }
     const int R = (a.n + LS_THREADS - 1) / LS_THREADS;
@@ -478,41 +499,9 @@ static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
     return fail(SGM_EINVAL, "logistic staged kernel: minibatch %d too large", a.n);
 }
 
-template <int V, bool HAT_DOT>
-static int launch_logistic_ring_t(sgm_handle* h, const ChainArgs& a) {
-    auto k = logistic_ring_kernel<V, HAT_DOT>;
-    const size_t smem = lr_smem_bytes(h->ld, a.n);
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int sms = 0;
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-    const int grid = a.C < sms ? a.C : sms;
-    k<<<grid, LR_THREADS, smem, h->stream>>>(a);
-    CU(cudaGetLastError());
-    return SGM_OK;
-}
-
-// long rows: warp-specialised TMA ring (logistic_ring.cuh)
-static bool logistic_use_ring(const sgm_handle* h, const ChainArgs& a) {
-    const char* force = getenv("SGM_LOGISTIC_KERNEL");
-    if (h->n_shards > 1) return false;
-    if (!(force && !strcmp(force, "ring"))) return false;   // opt-in: measured slower than the register-staged kernel (profiles/r01_c5_ring_vs_generic.txt)
-    const int V = (h->ld / 4 + 31) / 32;
-    return h->ld > 128 && V >= 2 && V <= 9 && lr_smem_bytes(h->ld, a.n) <= 227 * 1024;
-}
-
-static int launch_logistic_ring(sgm_handle* h, const ChainArgs& a) {
-    const bool hat_dot = a.cv && !h->rhat_cached;
-    const int V = (h->ld / 4 + 31) / 32;
-#define LR_CASE(v) case v: return hat_dot ? launch_logistic_ring_t<v, true>(h, a) : launch_logistic_ring_t<v, false>(h, a);
-    switch (V) { LR_CASE(2) LR_CASE(3) LR_CASE(4) LR_CASE(5) LR_CASE(6) LR_CASE(7) LR_CASE(8) LR_CASE(9) }
-#undef LR_CASE
-    return fail(SGM_EINVAL, "logistic ring kernel: unsupported row length %d", h->ld);
-}
-
 static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
     const_cast<ChainArgs&>(a).rhat_cached = h->rhat_cached ? 1 : 0;
     if (logistic_use_staged(h, a)) return launch_logistic_staged(h, a);
-    if (logistic_use_ring(h, a)) return launch_logistic_ring(h, a);
     LogiShape s;
     if (!logi_shape(h->ld, &s)) return fail(SGM_EINVAL, "logistic: d = %d too large", h->d);
     const int threads = logi_threads(h, s);
@@ -534,7 +523,7 @@ static int launch_fullgrad_stream_t(sgm_handle* h, int64_t row0, int64_t row1, c
     const int64_t n_tiles = cdiv(row1 - row0, tile_rows);
     const int grid = (int)(n_tiles < (int64_t)sms * per_sm ? n_tiles : (int64_t)sms * per_sm);
     if (grid < 1) return SGM_OK;
-    k<<<grid, FG_THREADS, smem, h->stream>>>(h->X, h->ld, h->d, row0, row1, tile_rows, (int)n_tiles, theta_hat, h->gsum);
+    SGM_LAUNCH(k, grid, FG_THREADS, smem, h->stream, h->X, h->ld, h->d, row0, row1, tile_rows, (int)n_tiles, theta_hat, h->gsum);
     CU(cudaGetLastError());
     return SGM_OK;
 }
@@ -560,9 +549,8 @@ static int cvg_encode_2d(CUtensorMap* map, const float* base, uint64_t inner, ui
 }
 
 static bool logistic_fullgrad_use_tc(const sgm_handle* h, int M) {
-    const char* force = getenv("SGM_FULLGRAD");
-    if (force && !strcmp(force, "tc")) return M >= 1;
-    if (force) return false;
+    if (h->opt_fullgrad == 1) return M >= 1 && (h->Pst % 4) == 0 && (h->ld % 4) == 0;
+    if (h->opt_fullgrad == 2) return false;
     return M >= 16 && (h->Pst % 4) == 0 && (h->ld % 4) == 0;   // below that the SIMT row-chunk x mode grid is HBM-bound anyway
 }
 
@@ -575,7 +563,7 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
         h->xt_pitch = (h->N + 3) / 4 * 4;
         CU(cudaMalloc(&h->Xt, (size_t)d * h->xt_pitch * sizeof(float)));
         dim3 tb(32, 8), tg((unsigned)cdiv(h->N, 32), (unsigned)cdiv(d, 32));
-        cvg_transpose_kernel<<<tg, tb, 0, h->stream>>>(h->X, h->N, h->ld, d, h->Xt, h->xt_pitch);
+        SGM_LAUNCH(cvg_transpose_kernel, tg, tb, 0, h->stream, h->X, h->N, h->ld, d, h->Xt, h->xt_pitch);
         CU(cudaGetLastError());
     }
     // row blocks: R^T of one block stays <= ~2 GB
@@ -604,7 +592,7 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
         const int64_t rows = b1 - b0;
         if (cvg_encode_2d(&mRt, h->Rt, (uint64_t)(rows + shift), (uint64_t)M, (uint64_t)pitch)) return fail(SGM_ECUDA, "logistic full gradient: tensor map (R^T)");
         if (shift) {
-            cvg_zero_cols_kernel<<<(unsigned)cdiv((int64_t)M * shift, 256), 256, 0, h->stream>>>(h->Rt, pitch, shift, M);
+            SGM_LAUNCH(cvg_zero_cols_kernel, (unsigned)cdiv((int64_t)M * shift, 256), 256, 0, h->stream, h->Rt, pitch, shift, M);
             CU(cudaGetLastError());
         }
         CvgArgs a{};
@@ -616,10 +604,10 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
             a.tiles_a = (int)cdiv(rows, CVG_TILE);
             a.n_items = a.tiles_a * tiles_m;
             const int grid = a.n_items < sms ? a.n_items : sms;
-            cvg_kernel<<<grid, CVG_THREADS, CVG_SMEM, h->stream>>>(a, mX, mTh);
+            SGM_LAUNCH(cvg_kernel, grid, CVG_THREADS, CVG_SMEM, h->stream, a, mX, mTh);
             CU(cudaGetLastError());
             const int64_t warps = (int64_t)M * cdiv(rows + shift, 4096);
-            cvg_rowsum_kernel<<<(unsigned)cdiv(warps * 32, 256), 256, 0, h->stream>>>(h->Rt, pitch, rows + shift, M, h->Pst, d, h->gsum);
+            SGM_LAUNCH(cvg_rowsum_kernel, (unsigned)cdiv(warps * 32, 256), 256, 0, h->stream, h->Rt, pitch, rows + shift, M, h->Pst, d, h->gsum);
             CU(cudaGetLastError());
         }
         // pass 2: gsum[m][k] += sum_i R^T[m][i] X^T[k][i], K (= rows) split over CTAs
@@ -640,7 +628,7 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
             a.tiles_a = tiles_k;
             a.n_items = (int)(tiles_k * tiles_m * splits);
             const int grid = a.n_items < sms ? a.n_items : sms;
-            cvg_kernel<<<grid, CVG_THREADS, CVG_SMEM, h->stream>>>(a, mXt, mRt);
+            SGM_LAUNCH(cvg_kernel, grid, CVG_THREADS, CVG_SMEM, h->stream, a, mXt, mRt);
             CU(cudaGetLastError());
         }
         h->last_launches += 3;
@@ -651,11 +639,10 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
 
 // one mode: streaming kernel (TMA bulk tile ring); per-chain modes: row-chunk x mode grid
 static int launch_logistic_fullgrad(sgm_handle* h, int64_t row0, int64_t row1, int M, const float* theta_hat) {
-    const char* force = getenv("SGM_FULLGRAD");
     const int Q = h->ld / 4;
     h->fullgrad_flops = 0;
     if (logistic_fullgrad_use_tc(h, M)) return launch_logistic_fullgrad_tc(h, row0, row1, M, theta_hat);
-    if (M == 1 && !(force && !strcmp(force, "generic")) && cdiv(row1 - row0, FG_SHORT_ROWS) < (1ll << 31)) {
+    if (M == 1 && h->opt_fullgrad != 2 && cdiv(row1 - row0, FG_SHORT_ROWS) < (1ll << 31)) {
         if (h->ld <= 128) {
             // lane-per-row needs conflict-free shared rows: odd float4 stride, or 2 (mod 4) with skewed lanes; <= 4 column slots per warp
             if (((Q & 1) || (Q % 4 == 2)) && fg_smem_bytes(h->ld, FG_SHORT_ROWS) <= 113 * 1024)
@@ -688,8 +675,8 @@ static int launch_chain(sgm_handle* h, const ChainArgs& a) {
             CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
             int64_t grid = cdiv((int64_t)a.C * 32, threads);
             if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
-            if (h->model == SGM_MODEL_GAUSS_MEAN) small_chain_kernel<SMALL_MODEL_GAUSS><<<(unsigned)grid, threads, 0, h->stream>>>(a);
-            else small_chain_kernel<SMALL_MODEL_MIX2><<<(unsigned)grid, threads, 0, h->stream>>>(a);
+            if (h->model == SGM_MODEL_GAUSS_MEAN) SGM_LAUNCH(small_chain_kernel<SMALL_MODEL_GAUSS>, (unsigned)grid, threads, 0, h->stream, a);
+            else SGM_LAUNCH(small_chain_kernel<SMALL_MODEL_MIX2>, (unsigned)grid, threads, 0, h->stream, a);
             CU(cudaGetLastError());
             return SGM_OK;
         }
@@ -746,6 +733,22 @@ static int64_t tensor_size(const sgm_param& p) {
     return s;
 }
 
+// Every chain at the user's start values, thermostats at `a`, momenta zero: what tf$global_variables_initializer() leaves behind
+// (initSess, R/update.R:126-131).  Called by sgm_create and again by every sgm_init, so a second initSess restarts the sampler.
+static int upload_initial_state(sgm_handle* h) {
+    const size_t sbytes = (size_t)h->C * h->Pst * sizeof(float);
+    std::vector<float> all((size_t)h->C * h->Pst);
+    for (int c = 0; c < h->C; ++c) std::memcpy(all.data() + (size_t)c * h->Pst, h->init_state.data(), h->Pst * sizeof(float));
+    CU(cudaMemcpyAsync(h->theta, all.data(), sbytes, cudaMemcpyHostToDevice, h->stream));
+    if (h->cv) CU(cudaMemcpyAsync(h->theta_hat, all.data(), sbytes, cudaMemcpyHostToDevice, h->stream));
+    std::vector<float> th((size_t)h->C * MAX_TENSORS, 0.f);
+    for (int c = 0; c < h->C; ++c) for (int t = 0; t < h->T; ++t) th[(size_t)c * MAX_TENSORS + t] = (float)h->a[t];
+    CU(cudaMemcpyAsync(h->thermo, th.data(), th.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->mom, 0, sbytes, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // the host vectors above go out of scope
+    return SGM_OK;
+}
+
 extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     if (!cfg || !out) return fail(SGM_EINVAL, "null argument");
     *out = nullptr;
@@ -759,6 +762,13 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
 
     sgm_handle* h = new sgm_handle();
     auto bail = [&](int rc) { sgm_destroy(h); return rc; };
+    // device failures inside sgm_create release everything the handle owns (dataset included) before returning
+#define CUB(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return bail(fail(SGM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
     h->model = cfg->model; h->algo = cfg->algo; h->cv = cfg->cv ? 1 : 0; h->C = cfg->n_chains;
     h->device = cfg->device; h->flags = cfg->flags; h->chain_offset = cfg->chain_offset; h->use_prior = cfg->use_prior ? 1 : 0;
     h->prior_sd = cfg->prior_sd; h->opt_stepsize = cfg->opt_stepsize; h->n_iters_opt = cfg->n_iters_opt;
@@ -855,45 +865,48 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
     if (int rc = set_device(h)) return bail(rc);
 
     // ---- device allocations
-    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
+    CUB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreate(&h->ev0)); CUB(cudaEventCreate(&h->ev1));
     const size_t xbytes = (size_t)h->N * h->ld * sizeof(float);
     if (cudaMalloc(&h->X, xbytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(SGM_ENOMEM, "cannot allocate %zu bytes for the dataset", xbytes)); }
     const uint32_t sk0 = (uint32_t)(cfg->synth_seed & 0xffffffffu), sk1 = (uint32_t)(cfg->synth_seed >> 32);
     if (synth) {
         const int64_t warps = h->N;
-        synth_logistic_kernel<<<(unsigned)cdiv(warps * 32, 256), 256, 0, h->stream>>>(h->X, h->N, h->d, h->ld, sk0, sk1);
-        CU(cudaGetLastError());
+        SGM_LAUNCH(synth_logistic_kernel, (unsigned)cdiv(warps * 32, 256), 256, 0, h->stream, h->X, h->N, h->d, h->ld, sk0, sk1);
+        CUB(cudaGetLastError());
     } else {
-        CU(cudaMemsetAsync(h->X, 0, xbytes, h->stream));
+        CUB(cudaMemsetAsync(h->X, 0, xbytes, h->stream));
         int col0 = 0;
         const int entries = (h->model == SGM_MODEL_GAUSS_MEAN || h->model == SGM_MODEL_MIXTURE2) ? 1 : 2;
-        // upload in row slabs to bound the double staging buffer
+        // one column-major double staging buffer per dataset entry (freed before the next entry is staged)
         for (int k = 0; k < entries; ++k) {
             const sgm_array& A = cfg->data[k];
             const int cols = A.ndim >= 2 ? (int)A.dims[1] : 1;
             double* stage = nullptr;
             const size_t bytes = (size_t)h->N * cols * sizeof(double);
             if (cudaMalloc(&stage, bytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(SGM_ENOMEM, "cannot allocate %zu staging bytes", bytes)); }
-            CU(cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream));
-            pack_rows_kernel<<<(unsigned)cdiv(h->N * cols, 256), 256, 0, h->stream>>>(stage, h->N, cols, h->X, h->ld, col0);
-            CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(h->stream));
+            cudaError_t se = cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream);
+            if (se == cudaSuccess) {
+                SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(h->N * cols, 256), 256, 0, h->stream, stage, h->N, cols, h->X, h->ld, col0);
+                se = cudaGetLastError();
+            }
+            if (se == cudaSuccess) se = cudaStreamSynchronize(h->stream);
             cudaFree(stage);
+            if (se != cudaSuccess) return bail(fail(SGM_ECUDA, "dataset upload failed: %s", cudaGetErrorString(se)));
             col0 += cols;
         }
     }
     const size_t sbytes = (size_t)h->C * h->Pst * sizeof(float);
-    CU(cudaMalloc(&h->theta, sbytes)); CU(cudaMalloc(&h->mom, sbytes)); CU(cudaMalloc(&h->scratch, sbytes));
-    CU(cudaMalloc(&h->thermo, (size_t)h->C * MAX_TENSORS * sizeof(float)));
-    CU(cudaMalloc(&h->d_flag, sizeof(int))); CU(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
-    CU(cudaMalloc(&h->dout, (size_t)h->C * sizeof(double)));
-    CU(cudaMemsetAsync(h->mom, 0, sbytes, h->stream));
+    CUB(cudaMalloc(&h->theta, sbytes)); CUB(cudaMalloc(&h->mom, sbytes)); CUB(cudaMalloc(&h->scratch, sbytes));
+    CUB(cudaMalloc(&h->thermo, (size_t)h->C * MAX_TENSORS * sizeof(float)));
+    CUB(cudaMalloc(&h->d_flag, sizeof(int))); CUB(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+    CUB(cudaMalloc(&h->dout, (size_t)h->C * sizeof(double)));
+    CUB(cudaMemsetAsync(h->mom, 0, sbytes, h->stream));
     if (h->cv) {
         const size_t hb = (size_t)hat_count(h) * h->Pst * sizeof(float);
-        CU(cudaMalloc(&h->theta_hat, sbytes)); CU(cudaMalloc(&h->g_hat, sbytes));
-        CU(cudaMalloc(&h->gsum, (size_t)h->C * h->Pst * sizeof(double)));
-        CU(cudaMemsetAsync(h->g_hat, 0, sbytes, h->stream));
+        CUB(cudaMalloc(&h->theta_hat, sbytes)); CUB(cudaMalloc(&h->g_hat, sbytes));
+        CUB(cudaMalloc(&h->gsum, (size_t)h->C * h->Pst * sizeof(double)));
+        CUB(cudaMemsetAsync(h->g_hat, 0, sbytes, h->stream));
         (void)hb;
     }
     if (h->model == SGM_MODEL_SOFTMAX_NET) {
@@ -902,22 +915,16 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
         if (rc != 0) return bail(fail(SGM_ECUDA, "softmax net workspace: %s", cudaGetErrorString((cudaError_t)rc)));
     }
     if (h->model == SGM_MODEL_LOGISTIC && h->ld <= 128) h->tmap_ok = (make_row_tensor_map(h) == 0);
-    // initial state: every chain starts at params (internal layout)
+    // initial state: every chain starts at params (internal layout); kept on the host so that initSess can restore it
     {
         std::vector<int> flat_of, tensor_of;
         host_tables(h, flat_of, tensor_of);
-        std::vector<float> init((size_t)h->Pst, 0.f), flat((size_t)h->P);
+        std::vector<float> flat((size_t)h->P);
         for (int t = 0; t < h->T; ++t)
             for (int64_t k = 0; k < h->tensors[t].size; ++k) flat[h->tensors[t].offset + k] = (float)cfg->params[t].init[k];
-        for (int e = 0; e < h->Pst; ++e) if (flat_of[e] >= 0) init[e] = flat[flat_of[e]];
-        std::vector<float> all((size_t)h->C * h->Pst);
-        for (int c = 0; c < h->C; ++c) std::memcpy(all.data() + (size_t)c * h->Pst, init.data(), h->Pst * sizeof(float));
-        CU(cudaMemcpyAsync(h->theta, all.data(), sbytes, cudaMemcpyHostToDevice, h->stream));
-        if (h->cv) CU(cudaMemcpyAsync(h->theta_hat, all.data(), sbytes, cudaMemcpyHostToDevice, h->stream));
-        std::vector<float> th((size_t)h->C * MAX_TENSORS, 0.f);
-        for (int c = 0; c < h->C; ++c) for (int t = 0; t < h->T; ++t) th[(size_t)c * MAX_TENSORS + t] = (float)h->a[t];
-        CU(cudaMemcpyAsync(h->thermo, th.data(), th.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        h->init_state.assign((size_t)h->Pst, 0.f);
+        for (int e = 0; e < h->Pst; ++e) if (flat_of[e] >= 0) h->init_state[e] = flat[flat_of[e]];
+        if (int rc = upload_initial_state(h)) return bail(rc);
     }
 
     // ---- kernel argument template
@@ -964,6 +971,7 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
 
     *out = h;
     return SGM_OK;
+#undef CUB
 }
 
 extern "C" void sgm_destroy(sgm_handle* h) {
@@ -976,6 +984,7 @@ extern "C" void sgm_destroy(sgm_handle* h) {
     void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,
                     h->d_flag, h->d_idx, h->d_noise, h->store, h->Xt, h->Rt, h->hat_all, h->gsum_all};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->base.prof) cudaFree(h->base.prof);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1009,8 +1018,9 @@ static int full_gradient(sgm_handle* h) {
         CU(cudaMemsetAsync(h->gsum_all, 0, (size_t)M * h->world * h->Pst * sizeof(double), h->stream));
     }
     CU(cudaMemsetAsync(h->gsum, 0, (size_t)M * h->Pst * sizeof(double), h->stream));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    EventPair ev;
+    CU(cudaEventCreate(&ev.e0)); CU(cudaEventCreate(&ev.e1));
+    cudaEvent_t e0 = ev.e0, e1 = ev.e1;
     CU(cudaEventRecord(e0, h->stream));
     switch (h->model) {
         case SGM_MODEL_GAUSS_MEAN:
@@ -1019,8 +1029,8 @@ static int full_gradient(sgm_handle* h) {
             int sms = 0; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
             int64_t gx = cdiv(row1 - row0, 256 * 4); if (gx > sms * 8) gx = sms * 8; if (gx < 1) gx = 1;
             dim3 grid((unsigned)gx, (unsigned)M);
-            if (h->model == SGM_MODEL_GAUSS_MEAN) small_fullsum_kernel<SMALL_MODEL_GAUSS><<<grid, 256, 0, h->stream>>>(a, row0, row1, h->gsum);
-            else small_fullsum_kernel<SMALL_MODEL_MIX2><<<grid, 256, 0, h->stream>>>(a, row0, row1, h->gsum);
+            if (h->model == SGM_MODEL_GAUSS_MEAN) SGM_LAUNCH(small_fullsum_kernel<SMALL_MODEL_GAUSS>, grid, 256, 0, h->stream, a, row0, row1, h->gsum);
+            else SGM_LAUNCH(small_fullsum_kernel<SMALL_MODEL_MIX2>, grid, 256, 0, h->stream, a, row0, row1, h->gsum);
             CU(cudaGetLastError());
             break;
         }
@@ -1052,11 +1062,11 @@ static int full_gradient(sgm_handle* h) {
     const int total = M * h->Pst;
     switch (h->model) {
         case SGM_MODEL_GAUSS_MEAN:
-            small_fullgrad_finish<SMALL_MODEL_GAUSS><<<(unsigned)cdiv(M, 128), 128, 0, h->stream>>>(h->base, M, h->gsum, h->g_hat, h->theta); break;
+            SGM_LAUNCH(small_fullgrad_finish<SMALL_MODEL_GAUSS>, (unsigned)cdiv(M, 128), 128, 0, h->stream, h->base, M, h->gsum, h->g_hat, h->theta); break;
         case SGM_MODEL_MIXTURE2:
-            small_fullgrad_finish<SMALL_MODEL_MIX2><<<(unsigned)cdiv(M, 128), 128, 0, h->stream>>>(h->base, M, h->gsum, h->g_hat, h->theta); break;
+            SGM_LAUNCH(small_fullgrad_finish<SMALL_MODEL_MIX2>, (unsigned)cdiv(M, 128), 128, 0, h->stream, h->base, M, h->gsum, h->g_hat, h->theta); break;
         case SGM_MODEL_LOGISTIC:
-            logistic_fullgrad_finish<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(h->gsum, h->theta_hat, h->g_hat, h->theta, h->Pst, h->d, h->use_prior, total); break;
+            SGM_LAUNCH(logistic_fullgrad_finish, (unsigned)cdiv(total, 256), 256, 0, h->stream, h->gsum, h->theta_hat, h->g_hat, h->theta, h->Pst, h->d, h->use_prior, total); break;
         case SGM_MODEL_SOFTMAX_NET: {
             const int rc = softmax_net_fullgrad_finish(h->nn, h->base, M, h->gsum, h->theta_hat, h->g_hat, h->theta, h->stream);
             if (rc != 0) return fail(SGM_ECUDA, "softmax net finish: %s", cudaGetErrorString((cudaError_t)rc));
@@ -1065,13 +1075,20 @@ static int full_gradient(sgm_handle* h) {
     }
     CU(cudaGetLastError());
     if (M == 1 && h->C > 1) {  // shared mode: every chain starts at the one mode (cV.R:98-99)
-        broadcast_rows_kernel<<<(unsigned)cdiv((int64_t)h->C * h->Pst, 256), 256, 0, h->stream>>>(h->theta, h->theta_hat, h->C, h->Pst);
+        SGM_LAUNCH(broadcast_rows_kernel, (unsigned)cdiv((int64_t)h->C * h->Pst, 256), 256, 0, h->stream, h->theta, h->theta_hat, h->C, h->Pst);
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaEventElapsedTime(&h->fullgrad_ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     h->fullgrad_bytes = (row1 - row0) * (int64_t)h->ld * 4 * (h->model == SGM_MODEL_LOGISTIC ? 1 : 1);
+    return SGM_OK;
+}
+
+// caller-supplied minibatch rows are dataset row numbers (global ones when the dataset is sharded over ranks)
+static int check_rows(const sgm_handle* h, const int32_t* idx, size_t count) {
+    const int64_t n_rows = (int64_t)h->base.N;
+    for (size_t i = 0; i < count; ++i)
+        if (idx[i] < 0 || (int64_t)idx[i] >= n_rows) return fail(SGM_EINVAL, "minibatch row %d (entry %zu) is outside [0, %lld)", idx[i], i, (long long)n_rows);
     return SGM_OK;
 }
 
@@ -1079,11 +1096,15 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
     if (!h) return fail(SGM_EINVAL, "null handle");
     if (int rc = set_device(h)) return rc;
     Timer tm(h);
+    // variable initialisation (R/update.R:127-129): params, optimiser params, thermostats and momenta back to their start values
+    if (int rc = upload_initial_state(h)) return rc;
+    h->rhat_cached = false;
     // momenta (sghmc's is overwritten by the first refresh; sgnht's persists) -- R/dynamics.R:47,84
     std::vector<int> flat_of, tensor_of;
     host_tables(h, flat_of, tensor_of);
-    int *d_flat = nullptr, *d_tens = nullptr;
-    CU(cudaMalloc(&d_flat, h->Pst * sizeof(int))); CU(cudaMalloc(&d_tens, h->Pst * sizeof(int)));
+    DevBuf<int> flat_buf, tens_buf;
+    CU(flat_buf.alloc(h->Pst)); CU(tens_buf.alloc(h->Pst));
+    int *d_flat = flat_buf.p, *d_tens = tens_buf.p;
     CU(cudaMemcpyAsync(d_flat, flat_of.data(), h->Pst * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_tens, tensor_of.data(), h->Pst * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->algo != SGM_ALGO_SGLD) {
@@ -1096,13 +1117,11 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
         }
         if (det && !momentum_noise) CU(cudaMemsetAsync(h->mom, 0, (size_t)h->C * h->Pst * sizeof(float), h->stream));
         else {
-            momentum_init_kernel<<<(unsigned)cdiv((int64_t)h->C * h->Pst, 256), 256, 0, h->stream>>>(
-                h->mom, h->C, h->Pst, h->P, d_flat, d_tens, h->base.tc, dn, h->base.k0, h->base.k1, h->base.chain0);
+            SGM_LAUNCH(momentum_init_kernel, (unsigned)cdiv((int64_t)h->C * h->Pst, 256), 256, 0, h->stream, h->mom, h->C, h->Pst, h->P, d_flat, d_tens, h->base.tc, dn, h->base.k0, h->base.k1, h->base.chain0);
             CU(cudaGetLastError());
         }
     }
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(d_flat); cudaFree(d_tens);
 
     if (h->cv) {
         // getMode (R/controlVariates.R:37-52): n_iters_opt plain SGD ascent steps on theta_hat
@@ -1114,6 +1133,7 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
         a.noise_len = 0;
         if (det) {
             if (h->n_iters_opt > 0 && !opt_idx) return fail(SGM_EINVAL, "opt_idx required for a deterministic *cv init");
+            if (opt_idx) if (int rc = check_rows(h, opt_idx, (size_t)M * h->n_iters_opt * h->n)) return rc;
             const size_t bytes = (size_t)M * h->n_iters_opt * h->n * sizeof(int32_t);
             if (bytes) {
                 if (int rc = ensure_buf((void**)&h->d_idx, &h->d_idx_cap, bytes)) return rc;
@@ -1129,8 +1149,12 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
         h->base.hat_stride = (M == 1 && h->C > 1) ? 0 : h->Pst;
         // one mode for every chain: cache the per-datum residual at the mode next to y (logistic_staged.cuh)
         h->rhat_cached = false;
-        if (h->model == SGM_MODEL_LOGISTIC && M == 1 && (h->d & 3) != 3) {
-            logistic_cache_rhat_kernel<<<(unsigned)cdiv(h->N * 32, 256), 256, 0, h->stream>>>(h->X, h->N, h->ld, h->d, h->theta_hat);
+        // Peers that map this rank's rows (sgm_attach_peer_shards) read the cached residual too, so with a sharded dataset the
+        // cache is only valid when every rank holds the SAME mode (SGM_FLAG_SHARED_MODE); one chain per rank without the flag
+        // means one mode per rank, and the kernels then recompute x . beta_hat per gathered row.
+        const bool same_mode_everywhere = (h->flags & SGM_FLAG_SHARED_MODE) || h->n_shards <= 1;
+        if (h->model == SGM_MODEL_LOGISTIC && M == 1 && same_mode_everywhere && (h->d & 3) != 3) {
+            SGM_LAUNCH(logistic_cache_rhat_kernel, (unsigned)cdiv(h->N * 32, 256), 256, 0, h->stream, h->X, h->N, h->ld, h->d, h->theta_hat);
             CU(cudaGetLastError());
             h->rhat_cached = true;
             h->last_launches += 1;
@@ -1160,6 +1184,7 @@ extern "C" int sgm_init_deterministic(sgm_handle* h, const float* momentum_noise
 extern "C" int sgm_step_deterministic(sgm_handle* h, const int32_t* idx, const float* noise) {
     if (!h || !idx || !noise) return fail(SGM_EINVAL, "null argument");
     if (!h->inited) return fail(SGM_ESTATE, "sgm_init has not been called");
+    if (int rc = check_rows(h, idx, (size_t)h->C * h->L * h->n)) return rc;
     if (int rc = set_device(h)) return rc;
     const size_t ib = (size_t)h->C * h->L * h->n * sizeof(int32_t);
     const size_t nb = (size_t)h->C * h->base.noise_len * sizeof(float);
@@ -1204,6 +1229,7 @@ extern "C" int sgm_reserve_chain(sgm_handle* h, int64_t n_iters) {
 
 extern "C" int sgm_run(sgm_handle* h, int64_t n_iters, int store) {
     if (!h || n_iters < 0) return fail(SGM_EINVAL, "bad argument");
+    if (n_iters > (int64_t)INT32_MAX / (h->L + 1)) return fail(SGM_EINVAL, "n_iters = %lld is more than one launch runs; call sgm_run in chunks", (long long)n_iters);
     if (!h->inited) return fail(SGM_ESTATE, "sgm_init has not been called");
     if (n_iters == 0) return SGM_OK;
     if (int rc = set_device(h)) return rc;
@@ -1239,15 +1265,15 @@ static int state_out(sgm_handle* h, const float* src, int count, double* out) {
     if (int rc = set_device(h)) return rc;
     std::vector<int> flat_of, tensor_of;
     host_tables(h, flat_of, tensor_of);
-    int* d_flat = nullptr; double* d_out = nullptr;
-    CU(cudaMalloc(&d_flat, h->Pst * sizeof(int)));
-    CU(cudaMalloc(&d_out, (size_t)count * h->P * sizeof(double)));
+    DevBuf<int> flat_buf; DevBuf<double> out_buf;
+    CU(flat_buf.alloc(h->Pst));
+    CU(out_buf.alloc((size_t)count * h->P));
+    int* d_flat = flat_buf.p; double* d_out = out_buf.p;
     CU(cudaMemcpyAsync(d_flat, flat_of.data(), h->Pst * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    state_to_double_kernel<<<(unsigned)cdiv((int64_t)count * h->Pst, 256), 256, 0, h->stream>>>(src, count, h->Pst, h->P, d_flat, d_out);
+    SGM_LAUNCH(state_to_double_kernel, (unsigned)cdiv((int64_t)count * h->Pst, 256), 256, 0, h->stream, src, count, h->Pst, h->P, d_flat, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, d_out, (size_t)count * h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(d_flat); cudaFree(d_out);
     return SGM_OK;
 }
 
@@ -1297,17 +1323,17 @@ extern "C" int sgm_copy_chain(sgm_handle* h, double* out) {
     if (slab < 1) slab = 1;
     if (slab > h->C) slab = h->C;
     if (slab > 65535) slab = 65535;
-    double* stage = nullptr;
-    if (cudaMalloc(&stage, (size_t)slab * per_chain) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate chain staging buffer"); }
+    DevBuf<double> stage_buf;
+    if (cudaMalloc(&stage_buf.p, (size_t)slab * per_chain) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate chain staging buffer"); }
+    double* stage = stage_buf.p;
     for (int c0 = 0; c0 < h->C; c0 += slab) {
         const int cn = (h->C - c0 < slab) ? h->C - c0 : slab;
         dim3 grid((unsigned)cdiv(iters, 32), (unsigned)cdiv(h->P, 32), (unsigned)cn), block(32, 8);
-        chain_transpose_kernel<<<grid, block, 0, h->stream>>>(h->store, iters, h->C, h->P, c0, cn, stage);
+        SGM_LAUNCH(chain_transpose_kernel, grid, block, 0, h->stream, h->store, iters, h->C, h->P, c0, cn, stage);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + (size_t)c0 * iters * h->P, stage, (size_t)cn * per_chain, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
-    cudaFree(stage);
     return SGM_OK;
 }
 
@@ -1324,11 +1350,11 @@ static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta,
     const uint32_t word2 = (uint32_t)h->check_ctr;
     switch (h->model) {
         case SGM_MODEL_GAUSS_MEAN:
-            small_logpost_kernel<SMALL_MODEL_GAUSS><<<(unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream>>>(a, word2, h->dout); break;
+            SGM_LAUNCH(small_logpost_kernel<SMALL_MODEL_GAUSS>, (unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream, a, word2, h->dout); break;
         case SGM_MODEL_MIXTURE2:
-            small_logpost_kernel<SMALL_MODEL_MIX2><<<(unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream>>>(a, word2, h->dout); break;
+            SGM_LAUNCH(small_logpost_kernel<SMALL_MODEL_MIX2>, (unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream, a, word2, h->dout); break;
         case SGM_MODEL_LOGISTIC:
-            logistic_logpost_kernel<<<h->C, 256, 0, h->stream>>>(a, word2, theta, h->dout); break;
+            SGM_LAUNCH(logistic_logpost_kernel, h->C, 256, 0, h->stream, a, word2, theta, h->dout); break;
         case SGM_MODEL_SOFTMAX_NET: {
             const int rc = softmax_net_logpost(h->nn, a, word2, theta, h->dout, h->stream);
             if (rc != 0) return fail(SGM_ECUDA, "softmax net logpost: %s", cudaGetErrorString((cudaError_t)rc));
@@ -1349,12 +1375,14 @@ extern "C" int sgm_est_logpost(sgm_handle* h, double* out) {
 
 extern "C" int sgm_est_logpost_deterministic(sgm_handle* h, const int32_t* idx, double* out) {
     if (!h || !out || !idx) return fail(SGM_EINVAL, "null argument");
+    if (int rc = check_rows(h, idx, (size_t)h->C * h->n)) return rc;
     return logpost_common(h, idx, h->theta, out);
 }
 
 extern "C" int sgm_grad_estimate(sgm_handle* h, const int32_t* idx, double* out) {
     if (!h || !idx || !out) return fail(SGM_EINVAL, "null argument");
     if (!h->inited) return fail(SGM_ESTATE, "sgm_init has not been called");
+    if (int rc = check_rows(h, idx, (size_t)h->C * h->n)) return rc;
     if (int rc = set_device(h)) return rc;
     const size_t ib = (size_t)h->C * h->n * sizeof(int32_t);
     if (int rc = ensure_buf((void**)&h->d_idx, &h->d_idx_cap, ib)) return rc;
@@ -1362,15 +1390,15 @@ extern "C" int sgm_grad_estimate(sgm_handle* h, const int32_t* idx, double* out)
     // plain-SGD kernel with unit step on a scratch copy: g = theta' - theta would lose bits, so the
     // kernels' ALGO_GRAD path writes the estimate into the momentum slot of a scratch state instead
     CU(cudaMemcpyAsync(h->scratch, h->theta, (size_t)h->C * h->Pst * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-    float* gbuf = nullptr;
-    CU(cudaMalloc(&gbuf, (size_t)h->C * h->Pst * sizeof(float)));
+    DevBuf<float> g_buf;
+    CU(g_buf.alloc((size_t)h->C * h->Pst));
+    float* gbuf = g_buf.p;
     CU(cudaMemsetAsync(gbuf, 0, (size_t)h->C * h->Pst * sizeof(float), h->stream));
     ChainArgs a = h->base;
     a.theta = h->scratch; a.mom = gbuf; a.algo = ALGO_GRAD; a.L = 1; a.det = 1; a.idx = h->d_idx; a.noise = nullptr;
     a.iters = 1; a.store = nullptr; a.noise_len = 0;
     int rc = launch_chain(h, a);
     if (rc == SGM_OK) rc = state_out(h, gbuf, h->C, out);
-    cudaFree(gbuf);
     return rc;
 }
 
@@ -1383,24 +1411,25 @@ extern "C" int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t 
     const int64_t Nh = data[0].dims[0];
     if (Nh < 1 || Nh >= (1ll << 31)) return fail(SGM_EINVAL, "held-out rows must be in [1, 2^31)");
     if (int rc = set_device(h)) return rc;
-    float* Xh = nullptr;
+    DevBuf<float> xh_buf;
     const size_t xbytes = (size_t)Nh * h->ld * sizeof(float);
-    if (cudaMalloc(&Xh, xbytes) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate %zu bytes for the held-out set", xbytes); }
+    if (cudaMalloc(&xh_buf.p, xbytes) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate %zu bytes for the held-out set", xbytes); }
+    float* Xh = xh_buf.p;
     CU(cudaMemsetAsync(Xh, 0, xbytes, h->stream));
     int col0 = 0;
     for (int k = 0; k < entries; ++k) {
         const sgm_array& A = data[k];
         const int cols = A.ndim >= 2 ? (int)A.dims[1] : 1;
         const int want = (k == 0) ? h->d : (h->ld >= h->d + cols ? cols : -1);
-        if (!A.data || A.dims[0] != Nh || (k == 0 && cols != want)) { cudaFree(Xh); return fail(SGM_EINVAL, "held-out entry %d has the wrong shape", k); }
-        double* stage = nullptr;
+        if (!A.data || A.dims[0] != Nh || (k == 0 && cols != want) || want < 0) return fail(SGM_EINVAL, "held-out entry %d has the wrong shape", k);
+        DevBuf<double> stage_buf;
         const size_t bytes = (size_t)Nh * cols * sizeof(double);
-        if (cudaMalloc(&stage, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(Xh); return fail(SGM_ENOMEM, "cannot allocate staging"); }
+        if (cudaMalloc(&stage_buf.p, bytes) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate staging"); }
+        double* stage = stage_buf.p;
         CU(cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream));
-        pack_rows_kernel<<<(unsigned)cdiv(Nh * cols, 256), 256, 0, h->stream>>>(stage, Nh, cols, Xh, h->ld, col0);
+        SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(Nh * cols, 256), 256, 0, h->stream, stage, Nh, cols, Xh, h->ld, col0);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));
-        cudaFree(stage);
         col0 += cols;
     }
     ChainArgs a = h->base;
@@ -1408,11 +1437,11 @@ extern "C" int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t 
     int rc = SGM_OK;
     switch (h->model) {
         case SGM_MODEL_GAUSS_MEAN:
-            small_logpost_kernel<SMALL_MODEL_GAUSS><<<(unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream>>>(a, 0u, h->dout); break;
+            SGM_LAUNCH(small_logpost_kernel<SMALL_MODEL_GAUSS>, (unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream, a, 0u, h->dout); break;
         case SGM_MODEL_MIXTURE2:
-            small_logpost_kernel<SMALL_MODEL_MIX2><<<(unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream>>>(a, 0u, h->dout); break;
+            SGM_LAUNCH(small_logpost_kernel<SMALL_MODEL_MIX2>, (unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream, a, 0u, h->dout); break;
         case SGM_MODEL_LOGISTIC:
-            logistic_logpost_kernel<<<h->C, 256, 0, h->stream>>>(a, 0u, h->theta, h->dout); break;
+            SGM_LAUNCH(logistic_logpost_kernel, h->C, 256, 0, h->stream, a, 0u, h->theta, h->dout); break;
         case SGM_MODEL_SOFTMAX_NET: {
             const int e = softmax_net_logpost(h->nn, a, 0u, h->theta, h->dout, h->stream);
             if (e != 0) rc = fail(SGM_ECUDA, "softmax net held-out: %s", cudaGetErrorString((cudaError_t)e));
@@ -1424,8 +1453,26 @@ extern "C" int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t 
         cudaMemcpyAsync(out, h->dout, (size_t)h->C * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(SGM_ECUDA, "held-out evaluation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    cudaFree(Xh);
     return rc;
+}
+
+// Pins one kernel path of a handle (tests and measurements; 0 restores the default dispatch).  Replaces the environment
+// switches of the first round: nothing on the dispatch path reads the environment.
+extern "C" int sgm_set_option(sgm_handle* h, const char* key, int32_t value) {
+    if (!h || !key) return fail(SGM_EINVAL, "null argument");
+    struct Opt { const char* key; int* slot; int max; };
+    const Opt opts[] = {{"logistic_kernel", &h->opt_logistic_kernel, 1}, {"gather", &h->opt_gather, 4}, {"fullgrad", &h->opt_fullgrad, 2}};
+    for (const Opt& o : opts)
+        if (!strcmp(key, o.key)) {
+            if (value < 0 || value > o.max) return fail(SGM_EINVAL, "option %s: value %d outside [0, %d]", key, value, o.max);
+            *o.slot = value;
+            return SGM_OK;
+        }
+    if (h->nn && !strncmp(key, "nn_", 3)) {
+        if (softmax_net_set_option(h->nn, key, value) == 0) return SGM_OK;
+        return fail(SGM_EINVAL, "option %s = %d is not one the softmax-net kernels know", key, value);
+    }
+    return fail(SGM_EINVAL, "unknown option '%s'", key);
 }
 
 extern "C" int64_t sgm_num_rows(const sgm_handle* h) { return h ? h->N : 0; }
@@ -1456,13 +1503,13 @@ extern "C" int sgm_copy_dataset(sgm_handle* h, int32_t entry, int64_t row0, int6
         else if (h->model == SGM_MODEL_SOFTMAX_NET) { col0 = h->d; cols = (int)h->tensors[2].size; }
         else return fail(SGM_EINVAL, "model has no dataset entry %d", entry);
     } else if (entry != 0) return fail(SGM_EINVAL, "model has no dataset entry %d", entry);
-    double* stage = nullptr;
-    CU(cudaMalloc(&stage, (size_t)rows * cols * sizeof(double)));
-    unpack_rows_kernel<<<(unsigned)cdiv(rows * cols, 256), 256, 0, h->stream>>>(h->X, row0, rows, cols, h->ld, col0, stage);
+    DevBuf<double> stage_buf;
+    CU(stage_buf.alloc((size_t)rows * cols));
+    double* stage = stage_buf.p;
+    SGM_LAUNCH(unpack_rows_kernel, (unsigned)cdiv(rows * cols, 256), 256, 0, h->stream, h->X, row0, rows, cols, h->ld, col0, stage);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, stage, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(stage);
     return SGM_OK;
 }
 
@@ -1536,6 +1583,7 @@ extern "C" int sgm_attach_peer_shards(sgm_handle* h, const void* handles, int32_
     if (h->model != SGM_MODEL_LOGISTIC) return fail(SGM_EINVAL, "a dataset sharded over ranks is implemented for the logistic family");
     if (h->inited) return fail(SGM_ESTATE, "attach the peer shards before sgm_init");
     if ((uint64_t)h->N * (uint64_t)world > 0xFFFFFFFFull) return fail(SGM_EINVAL, "more than 2^32 rows in total");
+    if (h->n_shards > 1 || h->d_shard_ptr) return fail(SGM_ESTATE, "peer shards are already attached (sgm_detach_peer_shards first)");
     if (int rc = set_device(h)) return rc;
     std::vector<const float*> table((size_t)world, nullptr);
     for (int r = 0; r < world; ++r) {
@@ -1543,7 +1591,11 @@ extern "C" int sgm_attach_peer_shards(sgm_handle* h, const void* handles, int32_
         cudaIpcMemHandle_t mh;
         memcpy(&mh, (const char*)handles + (size_t)r * sizeof mh, sizeof mh);
         void* p = nullptr;
-        CU(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        const cudaError_t oe = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (oe != cudaSuccess) {   // unmap what was mapped so far: the handle stays usable on its local rows
+            for (int q = 0; q < 16; ++q) if (h->peer_base[q]) { cudaIpcCloseMemHandle(h->peer_base[q]); h->peer_base[q] = nullptr; }
+            return fail(SGM_ECUDA, "cudaIpcOpenMemHandle (rank %d's shard) failed: %s", r, cudaGetErrorString(oe));
+        }
         h->peer_base[r] = p;
         table[r] = (const float*)p;
     }
@@ -1564,14 +1616,21 @@ extern "C" int sgm_detach_peer_shards(sgm_handle* h) {
     if (int rc = set_device(h)) return rc;
     CU(cudaStreamSynchronize(h->stream));
     for (int r = 0; r < 16; ++r) if (h->peer_base[r]) { cudaIpcCloseMemHandle(h->peer_base[r]); h->peer_base[r] = nullptr; }
-    h->n_shards = 1; h->base.n_shards = 0; h->base.shard_ptr = nullptr;
+    if (h->d_shard_ptr) { cudaFree((void*)h->d_shard_ptr); h->d_shard_ptr = nullptr; }
+    h->n_shards = 1; h->base.n_shards = 0; h->base.shard_ptr = nullptr; h->base.shard_rows = 0;
+    // back to the local row space: N, the permutation width and N / n (R/setup.R:116-118) were the global ones
+    h->base.N = (uint32_t)h->N; h->base.perm_bits = perm_bits((uint32_t)h->N);
+    h->base.corr = (float)((double)h->N / (double)h->n);
+    h->rhat_cached = false;
     h->inited = false;   // the sampler state referred to the global row space
     return SGM_OK;
 }
 
 extern "C" int sgm_comm_init(sgm_handle* h, const void* id, int32_t id_bytes, int32_t rank, int32_t world) {
     if (!h || !id || id_bytes < SGM_NCCL_ID_BYTES || world < 1 || rank < 0 || rank >= world) return fail(SGM_EINVAL, "bad argument");
-    if (h->cv && h->C > 1 && !(h->flags & SGM_FLAG_SHARED_MODE) && h->model != SGM_MODEL_LOGISTIC)
+    // without the flag every rank finds its own mode(s) (chain_offset differs), whatever the number of chains per rank: summing
+    // partial gradients taken at different modes is meaningless
+    if (h->cv && world > 1 && !(h->flags & SGM_FLAG_SHARED_MODE) && h->model != SGM_MODEL_LOGISTIC)
         return fail(SGM_EINVAL, "a row-sharded control-variate pass needs SGM_FLAG_SHARED_MODE (every rank must hold the same mode); "
                                 "one mode per chain across ranks is implemented for the logistic family");
     if (int rc = load_nccl()) return rc;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "ptx.cuh"
 #include "rng.cuh"
 
 namespace sgm {

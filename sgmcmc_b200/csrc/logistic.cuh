@@ -176,7 +176,7 @@ __device__ __forceinline__ void logi_pass(const ChainArgs& a, const LogiSmem& sm
 
 template <int G, int V>
 __global__ void __launch_bounds__(512) logistic_chain_kernel(const ChainArgs a) {
-    extern __shared__ __align__(16) float smem_f[];
+    SGM_DYN_SMEM(float, smem_f, 16);
     const int tid = threadIdx.x;
     const int ldp = V * G * 4;
     const int nw = blockDim.x >> 5;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(512) logistic_fullgrad_kernel(const float* __r
                                                                 int64_t row0, int64_t row1, int rows_per_cta,
                                                                 const float* __restrict__ theta_hat, int Pst,
                                                                 double* __restrict__ gsum) {
-    extern __shared__ __align__(16) float smem_f[];
+    SGM_DYN_SMEM(float, smem_f, 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ldp = V * G * 4;
     const int nw = blockDim.x >> 5;

@@ -58,48 +58,9 @@ struct CvgArgs {
     double* gsum;          // [M][Pst]: pass 1 adds the bias component (column d), pass 2 the feature components
 };
 
-__device__ __forceinline__ uint32_t cvg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cvg_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void cvg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cvg_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void cvg_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}"
-                 ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void cvg_tma_box2(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
 // K-major, 128-byte swizzle: 128-byte rows, 8-row groups 1024 bytes apart; a K step of 8 TF32 = +32 bytes in the start address
 __device__ __forceinline__ uint64_t cvg_desc(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void cvg_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
-}
-// A operand read from tensor memory (lane = row, one TF32 element per 32-bit column), B from shared memory
-__device__ __forceinline__ void cvg_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
-}
-__device__ __forceinline__ void cvg_tmem_st16(uint32_t taddr, const float (&v)[16]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-                 : "memory");
-}
-__device__ __forceinline__ void cvg_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool cvg_elect() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
 }
 __device__ __forceinline__ float cvg_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }   // round to nearest, ties away
 
@@ -121,9 +82,9 @@ __device__ __forceinline__ CvgItem cvg_item(const CvgArgs& a, int item) {
 }
 
 __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
-    extern __shared__ __align__(16) unsigned char cvg_smem[];
+    SGM_DYN_SMEM(unsigned char, cvg_smem, 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t base = (cvg_smem_u32(cvg_smem) + 1023u) & ~1023u;
+    const uint32_t base = (smem_u32(cvg_smem) + 1023u) & ~1023u;
     const uint32_t raw0 = base, lo0 = base + CVG_NRAW * CVG_STAGE_BYTES;   // lo stages hold only the B residuals
     const uint32_t bars = lo0 + CVG_NLO * CVG_OP_BYTES;
     // barriers: full[NRAW] | rawfree[NRAW] | conv[NLO] | lofree[NLO] | tfull[2] | tfree[2]; then the TMEM slot
@@ -131,20 +92,19 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                    b_tfull = b_lofree + 8 * CVG_NLO, b_tfree = b_tfull + 16, slot = b_tfree + 16;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        tmem_alloc<512>(slot);
+        tmem_relinquish();
     }
     if (tid == 0) {
-        for (int s = 0; s < CVG_NRAW; ++s) { cvg_mbar_init(b_full + 8 * s, 1); cvg_mbar_init(b_rawfree + 8 * s, 1); }
-        for (int l = 0; l < CVG_NLO; ++l) { cvg_mbar_init(b_conv + 8 * l, CVG_BCONV_WARPS); cvg_mbar_init(b_lofree + 8 * l, 1); }
-        for (int t = 0; t < 2; ++t) { cvg_mbar_init(b_tfull + 8 * t, 1); cvg_mbar_init(b_tfree + 8 * t, CVG_WARPS - CVG_DRAIN_WARP0); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < CVG_NRAW; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_rawfree + 8 * s, 1); }
+        for (int l = 0; l < CVG_NLO; ++l) { mbar_init(b_conv + 8 * l, CVG_BCONV_WARPS); mbar_init(b_lofree + 8 * l, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(b_tfull + 8 * t, 1); mbar_init(b_tfree + 8 * t, CVG_WARPS - CVG_DRAIN_WARP0); }
+        fence_mbar_init();
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+    tc_fence_after();
+    const uint32_t tmem = lds_u32(slot);
 
     // every role walks the same item sequence; g = running stage counter, sg = running segment counter (barrier phases never reset)
     if (warp == 0) {
@@ -155,11 +115,11 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                 const CvgItem w = cvg_item(a, item);
                 for (int c = 0; c < w.nchunks; ++c, ++g) {
                     const uint32_t s = g % CVG_NRAW;
-                    if (g >= CVG_NRAW) cvg_mbar_wait(b_rawfree + 8 * s, ((g / CVG_NRAW) - 1u) & 1u);
+                    if (g >= CVG_NRAW) mbar_wait(b_rawfree + 8 * s, ((g / CVG_NRAW) - 1u) & 1u);
                     const uint32_t dst = raw0 + s * CVG_STAGE_BYTES, bar = b_full + 8 * s;
-                    cvg_mbar_expect_tx(bar, CVG_STAGE_BYTES);
-                    cvg_tma_box2(dst, &tmA, w.ka0 + c * CVG_KC, a.a_row0 + w.tile_a * CVG_TILE, bar);
-                    cvg_tma_box2(dst + CVG_OP_BYTES, &tmB, w.kb0 + c * CVG_KC, w.tile_b * CVG_TILE, bar);
+                    mbar_expect_tx(bar, CVG_STAGE_BYTES);
+                    tma_box2(dst, &tmA, w.ka0 + c * CVG_KC, a.a_row0 + w.tile_a * CVG_TILE, bar);
+                    tma_box2(dst + CVG_OP_BYTES, &tmB, w.kb0 + c * CVG_KC, w.tile_b * CVG_TILE, bar);
                 }
             }
         }
@@ -172,23 +132,23 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
             for (int c = 0; c < w.nchunks; ++c, ++g) {
                 const uint32_t s = g % CVG_NRAW, l = g % CVG_NLO, tb = sg & 1u;
                 const bool seg_first = (c % CVG_SEG) == 0, seg_last = (c % CVG_SEG) == CVG_SEG - 1 || c == w.nchunks - 1;
-                if (seg_first && sg >= 2) cvg_mbar_wait(b_tfree + 8 * tb, ((sg >> 1) - 1u) & 1u);   // buffer drained
-                cvg_mbar_wait(b_conv + 8 * l, (g / CVG_NLO) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (cvg_elect()) {
+                if (seg_first && sg >= 2) mbar_wait(b_tfree + 8 * tb, ((sg >> 1) - 1u) & 1u);   // buffer drained
+                mbar_wait(b_conv + 8 * l, (g / CVG_NLO) & 1u);
+                tc_fence_after();
+                if (elect_one()) {
                     const uint32_t td = tmem + tb * CVG_TILE;
                     const uint64_t bhi = cvg_desc(raw0 + s * CVG_STAGE_BYTES + CVG_OP_BYTES), blo = cvg_desc(lo0 + l * CVG_OP_BYTES);
                     const uint32_t ahi = tmem + CVG_TMEM_A + l * 64u, alo = ahi + 32u;
 #pragma unroll
                     for (int k8 = 0; k8 < CVG_KC / 8; ++k8) {
                         const uint64_t ko = (uint64_t)(2 * k8);
-                        cvg_mma_ts(td, ahi + 8u * k8, bhi + ko, idesc, !(seg_first && k8 == 0));
-                        cvg_mma_ts(td, ahi + 8u * k8, blo + ko, idesc, true);
-                        cvg_mma_ts(td, alo + 8u * k8, bhi + ko, idesc, true);
+                        umma_tf32_ts(td, ahi + 8u * k8, bhi + ko, idesc, !(seg_first && k8 == 0));
+                        umma_tf32_ts(td, ahi + 8u * k8, blo + ko, idesc, true);
+                        umma_tf32_ts(td, alo + 8u * k8, bhi + ko, idesc, true);
                     }
-                    cvg_commit(b_rawfree + 8 * s);
-                    cvg_commit(b_lofree + 8 * l);
-                    if (seg_last) cvg_commit(b_tfull + 8 * tb);
+                    umma_commit(b_rawfree + 8 * s);
+                    umma_commit(b_lofree + 8 * l);
+                    if (seg_last) umma_commit(b_tfull + 8 * tb);
                 }
                 __syncwarp();
                 if (seg_last) ++sg;
@@ -213,19 +173,19 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
             for (int c = 0; c < w.nchunks; ++c, ++g) {
                 const uint32_t s = g % CVG_NRAW, l = g % CVG_NLO;
                 const uint32_t raw = raw0 + s * CVG_STAGE_BYTES, braw = raw + CVG_OP_BYTES, lo = lo0 + l * CVG_OP_BYTES;
-                if (g >= CVG_NLO) cvg_mbar_wait(b_lofree + 8 * l, ((g / CVG_NLO) - 1u) & 1u);
-                cvg_mbar_wait(b_full + 8 * s, (g / CVG_NRAW) & 1u);
+                if (g >= CVG_NLO) mbar_wait(b_lofree + 8 * l, ((g / CVG_NLO) - 1u) & 1u);
+                mbar_wait(b_full + 8 * s, (g / CVG_NRAW) & 1u);
                 // all shared loads of this thread first (one latency per stage), then the splits and the stores
                 float4 xb[6], xa[8];
 #pragma unroll
                 for (int u = 0; u < 6; ++u)
-                    if (u < b_rounds) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xb[u].x), "=f"(xb[u].y), "=f"(xb[u].z), "=f"(xb[u].w) : "r"(braw + 16u * (uint32_t)(b_first + u * b_step)));
+                    if (u < b_rounds) xb[u] = lds128(braw + 16u * (uint32_t)(b_first + u * b_step));
                 const uint32_t rowp = raw + (uint32_t)r * 128u;
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc)
                     if (cc < 4 * nhalf) {
                         const uint32_t chunk = (uint32_t)((4 * hb0 + cc) ^ (r & 7));
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xa[cc].x), "=f"(xa[cc].y), "=f"(xa[cc].z), "=f"(xa[cc].w) : "r"(rowp + 16u * chunk));
+                        xa[cc] = lds128(rowp + 16u * chunk);
                     }
 #pragma unroll
                 for (int u = 0; u < 6; ++u)
@@ -233,8 +193,8 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                         const uint32_t off = 16u * (uint32_t)(b_first + u * b_step);
                         const float hx = cvg_tf32(xb[u].x), hy = cvg_tf32(xb[u].y), hz = cvg_tf32(xb[u].z), hw = cvg_tf32(xb[u].w);
                         const float lx = cvg_tf32(xb[u].x - hx), ly = cvg_tf32(xb[u].y - hy), lz = cvg_tf32(xb[u].z - hz), lq = cvg_tf32(xb[u].w - hw);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(braw + off), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + off), "f"(lx), "f"(ly), "f"(lz), "f"(lq) : "memory");
+                        sts128(braw + off, make_float4(hx, hy, hz, hw));
+                        sts128(lo + off, make_float4(lx, ly, lz, lq));
                     }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh)
@@ -248,14 +208,14 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                             lv[4 * cc + 2] = cvg_tf32(x.z - hi[4 * cc + 2]); lv[4 * cc + 3] = cvg_tf32(x.w - hi[4 * cc + 3]);
                         }
                         const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + CVG_TMEM_A + l * 64u + 16u * (uint32_t)(hb0 + hh);
-                        cvg_tmem_st16(ta, hi);
-                        cvg_tmem_st16(ta + 32u, lv);
+                        tmem_st16(ta, hi);
+                        tmem_st16(ta + 32u, lv);
                     }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tmem_wait_st();
+                tc_fence_before();
+                fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) cvg_mbar_arrive(b_conv + 8 * l);
+                if (lane == 0) mbar_arrive(b_conv + 8 * l);
             }
         }
     } else {
@@ -272,22 +232,19 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
             const int nseg = (w.nchunks + CVG_SEG - 1) / CVG_SEG;
             for (int sl = 0; sl < nseg; ++sl, ++sg) {
                 const uint32_t tb = sg & 1u;
-                cvg_mbar_wait(b_tfull + 8 * tb, (sg >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                mbar_wait(b_tfull + 8 * tb, (sg >> 1) & 1u);
+                tc_fence_after();
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) {
                     uint32_t rr[16];
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                 : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]), "=r"(rr[9]),
-                                   "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
-                                 : "r"(tq + tb * CVG_TILE + 16u * gq));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    tmem_ld16(tq + tb * CVG_TILE + 16u * gq, rr);
+                    tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[16 * gq + j] += __uint_as_float(rr[j]);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) cvg_mbar_arrive(b_tfree + 8 * tb);
+                if (lane == 0) mbar_arrive(b_tfree + 8 * tb);
             }
             // ---- epilogue: this thread owns C row 32 q + lane, columns 64 hb .. 64 hb + 63 of the tile
             const int arow = w.tile_a * CVG_TILE + 32 * q + lane;
@@ -318,9 +275,9 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
             }
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 // zero the alignment columns [0, cols) of every row of R^T

@@ -27,7 +27,7 @@ template <bool LONG, int V>
 __global__ void __launch_bounds__(FG_THREADS, 2) logistic_fullgrad_stream_kernel(const float* __restrict__ X, int ld, int d, int64_t row0,
                                                                                  int64_t row1, int tile_rows, int n_tiles,
                                                                                  const float* __restrict__ theta_hat, double* __restrict__ gsum) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SGM_DYN_SMEM(unsigned char, smem_raw, 128);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Q = ld >> 2, qt = d >> 2, ct = d & 3;
     float* tiles = reinterpret_cast<float*>(smem_raw);
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(FG_THREADS, 2) logistic_fullgrad_stream_kernel
     for (int e = tid; e < ld; e += FG_THREADS) th[e] = (e < d) ? theta_hat[e] : 0.f;
     const float bias = theta_hat[d];
     if (tid < FG_STAGES) mbar_init(bars + 8u * tid, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbar_init();
     __syncthreads();
 
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(FG_THREADS, 2) logistic_fullgrad_stream_kernel
         }
         __syncthreads();   // the stage is free again
         if (tid == 0 && k + FG_STAGES < my_tiles) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fence_proxy_async();
             issue(k + FG_STAGES);
         }
     }

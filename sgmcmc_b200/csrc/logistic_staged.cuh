@@ -39,10 +39,6 @@ constexpr int LS_THREADS = 256;
 constexpr int LS_WARPS = LS_THREADS / 32;
 constexpr int LS_MAX_R = 4;   // rows per lane (n <= 1024)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // sigmoid with a full-precision exponential and a single-instruction reciprocal
 __device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.0f, 1.0f + expf(-z)); }
 __device__ __forceinline__ float fdot4(const float4 a, const float4 b, float acc) {
@@ -88,55 +84,14 @@ __global__ void logistic_cache_rhat_kernel(float* __restrict__ X, int64_t N, int
     if (lane == 0) X[row * ld + d + 1] = xr[d] - sigmoidf(theta_hat[d] + z);
 }
 
-// HAT_DOT: control variates whose residual at the mode is NOT cached in the rows (per-chain modes)
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-// TMA 1-D bulk copy global -> shared::cta, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// TMA tile::gather4: FOUR rows of a 2-D tensor (box = ld x 1) per instruction, landing contiguously in shared
-// memory (SASS: UTMALDG.2D.GATHER4).  Quarter the TMA requests and issue loops of one-bulk-copy-per-row.
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int r0, int r1, int r2, int r3, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-                 : "memory");
-}
-
 #define LS_TICK(slot)                                                                      \
     if (a.prof && tid == 0) { const long long t_ = clock64(); atomicAdd(a.prof + (slot), (unsigned long long)(t_ - t_prev)); t_prev = t_; }
-
-// explicit shared-space accessors: generic pointers into shared memory cost an address-window conversion per
-// access and keep ptxas from batching the loads (profiles/r01_c3_staged_v4.txt)
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 // HAT_DOT: control variates whose residual at the mode is NOT cached in the rows (per-chain modes)
 // R: rows per lane = ceil(n / 256)
 template <bool HAT_DOT, int R>
 __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const ChainArgs a, const __grid_constant__ CUtensorMap tmap) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SGM_DYN_SMEM(unsigned char, smem_raw, 128);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = a.d, ld = a.ld, n = a.n;
     const int Q = ld >> 2, S = ls_row_stride4(ld);
@@ -163,7 +118,7 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
     uint32_t bar_uses = 0;
     if (a.gather_tma) {
         if (lane == 0) mbar_init(bar_s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
     long long t_prev = clock64();
 
@@ -228,7 +183,7 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
                 auto via_tma = [&](int r) -> bool { return a.gather_tma == 1 || a.gather_tma == 3 || (a.gather_tma == 2 && (r & 1) == 0); };
                 int tma_rows = 0;
                 if (a.gather_tma) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    fence_proxy_async();
 #pragma unroll
                     for (int r = 0; r < R; ++r)
                         if (via_tma(r)) { int cnt = n - (r * LS_THREADS + warp * 32); tma_rows += cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt); }
@@ -244,7 +199,7 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
                         const int r2 = __shfl_down_sync(0xffffffffu, (int)next_row[r], 2);
                         const int r3 = __shfl_down_sync(0xffffffffu, (int)next_row[r], 3);
                         if ((j | 3) < n) {
-                            if ((lane & 3) == 0) tma_gather4(rows_s + (uint32_t)(j * S) * 16u, &tmap, (int)next_row[r], r1, r2, r3, bar_s);
+                            if ((lane & 3) == 0) tma_gather4(rows_s + (uint32_t)(j * S) * 16u, &tmap, 0, (int)next_row[r], r1, r2, r3, bar_s);
                         } else if (j < n) {
                             bulk_g2s(rows_s + (uint32_t)(j * S) * 16u, a.X + (size_t)next_row[r] * ld, (uint32_t)ld * 4u, bar_s);
                         }
@@ -259,7 +214,7 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
                             const uint32_t row = __shfl_sync(0xffffffffu, my_row, jr & 31);
                             if (g_live && jr < 32 && j0 + jr < n) {
                                 const float* src = a.X + ((size_t)row * ld + 4 * g_q);
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(i * rpi * S) * 16u), "l"(src) : "memory");
+                                cp_async16(dst0 + (uint32_t)(i * rpi * S) * 16u, src);
                             }
                         }
                     }

@@ -38,7 +38,7 @@ __host__ __device__ __forceinline__ U4 philox4x32(uint32_t c0, uint32_t c1, uint
     return U4{c0, c1, c2, c3};
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(SGM_EMU)
 // Two uint32 words -> two N(0,1) float32 (Box-Muller on 24-bit uniforms).
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
     const float u1 = ((float)(a >> 8) + 1.0f) * 5.9604644775390625e-8f;  // (0,1]

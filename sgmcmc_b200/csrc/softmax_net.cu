@@ -63,6 +63,10 @@ struct SoftmaxNetWork {
     struct MapEntry { const void* base; long long rows; long long stride; CUtensorMap map; };
     MapEntry maps[8];
     int n_maps = 0;
+    // kernel selectors (softmax_net_set_option); 0 = default
+    int opt_update = 0;   // 1: register-staged update of every tensor
+    int opt_stage1 = 0;   // 1: register-staged forward-GEMM operands (no TMA)
+    int opt_stage5 = 0;   // 1: S5 with the X tile on the tensor-memory side (only in builds with -DNN_ENABLE_S5_TMEM)
 };
 
 // TMA descriptors of one gradient evaluation: the dataset (rows gathered four at a time) and the parameter array that
@@ -1779,8 +1783,7 @@ static const CUtensorMap* nn_b_map(SoftmaxNetWork* w, const float* state, long l
 }
 
 static bool nn_tma_enabled(const SoftmaxNetWork* w) {
-    const char* f = getenv("SGM_NN_S1");
-    if (f && !strcmp(f, "regs")) return false;
+    if (w->opt_stage1 == 1) return false;
     return (w->dm.offB % 4) == 0 && (size_t)nn_s1_ring_bytes(w->dm) <= (size_t)(2 * NN_RB * w->dm.dh + nn_tile_floats_all(w->dm)) * 4;
 }
 
@@ -1804,6 +1807,16 @@ int softmax_net_create(SoftmaxNetWork** out, int d_in, int d_hidden, int d_out, 
     return 0;
 }
 
+int softmax_net_set_option(SoftmaxNetWork* w, const char* key, int value) {
+    if (!w || !key || value < 0 || value > 1) return -1;
+    if (!strcmp(key, "nn_update")) { w->opt_update = value; return 0; }
+    if (!strcmp(key, "nn_stage1")) { w->opt_stage1 = value; return 0; }
+#ifdef NN_ENABLE_S5_TMEM
+    if (!strcmp(key, "nn_stage5")) { w->opt_stage5 = value; return 0; }
+#endif
+    return -1;
+}
+
 void softmax_net_destroy(SoftmaxNetWork* w) {
     if (!w) return;
     if (w->G) cudaFree(w->G);
@@ -1824,11 +1837,9 @@ void softmax_net_tables(const SoftmaxNetWork* w, int* flat_of, int* tensor_of, i
 int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t stream, int* launches) {
     cudaMemcpyToSymbolAsync(nn_prof, &a.prof, sizeof(a.prof), 0, cudaMemcpyHostToDevice, stream);
     {
-        const char* u = getenv("SGM_NN_UPDATE");
-        const int on = (u && !strcmp(u, "regs")) ? 0 : 1;
+        const int on = w->opt_update == 1 ? 0 : 1;
         cudaMemcpyToSymbolAsync(nn_stream_updates, &on, sizeof(on), 0, cudaMemcpyHostToDevice, stream);
-        const char* s5 = getenv("SGM_NN_S5");
-        const int s5on = (s5 && !strcmp(s5, "tmem")) ? 1 : 0;   // opt-in until it has run on a GPU
+        const int s5on = w->opt_stage5 == 1 ? 1 : 0;   // opt-in until it has run on a GPU
         cudaMemcpyToSymbolAsync(nn_s5_tmem, &s5on, sizeof(s5on), 0, cudaMemcpyHostToDevice, stream);
     }
     int sms = 0;

@@ -8,6 +8,8 @@ int softmax_net_create(SoftmaxNetWork** out, int d_in, int d_hidden, int d_out, 
 void softmax_net_destroy(SoftmaxNetWork* w);
 // internal element -> flat (ABI) index / tensor id tables (A and B are stored row-major internally)
 void softmax_net_tables(const SoftmaxNetWork* w, int* flat_of, int* tensor_of, int Pst);
+// kernel selectors (sgm_set_option keys "nn_update", "nn_stage1"); returns 0 when the key / value is known
+int softmax_net_set_option(SoftmaxNetWork* w, const char* key, int value);
 int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t stream, int* launches);
 int softmax_net_fullgrad(SoftmaxNetWork* w, const ChainArgs& a, int64_t row0, int64_t row1, int M,
                          const float* theta_hat, double* gsum, cudaStream_t stream);

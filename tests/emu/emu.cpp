@@ -1,0 +1,841 @@
+// TEST INFRASTRUCTURE ONLY -- see include/cuda_runtime.h.  Scheduler, memory, runtime-API shims and the asynchronous engines of
+// the CPU emulation the kernel sources are compiled against in the GPU-less container.
+#define SGM_EMU 1
+#include "cuda_runtime.h"
+
+#include <signal.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <deque>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// context switch (x86-64 SysV): callee-saved registers + stack pointer
+// ------------------------------------------------------------------------------------------------------------------------------
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+
+namespace emu {
+
+uint3 threadIdx_, blockIdx_;
+dim3 blockDim_, gridDim_;
+
+static bool g_lazy = true;          // SGM_EMU_ASYNC
+static int g_sms = 2;               // SGM_EMU_SMS
+static bool g_verbose = false;
+
+// ---- sticky error ------------------------------------------------------------------------------------------------------------
+static int g_err = 0;               // sticky (context-destroying) error
+static int g_last = 0;              // non-sticky last error
+static std::string g_errmsg;
+
+// ---- fibers ------------------------------------------------------------------------------------------------------------------
+constexpr size_t STACK_BYTES = 256 * 1024;
+struct CpAsyncOp { uint32_t dst; const void* src; };
+struct Fiber {
+    void* sp = nullptr;
+    char* stack = nullptr;
+    bool done = true;
+    std::vector<std::vector<CpAsyncOp>> cp_groups;   // committed, not yet waited for
+    std::vector<CpAsyncOp> cp_open;                  // issued since the last commit
+    int bulk_store_groups = 0;
+};
+struct WarpEx {
+    uint64_t slot[2][32];
+    unsigned have[2] = {0, 0}, read[2] = {0, 0};
+    unsigned gen[32];
+    unsigned alive = 0;
+};
+struct PendingCopy { std::function<void()> run; uint32_t bytes; };
+struct Mbar {
+    bool inited = false;
+    uint32_t count = 0, pending = 0;
+    int64_t tx = 0;
+    uint32_t phase = 0;
+    std::deque<PendingCopy> copies;     // TMA loads that complete_tx on this barrier (lazy mode)
+    int mma_commits = 0;                // tcgen05.commit arrivals owed once the MMA queue has drained up to them
+};
+struct MmaOp { std::function<void()> run; };
+struct MmaCommit { size_t upto; uint32_t bar; };
+
+struct Cta {
+    std::vector<Fiber> fibers;
+    std::vector<WarpEx> warps;
+    int nthreads = 0, alive = 0, cur = -1;
+    int bar_count = 0; unsigned bar_gen = 0;
+    unsigned long long progress = 0;
+    unsigned char* smem = nullptr; size_t smem_bytes = 0; size_t smem_align = 16; uint32_t window = 0;
+    std::unordered_map<uint32_t, Mbar> mbars;
+    std::vector<uint32_t> tmem;         // [128][512]
+    uint32_t tmem_alloc_cols = 0; bool tmem_permit = true;
+    std::deque<MmaOp> mma_queue; size_t mma_issued = 0, mma_done = 0;
+    std::deque<MmaCommit> mma_commits;
+    const std::function<void()>* body = nullptr;
+    const char* kname = "";
+    bool aborted = false;
+};
+static Cta* g_cta = nullptr;
+static void* g_main_sp = nullptr;
+static std::vector<char*> g_stack_pool;
+static unsigned char* g_smem_pool = nullptr;
+constexpr size_t SMEM_POOL = 256 * 1024 + 4096;
+
+static char* get_stack() {
+    if (!g_stack_pool.empty()) { char* s = g_stack_pool.back(); g_stack_pool.pop_back(); return s; }
+    void* p = mmap(nullptr, STACK_BYTES + 4096, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (p == MAP_FAILED) { perror("emu: mmap stack"); abort(); }
+    mprotect(p, 4096, PROT_NONE);   // guard below the stack
+    return (char*)p + 4096;
+}
+
+static void fiber_exit();
+extern "C" void emu_trampoline() {
+    (*g_cta->body)();
+    fiber_exit();
+}
+
+static void switch_to_main() {
+    Fiber& f = g_cta->fibers[g_cta->cur];
+    emu_switch(&f.sp, g_main_sp);
+}
+
+void progress() { if (g_cta) ++g_cta->progress; }
+
+void yield() {
+    if (!g_cta) return;
+    switch_to_main();
+}
+
+static void release_barrier_if_complete(Cta& c) {
+    if (c.alive > 0 && c.bar_count >= c.alive) { c.bar_count = 0; ++c.bar_gen; ++c.progress; }
+}
+
+static void fiber_exit() {
+    Cta& c = *g_cta;
+    Fiber& f = c.fibers[c.cur];
+    if (!f.cp_open.empty() || !f.cp_groups.empty()) {
+        // outstanding cp.async at thread exit complete eventually on hardware; apply them now
+        for (auto& g : f.cp_groups) for (auto& op : g) std::memcpy(smem_ptr(op.dst, 16, 16), op.src, 16);
+        for (auto& op : f.cp_open) std::memcpy(smem_ptr(op.dst, 16, 16), op.src, 16);
+        f.cp_groups.clear(); f.cp_open.clear();
+    }
+    f.done = true;
+    --c.alive;
+    c.warps[c.cur >> 5].alive &= ~(1u << (c.cur & 31));
+    ++c.progress;
+    release_barrier_if_complete(c);
+    void* dummy;
+    emu_switch(&dummy, g_main_sp);
+    abort();   // never resumed
+}
+
+[[noreturn]] void fault(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    char where[256] = "";
+    if (g_cta && g_cta->cur >= 0)
+        snprintf(where, sizeof where, " [kernel %s, block (%u,%u,%u), thread %d]", g_cta->kname, blockIdx_.x, blockIdx_.y, blockIdx_.z, g_cta->cur);
+    g_errmsg = std::string("emu fault: ") + buf + where;
+    g_err = cudaErrorLaunchFailure;
+    if (g_verbose || getenv("SGM_EMU_TRACE")) fprintf(stderr, "%s\n", g_errmsg.c_str());
+    if (g_cta && g_cta->cur >= 0) {
+        g_cta->aborted = true;
+        void* dummy;
+        emu_switch(&dummy, g_main_sp);
+    }
+    fprintf(stderr, "%s (outside a kernel)\n", g_errmsg.c_str());
+    abort();
+}
+
+int linear_tid() { return g_cta ? g_cta->cur : 0; }
+int lane_id() { return linear_tid() & 31; }
+int warp_id() { return linear_tid() >> 5; }
+long long clock() { static long long t = 0; return t += 7; }
+
+void syncthreads() {
+    Cta& c = *g_cta;
+    const unsigned my = c.bar_gen;
+    ++c.bar_count; ++c.progress;
+    release_barrier_if_complete(c);
+    while (c.bar_gen == my) yield();
+}
+
+uint64_t shfl(unsigned mask, uint64_t v, int src) {
+    Cta& c = *g_cta;
+    WarpEx& w = c.warps[c.cur >> 5];
+    const int lane = c.cur & 31;
+    const unsigned b = w.gen[lane] & 1u;
+    if (!((mask >> lane) & 1u)) fault("warp shuffle/sync executed by lane %d which is not in its mask %08x", lane, mask);
+    w.slot[b][lane] = v; w.have[b] |= 1u << lane; ++c.progress;
+    for (;;) {
+        const unsigned need = mask & w.alive;
+        if ((w.have[b] & need) == need) break;
+        yield();
+    }
+    const uint64_t r = w.slot[b][src & 31];
+    w.read[b] |= 1u << lane;
+    const unsigned need = mask & w.alive;
+    if ((w.read[b] & need) == need) { w.have[b] = 0; w.read[b] = 0; }
+    ++w.gen[lane];
+    return r;
+}
+void syncwarp(unsigned mask) { (void)shfl(mask, 0, lane_id()); }
+bool elect_one() { return lane_id() == 0; }
+
+unsigned char* dyn_smem(size_t align) {
+    Cta& c = *g_cta;
+    if (align > c.smem_align) {
+        // the declared alignment of the extern array fixes the window base; all threads of a CTA declare the same one
+        c.smem_align = align;
+    }
+    return c.smem;
+}
+static uint32_t window_base(size_t align) { return align >= 1024 ? 2048u : 1024u + (uint32_t)align; }   // aligned to `align` and no further
+
+uint32_t smem_window(const void* p) {
+    Cta& c = *g_cta;
+    const unsigned char* q = (const unsigned char*)p;
+    if (q < c.smem || q > c.smem + c.smem_bytes) fault("cvta.to.shared of a pointer outside the CTA's dynamic shared memory");
+    return window_base(c.smem_align) + (uint32_t)(q - c.smem);
+}
+unsigned char* smem_ptr(uint32_t addr, size_t bytes, size_t align) {
+    Cta& c = *g_cta;
+    const uint32_t base = window_base(c.smem_align);
+    if (addr < base || (size_t)(addr - base) + bytes > c.smem_bytes)
+        fault("shared-memory access out of range: window address 0x%x + %zu, dynamic shared memory is [0x%x, 0x%zx)", addr, bytes, base, (size_t)base + c.smem_bytes);
+    if (align > 1 && (addr % align) != 0) fault("misaligned shared-memory access: address 0x%x, %zu-byte alignment required", addr, align);
+    return c.smem + (addr - base);
+}
+
+// ---- global memory -----------------------------------------------------------------------------------------------------------
+struct Alloc { size_t bytes; void* map; size_t map_bytes; };
+static std::map<const unsigned char*, Alloc> g_allocs;
+static const size_t PAGE = 4096;
+
+static const Alloc* find_alloc(const void* p, const unsigned char** base) {
+    auto it = g_allocs.upper_bound((const unsigned char*)p);
+    if (it == g_allocs.begin()) return nullptr;
+    --it;
+    if ((const unsigned char*)p < it->first + it->second.bytes) { *base = it->first; return &it->second; }
+    return nullptr;
+}
+void check_global(const void* p, size_t bytes, size_t align, const char* what) {
+    const unsigned char* base = nullptr;
+    const Alloc* a = find_alloc(p, &base);
+    if (!a || (const unsigned char*)p + bytes > base + a->bytes) fault("%s: global range [%p, +%zu) is not inside a device allocation", what, p, bytes);
+    if (align > 1 && ((uintptr_t)p % align) != 0) fault("%s: global address %p is not %zu-byte aligned", what, p, align);
+}
+
+static void segv_handler(int, siginfo_t* si, void*) {
+    if (g_cta && g_cta->cur >= 0) {
+        const unsigned char* base = nullptr;
+        (void)base;
+        // nearest allocation, for the message
+        auto it = g_allocs.upper_bound((const unsigned char*)si->si_addr);
+        char near[128] = "";
+        if (it != g_allocs.begin()) { --it; snprintf(near, sizeof near, " (%+lld bytes past the end of a %zu-byte allocation)", (long long)((const unsigned char*)si->si_addr - (it->first + it->second.bytes)), it->second.bytes); }
+        fault("illegal address %p%s", si->si_addr, near);
+    }
+    signal(SIGSEGV, SIG_DFL);
+    raise(SIGSEGV);
+}
+
+static void init_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char* a = getenv("SGM_EMU_ASYNC");
+    g_lazy = !(a && !strcmp(a, "eager"));
+    if (const char* s = getenv("SGM_EMU_SMS")) g_sms = atoi(s) > 0 ? atoi(s) : 2;
+    g_verbose = getenv("SGM_EMU_VERBOSE") != nullptr;
+    struct sigaction sa;
+    memset(&sa, 0, sizeof sa);
+    sa.sa_sigaction = segv_handler;
+    sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+    sigaction(SIGSEGV, &sa, nullptr);
+    g_smem_pool = (unsigned char*)mmap(nullptr, SMEM_POOL, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+}
+
+// ---- launch ------------------------------------------------------------------------------------------------------------------
+static std::unordered_map<const void*, int> g_dyn_limit;
+
+static void run_cta(Cta& c) {
+    g_cta = &c;
+    // round-robin; a pass without progress while threads are still alive = deadlock
+    int stalled = 0;
+    while (c.alive > 0 && !c.aborted) {
+        const unsigned long long before = c.progress;
+        for (int t = 0; t < c.nthreads && !c.aborted; ++t) {
+            Fiber& f = c.fibers[t];
+            if (f.done) continue;
+            c.cur = t;
+            threadIdx_.x = (unsigned)t % blockDim_.x;
+            threadIdx_.y = ((unsigned)t / blockDim_.x) % blockDim_.y;
+            threadIdx_.z = (unsigned)t / (blockDim_.x * blockDim_.y);
+            emu_switch(&g_main_sp, f.sp);
+        }
+        if (c.progress == before) { if (++stalled >= 4) break; } else stalled = 0;
+    }
+    if (!c.aborted && c.alive > 0) {
+        c.cur = -1;
+        std::string who;
+        for (int t = 0; t < c.nthreads && who.size() < 200; ++t) if (!c.fibers[t].done) who += std::to_string(t) + " ";
+        g_errmsg = std::string("emu fault: DEADLOCK in kernel ") + c.kname + ", block (" + std::to_string(blockIdx_.x) + "," + std::to_string(blockIdx_.y) + "," +
+                   std::to_string(blockIdx_.z) + "): threads still waiting: " + who;
+        g_err = cudaErrorLaunchTimeout;
+        c.aborted = true;
+        if (g_verbose || getenv("SGM_EMU_TRACE")) fprintf(stderr, "%s\n", g_errmsg.c_str());
+    }
+    c.cur = -1;
+    g_cta = nullptr;
+}
+
+void launch(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+    init_once();
+    if (g_err) return;
+    const size_t nthreads = (size_t)block.x * block.y * block.z;
+    if (nthreads == 0 || nthreads > 1024 || grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535 || grid.z > 65535) {
+        g_last = cudaErrorInvalidValue; g_errmsg = std::string("emu: invalid launch configuration for ") + name; return;
+    }
+    int limit = 48 * 1024;
+    auto it = g_dyn_limit.find(fn);
+    if (it != g_dyn_limit.end()) limit = it->second;
+    if (smem > (size_t)limit) {
+        g_last = cudaErrorInvalidValue;
+        g_errmsg = std::string("emu: ") + name + " launched with " + std::to_string(smem) + " B of dynamic shared memory, limit " + std::to_string(limit) +
+                   " (cudaFuncAttributeMaxDynamicSharedMemorySize)";
+        return;
+    }
+    gridDim_ = grid; blockDim_ = block;
+    for (unsigned bz = 0; bz < grid.z && !g_err; ++bz)
+        for (unsigned by = 0; by < grid.y && !g_err; ++by)
+            for (unsigned bx = 0; bx < grid.x && !g_err; ++bx) {
+                Cta c;
+                c.kname = name; c.body = &body; c.nthreads = (int)nthreads; c.alive = (int)nthreads;
+                c.fibers.resize(nthreads);
+                c.warps.resize((nthreads + 31) / 32);
+                for (size_t t = 0; t < nthreads; ++t) {
+                    Fiber& f = c.fibers[t];
+                    f.stack = get_stack(); f.done = false;
+                    uintptr_t top = ((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15;
+                    void** sp = (void**)(top - 16);
+                    sp[0] = (void*)&emu_trampoline;
+                    sp -= 6;
+                    for (int k = 0; k < 6; ++k) sp[k] = nullptr;
+                    f.sp = sp;
+                    WarpEx& w = c.warps[t >> 5];
+                    w.alive |= 1u << (t & 31); w.gen[t & 31] = 0;
+                }
+                // poison shared memory: uninitialised reads give NaNs, not zeros
+                memset(g_smem_pool, 0xff, SMEM_POOL);
+                c.smem = g_smem_pool + 1024; c.smem_bytes = smem;
+                blockIdx_.x = bx; blockIdx_.y = by; blockIdx_.z = bz;
+                run_cta(c);
+                for (auto& f : c.fibers) g_stack_pool.push_back(f.stack);
+                if (!c.aborted && c.tmem_alloc_cols != 0) {
+                    g_err = cudaErrorLaunchFailure; g_errmsg = std::string("emu fault: kernel ") + name + " exited without tcgen05.dealloc";
+                }
+            }
+}
+
+}  // namespace emu
+
+// --------------------------------------------------------------------------------------------------------------------------------
+// runtime API
+// --------------------------------------------------------------------------------------------------------------------------------
+using namespace emu;
+
+struct EmuStream { int dummy; };
+struct EmuEvent { std::chrono::steady_clock::time_point t; };
+
+#define EMU_STICKY() do { init_once(); if (g_err) return g_err; } while (0)
+
+cudaError_t cudaGetLastError() { init_once(); if (g_err) return g_err; const int e = g_last; g_last = 0; return e; }
+cudaError_t cudaPeekAtLastError() { init_once(); return g_err ? g_err : g_last; }
+const char* cudaGetErrorString(cudaError_t e) {
+    if (e == cudaSuccess) return "no error";
+    return g_errmsg.empty() ? "emu: error" : g_errmsg.c_str();
+}
+cudaError_t cudaGetDeviceCount(int* n) { init_once(); *n = getenv("SGM_EMU_NO_DEVICE") ? 0 : 1; return *n ? cudaSuccess : cudaErrorNoDevice; }
+cudaError_t cudaSetDevice(int d) { EMU_STICKY(); return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaDeviceSynchronize() { EMU_STICKY(); return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
+    EMU_STICKY();
+    if (a == cudaDevAttrMultiProcessorCount) *v = g_sms;
+    else if (a == cudaDevAttrMaxSharedMemoryPerBlockOptin) *v = 227 * 1024;
+    else return cudaErrorInvalidValue;
+    return cudaSuccess;
+}
+cudaError_t cudaMallocImpl(void** p, size_t bytes) {
+    EMU_STICKY();
+    if (bytes == 0) bytes = 16;
+    const size_t payload = (bytes + 15) & ~(size_t)15;
+    const size_t pages = (payload + PAGE - 1) / PAGE * PAGE;
+    const size_t total = pages + 2 * PAGE;
+    void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (m == MAP_FAILED) { g_last = cudaErrorMemoryAllocation; g_errmsg = "emu: out of memory"; *p = nullptr; return cudaErrorMemoryAllocation; }
+    mprotect(m, PAGE, PROT_NONE);
+    mprotect((char*)m + PAGE + pages, PAGE, PROT_NONE);
+    unsigned char* q = (unsigned char*)m + PAGE + pages - payload;   // the end of the payload touches the guard page
+    memset(q, 0xff, payload);                                         // uninitialised device memory is not zero
+    g_allocs[q] = Alloc{bytes, m, total};
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+    if (!p) return cudaSuccess;
+    auto it = g_allocs.find((const unsigned char*)p);
+    if (it == g_allocs.end()) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cudaFree of an unknown pointer"; return cudaErrorInvalidValue; }
+    munmap(it->second.map, it->second.map_bytes);
+    g_allocs.erase(it);
+    return cudaSuccess;
+}
+cudaError_t cudaHostAllocImpl(void** p, size_t bytes, unsigned) { EMU_STICKY(); *p = aligned_alloc(64, (bytes + 63) & ~(size_t)63); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+
+static cudaError_t checked_copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind k) {
+    EMU_STICKY();
+    if (bytes == 0) return cudaSuccess;
+    const unsigned char* b;
+    const bool dst_dev = (k == cudaMemcpyHostToDevice || k == cudaMemcpyDeviceToDevice), src_dev = (k == cudaMemcpyDeviceToHost || k == cudaMemcpyDeviceToDevice);
+    if (dst_dev) { const Alloc* a = find_alloc(dst, &b); if (!a || (unsigned char*)dst + bytes > b + a->bytes) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cudaMemcpy destination outside a device allocation"; return cudaErrorInvalidValue; } }
+    if (src_dev) { const Alloc* a = find_alloc(src, &b); if (!a || (const unsigned char*)src + bytes > b + a->bytes) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cudaMemcpy source outside a device allocation"; return cudaErrorInvalidValue; } }
+    memmove(dst, src, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind k) { return checked_copy(dst, src, bytes, k); }
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t) { return checked_copy(dst, src, bytes, k); }
+cudaError_t cudaMemset(void* dst, int v, size_t bytes) {
+    EMU_STICKY();
+    const unsigned char* b; const Alloc* a = find_alloc(dst, &b);
+    if (bytes && (!a || (unsigned char*)dst + bytes > b + a->bytes)) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cudaMemset outside a device allocation"; return cudaErrorInvalidValue; }
+    memset(dst, v, bytes); return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* dst, int v, size_t bytes, cudaStream_t) { return cudaMemset(dst, v, bytes); }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { EMU_STICKY(); *s = new EmuStream{0}; return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, 0); }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { EMU_STICKY(); return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { EMU_STICKY(); *e = new EmuEvent{std::chrono::steady_clock::now()}; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { EMU_STICKY(); e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { EMU_STICKY(); return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { EMU_STICKY(); *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
+cudaError_t cudaFuncSetAttributeImpl(const void* fn, cudaFuncAttribute a, int v) {
+    EMU_STICKY();
+    if (a != cudaFuncAttributeMaxDynamicSharedMemorySize) return cudaErrorInvalidValue;
+    if (v < 0 || v > 227 * 1024) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cudaFuncSetAttribute: more than 227 KB of dynamic shared memory (" + std::to_string(v) + ")"; return cudaErrorInvalidValue; }
+    g_dyn_limit[fn] = v > 48 * 1024 ? v : 48 * 1024;
+    return cudaSuccess;
+}
+cudaError_t cudaOccupancyImpl(int* n, const void*, int threads, size_t smem) {
+    EMU_STICKY();
+    int by_smem = (int)((228 * 1024) / (smem + 1024)), by_thr = 2048 / (threads > 0 ? threads : 1);
+    int v = by_smem < by_thr ? by_smem : by_thr;
+    *n = v > 32 ? 32 : v;
+    return cudaSuccess;
+}
+cudaError_t cudaGetDriverEntryPoint(const char* sym, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
+    EMU_STICKY();
+    if (!strcmp(sym, "cuTensorMapEncodeTiled")) { *fn = (void*)&emu::encode_tiled; if (q) *q = cudaDriverEntryPointSuccess; return cudaSuccess; }
+    *fn = nullptr; if (q) *q = cudaDriverEntryPointSymbolNotFound; return cudaErrorInvalidValue;
+}
+// in-process stand-in for CUDA IPC: the handle carries the pointer (lets one process play several ranks in tests)
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { EMU_STICKY(); memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { EMU_STICKY(); memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+// test hook: clear the sticky error (a new "context")
+extern "C" void emu_reset_error() { g_err = 0; g_last = 0; g_errmsg.clear(); }
+extern "C" const char* emu_last_message() { return g_errmsg.c_str(); }
+extern "C" int emu_async_is_lazy() { init_once(); return g_lazy ? 1 : 0; }
+
+// --------------------------------------------------------------------------------------------------------------------------------
+// asynchronous engines
+// --------------------------------------------------------------------------------------------------------------------------------
+namespace emu {
+
+// ---- cp.async
+void cp_async16(uint32_t dst, const void* src) {
+    check_global(src, 16, 16, "cp.async");
+    (void)smem_ptr(dst, 16, 16);
+    Fiber& f = g_cta->fibers[g_cta->cur];
+    if (g_lazy) f.cp_open.push_back(CpAsyncOp{dst, src});
+    else std::memcpy(smem_ptr(dst, 16, 16), src, 16);
+}
+void cp_async_commit() {
+    Fiber& f = g_cta->fibers[g_cta->cur];
+    f.cp_groups.push_back(std::move(f.cp_open));
+    f.cp_open.clear();
+}
+void cp_async_wait_group(int allowed) {
+    Fiber& f = g_cta->fibers[g_cta->cur];
+    while ((int)f.cp_groups.size() > allowed) {
+        for (auto& op : f.cp_groups.front()) std::memcpy(smem_ptr(op.dst, 16, 16), op.src, 16);
+        f.cp_groups.erase(f.cp_groups.begin());
+    }
+}
+
+// ---- mbarrier
+static Mbar& mbar_at(uint32_t bar, bool must_be_inited = true) {
+    (void)smem_ptr(bar, 8, 8);
+    Mbar& m = g_cta->mbars[bar];
+    if (must_be_inited && !m.inited) fault("mbarrier at 0x%x used before mbarrier.init", bar);
+    return m;
+}
+static void mbar_check(Mbar& m) {
+    if (m.pending == 0 && m.tx == 0) { m.phase ^= 1u; m.pending = m.count; progress(); }
+}
+void mbar_init(uint32_t bar, uint32_t count) {
+    Mbar& m = mbar_at(bar, false);
+    if (count == 0) fault("mbarrier.init with count 0");
+    m = Mbar();
+    m.inited = true; m.count = count; m.pending = count;
+    progress();
+}
+static void mbar_arrive_n(Mbar& m, uint32_t bar) {
+    if (m.pending == 0) fault("mbarrier at 0x%x: more arrivals than its count (%u) in one phase", bar, m.count);
+    --m.pending; progress();
+    mbar_check(m);
+}
+void mbar_arrive(uint32_t bar) { mbar_arrive_n(mbar_at(bar), bar); }
+void mbar_expect_tx(uint32_t bar, uint32_t bytes) { Mbar& m = mbar_at(bar); m.tx += bytes; progress(); mbar_check(m); }
+void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) { Mbar& m = mbar_at(bar); m.tx += bytes; mbar_arrive_n(m, bar); }
+
+static void mma_drain(size_t upto);
+// everything that may complete lazily on this barrier does so now (a thread is about to look at it)
+static void mbar_settle(Mbar& m, uint32_t bar) {
+    while (!m.copies.empty()) {
+        PendingCopy pc = std::move(m.copies.front());
+        m.copies.pop_front();
+        pc.run();
+        m.tx -= pc.bytes; progress();
+        mbar_check(m);
+    }
+    if (m.mma_commits > 0) {
+        Cta& c = *g_cta;
+        // the commits owed to this barrier, oldest first; each requires the MMA queue to be drained up to it
+        for (auto it = c.mma_commits.begin(); it != c.mma_commits.end();) {
+            if (it->bar != bar) { ++it; continue; }
+            mma_drain(it->upto);
+            it = c.mma_commits.erase(it);
+            --m.mma_commits;
+            mbar_arrive_n(m, bar);
+        }
+    }
+}
+bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    Mbar& m = mbar_at(bar);
+    if (m.phase != (parity & 1u)) return true;
+    mbar_settle(m, bar);
+    if (m.phase != (parity & 1u)) return true;
+    yield();
+    return g_cta->mbars[bar].phase != (parity & 1u);
+}
+void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        Mbar& m = mbar_at(bar);
+        if (m.phase != (parity & 1u)) return;
+        mbar_settle(m, bar);
+        if (m.phase != (parity & 1u)) return;
+        yield();
+    }
+}
+
+// ---- TMA
+static void tma_complete(uint32_t bar, uint32_t bytes, std::function<void()> run) {
+    Mbar& m = mbar_at(bar);
+    if (g_lazy) { m.copies.push_back(PendingCopy{std::move(run), bytes}); progress(); }
+    else { run(); m.tx -= bytes; progress(); mbar_check(m); }
+}
+void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    if (bytes == 0 || (bytes & 15u)) fault("cp.async.bulk: size %u is not a positive multiple of 16", bytes);
+    check_global(src, bytes, 16, "cp.async.bulk (global source)");
+    (void)smem_ptr(dst, bytes, 16);
+    tma_complete(bar, bytes, [=]() { std::memcpy(smem_ptr(dst, bytes, 16), src, bytes); });
+}
+void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    if (bytes == 0 || (bytes & 15u)) fault("cp.async.bulk (store): size %u is not a positive multiple of 16", bytes);
+    check_global(dst, bytes, 16, "cp.async.bulk (global destination)");
+    std::memcpy(dst, smem_ptr(src, bytes, 16), bytes);   // stores read shared memory at issue in both modes (the source must stay intact until wait_group.read)
+    ++g_cta->fibers[g_cta->cur].bulk_store_groups;
+}
+void bulk_commit_group() {}
+void bulk_wait_group(int, bool) {}
+
+static const TensorMapRec* map_rec(const CUtensorMap* map) {
+    const TensorMapRec* r = reinterpret_cast<const TensorMapRec*>(map->opaque);
+    if (r->magic != 0x544d4150454d5531ull) fault("TMA with a CUtensorMap that was not produced by cuTensorMapEncodeTiled");
+    return r;
+}
+static inline uint32_t swz(uint32_t addr, uint32_t mode) {
+    switch (mode) {
+        case CU_TENSOR_MAP_SWIZZLE_128B: return addr ^ (((addr >> 7) & 7u) << 4);
+        case CU_TENSOR_MAP_SWIZZLE_64B: return addr ^ (((addr >> 7) & 3u) << 4);
+        case CU_TENSOR_MAP_SWIZZLE_32B: return addr ^ (((addr >> 7) & 1u) << 4);
+    }
+    return addr;
+}
+// copy one box row (inner dimension) element by element with zero fill outside the tensor
+static void tma_row(const TensorMapRec* r, uint32_t dst_row, const long long* c /* coordinates of the row start */, uint32_t inner) {
+    bool outer_ok = true;
+    size_t off = 0;
+    for (uint32_t k = 1; k < r->rank; ++k) {
+        if (c[k] < 0 || (unsigned long long)c[k] >= r->dim[k]) outer_ok = false;
+        else off += (size_t)c[k] * r->stride[k];
+    }
+    for (uint32_t i = 0; i < inner; ++i) {
+        const long long ci = c[0] + i;
+        uint32_t v = 0;
+        if (outer_ok && ci >= 0 && (unsigned long long)ci < r->dim[0]) std::memcpy(&v, r->base + off + (size_t)ci * r->elem_bytes, 4);
+        const uint32_t a = swz(dst_row + i * 4u, r->swizzle);
+        std::memcpy(smem_ptr(a, 4, 4), &v, 4);
+    }
+}
+static void tma_check_common(const TensorMapRec* r, uint32_t dst, int c0, uint32_t total_bytes) {
+    if (r->elem_bytes != 4) fault("emulated TMA handles 4-byte elements only");
+    if (((long long)c0 * r->elem_bytes) % 16 != 0) fault("TMA: innermost start coordinate %d is not 16-byte aligned (illegal instruction on the device)", c0);
+    const uint32_t need = r->swizzle == CU_TENSOR_MAP_SWIZZLE_NONE ? 128u : 128u;
+    (void)smem_ptr(dst, total_bytes, need);
+    if (r->swizzle == CU_TENSOR_MAP_SWIZZLE_128B && (dst & 1023u)) fault("TMA into a 128-byte-swizzled tile needs a 1024-byte aligned shared-memory destination (0x%x)", dst);
+}
+void tma_tile(uint32_t dst, const CUtensorMap* map, const int* coord, int ncoord, uint32_t bar) {
+    const TensorMapRec* r = map_rec(map);
+    if ((uint32_t)ncoord != r->rank) fault("TMA tile: %d coordinates for a rank-%u tensor map", ncoord, r->rank);
+    uint32_t bytes = r->elem_bytes;
+    for (uint32_t k = 0; k < r->rank; ++k) bytes *= r->box[k];
+    tma_check_common(r, dst, coord[0], bytes);
+    long long c0[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k < ncoord; ++k) c0[k] = coord[k];
+    const TensorMapRec rec = *r;
+    tma_complete(bar, bytes, [=]() {
+        const uint32_t inner = rec.box[0];
+        uint32_t rows = 1;
+        for (uint32_t k = 1; k < rec.rank; ++k) rows *= rec.box[k];
+        for (uint32_t row = 0; row < rows; ++row) {
+            long long c[5] = {c0[0], 0, 0, 0, 0};
+            uint32_t rem = row;
+            for (uint32_t k = 1; k < rec.rank; ++k) { c[k] = c0[k] + (rem % rec.box[k]); rem /= rec.box[k]; }
+            tma_row(&rec, dst + row * inner * 4u, c, inner);
+        }
+    });
+}
+void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
+    const TensorMapRec* r = map_rec(map);
+    if (r->rank != 2) fault("TMA tile::gather4 needs a rank-2 tensor map");
+    if (r->box[1] != 1) fault("TMA tile::gather4 needs a box of one row (box[1] = %u)", r->box[1]);
+    const uint32_t inner = r->box[0], bytes = 4u * inner * 4u;
+    tma_check_common(r, dst, col, bytes);
+    const TensorMapRec rec = *r;
+    const int rows[4] = {r0, r1, r2, r3};
+    tma_complete(bar, bytes, [=]() {
+        for (int k = 0; k < 4; ++k) {
+            const long long c[5] = {col, rows[k], 0, 0, 0};
+            tma_row(&rec, dst + (uint32_t)k * inner * 4u, c, inner);
+        }
+    });
+}
+
+CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim, const cuuint64_t* gstride,
+                      const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il, CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+    init_once();
+    auto bad = [&](const char* why) { g_errmsg = std::string("emu: cuTensorMapEncodeTiled: ") + why; if (g_verbose) fprintf(stderr, "%s\n", g_errmsg.c_str()); return CUDA_ERROR_INVALID_VALUE; };
+    if (!map || rank < 1 || rank > 5) return bad("rank must be 1..5");
+    if (dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT32 && dt != CU_TENSOR_MAP_DATA_TYPE_TFLOAT32) return bad("only float32 is modelled");
+    if (il != CU_TENSOR_MAP_INTERLEAVE_NONE) return bad("interleave is not modelled");
+    if (((uintptr_t)base & 15u) != 0) return bad("globalAddress must be 16-byte aligned");
+    const unsigned char* ab = nullptr;
+    const Alloc* al = find_alloc(base, &ab);
+    if (!al) return bad("globalAddress is not a device allocation");
+    TensorMapRec r;
+    memset(&r, 0, sizeof r);
+    r.magic = 0x544d4150454d5531ull; r.base = (const unsigned char*)base; r.rank = rank; r.elem_bytes = 4; r.swizzle = (uint32_t)sw;
+    size_t extent = 0;
+    for (uint32_t k = 0; k < rank; ++k) {
+        if (gdim[k] == 0 || gdim[k] > (1ull << 32)) return bad("globalDim must be in [1, 2^32]");
+        if (box[k] == 0 || box[k] > 256) return bad("boxDim must be in [1, 256]");
+        if (estr[k] == 0 || estr[k] > 8) return bad("elementStrides must be in [1, 8]");
+        if (estr[k] != 1) return bad("element strides other than 1 are not modelled");
+        r.dim[k] = gdim[k]; r.box[k] = box[k];
+        r.stride[k] = k == 0 ? 4 : gstride[k - 1];
+        if (k > 0) {
+            if (gstride[k - 1] % 16 != 0) return bad("globalStrides must be multiples of 16 bytes");
+            if (gstride[k - 1] >= (1ull << 40)) return bad("globalStrides must be below 2^40");
+        }
+        extent += (size_t)(gdim[k] - 1) * r.stride[k];
+    }
+    extent += 4;
+    if ((const unsigned char*)base + extent > ab + al->bytes) return bad("the tensor (globalDim x globalStrides) extends past the end of the device allocation");
+    const uint32_t inner_bytes = box[0] * 4u;
+    if (inner_bytes % 16 != 0) return bad("boxDim[0] x elementSize must be a multiple of 16 bytes");
+    if (sw == CU_TENSOR_MAP_SWIZZLE_128B && inner_bytes > 128) return bad("SWIZZLE_128B: inner box dimension must be <= 128 bytes");
+    if (sw == CU_TENSOR_MAP_SWIZZLE_64B && inner_bytes > 64) return bad("SWIZZLE_64B: inner box dimension must be <= 64 bytes");
+    if (sw == CU_TENSOR_MAP_SWIZZLE_32B && inner_bytes > 32) return bad("SWIZZLE_32B: inner box dimension must be <= 32 bytes");
+    if (sw == CU_TENSOR_MAP_SWIZZLE_128B && inner_bytes != 128) return bad("SWIZZLE_128B with an inner box narrower than 128 bytes is not modelled");
+    static_assert(sizeof(TensorMapRec) <= sizeof(CUtensorMap), "record fits the opaque descriptor");
+    memcpy(map->opaque, &r, sizeof r);
+    return CUDA_SUCCESS;
+}
+
+// ---- tcgen05
+static inline uint32_t& tmem_at(uint32_t lane, uint32_t col) {
+    Cta& c = *g_cta;
+    if (lane >= 128 || col >= 512) fault("TMEM access out of range: lane %u, column %u", lane, col);
+    if (col >= c.tmem_alloc_cols) fault("TMEM column %u was not allocated (%u columns allocated)", col, c.tmem_alloc_cols);
+    return c.tmem[(size_t)lane * 512 + col];
+}
+void tmem_alloc(uint32_t slot, uint32_t ncols) {
+    Cta& c = *g_cta;
+    (void)shfl(0xffffffffu, 0, 0);   // .sync.aligned: the whole warp executes it
+    if (lane_id() != 0) { (void)shfl(0xffffffffu, 0, 0); return; }
+    if (ncols < 32 || ncols > 512 || (ncols & (ncols - 1))) fault("tcgen05.alloc: %u columns (must be a power of two in [32, 512])", ncols);
+    if (!c.tmem_permit) fault("tcgen05.alloc after relinquish_alloc_permit");
+    if (c.tmem_alloc_cols) fault("tcgen05.alloc twice (the emulation models one allocation per CTA)");
+    c.tmem.assign(128 * 512, 0x7fc00000u);   // NaN: uninitialised accumulators are visible
+    c.tmem_alloc_cols = ncols;
+    const uint32_t base = 0;
+    std::memcpy(smem_ptr(slot, 4, 4), &base, 4);
+    progress();
+    (void)shfl(0xffffffffu, 0, 0);
+}
+void tmem_relinquish() { g_cta->tmem_permit = false; }
+void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    Cta& c = *g_cta;
+    (void)shfl(0xffffffffu, 0, 0);
+    if (lane_id() != 0) return;
+    if (taddr != 0 || ncols != c.tmem_alloc_cols) fault("tcgen05.dealloc(%u, %u) does not match the allocation (0, %u)", taddr, ncols, c.tmem_alloc_cols);
+    if (c.mma_done != c.mma_issued && !c.mma_queue.empty()) {
+        // MMAs still in flight at dealloc: nobody ever observed their completion
+        fault("tcgen05.dealloc with %zu tcgen05.mma still uncommitted / unobserved", c.mma_queue.size());
+    }
+    c.tmem_alloc_cols = 0;
+}
+
+// shared-memory matrix descriptor (sm_100): start address [0,14), LBO [16,30), SBO [32,46), version [46,48), layout type [61,64)
+struct SmemDesc { uint32_t start, lbo, sbo, layout; };
+static SmemDesc decode_desc(uint64_t d) {
+    SmemDesc s;
+    s.start = (uint32_t)(d & 0x3FFF) << 4; s.lbo = (uint32_t)((d >> 16) & 0x3FFF) << 4; s.sbo = (uint32_t)((d >> 32) & 0x3FFF) << 4;
+    s.layout = (uint32_t)(d >> 61) & 7u;
+    if (((d >> 46) & 3u) != 1u) fault("UMMA shared-memory descriptor: version field must be 1 on sm_100 (got %u)", (unsigned)((d >> 46) & 3u));
+    return s;
+}
+static inline float tf32_in(uint32_t bits) { return __uint_as_float(bits & 0xFFFFE000u); }   // the tensor core reads 19 bits
+// element (row, k) of a K-major operand tile, k in [0, 8): rows are 128-byte lines, 8-row groups SBO apart, 128-byte swizzle on address bits
+static inline float desc_elem(const SmemDesc& s, uint32_t row, uint32_t k) {
+    if (s.layout != 2u && s.layout != 0u) fault("UMMA descriptor layout type %u is not modelled (2 = SWIZZLE_128B, 0 = none)", s.layout);
+    uint32_t addr;
+    if (s.layout == 2u) {
+        addr = s.start + (row >> 3) * s.sbo + (row & 7u) * 128u + k * 4u;
+        addr = swz(addr, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+        // no swizzle, K-major: 8 x 16-byte core matrices; LBO between core matrices along K, SBO between 8-row groups
+        addr = s.start + (row >> 3) * s.sbo + (k >> 2) * s.lbo + (row & 7u) * 16u + (k & 3u) * 4u;
+    }
+    uint32_t v;
+    std::memcpy(&v, smem_ptr(addr, 4, 4), 4);
+    return tf32_in(v);
+}
+struct IDesc { uint32_t M, N; };
+static IDesc decode_idesc(uint32_t id) {
+    if (((id >> 4) & 3u) != 1u) fault("UMMA instruction descriptor: D format must be F32");
+    if (((id >> 7) & 7u) != 2u || ((id >> 10) & 7u) != 2u) fault("UMMA instruction descriptor: A/B format must be TF32 for kind::tf32");
+    if ((id >> 15) & 1u) fault("UMMA instruction descriptor: MN-major A is not modelled");
+    if ((id >> 16) & 1u) fault("UMMA instruction descriptor: MN-major B is not modelled");
+    IDesc r; r.N = ((id >> 17) & 0x3Fu) << 3; r.M = ((id >> 24) & 0x1Fu) << 4;
+    if (r.M != 128) fault("UMMA: M = %u (the emulation models M = 128, cta_group::1)", r.M);
+    if (r.N < 16 || r.N > 256 || (r.N % 16)) fault("UMMA: N = %u is not a multiple of 16 in [16, 256]", r.N);
+    return r;
+}
+static void mma_issue(std::function<void()> run) {
+    Cta& c = *g_cta;
+    ++c.mma_issued;
+    if (g_lazy) c.mma_queue.push_back(MmaOp{std::move(run)});
+    else { run(); ++c.mma_done; }
+    progress();
+}
+static void mma_drain(size_t upto) {
+    Cta& c = *g_cta;
+    while (c.mma_done < upto && !c.mma_queue.empty()) { c.mma_queue.front().run(); c.mma_queue.pop_front(); ++c.mma_done; }
+}
+static void mma_body(uint32_t tmem_d, bool a_tmem, uint32_t tmem_a, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc) {
+    const IDesc id = decode_idesc(idesc);
+    const SmemDesc sb = decode_desc(bdesc);
+    SmemDesc sa{};
+    if (!a_tmem) sa = decode_desc(adesc);
+    const uint32_t dl = tmem_d >> 16, dc = tmem_d & 0xFFFFu;
+    if (dl != 0) fault("UMMA: accumulator address must be at TMEM lane 0 for M = 128 (got lane %u)", dl);
+    float bt[256][8];
+    for (uint32_t n = 0; n < id.N; ++n) for (uint32_t k = 0; k < 8; ++k) bt[n][k] = desc_elem(sb, n, k);
+    for (uint32_t m = 0; m < 128; ++m) {
+        float a[8];
+        for (uint32_t k = 0; k < 8; ++k) a[k] = a_tmem ? tf32_in(tmem_at(m + (tmem_a >> 16), (tmem_a & 0xFFFFu) + k)) : desc_elem(sa, m, k);
+        for (uint32_t n = 0; n < id.N; ++n) {
+            float s = 0.f;
+            for (uint32_t k = 0; k < 8; ++k) s += a[k] * bt[n][k];
+            uint32_t& d = tmem_at(m, dc + n);
+            const float r = acc ? __uint_as_float(d) + s : s;
+            d = __float_as_uint(r);
+        }
+    }
+}
+void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    (void)decode_idesc(idesc); (void)decode_desc(adesc); (void)decode_desc(bdesc);   // malformed descriptors fault at issue
+    mma_issue([=]() { mma_body(tmem_d, false, 0, adesc, bdesc, idesc, accumulate); });
+}
+void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    (void)decode_idesc(idesc); (void)decode_desc(bdesc);
+    mma_issue([=]() { mma_body(tmem_d, true, tmem_a, 0, bdesc, idesc, accumulate); });
+}
+void umma_commit(uint32_t bar) {
+    Cta& c = *g_cta;
+    Mbar& m = mbar_at(bar);
+    if (g_lazy) { c.mma_commits.push_back(MmaCommit{c.mma_issued, bar}); ++m.mma_commits; progress(); }
+    else mbar_arrive_n(m, bar);
+}
+static uint32_t tmem_lane_of_thread(uint32_t taddr) {
+    const uint32_t lane_field = taddr >> 16;
+    const uint32_t quarter = 32u * ((uint32_t)warp_id() & 3u);
+    if (lane_field != quarter) fault("tcgen05.ld/st .32x32b: warp %d may only touch TMEM lanes %u..%u (address names lane %u)", warp_id(), quarter, quarter + 31, lane_field);
+    return quarter + (uint32_t)lane_id();
+}
+void tmem_ld_32x32b(uint32_t taddr, uint32_t* regs, int n) {
+    const uint32_t lane = tmem_lane_of_thread(taddr), col = taddr & 0xFFFFu;
+    for (int j = 0; j < n; ++j) regs[j] = tmem_at(lane, col + j);
+}
+void tmem_st_32x32b(uint32_t taddr, const uint32_t* regs, int n) {
+    const uint32_t lane = tmem_lane_of_thread(taddr), col = taddr & 0xFFFFu;
+    for (int j = 0; j < n; ++j) tmem_at(lane, col + j) = regs[j];
+}
+
+}  // namespace emu
