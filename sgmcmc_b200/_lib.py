@@ -9,8 +9,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-# SGM_LIB: developer override (A/B builds of the same library); the default is the in-tree build
-LIB_PATH = os.environ.get("SGM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsgmcmc_b200.so")
+# the one library the product loads: the in-tree nvcc build (no environment override, no fallback)
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsgmcmc_b200.so")
 
 SGM_ABI_VERSION = 1
 SGM_OK, SGM_EINVAL, SGM_ECUDA, SGM_ENOMODEL, SGM_EDIVERGED, SGM_ENOMEM, SGM_ESTATE, SGM_ECOMM = 0, -1, -2, -3, -4, -5, -6, -7

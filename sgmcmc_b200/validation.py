@@ -116,3 +116,8 @@ def benchFullGradient(sgmcmc: Sgmcmc, reps: int = 20):
     ms, b = C.c_float(), C.c_int64()
     _lib.check(_lib.load().sgm_bench_full_gradient(sgmcmc.handle, reps, C.byref(ms), C.byref(b)))
     return ms.value, b.value
+
+
+def setOption(sgmcmc: Sgmcmc, key: str, value: int):
+    """Pins a kernel path of this sampler (include/sgmcmc_b200.h: sgm_set_option); 0 restores the default dispatch."""
+    _lib.check(_lib.load().sgm_set_option(sgmcmc.handle, key.encode(), int(value)))

@@ -36,15 +36,18 @@ def make_case(name: str, seed: int = 13):
         return dict(om=OM.Mixture2(2, 10.0), loglik=S.mixture2LogLik(), logprior=S.normalPrior(10.0),
                     data={"X": X}, params={"theta1": np.array([0.0, 0.0]), "theta2": np.array([0.1, 0.1])},
                     N=N, n=100, eps=2e-5, opt_eps=1e-5)
-    if name.startswith("logistic"):  # vignettes/logisticRegression.Rmd
-        d = int(name[len("logistic"):])
-        N = 4000
+    if name.startswith("logistic"):  # vignettes/logisticRegression.Rmd; "logistic<d>[_n<minibatch>][_N<rows>]"
+        import re
+        m = re.fullmatch(r"logistic(\d+)(?:_n(\d+))?(?:_N(\d+))?", name)
+        d = int(m.group(1))
+        n = int(m.group(2)) if m.group(2) else 200
+        N = int(m.group(3)) if m.group(3) else 4000
         X = rs.randn(N, d)
         beta = rs.randn(d) * 0.5 / np.sqrt(d)
         y = (rs.rand(N) < 1 / (1 + np.exp(-(0.2 + X @ beta)))).astype(np.float64)
         return dict(om=OM.Logistic(d), loglik=S.logisticLogLik(), logprior=S.laplacePrior(),
                     data={"X": X, "y": y}, params={"bias": np.array(0.05), "beta": (rs.randn(d, 1) * 0.05)},
-                    N=N, n=200, eps=5e-6, opt_eps=5e-6)
+                    N=N, n=n, eps=5e-6, opt_eps=5e-6)
     if name == "softmaxnet_small":  # vignettes/nn.Rmd at reduced width
         N, din, dh, do = 600, 20, 8, 4
         X = rs.rand(N, din)

@@ -21,14 +21,15 @@ CSRC = os.path.join(ROOT, "sgmcmc_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libsgmcmc_emu.so")
 CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-DSGM_EMU=1", "-fno-strict-aliasing", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-variable",
-            "-Wno-unused-but-set-variable", "-Wno-sign-compare", "-Wno-unused-function", "-Wno-maybe-uninitialized", "-Wno-array-bounds",
+            "-Wno-unused-but-set-variable", "-Wno-sign-compare", "-Wno-unused-function", "-Wno-maybe-uninitialized", "-Wno-array-bounds", "-Wno-psabi",
             "-I", os.path.join(HERE, "include")]
 # (source, language flag): the .cu files are plain C++ once the emulation headers stand in for the CUDA ones
-UNITS = [(os.path.join(CSRC, "api.cu"), ["-x", "c++"]), (os.path.join(HERE, "softmax_stub.cpp"), []), (os.path.join(HERE, "emu.cpp"), [])]
+UNITS = [(os.path.join(CSRC, "api.cu"), ["-x", "c++"]), (os.path.join(HERE, "softmax_stub.cpp"), []), (os.path.join(HERE, "emu.cpp"), []),
+         (os.path.join(HERE, "selftest.cpp"), [])]
 
 
 def _deps():
-    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "sgmcmc_b200.h"), os.path.join(HERE, "emu.cpp")]
+    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "sgmcmc_b200.h"), os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "selftest.cpp"), os.path.join(HERE, "softmax_stub.cpp")]
     inc = os.path.join(HERE, "include")
     return d + [os.path.join(inc, f) for f in os.listdir(inc)]
 

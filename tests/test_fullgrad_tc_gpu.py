@@ -4,8 +4,6 @@ tcgen05 contractions) against the float64 oracle and against the SIMT row-chunk 
 Reference path: calcFullGrads (R/controlVariates.R:105-111) once per independent chain.  Tolerance: 1e-5 relative to the
 per-datum gradient mass (the total is near zero at a mode), the same scale tests/test_parity_gpu.py uses for g_hat.
 """
-import os
-
 import numpy as np
 import pytest
 
@@ -15,20 +13,18 @@ from tests.cases import device_setup, make_case
 pytestmark = pytest.mark.gpu
 
 
+FULLGRAD_OPTION = {"tc": 1, "generic": 2}   # sgm_set_option(h, "fullgrad", ...)
+
+
 def _mode_and_grad(case, chains, path, n_opt=30):
     from sgmcmc_b200 import validation as V
     import sgmcmc_b200 as S
-    old = os.environ.get("SGM_FULLGRAD")
-    os.environ["SGM_FULLGRAD"] = path
-    try:
-        dev = device_setup(case, "sgld", True, n_chains=chains, n_iters_opt=n_opt)
-        S.initSess(dev, verbose=False)
-        return V.getMode(dev)
-    finally:
-        if old is None:
-            os.environ.pop("SGM_FULLGRAD", None)
-        else:
-            os.environ["SGM_FULLGRAD"] = old
+    dev = device_setup(case, "sgld", True, n_chains=chains, n_iters_opt=n_opt)
+    V.setOption(dev, "fullgrad", FULLGRAD_OPTION[path])
+    S.initSess(dev, verbose=False)
+    if path == "tc":
+        assert V.lastFullGradFlops(dev) > 0, "the tensor-core path did not run"
+    return V.getMode(dev)
 
 
 @pytest.mark.parametrize("case_name,chains", [("logistic54", 20), ("logistic54", 150), ("logistic130", 40), ("logistic5", 16)])
@@ -69,3 +65,25 @@ def test_many_mode_full_gradient_row_tail_and_blocks(lib):
         gl = OS.flat(case["om"].grad_loglik(th, case["data"], np.float64))
         scale = max(np.abs(ref).max(), np.abs(gl).max(), 1.0) * 10
         assert np.abs(g_tc[c] - ref).max() <= 1e-5 * scale + 1e-7
+
+
+@pytest.mark.parametrize("case_name,chains", [("logistic1024_n200_N4099", 256)])
+def test_many_mode_full_gradient_at_the_benchmarked_width(lib, case_name, chains):
+    """d = 1024 (the c5 shape bench.py times): pass 1 walks 32 K stages = 4 TMEM segments per item (buffer alternation, register
+    accumulation across segments), 2 mode tiles, a row tail (4099 = 32 x 128 + 3) and 8 feature tiles in pass 2."""
+    many_mode_check(make_case(case_name), chains, n_opt=4)
+
+
+def many_mode_check(case, chains, n_opt=4):
+    th_tc, g_tc = _mode_and_grad(case, chains, "tc", n_opt=n_opt)
+    post = OS.Posterior(case["om"], case["N"], case["n"], np.float64, use_prior=True)
+    worst = 0.0
+    for c in range(chains):
+        th = OS.unflat(th_tc[c], case["params"])
+        ref = OS.flat(post.full_grad(th, case["data"]))
+        gl = OS.flat(case["om"].grad_loglik(th, case["data"], np.float64))
+        scale = max(np.abs(ref).max(), np.abs(gl).max(), 1.0) * 10
+        err = np.abs(g_tc[c] - ref).max()
+        worst = max(worst, err / scale)
+        assert err <= 1e-5 * scale + 1e-7, f"chain {c}: tensor-core g_hat err {err:.3e} vs scale {scale:.3e}"
+    return worst

@@ -16,8 +16,10 @@ from tests.cases import ALGOS, device_setup, make_case, oracle_chain
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
+# logistic54_n500 and logistic1024_n1024_N3000 instantiate exactly the kernels bench.py times: logistic_staged_kernel<*, 2>
+# (c3: n = 500 -> two rows per lane) and logistic_chain_kernel<32, 9> + the long-row full-gradient stream (c5: d = 1024)
 CASES = ["gauss1d", "gauss2d", "gauss3d_fullcov", "gauss2d_flat", "mixture", "logistic5", "logistic54", "logistic130",
-         "softmaxnet_small", "softmaxnet"]
+         "logistic54_n500", "logistic1024_n1024_N3000", "softmaxnet_small", "softmaxnet"]
 
 
 def close(ours, ref, scale=None, rtol=RTOL, what=""):
@@ -62,6 +64,8 @@ def _deterministic_steps(case_name, algo, cv, shared):
     C, steps, n_opt = 3, 4, 25
     if case_name == "softmaxnet":  # full 784-100-10: keep the CPU oracle's share of the test short
         C, steps, n_opt = 2, 2, 3
+    if case_name.startswith("logistic1024"):
+        C, steps, n_opt = 2, 3, 6
     rs = np.random.RandomState(5)
     dev = device_setup(case, algo, cv, n_chains=C, n_iters_opt=n_opt, sharedMode=shared)
     chains32 = [oracle_chain(case, algo, cv, np.float32, graph=True) for _ in range(C)]
