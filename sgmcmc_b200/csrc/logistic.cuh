@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(512) logistic_chain_kernel(const ChainArgs a) 
     sm.grad = sm.mo + ldp; sm.red = sm.grad + ldp; sm.scratch = sm.red + (size_t)nw * ldp;
     sm.dots = sm.scratch + 32; sm.rhat = sm.dots + a.n; sm.ys = sm.rhat + a.n;
     const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
+    SGM_EMU_NOTE(a.n_shards > 1 ? "logistic_chain:sharded" : "logistic_chain");
 
     for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
         __syncthreads();

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = lds_u32(slot);
+    SGM_EMU_NOTE(a.epi == 0 ? "cvg:pass1" : "cvg:pass2");
 
     // every role walks the same item sequence; g = running stage counter, sg = running segment counter (barrier phases never reset)
     if (warp == 0) {

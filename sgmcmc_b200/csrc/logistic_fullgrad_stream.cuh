@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(FG_THREADS, 2) logistic_fullgrad_stream_kernel
     fence_mbar_init();
     __syncthreads();
 
+    SGM_EMU_NOTE(LONG ? "fullgrad_stream:long" : "fullgrad_stream:short");
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     auto issue = [&](int k) {   // thread 0: tile k of this CTA into stage k % FG_STAGES
         const int64_t t = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
         fence_mbar_init();
     }
     long long t_prev = clock64();
+    SGM_EMU_NOTE(a.gather_tma == 3 ? "logistic_staged:gather4" : (a.gather_tma == 0 ? "logistic_staged:cp.async" : "logistic_staged:bulk"));
 
     for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
         __syncthreads();

@@ -20,6 +20,14 @@
 #define SGM_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
 #endif
 
+#ifdef SGM_EMU
+#define SGM_NOINLINE __attribute__((noinline))
+#define SGM_EMU_NOTE(name) do { if (threadIdx.x == 0) ::emu::note(name); } while (0)   // "this path ran" counters for the emulated tests
+#else
+#define SGM_NOINLINE __noinline__
+#define SGM_EMU_NOTE(name) do { } while (0)
+#endif
+
 namespace sgm {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,6 +84,15 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 1-D bulk store shared::cta -> global, tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }   // sources may be reused
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }             // writes are complete
+// this CTA's generic-proxy accesses to GLOBAL memory <-> its async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // tile::gather4: FOUR rows of a 2-D tensor (box = cols x 1) per instruction, landing contiguously (SASS: UTMALDG.2D.GATHER4)
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -155,6 +172,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) { ::emu::mbar_arrive(b
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { ::emu::mbar_wait(bar, parity); }
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) { ::emu::bulk_g2s(dst, src, bytes, bar); }
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) { ::emu::bulk_s2g(dst, src, bytes); }
+__device__ __forceinline__ void bulk_commit_group() { ::emu::bulk_commit_group(); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() { ::emu::bulk_wait_group(N, true); }
+template <int N> __device__ __forceinline__ void bulk_wait_group() { ::emu::bulk_wait_group(N, false); }
+__device__ __forceinline__ void fence_proxy_async_global() {}
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
     ::emu::tma_gather4(dst, map, col, r0, r1, r2, r3, bar);
 }

@@ -31,8 +31,6 @@ namespace sgm {
 constexpr int NN_THREADS = 512;
 constexpr int NN_WARPS = NN_THREADS / 32;
 constexpr int NN_RB = 128;      // rows per block
-constexpr int NN_KC = 32;       // K chunk of S1
-constexpr int NN_JT = 64;       // j tile of S5
 constexpr int NN_MAXH = 128;    // hidden width limit (lanes x 4)
 constexpr int NN_MAXO = 16;     // output width limit
 
@@ -144,100 +142,9 @@ __device__ void nn_load_small(const NNDims& dm, const NNSmem& sm, const float* _
     __syncthreads();
 }
 
-// S1: H[r][k] = softmax_k( sum_j X[row_r][j] B[j][k] + b[k] ) for the nb rows listed in sm.rows.
-// K is walked in chunks of NN_KC through a double-buffered pair of shared tiles: the next chunk's X rows are
-// prefetched into registers and its B rows by cp.async while the current chunk is multiplied (one barrier per chunk).
-__device__ void nn_stage1(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb,
-                          const float* __restrict__ th) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ncg = dm.dh >> 2;           // column groups of 4
-    const bool live = lane < ncg;
-    const int XT = NN_KC * (NN_RB + 4), BT = NN_KC * dm.dh, TILE = XT + BT;   // per buffer: Xt [NN_KC][NN_RB + 4], Bt [NN_KC][dh]
-    const float* __restrict__ B = th + dm.offB;
-    const int xr = tid % NN_RB, xq = tid / NN_RB;      // this thread's X row and first float4 column (second: xq + 4)
-    const float* xrow = X + (size_t)sm.rows[xr < nb ? xr : 0] * ld;
-    float acc[8][4];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
-    float4 xv0, xv1;
-    auto fetch = [&](int j0, float* buf) {   // global -> registers (X) / cp.async -> shared (B)
-        const int kc = (dm.din - j0 < NN_KC) ? dm.din - j0 : NN_KC;
-        xv0 = (xr < nb && 4 * xq < kc) ? __ldg(reinterpret_cast<const float4*>(xrow + j0 + 4 * xq)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xv1 = (xr < nb && 4 * (xq + 4) < kc) ? __ldg(reinterpret_cast<const float4*>(xrow + j0 + 4 * (xq + 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float* Bt = buf + XT;
-        for (int t = tid; t < NN_KC * ncg; t += NN_THREADS) {
-            const int jj = t / ncg, cg = t % ncg;
-            if (jj < kc) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Bt + jj * dm.dh + 4 * cg);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(B + (size_t)(j0 + jj) * dm.dh + 4 * cg) : "memory");
-            } else {
-                *reinterpret_cast<float4*>(Bt + jj * dm.dh + 4 * cg) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto stash = [&](float* buf) {           // registers -> transposed shared X tile (lanes walk rows: conflict free)
-        float* Xt = buf;
-        Xt[(4 * xq + 0) * (NN_RB + 4) + xr] = xv0.x; Xt[(4 * xq + 1) * (NN_RB + 4) + xr] = xv0.y;
-        Xt[(4 * xq + 2) * (NN_RB + 4) + xr] = xv0.z; Xt[(4 * xq + 3) * (NN_RB + 4) + xr] = xv0.w;
-        Xt[(4 * xq + 16) * (NN_RB + 4) + xr] = xv1.x; Xt[(4 * xq + 17) * (NN_RB + 4) + xr] = xv1.y;
-        Xt[(4 * xq + 18) * (NN_RB + 4) + xr] = xv1.z; Xt[(4 * xq + 19) * (NN_RB + 4) + xr] = xv1.w;
-    };
-    __syncthreads();
-    fetch(0, sm.tile);
-    stash(sm.tile);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    int cur = 0;
-    for (int j0 = 0; j0 < dm.din; j0 += NN_KC, cur ^= 1) {
-        float* buf = sm.tile + cur * TILE;
-        float* nxt = sm.tile + (cur ^ 1) * TILE;
-        const bool more = j0 + NN_KC < dm.din;
-        if (more) fetch(j0 + NN_KC, nxt);
-        if (live) {
-            const float* Xt = buf;
-            const float* Bt = buf + XT;
-#pragma unroll 4
-            for (int jj = 0; jj < NN_KC; ++jj) {
-                const float4 bv = *reinterpret_cast<const float4*>(Bt + jj * dm.dh + 4 * lane);
-                const float4 x0 = *reinterpret_cast<const float4*>(Xt + jj * (NN_RB + 4) + 8 * warp);
-                const float4 x1 = *reinterpret_cast<const float4*>(Xt + jj * (NN_RB + 4) + 8 * warp + 4);
-                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    acc[r][0] = fmaf(xs[r], bv.x, acc[r][0]); acc[r][1] = fmaf(xs[r], bv.y, acc[r][1]);
-                    acc[r][2] = fmaf(xs[r], bv.z, acc[r][2]); acc[r][3] = fmaf(xs[r], bv.w, acc[r][3]);
-                }
-            }
-        }
-        if (more) { stash(nxt); asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-        __syncthreads();
-    }
-    // bias + row softmax: a row's dh entries live in the lanes of one warp
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) bb = *reinterpret_cast<const float4*>(sm.b + 4 * lane);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int row = 8 * warp + r;
-        float v0 = acc[r][0] + bb.x, v1 = acc[r][1] + bb.y, v2 = acc[r][2] + bb.z, v3 = acc[r][3] + bb.w;
-        float m = live ? fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) : -INFINITY;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-        if (live) { e0 = expf(v0 - m); e1 = expf(v1 - m); e2 = expf(v2 - m); e3 = expf(v3 - m); }
-        const float s = warp_sum(e0 + e1 + e2 + e3);
-        if (live && row < nb)
-            *reinterpret_cast<float4*>(sm.H + row * dm.dh + 4 * lane) = make_float4(e0 / s, e1 / s, e2 / s, e3 / s);
-    }
-    __syncthreads();
-}
-
-
 // ---------------------------------------------------------------------------------------------------------
 // tcgen05 helpers (5th-generation tensor cores: operands in shared memory, accumulator in tensor memory)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t nn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // Shared-memory operand descriptor, K-major, no swizzle: the operand is a grid of 8-row x 16-byte core matrices;
 // the 16-byte chunk (kg, row) lives at kg * lbo + row * 16, so LBO = distance between the two K chunks of one MMA,
 // SBO = distance between 8-row groups = 128 B.  (Bit layout: cute/arch/mma_sm100_desc.hpp, descriptor version 1.)
@@ -248,30 +155,10 @@ __device__ __forceinline__ uint64_t nn_umma_desc(uint32_t addr, uint32_t lbo_byt
 __device__ __forceinline__ uint32_t nn_umma_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void nn_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
-}
-// one lane of a fully converged warp (the MMA issuer): ptxas keeps warp-uniform operands in uniform registers around elect.sync
-__device__ __forceinline__ bool nn_elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void nn_umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void nn_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}"
-                 ::"r"(bar), "r"(parity) : "memory");
-}
 __device__ __forceinline__ void nn_tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tmem_ld16(taddr, r);
+    tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -290,25 +177,25 @@ __device__ __forceinline__ void nn_split4(const float4 x, float4& hi, float4& lo
 // kernel prologue / epilogue: TMEM allocation (all 512 columns: one CTA per SM), stage barriers
 __device__ void nn_tc_init(const NNSmem& sm, TcCtx& tc) {
     if ((threadIdx.x >> 5) == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(nn_smem_u32(sm.tc_slot)), "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        tmem_alloc<512>(smem_u32(sm.tc_slot));
+        tmem_relinquish();
     }
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(nn_smem_u32(sm.tc_bars)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(nn_smem_u32(sm.tc_bars + 1)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init(smem_u32(sm.tc_bars), 1);
+        mbar_init(smem_u32(sm.tc_bars + 1), 1);
+        fence_mbar_init();
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_fence_after();
     tc.tmem = *sm.tc_slot;
-    tc.bar[0] = nn_smem_u32(sm.tc_bars); tc.bar[1] = nn_smem_u32(sm.tc_bars + 1);
+    tc.bar[0] = smem_u32(sm.tc_bars); tc.bar[1] = smem_u32(sm.tc_bars + 1);
     tc.commits[0] = tc.commits[1] = 0;
 }
 __device__ void nn_tc_fini(const TcCtx& tc) {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "n"(512));
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc<512>(tc.tmem);
 }
 
 // S1 epilogue, shared by the register-staged and the TMA-fed pipelines: TMEM -> registers (K segments summed), + bias -> sm.H,
@@ -338,7 +225,7 @@ __device__ void nn_stage1_epilogue(const NNDims& dm, const NNSmem& sm, int nb, c
             }
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
     {
         const int ncg = dm.dh >> 2;
@@ -412,7 +299,7 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
     // shared-memory descriptors of stage 0 (stage 1 = + STAGE bytes in the address field, which counts 16-byte units)
     uint64_t d_ahi[TC_KC / 8], d_alo[TC_KC / 8], d_bhi[TC_KC / 8], d_blo[TC_KC / 8];
     {
-        const uint32_t a_hi = nn_smem_u32(sm.tile), a_lo = a_hi + A_FLOATS * 4, b_hi = a_hi + 2 * A_FLOATS * 4, b_lo = b_hi + B_FLOATS * 4;
+        const uint32_t a_hi = smem_u32(sm.tile), a_lo = a_hi + A_FLOATS * 4, b_hi = a_hi + 2 * A_FLOATS * 4, b_lo = b_hi + B_FLOATS * 4;
 #pragma unroll
         for (int k8 = 0; k8 < TC_KC / 8; ++k8) {
             d_ahi[k8] = nn_umma_desc(a_hi + (uint32_t)(2 * k8) * LBOA, LBOA); d_alo[k8] = nn_umma_desc(a_lo + (uint32_t)(2 * k8) * LBOA, LBOA);
@@ -424,7 +311,7 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
         const int buf = c & 1;
         float* stage = sm.tile + buf * STAGE;
         // the MMAs that read this buffer two chunks ago must have completed
-        if (tc.commits[buf] > 0) nn_mbar_wait(tc.bar[buf], (tc.commits[buf] - 1u) & 1u);
+        if (tc.commits[buf] > 0) mbar_wait(tc.bar[buf], (tc.commits[buf] - 1u) & 1u);
         {
             float4 hi, lo;
             const float4 xv = pr.x, bv0 = pr.b0, bv1 = pr.b1;
@@ -445,11 +332,11 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
             }
         }
         pr = fetch(c + 3);   // refill the SAME registers (no rotation moves: a move of an in-flight load result would stall on it)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        fence_proxy_async();
+        tc_fence_before();
         __syncthreads();
-        if (warp == 0 && nn_elect_one()) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == 0 && elect_one()) {
+            tc_fence_after();
             const int seg = c / seg_chunks;
             const uint32_t td = tc.tmem + (uint32_t)(seg * Npad);
             const bool fresh = (c % seg_chunks) == 0;
@@ -457,11 +344,11 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
             for (int k8 = 0; k8 < TC_KC / 8; ++k8) {
                 // descriptors were built once before the loop: only the buffer's base differs (added to the 14-bit address field)
                 const uint64_t bo = (uint64_t)(buf ? stage_step : 0u);
-                nn_umma_tf32(td, d_ahi[k8] + bo, d_bhi[k8] + bo, idesc, !(fresh && k8 == 0));
-                nn_umma_tf32(td, d_ahi[k8] + bo, d_blo[k8] + bo, idesc, true);
-                nn_umma_tf32(td, d_alo[k8] + bo, d_bhi[k8] + bo, idesc, true);
+                umma_tf32_ss(td, d_ahi[k8] + bo, d_bhi[k8] + bo, idesc, !(fresh && k8 == 0));
+                umma_tf32_ss(td, d_ahi[k8] + bo, d_blo[k8] + bo, idesc, true);
+                umma_tf32_ss(td, d_alo[k8] + bo, d_bhi[k8] + bo, idesc, true);
             }
-            nn_umma_commit(tc.bar[buf]);
+            umma_commit(tc.bar[buf]);
         }
         tc.commits[buf] += 1;
     };
@@ -474,8 +361,8 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
     // all MMAs complete in order: wait for the last commit of each buffer
 #pragma unroll
     for (int b2 = 0; b2 < 2; ++b2)
-        if (tc.commits[b2] > 0) nn_mbar_wait(tc.bar[b2], (tc.commits[b2] - 1u) & 1u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tc.commits[b2] > 0) mbar_wait(tc.bar[b2], (tc.commits[b2] - 1u) & 1u);
+    tc_fence_after();
     NN_TICK(9)    // S1: drain
     nn_stage1_epilogue(dm, sm, nb, tc, nseg, Npad);
 }
@@ -491,35 +378,11 @@ __device__ void nn_stage1_tc(const NNDims& dm, const NNSmem& sm, const float* __
 // The register-staged version of this loop paid one global-memory latency per chunk: ptxas drains every outstanding load at
 // fence.proxy.async (profiles/r01_c4_s1_scoreboard.txt).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void nn_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void nn_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void nn_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void nn_tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-                 : "memory");
-}
-__device__ __forceinline__ void nn_tma_box3(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
 // K-major operand descriptor, 128-byte swizzle: rows are 128 bytes, 8-row groups 1024 bytes apart (SBO); a K step of 8 TF32
 // advances the start address by 32 bytes inside the swizzle span
 __device__ __forceinline__ uint64_t nn_umma_desc_sw128(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ float4 nn_lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void nn_sts128(uint32_t addr, const float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
 // S1 operand ring (TMA path): raw stages (X 128 rows x 128 B | B round8(dh) rows x 128 B, 128-byte swizzle) and lo stages of the
 // same shape; the tensor core reads Npad = round16(dh) rows of B, i.e. up to 1 KB past a stage (garbage in, ignored columns out)
 constexpr int S1_KC = 32;       // floats per operand row per stage = one 128-byte swizzle span
@@ -537,17 +400,18 @@ __device__ void nn_stage1_tma(const NNDims& dm, const NNSmem& sm, const NNMaps& 
     const int nchunks = (dm.din + S1_KC - 1) / S1_KC;
     const int seg_chunks = (nchunks + TC_SEG - 1) / TC_SEG;
     const int nseg = (nchunks + seg_chunks - 1) / seg_chunks;
+    SGM_EMU_NOTE("nn_stage1_tma");
     const uint32_t raw0 = sm.ring, lo0 = sm.ring + S1_NRAW * STG;
     // barriers: full[S1_NRAW] | rawfree[S1_NRAW] | conv[S1_NLO] | lofree[S1_NLO] | done
-    const uint32_t bars = nn_smem_u32(sm.s1_bars);
+    const uint32_t bars = smem_u32(sm.s1_bars);
     const uint32_t b_full = bars, b_rawfree = bars + 8 * S1_NRAW, b_conv = bars + 16 * S1_NRAW, b_lofree = b_conv + 8 * S1_NLO, b_done = b_lofree + 8 * S1_NLO;
-    asm volatile("fence.proxy.async.global;" ::: "memory");   // this CTA's parameter updates (generic proxy) -> the TMA reads below
+    fence_proxy_async_global();   // this CTA's parameter updates (generic proxy) -> the TMA reads below
     __syncthreads();   // the previous users of H | dZ1 | tile are done
     if (tid == 0) {
-        for (int s = 0; s < S1_NRAW; ++s) { nn_mbar_init(b_full + 8 * s, 1); nn_mbar_init(b_rawfree + 8 * s, 1); }
-        for (int l = 0; l < S1_NLO; ++l) { nn_mbar_init(b_conv + 8 * l, S1_CONV_WARPS); nn_mbar_init(b_lofree + 8 * l, 1); }
-        nn_mbar_init(b_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < S1_NRAW; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_rawfree + 8 * s, 1); }
+        for (int l = 0; l < S1_NLO; ++l) { mbar_init(b_conv + 8 * l, S1_CONV_WARPS); mbar_init(b_lofree + 8 * l, 1); }
+        mbar_init(b_done, 1);
+        fence_mbar_init();
     }
     __syncthreads();
     if (warp == NN_WARPS - 2) {
@@ -556,25 +420,25 @@ __device__ void nn_stage1_tma(const NNDims& dm, const NNSmem& sm, const NNMaps& 
         const uint32_t tx = (uint32_t)ngroups * 512u + (uint32_t)dm.dh * 128u;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % S1_NRAW;
-            if (c >= S1_NRAW) nn_mbar_wait(b_rawfree + 8 * s, (uint32_t)((c / S1_NRAW) - 1) & 1u);
+            if (c >= S1_NRAW) mbar_wait(b_rawfree + 8 * s, (uint32_t)((c / S1_NRAW) - 1) & 1u);
             const uint32_t dst = raw0 + (uint32_t)s * STG, bar = b_full + 8 * s;
-            if (lane == 0) nn_mbar_expect_tx(bar, tx);
+            if (lane == 0) mbar_expect_tx(bar, tx);
             __syncwarp();
             for (int g = lane; g < ngroups; g += 32) {
                 const int r = 4 * g;
-                nn_tma_gather4(dst + (uint32_t)g * 512u, mp.x, c * S1_KC, sm.rows[r], sm.rows[r + 1 < nb ? r + 1 : 0], sm.rows[r + 2 < nb ? r + 2 : 0],
+                tma_gather4(dst + (uint32_t)g * 512u, mp.x, c * S1_KC, sm.rows[r], sm.rows[r + 1 < nb ? r + 1 : 0], sm.rows[r + 2 < nb ? r + 2 : 0],
                                sm.rows[r + 3 < nb ? r + 3 : 0], bar);
             }
-            if (lane == 31) nn_tma_box3(dst + XB, mp.b, c * S1_KC, 0, mp.bcoord, bar);
+            if (lane == 31) tma_box3(dst + XB, mp.b, c * S1_KC, 0, mp.bcoord, bar);
         }
     } else if (warp == NN_WARPS - 1) {
         // ---- MMA issuer
         const uint32_t idesc = nn_umma_idesc(NN_RB, Npad);
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % S1_NRAW, l = c % S1_NLO;
-            nn_mbar_wait(b_conv + 8 * l, (uint32_t)(c / S1_NLO) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (nn_elect_one()) {
+            mbar_wait(b_conv + 8 * l, (uint32_t)(c / S1_NLO) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t td = tc.tmem + (uint32_t)((c / seg_chunks) * Npad);
                 const bool fresh = (c % seg_chunks) == 0;
                 const uint64_t ahi = nn_umma_desc_sw128(raw0 + (uint32_t)s * STG), bhi = nn_umma_desc_sw128(raw0 + (uint32_t)s * STG + XB);
@@ -582,13 +446,13 @@ __device__ void nn_stage1_tma(const NNDims& dm, const NNSmem& sm, const NNMaps& 
 #pragma unroll
                 for (int k8 = 0; k8 < S1_KC / 8; ++k8) {
                     const uint64_t ko = (uint64_t)(2 * k8);   // 32 bytes per K step, in 16-byte units
-                    nn_umma_tf32(td, ahi + ko, bhi + ko, idesc, !(fresh && k8 == 0));
-                    nn_umma_tf32(td, ahi + ko, blo + ko, idesc, true);
-                    nn_umma_tf32(td, alo + ko, bhi + ko, idesc, true);
+                    umma_tf32_ss(td, ahi + ko, bhi + ko, idesc, !(fresh && k8 == 0));
+                    umma_tf32_ss(td, ahi + ko, blo + ko, idesc, true);
+                    umma_tf32_ss(td, alo + ko, bhi + ko, idesc, true);
                 }
-                nn_umma_commit(b_rawfree + 8 * s);
-                nn_umma_commit(b_lofree + 8 * l);
-                if (c == nchunks - 1) nn_umma_commit(b_done);
+                umma_commit(b_rawfree + 8 * s);
+                umma_commit(b_lofree + 8 * l);
+                if (c == nchunks - 1) umma_commit(b_done);
             }
             __syncwarp();
         }
@@ -600,24 +464,24 @@ __device__ void nn_stage1_tma(const NNDims& dm, const NNSmem& sm, const NNMaps& 
             const uint32_t raw = raw0 + (uint32_t)s * STG, lo = lo0 + (uint32_t)l * STG;
             const bool prof = nn_prof && tid == 0;   // sub-counters of the S1 slot: wait for the lo stage (MMA pace) / for the loads
             long long t0 = prof ? clock64() : 0;
-            if (c >= S1_NLO) nn_mbar_wait(b_lofree + 8 * l, (uint32_t)((c / S1_NLO) - 1) & 1u);
+            if (c >= S1_NLO) mbar_wait(b_lofree + 8 * l, (uint32_t)((c / S1_NLO) - 1) & 1u);
             if (prof) { const long long t1 = clock64(); atomicAdd(nn_prof + 9, (unsigned long long)(t1 - t0)); t0 = t1; }
-            nn_mbar_wait(b_full + 8 * s, (uint32_t)(c / S1_NRAW) & 1u);
+            mbar_wait(b_full + 8 * s, (uint32_t)(c / S1_NRAW) & 1u);
             if (prof) atomicAdd(nn_prof + 8, (unsigned long long)(clock64() - t0));
             for (int i = tid; i < nvec; i += 32 * S1_CONV_WARPS) {
-                const float4 x = nn_lds128(raw + 16u * (uint32_t)i);
+                const float4 x = lds128(raw + 16u * (uint32_t)i);
                 float4 hi, lw;
                 nn_split4(x, hi, lw);
-                nn_sts128(raw + 16u * (uint32_t)i, hi);
-                nn_sts128(lo + 16u * (uint32_t)i, lw);
+                sts128(raw + 16u * (uint32_t)i, hi);
+                sts128(lo + 16u * (uint32_t)i, lw);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) nn_mbar_arrive(b_conv + 8 * l);
+            if (lane == 0) mbar_arrive(b_conv + 8 * l);
         }
     }
-    nn_mbar_wait(b_done, 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mbar_wait(b_done, 0u);
+    tc_fence_after();
     nn_stage1_epilogue(dm, sm, nb, tc, nseg, Npad);
 }
 
@@ -738,68 +602,6 @@ __device__ void nn_stage4(const NNDims& dm, const NNSmem& sm, int nb, bool first
     __syncthreads();
 }
 
-// S5: GB[j][k] (+)= sum_r X[row_r][j] dZ1[r][k]; the X tiles (128 rows x 64 columns) are double-buffered by cp.async
-__device__ void nn_stage5(const NNDims& dm, const NNSmem& sm, const float* __restrict__ X, int ld, int nb, bool first,
-                          float* __restrict__ GB) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ncg = dm.dh >> 2;
-    const bool live = lane < ncg;
-    const int TILE = NN_RB * NN_JT;
-    auto fetch = [&](int j0, float* Xs) {
-        const int jt = (dm.din - j0 < NN_JT) ? dm.din - j0 : NN_JT;
-        for (int t = tid; t < NN_RB * (NN_JT / 4); t += NN_THREADS) {
-            const int r = t / (NN_JT / 4), q = t % (NN_JT / 4);
-            if (r < nb && 4 * q < jt) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Xs + r * NN_JT + 4 * q);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(X + (size_t)sm.rows[r] * ld + j0 + 4 * q) : "memory");
-            } else {
-                *reinterpret_cast<float4*>(Xs + r * NN_JT + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    __syncthreads();
-    fetch(0, sm.tile);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    int cur = 0;
-    for (int j0 = 0; j0 < dm.din; j0 += NN_JT, cur ^= 1) {
-        const float* Xs = sm.tile + cur * TILE;
-        const bool more = j0 + NN_JT < dm.din;
-        if (more) fetch(j0 + NN_JT, sm.tile + (cur ^ 1) * TILE);
-        float acc[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
-        if (live) {
-#pragma unroll 4
-            for (int r = 0; r < nb; ++r) {
-                const float4 xv = *reinterpret_cast<const float4*>(Xs + r * NN_JT + 4 * warp);
-                const float4 dz = *reinterpret_cast<const float4*>(sm.dZ1 + r * dm.dh + 4 * lane);
-                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    acc[a][0] = fmaf(xs[a], dz.x, acc[a][0]); acc[a][1] = fmaf(xs[a], dz.y, acc[a][1]);
-                    acc[a][2] = fmaf(xs[a], dz.z, acc[a][2]); acc[a][3] = fmaf(xs[a], dz.w, acc[a][3]);
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int j = j0 + 4 * warp + a;
-                if (j < dm.din) {
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {   // GB is stored like B: [hidden unit][input], R's column-major order
-                        float* dst = GB + (size_t)(4 * lane + c4) * dm.din + j;
-                        *dst = first ? acc[a][c4] : *dst + acc[a][c4];
-                    }
-                }
-            }
-        }
-        if (more) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-    }
-}
-
-
 constexpr int TC5_NT = 64;    // input columns (j) per S5 tile = MMA N
 constexpr int TC5_KH = 64;    // minibatch rows (K) per staging step
 
@@ -840,15 +642,15 @@ __device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __
     uint64_t e_ahi[TC5_KH / 8], e_alo[TC5_KH / 8], e_bhi[TC5_KH / 8], e_blo[TC5_KH / 8];
 #pragma unroll
     for (int k8 = 0; k8 < TC5_KH / 8; ++k8) {
-        e_ahi[k8] = nn_umma_desc(nn_smem_u32(Ahi) + (uint32_t)(2 * k8) * LBOA, LBOA); e_alo[k8] = nn_umma_desc(nn_smem_u32(Alo) + (uint32_t)(2 * k8) * LBOA, LBOA);
-        e_bhi[k8] = nn_umma_desc(nn_smem_u32(Bhi) + (uint32_t)(2 * k8) * LBOB, LBOB); e_blo[k8] = nn_umma_desc(nn_smem_u32(Blo) + (uint32_t)(2 * k8) * LBOB, LBOB);
+        e_ahi[k8] = nn_umma_desc(smem_u32(Ahi) + (uint32_t)(2 * k8) * LBOA, LBOA); e_alo[k8] = nn_umma_desc(smem_u32(Alo) + (uint32_t)(2 * k8) * LBOA, LBOA);
+        e_bhi[k8] = nn_umma_desc(smem_u32(Bhi) + (uint32_t)(2 * k8) * LBOB, LBOB); e_blo[k8] = nn_umma_desc(smem_u32(Blo) + (uint32_t)(2 * k8) * LBOB, LBOB);
     }
     for (int t0 = 0; t0 < ntiles; t0 += 8) {
         const int t1 = (t0 + 8 < ntiles) ? t0 + 8 : ntiles;
         for (int h = 0; h < halves; ++h) {
             prefetch(t0, h);
             // every MMA issued so far has completed before the A operand is overwritten
-            if (tc.commits[0] > 0) nn_mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
+            if (tc.commits[0] > 0) mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
             __syncthreads();
             for (int u = tid; u < NN_RB * KG; u += NN_THREADS) {   // A: (hidden unit n, chunk kg) <- dZ1[64h + 4kg .. +3][n]
                 const int n = u % NN_RB, kg = u / NN_RB;
@@ -864,31 +666,31 @@ __device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __
             }
             for (int t = t0; t < t1; ++t) {
                 // the MMAs of the previous tile read the B buffer
-                if (t > t0 && tc.commits[0] > 0) nn_mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
+                if (t > t0 && tc.commits[0] > 0) mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
                 scatter(xv0, sq0);
                 scatter(xv1, sq0 + 8);
                 if (t + 1 < t1) prefetch(t + 1, h);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                fence_proxy_async();
+                tc_fence_before();
                 __syncthreads();
-                if (warp == 0 && nn_elect_one()) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 0 && elect_one()) {
+                    tc_fence_after();
                     const uint32_t td = tc.tmem + (uint32_t)((t - t0) * TC5_NT);
 #pragma unroll
                     for (int k8 = 0; k8 < TC5_KH / 8; ++k8) {
-                        nn_umma_tf32(td, e_ahi[k8], e_bhi[k8], idesc, (h > 0) || (k8 > 0));
-                        nn_umma_tf32(td, e_ahi[k8], e_blo[k8], idesc, true);
-                        nn_umma_tf32(td, e_alo[k8], e_bhi[k8], idesc, true);
+                        umma_tf32_ss(td, e_ahi[k8], e_bhi[k8], idesc, (h > 0) || (k8 > 0));
+                        umma_tf32_ss(td, e_ahi[k8], e_blo[k8], idesc, true);
+                        umma_tf32_ss(td, e_alo[k8], e_bhi[k8], idesc, true);
                     }
-                    nn_umma_commit(tc.bar[0]);
+                    umma_commit(tc.bar[0]);
                 }
                 tc.commits[0] += 1;
             }
         }
         // ---- epilogue of the group: TMEM lane = hidden unit n, columns = inputs of the group's tiles; all 16 warps
         // (warp w reads lanes 32 (w % 4) .. +31, the tiles w / 4, w / 4 + 4 of the group)
-        nn_mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mbar_wait(tc.bar[0], (tc.commits[0] - 1u) & 1u);
+        tc_fence_after();
         {
             const int q = warp & 3, n = 32 * q + lane;
             const uint32_t tbase = tc.tmem + ((uint32_t)(32 * q) << 16);
@@ -912,7 +714,7 @@ __device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __
                 }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_fence_before();
         __syncthreads();
     }
 }
@@ -931,19 +733,6 @@ __device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __
 // TMEM: accumulators [0, 2 Npad), A hi [256, 384), A lo [384, 512).  Shared memory (inside the H | dZ1 | tile ring; dZ1 is read
 // before anything overwrites it): two raw X stages of 4 x Kp x 128 B at the start, dZ1^T hi / lo behind them.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void nn_umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
-}
-__device__ __forceinline__ void nn_tmem_st16(uint32_t taddr, const float (&v)[16]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-                 : "memory");
-}
-
 // the two raw stages must end behind dZ1 (H | dZ1 come first in the ring; dZ1 is read while the B operand is written behind the stages)
 __device__ __forceinline__ bool nn_s5_tmem_fits(const NNDims& dm, int nb, uint32_t ring_bytes) {
     const int Kp = (nb + 7) & ~7, Npad = (dm.dh + 15) & ~15;
@@ -951,7 +740,7 @@ __device__ __forceinline__ bool nn_s5_tmem_fits(const NNDims& dm, int nb, uint32
     return Kp <= 128 && Npad <= 112 && need <= (long)ring_bytes && stages >= 2L * NN_RB * dm.dh * 4;
 }
 
-__device__ __noinline__ void nn_stage5_tmem(const NNDims& dm, const NNSmem& sm, const CUtensorMap* xmap, int nb, bool first,
+__device__ SGM_NOINLINE void nn_stage5_tmem(const NNDims& dm, const NNSmem& sm, const CUtensorMap* xmap, int nb, bool first,
                                             float* __restrict__ GB, TcCtx& tc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = warp & 3, cg = warp >> 2;
@@ -960,7 +749,8 @@ __device__ __noinline__ void nn_stage5_tmem(const NNDims& dm, const NNSmem& sm, 
     const uint32_t x0 = sm.ring, bop = sm.ring + 2u * STG;            // raw X stages | dZ1^T hi | dZ1^T lo
     const uint32_t LBOB = (uint32_t)Npad * 16u, PLANE = (uint32_t)KG * LBOB;
     const int ntiles = (dm.din + 127) >> 7;
-    const uint32_t bars = nn_smem_u32(sm.s1_bars);
+    SGM_EMU_NOTE("nn_stage5_tmem");
+    const uint32_t bars = smem_u32(sm.s1_bars);
     const uint32_t b_full = bars, b_dfull = bars + 16;               // full[2] | dfull[2]
     const uint32_t idesc = nn_umma_idesc(NN_RB, Npad);
     // ---- B operand from dZ1 (shared, [r][dh]); rows >= nb and hidden units >= dh are zero
@@ -973,29 +763,29 @@ __device__ __noinline__ void nn_stage5_tmem(const NNDims& dm, const NNSmem& sm, 
             v.z = (r + 2 < nb) ? sm.dZ1[(r + 2) * dm.dh + n] : 0.f; v.w = (r + 3 < nb) ? sm.dZ1[(r + 3) * dm.dh + n] : 0.f;
         }
         nn_split4(v, hi, lo);
-        nn_sts128(bop + (uint32_t)(kg * Npad + n) * 16u, hi);
-        nn_sts128(bop + PLANE + (uint32_t)(kg * Npad + n) * 16u, lo);
+        sts128(bop + (uint32_t)(kg * Npad + n) * 16u, hi);
+        sts128(bop + PLANE + (uint32_t)(kg * Npad + n) * 16u, lo);
     }
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) nn_mbar_init(bars + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);
+        fence_mbar_init();
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // operand stores -> the tensor core
+    fence_proxy_async();      // operand stores -> the tensor core
     __syncthreads();                                                   // ... and dZ1 may now be overwritten by the X stages
     auto issue_tile = [&](int t) {   // warp 0: 4 blocks x Kp / 4 gather4 requests
         const uint32_t dst = x0 + (uint32_t)(t & 1) * STG, bar = b_full + 8 * (t & 1);
-        if (lane == 0) nn_mbar_expect_tx(bar, STG);
+        if (lane == 0) mbar_expect_tx(bar, STG);
         __syncwarp();
         for (int i = lane; i < 4 * KG; i += 32) {
             const int b = i / KG, g = i % KG, r = 4 * g;
-            nn_tma_gather4(dst + (uint32_t)b * BLK + (uint32_t)g * 512u, xmap, 128 * t + 32 * b, sm.rows[r < nb ? r : 0], sm.rows[r + 1 < nb ? r + 1 : 0],
+            tma_gather4(dst + (uint32_t)b * BLK + (uint32_t)g * 512u, xmap, 128 * t + 32 * b, sm.rows[r < nb ? r : 0], sm.rows[r + 1 < nb ? r + 1 : 0],
                            sm.rows[r + 2 < nb ? r + 2 : 0], sm.rows[r + 3 < nb ? r + 3 : 0], bar);
         }
     };
     if (warp == 0) { issue_tile(0); if (ntiles > 1) issue_tile(1); }
     auto epilogue = [&](int t) {     // TMEM lane = input j of tile t, columns = hidden units
-        nn_mbar_wait(b_dfull + 8 * (t & 1), (uint32_t)(t >> 1) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mbar_wait(b_dfull + 8 * (t & 1), (uint32_t)(t >> 1) & 1u);
+        tc_fence_after();
         const int j = 128 * t + 32 * q + lane;
         const uint32_t tb = tc.tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((t & 1) * Npad);
         for (int c0 = 32 * cg; c0 < 32 * cg + 32 && c0 < Npad; c0 += 16) {
@@ -1012,13 +802,13 @@ __device__ __noinline__ void nn_stage5_tmem(const NNDims& dm, const NNSmem& sm, 
                 }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_fence_before();
     };
     for (int t = 0; t < ntiles; ++t) {
         const uint32_t xs = x0 + (uint32_t)(t & 1) * STG + (uint32_t)q * BLK;
-        nn_mbar_wait(b_full + 8 * (t & 1), (uint32_t)(t >> 1) & 1u);
+        mbar_wait(b_full + 8 * (t & 1), (uint32_t)(t >> 1) & 1u);
         // the MMAs of tile t - 1 read the TMEM A buffer: they must be done before it is rewritten
-        if (t > 0) { nn_mbar_wait(b_dfull + 8 * ((t - 1) & 1), (uint32_t)((t - 1) >> 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        if (t > 0) { mbar_wait(b_dfull + 8 * ((t - 1) & 1), (uint32_t)((t - 1) >> 1) & 1u); tc_fence_after(); }
         // transpose: this thread's input column (lane) of block q, rows 32 cg .. 32 cg + 31 -> TMEM columns
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -1029,31 +819,31 @@ __device__ __noinline__ void nn_stage5_tmem(const NNDims& dm, const NNSmem& sm, 
                 for (int i = 0; i < 16; ++i) {
                     const int r = r0 + i;
                     float x = 0.f;
-                    if (r < Kp) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xs + (uint32_t)r * 128u + ((uint32_t)((lane >> 2) ^ (r & 7)) << 4) + ((uint32_t)(lane & 3) << 2)));
+                    if (r < Kp) x = lds32(xs + (uint32_t)r * 128u + ((uint32_t)((lane >> 2) ^ (r & 7)) << 4) + ((uint32_t)(lane & 3) << 2));
                     hi[i] = nn_tf32(x);
                     lo[i] = nn_tf32(x - hi[i]);
                 }
                 const uint32_t ta = tc.tmem + ((uint32_t)(32 * q) << 16) + 256u + (uint32_t)r0;
-                nn_tmem_st16(ta, hi);
-                nn_tmem_st16(ta + 128u, lo);
+                tmem_st16(ta, hi);
+                tmem_st16(ta + 128u, lo);
             }
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tmem_wait_st();
+        tc_fence_before();
         __syncthreads();
         if (warp == 0) {
             if (t + 2 < ntiles) issue_tile(t + 2);     // stage t & 1 is free: its tile lives in TMEM now
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (nn_elect_one()) {
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t td = tc.tmem + (uint32_t)((t & 1) * Npad);
                 for (int k8 = 0; k8 < (Kp >> 3); ++k8) {
                     const uint64_t bhi = nn_umma_desc(bop + (uint32_t)(2 * k8) * LBOB, LBOB), blo = nn_umma_desc(bop + PLANE + (uint32_t)(2 * k8) * LBOB, LBOB);
                     const uint32_t ahi = tc.tmem + 256u + 8u * (uint32_t)k8, alo = ahi + 128u;
-                    nn_umma_tf32_ts(td, ahi, bhi, idesc, k8 > 0);
-                    nn_umma_tf32_ts(td, ahi, blo, idesc, true);
-                    nn_umma_tf32_ts(td, alo, bhi, idesc, true);
+                    umma_tf32_ts(td, ahi, bhi, idesc, k8 > 0);
+                    umma_tf32_ts(td, ahi, blo, idesc, true);
+                    umma_tf32_ts(td, alo, bhi, idesc, true);
                 }
-                nn_umma_commit(b_dfull + 8 * (t & 1));
+                umma_commit(b_dfull + 8 * (t & 1));
             }
             __syncwarp();
         }
@@ -1198,12 +988,12 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
     const int ustages = (int)((sm.ring_bytes) / ustage) < 8 ? (int)(sm.ring_bytes / ustage) : 8;
     if (t < 4 && (lo & 3) == 0 && ((hi - lo) & 3) == 0 && (hi - lo) >= 8 * UCH && ustages >= 3 && nn_stream_updates) {
         const int count = hi - lo, nchunks = (count + UCH - 1) / UCH;
-        const uint32_t bars = nn_smem_u32(sm.s1_bars);
-        asm volatile("fence.proxy.async.global;" ::: "memory");   // this CTA's generic stores (gradient sums, state) -> the bulk reads
+        const uint32_t bars = smem_u32(sm.s1_bars);
+        fence_proxy_async_global();   // this CTA's generic stores (gradient sums, state) -> the bulk reads
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int s2 = 0; s2 < ustages; ++s2) nn_mbar_init(bars + 8 * s2, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int s2 = 0; s2 < ustages; ++s2) mbar_init(bars + 8 * s2, 1);
+            fence_mbar_init();
         }
         __syncthreads();
         const float* src[6] = {st.th + lo, st.mo + lo, st.G + lo, a.cv ? st.hat + lo : nullptr, a.cv ? st.ghat + lo : nullptr, a.cv ? st.Ghat + lo : nullptr};
@@ -1211,10 +1001,9 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
             const int s2 = k % ustages;
             const int n_el = (count - k * UCH < UCH) ? count - k * UCH : UCH;
             const uint32_t bytes = (uint32_t)n_el * 4u, bar = bars + 8 * s2, dst = sm.ring + (uint32_t)s2 * ustage;
-            nn_mbar_expect_tx(bar, bytes * (uint32_t)narr);
+            mbar_expect_tx(bar, bytes * (uint32_t)narr);
             for (int q = 0; q < narr; ++q)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst + (uint32_t)q * UCH * 4u), "l"(src[q] + (size_t)k * UCH), "r"(bytes), "r"(bar) : "memory");
+                bulk_g2s(dst + (uint32_t)q * UCH * 4u, src[q] + (size_t)k * UCH, bytes, bar);
         };
         if (threadIdx.x == 0) for (int k = 0; k < ustages - 1 && k < nchunks; ++k) issue(k);
         float ssq_new = 0.f;
@@ -1222,19 +1011,19 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
             const int s2 = k % ustages;
             const uint32_t stg = sm.ring + (uint32_t)s2 * ustage + 16u * threadIdx.x;
             const int e0 = lo + k * UCH + 4 * (int)threadIdx.x;
-            nn_mbar_wait(bars + 8 * s2, (uint32_t)(k / ustages) & 1u);
+            mbar_wait(bars + 8 * s2, (uint32_t)(k / ustages) & 1u);
             if (e0 < hi) {
                 float z4[4] = {0.f, 0.f, 0.f, 0.f};
                 if (noisy && !a.det) normal4_at((uint32_t)(e0 >> 2), a.chain0 + (uint32_t)c, word2_of(step, a.L, sub), TAG_NOISE, a.k0, a.k1, z4);
                 if (noisy && a.det)
                     for (int q = 0; q < 4; ++q)
                         z4[q] = a.noise[(size_t)c * a.noise_len + (a.algo == ALGO_SGHMC ? sub * a.P : 0) + nn_flat_of_internal(dm, e0 + q)];
-                const float4 tv = nn_lds128(stg), mv = nn_lds128(stg + UCH * 4u), gv = nn_lds128(stg + 2u * UCH * 4u);
+                const float4 tv = lds128(stg), mv = lds128(stg + UCH * 4u), gv = lds128(stg + 2u * UCH * 4u);
                 float th4[4] = {tv.x, tv.y, tv.z, tv.w}, mo4[4] = {mv.x, mv.y, mv.z, mv.w};
                 const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
                 float hat4[4] = {0.f, 0.f, 0.f, 0.f}, ghat4[4] = {0.f, 0.f, 0.f, 0.f}, gh4[4] = {0.f, 0.f, 0.f, 0.f};
                 if (a.cv) {
-                    const float4 hv = nn_lds128(stg + 3u * UCH * 4u), qv = nn_lds128(stg + 4u * UCH * 4u), pv = nn_lds128(stg + 5u * UCH * 4u);
+                    const float4 hv = lds128(stg + 3u * UCH * 4u), qv = lds128(stg + 4u * UCH * 4u), pv = lds128(stg + 5u * UCH * 4u);
                     hat4[0] = hv.x; hat4[1] = hv.y; hat4[2] = hv.z; hat4[3] = hv.w; ghat4[0] = qv.x; ghat4[1] = qv.y; ghat4[2] = qv.z; ghat4[3] = qv.w;
                     gh4[0] = pv.x; gh4[1] = pv.y; gh4[2] = pv.z; gh4[3] = pv.w;
                 }
@@ -1268,20 +1057,20 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
                     }
                     ssq_new += th4[q] * th4[q];
                 }
-                if (wr_th_) nn_sts128(stg, make_float4(th4[0], th4[1], th4[2], th4[3]));
-                if (wr_mo_) nn_sts128(stg + UCH * 4u, make_float4(mo4[0], mo4[1], mo4[2], mo4[3]));
+                if (wr_th_) sts128(stg, make_float4(th4[0], th4[1], th4[2], th4[3]));
+                if (wr_mo_) sts128(stg + UCH * 4u, make_float4(mo4[0], mo4[1], mo4[2], mo4[3]));
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> the bulk store's reads
+            fence_proxy_async();   // generic stores -> the bulk store's reads
             __syncthreads();
             if (threadIdx.x == 0) {
                 const int n_el = (count - k * UCH < UCH) ? count - k * UCH : UCH;
                 const uint32_t bytes = (uint32_t)n_el * 4u, srcs = sm.ring + (uint32_t)s2 * ustage;
-                if (wr_th_) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.th + lo + (size_t)k * UCH), "r"(srcs), "r"(bytes) : "memory");
-                if (wr_mo_) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.mo + lo + (size_t)k * UCH), "r"(srcs + UCH * 4u), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (wr_th_) bulk_s2g(st.th + lo + (size_t)k * UCH, srcs, bytes);
+                if (wr_mo_) bulk_s2g(st.mo + lo + (size_t)k * UCH, srcs + UCH * 4u, bytes);
+                bulk_commit_group();
                 // the stage of chunk k - 1 is free once ITS store has read shared memory: refill it with chunk k - 1 + ustages
                 if (k >= 1 && k - 1 + ustages < nchunks) {
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    bulk_wait_group_read<1>();
                     issue(k - 1 + ustages);
                 } else if (k == 0 && ustages - 1 < nchunks) {
                     issue(ustages - 1);   // the last stage was never used
@@ -1289,8 +1078,8 @@ __device__ void nn_update_tensor(const ChainArgs& a, const NNDims& dm, const NNS
             }
         }
         if (threadIdx.x == 0) {
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async.global;" ::: "memory");   // bulk stores (async proxy) -> later generic loads of the state
+            bulk_wait_group<0>();
+            fence_proxy_async_global();   // bulk stores (async proxy) -> later generic loads of the state
         }
         __syncthreads();
         if (wr_th_) {   // (SGNHT moves theta in a later pass: its ||W||^2 is not the one accumulated here)
@@ -1476,10 +1265,10 @@ __host__ __device__ inline int nn_tile_floats_all(const NNDims& dm) {
 
 __device__ void nn_carve(const NNDims& dm, float* base, NNSmem& sm) {
     // 1024-byte aligned start: the swizzled operand tiles need it (the launch reserves the slack)
-    const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(base);
+    const uint32_t b0 = smem_u32(base);
     float* p = base + (((1024u - (b0 & 1023u)) & 1023u) >> 2);
     const int t1 = nn_tile_floats_all(dm);
-    sm.ring = (uint32_t)__cvta_generic_to_shared(p);
+    sm.ring = smem_u32(p);
     sm.ring_bytes = (uint32_t)(2 * NN_RB * dm.dh + t1) * 4u;
     sm.H = p; p += NN_RB * dm.dh;
     sm.dZ1 = p; p += NN_RB * dm.dh;
@@ -1509,7 +1298,7 @@ static size_t nn_smem_bytes(const NNDims& dm) {
 __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const ChainArgs a, const NNDims dm, float* Gall, float* Ghatall,
                                                                           const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmTh,
                                                                           const __grid_constant__ CUtensorMap tmHat, int use_tma) {
-    extern __shared__ __align__(16) float smem_f[];
+    SGM_DYN_SMEM(float, smem_f, 16);
     NNSmem sm;
     nn_carve(dm, smem_f, sm);
     const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
@@ -1647,7 +1436,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
 __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_fullgrad_kernel(const ChainArgs a, const NNDims dm, int64_t row0, int64_t row1,
                                                                              int rows_per, const float* __restrict__ theta_hat, float* __restrict__ part,
                                                                              const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmHat, int use_tma) {
-    extern __shared__ __align__(16) float smem_f[];
+    SGM_DYN_SMEM(float, smem_f, 16);
     NNSmem sm;
     nn_carve(dm, smem_f, sm);
     const int m = blockIdx.y;
@@ -1697,7 +1486,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_logpost_kernel(cons
                                                                             const float* __restrict__ theta, float* Gscratch,
                                                                             double* __restrict__ out, const __grid_constant__ CUtensorMap tmX,
                                                                             const __grid_constant__ CUtensorMap tmTh, int use_tma) {
-    extern __shared__ __align__(16) float smem_f[];
+    SGM_DYN_SMEM(float, smem_f, 16);
     NNSmem sm;
     nn_carve(dm, smem_f, sm);
     const int c = blockIdx.x;
@@ -1850,8 +1639,8 @@ int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t strea
     const CUtensorMap* mt = mx ? nn_b_map(w, a.theta, a.C, a.Pst) : nullptr;
     const CUtensorMap* mh = (mx && a.cv) ? nn_b_map(w, a.theta_hat, a.hat_stride ? a.C : 1, a.hat_stride) : mt;
     const int use_tma = (mx && mt && mh) ? 1 : 0;
-    softmax_net_chain_kernel<<<grid, NN_THREADS, w->smem, stream>>>(a, w->dm, w->G, a.cv ? w->Ghat : nullptr, use_tma ? *mx : zero_map,
-                                                                   use_tma ? *mt : zero_map, use_tma ? *mh : zero_map, use_tma);
+    SGM_LAUNCH(softmax_net_chain_kernel, grid, NN_THREADS, w->smem, stream, a, w->dm, w->G, a.cv ? w->Ghat : nullptr, use_tma ? *mx : zero_map,
+               use_tma ? *mt : zero_map, use_tma ? *mh : zero_map, use_tma);
     *launches = 1;
     return (int)cudaGetLastError();
 }
@@ -1881,16 +1670,16 @@ int softmax_net_fullgrad(SoftmaxNetWork* w, const ChainArgs& a, int64_t row0, in
     const CUtensorMap* mx = nn_tma_enabled(w) ? nn_x_map(w, a.X, a.N, a.ld) : nullptr;
     const CUtensorMap* mh = mx ? nn_b_map(w, theta_hat, M, a.Pst) : nullptr;
     const int use_tma = (mx && mh) ? 1 : 0;
-    softmax_net_fullgrad_kernel<<<grid, NN_THREADS, w->smem, stream>>>(a, w->dm, row0, row1, (int)rows_per, theta_hat, w->part,
-                                                                      use_tma ? *mx : zero_map, use_tma ? *mh : zero_map, use_tma);
+    SGM_LAUNCH(softmax_net_fullgrad_kernel, grid, NN_THREADS, w->smem, stream, a, w->dm, row0, row1, (int)rows_per, theta_hat, w->part,
+               use_tma ? *mx : zero_map, use_tma ? *mh : zero_map, use_tma);
     const int total = M * a.Pst;
-    softmax_net_part_reduce<<<(total + 255) / 256, 256, 0, stream>>>(w->part, gx, a.Pst, gsum, total);
+    SGM_LAUNCH(softmax_net_part_reduce, (total + 255) / 256, 256, 0, stream, w->part, gx, a.Pst, gsum, total);
     return (int)cudaGetLastError();
 }
 
 int softmax_net_fullgrad_finish(SoftmaxNetWork* w, const ChainArgs& a, int M, const double* gsum, const float* theta_hat,
                                 float* g_hat, float* theta, cudaStream_t stream) {
-    softmax_net_finish_kernel<<<M, NN_THREADS, 0, stream>>>(a, w->dm, gsum, theta_hat, g_hat, theta);
+    SGM_LAUNCH(softmax_net_finish_kernel, M, NN_THREADS, 0, stream, a, w->dm, gsum, theta_hat, g_hat, theta);
     return (int)cudaGetLastError();
 }
 
@@ -1899,8 +1688,8 @@ int softmax_net_logpost(SoftmaxNetWork* w, const ChainArgs& a, uint32_t word2, c
     const CUtensorMap* mx = nn_tma_enabled(w) ? nn_x_map(w, a.X, a.N, a.ld) : nullptr;
     const CUtensorMap* mt = mx ? nn_b_map(w, theta, a.C, a.Pst) : nullptr;
     const int use_tma = (mx && mt) ? 1 : 0;
-    softmax_net_logpost_kernel<<<a.C, NN_THREADS, w->smem, stream>>>(a, w->dm, word2, theta, w->G, out, use_tma ? *mx : zero_map,
-                                                                    use_tma ? *mt : zero_map, use_tma);
+    SGM_LAUNCH(softmax_net_logpost_kernel, a.C, NN_THREADS, w->smem, stream, a, w->dm, word2, theta, w->G, out, use_tma ? *mx : zero_map,
+               use_tma ? *mt : zero_map, use_tma);
     return (int)cudaGetLastError();
 }
 

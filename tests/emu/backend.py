@@ -11,29 +11,31 @@ import sys
 
 from . import build as emu_build
 
-_emu = None
+_emu = {}
+
+# extra builds of the same sources: kernel generations that are compiled out of the product by default
+VARIANTS = {"": (), "s5tmem": ("-DNN_ENABLE_S5_TMEM",)}
 
 
-def library():
-    """The emulated library, typed like the real one (built on first use; a few seconds of g++)."""
-    global _emu
-    if _emu is None:
+def library(variant: str = ""):
+    """The emulated library, typed like the real one (built on first use; under a minute of g++)."""
+    if variant not in _emu:
         from sgmcmc_b200 import _lib
-        path = emu_build.build()
+        path = emu_build.build(variant=variant, defs=VARIANTS[variant])
         lib = C.CDLL(path, mode=C.RTLD_LOCAL)
         for name, (res, args) in _lib.SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
         lib.emu_last_message.restype = C.c_char_p
-        _emu = lib
-    return _emu
+        _emu[variant] = lib
+    return _emu[variant]
 
 
 @contextlib.contextmanager
-def emulated():
+def emulated(variant: str = ""):
     """`with emulated():` -- every C-ABI call made through sgmcmc_b200 goes to the emulated build."""
     from sgmcmc_b200 import _lib
-    lib = library()
+    lib = library(variant)
     lib.emu_reset_error()
     saved = _lib._lib
     _lib._lib = lib

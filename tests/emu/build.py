@@ -24,33 +24,40 @@ CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-DSGM_EMU=1", "-fno-strict-alia
             "-Wno-unused-but-set-variable", "-Wno-sign-compare", "-Wno-unused-function", "-Wno-maybe-uninitialized", "-Wno-array-bounds", "-Wno-psabi",
             "-I", os.path.join(HERE, "include")]
 # (source, language flag): the .cu files are plain C++ once the emulation headers stand in for the CUDA ones
-UNITS = [(os.path.join(CSRC, "api.cu"), ["-x", "c++"]), (os.path.join(HERE, "softmax_stub.cpp"), []), (os.path.join(HERE, "emu.cpp"), []),
+UNITS = [(os.path.join(CSRC, "api.cu"), ["-x", "c++"]), (os.path.join(CSRC, "softmax_net.cu"), ["-x", "c++"]), (os.path.join(HERE, "emu.cpp"), []),
          (os.path.join(HERE, "selftest.cpp"), [])]
 
 
 def _deps():
-    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "sgmcmc_b200.h"), os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "selftest.cpp"), os.path.join(HERE, "softmax_stub.cpp")]
+    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "sgmcmc_b200.h"), os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "selftest.cpp")]
     inc = os.path.join(HERE, "include")
     return d + [os.path.join(inc, f) for f in os.listdir(inc)]
 
 
-def build(force: bool = False) -> str:
-    os.makedirs(OUT_DIR, exist_ok=True)
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(p) <= os.path.getmtime(LIB) for p in _deps()):
-        return LIB
+def lib_path(variant: str = "") -> str:
+    return os.path.join(OUT_DIR + ("_" + variant if variant else ""), "libsgmcmc_emu.so")
+
+
+def build(force: bool = False, variant: str = "", defs=()) -> str:
+    """variant / defs: a second build of the same sources with extra -D flags (e.g. the compiled-out kernel generations)."""
+    out_dir = os.path.dirname(lib_path(variant))
+    lib = lib_path(variant)
+    os.makedirs(out_dir, exist_ok=True)
+    if not force and os.path.exists(lib) and all(os.path.getmtime(p) <= os.path.getmtime(lib) for p in _deps()):
+        return lib
     cxx = os.environ.get("CXX", "g++")
 
     def one(unit):
         src, lang = unit
-        obj = os.path.join(OUT_DIR, os.path.basename(src).rsplit(".", 1)[0] + ".o")
-        subprocess.check_call([cxx, *CXXFLAGS, "-c", *lang, src, "-o", obj], cwd=ROOT)
+        obj = os.path.join(out_dir, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        subprocess.check_call([cxx, *CXXFLAGS, *defs, "-c", *lang, src, "-o", obj], cwd=ROOT)
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(one, UNITS))
     # -Bsymbolic: the emulated cudaMalloc / cudaFree / ... must never be interposed by a real libcudart loaded in the same process
-    subprocess.check_call([cxx, "-shared", "-Wl,-Bsymbolic", "-o", LIB, *objs, "-ldl"], cwd=ROOT)
-    return LIB
+    subprocess.check_call([cxx, "-shared", "-Wl,-Bsymbolic", "-o", lib, *objs, "-ldl"], cwd=ROOT)
+    return lib
 
 
 if __name__ == "__main__":

@@ -59,13 +59,16 @@ static std::string g_errmsg;
 // ---- fibers ------------------------------------------------------------------------------------------------------------------
 constexpr size_t STACK_BYTES = 256 * 1024;
 struct CpAsyncOp { uint32_t dst; const void* src; };
+struct BulkStore { void* dst; uint32_t src; uint32_t bytes; std::vector<unsigned char> snap; bool read_done = false; };
 struct Fiber {
     void* sp = nullptr;
     char* stack = nullptr;
     bool done = true;
     std::vector<std::vector<CpAsyncOp>> cp_groups;   // committed, not yet waited for
     std::vector<CpAsyncOp> cp_open;                  // issued since the last commit
-    int bulk_store_groups = 0;
+    std::vector<std::vector<BulkStore>> bulk_groups;  // committed bulk stores, oldest first
+    std::vector<BulkStore> bulk_open;
+    char waiting[96] = "";   // what a blocked thread is waiting for (deadlock report)
 };
 struct WarpEx {
     uint64_t slot[2][32];
@@ -116,6 +119,7 @@ static char* get_stack() {
 }
 
 static void fiber_exit();
+static void bulk_store_write(BulkStore& b);
 extern "C" void emu_trampoline() {
     (*g_cta->body)();
     fiber_exit();
@@ -146,6 +150,9 @@ static void fiber_exit() {
         for (auto& op : f.cp_open) std::memcpy(smem_ptr(op.dst, 16, 16), op.src, 16);
         f.cp_groups.clear(); f.cp_open.clear();
     }
+    for (auto& g : f.bulk_groups) for (auto& b : g) bulk_store_write(b);   // stores still in flight at thread exit complete
+    for (auto& b : f.bulk_open) bulk_store_write(b);
+    f.bulk_groups.clear(); f.bulk_open.clear();
     f.done = true;
     --c.alive;
     c.warps[c.cur >> 5].alive &= ~(1u << (c.cur & 31));
@@ -181,12 +188,15 @@ int linear_tid() { return g_cta ? g_cta->cur : 0; }
 int lane_id() { return linear_tid() & 31; }
 int warp_id() { return linear_tid() >> 5; }
 long long clock() { static long long t = 0; return t += 7; }
+static std::map<std::string, long long> g_notes;
+void note(const char* name) { ++g_notes[name]; }
 
 void syncthreads() {
     Cta& c = *g_cta;
     const unsigned my = c.bar_gen;
     ++c.bar_count; ++c.progress;
     release_barrier_if_complete(c);
+    if (c.bar_gen == my) snprintf(c.fibers[c.cur].waiting, 96, "__syncthreads (%d of %d arrived)", c.bar_count, c.alive);
     while (c.bar_gen == my) yield();
 }
 
@@ -200,6 +210,7 @@ uint64_t shfl(unsigned mask, uint64_t v, int src) {
     for (;;) {
         const unsigned need = mask & w.alive;
         if ((w.have[b] & need) == need) break;
+        snprintf(c.fibers[c.cur].waiting, 96, "warp shuffle / __syncwarp (mask %08x, arrived %08x)", mask, w.have[b]);
         yield();
     }
     const uint64_t r = w.slot[b][src & 31];
@@ -309,7 +320,11 @@ static void run_cta(Cta& c) {
     if (!c.aborted && c.alive > 0) {
         c.cur = -1;
         std::string who;
-        for (int t = 0; t < c.nthreads && who.size() < 200; ++t) if (!c.fibers[t].done) who += std::to_string(t) + " ";
+        std::map<std::string, std::vector<int>> by_reason;
+        for (int t = 0; t < c.nthreads; ++t) if (!c.fibers[t].done) by_reason[c.fibers[t].waiting].push_back(t);
+        for (auto& kv : by_reason) {
+            who += "\n  " + std::to_string(kv.second.size()) + " thread(s) [" + std::to_string(kv.second.front()) + ".." + std::to_string(kv.second.back()) + "] at " + kv.first;
+        }
         g_errmsg = std::string("emu fault: DEADLOCK in kernel ") + c.kname + ", block (" + std::to_string(blockIdx_.x) + "," + std::to_string(blockIdx_.y) + "," +
                    std::to_string(blockIdx_.z) + "): threads still waiting: " + who;
         g_err = cudaErrorLaunchTimeout;
@@ -478,6 +493,7 @@ cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 // test hook: clear the sticky error (a new "context")
 extern "C" void emu_reset_error() { g_err = 0; g_last = 0; g_errmsg.clear(); }
 extern "C" const char* emu_last_message() { return g_errmsg.c_str(); }
+extern "C" long long emu_note_count(const char* name) { auto it = emu::g_notes.find(name); return it == emu::g_notes.end() ? 0 : it->second; }
 extern "C" int emu_async_is_lazy() { init_once(); return g_lazy ? 1 : 0; }
 
 // --------------------------------------------------------------------------------------------------------------------------------
@@ -516,9 +532,16 @@ static Mbar& mbar_at(uint32_t bar, bool must_be_inited = true) {
 static void mbar_check(Mbar& m) {
     if (m.pending == 0 && m.tx == 0) { m.phase ^= 1u; m.pending = m.count; progress(); }
 }
+static void mbar_settle(Mbar& m, uint32_t bar);
 void mbar_init(uint32_t bar, uint32_t count) {
     Mbar& m = mbar_at(bar, false);
     if (count == 0) fault("mbarrier.init with count 0");
+    if (m.inited) {
+        // re-initialisation: whatever was still owed to the old barrier object lands on it first (a kernel that re-initialises a
+        // barrier while a TMA copy to it is in flight corrupts the new phase on hardware)
+        if (!m.copies.empty()) fault("mbarrier.init at 0x%x while a TMA copy that signals it is still in flight", bar);
+        mbar_settle(m, bar);
+    }
     m = Mbar();
     m.inited = true; m.count = count; m.pending = count;
     progress();
@@ -544,13 +567,17 @@ static void mbar_settle(Mbar& m, uint32_t bar) {
     }
     if (m.mma_commits > 0) {
         Cta& c = *g_cta;
-        // the commits owed to this barrier, oldest first; each requires the MMA queue to be drained up to it
-        for (auto it = c.mma_commits.begin(); it != c.mma_commits.end();) {
-            if (it->bar != bar) { ++it; continue; }
-            mma_drain(it->upto);
-            it = c.mma_commits.erase(it);
-            --m.mma_commits;
-            mbar_arrive_n(m, bar);
+        // the tensor core completes MMAs and their commits IN ORDER: observing a commit owed to this barrier means every earlier
+        // commit (to whatever barrier) has arrived too.  Find the last commit owed to `bar` and retire the queue up to it.
+        size_t last = c.mma_commits.size();
+        for (size_t i = 0; i < c.mma_commits.size(); ++i) if (c.mma_commits[i].bar == bar) last = i;
+        for (size_t i = 0; i <= last && !c.mma_commits.empty(); ++i) {
+            const MmaCommit mc = c.mma_commits.front();
+            c.mma_commits.pop_front();
+            mma_drain(mc.upto);
+            Mbar& tgt = mbar_at(mc.bar);
+            --tgt.mma_commits;
+            mbar_arrive_n(tgt, mc.bar);
         }
     }
 }
@@ -568,6 +595,7 @@ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (m.phase != (parity & 1u)) return;
         mbar_settle(m, bar);
         if (m.phase != (parity & 1u)) return;
+        snprintf(g_cta->fibers[g_cta->cur].waiting, 96, "mbarrier 0x%x parity %u (phase %u, pending arrivals %u of %u, tx %lld)", bar, parity & 1u, m.phase, m.pending, m.count, (long long)m.tx);
         yield();
     }
 }
@@ -584,14 +612,38 @@ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     (void)smem_ptr(dst, bytes, 16);
     tma_complete(bar, bytes, [=]() { std::memcpy(smem_ptr(dst, bytes, 16), src, bytes); });
 }
+// bulk stores: lazy = shared memory is read when the issuing thread executes wait_group.read (or wait_group) for the store's
+// group, global memory is written when it executes wait_group; eager = both at issue
+static void bulk_store_read(BulkStore& b) {
+    if (b.read_done) return;
+    b.snap.assign(smem_ptr(b.src, b.bytes, 16), smem_ptr(b.src, b.bytes, 16) + b.bytes);
+    b.read_done = true;
+}
+static void bulk_store_write(BulkStore& b) { bulk_store_read(b); std::memcpy(b.dst, b.snap.data(), b.bytes); }
 void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
     if (bytes == 0 || (bytes & 15u)) fault("cp.async.bulk (store): size %u is not a positive multiple of 16", bytes);
     check_global(dst, bytes, 16, "cp.async.bulk (global destination)");
-    std::memcpy(dst, smem_ptr(src, bytes, 16), bytes);   // stores read shared memory at issue in both modes (the source must stay intact until wait_group.read)
-    ++g_cta->fibers[g_cta->cur].bulk_store_groups;
+    (void)smem_ptr(src, bytes, 16);
+    BulkStore b; b.dst = dst; b.src = src; b.bytes = bytes;
+    if (!g_lazy) bulk_store_write(b);
+    else g_cta->fibers[g_cta->cur].bulk_open.push_back(std::move(b));
 }
-void bulk_commit_group() {}
-void bulk_wait_group(int, bool) {}
+void bulk_commit_group() {
+    Fiber& f = g_cta->fibers[g_cta->cur];
+    f.bulk_groups.push_back(std::move(f.bulk_open));
+    f.bulk_open.clear();
+}
+void bulk_wait_group(int allowed, bool read_only) {
+    Fiber& f = g_cta->fibers[g_cta->cur];
+    const int n = (int)f.bulk_groups.size();
+    for (int g = 0; g < n - allowed; ++g)
+        for (auto& b : f.bulk_groups[g]) { if (read_only) bulk_store_read(b); else bulk_store_write(b); }
+    if (!read_only) f.bulk_groups.erase(f.bulk_groups.begin(), f.bulk_groups.begin() + (n - allowed > 0 ? n - allowed : 0));
+    else {
+        // groups whose reads are done stay queued until a full wait (or thread exit) performs the writes; wait_group.read counts
+        // only groups that still have unread sources, so mark and skip them on later calls
+    }
+}
 
 static const TensorMapRec* map_rec(const CUtensorMap* map) {
     const TensorMapRec* r = reinterpret_cast<const TensorMapRec*>(map->opaque);
@@ -625,9 +677,10 @@ static void tma_row(const TensorMapRec* r, uint32_t dst_row, const long long* c 
 static void tma_check_common(const TensorMapRec* r, uint32_t dst, int c0, uint32_t total_bytes) {
     if (r->elem_bytes != 4) fault("emulated TMA handles 4-byte elements only");
     if (((long long)c0 * r->elem_bytes) % 16 != 0) fault("TMA: innermost start coordinate %d is not 16-byte aligned (illegal instruction on the device)", c0);
-    const uint32_t need = r->swizzle == CU_TENSOR_MAP_SWIZZLE_NONE ? 128u : 128u;
-    (void)smem_ptr(dst, total_bytes, need);
-    if (r->swizzle == CU_TENSOR_MAP_SWIZZLE_128B && (dst & 1023u)) fault("TMA into a 128-byte-swizzled tile needs a 1024-byte aligned shared-memory destination (0x%x)", dst);
+    // destination: 128-byte aligned.  The swizzle is a function of the shared-memory ADDRESS bits (16-byte chunk index ^= bits 7..9),
+    // so a request may land anywhere inside a 1024-byte aligned tile (tile::gather4 fills it 512 bytes at a time) and still agree
+    // with the UMMA descriptor that reads the tile -- provided the TILE base is 1024-byte aligned, which the descriptor check enforces.
+    (void)smem_ptr(dst, total_bytes, 128);
 }
 void tma_tile(uint32_t dst, const CUtensorMap* map, const int* coord, int ncoord, uint32_t bar) {
     const TensorMapRec* r = map_rec(map);
@@ -756,6 +809,7 @@ static inline float desc_elem(const SmemDesc& s, uint32_t row, uint32_t k) {
     if (s.layout != 2u && s.layout != 0u) fault("UMMA descriptor layout type %u is not modelled (2 = SWIZZLE_128B, 0 = none)", s.layout);
     uint32_t addr;
     if (s.layout == 2u) {
+        if ((s.start & ~127u & 1023u) != 0 && (s.start & 1023u) >= 128u) fault("UMMA SWIZZLE_128B operand: the tile base (0x%x minus its K offset) is not 1024-byte aligned", s.start);
         addr = s.start + (row >> 3) * s.sbo + (row & 7u) * 128u + k * 4u;
         addr = swz(addr, CU_TENSOR_MAP_SWIZZLE_128B);
     } else {

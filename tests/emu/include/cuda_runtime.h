@@ -70,6 +70,7 @@ unsigned char* smem_ptr(uint32_t addr, size_t bytes, size_t align);   // checked
 // global memory registry (cudaMalloc'ed ranges, guard pages at both ends)
 void check_global(const void* p, size_t bytes, size_t align, const char* what);
 long long clock();
+void note(const char* name);   // counts executions of a named code path (SGM_EMU_NOTE)
 }  // namespace emu
 
 #define threadIdx (::emu::threadIdx_)

@@ -23,6 +23,14 @@ def emulated_library():
         assert not msg, msg.decode()
 
 
+def ran(lib, path: str) -> int:
+    """How often the named kernel path executed in the emulated build (SGM_EMU_NOTE in the kernel sources)."""
+    import ctypes as C
+    lib.emu_note_count.restype = C.c_longlong
+    lib.emu_note_count.argtypes = [C.c_char_p]
+    return int(lib.emu_note_count(path.encode()))
+
+
 FAMILIES = ["gauss1d", "gauss2d", "gauss3d_fullcov", "gauss2d_flat", "mixture", "logistic5", "logistic54", "logistic130"]
 BENCHED = ["logistic54_n500", "logistic1024_n1024_N3000"]   # the template instantiations bench.py times (c3: R = 2; c5: <32, 9>)
 
@@ -53,10 +61,72 @@ def test_chain_storage_layout_and_seeds():
     T.test_same_seed_reproduces(None)
 
 
+# ---- 784-100-10 softmax net: TMA-fed S1 (tile::gather4 + 3-D box, 128-byte swizzle), S5 on tcgen05, streamed B update (TMA bulk copies
+# and bulk stores), the register-staged fall-back at the reduced width
+@pytest.mark.parametrize("case_name,algo,mode", [
+    ("softmaxnet_small", "sgld", "plain"), ("softmaxnet_small", "sghmc", "cv"), ("softmaxnet_small", "sgnht", "cv_shared"),
+    ("softmaxnet_small", "sgld", "cv"), ("softmaxnet_small", "sghmc", "plain"), ("softmaxnet_small", "sgnht", "plain"),
+    ("softmaxnet", "sghmc", "plain"), ("softmaxnet", "sgld", "cv"), ("softmaxnet", "sgnht", "cv_shared")])
+def test_softmax_net_steps_match_oracle(emulated_library, case_name, algo, mode):
+    before = ran(emulated_library, "nn_stage1_tma")
+    T._deterministic_steps(case_name, algo, mode != "plain", shared=(mode == "cv_shared"))
+    assert ran(emulated_library, "nn_stage1_tma") > before, "the TMA-fed forward GEMM did not run"
+
+
+def test_softmax_net_register_staged_paths():
+    """sgm_set_option: the register-staged forward GEMM (no TMA) and the register-staged update give the same chain."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import validation as V
+    case = make_case("softmaxnet_small")
+    states = []
+    for opts in ((), (("nn_stage1", 1),), (("nn_update", 1),)):
+        dev = T.device_setup(case, "sghmc", True, n_chains=2, n_iters_opt=3)
+        for k, v in opts:
+            V.setOption(dev, k, v)
+        S.initSess(dev, verbose=False)
+        S.sgmcmcStep(dev, None)
+        states.append(V.flatParams(dev))
+    for other in states[1:]:
+        assert np.abs(states[0] - other).max() <= 2e-5 * np.abs(states[0]).max()
+
+
+def test_softmax_net_misc():
+    T.test_est_logpost_matches_oracle(None, "softmaxnet_small")
+    T.test_heldout_loglik_matches_oracle(None, "softmaxnet_small")
+    T.test_device_rng_streams_match_oracle(None, "softmaxnet_small", "sghmc", False)
+
+
+def test_softmax_net_stage5_on_the_tensor_memory_side():
+    """nn_stage5_tmem: written at the end of round 1, compiled out of the product (-DNN_ENABLE_S5_TMEM), never run on a GPU.  Here it
+    runs in a second emulated build, selected through sgm_set_option, and must give the oracle's chain."""
+    from sgmcmc_b200 import validation as V
+    from tests import cases
+    orig = T.device_setup
+
+    def with_s5(*a, **k):
+        dev = orig(*a, **k)
+        V.setOption(dev, "nn_stage5", 1)
+        return dev
+
+    with backend.emulated("s5tmem") as lib:
+        T.device_setup = with_s5
+        try:
+            before = ran(lib, "nn_stage5_tmem")
+            T._deterministic_steps("softmaxnet", "sghmc", True, shared=False)
+            T._deterministic_steps("softmaxnet", "sgld", False, shared=False)
+            assert ran(lib, "nn_stage5_tmem") > before
+            assert not lib.emu_last_message()
+        finally:
+            T.device_setup = orig
+    del cases
+
+
 # ---- every gather engine of the short-row kernel and the generic kernel on the same case (sgm_set_option) -----------------------
-@pytest.mark.parametrize("option,value", [("gather", 1), ("gather", 2), ("gather", 3), ("gather", 4), ("logistic_kernel", 1)])
+@pytest.mark.parametrize("option,value,path", [("gather", 1, "logistic_staged:cp.async"), ("gather", 2, "logistic_staged:bulk"), ("gather", 3, "logistic_staged:bulk"),
+                                               ("gather", 4, "logistic_staged:gather4"), ("logistic_kernel", 1, "logistic_chain")])
 @pytest.mark.parametrize("case_name", ["logistic54", "logistic54_n500"])
-def test_logistic_kernel_variants(case_name, option, value):
+def test_logistic_kernel_variants(emulated_library, case_name, option, value, path):
+    before = ran(emulated_library, path)
     import sgmcmc_b200 as S
     from sgmcmc_b200 import validation as V
     case = make_case(case_name)
@@ -73,13 +143,16 @@ def test_logistic_kernel_variants(case_name, option, value):
         states.append(V.flatParams(dev))
     scale = np.abs(states[0]).max()
     assert np.abs(states[0] - states[1]).max() <= 1e-5 * scale, "a pinned kernel path disagrees with the default dispatch"
+    assert ran(emulated_library, path) > before, f"{path} did not run"
     del rs
 
 
 # ---- tcgen05 many-mode full gradient (cvg_kernel): TMA 128-byte-swizzled tiles, UMMA descriptors, A operand in TMEM -------------
 @pytest.mark.parametrize("case_name,chains", [("logistic54", 20), ("logistic5", 16), ("logistic130", 40)])
-def test_many_mode_full_gradient(case_name, chains):
+def test_many_mode_full_gradient(emulated_library, case_name, chains):
+    before = ran(emulated_library, "cvg:pass1"), ran(emulated_library, "cvg:pass2")
     F.test_many_mode_full_gradient_matches_oracle(None, case_name, chains)
+    assert ran(emulated_library, "cvg:pass1") > before[0] and ran(emulated_library, "cvg:pass2") > before[1]
 
 
 def test_many_mode_full_gradient_row_tail():
@@ -102,6 +175,8 @@ with backend.emulated() as lib:
     for case in ("logistic54", "logistic54_n500", "logistic130"):
         for algo in T.ALGOS:
             T._deterministic_steps(case, algo, True, shared=(algo == "sgld"))
+    T._deterministic_steps("softmaxnet_small", "sghmc", True, shared=False)
+    T._deterministic_steps("softmaxnet", "sghmc", False, shared=False)
     F.test_many_mode_full_gradient_matches_oracle(None, "logistic54", 20)
     F.test_many_mode_full_gradient_row_tail_and_blocks(None)
     assert not lib.emu_last_message()
