@@ -68,7 +68,7 @@ struct Fiber {
     std::vector<CpAsyncOp> cp_open;                  // issued since the last commit
     std::vector<std::vector<BulkStore>> bulk_groups;  // committed bulk stores, oldest first
     std::vector<BulkStore> bulk_open;
-    char waiting[96] = "";   // what a blocked thread is waiting for (deadlock report)
+    int wait_kind = 0; uint32_t wait_a = 0, wait_b = 0;   // what a blocked thread is waiting for (formatted only in a deadlock report)
 };
 struct WarpEx {
     uint64_t slot[2][32];
@@ -196,7 +196,7 @@ void syncthreads() {
     const unsigned my = c.bar_gen;
     ++c.bar_count; ++c.progress;
     release_barrier_if_complete(c);
-    if (c.bar_gen == my) snprintf(c.fibers[c.cur].waiting, 96, "__syncthreads (%d of %d arrived)", c.bar_count, c.alive);
+    c.fibers[c.cur].wait_kind = 1;
     while (c.bar_gen == my) yield();
 }
 
@@ -210,7 +210,7 @@ uint64_t shfl(unsigned mask, uint64_t v, int src) {
     for (;;) {
         const unsigned need = mask & w.alive;
         if ((w.have[b] & need) == need) break;
-        snprintf(c.fibers[c.cur].waiting, 96, "warp shuffle / __syncwarp (mask %08x, arrived %08x)", mask, w.have[b]);
+        { Fiber& f = c.fibers[c.cur]; f.wait_kind = 2; f.wait_a = mask; f.wait_b = w.have[b]; }
         yield();
     }
     const uint64_t r = w.slot[b][src & 31];
@@ -267,7 +267,8 @@ void check_global(const void* p, size_t bytes, size_t align, const char* what) {
     if (align > 1 && ((uintptr_t)p % align) != 0) fault("%s: global address %p is not %zu-byte aligned", what, p, align);
 }
 
-static void segv_handler(int, siginfo_t* si, void*) {
+static struct sigaction g_old_segv;
+static void segv_handler(int sig, siginfo_t* si, void* uc) {
     if (g_cta && g_cta->cur >= 0) {
         const unsigned char* base = nullptr;
         (void)base;
@@ -277,6 +278,10 @@ static void segv_handler(int, siginfo_t* si, void*) {
         if (it != g_allocs.begin()) { --it; snprintf(near, sizeof near, " (%+lld bytes past the end of a %zu-byte allocation)", (long long)((const unsigned char*)si->si_addr - (it->first + it->second.bytes)), it->second.bytes); }
         fault("illegal address %p%s", si->si_addr, near);
     }
+    // not a fault inside one of THIS library's kernels: hand it to whoever was installed before (a second emulated build loaded in
+    // the same process, Python's faulthandler, ...)
+    if ((g_old_segv.sa_flags & SA_SIGINFO) && g_old_segv.sa_sigaction) { g_old_segv.sa_sigaction(sig, si, uc); return; }
+    if (!(g_old_segv.sa_flags & SA_SIGINFO) && g_old_segv.sa_handler != SIG_DFL && g_old_segv.sa_handler != SIG_IGN) { g_old_segv.sa_handler(sig); return; }
     signal(SIGSEGV, SIG_DFL);
     raise(SIGSEGV);
 }
@@ -293,7 +298,7 @@ static void init_once() {
     memset(&sa, 0, sizeof sa);
     sa.sa_sigaction = segv_handler;
     sa.sa_flags = SA_SIGINFO | SA_NODEFER;
-    sigaction(SIGSEGV, &sa, nullptr);
+    sigaction(SIGSEGV, &sa, &g_old_segv);
     g_smem_pool = (unsigned char*)mmap(nullptr, SMEM_POOL, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
 }
 
@@ -321,7 +326,19 @@ static void run_cta(Cta& c) {
         c.cur = -1;
         std::string who;
         std::map<std::string, std::vector<int>> by_reason;
-        for (int t = 0; t < c.nthreads; ++t) if (!c.fibers[t].done) by_reason[c.fibers[t].waiting].push_back(t);
+        for (int t = 0; t < c.nthreads; ++t) {
+            const Fiber& f = c.fibers[t];
+            if (f.done) continue;
+            char why[160] = "(running)";
+            if (f.wait_kind == 1) snprintf(why, sizeof why, "__syncthreads (%d of %d live threads arrived)", c.bar_count, c.alive);
+            else if (f.wait_kind == 2) snprintf(why, sizeof why, "warp shuffle / __syncwarp (mask %08x, arrived %08x)", f.wait_a, f.wait_b);
+            else if (f.wait_kind == 3) {
+                const Mbar& m = c.mbars[f.wait_a];
+                snprintf(why, sizeof why, "mbarrier 0x%x parity %u (phase %u, pending arrivals %u of %u, tx bytes %lld, TMA copies in flight %zu, commits owed %d)",
+                         f.wait_a, f.wait_b, m.phase, m.pending, m.count, (long long)m.tx, m.copies.size(), m.mma_commits);
+            }
+            by_reason[why].push_back(t);
+        }
         for (auto& kv : by_reason) {
             who += "\n  " + std::to_string(kv.second.size()) + " thread(s) [" + std::to_string(kv.second.front()) + ".." + std::to_string(kv.second.back()) + "] at " + kv.first;
         }
@@ -595,7 +612,7 @@ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (m.phase != (parity & 1u)) return;
         mbar_settle(m, bar);
         if (m.phase != (parity & 1u)) return;
-        snprintf(g_cta->fibers[g_cta->cur].waiting, 96, "mbarrier 0x%x parity %u (phase %u, pending arrivals %u of %u, tx %lld)", bar, parity & 1u, m.phase, m.pending, m.count, (long long)m.tx);
+        { Fiber& f = g_cta->fibers[g_cta->cur]; f.wait_kind = 3; f.wait_a = bar; f.wait_b = parity & 1u; }
         yield();
     }
 }
