@@ -201,10 +201,34 @@ int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops);
  *   "logistic_kernel"  1 = generic warp-group kernel also for short rows
  *   "gather"           short-row kernel: 1 = 16-byte cp.async, 2 = one TMA bulk copy per row, 3 = mixed, 4 = TMA tile::gather4
  *   "fullgrad"         logistic full-data gradient: 1 = tensor-core contractions, 2 = SIMT row-chunk x mode grid
+ *   "fullgrad_row0", "fullgrad_row1"   row1 > 0: the full-data pass sums rows [row0, row1) only (what one rank of a row-sharded
+ *                      job computes), without a communicator: single-GPU pre-flight of arbitrary shard starts
  *   "nn_update"        softmax net: 1 = register-staged update of every tensor (default: streamed through shared memory)
  *   "nn_stage1"        softmax net: 1 = register-staged forward GEMM operands (default: TMA-fed)
  * The library never reads environment variables on the dispatch path. */
 int sgm_set_option(sgm_handle* h, const char* key, int32_t value);
+/* Launch plan of a configuration WITHOUT touching a device (works in a process that has no GPU): every kernel of initSess /
+ * sgmcmcStep with its grid, block, shared memory and tensor memory, every TMA tensor map with its extents, and the violations of
+ * the rules the driver / the TMA unit enforce (16-byte aligned box starts and strides, box <= extent of the allocation, <= 227 KB
+ * of shared memory, <= 512 TMEM columns, grid limits).  The library runs the same check before it launches the tensor-core
+ * full-gradient pass; this entry point lets a test sweep full-size configurations, world sizes and shard starts on a CPU.
+ * Writes a JSON object into out (NUL-terminated, truncated at cap); returns the number of violations (>= 0) or a negative
+ * sgm_status. */
+typedef struct sgm_plan_query {
+    int32_t model;           /* sgm_model */
+    int32_t cv;
+    int64_t N;               /* rows held by this process */
+    int32_t d;               /* features / inputs */
+    int32_t d_hidden, d_out; /* SOFTMAX_NET only */
+    int32_t n;               /* minibatch rows */
+    int32_t n_chains;
+    uint32_t flags;          /* SGM_FLAG_SHARED_MODE */
+    int32_t world, rank;     /* row-sharded control-variate pass (sgm_comm_init); world = 1: one process */
+    int32_t sharded_dataset; /* 1: sgm_attach_peer_shards (every rank holds N rows) */
+    int64_t row0, row1;      /* full-gradient row range override (simulated shard starts); -1 = this rank's default range */
+    int32_t sms;             /* streaming multiprocessors (148 on B200) */
+} sgm_plan_query;
+int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap);
 /* Debug: per-phase clock64() totals of the logistic short-row kernel (thread 0 of every CTA). */
 int sgm_debug_phase_cycles(sgm_handle* h, int enable, unsigned long long* out, int n);
 /* Copies rows [row0, row0+rows) of the device dataset back as column-major doubles

@@ -42,6 +42,12 @@ class SgmConfig(C.Structure):
     ]
 
 
+class SgmPlanQuery(C.Structure):
+    _fields_ = [("model", C.c_int32), ("cv", C.c_int32), ("N", C.c_int64), ("d", C.c_int32), ("d_hidden", C.c_int32), ("d_out", C.c_int32),
+                ("n", C.c_int32), ("n_chains", C.c_int32), ("flags", C.c_uint32), ("world", C.c_int32), ("rank", C.c_int32),
+                ("sharded_dataset", C.c_int32), ("row0", C.c_int64), ("row1", C.c_int64), ("sms", C.c_int32)]
+
+
 # every symbol include/sgmcmc_b200.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 _PD = C.POINTER(C.c_double)
@@ -79,6 +85,7 @@ SYMBOLS = {
     "sgm_dataset_ipc_handle": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "sgm_attach_peer_shards": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "sgm_detach_peer_shards": (C.c_int, [_H]),
+    "sgm_debug_plan": (C.c_int, [C.POINTER(SgmPlanQuery), C.c_char_p, C.c_size_t]),
     "sgm_set_option": (C.c_int, [_H, C.c_char_p, C.c_int32]),
     "sgm_debug_phase_cycles": (C.c_int, [_H, C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),
     "sgm_copy_dataset": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, _PD]),

@@ -2,6 +2,7 @@
 // kernel dispatch, chain storage, NCCL row-sharded control-variate pass.
 // No CPU fallback: every entry point needs a CUDA device and fails with SGM_ECUDA
 // otherwise.
+#include <climits>
 #include <cmath>
 #include <chrono>
 #include <cstdarg>
@@ -145,6 +146,8 @@ struct sgm_handle {
     int opt_logistic_kernel = 0;   // 1: generic warp-group kernel even for short rows
     int opt_gather = 0;            // short-row kernel: 1 cp.async, 2 TMA bulk copy per row, 3 mixed, 4 TMA tile::gather4
     int opt_fullgrad = 0;          // logistic full-data gradient: 1 tensor-core contractions, 2 SIMT row-chunk x mode grid
+    int opt_row0 = 0, opt_row1 = 0;   // row1 > 0: the full-data pass sums rows [row0, row1) only -- what rank r of a row-sharded job does,
+                                      // without a communicator (single-GPU pre-flight of shard starts; the sums are then partial sums)
     SoftmaxNetWork* nn = nullptr;
     // comm
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
@@ -554,83 +557,172 @@ static bool logistic_fullgrad_use_tc(const sgm_handle* h, int M) {
     return M >= 16 && (h->Pst % 4) == 0 && (h->ld % 4) == 0;   // below that the SIMT row-chunk x mode grid is HBM-bound anyway
 }
 
-static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1, int M, const float* theta_hat) {
-    const int d = h->d;
+// ---- launch plan of the many-mode pass: every number the launches and tensor maps use, computed without touching the device.
+// launch_logistic_fullgrad_tc() executes exactly this plan; sgm_debug_plan() prints and checks it for any configuration
+// (full BASELINE sizes, any world size, any shard start) in a process that has no GPU.
+struct TmapPlan {          // a 2-D float32 tensor map with a (CVG_KC x CVG_TILE) box, 128-byte swizzle
+    const char* what;
+    uint64_t inner, rows, pitch_floats;      // globalDim[0], globalDim[1], globalStrides[0] / 4
+    uint64_t alloc_floats;                   // floats available behind the base pointer
+};
+struct CvgBlockPlan {
+    int64_t b0, b1;        // global rows of the block
+    CvgArgs p1, p2;        // kernel arguments of the two passes (device pointers left null)
+    int grid1, grid2;
+    int64_t rowsum_warps;
+    TmapPlan mRt;
+};
+struct CvgPlan {
+    int64_t blk = 0, pitch = 0, xt_pitch = 0;
+    int shift = 0, tiles_m = 0;
+    size_t rt_bytes = 0, xt_bytes = 0;
+    TmapPlan mX{}, mTh{}, mXt{};
+    std::vector<CvgBlockPlan> blocks;
+};
+
+static CvgPlan cvg_plan(int64_t N, int d, int ld, int Pst, int M, int64_t row0, int64_t row1, int sms) {
+    CvgPlan P;
     const int64_t rows_all = row1 - row0;
-    if (rows_all <= 0) return SGM_OK;
-    CU(cudaFuncSetAttribute(cvg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CVG_SMEM));
-    if (!h->Xt) {   // one-time transposed copy of the features (pass 2 reads it K-major); 16-byte aligned rows
-        h->xt_pitch = (h->N + 3) / 4 * 4;
-        CU(cudaMalloc(&h->Xt, (size_t)d * h->xt_pitch * sizeof(float)));
-        dim3 tb(32, 8), tg((unsigned)cdiv(h->N, 32), (unsigned)cdiv(d, 32));
-        SGM_LAUNCH(cvg_transpose_kernel, tg, tb, 0, h->stream, h->X, h->N, h->ld, d, h->Xt, h->xt_pitch);
-        CU(cudaGetLastError());
-    }
+    P.xt_pitch = (N + 3) / 4 * 4;
+    P.xt_bytes = (size_t)d * P.xt_pitch * sizeof(float);
     // row blocks: R^T of one block stays <= ~2 GB
     const int Mpad = (int)cdiv(M, CVG_TILE) * CVG_TILE;
     int64_t blk = ((int64_t)1 << 29) / Mpad;
     blk = blk / 256 * 256; if (blk < 256) blk = 256;
     if (blk > rows_all) blk = cdiv(rows_all, 256) * 256;
-    const int shift = (int)(row0 & 31);            // pass 2 walks K from the 32-row aligned global row row0 - shift (TMA box starts are 16-byte aligned)
-    const int64_t pitch = blk + 32;
-    const size_t rt_need = (size_t)M * pitch * sizeof(float);
-    if (rt_need > h->rt_cap) {
-        if (h->Rt) cudaFree(h->Rt);
-        h->Rt = nullptr; h->rt_cap = 0;
-        CU(cudaMalloc(&h->Rt, rt_need));
-        h->rt_cap = rt_need;
-    }
-    int sms = 0;
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-    CUtensorMap mX, mTh, mXt, mRt;
-    if (cvg_encode_2d(&mX, h->X, (uint64_t)d, (uint64_t)h->N, (uint64_t)h->ld) || cvg_encode_2d(&mTh, theta_hat, (uint64_t)d, (uint64_t)M, (uint64_t)h->Pst) ||
-        cvg_encode_2d(&mXt, h->Xt, (uint64_t)h->N, (uint64_t)d, (uint64_t)h->xt_pitch))
-        return fail(SGM_ECUDA, "logistic full gradient: cuTensorMapEncodeTiled failed");
-    const int tiles_m = (int)cdiv(M, CVG_TILE);
+    P.blk = blk;
+    P.shift = (int)(row0 & 31);   // pass 2 walks K from the 32-row aligned global row row0 - shift (TMA box starts are 16-byte aligned)
+    P.pitch = blk + 32;
+    P.rt_bytes = (size_t)M * P.pitch * sizeof(float);
+    P.tiles_m = (int)cdiv(M, CVG_TILE);
+    P.mX = TmapPlan{"X (pass 1, A)", (uint64_t)d, (uint64_t)N, (uint64_t)ld, (uint64_t)N * ld};
+    P.mTh = TmapPlan{"theta_hat (pass 1, B)", (uint64_t)d, (uint64_t)M, (uint64_t)Pst, (uint64_t)M * Pst};
+    P.mXt = TmapPlan{"X^T (pass 2, A)", (uint64_t)N, (uint64_t)d, (uint64_t)P.xt_pitch, (uint64_t)d * P.xt_pitch};
     for (int64_t b0 = row0; b0 < row1; b0 += blk) {
+        CvgBlockPlan B{};
         const int64_t b1 = (b0 + blk < row1) ? b0 + blk : row1;
         const int64_t rows = b1 - b0;
-        if (cvg_encode_2d(&mRt, h->Rt, (uint64_t)(rows + shift), (uint64_t)M, (uint64_t)pitch)) return fail(SGM_ECUDA, "logistic full gradient: tensor map (R^T)");
-        if (shift) {
-            SGM_LAUNCH(cvg_zero_cols_kernel, (unsigned)cdiv((int64_t)M * shift, 256), 256, 0, h->stream, h->Rt, pitch, shift, M);
-            CU(cudaGetLastError());
-        }
+        B.b0 = b0; B.b1 = b1;
+        B.mRt = TmapPlan{"R^T (pass 2, B)", (uint64_t)(rows + P.shift), (uint64_t)M, (uint64_t)P.pitch, (uint64_t)M * P.pitch};
         CvgArgs a{};
-        a.X = h->X; a.ld = h->ld; a.d = d; a.theta_hat = theta_hat; a.Pst = h->Pst; a.M = M; a.Rt = h->Rt; a.rt_pitch = pitch; a.rt_col0 = shift; a.gsum = h->gsum;
-        a.row_base = b0; a.row_end = b1; a.tiles_b = tiles_m;
+        a.ld = ld; a.d = d; a.Pst = Pst; a.M = M; a.rt_pitch = P.pitch; a.rt_col0 = P.shift;
+        a.row_base = b0; a.row_end = b1; a.tiles_b = P.tiles_m;
         // pass 1: R^T = y - sigmoid(X theta_hat^T + bias)
         a.epi = 0; a.k_chunks = (int)cdiv(d, CVG_KC); a.a_row0 = (int)b0; a.a_k0 = 0; a.b_k0 = 0; a.k_per_split = 0; a.k_end_a = d;
-        {
-            a.tiles_a = (int)cdiv(rows, CVG_TILE);
-            a.n_items = a.tiles_a * tiles_m;
-            const int grid = a.n_items < sms ? a.n_items : sms;
-            SGM_LAUNCH(cvg_kernel, grid, CVG_THREADS, CVG_SMEM, h->stream, a, mX, mTh);
-            CU(cudaGetLastError());
-            const int64_t warps = (int64_t)M * cdiv(rows + shift, 4096);
-            SGM_LAUNCH(cvg_rowsum_kernel, (unsigned)cdiv(warps * 32, 256), 256, 0, h->stream, h->Rt, pitch, rows + shift, M, h->Pst, d, h->gsum);
-            CU(cudaGetLastError());
-        }
+        a.tiles_a = (int)cdiv(rows, CVG_TILE);
+        a.n_items = a.tiles_a * P.tiles_m;
+        B.grid1 = a.n_items < sms ? a.n_items : sms;
+        B.rowsum_warps = (int64_t)M * cdiv(rows + P.shift, 4096);
+        B.p1 = a;
         // pass 2: gsum[m][k] += sum_i R^T[m][i] X^T[k][i], K (= rows) split over CTAs
         a.epi = 1; a.a_row0 = 0;
         const int tiles_k = (int)cdiv(d, CVG_TILE);
         // ~8 work items per CTA (static round-robin: the tail is at most one item), each at least 2 K segments long
-        int64_t splits = cdiv((int64_t)sms * 8, (int64_t)tiles_k * tiles_m);
-        const int64_t kext = rows + shift;
+        int64_t splits = cdiv((int64_t)sms * 8, (int64_t)tiles_k * P.tiles_m);
+        const int64_t kext = rows + P.shift;
         int64_t kps = cdiv(cdiv(kext, splits), CVG_KC * CVG_SEG) * (CVG_KC * CVG_SEG);
         if (kps < 2 * CVG_KC * CVG_SEG) kps = 2 * CVG_KC * CVG_SEG;
         splits = cdiv(kext, kps);
-        a.k_per_split = (int)kps; a.k_chunks = (int)(kps / CVG_KC); a.a_k0 = (int)(b0 - shift); a.b_k0 = 0; a.k_end_a = (int)b1;
-        // a TMA box whose inner start coordinate is not 16-byte aligned is an illegal instruction on the device: refuse on the host
-        if ((a.a_k0 & 3) || (a.k_per_split & 3) || (h->xt_pitch & 3) || (pitch & 3) || (h->ld & 3) || (h->Pst & 3))
-            return fail(SGM_EINVAL, "logistic full gradient: unaligned TMA coordinates (k0 %d, split %d, pitches %lld / %lld)", a.a_k0, a.k_per_split,
-                        (long long)h->xt_pitch, (long long)pitch);
-        {
-            a.tiles_a = tiles_k;
-            a.n_items = (int)(tiles_k * tiles_m * splits);
-            const int grid = a.n_items < sms ? a.n_items : sms;
-            SGM_LAUNCH(cvg_kernel, grid, CVG_THREADS, CVG_SMEM, h->stream, a, mXt, mRt);
+        a.k_per_split = (int)kps; a.k_chunks = (int)(kps / CVG_KC); a.a_k0 = (int)(b0 - P.shift); a.b_k0 = 0; a.k_end_a = (int)b1;
+        a.tiles_a = tiles_k;
+        a.n_items = (int)(tiles_k * P.tiles_m * splits);
+        B.grid2 = a.n_items < sms ? a.n_items : sms;
+        B.p2 = a;
+        P.blocks.push_back(B);
+    }
+    return P;
+}
+
+// the rules cuTensorMapEncodeTiled and the TMA unit enforce (a violation is CUDA_ERROR_INVALID_VALUE at best, an illegal
+// instruction -- Xid 13 -- at worst), applied to a plan before anything is launched
+static void tmap_plan_check(const TmapPlan& m, std::vector<std::string>& bad) {
+    char buf[256];
+    auto say = [&](const char* why) { snprintf(buf, sizeof buf, "tensor map %s: %s (dims %llu x %llu, pitch %llu floats)", m.what, why,
+                                               (unsigned long long)m.inner, (unsigned long long)m.rows, (unsigned long long)m.pitch_floats); bad.push_back(buf); };
+    if (m.inner == 0 || m.rows == 0 || m.inner > (1ull << 32) || m.rows > (1ull << 32)) say("globalDim outside [1, 2^32]");
+    if ((m.pitch_floats * 4) % 16 != 0) say("globalStrides[0] is not a multiple of 16 bytes");
+    if (m.pitch_floats * 4 >= (1ull << 40)) say("globalStrides[0] >= 2^40");
+    if (m.pitch_floats < m.inner) say("row pitch shorter than the row");
+    if (m.rows > 0 && (m.rows - 1) * m.pitch_floats + m.inner > m.alloc_floats) say("tensor extends past its allocation");
+    static_assert(CVG_KC * 4 == 128 && CVG_TILE <= 256, "box = one 128-byte swizzle span x <= 256 rows");
+}
+
+static std::vector<std::string> cvg_plan_check(const CvgPlan& P) {
+    std::vector<std::string> bad;
+    char buf[256];
+    tmap_plan_check(P.mX, bad); tmap_plan_check(P.mTh, bad); tmap_plan_check(P.mXt, bad);
+    if (CVG_SMEM > 227 * 1024) bad.push_back("cvg_kernel: more than 227 KB of shared memory");
+    for (const CvgBlockPlan& B : P.blocks) {
+        tmap_plan_check(B.mRt, bad);
+        for (const CvgArgs* a : {&B.p1, &B.p2}) {
+            // innermost TMA coordinates are a_k0 / b_k0 + split * k_per_split + chunk * CVG_KC: every term must be a multiple of 4 floats
+            if ((a->a_k0 & 3) || (a->b_k0 & 3) || (a->k_per_split & 3)) {
+                snprintf(buf, sizeof buf, "cvg pass %d, rows [%lld, %lld): TMA box start not 16-byte aligned (a_k0 %d, b_k0 %d, K per split %d)", a->epi + 1,
+                         (long long)B.b0, (long long)B.b1, a->a_k0, a->b_k0, a->k_per_split);
+                bad.push_back(buf);
+            }
+            if (a->n_items < 1 || a->k_chunks < 1 || a->tiles_a < 1 || a->tiles_b < 1) {
+                snprintf(buf, sizeof buf, "cvg pass %d, rows [%lld, %lld): empty work decomposition (%d items, %d chunks)", a->epi + 1, (long long)B.b0, (long long)B.b1, a->n_items, a->k_chunks);
+                bad.push_back(buf);
+            }
+            if (a->epi == 1 && (a->k_per_split % (CVG_KC * CVG_SEG)) != 0) bad.push_back("cvg pass 2: K per split is not a whole number of TMEM segments");
+        }
+        // pass 2 must cover [b0 - shift, b1) exactly once: splits x k_per_split >= extent, a_k0 + extent == b1
+        const int64_t splits = B.p2.n_items / (B.p2.tiles_a * B.p2.tiles_b);
+        if ((int64_t)B.p2.a_k0 + splits * B.p2.k_per_split < B.b1 || (int64_t)B.p2.a_k0 != B.b0 - P.shift) bad.push_back("cvg pass 2: the K walk does not cover the row block");
+        if (B.b1 > (int64_t)INT32_MAX) bad.push_back("cvg: row coordinates beyond int32");
+        if (P.shift + (B.b1 - B.b0) > P.pitch) bad.push_back("cvg: R^T pitch shorter than the block");
+    }
+    if (P.pitch & 3) bad.push_back("cvg: R^T pitch not a multiple of 4 floats");
+    return bad;
+}
+
+static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1, int M, const float* theta_hat) {
+    const int d = h->d;
+    const int64_t rows_all = row1 - row0;
+    if (rows_all <= 0) return SGM_OK;
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const CvgPlan P = cvg_plan(h->N, d, h->ld, h->Pst, M, row0, row1, sms);
+    {   // a plan that breaks a TMA rule is refused here, on the host: on the device it is an illegal instruction
+        const std::vector<std::string> bad = cvg_plan_check(P);
+        if (!bad.empty()) return fail(SGM_EINVAL, "logistic full gradient: %s%s", bad[0].c_str(), bad.size() > 1 ? " (and more)" : "");
+    }
+    CU(cudaFuncSetAttribute(cvg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CVG_SMEM));
+    if (!h->Xt) {   // one-time transposed copy of the features (pass 2 reads it K-major); 16-byte aligned rows
+        h->xt_pitch = P.xt_pitch;
+        CU(cudaMalloc(&h->Xt, P.xt_bytes));
+        dim3 tb(32, 8), tg((unsigned)cdiv(h->N, 32), (unsigned)cdiv(d, 32));
+        SGM_LAUNCH(cvg_transpose_kernel, tg, tb, 0, h->stream, h->X, h->N, h->ld, d, h->Xt, h->xt_pitch);
+        CU(cudaGetLastError());
+    }
+    if (P.rt_bytes > h->rt_cap) {
+        if (h->Rt) cudaFree(h->Rt);
+        h->Rt = nullptr; h->rt_cap = 0;
+        CU(cudaMalloc(&h->Rt, P.rt_bytes));
+        h->rt_cap = P.rt_bytes;
+    }
+    CUtensorMap mX, mTh, mXt, mRt;
+    if (cvg_encode_2d(&mX, h->X, P.mX.inner, P.mX.rows, P.mX.pitch_floats) || cvg_encode_2d(&mTh, theta_hat, P.mTh.inner, P.mTh.rows, P.mTh.pitch_floats) ||
+        cvg_encode_2d(&mXt, h->Xt, P.mXt.inner, P.mXt.rows, P.mXt.pitch_floats))
+        return fail(SGM_ECUDA, "logistic full gradient: cuTensorMapEncodeTiled failed");
+    for (const CvgBlockPlan& B : P.blocks) {
+        const int64_t rows = B.b1 - B.b0;
+        if (cvg_encode_2d(&mRt, h->Rt, B.mRt.inner, B.mRt.rows, B.mRt.pitch_floats)) return fail(SGM_ECUDA, "logistic full gradient: tensor map (R^T)");
+        if (P.shift) {
+            SGM_LAUNCH(cvg_zero_cols_kernel, (unsigned)cdiv((int64_t)M * P.shift, 256), 256, 0, h->stream, h->Rt, P.pitch, P.shift, M);
             CU(cudaGetLastError());
         }
+        CvgArgs a = B.p1;
+        a.X = h->X; a.theta_hat = theta_hat; a.Rt = h->Rt; a.gsum = h->gsum;
+        SGM_LAUNCH(cvg_kernel, B.grid1, CVG_THREADS, CVG_SMEM, h->stream, a, mX, mTh);
+        CU(cudaGetLastError());
+        SGM_LAUNCH(cvg_rowsum_kernel, (unsigned)cdiv(B.rowsum_warps * 32, 256), 256, 0, h->stream, h->Rt, P.pitch, rows + P.shift, M, h->Pst, d, h->gsum);
+        CU(cudaGetLastError());
+        a = B.p2;
+        a.X = h->X; a.theta_hat = theta_hat; a.Rt = h->Rt; a.gsum = h->gsum;
+        SGM_LAUNCH(cvg_kernel, B.grid2, CVG_THREADS, CVG_SMEM, h->stream, a, mXt, mRt);
+        CU(cudaGetLastError());
         h->last_launches += 3;
     }
     h->fullgrad_flops = 4.0 * (double)rows_all * (double)d * (double)M;
@@ -1011,7 +1103,11 @@ static int fullgrad_gather_modes(sgm_handle* h) {
 static int full_gradient(sgm_handle* h) {
     const int M = hat_count(h);
     // replicated dataset: this rank sums its 1/world slice; sharded dataset: its whole local shard
-    const int64_t row0 = h->n_shards > 1 ? 0 : h->N * h->rank / h->world, row1 = h->n_shards > 1 ? h->N : h->N * (h->rank + 1) / h->world;
+    int64_t row0 = h->n_shards > 1 ? 0 : h->N * h->rank / h->world, row1 = h->n_shards > 1 ? h->N : h->N * (h->rank + 1) / h->world;
+    if (h->opt_row1 > 0) {
+        if (h->opt_row0 >= h->opt_row1 || h->opt_row1 > h->N) return fail(SGM_EINVAL, "fullgrad_row0 / fullgrad_row1 = [%d, %d) is not a row range of this dataset", h->opt_row0, h->opt_row1);
+        row0 = h->opt_row0; row1 = h->opt_row1;
+    }
     const bool gathered = fullgrad_gathered(h);
     if (gathered) {
         if (int rc = fullgrad_gather_modes(h)) return rc;
@@ -1461,7 +1557,8 @@ extern "C" int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t 
 extern "C" int sgm_set_option(sgm_handle* h, const char* key, int32_t value) {
     if (!h || !key) return fail(SGM_EINVAL, "null argument");
     struct Opt { const char* key; int* slot; int max; };
-    const Opt opts[] = {{"logistic_kernel", &h->opt_logistic_kernel, 1}, {"gather", &h->opt_gather, 4}, {"fullgrad", &h->opt_fullgrad, 2}};
+    const Opt opts[] = {{"logistic_kernel", &h->opt_logistic_kernel, 1}, {"gather", &h->opt_gather, 4}, {"fullgrad", &h->opt_fullgrad, 2},
+                        {"fullgrad_row0", &h->opt_row0, INT32_MAX}, {"fullgrad_row1", &h->opt_row1, INT32_MAX}};
     for (const Opt& o : opts)
         if (!strcmp(key, o.key)) {
             if (value < 0 || value > o.max) return fail(SGM_EINVAL, "option %s: value %d outside [0, %d]", key, value, o.max);
@@ -1473,6 +1570,171 @@ extern "C" int sgm_set_option(sgm_handle* h, const char* key, int32_t value) {
         return fail(SGM_EINVAL, "option %s = %d is not one the softmax-net kernels know", key, value);
     }
     return fail(SGM_EINVAL, "unknown option '%s'", key);
+}
+
+// ------------------------------------------------------------------------------------
+// launch plan (host only)
+// ------------------------------------------------------------------------------------
+namespace {
+struct PlanOut {
+    std::string js;
+    std::vector<std::string> bad;
+    bool first_launch = true, first_map = true;
+    std::string launches, maps;
+    void launch(const char* kernel, int64_t gx, int64_t gy, int64_t gz, int threads, size_t smem, int tmem_cols, const char* note = "") {
+        char b[512];
+        snprintf(b, sizeof b, "%s{\"kernel\":\"%s\",\"grid\":[%lld,%lld,%lld],\"block\":%d,\"smem\":%zu,\"tmem_cols\":%d,\"note\":\"%s\"}", first_launch ? "" : ",", kernel,
+                 (long long)gx, (long long)gy, (long long)gz, threads, smem, tmem_cols, note);
+        launches += b; first_launch = false;
+        auto say = [&](const char* why) { snprintf(b, sizeof b, "%s: %s (grid %lld x %lld x %lld, %d threads, %zu B shared)", kernel, why, (long long)gx, (long long)gy, (long long)gz, threads, smem); bad.push_back(b); };
+        if (gx < 1 || gy < 1 || gz < 1) say("empty grid");
+        if (gx > 2147483647ll || gy > 65535 || gz > 65535) say("grid dimension over the limit (2^31-1, 65535, 65535)");
+        if (threads < 1 || threads > 1024) say("block size outside [1, 1024]");
+        if (smem > 227 * 1024) say("more than 227 KB of dynamic shared memory");
+        if (tmem_cols > 512) say("more than 512 TMEM columns");
+    }
+    void map(const TmapPlan& m, int box0, int box1, const char* swizzle) {
+        char b[512];
+        snprintf(b, sizeof b, "%s{\"what\":\"%s\",\"dims\":[%llu,%llu],\"pitch_bytes\":%llu,\"box\":[%d,%d],\"swizzle\":\"%s\"}", first_map ? "" : ",", m.what,
+                 (unsigned long long)m.inner, (unsigned long long)m.rows, (unsigned long long)m.pitch_floats * 4, box0, box1, swizzle);
+        maps += b; first_map = false;
+        tmap_plan_check(m, bad);
+        if (box0 < 1 || box0 > 256 || box1 < 1 || box1 > 256) bad.push_back(std::string("tensor map ") + m.what + ": boxDim outside [1, 256]");
+        if ((box0 * 4) % 16) bad.push_back(std::string("tensor map ") + m.what + ": inner box is not a multiple of 16 bytes");
+    }
+};
+}  // namespace
+
+extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
+    if (!q || !out || cap < 2) return fail(SGM_EINVAL, "null argument");
+    if (q->N < 1 || q->N >= (1ll << 31) || q->d < 1 || q->n < 1 || q->n > q->N * (q->sharded_dataset ? (q->world > 0 ? q->world : 1) : 1) || q->n_chains < 1 || q->sms < 1)
+        return fail(SGM_EINVAL, "plan query: bad sizes");
+    const int world = q->world > 0 ? q->world : 1, rank = q->rank;
+    if (rank < 0 || rank >= world) return fail(SGM_EINVAL, "plan query: rank outside the world");
+    PlanOut po;
+    // a handle shaped like the query, without a device: the dispatch predicates below are the ones the real launches use
+    sgm_handle hh;
+    sgm_handle* h = &hh;
+    h->model = q->model; h->cv = q->cv ? 1 : 0; h->N = q->N; h->d = q->d; h->n = q->n; h->C = q->n_chains; h->flags = q->flags;
+    h->world = world; h->rank = rank; h->n_shards = q->sharded_dataset ? world : 1;
+    const int M = h->cv ? hat_count(h) : 0;
+    int64_t row0 = h->n_shards > 1 ? 0 : h->N * rank / world, row1 = h->n_shards > 1 ? h->N : h->N * (rank + 1) / world;
+    if (q->row0 >= 0) row0 = q->row0;
+    if (q->row1 >= 0) row1 = q->row1;
+    if (row0 < 0 || row1 > h->N || row0 >= row1) return fail(SGM_EINVAL, "plan query: bad row range [%lld, %lld)", (long long)row0, (long long)row1);
+    const int sms = q->sms;
+    SoftmaxNetPlan np{};
+    switch (h->model) {
+        case SGM_MODEL_GAUSS_MEAN:
+        case SGM_MODEL_MIXTURE2: {
+            if (h->d > SMALL_MAXD) return fail(SGM_EINVAL, "Gaussian families support d <= %d", SMALL_MAXD);
+            h->ld = h->d; h->P = h->Pst = (h->model == SGM_MODEL_MIXTURE2 ? 2 : 1) * h->d;
+            int64_t grid = cdiv((int64_t)h->C * 32, 128);
+            if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
+            po.launch("small_chain_kernel", grid, 1, 1, 128, 0, 0, "one warp per chain");
+            if (h->cv) {
+                int64_t gx = cdiv(row1 - row0, 256 * 4); if (gx > sms * 8) gx = sms * 8; if (gx < 1) gx = 1;
+                po.launch("small_chain_kernel (mode finder)", cdiv((int64_t)M * 32, 128), 1, 1, 128, 0, 0);
+                po.launch("small_fullsum_kernel", gx, M, 1, 256, 0, 0);
+            }
+            break;
+        }
+        case SGM_MODEL_LOGISTIC: {
+            h->ld = 4 * (h->d / 4 + 1);
+            LogiShape s;
+            if (!logi_shape(h->ld, &s)) return fail(SGM_EINVAL, "logistic: d = %d too large", h->d);
+            h->Pst = s.G * s.V * 4; h->P = h->d + 1;
+            h->tmap_ok = h->ld <= 128;
+            ChainArgs a{}; a.n = h->n; a.C = h->C; a.cv = h->cv;
+            auto chain = [&](int chains, const char* what) {
+                a.C = chains;
+                char note[160];
+                if (logistic_use_staged(h, a)) {
+                    const size_t smem = ls_smem_bytes(h->ld, h->n);
+                    int per_sm = (int)((227 * 1024) / (smem + 1024)); if (per_sm > 2) per_sm = 2; if (per_sm < 1) per_sm = 1;
+                    const bool g4 = h->tmap_ok && (ls_row_stride4(h->ld) == h->ld / 4) && h->ld <= 256;
+                    snprintf(note, sizeof note, "%s; rows per lane R = %d; gather = %s", what, (h->n + LS_THREADS - 1) / LS_THREADS, g4 ? "TMA tile::gather4" : "TMA bulk copy per row");
+                    po.launch("logistic_staged_kernel", chains < sms * per_sm ? chains : sms * per_sm, 1, 1, LS_THREADS, smem, 0, note);
+                    if (g4) po.map(TmapPlan{"dataset rows (gather4)", (uint64_t)h->ld, (uint64_t)h->N, (uint64_t)h->ld, (uint64_t)h->N * h->ld}, h->ld, 1, "none");
+                } else {
+                    const int threads = logi_threads(h, s);
+                    const size_t smem = logi_smem_bytes(threads, s, h->n);
+                    snprintf(note, sizeof note, "%s; <G, V> = <%d, %d>%s", what, s.G, s.V, h->n_shards > 1 ? "; rows resolved through the peer-shard table" : "");
+                    po.launch("logistic_chain_kernel", chains < sms ? chains : sms, 1, 1, threads, smem, 0, note);
+                }
+            };
+            chain(h->C, "sampling");
+            if (h->cv) {
+                chain(M, "mode finder");
+                const bool gathered = world > 1 && !(h->flags & SGM_FLAG_SHARED_MODE);
+                const int Mg = gathered ? M * world : M;
+                const int Q = h->ld / 4;
+                if (logistic_fullgrad_use_tc(h, Mg)) {
+                    const CvgPlan P = cvg_plan(h->N, h->d, h->ld, h->Pst, Mg, row0, row1, sms);
+                    for (const std::string& b : cvg_plan_check(P)) po.bad.push_back(b);
+                    po.map(P.mX, CVG_KC, CVG_TILE, "128B"); po.map(P.mTh, CVG_KC, CVG_TILE, "128B"); po.map(P.mXt, CVG_KC, CVG_TILE, "128B");
+                    char note[160];
+                    snprintf(note, sizeof note, "%zu row block(s) of %lld rows, K walk starts %d rows before the range; X^T %zu B, R^T %zu B", P.blocks.size(), (long long)P.blk, P.shift, P.xt_bytes, P.rt_bytes);
+                    po.launch("cvg_transpose_kernel", cdiv(h->N, 32), cdiv(h->d, 32), 1, 256, 0, 0, note);
+                    size_t shown = 0;
+                    for (const CvgBlockPlan& B : P.blocks) {
+                        if (shown++ >= 2 && &B != &P.blocks.back()) continue;   // first two and the last block are printed; all are checked
+                        po.map(B.mRt, CVG_KC, CVG_TILE, "128B");
+                        snprintf(note, sizeof note, "pass 1, rows [%lld, %lld): %d items x %d K stages", (long long)B.b0, (long long)B.b1, B.p1.n_items, B.p1.k_chunks);
+                        po.launch("cvg_kernel", B.grid1, 1, 1, CVG_THREADS, CVG_SMEM, 512, note);
+                        po.launch("cvg_rowsum_kernel", cdiv(B.rowsum_warps * 32, 256), 1, 1, 256, 0, 0);
+                        snprintf(note, sizeof note, "pass 2: %d items, K per split %d (from global row %d)", B.p2.n_items, B.p2.k_per_split, B.p2.a_k0);
+                        po.launch("cvg_kernel", B.grid2, 1, 1, CVG_THREADS, CVG_SMEM, 512, note);
+                    }
+                } else if (Mg == 1 && h->ld <= 128 && ((Q & 1) || (Q % 4 == 2)) && fg_smem_bytes(h->ld, FG_SHORT_ROWS) <= 113 * 1024) {
+                    const int64_t tiles = cdiv(row1 - row0, FG_SHORT_ROWS);
+                    po.launch("logistic_fullgrad_stream_kernel<short>", tiles < (int64_t)sms * 2 ? tiles : (int64_t)sms * 2, 1, 1, FG_THREADS, fg_smem_bytes(h->ld, FG_SHORT_ROWS), 0, "TMA bulk tile ring");
+                } else if (Mg == 1 && h->ld > 128 && (Q + 31) / 32 <= 9 && fg_smem_bytes(h->ld, FG_LONG_ROWS) <= 113 * 1024) {
+                    const int64_t tiles = cdiv(row1 - row0, FG_LONG_ROWS);
+                    po.launch("logistic_fullgrad_stream_kernel<long>", tiles < (int64_t)sms * 2 ? tiles : (int64_t)sms * 2, 1, 1, FG_THREADS, fg_smem_bytes(h->ld, FG_LONG_ROWS), 0, "TMA bulk tile ring");
+                } else {
+                    const int threads = (s.V >= 5) ? 512 : 256;
+                    int64_t chunks = (int64_t)sms * 8, rpc = cdiv(row1 - row0, chunks);
+                    const int64_t min_rows = 4 * (threads / s.G);
+                    if (rpc < min_rows) rpc = min_rows;
+                    chunks = cdiv(row1 - row0, rpc);
+                    po.launch("logistic_fullgrad_kernel", chunks, Mg, 1, threads, sizeof(float) * (size_t)(1 + threads / 32) * (s.V * s.G * 4), 0, "row chunks x modes");
+                }
+                if (M == 1 && ((h->flags & SGM_FLAG_SHARED_MODE) || h->n_shards <= 1) && (h->d & 3) != 3)
+                    po.launch("logistic_cache_rhat_kernel", cdiv(h->N * 32, 256), 1, 1, 256, 0, 0, "residual at the shared mode cached in the rows");
+            }
+            break;
+        }
+        case SGM_MODEL_SOFTMAX_NET: {
+            if (softmax_net_plan(h->d, q->d_hidden, q->d_out, &np) != 0) return fail(SGM_EINVAL, "softmax net: unsupported widths");
+            h->ld = 4 * (int)cdiv(h->d + q->d_out, 4); h->Pst = np.Pst;
+            char note[160];
+            snprintf(note, sizeof note, "forward GEMM %s; S1 ring %zu of %zu B", np.tma_fed ? "TMA-fed (gather4 + 3-D box)" : "register-staged", np.s1_ring_bytes, np.ring_capacity_bytes);
+            po.launch("softmax_net_chain_kernel", h->C < sms ? h->C : sms, 1, 1, np.threads, np.smem_bytes, np.tmem_cols, note);
+            if (np.tma_fed) {
+                po.map(TmapPlan{"dataset inputs (gather4)", (uint64_t)h->d, (uint64_t)h->N, (uint64_t)h->ld, (uint64_t)h->N * h->ld}, np.s1_box_inner, 1, "128B");
+                // 3-D parameter map: (input, hidden unit, chain); checked as its 2-D (input, hidden x chain) footprint
+                po.map(TmapPlan{"B block of the chain states", (uint64_t)h->d, (uint64_t)q->d_hidden, (uint64_t)h->d, (uint64_t)h->d * q->d_hidden}, np.s1_box_inner, q->d_hidden, "128B");
+                if ((np.offB & 3) || (np.Pst & 3)) po.bad.push_back("softmax net: parameter map base / chain stride not 16-byte aligned");
+            }
+            if (h->cv) {
+                int gx = (int)((sms + M - 1) / M); if (gx < 1) gx = 1;
+                po.launch("softmax_net_fullgrad_kernel", gx, M, 1, np.threads, np.smem_bytes, np.tmem_cols);
+            }
+            break;
+        }
+        default: return fail(SGM_ENOMODEL, "unknown model %d", h->model);
+    }
+    std::string js = "{\"ld\":" + std::to_string(h->ld) + ",\"Pst\":" + std::to_string(h->Pst) + ",\"rows\":[" + std::to_string(row0) + "," + std::to_string(row1) + "],\"launches\":[" +
+                     po.launches + "],\"tensor_maps\":[" + po.maps + "],\"violations\":[";
+    for (size_t i = 0; i < po.bad.size(); ++i) {
+        std::string v = po.bad[i];
+        for (char& c : v) if (c == '"' || c == '\\') c = '\'';
+        js += (i ? ",\"" : "\"") + v + "\"";
+    }
+    js += "]}";
+    snprintf(out, cap, "%s", js.c_str());
+    return (int)po.bad.size();
 }
 
 extern "C" int64_t sgm_num_rows(const sgm_handle* h) { return h ? h->N : 0; }

@@ -1576,13 +1576,35 @@ static bool nn_tma_enabled(const SoftmaxNetWork* w) {
     return (w->dm.offB % 4) == 0 && (size_t)nn_s1_ring_bytes(w->dm) <= (size_t)(2 * NN_RB * w->dm.dh + nn_tile_floats_all(w->dm)) * 4;
 }
 
-int softmax_net_create(SoftmaxNetWork** out, int d_in, int d_hidden, int d_out, int n, int chains, int device) {
-    if (d_in % 4 || d_hidden % 4 || d_hidden > NN_MAXH || d_out > NN_MAXO || d_out < 1 || (d_hidden * d_out) % 4) return (int)cudaErrorInvalidValue;
-    SoftmaxNetWork* w = new SoftmaxNetWork();
-    NNDims& dm = w->dm;
+static bool nn_dims(NNDims& dm, int d_in, int d_hidden, int d_out) {
+    if (d_in % 4 || d_hidden % 4 || d_hidden > NN_MAXH || d_out > NN_MAXO || d_out < 1 || (d_hidden * d_out) % 4) return false;
     dm.din = d_in; dm.dh = d_hidden; dm.dout = d_out; dm.dop = 4 * ((d_out + 3) / 4);
     dm.offA = 0; dm.offB = d_hidden * d_out; dm.offa = dm.offB + d_in * d_hidden; dm.offb = dm.offa + d_out; dm.offl = dm.offb + d_hidden;
     dm.P = dm.offl + 4;
+    return true;
+}
+
+// host-only description of the launches of this family (sgm_debug_plan): no device is touched
+int softmax_net_plan(int d_in, int d_hidden, int d_out, SoftmaxNetPlan* out) {
+    NNDims dm;
+    if (!nn_dims(dm, d_in, d_hidden, d_out)) return -1;
+    out->threads = NN_THREADS;
+    out->smem_bytes = nn_smem_bytes(dm);
+    out->tmem_cols = 512;
+    out->Pst = 4 * ((dm.P + 3) / 4);
+    out->offB = dm.offB;
+    SoftmaxNetWork w; w.dm = dm;
+    out->tma_fed = nn_tma_enabled(&w) ? 1 : 0;
+    out->s1_box_inner = S1_KC;
+    out->s1_ring_bytes = (size_t)nn_s1_ring_bytes(dm);
+    out->ring_capacity_bytes = (size_t)(2 * NN_RB * dm.dh + nn_tile_floats_all(dm)) * 4;
+    return 0;
+}
+
+int softmax_net_create(SoftmaxNetWork** out, int d_in, int d_hidden, int d_out, int n, int chains, int device) {
+    SoftmaxNetWork* w = new SoftmaxNetWork();
+    NNDims& dm = w->dm;
+    if (!nn_dims(dm, d_in, d_hidden, d_out)) { delete w; return (int)cudaErrorInvalidValue; }
     w->n = n; w->chains = chains; w->device = device;
     w->smem = nn_smem_bytes(dm);
     const int Pst = 4 * ((dm.P + 3) / 4);

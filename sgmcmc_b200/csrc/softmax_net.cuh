@@ -8,6 +8,9 @@ int softmax_net_create(SoftmaxNetWork** out, int d_in, int d_hidden, int d_out, 
 void softmax_net_destroy(SoftmaxNetWork* w);
 // internal element -> flat (ABI) index / tensor id tables (A and B are stored row-major internally)
 void softmax_net_tables(const SoftmaxNetWork* w, int* flat_of, int* tensor_of, int Pst);
+// what sgm_debug_plan reports for this family (computed on the host, no device needed)
+struct SoftmaxNetPlan { int threads; size_t smem_bytes; int tmem_cols; int Pst; int offB; int tma_fed; int s1_box_inner; size_t s1_ring_bytes; size_t ring_capacity_bytes; };
+int softmax_net_plan(int d_in, int d_hidden, int d_out, SoftmaxNetPlan* out);
 // kernel selectors (sgm_set_option keys "nn_update", "nn_stage1"); returns 0 when the key / value is known
 int softmax_net_set_option(SoftmaxNetWork* w, const char* key, int value);
 int softmax_net_launch(SoftmaxNetWork* w, const ChainArgs& a, cudaStream_t stream, int* launches);

@@ -159,6 +159,11 @@ def test_many_mode_full_gradient_row_tail():
     F.test_many_mode_full_gradient_row_tail_and_blocks(None)
 
 
+@pytest.mark.parametrize("path", ["tc", "generic", "stream"])
+def test_full_gradient_row_ranges_that_start_anywhere(path):
+    F.test_full_gradient_over_a_row_range_that_starts_anywhere(None, path)
+
+
 def test_many_mode_full_gradient_wide_rows():
     """d = 1024: pass 1 spans four TMEM segments per item (the c5 shape of bench.py, at a row count the emulation finishes in seconds)."""
     worst = F.many_mode_check(make_case("logistic1024_n200_N515"), 128, n_opt=3)

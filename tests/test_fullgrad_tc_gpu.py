@@ -87,3 +87,35 @@ def many_mode_check(case, chains, n_opt=4):
         worst = max(worst, err / scale)
         assert err <= 1e-5 * scale + 1e-7, f"chain {c}: tensor-core g_hat err {err:.3e} vs scale {scale:.3e}"
     return worst
+
+
+ROW_RANGES = [(1, 700), (37, 37 + 1153), (2001, 4000), (333, 334), (3, 131), (1939, 3878)]
+
+
+@pytest.mark.parametrize("path", ["tc", "generic", "stream"])
+def test_full_gradient_over_a_row_range_that_starts_anywhere(lib, path):
+    """What rank r of a row-sharded job computes: the sum over rows [row0, row1) only, row0 odd / not a multiple of 4 or 32 (the
+    tensor-core pass walks K from the aligned row below and masks the rows before the range: TMA box starts must be 16-byte aligned).
+    Selected through sgm_set_option("fullgrad_row0" / "fullgrad_row1"), no communicator needed: a single-GPU pre-flight of the
+    shard starts that faulted at 8 GPUs in round 1."""
+    from sgmcmc_b200 import validation as V
+    import sgmcmc_b200 as S
+    case = make_case("logistic54")
+    chains = 1 if path == "stream" else 20
+    post = OS.Posterior(case["om"], case["N"], case["n"], np.float64, use_prior=True)
+    for row0, row1 in ROW_RANGES:
+        dev = device_setup(case, "sgld", True, n_chains=chains, n_iters_opt=3)
+        if path != "stream":
+            V.setOption(dev, "fullgrad", FULLGRAD_OPTION[path])
+        V.setOption(dev, "fullgrad_row0", row0)
+        V.setOption(dev, "fullgrad_row1", row1)
+        S.initSess(dev, verbose=False)
+        th_hat, g_hat = V.getMode(dev)
+        sub = {k: np.asarray(v)[row0:row1] for k, v in case["data"].items()}
+        for c in range(chains):
+            th = OS.unflat(th_hat[c], case["params"])
+            ref = OS.flat(post.full_grad(th, sub))
+            gl = OS.flat(case["om"].grad_loglik(th, sub, np.float64))
+            scale = max(np.abs(ref).max(), np.abs(gl).max(), 1.0) * 10
+            err = np.abs(g_hat[c] - ref).max()
+            assert err <= 1e-5 * scale + 1e-7, f"rows [{row0}, {row1}), chain {c}, {path}: err {err:.3e} vs scale {scale:.3e}"
