@@ -183,35 +183,13 @@ def measured_tensor_peak():
 
 
 def comm_init(sg, rank, world):
-    """Gives the handle an NCCL communicator over all ranks (id broadcast through torch.distributed)."""
-    import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from sgmcmc_b200 import _lib
-    lib = _lib.load()
-    idbuf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8)
-    if rank == 0:
-        raw = (C.c_char * _lib.NCCL_ID_BYTES)()
-        _lib.check(lib.sgm_comm_unique_id(raw, _lib.NCCL_ID_BYTES))
-        idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
-    idbuf = idbuf.cuda()
-    dist.broadcast(idbuf, 0)
-    _lib.check(lib.sgm_comm_init(sg.handle, idbuf.cpu().numpy().tobytes(), _lib.NCCL_ID_BYTES, rank, world))
+    from sgmcmc_b200 import distributed as D
+    D.comm_init(sg, rank, world)
 
 
 def attach_peer_shards(sg, rank, world):
-    """Every rank keeps its own N rows; the peers' shards are mapped through CUDA IPC so the chains sample from world x N rows."""
-    import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from sgmcmc_b200 import _lib
-    lib = _lib.load()
-    mine = (C.c_char * _lib.IPC_HANDLE_BYTES)()
-    _lib.check(lib.sgm_dataset_ipc_handle(sg.handle, mine, _lib.IPC_HANDLE_BYTES))
-    t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone().cuda()
-    allh = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(allh, t)
-    _lib.check(lib.sgm_attach_peer_shards(sg.handle, b"".join(x.cpu().numpy().tobytes() for x in allh), world, rank))
+    from sgmcmc_b200 import distributed as D
+    D.attach_peer_shards(sg, rank, world)
 
 
 def many_mode_full_gradient(w, rank, world, modes):

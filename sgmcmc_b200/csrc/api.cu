@@ -71,6 +71,9 @@ static NcclApi g_nccl;
 static int load_nccl() {
     if (g_nccl.lib) return SGM_OK;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
+#ifdef SGM_EMU   // the CPU-emulated test build talks to tests/emu/fake_nccl.c (multi-process collectives over shared memory)
+    if (const char* fake = getenv("SGM_EMU_NCCL")) names[0] = fake;
+#endif
     void* lib = nullptr;
     for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
     if (!lib) return fail(SGM_ECOMM, "cannot dlopen libnccl.so.2: %s", dlerror());

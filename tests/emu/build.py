@@ -60,6 +60,15 @@ def build(force: bool = False, variant: str = "", defs=()) -> str:
     return lib
 
 
+def build_fake_nccl(force: bool = False) -> str:
+    """tests/emu/fake_nccl.c -> _build/libnccl_fake.so: the NCCL entry points over POSIX shared memory (multi-process emulated runs)."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    src, lib = os.path.join(HERE, "fake_nccl.c"), os.path.join(OUT_DIR, "libnccl_fake.so")
+    if force or not os.path.exists(lib) or os.path.getmtime(src) > os.path.getmtime(lib):
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-shared", "-o", lib, src, "-lrt", "-lpthread"], cwd=ROOT)
+    return lib
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv))

@@ -3,6 +3,7 @@
 #define SGM_EMU 1
 #include "cuda_runtime.h"
 
+#include <fcntl.h>
 #include <signal.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -50,6 +51,7 @@ dim3 blockDim_, gridDim_;
 static bool g_lazy = true;          // SGM_EMU_ASYNC
 static int g_sms = 2;               // SGM_EMU_SMS
 static bool g_verbose = false;
+static bool g_shm_ipc = false;     // SGM_EMU_SHM_IPC
 
 // ---- sticky error ------------------------------------------------------------------------------------------------------------
 static int g_err = 0;               // sticky (context-destroying) error
@@ -249,7 +251,7 @@ unsigned char* smem_ptr(uint32_t addr, size_t bytes, size_t align) {
 }
 
 // ---- global memory -----------------------------------------------------------------------------------------------------------
-struct Alloc { size_t bytes; void* map; size_t map_bytes; };
+struct Alloc { size_t bytes; void* map; size_t map_bytes; std::string shm; size_t shm_off = 0; bool foreign = false; };
 static std::map<const unsigned char*, Alloc> g_allocs;
 static const size_t PAGE = 4096;
 
@@ -294,6 +296,7 @@ static void init_once() {
     g_lazy = !(a && !strcmp(a, "eager"));
     if (const char* s = getenv("SGM_EMU_SMS")) g_sms = atoi(s) > 0 ? atoi(s) : 2;
     g_verbose = getenv("SGM_EMU_VERBOSE") != nullptr;
+    g_shm_ipc = getenv("SGM_EMU_SHM_IPC") != nullptr;
     struct sigaction sa;
     memset(&sa, 0, sizeof sa);
     sa.sa_sigaction = segv_handler;
@@ -436,11 +439,24 @@ cudaError_t cudaMallocImpl(void** p, size_t bytes) {
     const size_t total = pages + 2 * PAGE;
     void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (m == MAP_FAILED) { g_last = cudaErrorMemoryAllocation; g_errmsg = "emu: out of memory"; *p = nullptr; return cudaErrorMemoryAllocation; }
+    std::string shm_name;
+    if (g_shm_ipc && bytes >= (64u << 10)) {
+        // SGM_EMU_SHM_IPC=1: large allocations live in POSIX shared memory so that cudaIpc* works ACROSS processes (multi-rank tests)
+        static int counter = 0;
+        char nm[40];
+        snprintf(nm, sizeof nm, "/sgm_emu_%d_%d", (int)getpid(), counter++);
+        const int fd = shm_open(nm, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd >= 0 && ftruncate(fd, (off_t)pages) == 0 && mmap((char*)m + PAGE, pages, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0) != MAP_FAILED) shm_name = nm;
+        if (fd >= 0) close(fd);
+        if (shm_name.empty()) { munmap(m, total); g_last = cudaErrorMemoryAllocation; g_errmsg = "emu: shared-memory allocation failed"; *p = nullptr; return cudaErrorMemoryAllocation; }
+    }
     mprotect(m, PAGE, PROT_NONE);
     mprotect((char*)m + PAGE + pages, PAGE, PROT_NONE);
     unsigned char* q = (unsigned char*)m + PAGE + pages - payload;   // the end of the payload touches the guard page
     memset(q, 0xff, payload);                                         // uninitialised device memory is not zero
-    g_allocs[q] = Alloc{bytes, m, total};
+    Alloc al{bytes, m, total};
+    al.shm = shm_name; al.shm_off = pages - payload;
+    g_allocs[q] = al;
     *p = q;
     return cudaSuccess;
 }
@@ -448,6 +464,8 @@ cudaError_t cudaFree(void* p) {
     if (!p) return cudaSuccess;
     auto it = g_allocs.find((const unsigned char*)p);
     if (it == g_allocs.end()) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cudaFree of an unknown pointer"; return cudaErrorInvalidValue; }
+    if (it->second.foreign) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cudaFree of a peer's IPC mapping (use cudaIpcCloseMemHandle)"; return cudaErrorInvalidValue; }
+    if (!it->second.shm.empty()) shm_unlink(it->second.shm.c_str());
     munmap(it->second.map, it->second.map_bytes);
     g_allocs.erase(it);
     return cudaSuccess;
@@ -502,10 +520,43 @@ cudaError_t cudaGetDriverEntryPoint(const char* sym, void** fn, unsigned long lo
     if (!strcmp(sym, "cuTensorMapEncodeTiled")) { *fn = (void*)&emu::encode_tiled; if (q) *q = cudaDriverEntryPointSuccess; return cudaSuccess; }
     *fn = nullptr; if (q) *q = cudaDriverEntryPointSymbolNotFound; return cudaErrorInvalidValue;
 }
-// in-process stand-in for CUDA IPC: the handle carries the pointer (lets one process play several ranks in tests)
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { EMU_STICKY(); memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
-cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { EMU_STICKY(); memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+// CUDA IPC stand-in.  Same process: the handle carries the pointer (one process can play several ranks).  Other process: the
+// allocation must live in shared memory (SGM_EMU_SHM_IPC=1); the handle names the object and the payload's offset in it.
+struct IpcRec { char name[32]; void* ptr; int pid; uint32_t pad; uint64_t off, bytes; };
+static_assert(sizeof(IpcRec) <= sizeof(cudaIpcMemHandle_t), "IPC record fits the opaque handle");
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+    EMU_STICKY();
+    auto it = g_allocs.find((const unsigned char*)p);
+    if (it == g_allocs.end()) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cudaIpcGetMemHandle of a pointer that is not the base of an allocation"; return cudaErrorInvalidValue; }
+    IpcRec r; memset(&r, 0, sizeof r);
+    snprintf(r.name, sizeof r.name, "%s", it->second.shm.c_str());
+    r.ptr = p; r.pid = (int)getpid(); r.off = it->second.shm_off; r.bytes = it->second.bytes;
+    memset(h, 0, sizeof *h); memcpy(h->reserved, &r, sizeof r);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+    EMU_STICKY();
+    IpcRec r; memcpy(&r, h.reserved, sizeof r);
+    if (r.pid == (int)getpid()) { *p = r.ptr; return cudaSuccess; }
+    if (!r.name[0]) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: IPC handle of another process whose allocation is not in shared memory (SGM_EMU_SHM_IPC=1)"; return cudaErrorInvalidValue; }
+    const int fd = shm_open(r.name, O_RDWR, 0600);
+    if (fd < 0) { g_last = cudaErrorInvalidValue; g_errmsg = "emu: cannot open the peer's shared-memory allocation"; return cudaErrorInvalidValue; }
+    const size_t map_bytes = (r.off + r.bytes + PAGE - 1) / PAGE * PAGE;
+    void* m = mmap(nullptr, map_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) { g_last = cudaErrorMemoryAllocation; g_errmsg = "emu: cannot map the peer's allocation"; return cudaErrorMemoryAllocation; }
+    unsigned char* q = (unsigned char*)m + r.off;
+    Alloc al{(size_t)r.bytes, m, map_bytes};
+    al.foreign = true;
+    g_allocs[q] = al;
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+    auto it = g_allocs.find((const unsigned char*)p);
+    if (it != g_allocs.end() && it->second.foreign) { munmap(it->second.map, it->second.map_bytes); g_allocs.erase(it); }
+    return cudaSuccess;
+}
 
 // test hook: clear the sticky error (a new "context")
 extern "C" void emu_reset_error() { g_err = 0; g_last = 0; g_errmsg.clear(); }

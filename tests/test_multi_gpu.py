@@ -19,8 +19,9 @@ def test_row_sharded_pass_with_one_mode_per_chain(lib):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
 
-@pytest.mark.xfail(reason="written after gpurun was closed for this round: not yet run on a GPU box", strict=False)
 def test_dataset_sharded_over_ranks_and_peer_mapped(lib):
+    """First GPU execution pending (gpurun closed in rounds 1 and 2); the same check passes on the CPU-emulated build as a 2-process
+    job (tests/test_emu_multirank.py).  Skipped, not xfailed, on a single-GPU box."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
