@@ -116,6 +116,14 @@ typedef struct sgm_handle sgm_handle;
  * -> row-major float32, 16-byte-aligned row stride), allocates chain state. */
 int sgm_create(const sgm_config* cfg, sgm_handle** out);
 
+/* Progress of the *cv mode finder.  The reference's getMode calls checkOptDivergence every 100 optimiser iterations
+ * (R/controlVariates.R:45-47,114-124): the log posterior estimate at the current mode estimate on a FRESH minibatch; NaN stops with
+ * "Chain diverged", otherwise -- when verbose -- "Iteration: i  Log posterior estimate: v" is printed.  sgm_init does the same on the
+ * device in launches of <= 100 iterations and hands the value(s) to fn (phase = 1, iter = optimiser iterations done, logpost[n] =
+ * one estimate per mode); the R shim / Python mirror prints the reference's line from it.  fn runs on the calling thread. */
+typedef void (*sgm_progress_fn)(void* user, int32_t phase, int64_t iter, const double* logpost, int32_t n);
+int sgm_set_progress(sgm_handle* h, sgm_progress_fn fn, void* user);
+
 /* initSess (R/update.R:126-140): draws the initial momenta (R/dynamics.R:47,84); for
  * *cv runs getMode + calcFullGrads and sets theta := theta_hat (cV.R:37-52,105-111).
  * Returns SGM_EDIVERGED with "Chain diverged" if the optimiser produced NaN (cV.R:119). */
@@ -203,6 +211,9 @@ int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops);
  *   "fullgrad"         logistic full-data gradient: 1 = tensor-core contractions, 2 = SIMT row-chunk x mode grid
  *   "fullgrad_row0", "fullgrad_row1"   row1 > 0: the full-data pass sums rows [row0, row1) only (what one rank of a row-sharded
  *                      job computes), without a communicator: single-GPU pre-flight of arbitrary shard starts
+ *   "sharded_mode_finder"  1 = the *cv mode finder sharded by data rows: every SGD step each rank sums the gradients of its part of the
+ *                      minibatch (drawn from its own rows) and the P-vector is all-reduced (needs sgm_comm_init and
+ *                      SGM_FLAG_SHARED_MODE; default: every rank runs the same finder on the rows it can reach, no communication)
  *   "nn_update"        softmax net: 1 = register-staged update of every tensor (default: streamed through shared memory)
  *   "nn_stage1"        softmax net: 1 = register-staged forward GEMM operands (default: TMA-fed)
  * The library never reads environment variables on the dispatch path. */

@@ -85,6 +85,7 @@ SYMBOLS = {
     "sgm_dataset_ipc_handle": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "sgm_attach_peer_shards": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "sgm_detach_peer_shards": (C.c_int, [_H]),
+    "sgm_set_progress": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "sgm_debug_plan": (C.c_int, [C.POINTER(SgmPlanQuery), C.c_char_p, C.c_size_t]),
     "sgm_set_option": (C.c_int, [_H, C.c_char_p, C.c_int32]),
     "sgm_debug_phase_cycles": (C.c_int, [_H, C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),
@@ -94,6 +95,8 @@ SYMBOLS = {
     "sgm_last_error": (C.c_char_p, []),
     "sgm_version": (C.c_char_p, []),
 }
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double), C.c_int32)
 
 _lib = None
 

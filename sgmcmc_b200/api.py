@@ -208,8 +208,22 @@ def sgnhtcvSetup(logLik, dataset, params, stepsize, optStepsize, logPrior=None, 
 
 def initSess(sgmcmc: Sgmcmc, verbose=True) -> Session:
     lib = _lib.load()
-    if sgmcmc.inherits("sgmcmccv") and verbose:
-        _message("\nFinding initial MAP estimates...")  # R/controlVariates.R:40
+    if sgmcmc.inherits("sgmcmccv"):
+        if verbose:
+            _message("\nFinding initial MAP estimates...")  # R/controlVariates.R:40
+
+        def report(_user, _phase, it, lp, n):   # checkOptDivergence's line (R/controlVariates.R:121-123), one value per mode
+            if verbose:
+                v = lp[0] if n == 1 else float(np.mean([lp[i] for i in range(n)]))
+                _message(f"Iteration: {it}\t\tLog posterior estimate: {v}")
+
+        cb = _lib.PROGRESS_FN(report)
+        _lib.check(lib.sgm_set_progress(sgmcmc.handle, C.cast(cb, C.c_void_p), None))
+        try:
+            _lib.check(lib.sgm_init(sgmcmc.handle))
+        finally:
+            lib.sgm_set_progress(sgmcmc.handle, None, None)
+        return Session(sgmcmc)
     _lib.check(lib.sgm_init(sgmcmc.handle))
     return Session(sgmcmc)
 

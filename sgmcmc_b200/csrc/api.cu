@@ -143,12 +143,15 @@ struct sgm_handle {
     float* hat_all = nullptr; double* gsum_all = nullptr;   // row-sharded pass with one mode per chain: the modes of ALL ranks / their sums
     double fullgrad_flops = 0;                      // 4 N d M of the last tensor-core full gradient (0: not used)
     bool rhat_cached = false;   // logistic *cv, shared mode: y - s(x.beta_hat) stored in the rows' spare slot
+    sgm_progress_fn progress = nullptr; void* progress_user = nullptr;   // every 100 iterations of the mode finder (checkOptDivergence)
     ChainArgs base;  // template of kernel arguments
     // kernel selectors (sgm_set_option; 0 = the default dispatch).  They exist so that tests can pin a path through the ABI;
     // nothing on the dispatch path reads the environment.
     int opt_logistic_kernel = 0;   // 1: generic warp-group kernel even for short rows
     int opt_gather = 0;            // short-row kernel: 1 cp.async, 2 TMA bulk copy per row, 3 mixed, 4 TMA tile::gather4
     int opt_fullgrad = 0;          // logistic full-data gradient: 1 tensor-core contractions, 2 SIMT row-chunk x mode grid
+    int opt_sharded_finder = 0;    // 1: mode finder sharded by data rows (each rank draws its part of every minibatch from its own rows, the
+                                   // P-vector is all-reduced every SGD step); needs sgm_comm_init + SGM_FLAG_SHARED_MODE
     int opt_row0 = 0, opt_row1 = 0;   // row1 > 0: the full-data pass sums rows [row0, row1) only -- what rank r of a row-sharded job does,
                                       // without a communicator (single-GPU pre-flight of shard starts; the sums are then partial sums)
     SoftmaxNetWork* nn = nullptr;
@@ -248,6 +251,23 @@ __global__ void state_to_double_kernel(const float* __restrict__ src, int C, int
     if (f >= 0) out[(size_t)c * P + f] = (double)src[i];
 }
 
+// row-sharded mode finder: this rank's part of one minibatch = n_r distinct rows of ITS row range [row0, row0 + rows), as absolute row numbers
+__global__ void opt_indices_kernel(int32_t* __restrict__ idx, int n_r, uint32_t row0, uint32_t rows, uint32_t bits, uint32_t stream_id, uint32_t word2,
+                                   uint32_t k0, uint32_t k1) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_r) return;
+    const Perm p = make_perm(rows, bits, stream_id, word2, TAG_OPT_INDEX, k0, k1);
+    idx[j] = (int32_t)(row0 + perm_at(p, (uint32_t)j));
+}
+// theta_hat += lr * g   (plain SGD ascent, R/controlVariates.R:87-88), g = all-reduced estimate (+ the prior gradient computed apart)
+__global__ void opt_apply_kernel(float* __restrict__ theta_hat, const float* __restrict__ g, const float* __restrict__ g_prior, float lr, int count, int* __restrict__ diverged) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const float v = theta_hat[e] + lr * (g[e] + (g_prior ? g_prior[e] : 0.f));
+    theta_hat[e] = v;
+    if (!isfinite(v)) *diverged = 1;
+}
+
 __global__ void broadcast_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int C, int Pst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (int64_t)C * Pst) dst[i] = src[i % Pst];
@@ -324,6 +344,9 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 template <class T>
 struct DevBuf {
     T* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;              // (a launch site must name the raw pointer, never the owner)
+    DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
 };
@@ -1191,6 +1214,94 @@ static int check_rows(const sgm_handle* h, const int32_t* idx, size_t count) {
     return SGM_OK;
 }
 
+static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta, double* out, int chains = -1);
+static inline uint32_t word2_host(uint64_t step, int L, int sub) { return (uint32_t)(step * (uint64_t)(L + 1) + (uint64_t)sub); }   // = word2_of (common.cuh)
+
+// checkOptDivergence (R/controlVariates.R:114-124): estLogPost at the mode estimate(s) on a fresh device-drawn minibatch
+static int opt_checkpoint(sgm_handle* h, int M, int64_t iter) {
+    std::vector<double> lp((size_t)M);
+    h->check_ctr += 1;
+    if (int rc = logpost_common(h, nullptr, h->theta_hat, lp.data(), M)) return rc;
+    for (double v : lp) if (std::isnan(v)) return fail(SGM_EDIVERGED, "Chain diverged");   // cV.R:118-120
+    if (h->progress) h->progress(h->progress_user, 1, iter, lp.data(), M);
+    return SGM_OK;
+}
+
+// Mode finder sharded by data rows (north star).  Every SGD step each rank sums the log-likelihood gradients of
+// ITS part of the minibatch -- n / world rows drawn without replacement from its own row range (its local shard when the dataset
+// is sharded), or, in the validation mode, the caller's rows that fall into its range -- with the global N / n factor; rank 0
+// adds the prior gradient; one ncclAllReduce of the P-vector; every rank applies theta_hat += optStepsize * g.  The per-rank
+// sums come from the family's chain kernel in its gradient-estimate mode on an index list, so no new gradient code exists here.
+static int mode_finder_sharded(sgm_handle* h, const ChainArgs& tmpl, bool det, const int32_t* opt_idx) {
+    if (!h->comm || h->world < 2) return fail(SGM_ESTATE, "the row-sharded mode finder needs sgm_comm_init with world > 1");
+    if (!(h->flags & SGM_FLAG_SHARED_MODE)) return fail(SGM_EINVAL, "the row-sharded mode finder finds ONE mode for the whole job: set SGM_FLAG_SHARED_MODE");
+    const int W = h->world, r = h->rank;
+    const bool sharded_data = h->n_shards > 1;
+    const int64_t n_glob = sharded_data ? h->N * W : h->N;                    // rows of the whole dataset
+    const int64_t row0 = sharded_data ? 0 : h->N * r / W, row1 = sharded_data ? h->N : h->N * (r + 1) / W;   // this rank's rows (local numbering)
+    const int64_t glob0 = sharded_data ? h->N * r : row0;                     // global number of local row `row0`
+    const int64_t rows = row1 - row0;
+    const int n_r = h->n / W + (r < h->n % W ? 1 : 0);
+    if (!det && (n_r < 1 || n_r > rows)) return fail(SGM_EINVAL, "row-sharded mode finder: minibatch %d over %d ranks leaves rank %d with %d of its %lld rows", h->n, W, r, n_r, (long long)rows);
+    // validation mode: the caller's GLOBAL rows of every iteration, filtered to this rank's range (local numbering)
+    std::vector<int32_t> mine; std::vector<int64_t> off((size_t)h->n_iters_opt + 1, 0);
+    if (det) {
+        for (int64_t it = 0; it < h->n_iters_opt; ++it) {
+            for (int j = 0; j < h->n; ++j) {
+                const int64_t g = opt_idx[it * h->n + j];
+                if (g >= glob0 && g < glob0 + rows) mine.push_back((int32_t)(g - glob0 + row0));
+            }
+            off[it + 1] = (int64_t)mine.size();
+        }
+    }
+    const size_t idx_bytes = std::max<size_t>(det ? mine.size() : (size_t)n_r, 1) * sizeof(int32_t);
+    if (int rc = ensure_buf((void**)&h->d_idx, &h->d_idx_cap, idx_bytes)) return rc;
+    if (det && !mine.empty()) CU(cudaMemcpyAsync(h->d_idx, mine.data(), mine.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    DevBuf<float> gbuf;
+    DevBuf<int32_t> d_zero;
+    CU(gbuf.alloc((size_t)h->Pst)); CU(d_zero.alloc(1));
+    float* const g_sum = gbuf.p;
+    const int32_t* const zero_row = d_zero.p;
+    CU(cudaMemsetAsync(d_zero.p, 0, sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(g_sum, 0, (size_t)h->Pst * sizeof(float), h->stream));   // the kernels write the live elements only: the padding must be zero, not garbage
+    ChainArgs a = tmpl;
+    a.C = 1; a.theta = h->theta_hat; a.algo = ALGO_GRAD; a.cv = 0; a.L = 1; a.iters = 1; a.det = 1; a.noise = nullptr; a.noise_len = 0; a.store = nullptr;
+    a.N = (uint32_t)h->N; a.n_shards = 0; a.shard_ptr = nullptr;              // every row named below is a LOCAL row
+    const float corr = (float)((double)n_glob / (double)h->n);
+    const uint32_t bits = perm_bits((uint32_t)rows);
+    for (int64_t it = 0; it < h->n_iters_opt; ++it) {
+        int cnt = n_r;
+        const int32_t* d_list = h->d_idx;
+        if (det) { cnt = (int)(off[it + 1] - off[it]); d_list = h->d_idx + off[it]; }
+        else {
+            SGM_LAUNCH(opt_indices_kernel, (unsigned)cdiv(n_r, 128), 128, 0, h->stream, h->d_idx, n_r, (uint32_t)row0, (uint32_t)rows, bits, (uint32_t)r,
+                       word2_host((uint64_t)it, 1, 1), h->base.k0, h->base.k1);
+            CU(cudaGetLastError());
+        }
+        if (cnt > 0) {
+            a.idx = d_list; a.n = cnt; a.corr = corr; a.use_prior = (r == 0) ? h->use_prior : 0; a.mom = g_sum; a.step0 = (uint64_t)it;
+            if (int rc = launch_chain(h, a)) return rc;
+        } else if (r == 0 && h->use_prior) {
+            // rank 0 holds none of this minibatch's rows (possible in the validation mode only) but still owes the prior gradient:
+            // the estimate on one row with a zero N / n factor is exactly the prior term
+            a.idx = zero_row; a.n = 1; a.corr = 0.f; a.use_prior = 1; a.mom = g_sum; a.step0 = (uint64_t)it;
+            if (int rc = launch_chain(h, a)) return rc;
+        } else {
+            CU(cudaMemsetAsync(g_sum, 0, (size_t)h->Pst * sizeof(float), h->stream));
+        }
+        const int rc = g_nccl.AllReduce(g_sum, g_sum, (size_t)h->Pst, 7 /* ncclFloat32 */, 0 /* ncclSum */, h->comm, h->stream);
+        if (rc != 0) return fail(SGM_ECOMM, "ncclAllReduce (mode finder) failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        SGM_LAUNCH(opt_apply_kernel, (unsigned)cdiv(h->Pst, 256), 256, 0, h->stream, h->theta_hat, (const float*)g_sum, (const float*)nullptr, a.opt_lr, h->Pst, h->d_flag);
+        CU(cudaGetLastError());
+        h->last_launches += 2;
+        if ((it + 1) % 100 == 0) {
+            if (int rc2 = check_diverged(h, "Chain diverged")) return rc2;
+            if (!det) if (int rc2 = opt_checkpoint(h, 1, it + 1)) return rc2;
+        }
+    }
+    return check_diverged(h, "Chain diverged");
+}
+
 static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t* opt_idx, bool det) {
     if (!h) return fail(SGM_EINVAL, "null handle");
     if (int rc = set_device(h)) return rc;
@@ -1240,9 +1351,25 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
             }
             a.det = 1; a.idx = h->d_idx;
         }
-        if (h->n_iters_opt > 0) {
-            if (int rc = launch_chain(h, a)) return rc;
-            if (int rc = check_diverged(h, "Chain diverged")) return rc;   // cV.R:119
+        const bool sharded_finder = h->opt_sharded_finder && h->n_iters_opt > 0;
+        if (sharded_finder) {
+            if (int rc = mode_finder_sharded(h, a, det, opt_idx)) return rc;
+        } else if (h->n_iters_opt > 0) {
+            if (det) {   // validation mode: one launch over the caller's index table
+                if (int rc = launch_chain(h, a)) return rc;
+                if (int rc = check_diverged(h, "Chain diverged")) return rc;   // cV.R:119
+            } else {
+                // getMode's loop (cV.R:42-47) in launches of <= 100 iterations: after each one checkOptDivergence -- the log posterior
+                // estimate at theta_hat on a FRESH minibatch; NaN stops with "Chain diverged"; the value goes to the progress callback
+                for (int64_t done = 0; done < h->n_iters_opt;) {
+                    const int64_t chunk = std::min<int64_t>(100 - done % 100, h->n_iters_opt - done);
+                    a.step0 = (uint64_t)done; a.iters = (int)chunk;
+                    if (int rc = launch_chain(h, a)) return rc;
+                    done += chunk;
+                    if (int rc = check_diverged(h, "Chain diverged")) return rc;
+                    if (done % 100 == 0) if (int rc = opt_checkpoint(h, M, done)) return rc;
+                }
+            }
         }
         if (int rc = full_gradient(h)) return rc;
         h->base.hat_stride = (M == 1 && h->C > 1) ? 0 : h->Pst;
@@ -1436,10 +1563,12 @@ extern "C" int sgm_copy_chain(sgm_handle* h, double* out) {
     return SGM_OK;
 }
 
-static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta, double* out) {
+static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta, double* out, int chains) {
     if (int rc = set_device(h)) return rc;
     ChainArgs a = h->base;
     a.theta = const_cast<float*>(theta);
+    if (chains > 0) a.C = chains;   // the mode estimates: hat_count(h) states
+    const int Cn = a.C;
     if (idx) {
         const size_t ib = (size_t)h->C * h->n * sizeof(int32_t);
         if (int rc = ensure_buf((void**)&h->d_idx, &h->d_idx_cap, ib)) return rc;
@@ -1449,11 +1578,11 @@ static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta,
     const uint32_t word2 = (uint32_t)h->check_ctr;
     switch (h->model) {
         case SGM_MODEL_GAUSS_MEAN:
-            SGM_LAUNCH(small_logpost_kernel<SMALL_MODEL_GAUSS>, (unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream, a, word2, h->dout); break;
+            SGM_LAUNCH(small_logpost_kernel<SMALL_MODEL_GAUSS>, (unsigned)cdiv((int64_t)Cn * 32, 128), 128, 0, h->stream, a, word2, h->dout); break;
         case SGM_MODEL_MIXTURE2:
-            SGM_LAUNCH(small_logpost_kernel<SMALL_MODEL_MIX2>, (unsigned)cdiv((int64_t)h->C * 32, 128), 128, 0, h->stream, a, word2, h->dout); break;
+            SGM_LAUNCH(small_logpost_kernel<SMALL_MODEL_MIX2>, (unsigned)cdiv((int64_t)Cn * 32, 128), 128, 0, h->stream, a, word2, h->dout); break;
         case SGM_MODEL_LOGISTIC:
-            SGM_LAUNCH(logistic_logpost_kernel, h->C, 256, 0, h->stream, a, word2, theta, h->dout); break;
+            SGM_LAUNCH(logistic_logpost_kernel, Cn, 256, 0, h->stream, a, word2, theta, h->dout); break;
         case SGM_MODEL_SOFTMAX_NET: {
             const int rc = softmax_net_logpost(h->nn, a, word2, theta, h->dout, h->stream);
             if (rc != 0) return fail(SGM_ECUDA, "softmax net logpost: %s", cudaGetErrorString((cudaError_t)rc));
@@ -1461,8 +1590,15 @@ static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta,
         }
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, h->dout, (size_t)h->C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out, h->dout, (size_t)Cn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return SGM_OK;
+}
+
+// what sgm_init reports every 100 iterations of the mode finder (include/sgmcmc_b200.h)
+extern "C" int sgm_set_progress(sgm_handle* h, sgm_progress_fn fn, void* user) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    h->progress = fn; h->progress_user = user;
     return SGM_OK;
 }
 
@@ -1561,7 +1697,8 @@ extern "C" int sgm_set_option(sgm_handle* h, const char* key, int32_t value) {
     if (!h || !key) return fail(SGM_EINVAL, "null argument");
     struct Opt { const char* key; int* slot; int max; };
     const Opt opts[] = {{"logistic_kernel", &h->opt_logistic_kernel, 1}, {"gather", &h->opt_gather, 4}, {"fullgrad", &h->opt_fullgrad, 2},
-                        {"fullgrad_row0", &h->opt_row0, INT32_MAX}, {"fullgrad_row1", &h->opt_row1, INT32_MAX}};
+                        {"fullgrad_row0", &h->opt_row0, INT32_MAX}, {"fullgrad_row1", &h->opt_row1, INT32_MAX},
+                        {"sharded_mode_finder", &h->opt_sharded_finder, 1}};
     for (const Opt& o : opts)
         if (!strcmp(key, o.key)) {
             if (value < 0 || value > o.max) return fail(SGM_EINVAL, "option %s: value %d outside [0, %d]", key, value, o.max);

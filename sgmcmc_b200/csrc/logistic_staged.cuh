@@ -46,8 +46,11 @@ __device__ __forceinline__ float fdot4(const float4 a, const float4 b, float acc
 }
 
 __host__ __device__ inline int ls_row_stride4(int ld) { const int Q = ld >> 2; return (Q % 4 == 2) ? Q : (Q | 1); }
+// coefficients [n] are followed by the scratch block, which holds the per-warp mbarriers (8-byte objects): n is rounded up to an even
+// count there, or an ODD minibatch size would misalign them (a misaligned-address fault on the device; found by the emulated build)
+__host__ __device__ inline int ls_coef_slots(int n) { return (n + 1) & ~1; }
 static inline size_t ls_smem_bytes(int ld, int n) {
-    return sizeof(float) * ((size_t)n * 4 * ls_row_stride4(ld) + 3 * (size_t)ld + (size_t)n + 64);
+    return sizeof(float) * ((size_t)n * 4 * ls_row_stride4(ld) + 3 * (size_t)ld + (size_t)ls_coef_slots(n) + 64);
 }
 
 // scratch slots
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(LS_THREADS, 2) logistic_staged_kernel(const Ch
     const float SQRT_HALF = 0.70710678118654752440f;
     LogiStagedSmem sm;
     sm.rows = reinterpret_cast<float*>(smem_raw);
-    sm.th = sm.rows + (size_t)n * 4 * S; sm.hat = sm.th + ld; sm.grad = sm.hat + ld; sm.coef = sm.grad + ld; sm.scratch = sm.coef + n;
+    sm.th = sm.rows + (size_t)n * 4 * S; sm.hat = sm.th + ld; sm.grad = sm.hat + ld; sm.coef = sm.grad + ld; sm.scratch = sm.coef + ls_coef_slots(n);
     const uint32_t rows_s = smem_u32(sm.rows), th_s = smem_u32(sm.th), hat_s = smem_u32(sm.hat), coef_s = smem_u32(sm.coef);
     const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
     const bool noisy = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC || a.algo == ALGO_SGNHT);

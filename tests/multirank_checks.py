@@ -167,3 +167,63 @@ def peer_shards(rank: int, world: int, device: int = 0, case_name: str = "logist
     _lib.check(_lib.load().sgm_run(sh.handle, 5, 0))
     dist.barrier()
     return bad
+
+
+def sharded_mode_finder(rank: int, world: int, device: int = 0, case_name: str = "logistic54"):
+    """The *cv mode finder sharded by data rows (north star / SURVEY.md 8e row 3): with the SAME minibatch rows per SGD step
+    (validation mode) the sharded finder -- per-rank partial sums of the rows each rank owns, all-reduced every step -- must land on
+    the mode the single-process finder finds; with device RNG (stratified minibatches) it must move towards the mode too."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import distributed as D
+    from sgmcmc_b200 import validation as V
+    from tests.cases import make_case
+    case = make_case(case_name)
+    N, n, n_opt = case["N"], case["n"], 60
+    kw = dict(logPrior=case["logprior"], minibatchSize=n, seed=5, sharedMode=True, device=device, nItersOpt=n_opt, verbose=False, nChains=2)
+    bad = []
+    rs = np.random.RandomState(17)
+    opt_idx = np.stack([rs.choice(N, n, replace=False) for _ in range(n_opt)]).astype(np.int32)[None]   # [1 mode][n_opt][n]
+    opt_idx[0, 7] = np.sort(rs.choice(np.arange(N // world, N), n, replace=False))                         # one minibatch with no row on rank 0
+    layouts = ("replicated", "sharded") if case_name.startswith("logistic") else ("replicated",)   # peer-mapped shards: logistic family
+    for layout in layouts:
+        if layout == "replicated":
+            data = case["data"]
+        else:
+            per = N // world
+            data = {k: v[rank * per:(rank + 1) * per] for k, v in case["data"].items()}
+        sg = S.sgldcvSetup(case["loglik"], data, case["params"], case["eps"], case["opt_eps"] * 20, **kw)
+        if layout == "sharded":
+            D.attach_peer_shards(sg, rank, world)
+        D.comm_init(sg, rank, world)
+        V.setOption(sg, "sharded_mode_finder", 1)
+        V.initSessDeterministic(sg, None, opt_idx)
+        th, g = V.getMode(sg)
+        ref = S.sgldcvSetup(case["loglik"], case["data"], case["params"], case["eps"], case["opt_eps"] * 20, **kw)
+        V.initSessDeterministic(ref, None, opt_idx)
+        th_r, g_r = V.getMode(ref)
+        moved = np.abs(th_r[0] - np.concatenate([np.ravel(v, order="F") for v in case["params"].values()])).max()
+        err = np.abs(th - th_r).max()
+        if not err <= 1e-5 * max(np.abs(th_r).max(), moved):
+            bad.append(f"rank {rank}: {layout}: row-sharded mode finder vs single process: |d theta_hat| = {err:.3e} (the finder moved {moved:.3e})")
+        eg = np.abs(g - g_r).max() / max(1.0, np.abs(g_r).max())
+        if not eg < 1e-4:
+            bad.append(f"rank {rank}: {layout}: full gradient at the sharded finder's mode differs: {eg:.2e}")
+        # device RNG: stratified minibatches (n / world rows from every rank's own rows)
+        sg2 = S.sgldcvSetup(case["loglik"], data, case["params"], case["eps"], case["opt_eps"] * 20, **dict(kw, nItersOpt=200))
+        if layout == "sharded":
+            D.attach_peer_shards(sg2, rank, world)
+        D.comm_init(sg2, rank, world)
+        V.setOption(sg2, "sharded_mode_finder", 1)
+        S.initSess(sg2, verbose=False)
+        th2, g2 = V.getMode(sg2)
+        ref2 = S.sgldcvSetup(case["loglik"], case["data"], case["params"], case["eps"], case["opt_eps"] * 20, **dict(kw, nItersOpt=200))
+        S.initSess(ref2, verbose=False)
+        th2r, g2r = V.getMode(ref2)
+        # different minibatches, same target: the full-data gradient norm at the two modes must be of the same size (both descended)
+        n2, n2r = np.linalg.norm(g2[0]), np.linalg.norm(g2r[0])
+        if not (np.isfinite(th2).all() and n2 <= 1.5 * n2r + 1e-3):
+            bad.append(f"rank {rank}: {layout}: device-RNG sharded finder did not descend like the single-process one (|g| {n2:.3e} vs {n2r:.3e})")
+        if layout == "sharded":
+            for o in (sg, sg2):
+                D.detach_peer_shards(o)
+    return bad

@@ -59,3 +59,9 @@ def test_row_sharded_pass_with_a_shared_mode_every_family():
 
 def test_dataset_sharded_over_ranks_and_peer_mapped():
     _run(2, [("peer_shards", {})])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_mode_finder_sharded_by_rows(world):
+    """SURVEY.md 8e row 3 (the north star's "mode-finding pass, sharded by data rows with an NCCL allreduce of the d-vector")."""
+    _run(world, [("sharded_mode_finder", dict(case_name="logistic54" if world == 2 else "gauss2d"))])

@@ -32,7 +32,8 @@ def ran(lib, path: str) -> int:
 
 
 FAMILIES = ["gauss1d", "gauss2d", "gauss3d_fullcov", "gauss2d_flat", "mixture", "logistic5", "logistic54", "logistic130"]
-BENCHED = ["logistic54_n500", "logistic1024_n1024_N3000"]   # the template instantiations bench.py times (c3: R = 2; c5: <32, 9>)
+BENCHED = ["logistic54_n500", "logistic1024_n1024_N3000",   # the template instantiations bench.py times (c3: R = 2; c5: <32, 9>)
+           "logistic54_n101"]                               # an odd minibatch size (mbarrier alignment behind the coefficient array)
 
 
 @pytest.mark.parametrize("case_name", FAMILIES + BENCHED)
@@ -54,6 +55,10 @@ def test_device_rng_streams_match_oracle(case_name, algo, cv):
 def test_est_logpost_and_heldout(case_name):
     T.test_est_logpost_matches_oracle(None, case_name)
     T.test_heldout_loglik_matches_oracle(None, case_name)
+
+
+def test_mode_finder_cadence(capsys):
+    T.test_mode_finder_reports_and_checks_every_100_iterations(None, capsys)
 
 
 def test_chain_storage_layout_and_seeds():

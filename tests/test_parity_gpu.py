@@ -19,7 +19,9 @@ RTOL = 1e-5
 # logistic54_n500 and logistic1024_n1024_N3000 instantiate exactly the kernels bench.py times: logistic_staged_kernel<*, 2>
 # (c3: n = 500 -> two rows per lane) and logistic_chain_kernel<32, 9> + the long-row full-gradient stream (c5: d = 1024)
 CASES = ["gauss1d", "gauss2d", "gauss3d_fullcov", "gauss2d_flat", "mixture", "logistic5", "logistic54", "logistic130",
-         "logistic54_n500", "logistic1024_n1024_N3000", "softmaxnet_small", "softmaxnet"]
+         "logistic54_n500", "logistic1024_n1024_N3000", "logistic54_n101", "softmaxnet_small", "softmaxnet"]
+# logistic54_n101: an ODD minibatch size (the per-warp mbarriers of the short-row kernel sit behind the n coefficients: they were
+# misaligned for odd n until round 2 -- found by the CPU emulation of the kernel sources)
 
 
 def close(ours, ref, scale=None, rtol=RTOL, what=""):
@@ -245,3 +247,35 @@ def test_heldout_loglik_matches_oracle(lib, case_name):
     assert got.shape == (2,)
     for c in range(2):
         assert abs(got[c] - want) <= 2e-5 * abs(want) + 1e-3, (got[c], want)
+
+
+def test_mode_finder_reports_and_checks_every_100_iterations(lib, capsys):
+    """getMode / checkOptDivergence (R/controlVariates.R:42-47,114-124): every 100 optimiser iterations the log posterior estimate at
+    the mode estimate on a fresh minibatch; verbose prints "Iteration: i  Log posterior estimate: v"; NaN stops with "Chain diverged"."""
+    import sgmcmc_b200 as S
+    from oracle import rng
+    from sgmcmc_b200 import validation as V
+    from sgmcmc_b200._lib import SgmcmcError
+    case = make_case("logistic54")
+    seed = 99
+    dev = device_setup(case, "sgld", True, n_chains=1, seed=seed, n_iters_opt=250)
+    S.initSess(dev, verbose=True)
+    err = capsys.readouterr().err
+    lines = [l for l in err.splitlines() if l.startswith("Iteration:")]
+    assert "Finding initial MAP estimates..." in err
+    assert [l.split()[1] for l in lines] == ["100", "200"], err
+    assert all(np.isfinite(float(l.split()[-1])) for l in lines)
+    # the reported number IS estLogPost(theta_hat) on the minibatch of the check stream: reproduce the first one with the oracle
+    dev100 = device_setup(case, "sgld", True, n_chains=1, seed=seed, n_iters_opt=100)
+    S.initSess(dev100, verbose=True)
+    line = [l for l in capsys.readouterr().err.splitlines() if l.startswith("Iteration: 100")][0]
+    th_hat, _ = V.getMode(dev100)
+    idx = rng.minibatch_indices(seed, 0, 1, rng.TAG_CHECK_INDEX, case["N"], case["n"])
+    post = OS.Posterior(case["om"], case["N"], case["n"], np.float64, use_prior=True)
+    want = post.est_logpost(OS.unflat(th_hat[0], case["params"]), OS.take(case["data"], idx))
+    assert abs(float(line.split()[-1]) - want) <= 1e-5 * abs(want) + 1e-3, (line, want)
+    # divergence: an absurd optimiser step
+    bad = dict(make_case("gauss2d"), opt_eps=1.0)   # |1 - optStepsize N| >> 1: the iterates overflow within a few dozen steps
+    dev_bad = device_setup(bad, "sgld", True, n_chains=2, seed=seed, n_iters_opt=300)
+    with pytest.raises(SgmcmcError, match="Chain diverged"):
+        S.initSess(dev_bad, verbose=False)
