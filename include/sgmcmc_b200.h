@@ -211,6 +211,8 @@ int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops);
  *   "fullgrad"         logistic full-data gradient: 1 = tensor-core contractions, 2 = SIMT row-chunk x mode grid
  *   "fullgrad_row0", "fullgrad_row1"   row1 > 0: the full-data pass sums rows [row0, row1) only (what one rank of a row-sharded
  *                      job computes), without a communicator: single-GPU pre-flight of arbitrary shard starts
+ *   "small_kernel"     Gaussian families: 1 = gather rows from global memory even when the dataset fits in shared memory,
+ *                      2 = stage the dataset in shared memory even for launches too short to amortise it
  *   "sharded_mode_finder"  1 = the *cv mode finder sharded by data rows: every SGD step each rank sums the gradients of its part of the
  *                      minibatch (drawn from its own rows) and the P-vector is all-reduced (needs sgm_comm_init and
  *                      SGM_FLAG_SHARED_MODE; default: every rank runs the same finder on the rows it can reach, no communication)

@@ -150,6 +150,7 @@ struct sgm_handle {
     int opt_logistic_kernel = 0;   // 1: generic warp-group kernel even for short rows
     int opt_gather = 0;            // short-row kernel: 1 cp.async, 2 TMA bulk copy per row, 3 mixed, 4 TMA tile::gather4
     int opt_fullgrad = 0;          // logistic full-data gradient: 1 tensor-core contractions, 2 SIMT row-chunk x mode grid
+    int opt_small_kernel = 0;      // Gaussian families: 1 = rows from global memory even when the dataset fits in shared memory
     int opt_sharded_finder = 0;    // 1: mode finder sharded by data rows (each rank draws its part of every minibatch from its own rows, the
                                    // P-vector is all-reduced every SGD step); needs sgm_comm_init + SGM_FLAG_SHARED_MODE
     int opt_row0 = 0, opt_row1 = 0;   // row1 > 0: the full-data pass sums rows [row0, row1) only -- what rank r of a row-sharded job does,
@@ -782,19 +783,49 @@ static int launch_logistic_fullgrad(sgm_handle* h, int64_t row0, int64_t row1, i
     LOGI_DISPATCH(launch_logistic_fullgrad_gv, h, row0, row1, M, theta_hat);
 }
 
+// Gaussian families: dataset small enough to live in shared memory (and a whole number of 16-byte TMA units)?
+static bool small_use_smem(const sgm_handle* h, const ChainArgs& a) {
+    if (h->opt_small_kernel == 1) return false;
+    const size_t bytes = (size_t)a.N * a.ld * sizeof(float);
+    // staging the whole dataset pays off once a launch gathers more than it stages: not for one step of one chain (sgmcmcStep)
+    const bool enough_work = (int64_t)a.C * (a.iters > 0 ? a.iters : 1) * a.L * a.n * a.ld * 4 >= (int64_t)bytes;
+    return a.X == h->X && bytes % 16 == 0 && bytes <= SMALL_SMEM_MAX_BYTES && (enough_work || h->opt_small_kernel == 2);
+}
+
 // one launch of the family's chain kernel
 static int launch_chain(sgm_handle* h, const ChainArgs& a) {
     h->last_launches += 1;
     switch (h->model) {
         case SGM_MODEL_GAUSS_MEAN:
         case SGM_MODEL_MIXTURE2: {
-            const int threads = 128;
             int sms = 0;
             CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            const bool gauss = h->model == SGM_MODEL_GAUSS_MEAN, narrow = h->d <= 2;   // d <= 2 (the vignettes): register arrays of 2, not 8, entries per tensor
+            if (small_use_smem(h, a)) {
+                // the dataset staged in shared memory once per CTA, 16 chains per CTA
+                const size_t smem = small_smem_bytes(a.N, a.ld);
+                int64_t grid = cdiv((int64_t)a.C * 32, SMALL_SMEM_THREADS);
+                if (grid > (int64_t)sms * 2) grid = (int64_t)sms * 2;
+#define SMALL_SMEM_LAUNCH(M, D)                                                                                                          \
+    do {                                                                                                                                 \
+        CU(cudaFuncSetAttribute((small_chain_kernel<M, true, D>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        SGM_LAUNCH((small_chain_kernel<M, true, D>), (unsigned)grid, SMALL_SMEM_THREADS, smem, h->stream, a);                           \
+    } while (0)
+                if (gauss && narrow) SMALL_SMEM_LAUNCH(SMALL_MODEL_GAUSS, 2);
+                else if (gauss) SMALL_SMEM_LAUNCH(SMALL_MODEL_GAUSS, SMALL_MAXD);
+                else if (narrow) SMALL_SMEM_LAUNCH(SMALL_MODEL_MIX2, 2);
+                else SMALL_SMEM_LAUNCH(SMALL_MODEL_MIX2, SMALL_MAXD);
+#undef SMALL_SMEM_LAUNCH
+                CU(cudaGetLastError());
+                return SGM_OK;
+            }
+            const int threads = 128;
             int64_t grid = cdiv((int64_t)a.C * 32, threads);
             if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
-            if (h->model == SGM_MODEL_GAUSS_MEAN) SGM_LAUNCH(small_chain_kernel<SMALL_MODEL_GAUSS>, (unsigned)grid, threads, 0, h->stream, a);
-            else SGM_LAUNCH(small_chain_kernel<SMALL_MODEL_MIX2>, (unsigned)grid, threads, 0, h->stream, a);
+            if (gauss && narrow) SGM_LAUNCH((small_chain_kernel<SMALL_MODEL_GAUSS, false, 2>), (unsigned)grid, threads, 0, h->stream, a);
+            else if (gauss) SGM_LAUNCH((small_chain_kernel<SMALL_MODEL_GAUSS, false, SMALL_MAXD>), (unsigned)grid, threads, 0, h->stream, a);
+            else if (narrow) SGM_LAUNCH((small_chain_kernel<SMALL_MODEL_MIX2, false, 2>), (unsigned)grid, threads, 0, h->stream, a);
+            else SGM_LAUNCH((small_chain_kernel<SMALL_MODEL_MIX2, false, SMALL_MAXD>), (unsigned)grid, threads, 0, h->stream, a);
             CU(cudaGetLastError());
             return SGM_OK;
         }
@@ -1698,7 +1729,7 @@ extern "C" int sgm_set_option(sgm_handle* h, const char* key, int32_t value) {
     struct Opt { const char* key; int* slot; int max; };
     const Opt opts[] = {{"logistic_kernel", &h->opt_logistic_kernel, 1}, {"gather", &h->opt_gather, 4}, {"fullgrad", &h->opt_fullgrad, 2},
                         {"fullgrad_row0", &h->opt_row0, INT32_MAX}, {"fullgrad_row1", &h->opt_row1, INT32_MAX},
-                        {"sharded_mode_finder", &h->opt_sharded_finder, 1}};
+                        {"sharded_mode_finder", &h->opt_sharded_finder, 1}, {"small_kernel", &h->opt_small_kernel, 2}};
     for (const Opt& o : opts)
         if (!strcmp(key, o.key)) {
             if (value < 0 || value > o.max) return fail(SGM_EINVAL, "option %s: value %d outside [0, %d]", key, value, o.max);
@@ -1769,9 +1800,16 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
         case SGM_MODEL_MIXTURE2: {
             if (h->d > SMALL_MAXD) return fail(SGM_EINVAL, "Gaussian families support d <= %d", SMALL_MAXD);
             h->ld = h->d; h->P = h->Pst = (h->model == SGM_MODEL_MIXTURE2 ? 2 : 1) * h->d;
-            int64_t grid = cdiv((int64_t)h->C * 32, 128);
-            if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
-            po.launch("small_chain_kernel", grid, 1, 1, 128, 0, 0, "one warp per chain");
+            const size_t dbytes = (size_t)h->N * h->ld * sizeof(float);
+            if (dbytes % 16 == 0 && dbytes <= SMALL_SMEM_MAX_BYTES) {
+                int64_t grid = cdiv((int64_t)h->C * 32, SMALL_SMEM_THREADS);
+                if (grid > (int64_t)sms * 2) grid = (int64_t)sms * 2;
+                po.launch("small_chain_kernel<smem>", grid, 1, 1, SMALL_SMEM_THREADS, small_smem_bytes(h->N, h->ld), 0, "one warp per chain; dataset staged in shared memory once per CTA (TMA bulk copies)");
+            } else {
+                int64_t grid = cdiv((int64_t)h->C * 32, 128);
+                if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
+                po.launch("small_chain_kernel", grid, 1, 1, 128, 0, 0, "one warp per chain; rows from global memory");
+            }
             if (h->cv) {
                 int64_t gx = cdiv(row1 - row0, 256 * 4); if (gx > sms * 8) gx = sms * 8; if (gx < 1) gx = 1;
                 po.launch("small_chain_kernel (mode finder)", cdiv((int64_t)M * 32, 128), 1, 1, 128, 0, 0);

@@ -19,34 +19,47 @@ constexpr int SMALL_MODEL_MIX2 = 2;
 // Sum over the minibatch of the per-datum log-likelihood gradients at `th`
 // (and at `hat` when cv), all-reduced over the warp.  Rows are either the first n
 // images of the keyed permutation (device sampling) or caller-supplied.
-template <int MODEL>
-__device__ __forceinline__ void small_minibatch_sums(const ChainArgs& a, int lane, const Perm& perm,
+// SMEM: `base` is the CTA's shared-memory copy of the whole dataset (rows of ld floats); otherwise the dataset in global memory
+template <int MODEL, bool SMEM, int D>
+__device__ __forceinline__ void small_minibatch_sums(const ChainArgs& a, const float* __restrict__ base, int lane, const Perm& perm,
                                                      const int32_t* __restrict__ idx,
-                                                     const float (&th)[SMALL_MAXP], const float (&hat)[SMALL_MAXP],
-                                                     float (&s)[SMALL_MAXP], float (&sh)[SMALL_MAXP]) {
+                                                     const float (&th)[(2 * D)], const float (&hat)[(2 * D)],
+                                                     float (&s)[(2 * D)], float (&sh)[(2 * D)]) {
     const int d = a.d;
 #pragma unroll
-    for (int k = 0; k < SMALL_MAXP; ++k) { s[k] = 0.f; sh[k] = 0.f; }
+    for (int k = 0; k < (2 * D); ++k) { s[k] = 0.f; sh[k] = 0.f; }
     for (int j = lane; j < a.n; j += 32) {
         const uint32_t row = idx ? (uint32_t)idx[j] : perm_at(perm, (uint32_t)j);
-        const float* __restrict__ xr = a.X + (size_t)row * a.ld;
-        float x[SMALL_MAXD];
+        const float* __restrict__ xr = base + (size_t)row * a.ld;
+        float x[D];
+        if (SMEM) {
+            if (a.ld == 2) {   // the vignette shape: one 8-byte shared load per row
+                const float2 v = *reinterpret_cast<const float2*>(xr);
+                x[0] = v.x; x[1] = v.y;
 #pragma unroll
-        for (int k = 0; k < SMALL_MAXD; ++k) x[k] = (k < d) ? __ldg(xr + k) : 0.f;
+                for (int k = 2; k < D; ++k) x[k] = 0.f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < D; ++k) x[k] = (k < d) ? xr[k] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[k] = (k < d) ? __ldg(xr + k) : 0.f;
+        }
         if (MODEL == SMALL_MODEL_GAUSS) {
 #pragma unroll
-            for (int k = 0; k < SMALL_MAXD; ++k)
+            for (int k = 0; k < D; ++k)
                 if (k < d) { s[k] += x[k] - th[k]; if (a.cv) sh[k] += x[k] - hat[k]; }
         } else {
             // responsibilities r_k = softmax_k(-0.5 |x - theta_k|^2) (equal weights cancel)
             float q1 = 0.f, q2 = 0.f, h1 = 0.f, h2 = 0.f;
 #pragma unroll
-            for (int k = 0; k < SMALL_MAXD; ++k)
+            for (int k = 0; k < D; ++k)
                 if (k < d) {
-                    const float e1 = x[k] - th[k], e2 = x[k] - th[SMALL_MAXD + k];
+                    const float e1 = x[k] - th[k], e2 = x[k] - th[D + k];
                     q1 += e1 * e1; q2 += e2 * e2;
                     if (a.cv) {
-                        const float f1 = x[k] - hat[k], f2 = x[k] - hat[SMALL_MAXD + k];
+                        const float f1 = x[k] - hat[k], f2 = x[k] - hat[D + k];
                         h1 += f1 * f1; h2 += f2 * f2;
                     }
                 }
@@ -56,39 +69,39 @@ __device__ __forceinline__ void small_minibatch_sums(const ChainArgs& a, int lan
             float g1 = 0.f, g2 = 0.f;
             if (a.cv) { g1 = 1.0f / (1.0f + expf(0.5f * (h1 - h2))); g2 = 1.0f - g1; }
 #pragma unroll
-            for (int k = 0; k < SMALL_MAXD; ++k)
+            for (int k = 0; k < D; ++k)
                 if (k < d) {
                     s[k] += p1 * (x[k] - th[k]);
-                    s[SMALL_MAXD + k] += p2 * (x[k] - th[SMALL_MAXD + k]);
+                    s[D + k] += p2 * (x[k] - th[D + k]);
                     if (a.cv) {
                         sh[k] += g1 * (x[k] - hat[k]);
-                        sh[SMALL_MAXD + k] += g2 * (x[k] - hat[SMALL_MAXD + k]);
+                        sh[D + k] += g2 * (x[k] - hat[D + k]);
                     }
                 }
         }
     }
 #pragma unroll
-    for (int k = 0; k < SMALL_MAXP; ++k) {
-        const bool live = (k % SMALL_MAXD) < d && (MODEL == SMALL_MODEL_MIX2 || k < SMALL_MAXD);
+    for (int k = 0; k < (2 * D); ++k) {
+        const bool live = (k % D) < d && (MODEL == SMALL_MODEL_MIX2 || k < D);
         if (live) { s[k] = warp_sum(s[k]); if (a.cv) sh[k] = warp_sum(sh[k]); }
     }
 }
 
 // d estLogPost / d theta (R/setup.R:116-125) from the minibatch sums.
-template <int MODEL>
-__device__ __forceinline__ void small_grad_from_sums(const ChainArgs& a, const float (&th)[SMALL_MAXP],
-                                                     const float (&s)[SMALL_MAXP], float (&g)[SMALL_MAXP]) {
+template <int MODEL, int D>
+__device__ __forceinline__ void small_grad_from_sums(const ChainArgs& a, const float (&th)[(2 * D)],
+                                                     const float (&s)[(2 * D)], float (&g)[(2 * D)]) {
     const int d = a.d;
 #pragma unroll
-    for (int k = 0; k < SMALL_MAXP; ++k) {
-        const int kk = k % SMALL_MAXD;
+    for (int k = 0; k < (2 * D); ++k) {
+        const int kk = k % D;
         g[k] = 0.f;
-        if (kk >= d || (MODEL == SMALL_MODEL_GAUSS && k >= SMALL_MAXD)) continue;
+        if (kk >= d || (MODEL == SMALL_MODEL_GAUSS && k >= D)) continue;
         float ll = s[k];
         if (MODEL == SMALL_MODEL_GAUSS) {
             ll = 0.f;
 #pragma unroll
-            for (int m = 0; m < SMALL_MAXD; ++m)
+            for (int m = 0; m < D; ++m)
                 if (m < d) ll += a.prec[kk * SMALL_MAXD + m] * s[m];
         }
         const float pr = a.use_prior ? -th[k] * a.prior_inv_var : 0.f;
@@ -97,25 +110,54 @@ __device__ __forceinline__ void small_grad_from_sums(const ChainArgs& a, const f
 }
 
 // Register slot k <-> flat parameter index (mixture: two tensors of d entries each).
-template <int MODEL>
+template <int MODEL, int D = SMALL_MAXD>
 __device__ __forceinline__ int small_flat_of_slot(int k, int d) {
     if (MODEL == SMALL_MODEL_GAUSS) return k < d ? k : -1;
-    const int t = k / SMALL_MAXD, kk = k % SMALL_MAXD;
+    const int t = k / D, kk = k % D;
     return kk < d ? t * d + kk : -1;
 }
 
-template <int MODEL>
-__global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
+constexpr int SMALL_SMEM_THREADS = 512;                 // dataset-in-shared-memory variant: 16 chains (warps) per CTA, 2 CTAs per SM
+constexpr size_t SMALL_SMEM_MAX_BYTES = 100 * 1024;     // dataset size up to which two CTAs (two copies) fit one SM
+constexpr uint32_t SMALL_SMEM_CHUNK = 32 * 1024;        // bytes per TMA bulk copy
+static inline size_t small_smem_bytes(int64_t N, int ld) { return (size_t)N * ld * sizeof(float) + 16; }
+
+// D: the dimension the register arrays are sized for (2 for the vignettes' d <= 2: a quarter of the registers of the general D = 8
+// instantiation, four times the resident warps).
+// SMEM = true: the whole dataset (80 KB at the vignettes' N = 1e4, d = 2) is staged in shared memory ONCE per CTA by TMA bulk copies
+// (mbarrier-tracked), and every gathered row is then one shared-memory load -- SURVEY.md section 7 ("rows of config 1-2 are 8 B: use
+// float2 loads of an SMEM-resident dataset").  SMEM = false: rows come from global memory through the read-only path (datasets that
+// do not fit, or whose byte size is not a multiple of 16).
+template <int MODEL, bool SMEM, int D>
+__global__ void __launch_bounds__(SMEM ? SMALL_SMEM_THREADS : 128) small_chain_kernel(const ChainArgs a) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     const int T = (MODEL == SMALL_MODEL_GAUSS) ? 1 : 2;
     const float SQRT_HALF = 0.70710678118654752440f;
+    const float* __restrict__ rows_base = a.X;
+    if (SMEM) {
+        SGM_DYN_SMEM(unsigned char, small_smem, 128);
+        const uint32_t data_s = smem_u32(small_smem);
+        const uint32_t bytes = (uint32_t)a.N * (uint32_t)a.ld * 4u;                 // host guarantees: a multiple of 16, <= SMALL_SMEM_MAX_BYTES
+        const uint32_t bar = data_s + ((bytes + 7u) & ~7u);
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(bar, bytes);
+            for (uint32_t off = 0; off < bytes; off += SMALL_SMEM_CHUNK)
+                bulk_g2s(data_s + off, reinterpret_cast<const unsigned char*>(a.X) + off, (bytes - off < SMALL_SMEM_CHUNK) ? bytes - off : SMALL_SMEM_CHUNK, bar);
+        }
+        __syncthreads();          // the barrier is initialised before anybody polls it
+        mbar_wait(bar, 0);
+        rows_base = reinterpret_cast<const float*>(small_smem);
+        SGM_EMU_NOTE("small_chain:smem");
+    }
     for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < a.C; c += warps_per_grid) {
-        float th[SMALL_MAXP], mo[SMALL_MAXP], hat[SMALL_MAXP], gh0[SMALL_MAXP];
+        float th[(2 * D)], mo[(2 * D)], hat[(2 * D)], gh0[(2 * D)];
         float zeta[2];
 #pragma unroll
-        for (int k = 0; k < SMALL_MAXP; ++k) {
-            const int f = small_flat_of_slot<MODEL>(k, a.d);
+        for (int k = 0; k < (2 * D); ++k) {
+            const int f = small_flat_of_slot<MODEL, D>(k, a.d);
             th[k] = f >= 0 ? a.theta[(size_t)c * a.Pst + f] : 0.f;
             mo[k] = f >= 0 ? a.mom[(size_t)c * a.Pst + f] : 0.f;
             hat[k] = (f >= 0 && a.cv) ? a.theta_hat[(size_t)c * a.hat_stride + f] : 0.f;
@@ -133,9 +175,9 @@ __global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
             };
             if (a.algo == ALGO_SGHMC) {  // momentum refresh, R/dynamics.R:62, R/update.R:52-57
 #pragma unroll
-                for (int k = 0; k < SMALL_MAXP; ++k) {
-                    const int f = small_flat_of_slot<MODEL>(k, a.d);
-                    if (f >= 0) mo[k] = 0.5f * (a.tc.sqrt_2eps[k / SMALL_MAXD] * noise_at(f, 0));
+                for (int k = 0; k < (2 * D); ++k) {
+                    const int f = small_flat_of_slot<MODEL, D>(k, a.d);
+                    if (f >= 0) mo[k] = 0.5f * (a.tc.sqrt_2eps[k / D] * noise_at(f, 0));
                 }
             }
             for (int l = 0; l < a.L; ++l) {
@@ -147,18 +189,18 @@ __global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
                 const bool seidel = (a.algo == ALGO_SGLD || a.algo == ALGO_SGHMC);
                 const int passes = seidel ? T : 1;
                 for (int pass = 0; pass < passes; ++pass) {
-                    float s[SMALL_MAXP], sh[SMALL_MAXP], g[SMALL_MAXP], gh[SMALL_MAXP];
-                    small_minibatch_sums<MODEL>(a, lane, perm, idx, th, hat, s, sh);
-                    small_grad_from_sums<MODEL>(a, th, s, g);
+                    float s[(2 * D)], sh[(2 * D)], g[(2 * D)], gh[(2 * D)];
+                    small_minibatch_sums<MODEL, SMEM, D>(a, rows_base, lane, perm, idx, th, hat, s, sh);
+                    small_grad_from_sums<MODEL, D>(a, th, s, g);
                     if (a.cv) {
-                        small_grad_from_sums<MODEL>(a, hat, sh, gh);
+                        small_grad_from_sums<MODEL, D>(a, hat, sh, gh);
 #pragma unroll
-                        for (int k = 0; k < SMALL_MAXP; ++k) g[k] = (gh0[k] - gh[k]) + g[k];  // R/setup.R:58
+                        for (int k = 0; k < (2 * D); ++k) g[k] = (gh0[k] - gh[k]) + g[k];  // R/setup.R:58
                     }
 #pragma unroll
-                    for (int k = 0; k < SMALL_MAXP; ++k) {
-                        const int t = k / SMALL_MAXD;
-                        const int f = small_flat_of_slot<MODEL>(k, a.d);
+                    for (int k = 0; k < (2 * D); ++k) {
+                        const int t = k / D;
+                        const int f = small_flat_of_slot<MODEL, D>(k, a.d);
                         if (f < 0 || (seidel && t != pass)) continue;
                         if (a.algo == ALGO_SGLD) {
                             const float z = noise_at(f, sub);
@@ -179,10 +221,10 @@ __global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
                     if (a.algo == ALGO_SGNHT) {  // theta pass then thermostat pass, R/update.R:75-80
                         float uu[2] = {0.f, 0.f};
 #pragma unroll
-                        for (int k = 0; k < SMALL_MAXP; ++k) {
-                            if (small_flat_of_slot<MODEL>(k, a.d) < 0) continue;
+                        for (int k = 0; k < (2 * D); ++k) {
+                            if (small_flat_of_slot<MODEL, D>(k, a.d) < 0) continue;
                             th[k] += mo[k];
-                            uu[k / SMALL_MAXD] += mo[k] * mo[k];
+                            uu[k / D] += mo[k] * mo[k];
                         }
 #pragma unroll
                         for (int t = 0; t < T; ++t) zeta[t] += uu[t] / (float)a.d - a.tc.eps[t];
@@ -190,8 +232,8 @@ __global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
                 }
             }
 #pragma unroll
-            for (int k = 0; k < SMALL_MAXP; ++k) {
-                const int f = small_flat_of_slot<MODEL>(k, a.d);
+            for (int k = 0; k < (2 * D); ++k) {
+                const int f = small_flat_of_slot<MODEL, D>(k, a.d);
                 if (f < 0) continue;
                 bad |= !isfinite(th[k]);
                 if (a.store && lane == (f & 31))
@@ -200,8 +242,8 @@ __global__ void __launch_bounds__(128) small_chain_kernel(const ChainArgs a) {
         }
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < SMALL_MAXP; ++k) {
-                const int f = small_flat_of_slot<MODEL>(k, a.d);
+            for (int k = 0; k < (2 * D); ++k) {
+                const int f = small_flat_of_slot<MODEL, D>(k, a.d);
                 if (f < 0) continue;
                 a.theta[(size_t)c * a.Pst + f] = th[k];
                 a.mom[(size_t)c * a.Pst + f] = mo[k];

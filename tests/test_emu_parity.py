@@ -57,6 +57,13 @@ def test_est_logpost_and_heldout(case_name):
     T.test_heldout_loglik_matches_oracle(None, case_name)
 
 
+@pytest.mark.parametrize("case_name,algo", [("gauss2d", "sgld"), ("mixture", "sghmc"), ("gauss3d_fullcov", "sgnht"), ("gauss1d", "sgld")])
+def test_small_models_shared_memory_dataset(emulated_library, case_name, algo):
+    before = ran(emulated_library, "small_chain:smem")
+    T.test_small_models_shared_memory_dataset_equals_global_gather(None, case_name, algo)
+    assert ran(emulated_library, "small_chain:smem") >= before + 2, "the default dispatch did not pick the shared-memory variant for a 60-iteration launch"
+
+
 def test_mode_finder_cadence(capsys):
     T.test_mode_finder_reports_and_checks_every_100_iterations(None, capsys)
 
