@@ -154,6 +154,16 @@ int sgm_step_deterministic(sgm_handle* h, const int32_t* idx, const float* noise
  * Callers loop in chunks (<= 100) to print progress at the reference's cadence. */
 int sgm_run(sgm_handle* h, int64_t n_iters, int store);
 
+/* runSGMCMC (R/update.R:145-163) in ONE call: n_iters sgmcmcSteps, every post-update state stored (storeState, R/storage.R:54-60) and
+ * the whole chain written to out in the layout of sgm_copy_chain.  The chain leaves the device WHILE later iterations run: device
+ * storage is two blocks of <= check_every iterations; block k is transposed and copied (as float32: half the PCIe bytes) on a second
+ * stream and widened to double by host threads while block k + 1 is being sampled, so device memory stays bounded and the copy-out
+ * hides behind the kernel.  Every check_every iterations (100 in the reference; 0 = never) checkDivergence (R/update.R:197-207) runs on
+ * the device: estLogPost on a fresh minibatch; NaN returns SGM_EDIVERGED ("Chain diverged, try decreasing stepsize"), otherwise the
+ * values go to the progress callback (sgm_set_progress, phase = 2, one estimate per chain).  The device-resident chain of sgm_run
+ * (sgm_chain_length / sgm_copy_chain) is not touched. */
+int sgm_sample(sgm_handle* h, int64_t n_iters, int32_t check_every, double* out);
+
 /* ---- reading results ------------------------------------------------------------- */
 
 /* getParams (R/storage.R:37-39): [n_chains][P] doubles, flat parameter order. */

@@ -61,6 +61,7 @@ SYMBOLS = {
     "sgm_step": (C.c_int, [_H]),
     "sgm_step_deterministic": (C.c_int, [_H, _PI, _PF]),
     "sgm_run": (C.c_int, [_H, C.c_int64, C.c_int]),
+    "sgm_sample": (C.c_int, [_H, C.c_int64, C.c_int32, _PD]),
     "sgm_get_params": (C.c_int, [_H, _PD]),
     "sgm_get_state": (C.c_int, [_H, _PD, _PD]),
     "sgm_get_mode": (C.c_int, [_H, _PD, _PD]),

@@ -326,11 +326,17 @@ def getChains(sgmcmc: Sgmcmc, reuse_buffer: bool = False) -> Dict[str, np.ndarra
         if reuse_buffer:
             sgmcmc._chain_buf = buf
     _lib.check(lib.sgm_copy_chain(sgmcmc.handle, _dptr(buf)))
+    return _chain_views(sgmcmc, buf, iters)
+
+
+def _chain_views(sgmcmc: Sgmcmc, buf: np.ndarray, iters: int) -> Dict[str, np.ndarray]:
+    """The library's chain buffer ([chain][flat parameter][iteration] doubles) as the reference's storage list (R/storage.R:42-51):
+    per parameter a zero-copy view (nIters, dims...); scalars give (nIters, 1); nChains > 1 adds a leading chain axis."""
+    C_, P = sgmcmc.nChains, sgmcmc.P
     out, o = {}, 0
     for k, shp in sgmcmc.paramShapes.items():
         shp = tuple(shp) if len(shp) else (1,)
         sz = int(np.prod(shp))
-        # chain c, this parameter: a column-major (iters, dims...) block at offset (c * P + o) * iters
         strides = [8]
         for dim in (iters,) + shp[:-1]:
             strides.append(strides[-1] * dim)
@@ -341,23 +347,28 @@ def getChains(sgmcmc: Sgmcmc, reuse_buffer: bool = False) -> Dict[str, np.ndarra
 
 
 def runSGMCMC(sgmcmc: Sgmcmc, paramsRaw, options) -> Dict[str, np.ndarray]:
-    """R/update.R:145-163 with the loop moved onto the device in chunks of 100 iterations
-    (the reference's divergence-check / progress cadence)."""
+    """R/update.R:145-163.  The loop, the per-iteration storeState and the divergence check every 100 iterations all run on the device
+    inside ONE library call (sgm_sample); the chain streams to the host while later iterations are sampled."""
     lib = _lib.load()
-    sess = initSess(sgmcmc, options["verbose"])
+    verbose = options["verbose"]
+    initSess(sgmcmc, verbose)
     nIters = int(options["nIters"])
-    _lib.check(lib.sgm_reset_chain(sgmcmc.handle))
-    _lib.check(lib.sgm_reserve_chain(sgmcmc.handle, nIters))
-    if options["verbose"]:
+    if verbose:
         _message("\nSimulating from SGMCMC algorithm...")
-    done = 0
-    while done < nIters:
-        chunk = min(100 - done % 100, nIters - done)
-        _lib.check(lib.sgm_run(sgmcmc.handle, chunk, 1))
-        done += chunk
-        if done % 100 == 0:
-            checkDivergence(sess, sgmcmc, done, options["verbose"])
-    return getChains(sgmcmc)
+
+    def report(_user, phase, it, lp, n):   # checkDivergence's progress line (R/update.R:204-206)
+        if verbose and phase == 2:
+            v = lp[0] if n == 1 else float(np.mean([lp[i] for i in range(n)]))
+            _message(f"Iteration: {it}\t\tLog posterior estimate: {v}")
+
+    cb = _lib.PROGRESS_FN(report)
+    buf = np.empty(sgmcmc.nChains * sgmcmc.P * nIters, dtype=np.float64)
+    _lib.check(lib.sgm_set_progress(sgmcmc.handle, C.cast(cb, C.c_void_p), None))
+    try:
+        _lib.check(lib.sgm_sample(sgmcmc.handle, nIters, 100, _dptr(buf)))
+    finally:
+        lib.sgm_set_progress(sgmcmc.handle, None, None)
+    return _chain_views(sgmcmc, buf, nIters)
 
 
 # ---- one-shot samplers (R/sgld.R:50-58, sghmc.R:40-48, sgnht.R:38-46, *cv) ----------------------

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <thread>
+#include <algorithm>
 #include <vector>
 #include <dlfcn.h>
 #include <cuda.h>
@@ -126,6 +128,18 @@ struct sgm_handle {
     float* d_noise = nullptr; size_t d_noise_cap = 0;
     float* store = nullptr; int64_t store_cap = 0, store_len = 0;
     cudaStream_t stream = nullptr;
+    // sgm_sample: chain streamed to the host while later iterations run (double-buffered blocks)
+    struct Pipe {
+        cudaStream_t copy = nullptr;
+        float* d_store[2] = {nullptr, nullptr};   // [blk][C][P]   written by the chain kernel
+        float* d_T[2] = {nullptr, nullptr};       // [C][P][blk]   transposed
+        float* h_T[2] = {nullptr, nullptr};       // pinned host copies of d_T
+        double* d_lp[2] = {nullptr, nullptr};     // [C] divergence-check log posteriors
+        double* h_lp[2] = {nullptr, nullptr};
+        int* h_flag[2] = {nullptr, nullptr};
+        cudaEvent_t ran[2] = {nullptr, nullptr}, transposed[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+        int64_t blk = 0;
+    } pipe;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0; int last_launches = 0;
     float fullgrad_ms = 0; int64_t fullgrad_bytes = 0;
@@ -226,9 +240,11 @@ __global__ void momentum_init_kernel(float* __restrict__ mom, int C, int Pst, in
     mom[i] = tc.sqrt_eps[tensor_of[e]] * z;
 }
 
-// [iter][C][P] float -> [C][P][iter] double (R layout: every tensor a column-major (iters, dims...) array)
+// [iter][C][P] float -> [C][P][iter] (R layout: every tensor a column-major (iters, dims...) array); OutT = double for the one-shot
+// copy-out, float for the streamed one (widened on the host: half the PCIe bytes)
+template <class OutT>
 __global__ void chain_transpose_kernel(const float* __restrict__ store, int64_t iters, int C, int P, int c0, int cn,
-                                       double* __restrict__ out) {
+                                       OutT* __restrict__ out) {
     __shared__ float tile[32][33];
     const int c = c0 + blockIdx.z;
     const int64_t it0 = (int64_t)blockIdx.x * 32; const int f0 = blockIdx.y * 32;
@@ -239,7 +255,7 @@ __global__ void chain_transpose_kernel(const float* __restrict__ store, int64_t 
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int f = f0 + r; const int64_t it = it0 + threadIdx.x;
-        if (f < P && it < iters) out[((size_t)blockIdx.z * P + f) * iters + it] = (double)tile[threadIdx.x][r];
+        if (f < P && it < iters) out[((size_t)blockIdx.z * P + f) * iters + it] = (OutT)tile[threadIdx.x][r];
     }
     (void)cn;
 }
@@ -1133,6 +1149,18 @@ extern "C" void sgm_destroy(sgm_handle* h) {
     void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,
                     h->d_flag, h->d_idx, h->d_noise, h->store, h->Xt, h->Rt, h->hat_all, h->gsum_all};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int b = 0; b < 2; ++b) {
+        if (h->pipe.d_store[b]) cudaFree(h->pipe.d_store[b]);
+        if (h->pipe.d_T[b]) cudaFree(h->pipe.d_T[b]);
+        if (h->pipe.d_lp[b]) cudaFree(h->pipe.d_lp[b]);
+        if (h->pipe.h_T[b]) cudaFreeHost(h->pipe.h_T[b]);
+        if (h->pipe.h_lp[b]) cudaFreeHost(h->pipe.h_lp[b]);
+        if (h->pipe.h_flag[b]) cudaFreeHost(h->pipe.h_flag[b]);
+        if (h->pipe.ran[b]) cudaEventDestroy(h->pipe.ran[b]);
+        if (h->pipe.transposed[b]) cudaEventDestroy(h->pipe.transposed[b]);
+        if (h->pipe.copied[b]) cudaEventDestroy(h->pipe.copied[b]);
+    }
+    if (h->pipe.copy) cudaStreamDestroy(h->pipe.copy);
     if (h->base.prof) cudaFree(h->base.prof);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1246,6 +1274,7 @@ static int check_rows(const sgm_handle* h, const int32_t* idx, size_t count) {
 }
 
 static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta, double* out, int chains = -1);
+static int logpost_launch(sgm_handle* h, const int32_t* idx, const float* theta, int chains);
 static inline uint32_t word2_host(uint64_t step, int L, int sub) { return (uint32_t)(step * (uint64_t)(L + 1) + (uint64_t)sub); }   // = word2_of (common.cuh)
 
 // checkOptDivergence (R/controlVariates.R:114-124): estLogPost at the mode estimate(s) on a fresh device-drawn minibatch
@@ -1504,6 +1533,121 @@ extern "C" int sgm_run(sgm_handle* h, int64_t n_iters, int store) {
 
 extern "C" int sgm_step(sgm_handle* h) { return sgm_run(h, 1, 0); }
 
+// ---- runSGMCMC's loop (R/update.R:145-163) in ONE call, the chain streamed to the host while later iterations run ---------------
+static int pipe_setup(sgm_handle* h, int64_t blk) {
+    sgm_handle::Pipe& p = h->pipe;
+    if (p.blk == blk && p.copy) return SGM_OK;
+    for (int b = 0; b < 2; ++b) {
+        if (p.d_store[b]) { cudaFree(p.d_store[b]); p.d_store[b] = nullptr; }
+        if (p.d_T[b]) { cudaFree(p.d_T[b]); p.d_T[b] = nullptr; }
+        if (p.h_T[b]) { cudaFreeHost(p.h_T[b]); p.h_T[b] = nullptr; }
+    }
+    const size_t bytes = (size_t)blk * h->C * h->P * sizeof(float);
+    if (!p.copy) CU(cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaMalloc(&p.d_store[b], bytes)); CU(cudaMalloc(&p.d_T[b], bytes));
+        CU(cudaHostAlloc(&p.h_T[b], bytes, cudaHostAllocDefault));
+        if (!p.d_lp[b]) {
+            CU(cudaMalloc(&p.d_lp[b], (size_t)h->C * sizeof(double)));
+            CU(cudaHostAlloc(&p.h_lp[b], (size_t)h->C * sizeof(double), cudaHostAllocDefault));
+            CU(cudaHostAlloc(&p.h_flag[b], sizeof(int), cudaHostAllocDefault));
+            CU(cudaEventCreate(&p.ran[b])); CU(cudaEventCreate(&p.transposed[b])); CU(cudaEventCreate(&p.copied[b]));
+        }
+    }
+    p.blk = blk;
+    return SGM_OK;
+}
+
+// float [C][P][cnt] (one block) -> double out[(c * P + f) * n_iters + it0 + i], rows of `cnt` contiguous values; split over host threads
+static void widen_block(const float* src, double* out, int C, int P, int64_t cnt, int64_t n_iters, int64_t it0) {
+    const int64_t rows = (int64_t)C * P;
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)(hw ? (hw > 8 ? 8 : hw) : 1);
+    if (rows * cnt < (1 << 16)) T = 1;
+    auto work = [=](int64_t r0, int64_t r1) {
+        for (int64_t r = r0; r < r1; ++r) {
+            const float* s_ = src + r * cnt;
+            double* d_ = out + r * n_iters + it0;
+            for (int64_t i = 0; i < cnt; ++i) d_[i] = (double)s_[i];
+        }
+    };
+    if (T == 1) { work(0, rows); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back(work, rows * t / T, rows * (t + 1) / T);
+    for (auto& x : th) x.join();
+}
+
+extern "C" int sgm_sample(sgm_handle* h, int64_t n_iters, int32_t check_every, double* out) {
+    if (!h || !out || n_iters < 0 || check_every < 0) return fail(SGM_EINVAL, "bad argument");
+    if (!h->inited) return fail(SGM_ESTATE, "sgm_init has not been called");
+    if (n_iters == 0) return SGM_OK;
+    if (int rc = set_device(h)) return rc;
+    // block = the divergence-check cadence (100 in runSGMCMC), shortened so that one block of the chain stays <= 128 MiB
+    int64_t blk = check_every > 0 ? check_every : 100;
+    const size_t per_iter = (size_t)h->C * h->P * sizeof(float);
+    while (blk > 1 && (size_t)blk * per_iter > (128ull << 20)) blk = (blk + 1) / 2;
+    if (check_every > 0) while (check_every % blk) --blk;     // checks fall on block boundaries
+    if (int rc = pipe_setup(h, blk)) return rc;
+    sgm_handle::Pipe& p = h->pipe;
+    Timer tm(h);
+    const int64_t n_blocks = cdiv(n_iters, blk);
+    int status = SGM_OK;
+    auto retire = [&](int64_t k) -> int {   // block k is on its way to the host: wait for it, check it, widen it into `out`
+        const int b = (int)(k & 1);
+        const int64_t it0 = k * blk, cnt = std::min(blk, n_iters - it0);
+        CU(cudaEventSynchronize(p.copied[b]));
+        if (*p.h_flag[b]) return fail(SGM_EDIVERGED, "Chain diverged, try decreasing stepsize");   // R/update.R:202
+        if (check_every > 0 && (it0 + cnt) % check_every == 0) {
+            for (int c = 0; c < h->C; ++c) if (std::isnan(p.h_lp[b][c])) return fail(SGM_EDIVERGED, "Chain diverged, try decreasing stepsize");
+            if (h->progress) h->progress(h->progress_user, 2, it0 + cnt, p.h_lp[b], h->C);
+        }
+        widen_block(p.h_T[b], out, h->C, h->P, cnt, n_iters, it0);
+        return SGM_OK;
+    };
+    for (int64_t k = 0; k < n_blocks && status == SGM_OK; ++k) {
+        const int b = (int)(k & 1);
+        const int64_t it0 = k * blk, cnt = std::min(blk, n_iters - it0);
+        // compute stream: block k's kernel may overwrite d_store[b] once block k - 2 has been transposed out of it
+        if (k >= 2) CU(cudaStreamWaitEvent(h->stream, p.transposed[b], 0));
+        ChainArgs a = h->base;
+        a.det = 0; a.iters = (int)cnt; a.step0 = h->step; a.store = p.d_store[b]; a.store_pos = 0;
+        if (int rc = launch_chain(h, a)) { status = rc; break; }
+        h->step += (uint64_t)cnt;
+        const bool check = check_every > 0 && (it0 + cnt) % check_every == 0;
+        if (check) {   // checkDivergence (R/update.R:197-207): estLogPost on a fresh minibatch, on the device, result copied with the block
+            h->check_ctr += 1;
+            if (int rc = logpost_launch(h, nullptr, h->theta, h->C)) { status = rc; break; }
+            CU(cudaMemcpyAsync(p.d_lp[b], h->dout, (size_t)h->C * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
+        CU(cudaEventRecord(p.ran[b], h->stream));
+        // copy stream: transpose block k, ship it (float), the divergence flag and the check values
+        if (k >= 2) { /* h_T[b] was consumed by retire(k - 2) below before this point */ }
+        CU(cudaStreamWaitEvent(p.copy, p.ran[b], 0));
+        {
+            dim3 grid((unsigned)cdiv(cnt, 32), (unsigned)cdiv(h->P, 32), (unsigned)1), block(32, 8);
+            for (int c0 = 0; c0 < h->C; c0 += 65535) {
+                const int cn = std::min(65535, h->C - c0);
+                grid.z = (unsigned)cn;
+                SGM_LAUNCH(chain_transpose_kernel<float>, grid, block, 0, p.copy, (const float*)p.d_store[b], cnt, h->C, h->P, c0, cn, p.d_T[b] + (size_t)c0 * h->P * cnt);
+            }
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(p.transposed[b], p.copy));
+        CU(cudaMemcpyAsync(p.h_T[b], p.d_T[b], (size_t)cnt * per_iter, cudaMemcpyDeviceToHost, p.copy));
+        CU(cudaMemcpyAsync(p.h_flag[b], h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, p.copy));
+        if (check) CU(cudaMemcpyAsync(p.h_lp[b], p.d_lp[b], (size_t)h->C * sizeof(double), cudaMemcpyDeviceToHost, p.copy));
+        CU(cudaEventRecord(p.copied[b], p.copy));
+        // host: while block k runs, finish block k - 1 (its buffers are the OTHER pair)
+        if (k >= 1) status = retire(k - 1);
+    }
+    if (status == SGM_OK) status = retire(n_blocks - 1);
+    cudaStreamSynchronize(p.copy);
+    cudaStreamSynchronize(h->stream);
+    if (status == SGM_EDIVERGED) cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream);
+    if (status != SGM_OK) return status;
+    return tm.stop();
+}
+
 // debug: per-phase clock64() totals of thread 0 of every CTA (see LS_TICK in logistic_staged.cuh); n slots of uint64
 extern "C" int sgm_debug_phase_cycles(sgm_handle* h, int enable, unsigned long long* out, int n) {
     if (!h) return fail(SGM_EINVAL, "null handle");
@@ -1586,7 +1730,7 @@ extern "C" int sgm_copy_chain(sgm_handle* h, double* out) {
     for (int c0 = 0; c0 < h->C; c0 += slab) {
         const int cn = (h->C - c0 < slab) ? h->C - c0 : slab;
         dim3 grid((unsigned)cdiv(iters, 32), (unsigned)cdiv(h->P, 32), (unsigned)cn), block(32, 8);
-        SGM_LAUNCH(chain_transpose_kernel, grid, block, 0, h->stream, h->store, iters, h->C, h->P, c0, cn, stage);
+        SGM_LAUNCH(chain_transpose_kernel<double>, grid, block, 0, h->stream, h->store, iters, h->C, h->P, c0, cn, stage);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + (size_t)c0 * iters * h->P, stage, (size_t)cn * per_chain, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -1594,7 +1738,8 @@ extern "C" int sgm_copy_chain(sgm_handle* h, double* out) {
     return SGM_OK;
 }
 
-static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta, double* out, int chains) {
+// launches the family's estLogPost kernel into h->dout (no copy, no synchronisation)
+static int logpost_launch(sgm_handle* h, const int32_t* idx, const float* theta, int chains) {
     if (int rc = set_device(h)) return rc;
     ChainArgs a = h->base;
     a.theta = const_cast<float*>(theta);
@@ -1621,6 +1766,13 @@ static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta,
         }
     }
     CU(cudaGetLastError());
+    (void)Cn;
+    return SGM_OK;
+}
+
+static int logpost_common(sgm_handle* h, const int32_t* idx, const float* theta, double* out, int chains) {
+    if (int rc = logpost_launch(h, idx, theta, chains)) return rc;
+    const int Cn = chains > 0 ? chains : h->C;
     CU(cudaMemcpyAsync(out, h->dout, (size_t)Cn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return SGM_OK;

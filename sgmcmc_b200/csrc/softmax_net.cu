@@ -1416,6 +1416,10 @@ __global__ void __launch_bounds__(NN_THREADS, 1) softmax_net_chain_kernel(const 
                     }
                 }
             }
+            // the last updates of the step (the precisions: thread 0 writes them through to global memory) must be visible to the
+            // threads that store the state below -- without this barrier the stored chain carried the PREVIOUS step's lambdaB / lambdaa /
+            // lambdab while getParams was right (a race found by the emulated build: tests/test_emu_parity.py::test_streamed_sampling)
+            __syncthreads();
             bool bad = false;
             for (int e = threadIdx.x; e < a.P; e += NN_THREADS) {
                 const float v = st.th[e];

@@ -500,6 +500,7 @@ cudaError_t cudaEventCreate(cudaEvent_t* e) { EMU_STICKY(); *e = new EmuEvent{st
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { EMU_STICKY(); e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { EMU_STICKY(); return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { EMU_STICKY(); return cudaSuccess; }   // every emulated stream is synchronous
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { EMU_STICKY(); *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
 cudaError_t cudaFuncSetAttributeImpl(const void* fn, cudaFuncAttribute a, int v) {
     EMU_STICKY();

@@ -188,6 +188,7 @@ cudaError_t cudaEventCreate(cudaEvent_t* e);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags = 0);
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaFuncSetAttributeImpl(const void* fn, cudaFuncAttribute a, int v);
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F fn, cudaFuncAttribute a, int v) { return cudaFuncSetAttributeImpl((const void*)fn, a, v); }

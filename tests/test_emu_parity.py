@@ -64,6 +64,22 @@ def test_small_models_shared_memory_dataset(emulated_library, case_name, algo):
     assert ran(emulated_library, "small_chain:smem") >= before + 2, "the default dispatch did not pick the shared-memory variant for a 60-iteration launch"
 
 
+@pytest.mark.parametrize("case_name,algo,cv,n_iters", [("gauss2d", "sgld", False, 250), ("mixture", "sghmc", False, 137), ("logistic54", "sgld", True, 230),
+                                                       ("logistic130", "sgnht", True, 101), ("softmaxnet_small", "sghmc", False, 120)])
+def test_streamed_sampling(case_name, algo, cv, n_iters, capsys):
+    T.test_streamed_sampling_equals_run_then_copy(None, case_name, algo, cv, n_iters, capsys)
+
+
+def test_streamed_sampling_reports_divergence():
+    T.test_streamed_sampling_reports_divergence(None)
+
+
+@pytest.mark.parametrize("case_name", ["gauss2d", "mixture", "logistic54", "logistic130", "softmaxnet_small"])
+@pytest.mark.parametrize("algo", T.ALGOS)
+def test_last_stored_state_is_the_sampler_state(case_name, algo):
+    T.test_last_stored_state_is_the_sampler_state(None, case_name, algo)
+
+
 def test_mode_finder_cadence(capsys):
     T.test_mode_finder_reports_and_checks_every_100_iterations(None, capsys)
 

@@ -299,3 +299,57 @@ def test_small_models_shared_memory_dataset_equals_global_gather(lib, case_name,
     for k in chains[0]:
         assert np.array_equal(chains[1][k], chains[2][k]), f"{k}: shared-memory and global-memory gathers differ"
         assert np.array_equal(chains[0][k], chains[1][k]), f"{k}: default dispatch differs"
+
+
+@pytest.mark.parametrize("case_name,algo,cv,n_iters", [("gauss2d", "sgld", False, 250), ("mixture", "sghmc", False, 137), ("logistic54", "sgld", True, 230),
+                                                       ("logistic130", "sgnht", True, 101), ("softmaxnet_small", "sghmc", False, 120)])
+def test_streamed_sampling_equals_run_then_copy(lib, case_name, algo, cv, n_iters, capsys):
+    """sgm_sample (the whole runSGMCMC loop in one call, the chain streamed out in double-buffered blocks while later iterations run)
+    against sgm_run + sgm_copy_chain with the same seed: identical chains; the reference's progress lines every 100 iterations."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib
+    case = make_case(case_name)
+    one = device_setup(case, algo, cv, n_chains=3, seed=77, n_iters_opt=20)
+    S.initSess(one, verbose=False)
+    _lib.check(_lib.load().sgm_run(one.handle, n_iters, 1))
+    want = {k: np.array(v) for k, v in S.getChains(one).items()}
+    two = device_setup(case, algo, cv, n_chains=3, seed=77, n_iters_opt=20)
+    from sgmcmc_b200 import api as A
+    got = A.runSGMCMC(two, case["params"], {"nIters": n_iters, "verbose": True})
+    err = capsys.readouterr().err
+    assert "Simulating from SGMCMC algorithm..." in err
+    its = [l.split()[1] for l in err.splitlines() if l.startswith("Iteration:")]
+    opt_lines = 0   # n_iters_opt = 20 < 100: the mode finder prints nothing
+    assert its[opt_lines:] == [str(i) for i in range(100, n_iters + 1, 100)], err
+    for k in want:
+        assert got[k].shape == want[k].shape
+        assert np.array_equal(np.asarray(got[k]), want[k]), f"{k}: streamed chain differs from run + copy"
+    # the sampler state after the call is the last stored state
+    last = S.getParams(two, None)
+    for k in want:
+        np.testing.assert_array_equal(np.asarray(last[k]).reshape(3, -1), np.asarray(got[k])[:, -1].reshape(3, -1))
+
+
+def test_streamed_sampling_reports_divergence(lib):
+    import sgmcmc_b200 as S
+    from sgmcmc_b200._lib import SgmcmcError
+    case = make_case("gauss2d")
+    with pytest.raises(SgmcmcError, match="Chain diverged, try decreasing stepsize"):
+        S.sgld(case["loglik"], case["data"], case["params"], 1.0, logPrior=case["logprior"], minibatchSize=case["n"], nIters=400, verbose=False, seed=1)
+
+
+@pytest.mark.parametrize("case_name", ["gauss2d", "mixture", "logistic54", "logistic130", "softmaxnet_small"])
+@pytest.mark.parametrize("algo", ALGOS)
+def test_last_stored_state_is_the_sampler_state(lib, case_name, algo):
+    """storeState (R/storage.R:54-60) stores what getParams returns (R/storage.R:37-39): every parameter tensor of the last stored
+    iteration equals the sampler state, for every family and sampler (the softmax net's precisions were stored one step stale by the
+    Gauss-Seidel fast path until round 2)."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib
+    case = make_case(case_name)
+    dev = device_setup(case, algo, False, n_chains=2, seed=5)
+    sess = S.initSess(dev, verbose=False)
+    _lib.check(_lib.load().sgm_run(dev.handle, 7, 1))
+    ch, last = S.getChains(dev), S.getParams(dev, sess)
+    for k in ch:
+        np.testing.assert_array_equal(np.asarray(ch[k])[:, -1].reshape(2, -1), np.asarray(last[k]).reshape(2, -1), err_msg=k)
