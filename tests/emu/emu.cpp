@@ -52,6 +52,8 @@ static bool g_lazy = true;          // SGM_EMU_ASYNC
 static int g_sms = 2;               // SGM_EMU_SMS
 static bool g_verbose = false;
 static bool g_shm_ipc = false;     // SGM_EMU_SHM_IPC
+static int g_sched = 0;             // SGM_EMU_SCHED: 0 rr, 1 reverse, >= 2 random (seed)
+static unsigned long long g_sched_state = 1;
 
 // ---- sticky error ------------------------------------------------------------------------------------------------------------
 static int g_err = 0;               // sticky (context-destroying) error
@@ -297,6 +299,10 @@ static void init_once() {
     if (const char* s = getenv("SGM_EMU_SMS")) g_sms = atoi(s) > 0 ? atoi(s) : 2;
     g_verbose = getenv("SGM_EMU_VERBOSE") != nullptr;
     g_shm_ipc = getenv("SGM_EMU_SHM_IPC") != nullptr;
+    if (const char* sc = getenv("SGM_EMU_SCHED")) {
+        if (!strcmp(sc, "reverse")) g_sched = 1;
+        else if (atoi(sc) > 0) { g_sched = 2; g_sched_state = (unsigned long long)atoi(sc) * 0x9E3779B97F4A7C15ull + 1; }
+    }
     struct sigaction sa;
     memset(&sa, 0, sizeof sa);
     sa.sa_sigaction = segv_handler;
@@ -314,7 +320,17 @@ static void run_cta(Cta& c) {
     int stalled = 0;
     while (c.alive > 0 && !c.aborted) {
         const unsigned long long before = c.progress;
-        for (int t = 0; t < c.nthreads && !c.aborted; ++t) {
+        // SGM_EMU_SCHED: the order in which the WARPS of the CTA get their turn in a pass ("rr" = warp 0 first, "reverse", or a
+        // number = seed of a fresh random order per pass).  Lanes of a warp always run in lane order: inter-warp races are real on the
+        // device, intra-warp orders that converged code never produces are not explored.
+        const int nwarps = (c.nthreads + 31) / 32;
+        std::vector<int> order(nwarps);
+        for (int w = 0; w < nwarps; ++w) order[w] = w;
+        if (g_sched == 1) for (int w = 0; w < nwarps; ++w) order[w] = nwarps - 1 - w;
+        else if (g_sched >= 2) for (int w = nwarps - 1; w > 0; --w) { g_sched_state = g_sched_state * 6364136223846793005ull + 1442695040888963407ull; std::swap(order[w], order[(g_sched_state >> 33) % (unsigned)(w + 1)]); }
+        for (int ti = 0; ti < c.nthreads && !c.aborted; ++ti) {
+            const int t = order[ti >> 5] * 32 + (ti & 31);
+            if (t >= c.nthreads) continue;
             Fiber& f = c.fibers[t];
             if (f.done) continue;
             c.cur = t;

@@ -198,22 +198,26 @@ def test_many_mode_full_gradient_wide_rows():
     assert worst < 1e-5
 
 
-# ---- the "eager" timing model of the asynchronous engines (copies land at issue) in a fresh interpreter ---------------------------
-def test_logistic_and_many_mode_under_eager_async():
-    code = """
+# ---- other timing models / schedules, each in a fresh interpreter: "eager" asynchronous engines (copies land at issue), warps
+# scheduled in reverse and in random order (inter-warp races are schedule dependent; the default order starts every pass at warp 0)
+@pytest.mark.parametrize("env,lazy", [({"SGM_EMU_ASYNC": "eager"}, 0), ({"SGM_EMU_SCHED": "reverse"}, 1), ({"SGM_EMU_SCHED": "20261020"}, 1)])
+def test_kernels_under_other_timing_models(env, lazy):
+    code = f"""
 from tests.emu import backend
 from tests import test_parity_gpu as T, test_fullgrad_tc_gpu as F
 with backend.emulated() as lib:
-    assert lib.emu_async_is_lazy() == 0
-    for case in ("logistic54", "logistic54_n500", "logistic130"):
+    assert lib.emu_async_is_lazy() == {lazy}
+    for case in ("logistic54", "logistic54_n101", "logistic130"):
         for algo in T.ALGOS:
             T._deterministic_steps(case, algo, True, shared=(algo == "sgld"))
+    T._deterministic_steps("mixture", "sghmc", True, shared=False)
     T._deterministic_steps("softmaxnet_small", "sghmc", True, shared=False)
     T._deterministic_steps("softmaxnet", "sghmc", False, shared=False)
+    T.test_last_stored_state_is_the_sampler_state(None, "softmaxnet_small", "sghmc")
     F.test_many_mode_full_gradient_matches_oracle(None, "logistic54", 20)
     F.test_many_mode_full_gradient_row_tail_and_blocks(None)
     assert not lib.emu_last_message()
-print("eager ok")
+print("variant ok")
 """
-    out = backend.run_isolated(code, env={"SGM_EMU_ASYNC": "eager", "SGM_EMU_SMS": "1"})
-    assert out.returncode == 0 and "eager ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    out = backend.run_isolated(code, env=dict(env, SGM_EMU_SMS="1"))
+    assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
