@@ -263,9 +263,14 @@ int sgm_copy_dataset(sgm_handle* h, int32_t entry, int64_t row0, int64_t rows, d
 #define SGM_NCCL_ID_BYTES 128
 /* Rank 0 fills id (an ncclUniqueId); every rank then calls sgm_comm_init with the same id. */
 int sgm_comm_unique_id(void* id_out, int32_t id_bytes);
-/* After this, sgm_init computes the full-data gradient on rows [rank*N/world, (rank+1)*N/world)
+/* Communicators are process-level: handles given the SAME unique id share one ncclComm (created by the first call; it lives until
+ * the process exits), so a job pays ncclCommInitRank once, not once per sampler.
+ * After this, sgm_init computes the full-data gradient on rows [rank*N/world, (rank+1)*N/world)
  * and all-reduces (sum, float32) the [n_chains][P] result with NCCL. */
 int sgm_comm_init(sgm_handle* h, const void* id, int32_t id_bytes, int32_t rank, int32_t world);
+/* Device time of the collectives of the last control-variate full-data pass: the reduction of the sums (all-reduce, or
+ * reduce-scatter with one mode per chain) and the all-gather of the modes (0 when there was none). */
+int sgm_last_collective_timing(const sgm_handle* h, float* reduce_ms, float* gather_ms);
 /* Dataset sharded over ranks (one process per GPU, equal shards of N rows each; new: the reference is single-process).
  * sgm_dataset_ipc_handle writes the CUDA IPC handle (64 bytes) of this rank's device dataset; after an all-gather of the
  * handles, sgm_attach_peer_shards maps the peers' shards: the chains then sample minibatches from all world x N rows

@@ -81,6 +81,7 @@ SYMBOLS = {
     "sgm_noise_len": (C.c_int32, [_H]),
     "sgm_last_timing": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "sgm_last_fullgrad_timing": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "sgm_last_collective_timing": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "sgm_bench_full_gradient": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "sgm_last_fullgrad_flops": (C.c_int, [_H, _PD]),
     "sgm_dataset_ipc_handle": (C.c_int, [_H, C.c_void_p, C.c_int32]),

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <map>
 #include <string>
 #include <thread>
 #include <algorithm>
@@ -69,6 +70,10 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
+// communicators are process-level resources (creating one costs hundreds of milliseconds): handles that are given the same unique
+// id share one ncclComm, which then lives until the process exits
+struct SharedComm { ncclComm_t comm; int refs; int rank, world; };
+static std::map<std::string, SharedComm> g_comms;
 
 static int load_nccl() {
     if (g_nccl.lib) return SGM_OK;
@@ -143,6 +148,7 @@ struct sgm_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0; int last_launches = 0;
     float fullgrad_ms = 0; int64_t fullgrad_bytes = 0;
+    float collective_ms = 0, gather_ms = 0;   // device time of the last full-data pass's collectives (reduction; all-gather of the modes)
     uint64_t step = 0, check_ctr = 0;
     bool inited = false;
     CUtensorMap tmap;           // 2-D map of the dataset (box = one row) for TMA tile::gather4
@@ -172,6 +178,7 @@ struct sgm_handle {
     SoftmaxNetWork* nn = nullptr;
     // comm
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
+    std::string comm_key;
 };
 
 static int hat_count(const sgm_handle* h) { return (h->flags & SGM_FLAG_SHARED_MODE) ? 1 : h->C; }
@@ -1142,7 +1149,10 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
 extern "C" void sgm_destroy(sgm_handle* h) {
     if (!h) return;
     if (h->stream) cudaSetDevice(h->device);
-    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->comm) {   // the communicator itself lives until the process exits: a unique id must never be used for a second ncclCommInitRank
+        auto it = g_comms.find(h->comm_key);
+        if (it != g_comms.end()) --it->second.refs;
+    }
     if (h->nn) softmax_net_destroy(h->nn);
     for (int r = 0; r < 16; ++r) if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     if (h->d_shard_ptr) cudaFree((void*)h->d_shard_ptr);
@@ -1194,8 +1204,15 @@ static int full_gradient(sgm_handle* h) {
         row0 = h->opt_row0; row1 = h->opt_row1;
     }
     const bool gathered = fullgrad_gathered(h);
+    h->gather_ms = 0.f;
     if (gathered) {
+        EventPair evg;
+        CU(cudaEventCreate(&evg.e0)); CU(cudaEventCreate(&evg.e1));
+        CU(cudaEventRecord(evg.e0, h->stream));
         if (int rc = fullgrad_gather_modes(h)) return rc;
+        CU(cudaEventRecord(evg.e1, h->stream));
+        CU(cudaEventSynchronize(evg.e1));
+        CU(cudaEventElapsedTime(&h->gather_ms, evg.e0, evg.e1));
         CU(cudaMemsetAsync(h->gsum_all, 0, (size_t)M * h->world * h->Pst * sizeof(double), h->stream));
     }
     CU(cudaMemsetAsync(h->gsum, 0, (size_t)M * h->Pst * sizeof(double), h->stream));
@@ -1232,6 +1249,8 @@ static int full_gradient(sgm_handle* h) {
     }
     CU(cudaEventRecord(e1, h->stream));
     h->last_launches += 1;
+    EventPair evc;
+    if (h->comm) { CU(cudaEventCreate(&evc.e0)); CU(cudaEventCreate(&evc.e1)); CU(cudaEventRecord(evc.e0, h->stream)); }
     if (gathered) {
         const int rc = g_nccl.ReduceScatter(h->gsum_all, h->gsum, (size_t)M * h->Pst, 8 /* ncclFloat64 */, 0 /* ncclSum */, h->comm, h->stream);
         if (rc != 0) return fail(SGM_ECOMM, "ncclReduceScatter failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
@@ -1240,6 +1259,7 @@ static int full_gradient(sgm_handle* h) {
         const int rc = g_nccl.AllReduce(h->gsum, h->gsum, (size_t)M * h->Pst, 8, 0, h->comm, h->stream);
         if (rc != 0) return fail(SGM_ECOMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }
+    if (h->comm) CU(cudaEventRecord(evc.e1, h->stream));
     const int total = M * h->Pst;
     switch (h->model) {
         case SGM_MODEL_GAUSS_MEAN:
@@ -1261,6 +1281,8 @@ static int full_gradient(sgm_handle* h) {
     }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaEventElapsedTime(&h->fullgrad_ms, e0, e1));
+    h->collective_ms = 0.f;
+    if (h->comm) CU(cudaEventElapsedTime(&h->collective_ms, evc.e0, evc.e1));   // the reduction of the sums (all-reduce, or reduce-scatter), on the device
     h->fullgrad_bytes = (row1 - row0) * (int64_t)h->ld * 4 * (h->model == SGM_MODEL_LOGISTIC ? 1 : 1);
     return SGM_OK;
 }
@@ -2086,6 +2108,13 @@ extern "C" int sgm_last_fullgrad_timing(const sgm_handle* h, float* kernel_ms, i
     return SGM_OK;
 }
 
+extern "C" int sgm_last_collective_timing(const sgm_handle* h, float* reduce_ms, float* gather_ms) {
+    if (!h) return fail(SGM_EINVAL, "null handle");
+    if (reduce_ms) *reduce_ms = h->collective_ms;
+    if (gather_ms) *gather_ms = h->gather_ms;
+    return SGM_OK;
+}
+
 extern "C" int sgm_copy_dataset(sgm_handle* h, int32_t entry, int64_t row0, int64_t rows, double* out) {
     if (!h || !out || row0 < 0 || rows < 0 || row0 + rows > h->N) return fail(SGM_EINVAL, "bad argument");
     if (int rc = set_device(h)) return rc;
@@ -2227,10 +2256,20 @@ extern "C" int sgm_comm_init(sgm_handle* h, const void* id, int32_t id_bytes, in
                                 "one mode per chain across ranks is implemented for the logistic family");
     if (int rc = load_nccl()) return rc;
     if (int rc = set_device(h)) return rc;
-    NcclId nid;
-    std::memcpy(nid.internal, id, SGM_NCCL_ID_BYTES);
-    const int rc = g_nccl.CommInitRank(&h->comm, world, nid, rank);
-    if (rc != 0) return fail(SGM_ECOMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    if (h->comm) return fail(SGM_ESTATE, "the handle already has a communicator");
+    const std::string key((const char*)id, SGM_NCCL_ID_BYTES);
+    auto it = g_comms.find(key);
+    if (it != g_comms.end()) {
+        if (it->second.rank != rank || it->second.world != world) return fail(SGM_EINVAL, "this unique id already names a communicator with another rank / world size");
+        h->comm = it->second.comm; ++it->second.refs;
+    } else {
+        NcclId nid;
+        std::memcpy(nid.internal, id, SGM_NCCL_ID_BYTES);
+        const int rc = g_nccl.CommInitRank(&h->comm, world, nid, rank);
+        if (rc != 0) return fail(SGM_ECOMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        g_comms[key] = SharedComm{h->comm, 1, rank, world};
+    }
+    h->comm_key = key;
     h->rank = rank; h->world = world;
     return SGM_OK;
 }

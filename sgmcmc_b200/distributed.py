@@ -21,16 +21,22 @@ def _bytes_tensor(raw: bytes):
     return t.cuda() if dist.get_backend() == "nccl" else t
 
 
+_job_id = None   # the unique id of this job's communicator: exchanged once, every sampler of the process then shares one ncclComm
+
+
 def comm_init(sg, rank: int, world: int):
-    """Gives the handle an NCCL communicator over all ranks (id broadcast from rank 0)."""
+    """Gives the handle the job's NCCL communicator (created by the first call: id broadcast from rank 0; later calls reuse it)."""
+    global _job_id
     import torch.distributed as dist
     lib = _lib.load()
-    raw = (C.c_char * _lib.NCCL_ID_BYTES)()
-    if rank == 0:
-        _lib.check(lib.sgm_comm_unique_id(raw, _lib.NCCL_ID_BYTES))
-    idbuf = _bytes_tensor(raw.raw)
-    dist.broadcast(idbuf, 0)
-    _lib.check(lib.sgm_comm_init(sg.handle, idbuf.cpu().numpy().tobytes(), _lib.NCCL_ID_BYTES, rank, world))
+    if _job_id is None or _job_id[1] != (rank, world):
+        raw = (C.c_char * _lib.NCCL_ID_BYTES)()
+        if rank == 0:
+            _lib.check(lib.sgm_comm_unique_id(raw, _lib.NCCL_ID_BYTES))
+        idbuf = _bytes_tensor(raw.raw)
+        dist.broadcast(idbuf, 0)
+        _job_id = (idbuf.cpu().numpy().tobytes(), (rank, world))
+    _lib.check(lib.sgm_comm_init(sg.handle, _job_id[0], _lib.NCCL_ID_BYTES, rank, world))
 
 
 def attach_peer_shards(sg, rank: int, world: int):

@@ -121,3 +121,10 @@ def benchFullGradient(sgmcmc: Sgmcmc, reps: int = 20):
 def setOption(sgmcmc: Sgmcmc, key: str, value: int):
     """Pins a kernel path of this sampler (include/sgmcmc_b200.h: sgm_set_option); 0 restores the default dispatch."""
     _lib.check(_lib.load().sgm_set_option(sgmcmc.handle, key.encode(), int(value)))
+
+
+def lastCollectiveTiming(sgmcmc: Sgmcmc):
+    """(reduction ms, all-gather ms) of the last control-variate full-data pass's collectives, timed on the device."""
+    a, b = C.c_float(), C.c_float()
+    _lib.check(_lib.load().sgm_last_collective_timing(sgmcmc.handle, C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -43,7 +43,7 @@ static void barrier(FakeComm* c) {
     } else {
         long spins = 0;
         while (atomic_load(&c->hdr->generation) == gen) {
-            if (++spins > 2000000000L) { fprintf(stderr, "fake_nccl: rank %d waited too long in a collective\n", c->rank); abort(); }
+            if (++spins > 60000000L) { fprintf(stderr, "fake_nccl: rank %d waited too long in a collective\n", c->rank); abort(); }
             sched_yield();
         }
     }
