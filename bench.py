@@ -182,6 +182,41 @@ def measured_tensor_peak():
     return 1500.0, "fallback (B200_PROFILING.md dense bf16)"
 
 
+def measure_tf32_peak(seconds=1.5):
+    """cuBLAS TF32 (fp32 inputs, allow_tf32) 8192^3 on this GPU, now: (burst TFLOP/s = best of 10, sustained = back to back for `seconds`).
+    MEASURED_PEAKS.json only has bf16; the many-mode control-variate pass computes in 3xTF32, so its ceiling is THIS number / 3."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device="cuda", dtype=torch.float32)
+        b = torch.randn(n, n, device="cuda", dtype=torch.float32)
+        for _ in range(3):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        flops = 2.0 * n ** 3
+        best = 0.0
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps, t0 = 0, time.perf_counter()
+        e0.record()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(10):
+                torch.matmul(a, b)
+            reps += 10
+            torch.cuda.synchronize()
+        e1.record(); torch.cuda.synchronize()
+        sustained = reps * flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b
+        return best, sustained
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def comm_init(sg, rank, world):
     from sgmcmc_b200 import distributed as D
     D.comm_init(sg, rank, world)
@@ -207,18 +242,26 @@ def many_mode_full_gradient(w, rank, world, modes):
         comm_init(sg, rank, world)
     S.initSess(sg, verbose=False)
     flops = V.lastFullGradFlops(sg)
+    reduce_ms, gather_ms = V.lastCollectiveTiming(sg)
     reps = 3 if flops > 2e14 else 20
     ms, _ = V.benchFullGradient(sg, reps)
-    peak, src = measured_tensor_peak()
+    bf16_peak, bf16_src = measured_tensor_peak()
+    tf32_burst, tf32_sustained = measure_tf32_peak()
     rows = (synth["rows"] if synth else np.asarray(w["data"]["X"]).shape[0]) // world
     d = w["params"]["beta"].shape[0]
     tf = flops / (ms * 1e-3) / 1e12 if ms > 0 and flops > 0 else None
     del sg
-    return {"modes": max(1, modes // world) * world, "rows_per_rank": rows, "d": d, "ms": ms, "flops": flops, "TFLOPs": tf, "TFLOPs_all_ranks": (tf * world) if tf else None, "bound": "tensor",
-            "peak": peak, "peak_source": src, "frac": (tf / peak) if tf else None,
-            "frac_of_3xtf32_ceiling": (tf / (peak / 6.0)) if tf else None,   # TF32 = bf16 / 2 (B200 datasheet ratio), three MMAs per fp32 product
+    # ONE stated denominator: the TF32 throughput cuBLAS reaches on this GPU now (sustained).  Three TF32 MMAs are spent per float32
+    # product, so the ceiling of this arithmetic is that / 3; the bf16 figure of MEASURED_PEAKS.json is printed for reference only.
+    return {"modes": max(1, modes // world) * world, "rows_per_rank": rows, "d": d, "ms": ms, "flops": flops, "TFLOPs": tf, "TFLOPs_all_ranks": (tf * world) if tf else None,
+            "bound": "tensor", "peak": tf32_sustained, "peak_source": "cuBLAS TF32 8192^3 measured in this run (sustained); burst %.1f" % tf32_burst,
+            "frac": (tf / tf32_sustained) if tf else None,
+            "frac_of_3xtf32_ceiling": (tf / (tf32_sustained / 3.0)) if tf else None,
+            "tensor_pipe_TFLOPs": (3.0 * tf) if tf else None,
+            "bf16_peak_reference": bf16_peak, "bf16_peak_source": bf16_src,
+            "collective_ms": {"all_gather_modes": gather_ms, "reduce_scatter_sums": reduce_ms} if world > 1 else None,
             "arithmetic": "3xTF32 (hi*hi + hi*lo + lo*hi) on tcgen05, float32-level accuracy: three TF32 MMAs per float32 product, "
-                          "so the ceiling of this arithmetic is about TF32 peak / 3 = bf16 peak / 6",
+                          "so the ceiling of the ALGORITHMIC rate is the TF32 peak / 3; tensor_pipe_TFLOPs = 3 x the algorithmic rate",
             "passes": "R = y - sigmoid(X theta_hat^T + bias); G = X^T R (K split over row ranges), per row block",
             "sample": "whole dataset" if not synth or synth["rows"] == w["synth"]["rows"] else "bounded row sample of the c5 shape"}
 
@@ -278,10 +321,53 @@ def run_reference(args, w):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def device_leg(sg, lib, V, _lib, I, steps, warmup, barrier):
+    """W warm-up launches, then exactly K timed ones (device-resident chain): returns (wall seconds, per-launch kernel ms list, launches)."""
+    for _ in range(max(3, warmup)):
+        _lib.check(lib.sgm_reset_chain(sg.handle))
+        _lib.check(lib.sgm_run(sg.handle, I, 1))
+    kernel_ms, launches = [], 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.sgm_reset_chain(sg.handle)
+        _lib.check(lib.sgm_run(sg.handle, I, 1))
+        ms, nl = V.lastTiming(sg)
+        kernel_ms.append(ms)
+        launches += nl
+    barrier()
+    return time.perf_counter() - t0, kernel_ms, launches
+
+
+def quick_workload(name, steps=5, iters=None):
+    """A compact device-resident measurement of another BASELINE config (N = 1 only), for the same JSON line."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib
+    from sgmcmc_b200 import validation as V
+    import torch
+    w = workload(name, None)
+    I = iters or (550 if name in ("c1", "c2") else 20)
+    lib = _lib.load()
+    sg = make_sampler(w, 0, 1, w["chains"])
+    S.initSess(sg, verbose=False)
+    _lib.check(lib.sgm_reserve_chain(sg.handle, I))
+
+    def barrier():
+        torch.cuda.synchronize()
+    dt, kms, launches = device_leg(sg, lib, V, _lib, I, steps, 3, barrier)
+    peak, _ = measured_peaks()
+    k_ms = float(np.mean(kms))
+    achieved = w["chains"] * I * w["bytes_per_chain_iter"] / (k_ms * 1e-3) / 1e9
+    del sg
+    return {"desc": w["desc"], "value": w["chains"] * I * steps / dt, "unit": UNIT, "chains": w["chains"], "iters_per_step": I, "steps": steps,
+            "kernel_ms_per_launch": k_ms, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "bytes_per_chain_iter": w["bytes_per_chain_iter"], "note": w["bound_note"]}}
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
-    import ctypes as C
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -308,7 +394,19 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- end-to-end leg (public API, host buffers): Setup (dataset H2D) + initSess + K x [run + copy-out (D2H)]
+    # ---- process-level one-time cost, outside the end-to-end region and reported apart: the job's NCCL communicator (like the CUDA
+    # context, it is created once per process; every sampler of the job then shares it -- sgmcmc_b200/distributed.py)
+    comm_ms = None
+    if world > 1 and w["cv"]:
+        t0 = time.perf_counter()
+        tiny = S.sgldcvSetup(S.gaussMeanLogLik(), {"X": np.zeros((64, 2))}, {"theta": np.zeros(2)}, 1e-4, 1e-4, logPrior=S.normalPrior(10.0), minibatchSize=8,
+                             nItersOpt=1, verbose=False, seed=1, sharedMode=True, device=local)
+        comm_init(tiny, rank, world)
+        barrier()
+        comm_ms = 1000.0 * (time.perf_counter() - t0)
+
+    # ---- end-to-end leg through the public API with HOST buffers: Setup (dataset H2D) + initSess + K x sgm_sample (runSGMCMC's loop in one
+    # call: the chain streams to the host as float32 while later iterations run, widened to float64 into the caller's array)
     barrier()
     t_e2e0 = time.perf_counter()
     sharded = bool(args.peer_shards and world > 1 and w["family"] == "logistic")
@@ -318,41 +416,37 @@ def run_ours(args, w):
         attach_peer_shards(sg, rank, world)
     if world > 1 and w["cv"]:
         comm_init(sg, rank, world)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter()
     sess = S.initSess(sg, verbose=False)
     init_ms, init_launches = V.lastTiming(sg)
     fg_ms, fg_bytes = V.lastFullGradTiming(sg) if w["cv"] else (0.0, 0)
-    _lib.check(lib.sgm_reserve_chain(sg.handle, I))
-    d2h_bytes = 0
+    reduce_ms, _ = V.lastCollectiveTiming(sg) if w["cv"] else (0.0, 0.0)
+    torch.cuda.synchronize()
+    t_init = time.perf_counter()
+    host_chain = np.empty(chains_local * sg.P * I, dtype=np.float64)
+    hptr = host_chain.ctypes.data_as(_lib._PD)
+    e2e_launches = 0
     for _ in range(args.steps):
-        _lib.check(lib.sgm_reset_chain(sg.handle))
-        _lib.check(lib.sgm_run(sg.handle, I, 1))
-        ch = S.getChains(sg, reuse_buffer=True)
-        d2h_bytes = sum(v.nbytes for v in ch.values())
-        del ch
+        _lib.check(lib.sgm_sample(sg.handle, I, 100, hptr))
+        e2e_launches += V.lastTiming(sg)[1]
     barrier()
     t_e2e = time.perf_counter() - t_e2e0
+    t_run = time.perf_counter() - t_init
     if world > 1:
-        t = torch.tensor([t_e2e], device="cuda")
+        t = torch.tensor([t_e2e, t_run, t_setup - t_e2e0, t_init - t_setup], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t)
+        t_e2e, t_run, t_up, t_in = (float(x) for x in t)
+    else:
+        t_up, t_in = t_setup - t_e2e0, t_init - t_setup
+    d2h_bytes = chains_local * sg.P * I * 4
     h2d_total = sum(np.asarray(v).size * 8 for v in (w["data"] or {}).values())
+    del host_chain
 
     # ---- device-resident leg: W warm-up steps, then exactly K timed steps
-    for _ in range(max(3, args.warmup)):
-        _lib.check(lib.sgm_reset_chain(sg.handle))
-        _lib.check(lib.sgm_run(sg.handle, I, 1))
-    kernel_ms, launches = [], 0
+    _lib.check(lib.sgm_reserve_chain(sg.handle, I))
     with ClockSampler(local) as clk:
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            lib.sgm_reset_chain(sg.handle)
-            _lib.check(lib.sgm_run(sg.handle, I, 1))
-            ms, nl = V.lastTiming(sg)
-            kernel_ms.append(ms)
-            launches += nl
-        barrier()
-        dt = time.perf_counter() - t0
+        dt, kernel_ms, launches = device_leg(sg, lib, V, _lib, I, args.steps, args.warmup, barrier)
     if world > 1:
         t = torch.tensor([dt, max(kernel_ms)], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -361,36 +455,40 @@ def run_ours(args, w):
 
     total_chains = chains_local * world
     value = total_chains * I * args.steps / dt
-    traffic, traffic_src = None, None
-    try:   # measured DRAM bytes per chain-iteration of the dominant kernel (one ncu --set full capture), scaled to this launch
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
-        if tj:
-            traffic = tj["dram_bytes_per_chain_iter"] * chains_local * I
-            traffic_src = f"{tj['capture']}: {tj['dram_bytes_per_chain_iter']:.0f} B per chain-iteration ({tj['note']})"
-    except Exception:
-        pass
     peak, peak_src = measured_peaks()
     k_ms = float(np.mean(kernel_ms))
     achieved = chains_local * I * w["bytes_per_chain_iter"] / (k_ms * 1e-3) / 1e9
+    dataset_mb = {"c1": 0.08, "c2": 0.08, "c3": 130.1, "c4": 191.0, "c5": 51400.0}.get(args.workload)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "chains_per_gpu": chains_local, "chains_total": total_chains,
                    "iters_per_step": I, "minibatch": w["n"], "store": "device-resident chain, every iteration",
-                   "l2": "inputs larger than L2" if args.workload in ("c3", "c4", "c5") else "dataset smaller than L2 (stated; not an HBM-bound case)",
+                   "l2": ("dataset %.0f MB >> the 126 MB L2: gathers come from HBM" % dataset_mb) if args.workload == "c5" else
+                         ("dataset %.1f MB is about the size of the 126 MB L2: the gathers are served partly from L2 (the figure is algorithmic bytes / time, "
+                          "NOT an HBM-traffic claim; the per-chain state is re-read from L2 too)" % dataset_mb) if args.workload in ("c3", "c4") else
+                         "dataset 80 KB lives in shared memory / L1: not an HBM-bound case (stated)",
                    "sampling": "device Philox, without replacement", "shared_mode": bool(w["cv"]),
                    "dataset": (f"sharded over {world} ranks, peers mapped by CUDA IPC: chains sample from {world}x the rows, "
                                f"{world - 1}/{world} of the gathered bytes arrive over NVLink") if sharded else "replicated per GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": chains_local * I * w["bytes_per_chain_iter"],
+                     "traffic": None, "traffic_note": "no ncu capture of this commit exists (gpurun was closed for the whole round): measured DRAM traffic is not claimed",
+                     "algorithmic_bytes_per_launch": chains_local * I * w["bytes_per_chain_iter"],
                      "kernel": "persistent chain kernel (gather + gradient + update + store)",
                      "kernel_ms_per_launch": k_ms, "bytes_per_chain_iter": w["bytes_per_chain_iter"], "peak_source": peak_src,
                      "note": w["bound_note"]},
         "clocks": clocks,
         "e2e": {"value": total_chains * I * args.steps / t_e2e, "unit": UNIT,
                 "h2d_bytes_per_step": h2d_total / args.steps, "d2h_bytes_per_step": d2h_bytes,
-                "seconds": t_e2e, "includes": "Setup (dataset upload) + initSess (mode finder, full gradient) + K x [run + chain copy-out as doubles]"},
+                "seconds": t_e2e,
+                "breakdown_ms": {"upload_setup": 1000.0 * t_up, "init_mode_and_full_gradient": 1000.0 * t_in, "run_and_copy_out": 1000.0 * t_run,
+                                 "run_and_copy_out_per_step": 1000.0 * t_run / args.steps},
+                "steady_state_value": total_chains * I * args.steps / t_run,
+                "comm_init_ms_outside": comm_ms,
+                "includes": "Setup (dataset upload, float64 host arrays) + initSess (mode finder, full gradient) + K x sgm_sample (sampling with the chain streamed "
+                            "out as float32 in 100-iteration blocks on a second stream and widened to float64 into a host array; divergence check every 100 iterations)",
+                "gpu_launches": e2e_launches},
         "gpu_launches": launches,
     }
     if w["cv"]:
@@ -400,13 +498,25 @@ def run_ours(args, w):
                                     "frac_of_hbm_peak": (fg_bytes / (fg_ms * 1e-3) / 1e9 / peak) if fg_ms > 0 else None,
                                     "rows_per_rank": fg_bytes // (16 * (w["params"]["beta"].shape[0] // 4 + 1)) if w["family"] == "logistic" else None,
                                     "init_ms_total": init_ms,
-                                    "note": "one mode (shared by all chains): HBM-bound stream, not a GEMM; bytes = rows x row stride"}
+                                    "collective_ms": reduce_ms if world > 1 else None,
+                                    "note": "one mode (shared by all chains): HBM-bound stream, not a GEMM; bytes = rows x row stride; collective_ms = the all-reduce "
+                                            "of the P-vector inside initSess, timed on the device (sharding this pass pays only while rows/rank x row bytes is tens of MB: "
+                                            "the reduction of 55 doubles costs more than a 12 us kernel saves)"}
     if sharded:   # unmap on every rank before any owner frees its shard
         _lib.check(lib.sgm_detach_peer_shards(sg.handle))
         barrier()
     if w["cv"] and w["family"] == "logistic" and not args.no_modes:
         del sg, sess
         line["cv_full_gradient_modes"] = many_mode_full_gradient(w, rank, world, args.modes)
+    if world == 1 and not args.no_extra:
+        extra = {}
+        for name in ("c1", "c2", "c4"):
+            if name != args.workload:
+                try:
+                    extra[name] = quick_workload(name)
+                except Exception as e:   # noqa: BLE001  (an extra measurement must not lose the main line)
+                    extra[name] = {"error": str(e)[:300]}
+        line["other_workloads"] = extra
     if rank == 0 and world == 1 and not args.no_cpu:
         ips, note, fg, _ = cpu_proxy(w, args.cpu_budget, 1)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": 1, "kind": "port", "sample": note,
@@ -430,6 +540,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--modes", type=int, default=1024, help="modes of the many-mode control-variate full gradient leg (logistic *cv workloads)")
     ap.add_argument("--no-modes", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the compact c1 / c2 / c4 measurements added to the line at N = 1")
     ap.add_argument("--peer-shards", action="store_true",
                     help="N > 1, logistic workloads: every rank keeps its own rows and maps the peers' (the c5 config at N = world x rows/GPU)")
     args = ap.parse_args()

@@ -1,0 +1,98 @@
+"""bench.py end to end on the CPU-emulated build: the GPU arm's whole code path (Setup, initSess, sgm_sample e2e leg, device-resident
+leg, roofline / e2e / cv_full_gradient / many-mode objects, extra workloads, cpu_baseline) at toy sizes, with torch.cuda stubbed.
+bench.py cannot run in this container otherwise, and a Python error in it at round end would cost the round its only numbers.
+The VALUES are meaningless here (emulated kernels); the test checks the contract: one JSON line with the keys the driver reads."""
+import io
+import json
+import sys
+import types
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from tests.emu import backend
+
+REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+            "config", "roofline", "clocks", "e2e", "gpu_launches", "cpu_baseline"]
+
+
+def tiny_workload(name, chains):
+    import bench
+    rs = np.random.RandomState(13)
+    if name == "c3":
+        N, d = 1500, 54
+        X = rs.randn(N, d)
+        y = (rs.rand(N) < 0.5).astype(np.float64)
+        return dict(desc="toy c3", algo="sgld", cv=True, family="logistic", data={"X": X, "y": y}, params={"bias": np.array(0.0), "beta": np.zeros((d, 1))},
+                    stepsize=5e-6, opt_stepsize=5e-6, n_iters_opt=120, n=300, chains=chains or 3, bytes_per_chain_iter=111100, fullgrad_bytes=N * 55 * 4, bound_note="toy")
+    if name in ("c1", "c2"):
+        w = bench.workload.__wrapped__(name, 4)
+        w["data"] = {"X": w["data"]["X"][:2000]}
+        return w
+    if name == "c4":
+        N = 300
+        X = rs.rand(N, 20)
+        Y = np.eye(4)[rs.randint(0, 4, N)]
+        p = {"A": rs.randn(8, 4), "B": rs.randn(20, 8), "a": rs.randn(4), "b": rs.randn(8), "lambdaA": np.array(1.0), "lambdaB": np.array(1.0),
+             "lambdaa": np.array(1.0), "lambdab": np.array(1.0)}
+        return dict(desc="toy c4", algo="sghmc", cv=False, family="nn", data={"X": X, "y": Y}, params=p, stepsize=1e-6, n=40, chains=2, L=2, alpha=0.01,
+                    bytes_per_chain_iter=1000, bound_note="toy")
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("main", ["c3", "c1"])
+def test_bench_prints_one_contract_line(monkeypatch, main):
+    import torch
+    import bench
+    import __graft_entry__
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *_: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
+    monkeypatch.setattr(__graft_entry__, "build", lambda *a, **k: None)
+    monkeypatch.setattr(bench, "measure_tf32_peak", lambda *a, **k: (900.0, 800.0))
+    orig = bench.workload
+    tiny_workload_w = tiny_workload
+    bench.workload = types.FunctionType(tiny_workload_w.__code__, tiny_workload_w.__globals__)
+    bench.workload.__wrapped__ = orig
+    monkeypatch.setattr(bench, "oracle_model", lambda w: __import__("oracle.models", fromlist=["x"]).Logistic(54) if w["family"] == "logistic" else
+                        (__import__("oracle.models", fromlist=["x"]).GaussMean(2, prior_sd=10.0) if w["family"] == "gauss" else __import__("oracle.models", fromlist=["x"]).Mixture2(2, 10.0)))
+    try:
+        args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="ours", workload=main, chains=None, iters_per_step=120, cpu_budget=0.5, no_cpu=False, modes=32,
+                                     no_modes=False, peer_shards=False, no_extra=False)
+        out = io.StringIO()
+        with backend.emulated() as lib, redirect_stdout(out):
+            bench.run_ours(args, bench.workload(main, None))
+            assert not lib.emu_last_message()
+    finally:
+        bench.workload = orig
+    lines = [l for l in out.getvalue().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.getvalue()[-2000:]
+    line = json.loads(lines[0])
+    for k in REQUIRED:
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["config"]["workload"] == main
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["traffic"] is None
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "breakdown_ms"} and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    assert line["gpu_launches"] >= 2
+    assert set(line["other_workloads"]) == {"c1", "c2", "c4"} - {main}
+    assert all("error" not in v for v in line["other_workloads"].values()), line["other_workloads"]
+    if main == "c3":
+        assert line["cv_full_gradient"]["GBps"] > 0
+        m = line["cv_full_gradient_modes"]
+        assert m["TFLOPs"] > 0 and m["peak"] == 800.0 and abs(m["frac_of_3xtf32_ceiling"] - 3 * m["frac"]) < 1e-12
+
+
+def test_smoke_runs_on_the_emulated_build(monkeypatch, capsys):
+    """__graft_entry__.smoke(): the SIMT / TMA logistic step and the tcgen05 many-mode full gradient, each checked against the oracle."""
+    import __graft_entry__
+    monkeypatch.setattr(__graft_entry__, "build", lambda *a, **k: None)
+    with backend.emulated() as lib:
+        lib.emu_note_count.restype = __import__("ctypes").c_longlong
+        lib.emu_note_count.argtypes = [__import__("ctypes").c_char_p]
+        before = lib.emu_note_count(b"cvg:pass1"), lib.emu_note_count(b"logistic_staged:gather4")
+        __graft_entry__.smoke()
+        assert lib.emu_note_count(b"cvg:pass1") > before[0] and lib.emu_note_count(b"logistic_staged:gather4") > before[1]
+    assert capsys.readouterr().out.count("smoke ok") == 2
