@@ -80,6 +80,13 @@ def test_last_stored_state_is_the_sampler_state(case_name, algo):
     T.test_last_stored_state_is_the_sampler_state(None, case_name, algo)
 
 
+@pytest.mark.parametrize("case_name,algo,cv,shared", [("mixture", "sgld", True, True), ("logistic5", "sgld", False, False)])
+def test_posterior_moments_match_the_oracle(case_name, algo, cv, shared):
+    """Reduced-size run of tests/test_statistics_gpu.py::test_posterior_moments_match_the_oracle (device RNG vs float64 oracle chains)."""
+    from tests import test_statistics_gpu as ST
+    ST.test_posterior_moments_match_the_oracle(None, case_name, algo, cv, shared, n_dev=48, n_orc=8, burn=200, keep=600)
+
+
 def test_mode_finder_cadence(capsys):
     T.test_mode_finder_reports_and_checks_every_100_iterations(None, capsys)
 

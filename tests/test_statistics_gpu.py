@@ -116,3 +116,74 @@ def test_divergence_is_reported_with_the_reference_message(lib):
     with pytest.raises(S.SgmcmcError) as e:
         S.sgld(S.gaussMeanLogLik(), data, {"theta": np.array(0.0)}, 10.0, minibatchSize=10, nIters=300, verbose=False, seed=1)
     assert "Chain diverged, try decreasing stepsize" in str(e.value)
+
+
+# ---- posterior moments of the non-Gaussian families against long float64 oracle chains ------------------------------------------
+def _oracle_moments(case, algo, cv, n_chains, burn, keep, seed, L=3, opt_iters=0):
+    """Independent float64 oracle chains (numpy RNG for rows and noise): per-chain means and variances of every flat coordinate."""
+    from oracle import samplers as OS
+    from tests.cases import oracle_chain
+    rs = np.random.RandomState(seed)
+    P = sum(int(np.size(v)) for v in case["params"].values())
+    means, variances = [], []
+    mode = None
+    if cv:   # ONE mode for every oracle chain (the mode is part of the estimator, not of the posterior)
+        ch0 = oracle_chain(case, algo, cv, np.float64, L=L)
+        ch0.find_mode([rs.choice(case["N"], case["n"], replace=False) for _ in range(opt_iters)])
+        mode = ch0
+    for _ in range(n_chains):
+        ch = oracle_chain(case, algo, cv, np.float64, L=L)
+        if cv:
+            ch.theta_hat, ch.g_hat = mode.theta_hat, mode.g_hat
+            ch.theta = {k: np.array(v, dtype=np.float64) for k, v in mode.theta_hat.items()}
+        if algo != "sgld":
+            ch.init_momentum(rs.randn(P))
+        xs = np.empty((keep, P))
+        for it in range(burn + keep):
+            idx = np.stack([rs.choice(case["N"], case["n"], replace=False) for _ in range(ch.n_sub())])
+            ch.step(idx, rs.randn(ch.noise_len()))
+            if it >= burn:
+                xs[it - burn] = OS.flat(ch.theta)
+        means.append(xs.mean(0)); variances.append(xs.var(0))
+    return np.array(means), np.array(variances)
+
+
+def _device_moments(case, algo, cv, n_chains, burn, keep, seed, shared, opt_iters):
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib
+    from tests.cases import device_setup
+    dev = device_setup(case, algo, cv, n_chains=n_chains, seed=seed, L=3, n_iters_opt=opt_iters, sharedMode=shared)
+    S.initSess(dev, verbose=False)
+    L = _lib.load()
+    _lib.check(L.sgm_run(dev.handle, burn, 0))
+    _lib.check(L.sgm_run(dev.handle, keep, 1))
+    ch = S.getChains(dev)
+    flat = np.concatenate([np.asarray(v).reshape(n_chains, keep, -1) for v in ch.values()], axis=2)   # [C, keep, P] in flat parameter order
+    return flat.mean(1), flat.var(1)
+
+
+MOMENT_CASES = [("mixture", "sghmc", False, False), ("mixture", "sgld", True, True), ("logistic5", "sgld", False, False),
+                ("logistic5", "sgldcv_per_chain", True, False), ("logistic5", "sgld", True, True), ("logistic5", "sgnht", True, True)]
+
+
+@pytest.mark.parametrize("case_name,algo,cv,shared", MOMENT_CASES)
+def test_posterior_moments_match_the_oracle(lib, case_name, algo, cv, shared, n_dev=96, n_orc=12, burn=300, keep=1500):
+    """North star: "with device RNG, posterior mean and variance agree with the reference within Monte Carlo error".  Many device chains
+    (Philox streams) against independent float64 oracle chains (numpy streams) of the SAME algorithm and tuning: per coordinate, the
+    difference of the across-chain averages of the chain means (and of the chain variances) must be within 4 standard errors.
+    shared = one mode for all device chains: pooling chains that share a mode must not bias the posterior."""
+    from tests.cases import make_case
+    algo = "sgld" if algo == "sgldcv_per_chain" else algo
+    case = make_case(case_name)
+    # step sizes large enough to mix within a few hundred iterations on the N = 3000-4000 row test datasets
+    case = dict(case, eps={"mixture": 2e-4, "logistic5": 2e-4}[case_name], opt_eps=1e-4)
+    if algo == "sgnht":
+        case["eps"] = 5e-5
+    opt_iters = 300 if cv else 0
+    m_dev, v_dev = _device_moments(case, algo, cv, n_dev, burn, keep, seed=2026, shared=shared, opt_iters=opt_iters)
+    m_orc, v_orc = _oracle_moments(case, algo, cv, n_orc, burn, keep, seed=7, opt_iters=opt_iters)
+    for what, d, o in (("mean", m_dev, m_orc), ("variance", v_dev, v_orc)):
+        diff = d.mean(0) - o.mean(0)
+        se = np.sqrt(d.var(0, ddof=1) / len(d) + o.var(0, ddof=1) / len(o))
+        z = np.abs(diff) / np.maximum(se, 1e-300)
+        assert (z < 4.0).all(), f"{case_name} {algo} cv={cv} shared={shared}: posterior {what} differs: z = {np.round(z, 2)}, diff = {diff}, se = {se}"
