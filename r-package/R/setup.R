@@ -15,7 +15,7 @@ createSGMCMC = function( logLik, logPrior, dataset, params, stepsize, minibatchS
             as.double( unlist( alpha[ names( params ) ] ) ), as.double( unlist( a[ names( params ) ] ) ) )
     info = .Call( C_sgm_info, handle )
     list( "N" = info[1], "data" = dataset, "n" = info[2], "stepsize" = stepsize, "params" = params,
-            "handle" = handle, "nChains" = as.integer( nChains ), "P" = info[3] )
+            "handle" = handle, "nChains" = as.integer( nChains ), "P" = info[3], "logLik" = logLik )
 }
 
 # If stepsizes or a or alpha tuning constants are not in a list format then convert (reference R/setup.R:160-170)

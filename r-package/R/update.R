@@ -7,32 +7,33 @@ sgmcmcStep.sgnht = function( sgmcmc, sess ) invisible( .Call( C_sgm_step, sess )
 
 initSess = function( sgmcmc, verbose = TRUE ) UseMethod( "initSess" )
 initSess.sgmcmc = function( sgmcmc, verbose = TRUE ) {
-    .Call( C_sgm_init, sgmcmc$handle )
+    .Call( C_sgm_init, sgmcmc$handle, as.integer( verbose ) )
     return( sgmcmc$handle )
 }
 initSess.sgmcmccv = function( sgmcmc, verbose = TRUE ) {
     if ( verbose ) message( "\nFinding initial MAP estimates..." )
-    .Call( C_sgm_init, sgmcmc$handle )    # mode finder + full-data gradient + theta := theta_hat, all on the device
+    # mode finder (progress line + NaN check every 100 iterations, printed by the shim), full-data gradient, theta := theta_hat: on the device
+    .Call( C_sgm_init, sgmcmc$handle, as.integer( verbose ) )
     return( sgmcmc$handle )
 }
 
+# reference R/update.R:145-163.  The loop, storeState and checkDivergence (every 100 iterations) run inside ONE library call; the chain
+# streams to the host while later iterations are sampled.  "Chain diverged, try decreasing stepsize" arrives as an R error.
 runSGMCMC = function( sgmcmc, paramsRaw, options ) {
     sess = initSess( sgmcmc, options$verbose )
-    .Call( C_sgm_reset_chain, sess )
-    .Call( C_sgm_reserve_chain, sess, options$nIters )
     if ( options$verbose ) message( "\nSimulating from SGMCMC algorithm..." )
-    done = 0
-    while ( done < options$nIters ) {
-        chunk = min( 100 - done %% 100, options$nIters - done )      # the reference's check / progress cadence
-        .Call( C_sgm_run, sess, chunk, 1L )
-        done = done + chunk
-        if ( done %% 100 == 0 ) checkDivergence( sess, sgmcmc, done, options$verbose )
-    }
-    return( getChains( sgmcmc, sess, paramsRaw, options$nIters ) )
+    buf = .Call( C_sgm_sample, sess, options$nIters, sgmcmc$nChains, as.integer( options$verbose ) )
+    return( splitChains( sgmcmc, buf, paramsRaw, options$nIters ) )
 }
 
-checkDivergence = function( sess, sgmcmc, iter, verbose ) {
-    currentEstimate = .Call( C_sgm_est_logpost, sess, sgmcmc$nChains )
-    if ( any( is.nan( currentEstimate ) ) ) stop( "Chain diverged, try decreasing stepsize" )
-    if ( verbose ) message( paste0( "Iteration: ", iter, "\t\tLog posterior estimate: ", currentEstimate[1] ) )
+# sess$run( sgmcmc$estLogPost, fresh minibatch ) of the reference (R/update.R:198-199), one value per chain
+estLogPost = function( sgmcmc, sess ) .Call( C_sgm_est_logpost, sess, sgmcmc$nChains )
+
+# logLik( current params, testset ) per chain, on the device: replaces the TensorFlow tensors a user of the reference builds from
+# sgld$params to monitor a test-set log loss (vignettes/nn.Rmd:113-123, logisticRegression.Rmd:89-115)
+heldoutLogLik = function( sgmcmc, sess, testset ) {
+    m = resolveModel( sgmcmc$logLik, NULL )
+    data = lapply( testset[ m$dataNames ], function( x ) { storage.mode( x ) = "double"; x } )
+    if ( any( sapply( data, is.null ) ) ) stop( paste0( "testset entries required: ", paste( m$dataNames, collapse = ", " ) ) )
+    .Call( C_sgm_heldout_loglik, sess, data, sgmcmc$nChains )
 }

@@ -81,7 +81,62 @@ SEXP C_sgm_create(SEXP spec, SEXP dataset, SEXP params, SEXP stepsize, SEXP alph
     return ptr;
 }
 
-SEXP C_sgm_init(SEXP ptr) { check(sgm_init(handle_of(ptr))); return R_NilValue; }
+/* checkOptDivergence / checkDivergence progress lines (reference R/controlVariates.R:121-123, R/update.R:204-206): the library
+ * computes the log posterior estimate on the device every 100 iterations and calls back on this (the R main) thread */
+static void progress_line(void* user, int32_t phase, int64_t iter, const double* logpost, int32_t n) {
+    (void)phase;
+    if (!user || !*(const int*)user) return;   /* verbose = FALSE */
+    double v = 0;
+    for (int i = 0; i < n; ++i) v += logpost[i];
+    REprintf("Iteration: %lld\t\tLog posterior estimate: %g\n", (long long)iter, n > 0 ? v / n : v);   /* message() writes to stderr */
+}
+
+SEXP C_sgm_init(SEXP ptr, SEXP verbose) {
+    sgm_handle* h = handle_of(ptr);
+    int v = Rf_asInteger(verbose);
+    check(sgm_set_progress(h, progress_line, &v));
+    const int rc = sgm_init(h);
+    sgm_set_progress(h, NULL, NULL);
+    check(rc);
+    return R_NilValue;
+}
+
+/* runSGMCMC's whole loop in one call (reference R/update.R:145-163): n_iters steps, every state stored, the chain streamed to the host
+ * while later iterations run, divergence check + progress line every 100 iterations.  Returns [iters x P x nChains] doubles. */
+SEXP C_sgm_sample(SEXP ptr, SEXP n_iters, SEXP n_chains, SEXP verbose) {
+    sgm_handle* h = handle_of(ptr);
+    const R_xlen_t iters = (R_xlen_t)Rf_asReal(n_iters);
+    const int P = sgm_num_scalars(h), C = Rf_asInteger(n_chains);
+    int v = Rf_asInteger(verbose);
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, iters * P * C));
+    check(sgm_set_progress(h, progress_line, &v));
+    const int rc = sgm_sample(h, (int64_t)iters, 100, REAL(out));
+    sgm_set_progress(h, NULL, NULL);
+    check(rc);
+    R_CheckUserInterrupt();
+    UNPROTECT(1);
+    return out;
+}
+
+/* logLik(current params, testset) per chain on the device (replaces the user-built TensorFlow tensors of the reference's vignettes,
+ * vignettes/nn.Rmd:113-123, logisticRegression.Rmd:89-115).  testset: named list of double arrays like the dataset. */
+SEXP C_sgm_heldout_loglik(SEXP ptr, SEXP testset, SEXP n_chains) {
+    sgm_handle* h = handle_of(ptr);
+    const int nd = (int)XLENGTH(testset);
+    sgm_array* arr = (sgm_array*)R_alloc(nd, sizeof(sgm_array));
+    SEXP dn = Rf_getAttrib(testset, R_NamesSymbol);
+    for (int i = 0; i < nd; ++i) {
+        SEXP x = VECTOR_ELT(testset, i);
+        memset(&arr[i], 0, sizeof arr[i]);
+        arr[i].name = CHAR(STRING_ELT(dn, i)); arr[i].data = REAL(x);
+        fill_dims(x, &arr[i].ndim, arr[i].dims);
+        if (arr[i].ndim == 0) arr[i].ndim = 1;
+    }
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(n_chains)));
+    check(sgm_heldout_loglik(h, arr, nd, REAL(out)));
+    UNPROTECT(1);
+    return out;
+}
 SEXP C_sgm_step(SEXP ptr) { check(sgm_step(handle_of(ptr))); return R_NilValue; }
 
 /* runSGMCMC's inner loop: n_iters steps on the device, then back to R (progress line, R_CheckUserInterrupt) */
@@ -131,7 +186,8 @@ SEXP C_sgm_info(SEXP ptr) {
 }
 
 static const R_CallMethodDef call_methods[] = {
-    {"C_sgm_create", (DL_FUNC)&C_sgm_create, 6}, {"C_sgm_init", (DL_FUNC)&C_sgm_init, 1},
+    {"C_sgm_create", (DL_FUNC)&C_sgm_create, 6}, {"C_sgm_init", (DL_FUNC)&C_sgm_init, 2},
+    {"C_sgm_sample", (DL_FUNC)&C_sgm_sample, 4}, {"C_sgm_heldout_loglik", (DL_FUNC)&C_sgm_heldout_loglik, 3},
     {"C_sgm_step", (DL_FUNC)&C_sgm_step, 1}, {"C_sgm_run", (DL_FUNC)&C_sgm_run, 3},
     {"C_sgm_reserve_chain", (DL_FUNC)&C_sgm_reserve_chain, 2}, {"C_sgm_reset_chain", (DL_FUNC)&C_sgm_reset_chain, 1},
     {"C_sgm_get_params", (DL_FUNC)&C_sgm_get_params, 2}, {"C_sgm_copy_chain", (DL_FUNC)&C_sgm_copy_chain, 2},

@@ -31,3 +31,25 @@ test_that( "the same seed gives the same chain", {
 test_that( "an ordinary closure is rejected, never differentiated on the CPU", {
     expect_error( sgldSetup( function( params, dataset ) 0, list( X = rnorm( 10 ) ), list( theta = 0 ), 1e-4 ), "cannot be differentiated on the device" )
 } )
+
+test_that( "several chains come back with a leading chain dimension; one chain keeps the reference's shapes", {
+    skipWithoutDevice()
+    data = list( "X" = matrix( rnorm( 2000 ), ncol = 2 ) )
+    params = list( "theta" = c( 0, 0 ) )
+    one = sgld( gaussMeanLogLik(), data, params, 1e-4, logPrior = normalPrior( 10 ), minibatchSize = 50, nIters = 120, verbose = FALSE, seed = 1 )
+    expect_equal( dim( one$theta ), c( 120, 2 ) )
+    sg = sgldSetup( gaussMeanLogLik(), data, params, 1e-4, logPrior = normalPrior( 10 ), minibatchSize = 50, seed = 1, nChains = 4L )
+    many = sgmcmc:::runSGMCMC( sg, params, list( "nIters" = 120, "verbose" = FALSE ) )
+    expect_equal( dim( many$theta ), c( 4, 120, 2 ) )
+    expect_equal( many$theta[ 1, , ], one$theta )           # chain 1 of a multi-chain run is the single-chain run (same stream)
+} )
+
+test_that( "heldoutLogLik replaces the user-built TensorFlow tensors of the vignettes", {
+    skipWithoutDevice()
+    X = matrix( rnorm( 4000 ), ncol = 4 ); y = as.numeric( runif( 1000 ) < 0.5 )
+    sg = sgldSetup( logisticLogLik(), list( "X" = X, "y" = y ), list( "bias" = 0, "beta" = matrix( 0, 4, 1 ) ), 1e-4,
+            logPrior = laplacePrior(), minibatchSize = 100, seed = 2 )
+    sess = initSess( sg, verbose = FALSE )
+    ll = heldoutLogLik( sg, sess, list( "X" = X[ 1:200, ], "y" = y[ 1:200 ] ) )
+    expect_equal( ll, 200 * log( 0.5 ), tolerance = 1e-6 )    # bias = 0, beta = 0: every label has probability 1/2
+} )

@@ -29,6 +29,8 @@ SEXP Rf_mkChar(const char* s);
 double Rf_asReal(SEXP x);
 int Rf_asInteger(SEXP x);
 void Rf_error(const char* fmt, ...) __attribute__((noreturn));
+void REprintf(const char* fmt, ...);
+void Rprintf(const char* fmt, ...);
 char* R_alloc(size_t n, int size);
 void R_CheckUserInterrupt(void);
 SEXP R_MakeExternalPtr(void* p, SEXP tag, SEXP prot);

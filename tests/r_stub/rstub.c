@@ -43,6 +43,8 @@ void rstub_set_names(SEXP x, const char* const* names) {
 SEXP Rf_getAttrib(SEXP x, SEXP name) { return name == R_DimSymbol ? x->dim : name == R_NamesSymbol ? x->names : R_NilValue; }
 double Rf_asReal(SEXP x) { return x->type == REALSXP ? REAL(x)[0] : x->type == INTSXP ? (double)INTEGER(x)[0] : 0.0; }
 int Rf_asInteger(SEXP x) { return (int)Rf_asReal(x); }
+void REprintf(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); }
+void Rprintf(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stdout, fmt, ap); va_end(ap); }
 void Rf_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -14,7 +14,9 @@
 #include "R_ext/Rdynload.h"
 
 SEXP C_sgm_create(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
-SEXP C_sgm_init(SEXP);
+SEXP C_sgm_init(SEXP, SEXP);
+SEXP C_sgm_sample(SEXP, SEXP, SEXP, SEXP);
+SEXP C_sgm_heldout_loglik(SEXP, SEXP, SEXP);
 SEXP C_sgm_step(SEXP);
 SEXP C_sgm_run(SEXP, SEXP, SEXP);
 SEXP C_sgm_get_params(SEXP, SEXP);
@@ -37,7 +39,7 @@ int main(int argc, char** argv) {
     int n_reg = 0;
     for (const R_CallMethodDef* m = rstub_registered; m && m->name; ++m) ++n_reg;
     printf("registered %d .Call routines\n", n_reg);
-    if (argc < 2 || strcmp(argv[1], "run") != 0) return n_reg == 10 ? 0 : 1;
+    if (argc < 2 || strcmp(argv[1], "run") != 0) return n_reg == 12 ? 0 : 1;
 
     const int N = 2000, d = 6, chains = 3;
     SEXP X = Rf_allocMatrix(REALSXP, N, d), y = Rf_allocVector(REALSXP, N);
@@ -66,7 +68,7 @@ int main(int argc, char** argv) {
     SEXP h = C_sgm_create(spec, dataset, params, step, alpha, a);
     SEXP info = C_sgm_info(h);
     printf("info N=%.0f n=%.0f P=%.0f\n", REAL(info)[0], REAL(info)[1], REAL(info)[2]);
-    C_sgm_init(h);
+    C_sgm_init(h, num(0));
     C_sgm_step(h);
     C_sgm_run(h, num(20), num(1));
     SEXP th = C_sgm_get_params(h, num(chains));
@@ -82,6 +84,27 @@ int main(int argc, char** argv) {
         for (int p = 0; p < P; ++p) printf(" %.17g", REAL(ch)[(iters - 1) + iters * p]);
     }
     printf("\nlogpost_finite %d\n", isfinite(REAL(lp)[0]) ? 1 : 0);
+    {   /* runSGMCMC as the R file makes it: a second sampler, initSess (verbose: progress lines on stderr), ONE C_sgm_sample call */
+        SEXP h2 = C_sgm_create(spec, dataset, params, step, alpha, a);
+        C_sgm_init(h2, num(1));
+        SEXP ch2 = C_sgm_sample(h2, num(230), num(chains), num(1));
+        const int P = (int)REAL(info)[2];
+        printf("sampled_doubles %ld\nsampled_last", (long)XLENGTH(ch2));
+        for (int p = 0; p < P; ++p) printf(" %.17g", REAL(ch2)[229 + 230 * p]);
+        SEXP th2 = C_sgm_get_params(h2, num(chains));
+        printf("\nsampled_state");
+        for (int p = 0; p < P; ++p) printf(" %.17g", REAL(th2)[p]);
+        /* heldoutLogLik on the first 300 rows */
+        SEXP Xt = Rf_allocMatrix(REALSXP, 300, d), yt = Rf_allocVector(REALSXP, 300);
+        for (int i = 0; i < 300; ++i) { for (int j = 0; j < d; ++j) REAL(Xt)[i + 300 * (size_t)j] = REAL(X)[i + (size_t)N * j]; REAL(yt)[i] = REAL(y)[i]; }
+        SEXP testset = Rf_allocVector(VECSXP, 2);
+        SET_VECTOR_ELT(testset, 0, Xt); SET_VECTOR_ELT(testset, 1, yt);
+        rstub_set_names(testset, dnames);
+        SEXP ho = C_sgm_heldout_loglik(h2, testset, num(chains));
+        printf("\nheldout");
+        for (int c = 0; c < chains; ++c) printf(" %.17g", REAL(ho)[c]);
+        printf("\n");
+    }
     rstub_run_finalizers();   /* what R's garbage collector does with the external pointer */
     return 0;
 }
