@@ -365,6 +365,49 @@ def quick_workload(name, steps=5, iters=None):
                          "bytes_per_chain_iter": w["bytes_per_chain_iter"], "note": w["bound_note"]}}
 
 
+
+def run_leg_in_child(leg, args, timeout_s=420):
+    """Runs one optional leg (`--leg NAME`) of this script in its own process (N = 1 only) and returns its JSON object.  A leg that
+    faults on the device (a sticky CUDA error ends every later call of the process that raised it) or hangs then costs its own entry,
+    not the main line.  The child measures with CUDA events exactly as the parent would; process start-up is outside its timed regions."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--leg", leg, "--workload", args.workload, "--modes", str(args.modes), "--gpus", "1"]
+    if args.chains:
+        cmd += ["--chains", str(args.chains)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"error": f"leg {leg}: no result within {timeout_s} s (child process killed)"}
+    for ln in reversed(p.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            try:
+                return json.loads(ln)
+            except ValueError:
+                break
+    return {"error": f"leg {leg}: child exited {p.returncode} without a result", "stderr_tail": p.stderr[-400:]}
+
+
+def leg_result(leg, w, args):
+    """One optional measurement by name (the body of a `--leg` child)."""
+    try:
+        if leg == "modes":
+            return many_mode_full_gradient(w, 0, 1, args.modes)
+        if leg.startswith("quick:"):
+            return quick_workload(leg.split(":", 1)[1])
+        return {"error": f"unknown leg {leg}"}
+    except Exception as e:   # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
+def run_leg(args, w):
+    """Child side of run_leg_in_child: one JSON object on stdout."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(0)
+    print(json.dumps(leg_result(args.leg, w, args)))
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -388,6 +431,9 @@ def run_ours(args, w):
     lib = _lib.load()
     chains_local = w["chains"]
     I = args.iters_per_step
+    total_chains = chains_local * world
+    peak, peak_src = measured_peaks()
+    errors = {}
 
     def barrier():
         if world > 1:
@@ -405,45 +451,28 @@ def run_ours(args, w):
         barrier()
         comm_ms = 1000.0 * (time.perf_counter() - t0)
 
-    # ---- end-to-end leg through the public API with HOST buffers: Setup (dataset H2D) + initSess + K x sgm_sample (runSGMCMC's loop in one
-    # call: the chain streams to the host as float32 while later iterations run, widened to float64 into the caller's array)
-    barrier()
-    t_e2e0 = time.perf_counter()
     sharded = bool(args.peer_shards and world > 1 and w["family"] == "logistic")
     synth_main = dict(w["synth"], seed=w["synth"].get("seed", 13) + rank) if (sharded and w.get("synth")) else None   # different rows per rank
-    sg = make_sampler(w, rank, world, chains_local, synth=synth_main)
-    if sharded:
-        attach_peer_shards(sg, rank, world)
-    if world > 1 and w["cv"]:
-        comm_init(sg, rank, world)
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter()
+
+    def new_sampler():
+        sg = make_sampler(w, rank, world, chains_local, synth=synth_main)
+        if sharded:
+            attach_peer_shards(sg, rank, world)
+        if world > 1 and w["cv"]:
+            comm_init(sg, rank, world)
+        return sg
+
+    def drop(sg):
+        if sharded:   # unmap on every rank before any owner frees its shard
+            _lib.check(lib.sgm_detach_peer_shards(sg.handle))
+            barrier()
+
+    # ---- device-resident leg FIRST (the line's `value` and roofline): W warm-up steps, then exactly K timed steps
+    sg = new_sampler()
     sess = S.initSess(sg, verbose=False)
     init_ms, init_launches = V.lastTiming(sg)
     fg_ms, fg_bytes = V.lastFullGradTiming(sg) if w["cv"] else (0.0, 0)
     reduce_ms, _ = V.lastCollectiveTiming(sg) if w["cv"] else (0.0, 0.0)
-    torch.cuda.synchronize()
-    t_init = time.perf_counter()
-    host_chain = np.empty(chains_local * sg.P * I, dtype=np.float64)
-    hptr = host_chain.ctypes.data_as(_lib._PD)
-    e2e_launches = 0
-    for _ in range(args.steps):
-        _lib.check(lib.sgm_sample(sg.handle, I, 100, hptr))
-        e2e_launches += V.lastTiming(sg)[1]
-    barrier()
-    t_e2e = time.perf_counter() - t_e2e0
-    t_run = time.perf_counter() - t_init
-    if world > 1:
-        t = torch.tensor([t_e2e, t_run, t_setup - t_e2e0, t_init - t_setup], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e, t_run, t_up, t_in = (float(x) for x in t)
-    else:
-        t_up, t_in = t_setup - t_e2e0, t_init - t_setup
-    d2h_bytes = chains_local * sg.P * I * 4
-    h2d_total = sum(np.asarray(v).size * 8 for v in (w["data"] or {}).values())
-    del host_chain
-
-    # ---- device-resident leg: W warm-up steps, then exactly K timed steps
     _lib.check(lib.sgm_reserve_chain(sg.handle, I))
     with ClockSampler(local) as clk:
         dt, kernel_ms, launches = device_leg(sg, lib, V, _lib, I, args.steps, args.warmup, barrier)
@@ -452,10 +481,7 @@ def run_ours(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t[0])
     clocks = clk.summary()
-
-    total_chains = chains_local * world
     value = total_chains * I * args.steps / dt
-    peak, peak_src = measured_peaks()
     k_ms = float(np.mean(kernel_ms))
     achieved = chains_local * I * w["bytes_per_chain_iter"] / (k_ms * 1e-3) / 1e9
     dataset_mb = {"c1": 0.08, "c2": 0.08, "c3": 130.1, "c4": 191.0, "c5": 51400.0}.get(args.workload)
@@ -479,48 +505,89 @@ def run_ours(args, w):
                      "kernel_ms_per_launch": k_ms, "bytes_per_chain_iter": w["bytes_per_chain_iter"], "peak_source": peak_src,
                      "note": w["bound_note"]},
         "clocks": clocks,
-        "e2e": {"value": total_chains * I * args.steps / t_e2e, "unit": UNIT,
-                "h2d_bytes_per_step": h2d_total / args.steps, "d2h_bytes_per_step": d2h_bytes,
-                "seconds": t_e2e,
-                "breakdown_ms": {"upload_setup": 1000.0 * t_up, "init_mode_and_full_gradient": 1000.0 * t_in, "run_and_copy_out": 1000.0 * t_run,
-                                 "run_and_copy_out_per_step": 1000.0 * t_run / args.steps},
-                "steady_state_value": total_chains * I * args.steps / t_run,
-                "comm_init_ms_outside": comm_ms,
-                "includes": "Setup (dataset upload, float64 host arrays) + initSess (mode finder, full gradient) + K x sgm_sample (sampling with the chain streamed "
-                            "out as float32 in 100-iteration blocks on a second stream and widened to float64 into a host array; divergence check every 100 iterations)",
-                "gpu_launches": e2e_launches},
+        "e2e": None,
         "gpu_launches": launches,
     }
-    if w["cv"]:
-        if w["family"] == "logistic":   # steady-state figure: 20 launches back to back (the one inside initSess sits between launch gaps)
-            fg_ms, fg_bytes = V.benchFullGradient(sg, 20)
-        line["cv_full_gradient"] = {"ms": fg_ms, "bytes": fg_bytes, "GBps": (fg_bytes / (fg_ms * 1e-3) / 1e9) if fg_ms > 0 else None,
-                                    "frac_of_hbm_peak": (fg_bytes / (fg_ms * 1e-3) / 1e9 / peak) if fg_ms > 0 else None,
-                                    "rows_per_rank": fg_bytes // (16 * (w["params"]["beta"].shape[0] // 4 + 1)) if w["family"] == "logistic" else None,
-                                    "init_ms_total": init_ms,
-                                    "collective_ms": reduce_ms if world > 1 else None,
-                                    "note": "one mode (shared by all chains): HBM-bound stream, not a GEMM; bytes = rows x row stride; collective_ms = the all-reduce "
-                                            "of the P-vector inside initSess, timed on the device (sharding this pass pays only while rows/rank x row bytes is tens of MB: "
-                                            "the reduction of 55 doubles costs more than a 12 us kernel saves)"}
-    if sharded:   # unmap on every rank before any owner frees its shard
-        _lib.check(lib.sgm_detach_peer_shards(sg.handle))
+    try:
+        if w["cv"]:
+            if w["family"] == "logistic":   # steady-state figure: 20 launches back to back (the one inside initSess sits between launch gaps)
+                fg_ms, fg_bytes = V.benchFullGradient(sg, 20)
+            line["cv_full_gradient"] = {"ms": fg_ms, "bytes": fg_bytes, "GBps": (fg_bytes / (fg_ms * 1e-3) / 1e9) if fg_ms > 0 else None,
+                                        "frac_of_hbm_peak": (fg_bytes / (fg_ms * 1e-3) / 1e9 / peak) if fg_ms > 0 else None,
+                                        "rows_per_rank": fg_bytes // (16 * (w["params"]["beta"].shape[0] // 4 + 1)) if w["family"] == "logistic" else None,
+                                        "init_ms_total": init_ms,
+                                        "collective_ms": reduce_ms if world > 1 else None,
+                                        "note": "one mode (shared by all chains): HBM-bound stream, not a GEMM; bytes = rows x row stride; collective_ms = the all-reduce "
+                                                "of the P-vector inside initSess, timed on the device (sharding this pass pays only while rows/rank x row bytes is tens of MB: "
+                                                "the reduction of 55 doubles costs more than a 12 us kernel saves)"}
+    except Exception as e:   # noqa: BLE001
+        errors["cv_full_gradient"] = f"{type(e).__name__}: {str(e)[:300]}"
+    drop(sg)
+    del sess, sg
+
+    # ---- end-to-end leg through the public API with HOST buffers: Setup (dataset H2D) + initSess + K x sgm_sample (runSGMCMC's loop in one
+    # call: the chain streams to the host as float32 while later iterations run, widened to float64 into the caller's array).  A fresh sampler:
+    # nothing of the device leg above is reused.
+    try:
         barrier()
+        t_e2e0 = time.perf_counter()
+        sg = new_sampler()
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter()
+        sess = S.initSess(sg, verbose=False)
+        torch.cuda.synchronize()
+        t_init = time.perf_counter()
+        host_chain = np.empty(chains_local * sg.P * I, dtype=np.float64)
+        hptr = host_chain.ctypes.data_as(_lib._PD)
+        e2e_launches = 0
+        for _ in range(args.steps):
+            _lib.check(lib.sgm_sample(sg.handle, I, 100, hptr))
+            e2e_launches += V.lastTiming(sg)[1]
+        barrier()
+        t_e2e = time.perf_counter() - t_e2e0
+        t_run = time.perf_counter() - t_init
+        if world > 1:
+            t = torch.tensor([t_e2e, t_run, t_setup - t_e2e0, t_init - t_setup], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e, t_run, t_up, t_in = (float(x) for x in t)
+        else:
+            t_up, t_in = t_setup - t_e2e0, t_init - t_setup
+        finite = bool(np.isfinite(host_chain[-sg.P:]).all())
+        d2h_bytes = chains_local * sg.P * I * 4
+        h2d_total = sum(np.asarray(v).size * 8 for v in (w["data"] or {}).values())
+        del host_chain
+        line["e2e"] = {"value": total_chains * I * args.steps / t_e2e, "unit": UNIT,
+                       "h2d_bytes_per_step": h2d_total / args.steps, "d2h_bytes_per_step": d2h_bytes,
+                       "seconds": t_e2e,
+                       "breakdown_ms": {"upload_setup": 1000.0 * t_up, "init_mode_and_full_gradient": 1000.0 * t_in, "run_and_copy_out": 1000.0 * t_run,
+                                        "run_and_copy_out_per_step": 1000.0 * t_run / args.steps},
+                       "steady_state_value": total_chains * I * args.steps / t_run,
+                       "comm_init_ms_outside": comm_ms, "last_draw_finite": finite,
+                       "includes": "Setup (dataset upload, float64 host arrays) + initSess (mode finder, full gradient) + K x sgm_sample (sampling with the chain streamed "
+                                   "out as float32 in 100-iteration blocks on a second stream and widened to float64 into a host array; divergence check every 100 iterations)",
+                       "gpu_launches": e2e_launches}
+        drop(sg)
+        del sess, sg
+    except Exception as e:   # noqa: BLE001  (the device-timed line above must survive a failure of this leg)
+        errors["e2e"] = f"{type(e).__name__}: {str(e)[:300]}"
+
+    # ---- optional legs.  N = 1: each in its own process (a device fault there cannot take the main line with it)
     if w["cv"] and w["family"] == "logistic" and not args.no_modes:
-        del sg, sess
-        line["cv_full_gradient_modes"] = many_mode_full_gradient(w, rank, world, args.modes)
+        try:
+            line["cv_full_gradient_modes"] = (run_leg_in_child("modes", args) if world == 1 else many_mode_full_gradient(w, rank, world, args.modes))
+        except Exception as e:   # noqa: BLE001
+            errors["cv_full_gradient_modes"] = f"{type(e).__name__}: {str(e)[:300]}"
     if world == 1 and not args.no_extra:
-        extra = {}
-        for name in ("c1", "c2", "c4"):
-            if name != args.workload:
-                try:
-                    extra[name] = quick_workload(name)
-                except Exception as e:   # noqa: BLE001  (an extra measurement must not lose the main line)
-                    extra[name] = {"error": str(e)[:300]}
-        line["other_workloads"] = extra
+        line["other_workloads"] = {name: run_leg_in_child("quick:" + name, args) for name in ("c1", "c2", "c4") if name != args.workload}
     if rank == 0 and world == 1 and not args.no_cpu:
-        ips, note, fg, _ = cpu_proxy(w, args.cpu_budget, 1)
-        line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": 1, "kind": "port", "sample": note,
-                                "full_gradient_s": fg, "label": "TF-proxy (torch CPU) -- not the reference binary"}
+        try:
+            ips, note, fg, _ = cpu_proxy(w, args.cpu_budget, 1)
+            line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": 1, "kind": "port", "sample": note,
+                                    "full_gradient_s": fg, "label": "TF-proxy (torch CPU) -- not the reference binary"}
+        except Exception as e:   # noqa: BLE001
+            errors["cpu_baseline"] = f"{type(e).__name__}: {str(e)[:300]}"
+    if errors:
+        line["errors"] = errors
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -541,11 +608,14 @@ def main():
     ap.add_argument("--modes", type=int, default=1024, help="modes of the many-mode control-variate full gradient leg (logistic *cv workloads)")
     ap.add_argument("--no-modes", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the compact c1 / c2 / c4 measurements added to the line at N = 1")
+    ap.add_argument("--leg", default=None, help="internal: run ONE optional leg (modes | quick:c1 | quick:c2 | quick:c4) and print its JSON object")
     ap.add_argument("--peer-shards", action="store_true",
                     help="N > 1, logistic workloads: every rank keeps its own rows and maps the peers' (the c5 config at N = world x rows/GPU)")
     args = ap.parse_args()
     w = workload(args.workload, args.chains)
-    if args.impl == "reference":
+    if args.leg:
+        run_leg(args, w)
+    elif args.impl == "reference":
         run_reference(args, w)
     else:
         run_ours(args, w)

@@ -51,6 +51,8 @@ def test_bench_prints_one_contract_line(monkeypatch, main):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
     monkeypatch.setattr(__graft_entry__, "build", lambda *a, **k: None)
     monkeypatch.setattr(bench, "measure_tf32_peak", lambda *a, **k: (900.0, 800.0))
+    # the optional legs run in child processes on a GPU box; here (emulated build, loaded into THIS process) they run in place
+    monkeypatch.setattr(bench, "run_leg_in_child", lambda leg, args, timeout_s=0: bench.leg_result(leg, bench.workload(args.workload, None), args))
     orig = bench.workload
     tiny_workload_w = tiny_workload
     bench.workload = types.FunctionType(tiny_workload_w.__code__, tiny_workload_w.__globals__)
@@ -76,13 +78,23 @@ def test_bench_prints_one_contract_line(monkeypatch, main):
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["traffic"] is None
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "breakdown_ms"} and line["e2e"]["d2h_bytes_per_step"] > 0
     assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
-    assert line["gpu_launches"] >= 2
+    assert line["gpu_launches"] >= 2 and "errors" not in line, line.get("errors")
+    assert line["e2e"]["last_draw_finite"] is True
     assert set(line["other_workloads"]) == {"c1", "c2", "c4"} - {main}
     assert all("error" not in v for v in line["other_workloads"].values()), line["other_workloads"]
     if main == "c3":
         assert line["cv_full_gradient"]["GBps"] > 0
         m = line["cv_full_gradient_modes"]
         assert m["TFLOPs"] > 0 and m["peak"] == 800.0 and abs(m["frac_of_3xtf32_ceiling"] - 3 * m["frac"]) < 1e-12
+
+
+def test_optional_leg_failure_costs_only_its_own_entry():
+    """A leg's child process that cannot produce a result (here: no CUDA device in this container) comes back as an error object."""
+    import bench
+    args = types.SimpleNamespace(workload="c1", modes=16, chains=None)
+    r = bench.run_leg_in_child("quick:c2", args, timeout_s=300)
+    assert set(r) >= {"error"} and "child exited" in r["error"], r
+    assert "CUDA device" in r.get("stderr_tail", "")
 
 
 def test_smoke_runs_on_the_emulated_build(monkeypatch, capsys):
