@@ -64,10 +64,11 @@ def test_small_models_shared_memory_dataset(emulated_library, case_name, algo):
     assert ran(emulated_library, "small_chain:smem") >= before + 2, "the default dispatch did not pick the shared-memory variant for a 60-iteration launch"
 
 
-@pytest.mark.parametrize("case_name,algo,cv,n_iters", [("gauss2d", "sgld", False, 250), ("mixture", "sghmc", False, 137), ("logistic54", "sgld", True, 230),
-                                                       ("logistic130", "sgnht", True, 101), ("softmaxnet_small", "sghmc", False, 120)])
-def test_streamed_sampling(case_name, algo, cv, n_iters, capsys):
-    T.test_streamed_sampling_equals_run_then_copy(None, case_name, algo, cv, n_iters, capsys)
+@pytest.mark.parametrize("case_name,algo,cv,n_iters,n_chains", [("gauss2d", "sgld", False, 250, 3), ("mixture", "sghmc", False, 137, 3), ("logistic54", "sgld", True, 230, 3),
+                                                                ("logistic130", "sgnht", True, 101, 3), ("softmaxnet_small", "sghmc", False, 120, 3),
+                                                                ("gauss2d", "sgld", False, 233, 340)])
+def test_streamed_sampling(case_name, algo, cv, n_iters, n_chains, capsys):
+    T.test_streamed_sampling_equals_run_then_copy(None, case_name, algo, cv, n_iters, n_chains, capsys)
 
 
 def test_streamed_sampling_reports_divergence():

@@ -301,19 +301,20 @@ def test_small_models_shared_memory_dataset_equals_global_gather(lib, case_name,
         assert np.array_equal(chains[0][k], chains[1][k]), f"{k}: default dispatch differs"
 
 
-@pytest.mark.parametrize("case_name,algo,cv,n_iters", [("gauss2d", "sgld", False, 250), ("mixture", "sghmc", False, 137), ("logistic54", "sgld", True, 230),
-                                                       ("logistic130", "sgnht", True, 101), ("softmaxnet_small", "sghmc", False, 120)])
-def test_streamed_sampling_equals_run_then_copy(lib, case_name, algo, cv, n_iters, capsys):
+@pytest.mark.parametrize("case_name,algo,cv,n_iters,n_chains", [("gauss2d", "sgld", False, 250, 3), ("mixture", "sghmc", False, 137, 3), ("logistic54", "sgld", True, 230, 3),
+                                                                ("logistic130", "sgnht", True, 101, 3), ("softmaxnet_small", "sghmc", False, 120, 3),
+                                                                ("gauss2d", "sgld", False, 233, 340)])   # wide enough for the threaded, streaming-store widening
+def test_streamed_sampling_equals_run_then_copy(lib, case_name, algo, cv, n_iters, n_chains, capsys):
     """sgm_sample (the whole runSGMCMC loop in one call, the chain streamed out in double-buffered blocks while later iterations run)
     against sgm_run + sgm_copy_chain with the same seed: identical chains; the reference's progress lines every 100 iterations."""
     import sgmcmc_b200 as S
     from sgmcmc_b200 import _lib
     case = make_case(case_name)
-    one = device_setup(case, algo, cv, n_chains=3, seed=77, n_iters_opt=20)
+    one = device_setup(case, algo, cv, n_chains=n_chains, seed=77, n_iters_opt=20)
     S.initSess(one, verbose=False)
     _lib.check(_lib.load().sgm_run(one.handle, n_iters, 1))
     want = {k: np.array(v) for k, v in S.getChains(one).items()}
-    two = device_setup(case, algo, cv, n_chains=3, seed=77, n_iters_opt=20)
+    two = device_setup(case, algo, cv, n_chains=n_chains, seed=77, n_iters_opt=20)
     from sgmcmc_b200 import api as A
     got = A.runSGMCMC(two, case["params"], {"nIters": n_iters, "verbose": True})
     err = capsys.readouterr().err
@@ -327,7 +328,7 @@ def test_streamed_sampling_equals_run_then_copy(lib, case_name, algo, cv, n_iter
     # the sampler state after the call is the last stored state
     last = S.getParams(two, None)
     for k in want:
-        np.testing.assert_array_equal(np.asarray(last[k]).reshape(3, -1), np.asarray(got[k])[:, -1].reshape(3, -1))
+        np.testing.assert_array_equal(np.asarray(last[k]).reshape(n_chains, -1), np.asarray(got[k])[:, -1].reshape(n_chains, -1))
 
 
 def test_streamed_sampling_reports_divergence(lib):
