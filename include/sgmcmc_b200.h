@@ -58,8 +58,11 @@ typedef enum sgm_algo { SGM_ALGO_SGLD = 1, SGM_ALGO_SGHMC = 2, SGM_ALGO_SGNHT = 
 /* One entry of the reference's `dataset` list (R/setup.R:105-113): sliced on dim 0. */
 typedef struct sgm_array {
     const char* name;
-    const double* data; /* column-major; may be NULL iff sgm_config.synth_rows > 0 */
+    const double* data; /* may be NULL iff sgm_config.synth_rows > 0 */
     int32_t ndim;       /* 1 or 2 */
+    int32_t row_major;  /* 0: column-major (R's layout, what the reference passes); 1: row-major (C order, numpy's default).
+                         * Either is packed into the device row format by a kernel; no host-side transposition is ever needed.
+                         * (Occupies what was padding: size and offsets of the struct are unchanged.) */
     int64_t dims[4];
 } sgm_array;
 

@@ -22,7 +22,7 @@ IPC_HANDLE_BYTES = 64
 
 
 class SgmArray(C.Structure):
-    _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_double)), ("ndim", C.c_int32), ("dims", C.c_int64 * 4)]
+    _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_double)), ("ndim", C.c_int32), ("row_major", C.c_int32), ("dims", C.c_int64 * 4)]
 
 
 class SgmParam(C.Structure):

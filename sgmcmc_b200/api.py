@@ -72,6 +72,16 @@ class Session:
         return self.sgmcmc.handle
 
 
+def _host_matrix(x):
+    """A dataset entry as the library takes it: float64, contiguous in EITHER order (sgm_array.row_major says which; the packing into
+    device rows happens in a kernel).  A float64 numpy array in C or Fortran order is passed as it is -- transposing 581,012 x 54
+    doubles on the host (np.asfortranarray) took 0.42 s, more than the rest of a c3 job; anything else is copied once, in C order."""
+    v = np.asarray(x, dtype=np.float64)
+    if v.ndim == 2 and v.flags.f_contiguous and not v.flags.c_contiguous:
+        return v, 0
+    return np.ascontiguousarray(v), 1
+
+
 def _create(logLik, logPrior, dataset, params, stepsize, minibatchSize, seed, algo, cv, *,
             optStepsize=0.0, nItersOpt=0, alpha=0.01, L=5, a=0.01, nChains=1, device=0, sharedMode=False,
             synth=None, chainOffset=0) -> Sgmcmc:
@@ -92,12 +102,13 @@ def _create(logLik, logPrior, dataset, params, stepsize, minibatchSize, seed, al
         if synth is None:
             if nm not in dataset:
                 raise SgmcmcError(_lib.SGM_EINVAL, f"dataset entry '{nm}' is required by {type(logLik).__name__}")
-            v = np.asfortranarray(np.asarray(dataset[nm], dtype=np.float64))
+            v, row_major = _host_matrix(dataset[nm])
             if v.ndim == 0 or v.ndim > 2:
                 raise SgmcmcError(_lib.SGM_EINVAL, f"dataset entry '{nm}' must be a vector or a matrix")
             keep.append(v)
             arrs[i].data = _dptr(v)
             arrs[i].ndim = v.ndim
+            arrs[i].row_major = row_major
             for j, s in enumerate(v.shape):
                 arrs[i].dims[j] = s
     pars = (_lib.SgmParam * len(params))()
@@ -279,7 +290,8 @@ def heldoutLogLik(sgmcmc: Sgmcmc, sess: Session, testset) -> np.ndarray:
     arrs = (_lib.SgmArray * len(names))()
     keep = []
     for i, nm in enumerate(names):
-        v = np.asfortranarray(np.asarray(testset[nm], dtype=np.float64))
+        v, row_major = _host_matrix(testset[nm])
+        arrs[i].row_major = row_major
         keep.append(v)
         arrs[i].name = nm.encode(); arrs[i].data = _dptr(v); arrs[i].ndim = v.ndim
         for j, s_ in enumerate(v.shape):

@@ -189,11 +189,12 @@ static int hat_count(const sgm_handle* h) { return (h->flags & SGM_FLAG_SHARED_M
 // ------------------------------------------------------------------------------------
 // small kernels used by the host layer
 // ------------------------------------------------------------------------------------
-// column-major double [N, cols] -> row-major float rows with stride ld at column offset col0
-__global__ void pack_rows_kernel(const double* __restrict__ src, int64_t N, int cols, float* __restrict__ dst, int ld, int col0) {
+// double [N, cols] (column-major, or row-major when row_major != 0) -> row-major float rows with stride ld at column offset col0;
+// reads are coalesced in either layout
+__global__ void pack_rows_kernel(const double* __restrict__ src, int64_t N, int cols, float* __restrict__ dst, int ld, int col0, int row_major) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * cols) return;
-    const int64_t r = i % N; const int c = (int)(i / N);
+    const int64_t r = row_major ? i / cols : i % N; const int c = (int)(row_major ? i % cols : i / N);
     dst[r * ld + col0 + c] = (float)src[i];
 }
 
@@ -1053,7 +1054,7 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
         CUB(cudaMemsetAsync(h->X, 0, xbytes, h->stream));
         int col0 = 0;
         const int entries = (h->model == SGM_MODEL_GAUSS_MEAN || h->model == SGM_MODEL_MIXTURE2) ? 1 : 2;
-        // one column-major double staging buffer per dataset entry (freed before the next entry is staged)
+        // one double staging buffer per dataset entry, in the caller's layout (freed before the next entry is staged)
         for (int k = 0; k < entries; ++k) {
             const sgm_array& A = cfg->data[k];
             const int cols = A.ndim >= 2 ? (int)A.dims[1] : 1;
@@ -1062,7 +1063,7 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
             if (cudaMalloc(&stage, bytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(SGM_ENOMEM, "cannot allocate %zu staging bytes", bytes)); }
             cudaError_t se = cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream);
             if (se == cudaSuccess) {
-                SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(h->N * cols, 256), 256, 0, h->stream, stage, h->N, cols, h->X, h->ld, col0);
+                SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(h->N * cols, 256), 256, 0, h->stream, stage, h->N, cols, h->X, h->ld, col0, (int)(A.row_major != 0));
                 se = cudaGetLastError();
             }
             if (se == cudaSuccess) se = cudaStreamSynchronize(h->stream);
@@ -1884,7 +1885,7 @@ extern "C" int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t 
         if (cudaMalloc(&stage_buf.p, bytes) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate staging"); }
         double* stage = stage_buf.p;
         CU(cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream));
-        SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(Nh * cols, 256), 256, 0, h->stream, stage, Nh, cols, Xh, h->ld, col0);
+        SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(Nh * cols, 256), 256, 0, h->stream, stage, Nh, cols, Xh, h->ld, col0, (int)(A.row_major != 0));
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));
         col0 += cols;

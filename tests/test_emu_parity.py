@@ -71,6 +71,11 @@ def test_streamed_sampling(case_name, algo, cv, n_iters, n_chains, capsys):
     T.test_streamed_sampling_equals_run_then_copy(None, case_name, algo, cv, n_iters, n_chains, capsys)
 
 
+@pytest.mark.parametrize("case_name", ["gauss2d", "logistic54", "softmaxnet_small"])
+def test_dataset_layouts_upload_identically(case_name):
+    T.test_dataset_layouts_upload_identically(None, case_name)
+
+
 def test_streamed_sampling_reports_divergence():
     T.test_streamed_sampling_reports_divergence(None)
 

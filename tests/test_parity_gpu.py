@@ -331,6 +331,36 @@ def test_streamed_sampling_equals_run_then_copy(lib, case_name, algo, cv, n_iter
         np.testing.assert_array_equal(np.asarray(last[k]).reshape(n_chains, -1), np.asarray(got[k])[:, -1].reshape(n_chains, -1))
 
 
+@pytest.mark.parametrize("case_name", ["gauss2d", "logistic54", "softmaxnet_small"])
+def test_dataset_layouts_upload_identically(lib, case_name):
+    """sgm_array.row_major: a C-order (numpy default), a Fortran-order (R) and a non-contiguous / float32 host matrix all land as the
+    same device rows, equal to float32(host values) (R/setup.R:105-113 feeds float32 placeholders)."""
+    import copy
+    from sgmcmc_b200 import validation as V
+    case = make_case(case_name)
+    names = list(case["loglik"].data_names)
+    got = []
+    for variant in ("C", "F", "strided32"):
+        c2 = copy.copy(case)
+        if variant == "C":
+            c2["data"] = {k: np.ascontiguousarray(np.asarray(v, dtype=np.float64)) for k, v in case["data"].items()}
+        elif variant == "F":
+            c2["data"] = {k: np.asfortranarray(np.asarray(v, dtype=np.float64)) for k, v in case["data"].items()}
+        else:
+            c2["data"] = {k: np.repeat(np.asarray(v, dtype=np.float32), 2, axis=0)[::2] for k, v in case["data"].items()}
+        dev = device_setup(c2, "sgld", False)
+        rows = []
+        for e, nm in enumerate(names):
+            v = np.asarray(case["data"][nm])
+            cols = 1 if v.ndim == 1 else v.shape[1]
+            rows.append(V.copyDataset(dev, e, 0, case["N"], cols).reshape(case["N"], -1))
+        got.append(rows)
+    for e, nm in enumerate(names):
+        want = np.asarray(case["data"][nm], dtype=np.float64).astype(np.float32).astype(np.float64).reshape(case["N"], -1)
+        for rows in got:
+            np.testing.assert_array_equal(rows[e], want, err_msg=nm)
+
+
 def test_streamed_sampling_reports_divergence(lib):
     import sgmcmc_b200 as S
     from sgmcmc_b200._lib import SgmcmcError
