@@ -62,6 +62,14 @@ S.initSess(dev, verbose=False); S.sgmcmcStep(dev, None); assert np.isfinite(V.fl
     ("softmax net: register-staged forward GEMM and update", """
 case = make_case('softmaxnet_small'); dev = device_setup(case, 'sgld', True, n_chains=2, n_iters_opt=3); V.setOption(dev, 'nn_stage1', 1); V.setOption(dev, 'nn_update', 1)
 S.initSess(dev, verbose=False); S.sgmcmcStep(dev, None); assert np.isfinite(V.flatParams(dev)).all()"""),
+    ("Gaussian families: dataset staged in shared memory once per CTA (TMA bulk copies)", "T.test_small_models_shared_memory_dataset_equals_global_gather(None, 'gauss2d', 'sgld'); T.test_small_models_shared_memory_dataset_equals_global_gather(None, 'mixture', 'sghmc')"),
+    ("dataset upload from C-order / column-major / strided host matrices", "T.test_dataset_layouts_upload_identically(None, 'logistic54')"),
+    ("sgm_sample: chain streamed to the host on a second stream while later blocks run", """
+case = make_case('logistic54')
+ch = S.sgldcv(case['loglik'], case['data'], case['params'], case['eps'], case['opt_eps'], logPrior=case['logprior'], minibatchSize=case['n'], nIters=230, nItersOpt=120, verbose=False, seed=3, nChains=340)
+assert all(np.isfinite(np.asarray(v)).all() for v in ch.values())"""),
+    ("mode finder: launches of 100 iterations with checkOptDivergence between them", """
+case = make_case('logistic54'); dev = device_setup(case, 'sgld', True, n_chains=2, n_iters_opt=250); S.initSess(dev, verbose=False); assert np.isfinite(V.flatParams(dev)).all()"""),
     ("estLogPost / held-out log-likelihood / chain copy-out", "T.test_est_logpost_matches_oracle(None, 'logistic54'); T.test_heldout_loglik_matches_oracle(None, 'mixture'); T.test_chain_storage_layout_and_shapes(None)"),
 ]
 
