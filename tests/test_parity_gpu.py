@@ -133,7 +133,14 @@ def _deterministic_steps(case_name, algo, cv, shared):
             for k, v in chains64[c].mom.items():
                 sz = int(np.size(v))
                 scale = max(np.abs(v).max(), np.abs(chains64[c].theta[k]).max() * 1e-2)
-                close(mom[c][o:o + sz], np.asarray(v).reshape(-1, order="F"), scale=scale, rtol=1e-4, what=f"momentum[{k}]")
+                ref = np.asarray(v).reshape(-1, order="F")
+                # north_star's 1e-5 is a float32-against-float32 tolerance: a momentum is eta x (a difference of O(1) gradient terms), so
+                # against float64 the float32 GRAPH REPLICA itself is off by more than 1e-5 of the momentum's size.  Asserted: ours is no
+                # further from float64 than that replica (+ 1e-5 of the scale), and within 1e-4 of it outright.
+                e32 = np.abs(np.asarray(chains32[c].mom[k]).reshape(-1, order="F") - ref).max()
+                eours = np.abs(mom[c][o:o + sz] - ref).max()
+                assert eours <= e32 + RTOL * scale, f"momentum[{k}]: ours {eours:.2e} from float64, the float32 replica {e32:.2e} (scale {scale:.2e})"
+                close(mom[c][o:o + sz], ref, scale=scale, rtol=1e-4, what=f"momentum[{k}]")
                 o += sz
         if algo == "sgnht":
             ref = np.array([chains64[c].thermo[k] for k in chains64[c].theta])
