@@ -528,17 +528,24 @@ static int launch_logistic_staged_t(sgm_handle* h, const ChainArgs& a) {
     return SGM_OK;
 }
 
+// tile::gather4 drops four rows contiguously at a 128-byte aligned shared-memory address: the rows must be unpadded there (stride == ld)
+// and four of them a whole number of 128-byte lines (ld % 8 == 0), or every second group of four would start 64 bytes off -- a
+// misaligned TMA destination (d = 72: ld = 76, found by the shape fuzz on the emulated build; every tested shape had ld % 8 == 0)
+static bool logistic_can_gather4(const sgm_handle* h) {
+    return h->tmap_ok && (ls_row_stride4(h->ld) == h->ld / 4) && h->ld % 8 == 0 && h->ld <= 256;
+}
+
 static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
     // control variates need x.beta_hat per row unless the residual at the (shared) mode is cached in the rows
     const bool hat_dot = a.cv && !h->rhat_cached;
     {   // gather engine: TMA tile::gather4 when the shared-memory rows are unpadded, else one TMA bulk copy per row
-        const bool can_gather4 = h->tmap_ok && (ls_row_stride4(h->ld) == h->ld / 4) && h->ld <= 256;
+        const bool can_gather4 = logistic_can_gather4(h);
         int mode = can_gather4 ? 3 : 1;
         switch (h->opt_gather) {
             case 1: mode = 0; break;
             case 2: mode = 1; break;
             case 3: mode = 2; break;
-            case 4: if (!can_gather4) return fail(SGM_EINVAL, "gather = tile::gather4 needs unpadded shared-memory rows and a tensor map (ld = %d)", h->ld); mode = 3; break;
+            case 4: if (!can_gather4) return fail(SGM_EINVAL, "gather = tile::gather4 needs unpadded shared-memory rows of ld %% 8 == 0 floats and a tensor map (ld = %d)", h->ld); mode = 3; break;
         }
         const_cast<ChainArgs&>(a).gather_tma = mode;
     }
@@ -2022,7 +2029,7 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
                 if (logistic_use_staged(h, a)) {
                     const size_t smem = ls_smem_bytes(h->ld, h->n);
                     int per_sm = (int)((227 * 1024) / (smem + 1024)); if (per_sm > 2) per_sm = 2; if (per_sm < 1) per_sm = 1;
-                    const bool g4 = h->tmap_ok && (ls_row_stride4(h->ld) == h->ld / 4) && h->ld <= 256;
+                    const bool g4 = logistic_can_gather4(h);
                     snprintf(note, sizeof note, "%s; rows per lane R = %d; gather = %s", what, (h->n + LS_THREADS - 1) / LS_THREADS, g4 ? "TMA tile::gather4" : "TMA bulk copy per row");
                     po.launch("logistic_staged_kernel", chains < sms * per_sm ? chains : sms * per_sm, 1, 1, LS_THREADS, smem, 0, note);
                     if (g4) po.map(TmapPlan{"dataset rows (gather4)", (uint64_t)h->ld, (uint64_t)h->N, (uint64_t)h->ld, (uint64_t)h->N * h->ld}, h->ld, 1, "none");

@@ -36,8 +36,35 @@ def make_case(name: str, seed: int = 13):
         return dict(om=OM.Mixture2(2, 10.0), loglik=S.mixture2LogLik(), logprior=S.normalPrior(10.0),
                     data={"X": X}, params={"theta1": np.array([0.0, 0.0]), "theta2": np.array([0.1, 0.1])},
                     N=N, n=100, eps=2e-5, opt_eps=1e-5)
+    import re
+    m = re.fullmatch(r"gauss(\d+)d(_full)?_n(\d+)_N(\d+)", name)   # random shapes (tests/fuzz_emu.py): "gauss<d>d[_full]_n<minibatch>_N<rows>"
+    if m:
+        d, full, n, N = int(m.group(1)), bool(m.group(2)), int(m.group(3)), int(m.group(4))
+        if full:
+            A = rs.randn(d, d) * 0.3 + np.eye(d)
+            Sig = A @ A.T
+            X = rs.multivariate_normal(np.zeros(d), Sig, N)
+            return dict(om=OM.GaussMean(d, precision=np.linalg.inv(Sig), prior_sd=5.0), loglik=S.gaussMeanLogLik(Sig), logprior=S.normalPrior(5.0),
+                        data={"X": X}, params={"theta": rs.randn(d)}, N=N, n=n, eps=1e-4, opt_eps=1e-5)
+        return dict(om=OM.GaussMean(d, prior_sd=10.0), loglik=S.gaussMeanLogLik(), logprior=S.normalPrior(10.0),
+                    data={"X": rs.randn(N, d)}, params={"theta": rs.randn(d) * 0.3}, N=N, n=n, eps=1e-5, opt_eps=1e-5)
+    m = re.fullmatch(r"mixture(\d+)d_n(\d+)_N(\d+)", name)
+    if m:
+        d, n, N = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        z = rs.rand(N) < 0.5
+        X = rs.randn(N, d) + np.where(z[:, None], 0.0, 0.1)
+        return dict(om=OM.Mixture2(d, 10.0), loglik=S.mixture2LogLik(), logprior=S.normalPrior(10.0),
+                    data={"X": X}, params={"theta1": np.zeros(d), "theta2": np.full(d, 0.1)}, N=N, n=n, eps=2e-5, opt_eps=1e-5)
+    m = re.fullmatch(r"softmaxnet_(\d+)_(\d+)_(\d+)_n(\d+)_N(\d+)", name)
+    if m:
+        din, dh, do, n, N = (int(g) for g in m.groups())
+        X = rs.rand(N, din)
+        Y = np.eye(do)[rs.randint(0, do, N)]
+        p = {"A": rs.randn(dh, do), "B": rs.randn(din, dh), "a": rs.randn(do), "b": rs.randn(dh),
+             "lambdaA": np.array(1.3), "lambdaB": np.array(0.7), "lambdaa": np.array(2.0), "lambdab": np.array(0.5)}
+        return dict(om=OM.SoftmaxNet(din, dh, do), loglik=S.softmaxNetLogLik(), logprior=S.gammaPrecisionPrior(),
+                    data={"X": X, "y": Y}, params=p, N=N, n=n, eps=1e-5, opt_eps=1e-6)
     if name.startswith("logistic"):  # vignettes/logisticRegression.Rmd; "logistic<d>[_n<minibatch>][_N<rows>]"
-        import re
         m = re.fullmatch(r"logistic(\d+)(?:_n(\d+))?(?:_N(\d+))?", name)
         d = int(m.group(1))
         n = int(m.group(2)) if m.group(2) else 200

@@ -60,7 +60,18 @@ def test_deterministic_steps_shared_mode(lib, case_name, algo):
     _deterministic_steps(case_name, algo, True, shared=True)
 
 
-def _deterministic_steps(case_name, algo, cv, shared):
+def _summand_mass(case, theta, rows):
+    """Logistic family: (N/n) sum_i |y_i - sigmoid(z_i)| |x_ik| per coordinate -- the size of what a float32 sum of the minibatch
+    gradient rounds against (the gradient itself can cancel to nearly nothing, e.g. N = 9, n = 8)."""
+    X, y = np.asarray(case["data"]["X"], dtype=np.float64)[rows], np.asarray(case["data"]["y"], dtype=np.float64)[rows]
+    X = X.reshape(len(rows), -1)
+    z = float(np.asarray(theta["bias"]).reshape(-1)[0]) + X @ np.asarray(theta["beta"], dtype=np.float64).reshape(-1)
+    r = np.abs(y - 1.0 / (1.0 + np.exp(-z)))
+    corr = case["N"] / case["n"]
+    return {"bias": corr * r.sum(), "beta": corr * (r[:, None] * np.abs(X)).sum(0).max()}
+
+
+def _deterministic_steps(case_name, algo, cv, shared, mass_scaled=False):
     from sgmcmc_b200 import validation as V
     case = make_case(case_name)
     C, steps, n_opt = 3, 4, 25
@@ -111,6 +122,8 @@ def _deterministic_steps(case_name, algo, cv, shared):
                 sz = int(np.size(v))
                 ref = np.asarray(v).reshape(-1, order="F")
                 scale = np.abs(plain[k]).max()
+                if mass_scaled and "bias" in chains64[c].theta:   # random shapes (tests/fuzz_emu.py): degenerate minibatches whose gradient cancels
+                    scale = max(scale, _summand_mass(case, chains64[c].theta, gidx[c])[k])
                 close(g_dev[c][o:o + sz], ref, scale=scale, what=f"cv grad[{k}] vs f64")
                 e32 = np.abs(np.asarray(g32[k]).reshape(-1, order="F") - ref).max()
                 eours = np.abs(g_dev[c][o:o + sz] - ref).max()
