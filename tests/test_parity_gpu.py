@@ -39,6 +39,24 @@ def tensor_close(ours_flat, ref_params, what, rtol=RTOL):
         o += sz
 
 
+def tensor_close_ref(ours_flat, ref32, ref64, what, lenient):
+    """ours against the float32 graph replica AND float64 at the curated cases; at random shapes (lenient: tests/fuzz_emu.py -- sums that
+    cancel, a float32 replica that is itself 1e-4 from float64) SURVEY 8c's second criterion decides: ours is no further from float64
+    than the replica is, + RTOL of the tensor's size."""
+    if not lenient:
+        tensor_close(ours_flat, ref32, f"{what} vs f32 graph")
+        return
+    o = 0
+    for k, v in ref64.items():
+        sz = int(np.size(v))
+        r64 = np.asarray(v, np.float64).reshape(-1, order="F")
+        r32 = np.asarray(ref32[k], np.float64).reshape(-1, order="F")
+        ours = np.asarray(ours_flat[o:o + sz], np.float64)
+        e_ours, e_32 = np.abs(ours - r64).max(), np.abs(r32 - r64).max()
+        assert e_ours <= e_32 + RTOL * np.abs(r64).max() + 1e-7, f"{what}[{k}]: ours {e_ours:.3e} from float64, the float32 replica {e_32:.3e}"
+        o += sz
+
+
 def draw_inputs(rs, chain: OS.Chain, N, n, C):
     idx = np.stack([np.stack([rs.choice(N, n, replace=False) for _ in range(chain.n_sub())]) for _ in range(C)])
     noise = rs.randn(C, chain.noise_len()).astype(np.float32)
@@ -96,7 +114,7 @@ def _deterministic_steps(case_name, algo, cv, shared, mass_scaled=False):
     if cv:
         th_hat, g_hat = V.getMode(dev)
         for c in range(C):
-            tensor_close(th_hat[c], chains32[c].theta_hat, "theta_hat")
+            tensor_close_ref(th_hat[c], chains32[c].theta_hat, chains64[c].theta_hat, "theta_hat", mass_scaled)
             # full-data gradient: scale by the per-datum gradient mass, not by the (near-zero at the mode) total
             gl = case["om"].grad_loglik(chains64[c].theta_hat, case["data"], np.float64)
             o = 0
@@ -112,8 +130,9 @@ def _deterministic_steps(case_name, algo, cv, shared, mass_scaled=False):
         g32 = chains32[c].grad_estimate(OS.take(case["data"], gidx[c]))
         g64 = chains64[c].grad_estimate(OS.take(case["data"], gidx[c]))
         if not cv:
-            tensor_close(g_dev[c], g32, "grad vs f32 graph")
-            tensor_close(g_dev[c], g64, "grad vs f64")
+            tensor_close_ref(g_dev[c], g32, g64, "grad", mass_scaled)
+            if not mass_scaled:
+                tensor_close(g_dev[c], g64, "grad vs f64")
         else:
             # control-variate estimate: tolerance scaled by the summand magnitude
             plain = chains64[c].grad_fn(chains64[c].theta, OS.take(case["data"], gidx[c]))
@@ -139,8 +158,9 @@ def _deterministic_steps(case_name, algo, cv, shared, mass_scaled=False):
     th = V.flatParams(dev)
     mom, thermo = V.getState(dev)
     for c in range(C):
-        tensor_close(th[c], chains32[c].theta, f"theta after {steps} steps vs f32 graph")
-        tensor_close(th[c], chains64[c].theta, f"theta after {steps} steps vs f64", rtol=2e-5)
+        tensor_close_ref(th[c], chains32[c].theta, chains64[c].theta, f"theta after {steps} steps", mass_scaled)
+        if not mass_scaled:
+            tensor_close(th[c], chains64[c].theta, f"theta after {steps} steps vs f64", rtol=2e-5)
         if algo != "sgld":
             o = 0
             for k, v in chains64[c].mom.items():
