@@ -31,7 +31,7 @@ _GPU_ORDER = [
     ("test_parity_gpu.py", "test_chain_storage_layout_and_shapes"), ("test_parity_gpu.py", "test_same_seed_reproduces"),
     ("test_parity_gpu.py", "test_heldout_loglik_matches_oracle"), ("test_fullgrad_tc_gpu.py", ""), ("test_statistics_gpu.py", "test_1d_gauss"),
     ("test_statistics_gpu.py", "test_3d_gauss"), ("test_statistics_gpu.py", "test_step_by_step"), ("test_statistics_gpu.py", "test_optional_arguments"),
-    ("test_statistics_gpu.py", "test_stationary_moments"), ("test_statistics_gpu.py", "test_divergence"), ("test_parity_gpu.py", ""),
+    ("test_statistics_gpu.py", "test_stationary_moments"), ("test_statistics_gpu.py", "test_divergence"), ("test_parity_gpu.py", "test_call_sequences"), ("test_parity_gpu.py", ""),
     ("test_statistics_gpu.py", ""), ("test_r_shim.py", ""), ("test_multi_gpu.py", ""),
 ]
 

@@ -76,6 +76,12 @@ def test_dataset_layouts_upload_identically(case_name):
     T.test_dataset_layouts_upload_identically(None, case_name)
 
 
+@pytest.mark.parametrize("case_name,algo,cv", [("gauss2d", "sgld", False), ("mixture", "sghmc", False), ("logistic54", "sgnht", True),
+                                               ("logistic130", "sgld", True), ("softmaxnet_small", "sghmc", False)])
+def test_call_sequences_walk_one_rng_stream(case_name, algo, cv):
+    T.test_call_sequences_walk_one_rng_stream(None, case_name, algo, cv)
+
+
 def test_streamed_sampling_reports_divergence():
     T.test_streamed_sampling_reports_divergence(None)
 

@@ -251,6 +251,54 @@ def test_chain_storage_layout_and_shapes(lib):
     np.testing.assert_allclose(ch["theta"][:, -1, :], S.getParams(sg, sess)["theta"], rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("case_name,algo,cv", [("gauss2d", "sgld", False), ("mixture", "sghmc", False), ("logistic54", "sgnht", True),
+                                               ("logistic130", "sgld", True), ("softmaxnet_small", "sghmc", False)])
+def test_call_sequences_walk_one_rng_stream(lib, case_name, algo, cv):
+    """However the iterations are requested -- one sgm_run, sgmcmcStep by sgmcmcStep (R/update.R:37-81), runs split in two, a streamed
+    sgm_sample after a stored run, with or without storage -- the chain is the same function of (seed, iteration): the device RNG and
+    the minibatch permutation are keyed by the iteration counter, not by the launch."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib
+    L = _lib.load()
+    case = make_case(case_name)
+    total = 23
+
+    def fresh():
+        sg = device_setup(case, algo, cv, n_chains=2, seed=11, n_iters_opt=12)
+        return sg, S.initSess(sg, verbose=False)
+
+    a, _ = fresh()
+    _lib.check(L.sgm_run(a.handle, total, 1))
+    want = {k: np.array(v) for k, v in S.getChains(a).items()}
+
+    b, sess_b = fresh()                      # step by step, storing nothing: the state after `total` steps
+    for _ in range(total):
+        S.sgmcmcStep(b, sess_b)
+    last = S.getParams(b, sess_b)
+    for k in want:
+        np.testing.assert_array_equal(np.asarray(last[k]).reshape(2, -1), want[k][:, -1].reshape(2, -1), err_msg=f"{k}: steps vs one run")
+
+    c, _ = fresh()                           # 5 unstored + 7 stored + 11 stored: the stored part is iterations 6..23
+    _lib.check(L.sgm_run(c.handle, 5, 0))
+    _lib.check(L.sgm_run(c.handle, 7, 1))
+    _lib.check(L.sgm_run(c.handle, 11, 1))
+    assert L.sgm_chain_length(c.handle) == 18
+    got = S.getChains(c)
+    for k in want:
+        np.testing.assert_array_equal(np.asarray(got[k]), want[k][:, 5:], err_msg=f"{k}: split runs")
+
+    d, _ = fresh()                           # a stored run, then the streamed call continues the same stream
+    _lib.check(L.sgm_run(d.handle, 9, 1))
+    out = np.empty(2 * d.P * (total - 9), dtype=np.float64)
+    _lib.check(L.sgm_sample(d.handle, total - 9, 5, out.ctypes.data_as(_lib._PD)))
+    def flat_f(v):   # (chains, iters, dims...) -> (chains, iters, prod dims) with R's column-major order inside a parameter
+        return v.transpose(0, 1, *range(v.ndim - 1, 1, -1)).reshape(2, total, -1)
+    tail = np.concatenate([flat_f(want[k])[:, 9:, :].transpose(0, 2, 1).reshape(2, -1) for k in want], axis=1)
+    np.testing.assert_array_equal(out.reshape(2, -1), tail, err_msg="sgm_sample after sgm_run")
+    _lib.check(L.sgm_reset_chain(d.handle))
+    assert L.sgm_chain_length(d.handle) == 0
+
+
 def test_same_seed_reproduces(lib):
     """tests/testthat/testSeeds.R: same seed twice => identical chains (all six samplers)."""
     import sgmcmc_b200 as S
