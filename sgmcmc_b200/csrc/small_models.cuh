@@ -128,8 +128,11 @@ static inline size_t small_smem_bytes(int64_t N, int ld) { return (size_t)N * ld
 // (mbarrier-tracked), and every gathered row is then one shared-memory load -- SURVEY.md section 7 ("rows of config 1-2 are 8 B: use
 // float2 loads of an SMEM-resident dataset").  SMEM = false: rows come from global memory through the read-only path (datasets that
 // do not fit, or whose byte size is not a multiple of 16).
+// Launch bounds: the shared-memory variant is sized for TWO CTAs per SM (2 x 80 KB of dataset, 32 resident chains); with d <= 2 that
+// means <= 64 registers per thread, which ptxas only honours when told (ptxas -v: Gaussian 64 registers + 28 B of spills without the
+// bound, 47 and none with it; mixture 86 -> 64 with 18 B of spills outside the row loop: one CTA per SM -> two).
 template <int MODEL, bool SMEM, int D>
-__global__ void __launch_bounds__(SMEM ? SMALL_SMEM_THREADS : 128) small_chain_kernel(const ChainArgs a) {
+__global__ void __launch_bounds__(SMEM ? SMALL_SMEM_THREADS : 128, (SMEM && D <= 2) ? 2 : 0) small_chain_kernel(const ChainArgs a) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     const int T = (MODEL == SMALL_MODEL_GAUSS) ? 1 : 2;
