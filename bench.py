@@ -217,6 +217,17 @@ def measure_tf32_peak(seconds=1.5):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
+def max_over_ranks(vals):
+    """Element-wise maximum over the ranks of a short list of floats (timings): one all-reduce on the backend's own device."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v) for v in vals], dtype=torch.float64)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.cpu()]
+
+
 def comm_init(sg, rank, world):
     from sgmcmc_b200 import distributed as D
     D.comm_init(sg, rank, world)
@@ -366,7 +377,7 @@ def quick_workload(name, steps=5, iters=None):
 
 
 
-def run_leg_in_child(leg, args, timeout_s=420):
+def run_leg_in_child(leg, args, timeout_s=300):
     """Runs one optional leg (`--leg NAME`) of this script in its own process (N = 1 only) and returns its JSON object.  A leg that
     faults on the device (a sticky CUDA error ends every later call of the process that raised it) or hangs then costs its own entry,
     not the main line.  The child measures with CUDA events exactly as the parent would; process start-up is outside its timed regions."""
@@ -418,7 +429,8 @@ def run_ours(args, w):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
+    own_group = world > 1 and not dist.is_initialized()   # (a test on the emulated build arrives with a gloo group already up)
+    if own_group:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__
     if local == 0:
@@ -477,9 +489,7 @@ def run_ours(args, w):
     with ClockSampler(local) as clk:
         dt, kernel_ms, launches = device_leg(sg, lib, V, _lib, I, args.steps, args.warmup, barrier)
     if world > 1:
-        t = torch.tensor([dt, max(kernel_ms)], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t[0])
+        dt = max_over_ranks([dt])[0]
     clocks = clk.summary()
     value = total_chains * I * args.steps / dt
     k_ms = float(np.mean(kernel_ms))
@@ -547,9 +557,7 @@ def run_ours(args, w):
         t_e2e = time.perf_counter() - t_e2e0
         t_run = time.perf_counter() - t_init
         if world > 1:
-            t = torch.tensor([t_e2e, t_run, t_setup - t_e2e0, t_init - t_setup], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e, t_run, t_up, t_in = (float(x) for x in t)
+            t_e2e, t_run, t_up, t_in = max_over_ranks([t_e2e, t_run, t_setup - t_e2e0, t_init - t_setup])
         else:
             t_up, t_in = t_setup - t_e2e0, t_init - t_setup
         finite = bool(np.isfinite(host_chain[-sg.P:]).all())
@@ -590,7 +598,7 @@ def run_ours(args, w):
         line["errors"] = errors
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
+    if own_group:
         dist.destroy_process_group()
 
 

@@ -88,6 +88,70 @@ def test_bench_prints_one_contract_line(monkeypatch, main):
         assert m["TFLOPs"] > 0 and m["peak"] == 800.0 and abs(m["frac_of_3xtf32_ceiling"] - 3 * m["frac"]) < 1e-12
 
 
+def _bench_worker(rank, world, port, peer_shards, out):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0",
+                      SGM_EMU_SHM_IPC="1", SGM_EMU_SMS="2")
+    import torch
+    import torch.distributed as dist
+    from tests.emu import build
+    os.environ["SGM_EMU_NCCL"] = build.build_fake_nccl()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    import __graft_entry__
+    torch.cuda.is_available = lambda: True
+    torch.cuda.set_device = lambda *_: None
+    torch.cuda.synchronize = lambda *_: None
+    __graft_entry__.build = lambda *a, **k: None
+    bench.measure_tf32_peak = lambda *a, **k: (900.0, 800.0)
+    rs = np.random.RandomState(13)
+    N, d = (1200, 130) if peer_shards else (1500, 54)   # a sharded dataset takes the long-row kernel (rows resolved through the shard table)
+    w = dict(desc="toy", algo="sgnht" if peer_shards else "sgld", cv=True, family="logistic", data={"X": rs.randn(N, d), "y": (rs.rand(N) < 0.5).astype(np.float64)},
+             params={"bias": np.array(0.0), "beta": np.zeros((d, 1))}, stepsize=5e-6, opt_stepsize=5e-6, n_iters_opt=110, n=128, chains=2, a=0.01,
+             bytes_per_chain_iter=1000, fullgrad_bytes=N * (d + 1) * 4, bound_note="toy")
+    args = types.SimpleNamespace(gpus=world, steps=2, warmup=1, impl="ours", workload="c3", chains=None, iters_per_step=110, cpu_budget=0.5, no_cpu=True, modes=32,
+                                 no_modes=False, peer_shards=peer_shards, no_extra=True)
+    buf = io.StringIO()
+    try:
+        with backend.emulated() as lib, redirect_stdout(buf):
+            bench.run_ours(args, w)
+            msg = lib.emu_last_message()
+        out[rank] = (buf.getvalue(), msg.decode() if msg else "")
+    except BaseException as e:   # noqa: BLE001
+        import traceback
+        out[rank] = ("", f"{type(e).__name__}: {e}\n{traceback.format_exc()[-2000:]}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("peer_shards", [False, True])
+def test_bench_two_ranks_prints_one_line_on_rank_0(peer_shards):
+    """The N > 1 arm (what the driver launches under torchrun for the scaling record) as a 2-process job on the emulated build: gloo
+    carries the rendezvous, tests/emu/fake_nccl.c the library's collectives; replicated dataset and --peer-shards."""
+    import socket
+    import torch.multiprocessing as mp
+    from tests.emu import build
+    backend.library()
+    build.build_fake_nccl()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_bench_worker, args=(2, port, peer_shards, out), nprocs=2, join=True)
+    for r in range(2):
+        assert r in out and not out[r][1], out.get(r)
+    lines0 = [l for l in out[0][0].splitlines() if l.startswith("{")]
+    assert len(lines0) == 1 and not [l for l in out[1][0].splitlines() if l.startswith("{")]
+    line = json.loads(lines0[0])
+    assert "errors" not in line, line["errors"]
+    assert line["n_gpus"] == 2 and line["config"]["chains_total"] == 4 and line["scaling"] == "weak"
+    assert line["e2e"]["value"] > 0 and line["e2e"]["comm_init_ms_outside"] is not None
+    assert line["cv_full_gradient"]["collective_ms"] is not None
+    m = line["cv_full_gradient_modes"]
+    assert m["modes"] == 32 and m["collective_ms"] is not None and m["TFLOPs_all_ranks"] > 0
+    assert ("sharded over 2 ranks" in line["config"]["dataset"]) == peer_shards
+
+
 def test_optional_leg_failure_costs_only_its_own_entry():
     """A leg's child process that cannot produce a result (here: no CUDA device in this container) comes back as an error object."""
     import bench
