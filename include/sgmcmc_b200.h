@@ -229,6 +229,9 @@ int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops);
  *   "sharded_mode_finder"  1 = the *cv mode finder sharded by data rows: every SGD step each rank sums the gradients of its part of the
  *                      minibatch (drawn from its own rows) and the P-vector is all-reduced (needs sgm_comm_init and
  *                      SGM_FLAG_SHARED_MODE; default: every rank runs the same finder on the rows it can reach, no communication)
+ *   "mode_finder_split"  logistic *cv mode finder: 1 = one CTA per mode always; 2, 4, 8 = a thread-block cluster of that many CTAs per
+ *                      mode, each summing its part of every minibatch, partial sums exchanged through distributed shared memory
+ *                      (default: the largest of these that fits modes x CTAs on the device and leaves every CTA >= 16 rows)
  *   "nn_update"        softmax net: 1 = register-staged update of every tensor (default: streamed through shared memory)
  *   "nn_stage1"        softmax net: 1 = register-staged forward GEMM operands (default: TMA-fed)
  * The library never reads environment variables on the dispatch path. */

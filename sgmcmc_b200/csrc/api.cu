@@ -26,6 +26,7 @@
 #include "small_models.cuh"
 #include "logistic.cuh"
 #include "logistic_staged.cuh"
+#include "logistic_opt_split.cuh"
 #include "logistic_fullgrad_stream.cuh"
 #include "logistic_cv_gemm.cuh"
 #include "softmax_net.cuh"
@@ -174,6 +175,7 @@ struct sgm_handle {
     int opt_gather = 0;            // short-row kernel: 1 cp.async, 2 TMA bulk copy per row, 3 mixed, 4 TMA tile::gather4
     int opt_fullgrad = 0;          // logistic full-data gradient: 1 tensor-core contractions, 2 SIMT row-chunk x mode grid
     int opt_small_kernel = 0;      // Gaussian families: 1 = rows from global memory even when the dataset fits in shared memory
+    int opt_mode_finder_split = 0; // logistic mode finder: 1 = always one CTA per mode; 2, 4, 8 = a cluster of that many CTAs per mode (default: by occupancy)
     int opt_sharded_finder = 0;    // 1: mode finder sharded by data rows (each rank draws its part of every minibatch from its own rows, the
                                    // P-vector is all-reduced every SGD step); needs sgm_comm_init + SGM_FLAG_SHARED_MODE
     int opt_row0 = 0, opt_row1 = 0;   // row1 > 0: the full-data pass sums rows [row0, row1) only -- what rank r of a row-sharded job does,
@@ -563,8 +565,63 @@ static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
     return fail(SGM_EINVAL, "logistic staged kernel: minibatch %d too large", a.n);
 }
 
+// ---- mode finder with fewer modes than SMs: a thread-block cluster per mode (logistic_opt_split.cuh)
+// CTAs per mode: the largest power of two <= 8 that still leaves every CTA OS_MIN_ROWS minibatch rows and fits modes x CTAs on the
+// device; 1 = keep one CTA per mode (many modes: the SMs are busy anyway)
+constexpr int OS_MIN_ROWS = 16;
+static int opt_split_of(int opt, int modes, int n, int sms) {
+    if (opt == 1) return 1;
+    int split = 1;
+    for (int s = 2; s <= OS_MAX_SPLIT; s *= 2)
+        if ((int64_t)modes * s <= sms && n / s >= OS_MIN_ROWS) split = s;
+    if (opt >= 2) { split = 1; while (split * 2 <= opt) split *= 2; if (n / split < 1) split = 1; }
+    return split;
+}
+
+// *launched = false: the device cannot co-schedule such a cluster (or refuses the launch configuration) -- the caller falls back to
+// one CTA per mode; nothing has run in that case
+template <int G, int V>
+static int launch_logistic_opt_split_gv(sgm_handle* h, const ChainArgs& a, int split, int sms, bool* launched) {
+    *launched = false;
+    const size_t smem = os_smem_bytes(G, V, h->ld);
+    if (smem > 227 * 1024) return SGM_OK;
+    CU(cudaFuncSetAttribute((logistic_opt_split_kernel<G, V>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (; split > 1; split /= 2) {   // the largest cluster the device can hold
+        int fit = 0;
+        cudaError_t qe;
+        SGM_CLUSTER_OCCUPANCY(qe, &fit, (logistic_opt_split_kernel<G, V>), (unsigned)split, OS_THREADS, smem, split);
+        if (qe == cudaSuccess && fit > 0) break;
+        cudaGetLastError();
+    }
+    if (split <= 1) return SGM_OK;
+    int clusters = sms / split;
+    if (clusters > a.C) clusters = a.C;
+    if (clusters < 1) clusters = 1;
+    cudaError_t err;
+    SGM_LAUNCH_CLUSTER(err, (logistic_opt_split_kernel<G, V>), (unsigned)(clusters * split), OS_THREADS, smem, h->stream, split, a);
+    if (err != cudaSuccess) { cudaGetLastError(); return SGM_OK; }   // a refused configuration is not a fault: nothing was launched
+    CU(cudaGetLastError());
+    *launched = true;
+    return SGM_OK;
+}
+
+static int launch_logistic_opt_split(sgm_handle* h, const ChainArgs& a, int split, int sms, bool* launched) {
+    LOGI_DISPATCH(launch_logistic_opt_split_gv, h, a, split, sms, launched);
+}
+
 static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
     const_cast<ChainArgs&>(a).rhat_cached = h->rhat_cached ? 1 : 0;
+    if (a.algo == ALGO_OPT && !a.cv && a.L == 1 && h->n_shards <= 1 && a.X == h->X) {
+        int sms = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        LogiShape s;
+        const int split = opt_split_of(h->opt_mode_finder_split, a.C, a.n, sms);
+        if (split > 1 && logi_shape(h->ld, &s) && os_smem_bytes(s.G, s.V, h->ld) <= 227 * 1024) {
+            bool launched = false;
+            const int rc = launch_logistic_opt_split(h, a, split, sms, &launched);
+            if (rc != SGM_OK || launched) return rc;
+        }
+    }
     if (logistic_use_staged(h, a)) return launch_logistic_staged(h, a);
     LogiShape s;
     if (!logi_shape(h->ld, &s)) return fail(SGM_EINVAL, "logistic: d = %d too large", h->d);
@@ -1928,7 +1985,8 @@ extern "C" int sgm_set_option(sgm_handle* h, const char* key, int32_t value) {
     struct Opt { const char* key; int* slot; int max; };
     const Opt opts[] = {{"logistic_kernel", &h->opt_logistic_kernel, 1}, {"gather", &h->opt_gather, 4}, {"fullgrad", &h->opt_fullgrad, 2},
                         {"fullgrad_row0", &h->opt_row0, INT32_MAX}, {"fullgrad_row1", &h->opt_row1, INT32_MAX},
-                        {"sharded_mode_finder", &h->opt_sharded_finder, 1}, {"small_kernel", &h->opt_small_kernel, 2}};
+                        {"sharded_mode_finder", &h->opt_sharded_finder, 1}, {"small_kernel", &h->opt_small_kernel, 2},
+                        {"mode_finder_split", &h->opt_mode_finder_split, OS_MAX_SPLIT}};
     for (const Opt& o : opts)
         if (!strcmp(key, o.key)) {
             if (value < 0 || value > o.max) return fail(SGM_EINVAL, "option %s: value %d outside [0, %d]", key, value, o.max);
@@ -2042,7 +2100,15 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
             };
             chain(h->C, "sampling");
             if (h->cv) {
-                chain(M, "mode finder");
+                const int split = h->n_shards <= 1 ? opt_split_of(h->opt_mode_finder_split, M, h->n, sms) : 1;
+                if (split > 1 && os_smem_bytes(s.G, s.V, h->ld) <= 227 * 1024) {
+                    char note[160];
+                    int clusters = sms / split; if (clusters > M) clusters = M;
+                    snprintf(note, sizeof note, "mode finder; thread-block clusters of %d CTAs per mode (DSMEM reduction), %d minibatch rows per CTA; <G, V> = <%d, %d>", split, (h->n + split - 1) / split, s.G, s.V);
+                    po.launch("logistic_opt_split_kernel", (int64_t)clusters * split, 1, 1, OS_THREADS, os_smem_bytes(s.G, s.V, h->ld), 0, note);
+                } else {
+                    chain(M, "mode finder");
+                }
                 const bool gathered = world > 1 && !(h->flags & SGM_FLAG_SHARED_MODE);
                 const int Mg = gathered ? M * world : M;
                 const int Q = h->ld / 4;

@@ -15,9 +15,34 @@
 #define SGM_LAUNCH(kern, grid, block, smem, stream, ...) \
     ::emu::launch(#kern, (const void*)(kern), dim3(grid), dim3(block), (size_t)(smem), [=]() { (kern)(__VA_ARGS__); })
 #define SGM_DYN_SMEM(type, name, align) type* name = reinterpret_cast<type*>(::emu::dyn_smem(align))
+#define SGM_CLUSTER_OCCUPANCY(err, n_out, kern, grid_, block_, smem_, cluster_) do { *(n_out) = 2; (err) = cudaSuccess; } while (0)
+#define SGM_LAUNCH_CLUSTER(err, kern, grid, block, smem, stream, cluster, ...)                                                           \
+    do { ::emu::launch_cluster(#kern, (const void*)(kern), dim3(grid), dim3(block), (size_t)(smem), (unsigned)(cluster), [=]() { (kern)(__VA_ARGS__); }); (err) = cudaSuccess; } while (0)
 #else
 #define SGM_LAUNCH(kern, grid, block, smem, stream, ...) (kern)<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define SGM_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
+// how many clusters of `cluster_` CTAs of this kernel the device can hold at once (0: it cannot co-schedule one)
+#define SGM_CLUSTER_OCCUPANCY(err, n_out, kern, grid_, block_, smem_, cluster_)                                                          \
+    do {                                                                                                                                 \
+        cudaLaunchConfig_t cfg_ = {};                                                                                                    \
+        cfg_.gridDim = dim3(grid_); cfg_.blockDim = dim3(block_); cfg_.dynamicSmemBytes = (size_t)(smem_);                               \
+        cudaLaunchAttribute attr_[1];                                                                                                    \
+        attr_[0].id = cudaLaunchAttributeClusterDimension;                                                                               \
+        attr_[0].val.clusterDim.x = (unsigned)(cluster_); attr_[0].val.clusterDim.y = 1; attr_[0].val.clusterDim.z = 1;                  \
+        cfg_.attrs = attr_; cfg_.numAttrs = 1;                                                                                           \
+        (err) = cudaOccupancyMaxActiveClusters((n_out), (kern), &cfg_);                                                                  \
+    } while (0)
+// thread-block clusters of `cluster` CTAs along x; `err` receives the launch status
+#define SGM_LAUNCH_CLUSTER(err, kern, grid_, block_, smem_, stream_, cluster_, ...)                                                      \
+    do {                                                                                                                                 \
+        cudaLaunchConfig_t cfg_ = {};                                                                                                    \
+        cfg_.gridDim = dim3(grid_); cfg_.blockDim = dim3(block_); cfg_.dynamicSmemBytes = (size_t)(smem_); cfg_.stream = (stream_);      \
+        cudaLaunchAttribute attr_[1];                                                                                                    \
+        attr_[0].id = cudaLaunchAttributeClusterDimension;                                                                               \
+        attr_[0].val.clusterDim.x = (unsigned)(cluster_); attr_[0].val.clusterDim.y = 1; attr_[0].val.clusterDim.z = 1;                  \
+        cfg_.attrs = attr_; cfg_.numAttrs = 1;                                                                                           \
+        (err) = cudaLaunchKernelEx(&cfg_, (kern), __VA_ARGS__);                                                                          \
+    } while (0)
 #endif
 
 #ifdef SGM_EMU
@@ -155,6 +180,23 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- thread-block clusters: rank, the cluster-wide barrier (split arrive / wait, release / acquire at cluster scope) and loads
+// from a peer CTA's shared memory (distributed shared memory)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {   // the same shared-memory offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 #else   // ---- SGM_EMU: the same interface on the emulated engines (tests/emu/include/emu_async.h) ---------------------------------
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) { float4 v; std::memcpy(&v, ::emu::smem_ptr(addr, 16, 16), 16); return v; }
@@ -195,6 +237,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) { :
 __device__ __forceinline__ void tmem_wait_ld() {}
 __device__ __forceinline__ void tmem_wait_st() {}
 __device__ __forceinline__ bool elect_one() { return ::emu::elect_one(); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { return ::emu::cluster_ctarank(); }
+__device__ __forceinline__ uint32_t cluster_nctarank() { return ::emu::cluster_nctarank(); }
+__device__ __forceinline__ void cluster_arrive() { ::emu::cluster_arrive(); }
+__device__ __forceinline__ void cluster_wait() { ::emu::cluster_wait(); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) { return ::emu::mapa(addr, rank); }
+__device__ __forceinline__ float ld_dsmem32(uint32_t addr) { float v; std::memcpy(&v, ::emu::dsmem_ptr(addr, 4, 4), 4); return v; }
 #endif
 
 }  // namespace sgm

@@ -53,6 +53,7 @@ static int g_sms = 2;               // SGM_EMU_SMS
 static bool g_verbose = false;
 static bool g_shm_ipc = false;     // SGM_EMU_SHM_IPC
 static int g_sched = 0;             // SGM_EMU_SCHED: 0 rr, 1 reverse, >= 2 random (seed)
+static bool g_cluster_lockstep = false;   // SGM_EMU_CLUSTER=lockstep (default: each CTA of a cluster runs as far as it can in turn)
 static unsigned long long g_sched_state = 1;
 
 // ---- sticky error ------------------------------------------------------------------------------------------------------------
@@ -73,6 +74,7 @@ struct Fiber {
     std::vector<std::vector<BulkStore>> bulk_groups;  // committed bulk stores, oldest first
     std::vector<BulkStore> bulk_open;
     int wait_kind = 0; uint32_t wait_a = 0, wait_b = 0;   // what a blocked thread is waiting for (formatted only in a deadlock report)
+    bool cl_arrived = false; unsigned cl_gen = 0;         // barrier.cluster: arrived and not yet waited; the generation arrived in
 };
 struct WarpEx {
     uint64_t slot[2][32];
@@ -107,7 +109,17 @@ struct Cta {
     const std::function<void()>* body = nullptr;
     const char* kname = "";
     bool aborted = false;
+    unsigned bx = 0, by = 0, bz = 0;    // blockIdx of this CTA (the CTAs of a thread-block cluster run interleaved)
+    int rank = 0;                       // %cluster_ctarank
+    struct Cluster* cl = nullptr;
 };
+// a thread-block cluster: its CTAs are co-scheduled (fibers of all of them take turns), share one hardware barrier
+// (barrier.cluster.arrive / wait) and can address each other's shared memory (mapa + ld/st.shared::cluster)
+struct Cluster {
+    std::vector<Cta*> ctas;
+    int bar_arrived = 0; unsigned bar_gen = 0;
+};
+constexpr int MAX_CLUSTER = 16;
 static Cta* g_cta = nullptr;
 static void* g_main_sp = nullptr;
 static std::vector<char*> g_stack_pool;
@@ -124,6 +136,7 @@ static char* get_stack() {
 
 static void fiber_exit();
 static void bulk_store_write(BulkStore& b);
+static void cluster_release_if_complete(struct Cluster& cl);
 extern "C" void emu_trampoline() {
     (*g_cta->body)();
     fiber_exit();
@@ -162,6 +175,10 @@ static void fiber_exit() {
     c.warps[c.cur >> 5].alive &= ~(1u << (c.cur & 31));
     ++c.progress;
     release_barrier_if_complete(c);
+    if (c.cl) {
+        if (f.cl_arrived && f.cl_gen == c.cl->bar_gen) --c.cl->bar_arrived;   // an arrival of this phase by a thread that is gone: the count is over live threads
+        cluster_release_if_complete(*c.cl);
+    }
     void* dummy;
     emu_switch(&dummy, g_main_sp);
     abort();   // never resumed
@@ -303,23 +320,30 @@ static void init_once() {
         if (!strcmp(sc, "reverse")) g_sched = 1;
         else if (atoi(sc) > 0) { g_sched = 2; g_sched_state = (unsigned long long)atoi(sc) * 0x9E3779B97F4A7C15ull + 1; }
     }
+    if (const char* cs = getenv("SGM_EMU_CLUSTER")) g_cluster_lockstep = !strcmp(cs, "lockstep");
     struct sigaction sa;
     memset(&sa, 0, sizeof sa);
     sa.sa_sigaction = segv_handler;
     sa.sa_flags = SA_SIGINFO | SA_NODEFER;
     sigaction(SIGSEGV, &sa, &g_old_segv);
-    g_smem_pool = (unsigned char*)mmap(nullptr, SMEM_POOL, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    g_smem_pool = (unsigned char*)mmap(nullptr, SMEM_POOL * MAX_CLUSTER, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
 }
 
 // ---- launch ------------------------------------------------------------------------------------------------------------------
 static std::unordered_map<const void*, int> g_dyn_limit;
 
-static void run_cta(Cta& c) {
-    g_cta = &c;
-    // round-robin; a pass without progress while threads are still alive = deadlock
+// runs the CTAs of one cluster (a plain launch: a cluster of one) to completion
+static void run_group(std::vector<Cta*>& grp) {
+    // round-robin over the fibers of every CTA; a pass without progress while threads are still alive = deadlock
     int stalled = 0;
-    while (c.alive > 0 && !c.aborted) {
-        const unsigned long long before = c.progress;
+    auto alive = [&]() { int n = 0; for (Cta* c : grp) n += c->alive; return n; };
+    auto aborted = [&]() { for (Cta* c : grp) if (c->aborted) return true; return false; };
+    auto progress_sum = [&]() { unsigned long long p = 0; for (Cta* c : grp) p += c->progress; return p; };
+    // one pass over the live fibers of one CTA
+    auto pass = [&](Cta* cp) {
+        Cta& c = *cp;
+        g_cta = cp;
+        blockIdx_.x = c.bx; blockIdx_.y = c.by; blockIdx_.z = c.bz;
         // SGM_EMU_SCHED: the order in which the WARPS of the CTA get their turn in a pass ("rr" = warp 0 first, "reverse", or a
         // number = seed of a fresh random order per pass).  Lanes of a warp always run in lane order: inter-warp races are real on the
         // device, intra-warp orders that converged code never produces are not explored.
@@ -328,7 +352,7 @@ static void run_cta(Cta& c) {
         for (int w = 0; w < nwarps; ++w) order[w] = w;
         if (g_sched == 1) for (int w = 0; w < nwarps; ++w) order[w] = nwarps - 1 - w;
         else if (g_sched >= 2) for (int w = nwarps - 1; w > 0; --w) { g_sched_state = g_sched_state * 6364136223846793005ull + 1442695040888963407ull; std::swap(order[w], order[(g_sched_state >> 33) % (unsigned)(w + 1)]); }
-        for (int ti = 0; ti < c.nthreads && !c.aborted; ++ti) {
+        for (int ti = 0; ti < c.nthreads && !aborted(); ++ti) {
             const int t = order[ti >> 5] * 32 + (ti & 31);
             if (t >= c.nthreads) continue;
             Fiber& f = c.fibers[t];
@@ -339,44 +363,74 @@ static void run_cta(Cta& c) {
             threadIdx_.z = (unsigned)t / (blockDim_.x * blockDim_.y);
             emu_switch(&g_main_sp, f.sp);
         }
-        if (c.progress == before) { if (++stalled >= 4) break; } else stalled = 0;
-    }
-    if (!c.aborted && c.alive > 0) {
         c.cur = -1;
-        std::string who;
-        std::map<std::string, std::vector<int>> by_reason;
-        for (int t = 0; t < c.nthreads; ++t) {
-            const Fiber& f = c.fibers[t];
-            if (f.done) continue;
-            char why[160] = "(running)";
-            if (f.wait_kind == 1) snprintf(why, sizeof why, "__syncthreads (%d of %d live threads arrived)", c.bar_count, c.alive);
-            else if (f.wait_kind == 2) snprintf(why, sizeof why, "warp shuffle / __syncwarp (mask %08x, arrived %08x)", f.wait_a, f.wait_b);
-            else if (f.wait_kind == 3) {
-                const Mbar& m = c.mbars[f.wait_a];
-                snprintf(why, sizeof why, "mbarrier 0x%x parity %u (phase %u, pending arrivals %u of %u, tx bytes %lld, TMA copies in flight %zu, commits owed %d)",
-                         f.wait_a, f.wait_b, m.phase, m.pending, m.count, (long long)m.tx, m.copies.size(), m.mma_commits);
+    };
+    while (alive() > 0 && !aborted()) {
+        const unsigned long long before = progress_sum();
+        // CTAs of a cluster run on different SMs at unrelated speeds.  Default ("depth"): each CTA in turn runs as far as it can before
+        // the next one gets the machine -- the CTA that completes a cluster barrier races ahead of its peers (reads their shared memory
+        // late, overwrites its own early, exits first), the order that exposes a missing barrier.  SGM_EMU_CLUSTER=lockstep: one pass
+        // per CTA in turn.  SGM_EMU_SCHED=reverse also reverses the order of the CTAs.
+        for (size_t k = 0; k < grp.size(); ++k) {
+            Cta* cp = grp[g_sched == 1 ? grp.size() - 1 - k : k];
+            if (cp->alive == 0) continue;
+            for (;;) {
+                const unsigned long long p0 = cp->progress;
+                pass(cp);
+                if (g_cluster_lockstep || grp.size() == 1 || cp->alive == 0 || cp->progress == p0 || aborted()) break;
             }
-            by_reason[why].push_back(t);
         }
-        for (auto& kv : by_reason) {
-            who += "\n  " + std::to_string(kv.second.size()) + " thread(s) [" + std::to_string(kv.second.front()) + ".." + std::to_string(kv.second.back()) + "] at " + kv.first;
+        if (progress_sum() == before) { if (++stalled >= 4) break; } else stalled = 0;
+    }
+    if (!aborted() && alive() > 0) {
+        std::string who;
+        Cta* first = nullptr;
+        for (Cta* cp : grp) {
+            Cta& c = *cp;
+            if (c.alive == 0) continue;
+            if (!first) first = cp;
+            c.cur = -1;
+            std::map<std::string, std::vector<int>> by_reason;
+            for (int t = 0; t < c.nthreads; ++t) {
+                const Fiber& f = c.fibers[t];
+                if (f.done) continue;
+                char why[200] = "(running)";
+                if (f.wait_kind == 1) snprintf(why, sizeof why, "__syncthreads (%d of %d live threads arrived)", c.bar_count, c.alive);
+                else if (f.wait_kind == 2) snprintf(why, sizeof why, "warp shuffle / __syncwarp (mask %08x, arrived %08x)", f.wait_a, f.wait_b);
+                else if (f.wait_kind == 3) {
+                    const Mbar& m = c.mbars[f.wait_a];
+                    snprintf(why, sizeof why, "mbarrier 0x%x parity %u (phase %u, pending arrivals %u of %u, tx bytes %lld, TMA copies in flight %zu, commits owed %d)",
+                             f.wait_a, f.wait_b, m.phase, m.pending, m.count, (long long)m.tx, m.copies.size(), m.mma_commits);
+                }
+                else if (f.wait_kind == 4) snprintf(why, sizeof why, "barrier.cluster.wait (%d threads of the cluster have arrived)", c.cl ? c.cl->bar_arrived : 0);
+                by_reason[why].push_back(t);
+            }
+            for (auto& kv : by_reason) {
+                who += "\n  " + (grp.size() > 1 ? "cluster rank " + std::to_string(c.rank) + ": " : std::string()) + std::to_string(kv.second.size()) + " thread(s) [" +
+                       std::to_string(kv.second.front()) + ".." + std::to_string(kv.second.back()) + "] at " + kv.first;
+            }
         }
-        g_errmsg = std::string("emu fault: DEADLOCK in kernel ") + c.kname + ", block (" + std::to_string(blockIdx_.x) + "," + std::to_string(blockIdx_.y) + "," +
-                   std::to_string(blockIdx_.z) + "): threads still waiting: " + who;
+        g_errmsg = std::string("emu fault: DEADLOCK in kernel ") + first->kname + ", block (" + std::to_string(first->bx) + "," + std::to_string(first->by) + "," +
+                   std::to_string(first->bz) + "): threads still waiting: " + who;
         g_err = cudaErrorLaunchTimeout;
-        c.aborted = true;
+        for (Cta* cp : grp) cp->aborted = true;
         if (g_verbose || getenv("SGM_EMU_TRACE")) fprintf(stderr, "%s\n", g_errmsg.c_str());
     }
-    c.cur = -1;
+    for (Cta* cp : grp) cp->cur = -1;
     g_cta = nullptr;
 }
 
-void launch(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+static void launch_impl(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem, unsigned cluster_x, const std::function<void()>& body) {
     init_once();
     if (g_err) return;
     const size_t nthreads = (size_t)block.x * block.y * block.z;
     if (nthreads == 0 || nthreads > 1024 || grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535 || grid.z > 65535) {
         g_last = cudaErrorInvalidValue; g_errmsg = std::string("emu: invalid launch configuration for ") + name; return;
+    }
+    if (cluster_x == 0 || cluster_x > 8 || (grid.x % cluster_x) != 0) {   // portable cluster sizes only (16 needs cudaFuncAttributeNonPortableClusterSizeAllowed)
+        g_last = cudaErrorInvalidValue;
+        g_errmsg = std::string("emu: ") + name + ": cluster dimension " + std::to_string(cluster_x) + " must be in [1, 8] and divide gridDim.x = " + std::to_string(grid.x);
+        return;
     }
     int limit = 48 * 1024;
     auto it = g_dyn_limit.find(fn);
@@ -390,33 +444,94 @@ void launch(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem
     gridDim_ = grid; blockDim_ = block;
     for (unsigned bz = 0; bz < grid.z && !g_err; ++bz)
         for (unsigned by = 0; by < grid.y && !g_err; ++by)
-            for (unsigned bx = 0; bx < grid.x && !g_err; ++bx) {
-                Cta c;
-                c.kname = name; c.body = &body; c.nthreads = (int)nthreads; c.alive = (int)nthreads;
-                c.fibers.resize(nthreads);
-                c.warps.resize((nthreads + 31) / 32);
-                for (size_t t = 0; t < nthreads; ++t) {
-                    Fiber& f = c.fibers[t];
-                    f.stack = get_stack(); f.done = false;
-                    uintptr_t top = ((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15;
-                    void** sp = (void**)(top - 16);
-                    sp[0] = (void*)&emu_trampoline;
-                    sp -= 6;
-                    for (int k = 0; k < 6; ++k) sp[k] = nullptr;
-                    f.sp = sp;
-                    WarpEx& w = c.warps[t >> 5];
-                    w.alive |= 1u << (t & 31); w.gen[t & 31] = 0;
+            for (unsigned bx0 = 0; bx0 < grid.x && !g_err; bx0 += cluster_x) {
+                std::vector<Cta> ctas(cluster_x);
+                Cluster cl;
+                std::vector<Cta*> grp;
+                for (unsigned r = 0; r < cluster_x; ++r) {
+                    Cta& c = ctas[r];
+                    c.kname = name; c.body = &body; c.nthreads = (int)nthreads; c.alive = (int)nthreads;
+                    c.bx = bx0 + r; c.by = by; c.bz = bz; c.rank = (int)r; c.cl = &cl;
+                    c.fibers.resize(nthreads);
+                    c.warps.resize((nthreads + 31) / 32);
+                    for (size_t t = 0; t < nthreads; ++t) {
+                        Fiber& f = c.fibers[t];
+                        f.stack = get_stack(); f.done = false;
+                        uintptr_t top = ((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15;
+                        void** sp = (void**)(top - 16);
+                        sp[0] = (void*)&emu_trampoline;
+                        sp -= 6;
+                        for (int k = 0; k < 6; ++k) sp[k] = nullptr;
+                        f.sp = sp;
+                        WarpEx& w = c.warps[t >> 5];
+                        w.alive |= 1u << (t & 31); w.gen[t & 31] = 0;
+                    }
+                    // poison shared memory: uninitialised reads give NaNs, not zeros
+                    unsigned char* pool = g_smem_pool + (size_t)r * SMEM_POOL;
+                    memset(pool, 0xff, smem + 2048 < SMEM_POOL ? smem + 2048 : SMEM_POOL);
+                    c.smem = pool + 1024; c.smem_bytes = smem;
+                    cl.ctas.push_back(&c);
+                    grp.push_back(&c);
                 }
-                // poison shared memory: uninitialised reads give NaNs, not zeros
-                memset(g_smem_pool, 0xff, SMEM_POOL);
-                c.smem = g_smem_pool + 1024; c.smem_bytes = smem;
-                blockIdx_.x = bx; blockIdx_.y = by; blockIdx_.z = bz;
-                run_cta(c);
-                for (auto& f : c.fibers) g_stack_pool.push_back(f.stack);
-                if (!c.aborted && c.tmem_alloc_cols != 0) {
-                    g_err = cudaErrorLaunchFailure; g_errmsg = std::string("emu fault: kernel ") + name + " exited without tcgen05.dealloc";
+                run_group(grp);
+                for (Cta& c : ctas) {
+                    for (auto& f : c.fibers) g_stack_pool.push_back(f.stack);
+                    if (!c.aborted && c.tmem_alloc_cols != 0 && !g_err) {
+                        g_err = cudaErrorLaunchFailure; g_errmsg = std::string("emu fault: kernel ") + name + " exited without tcgen05.dealloc";
+                    }
                 }
             }
+}
+void launch(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) { launch_impl(name, fn, grid, block, smem, 1, body); }
+void launch_cluster(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem, unsigned cluster_x, const std::function<void()>& body) {
+    launch_impl(name, fn, grid, block, smem, cluster_x, body);
+}
+
+// ---- thread-block clusters ----------------------------------------------------------------------------------------------------
+unsigned cluster_ctarank() { return (unsigned)g_cta->rank; }
+unsigned cluster_nctarank() { return (unsigned)g_cta->cl->ctas.size(); }
+static int cluster_alive(const Cluster& cl) { int n = 0; for (const Cta* c : cl.ctas) n += c->alive; return n; }
+static void cluster_release_if_complete(Cluster& cl) {
+    const int need = cluster_alive(cl);
+    if (need > 0 && cl.bar_arrived >= need) { cl.bar_arrived = 0; ++cl.bar_gen; for (Cta* c : cl.ctas) ++c->progress; }
+}
+// barrier.cluster.arrive (+ .release) and barrier.cluster.wait (+ .acquire): every thread of every CTA of the cluster arrives once
+// per phase; threads that have exited count as arrived (hardware behaviour)
+void cluster_arrive() {
+    Cta& c = *g_cta;
+    Fiber& f = c.fibers[c.cur];
+    if (f.cl_arrived) fault("barrier.cluster.arrive executed twice without a barrier.cluster.wait in between");
+    f.cl_arrived = true; f.cl_gen = c.cl->bar_gen;
+    ++c.cl->bar_arrived; ++c.progress;
+    cluster_release_if_complete(*c.cl);
+}
+void cluster_wait() {
+    Cta& c = *g_cta;
+    Fiber& f = c.fibers[c.cur];
+    if (!f.cl_arrived) fault("barrier.cluster.wait without a preceding barrier.cluster.arrive");
+    f.wait_kind = 4;
+    while (c.cl->bar_gen == f.cl_gen) yield();
+    f.cl_arrived = false;
+}
+// mapa.shared::cluster: the shared-window address of the same offset in CTA `rank` of the cluster (the rank rides in bits 24..)
+uint32_t mapa(uint32_t addr, uint32_t rank) {
+    Cta& c = *g_cta;
+    if (rank >= c.cl->ctas.size()) fault("mapa: target rank %u outside the cluster of %zu CTAs", rank, c.cl->ctas.size());
+    (void)smem_ptr(addr & 0xFFFFFFu, 1, 1);
+    return (addr & 0xFFFFFFu) | ((rank + 1u) << 24);
+}
+unsigned char* dsmem_ptr(uint32_t addr, size_t bytes, size_t align) {
+    Cta& c = *g_cta;
+    const uint32_t tag = addr >> 24;
+    if (tag == 0) return smem_ptr(addr, bytes, align);   // a shared::cta address is a valid shared::cluster address of the own CTA
+    if (tag > c.cl->ctas.size()) fault("shared::cluster access with a malformed address 0x%x", addr);
+    Cta& t = *c.cl->ctas[tag - 1];
+    if (t.alive == 0) fault("shared::cluster access to CTA rank %u, which has already exited (its shared memory is gone): missing cluster barrier before exit", tag - 1);
+    const uint32_t a = addr & 0xFFFFFFu, base = window_base(t.smem_align);
+    if (a < base || (size_t)(a - base) + bytes > t.smem_bytes)
+        fault("shared::cluster access out of range: rank %u window address 0x%x + %zu, dynamic shared memory is [0x%x, 0x%zx)", tag - 1, a, bytes, base, (size_t)base + t.smem_bytes);
+    if (align > 1 && (a % align) != 0) fault("misaligned shared::cluster access: address 0x%x, %zu-byte alignment required", a, align);
+    return t.smem + (a - base);
 }
 
 }  // namespace emu

@@ -54,6 +54,14 @@ extern uint3 threadIdx_, blockIdx_;
 extern dim3 blockDim_, gridDim_;
 
 void launch(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+// thread-block clusters of cluster_x CTAs along x (cudaLaunchKernelEx + cudaLaunchAttributeClusterDimension on the device)
+void launch_cluster(const char* name, const void* fn, dim3 grid, dim3 block, size_t smem, unsigned cluster_x, const std::function<void()>& body);
+unsigned cluster_ctarank();
+unsigned cluster_nctarank();
+void cluster_arrive();             // barrier.cluster.arrive.release
+void cluster_wait();               // barrier.cluster.wait.acquire
+uint32_t mapa(uint32_t addr, uint32_t rank);                           // mapa.shared::cluster
+unsigned char* dsmem_ptr(uint32_t addr, size_t bytes, size_t align);   // checked shared::cluster address -> host pointer
 void yield();                      // back to the scheduler (the calling fiber stays runnable)
 void progress();                   // "something changed": resets the deadlock detector
 [[noreturn]] void fault(const char* fmt, ...);   // device-side fault (illegal address / instruction): aborts the launch, sticky error

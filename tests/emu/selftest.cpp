@@ -83,6 +83,23 @@ __global__ void k_refill_race(const float* src, float* out) {
     mbar_wait(bar, 1);
 }
 
+// ---- 8. thread-block clusters: every CTA publishes a value in its shared memory and sums its peers' values through distributed
+// shared memory.  mode 0: correct (barrier before the reads, barrier before exit); 1: no barrier before the reads (a peer's slot is
+// still poison); 2: no barrier before exit (a CTA that is done leaves while a peer has yet to read its slot)
+__global__ void k_cluster_exchange(float* out, int mode) {
+    SGM_DYN_SMEM(float, smem, 16);
+    const uint32_t slot = smem_u32(smem);
+    const uint32_t S = cluster_nctarank(), rank = cluster_ctarank();
+    if (threadIdx.x == 0) smem[0] = (float)(rank + 1);
+    if (mode != 1) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (uint32_t p = 0; p < S; ++p) s += ld_dsmem32(mapa(slot, p));
+        out[blockIdx.x] = s;
+    }
+    if (mode != 2) { cluster_arrive(); cluster_wait(); }
+}
+
 const char* finish() {
     static char buf[1024];
     cudaError_t e = cudaDeviceSynchronize();
@@ -135,6 +152,19 @@ const char* selftest_tma_unaligned(int c0) {
     SGM_LAUNCH(k_tma_unaligned, 1, 32, 32 * 1024, 0, map, c0);
     const char* m = finish();
     if (!*m) cudaFree(g);
+    return m;
+}
+// out[0] = the sum CTA 0 computed (1 + 2 + ... + cluster size when the protocol is right)
+const char* selftest_cluster_exchange(int cluster, int mode, float* sum0) {
+    emu_reset_error();
+    float* out; cudaMalloc(&out, 16 * 4);
+    cudaError_t err;
+    SGM_LAUNCH_CLUSTER(err, k_cluster_exchange, 2 * cluster, 64, 64, 0, cluster, out, mode);
+    (void)err;
+    const char* m = finish();
+    float o[16] = {0};
+    if (!*m) { cudaMemcpy(o, out, 2 * cluster * 4, cudaMemcpyDeviceToHost); cudaFree(out); }
+    *sum0 = o[0];
     return m;
 }
 const char* selftest_divergent_barrier() { emu_reset_error(); SGM_LAUNCH(k_divergent_barrier, 1, 64, 64, 0); return finish(); }

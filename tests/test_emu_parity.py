@@ -194,6 +194,33 @@ def test_logistic_kernel_variants(emulated_library, case_name, option, value, pa
     del rs
 
 
+# ---- mode finder on a thread-block cluster per mode (logistic_opt_split.cuh): cluster launch, barrier.cluster, DSMEM loads ------
+@pytest.mark.parametrize("case_name,split,shared", [("logistic54", 8, True), ("logistic54_n500", 4, True), ("logistic5", 2, True), ("logistic130", 8, True),
+                                                    ("logistic54_n101", 4, True), ("logistic1024_n1024_N3000", 8, True), ("logistic54", 2, False), ("logistic130", 4, False),
+                                                    ("logistic54_n20", 8, True)])
+def test_mode_finder_cluster_split(emulated_library, case_name, split, shared):
+    before = ran(emulated_library, "logistic_opt_split")
+    T._deterministic_steps(case_name, "sgld", True, shared=shared, options={"mode_finder_split": split}, n_opt=6 if "1024" in case_name else 25)
+    assert ran(emulated_library, "logistic_opt_split") > before, "the cluster mode finder did not run"
+
+
+def test_mode_finder_cluster_split_equals_one_cta_per_mode(emulated_library):
+    """Device-drawn minibatches: the cluster of CTAs draws exactly the rows the one-CTA finder draws (same keyed permutation, positions
+    split over the ranks), so both arrive at the same mode up to the order of the float32 sums; 137 steps cross the 100-iteration
+    launch boundary of checkOptDivergence."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import validation as V
+    case = make_case("logistic54")
+    modes = []
+    for split in (1, 4):
+        dev = T.device_setup(case, "sgld", True, n_chains=2, n_iters_opt=137, sharedMode=True)
+        V.setOption(dev, "mode_finder_split", split)
+        S.initSess(dev, verbose=False)
+        modes.append(V.getMode(dev)[0])
+    scale = np.abs(modes[0]).max()
+    assert np.abs(modes[0] - modes[1]).max() <= 1e-5 * scale
+
+
 # ---- tcgen05 many-mode full gradient (cvg_kernel): TMA 128-byte-swizzled tiles, UMMA descriptors, A operand in TMEM -------------
 @pytest.mark.parametrize("case_name,chains", [("logistic54", 20), ("logistic5", 16), ("logistic130", 40)])
 def test_many_mode_full_gradient(emulated_library, case_name, chains):
@@ -219,7 +246,8 @@ def test_many_mode_full_gradient_wide_rows():
 
 # ---- other timing models / schedules, each in a fresh interpreter: "eager" asynchronous engines (copies land at issue), warps
 # scheduled in reverse and in random order (inter-warp races are schedule dependent; the default order starts every pass at warp 0)
-@pytest.mark.parametrize("env,lazy", [({"SGM_EMU_ASYNC": "eager"}, 0), ({"SGM_EMU_SCHED": "reverse"}, 1), ({"SGM_EMU_SCHED": "20261020"}, 1)])
+@pytest.mark.parametrize("env,lazy", [({"SGM_EMU_ASYNC": "eager"}, 0), ({"SGM_EMU_SCHED": "reverse"}, 1), ({"SGM_EMU_SCHED": "20261020"}, 1),
+                                      ({"SGM_EMU_CLUSTER": "lockstep", "SGM_EMU_ASYNC": "eager"}, 0)])
 def test_kernels_under_other_timing_models(env, lazy):
     code = f"""
 from tests.emu import backend
@@ -229,6 +257,8 @@ with backend.emulated() as lib:
     for case in ("logistic54", "logistic54_n101", "logistic130"):
         for algo in T.ALGOS:
             T._deterministic_steps(case, algo, True, shared=(algo == "sgld"))
+    for case, split, shared in (("logistic54", 4, False), ("logistic54_n101", 8, True), ("logistic130", 2, False)):   # clusters: CTA order, lockstep / depth-first
+        T._deterministic_steps(case, "sgld", True, shared=shared, options={{"mode_finder_split": split}})
     T._deterministic_steps("mixture", "sghmc", True, shared=False)
     T._deterministic_steps("softmaxnet_small", "sghmc", True, shared=False)
     T._deterministic_steps("softmaxnet", "sghmc", False, shared=False)

@@ -17,6 +17,8 @@ def emu():
     lib.selftest_missing_wait.argtypes = [C.c_int, C.POINTER(C.c_float)]
     lib.selftest_tma_unaligned.restype = C.c_char_p
     lib.selftest_tma_unaligned.argtypes = [C.c_int]
+    lib.selftest_cluster_exchange.restype = C.c_char_p
+    lib.selftest_cluster_exchange.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
     yield lib
     lib.emu_reset_error()
 
@@ -42,6 +44,19 @@ def test_out_of_range_accesses_fault(emu):
 def test_unaligned_tma_coordinate_is_an_illegal_instruction(emu):
     assert emu.selftest_tma_unaligned(32) == b""
     assert b"not 16-byte aligned" in emu.selftest_tma_unaligned(33)
+
+
+def test_cluster_protocol_errors_are_reported(emu):
+    """Thread-block clusters (the cluster mode finder, csrc/logistic_opt_split.cuh): the CTAs of a cluster run one after another as far
+    as each can get, so a CTA that should have waited for its peers reads their shared memory before it is written, and a CTA that
+    leaves without the final barrier is gone when a peer comes to read it."""
+    v = C.c_float()
+    for cluster in (2, 4, 8):
+        assert emu.selftest_cluster_exchange(cluster, 0, C.byref(v)) == b"" and v.value == cluster * (cluster + 1) / 2
+    msg = emu.selftest_cluster_exchange(4, 1, C.byref(v))
+    assert msg == b"" and v.value != v.value, "a read of a peer's slot before the cluster barrier sees unwritten (poisoned) shared memory"
+    assert b"already exited" in emu.selftest_cluster_exchange(4, 2, C.byref(v))
+    emu.emu_reset_error()
 
 
 def test_refilled_stage_is_seen_by_late_readers(emu):

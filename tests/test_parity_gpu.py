@@ -57,6 +57,9 @@ def tensor_close_ref(ours_flat, ref32, ref64, what, lenient):
         o += sz
 
 
+ONE_CTA_FINDER = {"mode_finder_split": 1}
+
+
 def draw_inputs(rs, chain: OS.Chain, N, n, C):
     idx = np.stack([np.stack([rs.choice(N, n, replace=False) for _ in range(chain.n_sub())]) for _ in range(C)])
     noise = rs.randn(C, chain.noise_len()).astype(np.float32)
@@ -67,7 +70,9 @@ def draw_inputs(rs, chain: OS.Chain, N, n, C):
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("cv", [False, True])
 def test_deterministic_steps_match_oracle(lib, case_name, algo, cv):
-    _deterministic_steps(case_name, algo, cv, shared=False)
+    # the mode finder pinned to one CTA per mode: these tests run first on a GPU (tests/conftest.py) and keep to the kernels with the
+    # longest record on hardware; the cluster finder (the default for few modes) has its own test further down the order
+    _deterministic_steps(case_name, algo, cv, shared=False, options=ONE_CTA_FINDER if case_name.startswith("logistic") else None)
 
 
 @pytest.mark.parametrize("case_name", ["gauss2d", "mixture", "logistic5", "logistic54", "logistic130", "softmaxnet_small"])
@@ -75,7 +80,18 @@ def test_deterministic_steps_match_oracle(lib, case_name, algo, cv):
 def test_deterministic_steps_shared_mode(lib, case_name, algo):
     """*cv with ONE mode shared by all chains (SGM_FLAG_SHARED_MODE): the logistic short-row kernel then
     reads the residual at the mode from the rows (cached once) instead of recomputing x.beta_hat."""
-    _deterministic_steps(case_name, algo, True, shared=True)
+    _deterministic_steps(case_name, algo, True, shared=True, options=ONE_CTA_FINDER if case_name.startswith("logistic") else None)
+
+
+@pytest.mark.parametrize("case_name,split,shared", [("logistic54", 8, True), ("logistic54_n500", 4, True), ("logistic5", 2, True), ("logistic130", 8, True),
+                                                    ("logistic54_n101", 4, True), ("logistic1024_n1024_N3000", 8, True), ("logistic54", 2, False), ("logistic130", 4, False),
+                                                    ("logistic54", 1, True), ("logistic1024_n1024_N3000", 1, False),   # 1 = one CTA per mode (the default once modes x 2 > SMs)
+                                                    ("logistic54", 0, True), ("logistic130", 0, False), ("logistic54_n500", 0, True)])   # 0 = the default dispatch
+def test_mode_finder_cluster_split(lib, case_name, split, shared):
+    """The *cv mode finder with a thread-block cluster per mode (logistic_opt_split.cuh: the minibatch split over the cluster's CTAs,
+    partial sums exchanged through distributed shared memory, rows prefetched across steps) finds the oracle's mode -- cluster sizes
+    2 / 4 / 8, one shared mode and one mode per chain, minibatches that do not divide by the cluster size, long rows."""
+    _deterministic_steps(case_name, "sgld", True, shared=shared, options={"mode_finder_split": split})
 
 
 def _summand_mass(case, theta, rows):
@@ -89,16 +105,19 @@ def _summand_mass(case, theta, rows):
     return {"bias": corr * r.sum(), "beta": corr * (r[:, None] * np.abs(X)).sum(0).max()}
 
 
-def _deterministic_steps(case_name, algo, cv, shared, mass_scaled=False):
+def _deterministic_steps(case_name, algo, cv, shared, mass_scaled=False, options=None, n_opt=None):
     from sgmcmc_b200 import validation as V
     case = make_case(case_name)
-    C, steps, n_opt = 3, 4, 25
+    C, steps, n_opt_default = 3, 4, 25
     if case_name == "softmaxnet":  # full 784-100-10: keep the CPU oracle's share of the test short
-        C, steps, n_opt = 2, 2, 3
+        C, steps, n_opt_default = 2, 2, 3
     if case_name.startswith("logistic1024"):
-        C, steps, n_opt = 2, 3, 6
+        C, steps, n_opt_default = 2, 3, 6
+    n_opt = n_opt_default if n_opt is None else n_opt
     rs = np.random.RandomState(5)
     dev = device_setup(case, algo, cv, n_chains=C, n_iters_opt=n_opt, sharedMode=shared)
+    for key, value in (options or {}).items():   # pins a kernel path (sgm_set_option)
+        V.setOption(dev, key, value)
     chains32 = [oracle_chain(case, algo, cv, np.float32, graph=True) for _ in range(C)]
     chains64 = [oracle_chain(case, algo, cv, np.float64) for _ in range(C)]
     P = sum(int(np.size(v)) for v in case["params"].values())
