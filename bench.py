@@ -103,7 +103,38 @@ def oracle_model(w):
     return OM.SoftmaxNet()
 
 
+PIN_ONE_CTA_FINDER = False   # set when the cluster mode finder failed its probe (probe_cluster_finder below)
+
+
 def make_sampler(w, rank, world, chains_local, seed=13, shared=True, synth=None, n_iters_opt=None):
+    sg = _make_sampler(w, rank, world, chains_local, seed, shared, synth, n_iters_opt)
+    if PIN_ONE_CTA_FINDER and w["cv"] and w["family"] == "logistic":
+        from sgmcmc_b200 import validation as V
+        V.setOption(sg, "mode_finder_split", 1)
+    return sg
+
+
+def probe_cluster_finder(timeout_s=600):
+    """tools/probe_cluster_finder.py in a process of its own: the cluster mode finder (default dispatch for a shared mode) had never run
+    on hardware when this round ended.  Returns the probe's JSON object; {"ok": False, ...} makes this run keep the finder on one CTA
+    per mode, so a fault in the new kernel costs the `mode_finder` entry of the line and not the line."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_cluster_finder.py")], capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"ok": False, "why": f"no answer within {timeout_s} s (killed)"}
+    for ln in reversed(p.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            try:
+                r = json.loads(ln)
+                r["ok"] = bool(r.get("ok")) and p.returncode == 0
+                return r
+            except ValueError:
+                break
+    return {"ok": False, "why": f"probe exited {p.returncode} without a result", "stderr_tail": p.stderr[-400:]}
+
+
+def _make_sampler(w, rank, world, chains_local, seed=13, shared=True, synth=None, n_iters_opt=None):
     import sgmcmc_b200 as S
     ll, lp = model_objects(w["family"])
     kw = dict(logPrior=lp, minibatchSize=w["n"], seed=seed, nChains=chains_local, chainOffset=rank * chains_local,
@@ -304,26 +335,51 @@ def cpu_proxy(w, budget_s, threads):
     return ips, f"{sample_note}1 chain, {iters} sgmcmcSteps in {dt:.1f} s, torch CPU float32 graph replica, {threads} thread(s)", fg, data
 
 
+def cpu_chain_leg(w, budget_s):
+    """Child of run_reference: ONE chain of the reference-structured proxy on one thread; prints its rate."""
+    ips, note, fg, _ = cpu_proxy(w, budget_s, 1)
+    return {"ips": ips, "note": note, "full_gradient_s": fg}
+
+
 def run_reference(args, w):
-    """--impl reference: the reference's own structure on the host cores (the real R+TF stack is absent)."""
-    import torch
+    """--impl reference: the reference's own structure on the host cores (the real R+TF stack is absent).  A chain of the reference is
+    sequential and its per-op work is far too small for intra-op threads to help (torch with 8 threads: 27 iterations/s against 634 on one
+    thread for c3, measured on the development host), so "all the host threads it can use" means what a user of the reference would do
+    with a many-core host: one independent chain per core (one R process each).  Each step of the arm = P single-thread chain processes
+    running concurrently for a bounded time; value = the sum of their rates, mean over the K timed steps."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    times, iters_tot = [], 0
-    ips_all = []
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))        # <= 32 processes: each holds its own copy of the dataset (0.7 GB for c3)
+    budget = max(2.0, min(15.0, 100.0 / max(1, args.steps + args.warmup)))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    env.update(OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    cmd = [sys.executable, os.path.abspath(__file__), "--leg", "cpu_chain", "--workload", args.workload, "--gpus", "1"]
+    vals, note, failed = [], "", 0
     for i in range(args.warmup + args.steps):
-        ips, note, fg, _ = cpu_proxy(w, budget if i >= args.warmup else 1.0, threads)
-        if i >= args.warmup:
-            ips_all.append(ips)
-    val = float(np.mean(ips_all))
+        b = budget if i >= args.warmup else 1.0
+        children = [subprocess.Popen(cmd + ["--cpu-budget", str(b)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env, cwd=ROOT) for _ in range(procs)]
+        rates = []
+        for ch in children:
+            try:
+                out, _ = ch.communicate(timeout=b * 4 + 240)
+                r = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+                rates.append(r["ips"]); note = r["note"]
+            except Exception:   # noqa: BLE001
+                ch.kill(); failed += 1
+        if i >= args.warmup and rates:
+            vals.append(float(np.sum(rates)))
+    if not vals:
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU chain process produced a rate"}))
+        return
+    val = float(np.mean(vals))
+    sample = f"{procs} independent single-thread chains at once, each: {note}" + (f"; {failed} process(es) failed" if failed else "")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * budget, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": w["desc"], "chains": 1},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": note},
+            "config": {"workload": args.workload, "desc": w["desc"], "chains": procs},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "TF-proxy (torch CPU) -- not the reference binary: R and TensorFlow are absent from this image"}
     print(json.dumps(line))
@@ -377,6 +433,25 @@ def quick_workload(name, steps=5, iters=None):
 
 
 
+def mode_finder_ab(w, n_iters_opt=None):
+    """The *cv mode finder (getMode: nItersOpt sequential SGD steps) with one CTA per mode and with the default dispatch (a thread-block
+    cluster per mode when there are few modes), each on a fresh sampler: device time of initSess, which is the finder plus one full-data
+    gradient and a log-posterior check every 100 steps -- an upper bound on the time per SGD step."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import validation as V
+    n_opt = n_iters_opt or min(int(w.get("n_iters_opt", 2000)), 2000)
+    out = {"n_iters_opt": n_opt, "modes": 1}
+    for name, split in (("one_cta_per_mode", 1), ("default_dispatch", 0)):
+        sg = make_sampler(w, 0, 1, w["chains"], n_iters_opt=n_opt)
+        V.setOption(sg, "mode_finder_split", split)
+        S.initSess(sg, verbose=False)      # warm-up (first launch of every kernel)
+        S.initSess(sg, verbose=False)
+        ms, launches = V.lastTiming(sg)
+        out[name] = {"init_ms": ms, "us_per_sgd_step_upper_bound": ms * 1e3 / n_opt, "launches": launches}
+        del sg
+    return out
+
+
 def run_leg_in_child(leg, args, timeout_s=300):
     """Runs one optional leg (`--leg NAME`) of this script in its own process (N = 1 only) and returns its JSON object.  A leg that
     faults on the device (a sticky CUDA error ends every later call of the process that raised it) or hangs then costs its own entry,
@@ -403,6 +478,8 @@ def leg_result(leg, w, args):
     try:
         if leg == "modes":
             return many_mode_full_gradient(w, 0, 1, args.modes)
+        if leg == "finder":
+            return mode_finder_ab(w)
         if leg.startswith("quick:"):
             return quick_workload(leg.split(":", 1)[1])
         return {"error": f"unknown leg {leg}"}
@@ -412,6 +489,9 @@ def leg_result(leg, w, args):
 
 def run_leg(args, w):
     """Child side of run_leg_in_child: one JSON object on stdout."""
+    if args.leg == "cpu_chain":     # the reference arm's worker: CPU only
+        print(json.dumps(cpu_chain_leg(w, args.cpu_budget)))
+        return
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -446,6 +526,16 @@ def run_ours(args, w):
     total_chains = chains_local * world
     peak, peak_src = measured_peaks()
     errors = {}
+    # ---- the cluster mode finder, tried in a child process before this process depends on it (rank 0 asks, every rank follows)
+    global PIN_ONE_CTA_FINDER
+    finder_probe = None
+    if w["cv"] and w["family"] == "logistic":
+        if rank == 0:
+            finder_probe = probe_cluster_finder()
+        bad = 0.0 if (finder_probe is None or finder_probe.get("ok")) else 1.0
+        if world > 1:
+            bad = max_over_ranks([bad])[0]
+        PIN_ONE_CTA_FINDER = bad > 0
 
     def barrier():
         if world > 1:
@@ -585,6 +675,10 @@ def run_ours(args, w):
             line["cv_full_gradient_modes"] = (run_leg_in_child("modes", args) if world == 1 else many_mode_full_gradient(w, rank, world, args.modes))
         except Exception as e:   # noqa: BLE001
             errors["cv_full_gradient_modes"] = f"{type(e).__name__}: {str(e)[:300]}"
+    if finder_probe is not None:
+        line["mode_finder_probe"] = dict(finder_probe, pinned_to_one_cta_per_mode=PIN_ONE_CTA_FINDER)
+    if world == 1 and w["cv"] and w["family"] == "logistic" and not args.no_extra:
+        line["mode_finder"] = run_leg_in_child("finder", args) if not PIN_ONE_CTA_FINDER else {"error": "the cluster finder failed its probe; see mode_finder_probe"}
     if world == 1 and not args.no_extra:
         line["other_workloads"] = {name: run_leg_in_child("quick:" + name, args) for name in ("c1", "c2", "c4") if name != args.workload}
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -616,7 +710,7 @@ def main():
     ap.add_argument("--modes", type=int, default=1024, help="modes of the many-mode control-variate full gradient leg (logistic *cv workloads)")
     ap.add_argument("--no-modes", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the compact c1 / c2 / c4 measurements added to the line at N = 1")
-    ap.add_argument("--leg", default=None, help="internal: run ONE optional leg (modes | quick:c1 | quick:c2 | quick:c4) and print its JSON object")
+    ap.add_argument("--leg", default=None, help="internal: run ONE optional leg (modes | finder | quick:c1 | quick:c2 | quick:c4) and print its JSON object")
     ap.add_argument("--peer-shards", action="store_true",
                     help="N > 1, logistic workloads: every rank keeps its own rows and maps the peers' (the c5 config at N = world x rows/GPU)")
     args = ap.parse_args()

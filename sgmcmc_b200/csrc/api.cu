@@ -611,7 +611,7 @@ static int launch_logistic_opt_split(sgm_handle* h, const ChainArgs& a, int spli
 
 static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
     const_cast<ChainArgs&>(a).rhat_cached = h->rhat_cached ? 1 : 0;
-    if (a.algo == ALGO_OPT && !a.cv && a.L == 1 && h->n_shards <= 1 && a.X == h->X) {
+    if (a.algo == ALGO_OPT && !a.cv && a.L == 1 && a.X == h->X) {   // (a dataset sharded over ranks too: rows resolve through the shard table, the bulk copies then cross NVLink)
         int sms = 0;
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
         LogiShape s;
@@ -1670,9 +1670,11 @@ static void widen_rows(const float* src, double* out, int64_t r0, int64_t r1, in
     _mm_sfence();
 #endif
 }
-static void widen_block(const float* src, double* out, int C, int P, int64_t cnt, int64_t n_iters, int64_t it0) {
+// `ranks_on_host`: the processes of the job that share this host's cores (sgm_comm_init's world on a single node): each takes its share
+static void widen_block(const float* src, double* out, int C, int P, int64_t cnt, int64_t n_iters, int64_t it0, int ranks_on_host) {
     const int64_t rows = (int64_t)C * P;
     unsigned hw = std::thread::hardware_concurrency();
+    if (ranks_on_host > 1) hw = hw / (unsigned)ranks_on_host > 0 ? hw / (unsigned)ranks_on_host : 1;
     int T = (int)(hw ? (hw > 16 ? 16 : hw) : 1);
     if (rows * cnt < (1 << 16)) T = 1;
     if (T == 1) { widen_rows(src, out, 0, rows, cnt, n_iters, it0); return; }
@@ -1705,7 +1707,7 @@ extern "C" int sgm_sample(sgm_handle* h, int64_t n_iters, int32_t check_every, d
             for (int c = 0; c < h->C; ++c) if (std::isnan(p.h_lp[b][c])) return fail(SGM_EDIVERGED, "Chain diverged, try decreasing stepsize");
             if (h->progress) h->progress(h->progress_user, 2, it0 + cnt, p.h_lp[b], h->C);
         }
-        widen_block(p.h_T[b], out, h->C, h->P, cnt, n_iters, it0);
+        widen_block(p.h_T[b], out, h->C, h->P, cnt, n_iters, it0, h->world);
         return SGM_OK;
     };
     for (int64_t k = 0; k < n_blocks && status == SGM_OK; ++k) {
@@ -2100,7 +2102,7 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
             };
             chain(h->C, "sampling");
             if (h->cv) {
-                const int split = h->n_shards <= 1 ? opt_split_of(h->opt_mode_finder_split, M, h->n, sms) : 1;
+                const int split = opt_split_of(h->opt_mode_finder_split, M, h->n, sms);
                 if (split > 1 && os_smem_bytes(s.G, s.V, h->ld) <= 227 * 1024) {
                     char note[160];
                     int clusters = sms / split; if (clusters > M) clusters = M;

@@ -16,6 +16,9 @@
 // buffer of its step s at step s + 2, which it reaches only after the barrier of step s + 1, at which every peer has finished
 // reading step s.  One cluster barrier per step suffices.
 //
+// A dataset sharded over ranks and peer-mapped (common.cuh: row_ptr) is gathered the same way: the bulk copy's source is then a peer's
+// memory and the copy crosses NVLink -- the scale-out config's shared mode is where one SM's load path hurt most.
+//
 // Row -> thread mapping as in logistic.cuh: G lanes per row, lane lg owns the float4 columns lg + G v (v < V); the bias rides
 // as a constant-1 feature in the slot y occupies.  Internal parameter order beta[0..d-1], bias at d (logistic.cuh).
 #pragma once
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(OS_THREADS, 1) logistic_opt_split_kernel(const
         for (int s = 0; s < OS_STAGES; ++s) mbar_init(bars + 8u * s, 1);
     fence_mbar_init();
     __syncwarp();
-    SGM_EMU_NOTE("logistic_opt_split");
+    SGM_EMU_NOTE(a.n_shards > 1 ? "logistic_opt_split:sharded" : "logistic_opt_split");
     uint32_t gg = 0;        // rounds consumed so far by this warp (stage = gg % OS_STAGES, phase parity = (gg / OS_STAGES) & 1)
     uint32_t tt = 0;        // steps finished so far by this CTA, over ALL its modes: the partial-sum buffer alternates with it (a new mode
                             // must not start on the buffer the previous mode's last step may still be read from)

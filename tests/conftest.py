@@ -19,7 +19,26 @@ def lib():
     if not os.path.exists(_lib.LIB_PATH):
         import __graft_entry__
         __graft_entry__.build()
+    _probe_cluster_finder()
     return _lib.load()
+
+
+def _probe_cluster_finder():
+    """GPU sessions only (this fixture is what the `-m gpu` tests ask for): the cluster mode finder -- the default dispatch for few
+    modes, never run on hardware before this session -- is tried in a process of its own first (tools/probe_cluster_finder.py).  If
+    that process does not exit 0, the samplers of tests/cases.py keep to one CTA per mode and test_mode_finder_cluster_split reports
+    the probe's output; a sticky device fault then never happens inside the pytest process."""
+    import subprocess
+    import torch
+    from tests import cases
+    if not torch.cuda.is_available():
+        return
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_cluster_finder.py")], capture_output=True, text=True, timeout=600, cwd=ROOT)
+        if p.returncode != 0:
+            cases.CLUSTER_PROBE_ERROR = f"probe exited {p.returncode}: {p.stdout[-600:]} {p.stderr[-1200:]}"
+    except subprocess.TimeoutExpired:
+        cases.CLUSTER_PROBE_ERROR = "probe did not finish within 600 s (killed)"
 
 
 # GPU run order: the paths with the longest record on hardware first, the paths whose first execution on a GPU this run is last

@@ -51,6 +51,7 @@ def test_bench_prints_one_contract_line(monkeypatch, main):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
     monkeypatch.setattr(__graft_entry__, "build", lambda *a, **k: None)
     monkeypatch.setattr(bench, "measure_tf32_peak", lambda *a, **k: (900.0, 800.0))
+    monkeypatch.setattr(bench, "probe_cluster_finder", lambda *a, **k: {"ok": True, "checks": []})   # (a child process of the real probe finds no GPU here)
     # the optional legs run in child processes on a GPU box; here (emulated build, loaded into THIS process) they run in place
     monkeypatch.setattr(bench, "run_leg_in_child", lambda leg, args, timeout_s=0: bench.leg_result(leg, bench.workload(args.workload, None), args))
     orig = bench.workload
@@ -83,6 +84,8 @@ def test_bench_prints_one_contract_line(monkeypatch, main):
     assert set(line["other_workloads"]) == {"c1", "c2", "c4"} - {main}
     assert all("error" not in v for v in line["other_workloads"].values()), line["other_workloads"]
     if main == "c3":
+        f = line["mode_finder"]
+        assert "error" not in f and f["one_cta_per_mode"]["init_ms"] > 0 and f["default_dispatch"]["us_per_sgd_step_upper_bound"] > 0, f
         assert line["cv_full_gradient"]["GBps"] > 0
         m = line["cv_full_gradient_modes"]
         assert m["TFLOPs"] > 0 and m["peak"] == 800.0 and abs(m["frac_of_3xtf32_ceiling"] - 3 * m["frac"]) < 1e-12
@@ -104,6 +107,7 @@ def _bench_worker(rank, world, port, peer_shards, out):
     torch.cuda.synchronize = lambda *_: None
     __graft_entry__.build = lambda *a, **k: None
     bench.measure_tf32_peak = lambda *a, **k: (900.0, 800.0)
+    bench.probe_cluster_finder = lambda *a, **k: {"ok": rank != 0 or not peer_shards, "why": "test: rank 0 reports a failed probe"}   # both ranks must then pin
     rs = np.random.RandomState(13)
     N, d = (1200, 130) if peer_shards else (1500, 54)   # a sharded dataset takes the long-row kernel (rows resolved through the shard table)
     w = dict(desc="toy", algo="sgnht" if peer_shards else "sgld", cv=True, family="logistic", data={"X": rs.randn(N, d), "y": (rs.rand(N) < 0.5).astype(np.float64)},
@@ -150,6 +154,7 @@ def test_bench_two_ranks_prints_one_line_on_rank_0(peer_shards):
     m = line["cv_full_gradient_modes"]
     assert m["modes"] == 32 and m["collective_ms"] is not None and m["TFLOPs_all_ranks"] > 0
     assert ("sharded over 2 ranks" in line["config"]["dataset"]) == peer_shards
+    assert line["mode_finder_probe"]["pinned_to_one_cta_per_mode"] == peer_shards
 
 
 def test_optional_leg_failure_costs_only_its_own_entry():

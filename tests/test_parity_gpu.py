@@ -91,6 +91,9 @@ def test_mode_finder_cluster_split(lib, case_name, split, shared):
     """The *cv mode finder with a thread-block cluster per mode (logistic_opt_split.cuh: the minibatch split over the cluster's CTAs,
     partial sums exchanged through distributed shared memory, rows prefetched across steps) finds the oracle's mode -- cluster sizes
     2 / 4 / 8, one shared mode and one mode per chain, minibatches that do not divide by the cluster size, long rows."""
+    from tests import cases
+    if lib is not None and cases.CLUSTER_PROBE_ERROR and split != 1:
+        pytest.fail("the cluster mode finder failed its probe in a separate process (tests/conftest.py): " + cases.CLUSTER_PROBE_ERROR)
     _deterministic_steps(case_name, "sgld", True, shared=shared, options={"mode_finder_split": split})
 
 

@@ -9,6 +9,8 @@ step() { echo "=== $1"; }
 step "1 pre-flight (compute-sanitizer, one process per path)"
 timeout 1500 python tools/preflight.py > gpurun_out/r02_preflight.log 2>&1; rc=$?; tail -30 gpurun_out/r02_preflight.log
 [ $rc -eq 0 ] || { echo "preflight failed (rc=$rc)"; exit 1; }
+step "1b cluster mode finder probe (its own process; bench.py and the GPU tests repeat it and fall back to one CTA per mode if it fails)"
+timeout 600 python tools/probe_cluster_finder.py > gpurun_out/r02_cluster_probe.json 2> gpurun_out/r02_cluster_probe.err; echo "probe rc=$?"; tail -c 600 gpurun_out/r02_cluster_probe.json
 step "2 pytest -m gpu"
 timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gpu_tests.log 2>&1; rc=$?; tail -15 gpurun_out/r02_gpu_tests.log
 [ $rc -eq 0 ] || { echo "gpu tests failed (rc=$rc)"; exit 2; }

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Probe of the cluster mode finder (csrc/logistic_opt_split.cuh) in a process of its own.
+
+    python tools/probe_cluster_finder.py        # exit 0: the cluster finder runs on this device and agrees with the one-CTA finder
+
+The cluster finder is the default dispatch for few modes and has never executed on hardware (round 2 had no GPU access).  A device
+fault is sticky for the process that raised it, so bench.py and the GPU test session ask THIS script first, in a child process:
+when it does not exit 0 they pin "mode_finder_split" = 1 (the kernels measured in round 1) for everything else they do, and only the
+cluster finder's own test / bench entry reports the failure.  Prints one JSON line.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main() -> int:
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"ok": False, "why": "no CUDA device"}))
+        return 2
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import validation as V
+    from tests.cases import device_setup, make_case
+    out = {"ok": True, "checks": []}
+    for case_name, split in (("logistic54", 8), ("logistic54_n101", 4), ("logistic130", 2), ("logistic1024_n1024_N3000", 8)):
+        case = make_case(case_name)
+        modes = []
+        for s in (1, split):
+            dev = device_setup(case, "sgld", True, n_chains=2, n_iters_opt=60, sharedMode=True, pin_finder=False)
+            V.setOption(dev, "mode_finder_split", s)
+            S.initSess(dev, verbose=False)
+            modes.append(V.getMode(dev)[0])
+            del dev
+        err = float(np.abs(modes[0] - modes[1]).max() / max(np.abs(modes[0]).max(), 1e-30))
+        out["checks"].append({"case": case_name, "split": split, "rel_err_vs_one_cta": err})
+        if not (err <= 1e-5):
+            out["ok"] = False
+            out["why"] = f"{case_name}: cluster of {split} CTAs differs from one CTA per mode by {err:.2e}"
+            break
+    print(json.dumps(out))
+    return 0 if out["ok"] else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
