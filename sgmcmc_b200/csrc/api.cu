@@ -157,7 +157,6 @@ struct sgm_handle {
     bool inited = false;
     CUtensorMap tmap;           // 2-D map of the dataset (box = one row) for TMA tile::gather4
     bool tmap_ok = false;
-    float* Xt = nullptr; int64_t xt_pitch = 0;      // logistic, many modes: transposed copy of the features [d][xt_pitch] (tensor-core pass 2)
     float* Rt = nullptr; size_t rt_cap = 0;         // residuals of one row block, transposed [M][rt_pitch]
     // dataset row-sharded over the ranks, peers mapped through CUDA IPC (sgm_attach_peer_shards): every rank holds N rows, the
     // chains sample from world x N rows and gather remote rows over NVLink; the control-variate pass sums the local shard
@@ -650,7 +649,8 @@ static int launch_fullgrad_stream_t(sgm_handle* h, int64_t row0, int64_t row1, c
 }
 
 // ---- many modes: two tensor-core contractions per row block (logistic_cv_gemm.cuh)
-static int cvg_encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t pitch_floats) {
+static int cvg_encode_2d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t pitch_floats, uint32_t box_inner = CVG_KC,
+                         uint32_t box_rows = CVG_TILE, bool swizzle128 = true) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -663,10 +663,10 @@ static int cvg_encode_2d(CUtensorMap* map, const float* base, uint64_t inner, ui
     }
     const cuuint64_t gdim[2] = {inner, rows};
     const cuuint64_t gstride[1] = {pitch_floats * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)CVG_KC, (cuuint32_t)CVG_TILE};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
+              swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
 }
 
 static bool logistic_fullgrad_use_tc(const sgm_handle* h, int M) {
@@ -678,10 +678,12 @@ static bool logistic_fullgrad_use_tc(const sgm_handle* h, int M) {
 // ---- launch plan of the many-mode pass: every number the launches and tensor maps use, computed without touching the device.
 // launch_logistic_fullgrad_tc() executes exactly this plan; sgm_debug_plan() prints and checks it for any configuration
 // (full BASELINE sizes, any world size, any shard start) in a process that has no GPU.
-struct TmapPlan {          // a 2-D float32 tensor map with a (CVG_KC x CVG_TILE) box, 128-byte swizzle
+struct TmapPlan {          // a 2-D float32 tensor map; box (CVG_KC x CVG_TILE) with the 128-byte swizzle unless stated otherwise
     const char* what;
     uint64_t inner, rows, pitch_floats;      // globalDim[0], globalDim[1], globalStrides[0] / 4
     uint64_t alloc_floats;                   // floats available behind the base pointer
+    uint32_t box_inner = CVG_KC, box_rows = CVG_TILE;
+    bool swizzle128 = true;
 };
 struct CvgBlockPlan {
     int64_t b0, b1;        // global rows of the block
@@ -691,31 +693,31 @@ struct CvgBlockPlan {
     TmapPlan mRt;
 };
 struct CvgPlan {
-    int64_t blk = 0, pitch = 0, xt_pitch = 0;
-    int shift = 0, tiles_m = 0;
-    size_t rt_bytes = 0, xt_bytes = 0;
-    TmapPlan mX{}, mTh{}, mXt{};
+    int64_t blk = 0, pitch = 0;
+    int shift = 0, tiles_m = 0;              // shift: always 0 (kept in the arithmetic: the column of a block's first row in R^T)
+    int a_box_w = 0;                         // pass 2: features per row of the A tile (<= 128)
+    size_t rt_bytes = 0;
+    TmapPlan mX{}, mTh{}, mX2{};
     std::vector<CvgBlockPlan> blocks;
 };
 
 static CvgPlan cvg_plan(int64_t N, int d, int ld, int Pst, int M, int64_t row0, int64_t row1, int sms) {
     CvgPlan P;
     const int64_t rows_all = row1 - row0;
-    P.xt_pitch = (N + 3) / 4 * 4;
-    P.xt_bytes = (size_t)d * P.xt_pitch * sizeof(float);
     // row blocks: R^T of one block stays <= ~2 GB
     const int Mpad = (int)cdiv(M, CVG_TILE) * CVG_TILE;
     int64_t blk = ((int64_t)1 << 29) / Mpad;
     blk = blk / 256 * 256; if (blk < 256) blk = 256;
     if (blk > rows_all) blk = cdiv(rows_all, 256) * 256;
     P.blk = blk;
-    P.shift = (int)(row0 & 31);   // pass 2 walks K from the 32-row aligned global row row0 - shift (TMA box starts are 16-byte aligned)
+    P.shift = 0;                  // pass 2's K coordinate is a ROW of X (outer dimension of its tensor map) and a block-relative column of R^T: no alignment rule binds the row a range starts at
+    P.a_box_w = ld < CVG_TILE ? ld : CVG_TILE;
     P.pitch = blk + 32;
     P.rt_bytes = (size_t)M * P.pitch * sizeof(float);
     P.tiles_m = (int)cdiv(M, CVG_TILE);
     P.mX = TmapPlan{"X (pass 1, A)", (uint64_t)d, (uint64_t)N, (uint64_t)ld, (uint64_t)N * ld};
     P.mTh = TmapPlan{"theta_hat (pass 1, B)", (uint64_t)d, (uint64_t)M, (uint64_t)Pst, (uint64_t)M * Pst};
-    P.mXt = TmapPlan{"X^T (pass 2, A)", (uint64_t)N, (uint64_t)d, (uint64_t)P.xt_pitch, (uint64_t)d * P.xt_pitch};
+    P.mX2 = TmapPlan{"X (pass 2, A: 32 data rows x features, no swizzle)", (uint64_t)d, (uint64_t)N, (uint64_t)ld, (uint64_t)N * ld, (uint32_t)P.a_box_w, (uint32_t)CVG_KC, false};
     for (int64_t b0 = row0; b0 < row1; b0 += blk) {
         CvgBlockPlan B{};
         const int64_t b1 = (b0 + blk < row1) ? b0 + blk : row1;
@@ -733,7 +735,7 @@ static CvgPlan cvg_plan(int64_t N, int d, int ld, int Pst, int M, int64_t row0, 
         B.rowsum_warps = (int64_t)M * cdiv(rows + P.shift, 4096);
         B.p1 = a;
         // pass 2: gsum[m][k] += sum_i R^T[m][i] X^T[k][i], K (= rows) split over CTAs
-        a.epi = 1; a.a_row0 = 0;
+        a.epi = 1; a.a_row0 = 0; a.a_box_w = P.a_box_w;
         const int tiles_k = (int)cdiv(d, CVG_TILE);
         // ~8 work items per CTA (static round-robin: the tail is at most one item), each at least 2 K segments long
         int64_t splits = cdiv((int64_t)sms * 8, (int64_t)tiles_k * P.tiles_m);
@@ -762,19 +764,24 @@ static void tmap_plan_check(const TmapPlan& m, std::vector<std::string>& bad) {
     if (m.pitch_floats * 4 >= (1ull << 40)) say("globalStrides[0] >= 2^40");
     if (m.pitch_floats < m.inner) say("row pitch shorter than the row");
     if (m.rows > 0 && (m.rows - 1) * m.pitch_floats + m.inner > m.alloc_floats) say("tensor extends past its allocation");
+    if (m.box_inner < 1 || m.box_inner > 256 || m.box_rows < 1 || m.box_rows > 256) say("box dimension outside [1, 256]");
+    if ((m.box_inner * 4) % 16 != 0) say("inner box extent is not a multiple of 16 bytes");
+    if (m.swizzle128 && m.box_inner * 4 > 128) say("inner box extent exceeds the 128-byte swizzle span");
     static_assert(CVG_KC * 4 == 128 && CVG_TILE <= 256, "box = one 128-byte swizzle span x <= 256 rows");
 }
 
 static std::vector<std::string> cvg_plan_check(const CvgPlan& P) {
     std::vector<std::string> bad;
     char buf[256];
-    tmap_plan_check(P.mX, bad); tmap_plan_check(P.mTh, bad); tmap_plan_check(P.mXt, bad);
+    tmap_plan_check(P.mX, bad); tmap_plan_check(P.mTh, bad); tmap_plan_check(P.mX2, bad);
     if (CVG_SMEM > 227 * 1024) bad.push_back("cvg_kernel: more than 227 KB of shared memory");
+    if ((size_t)P.a_box_w * CVG_KC * 4 > CVG_OP_BYTES) bad.push_back("cvg pass 2: the A tile exceeds its stage");
     for (const CvgBlockPlan& B : P.blocks) {
         tmap_plan_check(B.mRt, bad);
         for (const CvgArgs* a : {&B.p1, &B.p2}) {
-            // innermost TMA coordinates are a_k0 / b_k0 + split * k_per_split + chunk * CVG_KC: every term must be a multiple of 4 floats
-            if ((a->a_k0 & 3) || (a->b_k0 & 3) || (a->k_per_split & 3)) {
+            // innermost TMA coordinates: pass 1 a_k0 / b_k0 + chunk * CVG_KC for both operands; pass 2 b_k0 + split * k_per_split + chunk * CVG_KC for
+            // R^T (the A operand's K coordinate is a row of X there: any integer) -- every term must be a multiple of 4 floats
+            if ((a->epi == 0 && (a->a_k0 & 3)) || (a->b_k0 & 3) || (a->k_per_split & 3)) {
                 snprintf(buf, sizeof buf, "cvg pass %d, rows [%lld, %lld): TMA box start not 16-byte aligned (a_k0 %d, b_k0 %d, K per split %d)", a->epi + 1,
                          (long long)B.b0, (long long)B.b1, a->a_k0, a->b_k0, a->k_per_split);
                 bad.push_back(buf);
@@ -807,30 +814,19 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
         if (!bad.empty()) return fail(SGM_EINVAL, "logistic full gradient: %s%s", bad[0].c_str(), bad.size() > 1 ? " (and more)" : "");
     }
     CU(cudaFuncSetAttribute(cvg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CVG_SMEM));
-    if (!h->Xt) {   // one-time transposed copy of the features (pass 2 reads it K-major); 16-byte aligned rows
-        h->xt_pitch = P.xt_pitch;
-        CU(cudaMalloc(&h->Xt, P.xt_bytes));
-        dim3 tb(32, 8), tg((unsigned)cdiv(h->N, 32), (unsigned)cdiv(d, 32));
-        SGM_LAUNCH(cvg_transpose_kernel, tg, tb, 0, h->stream, h->X, h->N, h->ld, d, h->Xt, h->xt_pitch);
-        CU(cudaGetLastError());
-    }
     if (P.rt_bytes > h->rt_cap) {
         if (h->Rt) cudaFree(h->Rt);
         h->Rt = nullptr; h->rt_cap = 0;
         CU(cudaMalloc(&h->Rt, P.rt_bytes));
         h->rt_cap = P.rt_bytes;
     }
-    CUtensorMap mX, mTh, mXt, mRt;
+    CUtensorMap mX, mTh, mX2, mRt;
     if (cvg_encode_2d(&mX, h->X, P.mX.inner, P.mX.rows, P.mX.pitch_floats) || cvg_encode_2d(&mTh, theta_hat, P.mTh.inner, P.mTh.rows, P.mTh.pitch_floats) ||
-        cvg_encode_2d(&mXt, h->Xt, P.mXt.inner, P.mXt.rows, P.mXt.pitch_floats))
+        cvg_encode_2d(&mX2, h->X, P.mX2.inner, P.mX2.rows, P.mX2.pitch_floats, P.mX2.box_inner, P.mX2.box_rows, P.mX2.swizzle128))
         return fail(SGM_ECUDA, "logistic full gradient: cuTensorMapEncodeTiled failed");
     for (const CvgBlockPlan& B : P.blocks) {
         const int64_t rows = B.b1 - B.b0;
         if (cvg_encode_2d(&mRt, h->Rt, B.mRt.inner, B.mRt.rows, B.mRt.pitch_floats)) return fail(SGM_ECUDA, "logistic full gradient: tensor map (R^T)");
-        if (P.shift) {
-            SGM_LAUNCH(cvg_zero_cols_kernel, (unsigned)cdiv((int64_t)M * P.shift, 256), 256, 0, h->stream, h->Rt, P.pitch, P.shift, M);
-            CU(cudaGetLastError());
-        }
         CvgArgs a = B.p1;
         a.X = h->X; a.theta_hat = theta_hat; a.Rt = h->Rt; a.gsum = h->gsum;
         SGM_LAUNCH(cvg_kernel, B.grid1, CVG_THREADS, CVG_SMEM, h->stream, a, mX, mTh);
@@ -839,7 +835,7 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
         CU(cudaGetLastError());
         a = B.p2;
         a.X = h->X; a.theta_hat = theta_hat; a.Rt = h->Rt; a.gsum = h->gsum;
-        SGM_LAUNCH(cvg_kernel, B.grid2, CVG_THREADS, CVG_SMEM, h->stream, a, mXt, mRt);
+        SGM_LAUNCH(cvg_kernel, B.grid2, CVG_THREADS, CVG_SMEM, h->stream, a, mX2, mRt);
         CU(cudaGetLastError());
         h->last_launches += 3;
     }
@@ -1225,7 +1221,7 @@ extern "C" void sgm_destroy(sgm_handle* h) {
     for (int r = 0; r < 16; ++r) if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     if (h->d_shard_ptr) cudaFree((void*)h->d_shard_ptr);
     void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,
-                    h->d_flag, h->d_idx, h->d_noise, h->store, h->Xt, h->Rt, h->hat_all, h->gsum_all};
+                    h->d_flag, h->d_idx, h->d_noise, h->store, h->Rt, h->hat_all, h->gsum_all};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int b = 0; b < 2; ++b) {
         if (h->pipe.d_store[b]) cudaFree(h->pipe.d_store[b]);
@@ -2117,10 +2113,8 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
                 if (logistic_fullgrad_use_tc(h, Mg)) {
                     const CvgPlan P = cvg_plan(h->N, h->d, h->ld, h->Pst, Mg, row0, row1, sms);
                     for (const std::string& b : cvg_plan_check(P)) po.bad.push_back(b);
-                    po.map(P.mX, CVG_KC, CVG_TILE, "128B"); po.map(P.mTh, CVG_KC, CVG_TILE, "128B"); po.map(P.mXt, CVG_KC, CVG_TILE, "128B");
-                    char note[160];
-                    snprintf(note, sizeof note, "%zu row block(s) of %lld rows, K walk starts %d rows before the range; X^T %zu B, R^T %zu B", P.blocks.size(), (long long)P.blk, P.shift, P.xt_bytes, P.rt_bytes);
-                    po.launch("cvg_transpose_kernel", cdiv(h->N, 32), cdiv(h->d, 32), 1, 256, 0, 0, note);
+                    po.map(P.mX, CVG_KC, CVG_TILE, "128B"); po.map(P.mTh, CVG_KC, CVG_TILE, "128B"); po.map(P.mX2, (int)P.mX2.box_inner, (int)P.mX2.box_rows, "none");
+                    char note[320];
                     size_t shown = 0;
                     for (const CvgBlockPlan& B : P.blocks) {
                         if (shown++ >= 2 && &B != &P.blocks.back()) continue;   // first two and the last block are printed; all are checked
@@ -2128,7 +2122,8 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
                         snprintf(note, sizeof note, "pass 1, rows [%lld, %lld): %d items x %d K stages", (long long)B.b0, (long long)B.b1, B.p1.n_items, B.p1.k_chunks);
                         po.launch("cvg_kernel", B.grid1, 1, 1, CVG_THREADS, CVG_SMEM, 512, note);
                         po.launch("cvg_rowsum_kernel", cdiv(B.rowsum_warps * 32, 256), 1, 1, 256, 0, 0);
-                        snprintf(note, sizeof note, "pass 2: %d items, K per split %d (from global row %d)", B.p2.n_items, B.p2.k_per_split, B.p2.a_k0);
+                        snprintf(note, sizeof note, "pass 2: %d items, K per split %d (from global row %d); A = %d features x 32 rows of X as stored (no transposed copy); %zu block(s), R^T %zu B",
+                                 B.p2.n_items, B.p2.k_per_split, B.p2.a_k0, P.a_box_w, P.blocks.size(), P.rt_bytes);
                         po.launch("cvg_kernel", B.grid2, 1, 1, CVG_THREADS, CVG_SMEM, 512, note);
                     }
                 } else if (Mg == 1 && h->ld <= 128 && ((Q & 1) || (Q % 4 == 2)) && fg_smem_bytes(h->ld, FG_SHORT_ROWS) <= 113 * 1024) {

@@ -7,9 +7,14 @@
 //     G[m][k] = sum_i R[i][m] X[i][k]            [d x N] x [N x M]          (pass 2, split over row ranges)
 // 4 N d M flops against N d 4 bytes: tensor-bound from a few dozen modes on.
 //
-// Both passes are ONE kernel, C[128 x 128] = A[128 x K] B[128 x K]^T with both operands K-major:
-//     pass 1: A = X (rows i), B = theta_hat (rows m), K = features;
-//     pass 2: A = X^T (rows k; a transposed copy of the data kept in HBM), B = R^T (rows m; written by pass 1), K = data rows.
+// Both passes are ONE kernel, C[128 x 128] = A[128 x K] B[128 x K]^T:
+//     pass 1: A = X (rows i), B = theta_hat (rows m), K = features: both tiles arrive K-major (128-byte swizzle);
+//     pass 2: A = X^T (rows k), B = R^T (rows m; written by pass 1), K = data rows.  No transposed copy of the data exists: the
+//             TMA box is 32 data rows x 128 features of X as it lies in HBM, and the warps that split A into tensor memory read
+//             it column-wise (lane = feature, one 4-byte load per K element: 128 contiguous bytes per warp load, conflict free) --
+//             the A operand goes through registers on its way to TMEM anyway, so the transposition is free.  (Round 1 kept a
+//             second, transposed copy of X in HBM for this pass: + 51 GB at the c5 shard, and a 16-byte alignment rule on the
+//             K coordinate that an odd shard start broke.)
 // float32 accuracy on TF32 tensor cores by the 3-term split hi*hi + hi*lo + lo*hi (tcgen05.mma kind::tf32, accumulators in
 // TMEM).  Pipeline per 32-wide K stage: warp 0 issues two TMA boxes (128-byte swizzle) into a raw stage; warps 2..7 round the
 // raw B tile to TF32 in place (hi), write the residual (lo) into a lo stage and split the raw A tile into TENSOR MEMORY
@@ -47,14 +52,14 @@ struct CvgArgs {
     int a_k0, b_k0;        // K coordinate offsets of split 0 into the A and B tensors (pass 2: global row / block-relative row)
     int k_per_split;       // K elements per split (multiple of 32 x 8)
     int k_end_a;           // exclusive K bound of the A tensor coordinates (pass 2: row1)
+    int a_box_w;           // pass 2: features per row of the A tile in shared memory (the TMA box is a_box_w features x 32 data rows, no swizzle)
     // pass 1 epilogue
     const float* X; int ld; int d;
     int64_t row_base;      // global row of A-tile 0 (this launch's row block)
     int64_t row_end;       // rows >= row_end write r = 0
     const float* theta_hat; int Pst; int M;
     float* Rt; int64_t rt_pitch;   // R^T [M][rt_pitch], column = rt_col0 + row - row_base
-    int rt_col0;           // (TMA box starts must be 16-byte aligned: pass 2 walks K from a 32-row aligned global row, so the
-                           //  block's first row sits at column row_base % 32 and the columns before it are zero)
+    int rt_col0;           // column of the block's first row (0: the R^T coordinates are block-relative, so every box start is 16-byte aligned)
     double* gsum;          // [M][Pst]: pass 1 adds the bias component (column d), pass 2 the feature components
 };
 
@@ -118,8 +123,13 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                     const uint32_t s = g % CVG_NRAW;
                     if (g >= CVG_NRAW) mbar_wait(b_rawfree + 8 * s, ((g / CVG_NRAW) - 1u) & 1u);
                     const uint32_t dst = raw0 + s * CVG_STAGE_BYTES, bar = b_full + 8 * s;
-                    mbar_expect_tx(bar, CVG_STAGE_BYTES);
-                    tma_box2(dst, &tmA, w.ka0 + c * CVG_KC, a.a_row0 + w.tile_a * CVG_TILE, bar);
+                    if (a.epi == 0) {
+                        mbar_expect_tx(bar, CVG_STAGE_BYTES);
+                        tma_box2(dst, &tmA, w.ka0 + c * CVG_KC, a.a_row0 + w.tile_a * CVG_TILE, bar);
+                    } else {   // 32 data rows (K) x a_box_w features of X, rows as they lie in HBM
+                        mbar_expect_tx(bar, (uint32_t)a.a_box_w * CVG_KC * 4u + CVG_OP_BYTES);
+                        tma_box2(dst, &tmA, w.tile_a * CVG_TILE, w.ka0 + c * CVG_KC, bar);
+                    }
                     tma_box2(dst + CVG_OP_BYTES, &tmB, w.kb0 + c * CVG_KC, w.tile_b * CVG_TILE, bar);
                 }
             }
@@ -181,13 +191,26 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
 #pragma unroll
                 for (int u = 0; u < 6; ++u)
                     if (u < b_rounds) xb[u] = lds128(braw + 16u * (uint32_t)(b_first + u * b_step));
-                const uint32_t rowp = raw + (uint32_t)r * 128u;
+                if (a.epi == 0) {
+                    const uint32_t rowp = raw + (uint32_t)r * 128u;
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-                    if (cc < 4 * nhalf) {
-                        const uint32_t chunk = (uint32_t)((4 * hb0 + cc) ^ (r & 7));
-                        xa[cc] = lds128(rowp + 16u * chunk);
-                    }
+                    for (int cc = 0; cc < 8; ++cc)
+                        if (cc < 4 * nhalf) {
+                            const uint32_t chunk = (uint32_t)((4 * hb0 + cc) ^ (r & 7));
+                            xa[cc] = lds128(rowp + 16u * chunk);
+                        }
+                } else {
+                    // pass 2: the tile is [32 data rows][a_box_w features]; this thread's A row is feature r, its K elements one per data row
+                    const bool have = r < a.a_box_w;
+                    const uint32_t colp = raw + 4u * (uint32_t)r, pitch = 4u * (uint32_t)a.a_box_w;
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc)
+                        if (cc < 4 * nhalf) {
+                            const uint32_t k0 = (uint32_t)(4 * (4 * hb0 + cc));
+                            xa[cc].x = have ? lds32(colp + (k0 + 0u) * pitch) : 0.f; xa[cc].y = have ? lds32(colp + (k0 + 1u) * pitch) : 0.f;
+                            xa[cc].z = have ? lds32(colp + (k0 + 2u) * pitch) : 0.f; xa[cc].w = have ? lds32(colp + (k0 + 3u) * pitch) : 0.f;
+                        }
+                }
 #pragma unroll
                 for (int u = 0; u < 6; ++u)
                     if (u < b_rounds) {
@@ -281,12 +304,6 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// zero the alignment columns [0, cols) of every row of R^T
-__global__ void cvg_zero_cols_kernel(float* __restrict__ Rt, int64_t pitch, int cols, int M) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < M * cols) Rt[(size_t)(i / cols) * pitch + (i % cols)] = 0.f;
-}
-
 // bias component of the gradient: gsum[m][d] += sum_i R^T[m][i]   (one warp per 4096-column slice of a row of R^T)
 __global__ void cvg_rowsum_kernel(const float* __restrict__ Rt, int64_t pitch, int64_t rows, int M, int Pst, int d, double* __restrict__ gsum) {
     const int lane = threadIdx.x & 31;
@@ -299,22 +316,6 @@ __global__ void cvg_rowsum_kernel(const float* __restrict__ Rt, int64_t pitch, i
     for (int64_t i = i0 + lane; i < i1; i += 32) s += Rt[(size_t)m * pitch + i];
     s = warp_sum(s);
     if (lane == 0) atomicAdd(gsum + (size_t)m * Pst + d, (double)s);
-}
-
-// X [rows][ld] (features in the first d columns) -> X^T [d][pitch], tiled through shared memory
-__global__ void cvg_transpose_kernel(const float* __restrict__ X, int64_t N, int ld, int d, float* __restrict__ Xt, int64_t pitch) {
-    __shared__ float tile[32][33];
-    const int64_t i0 = (int64_t)blockIdx.x * 32;
-    const int k0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int64_t i = i0 + r; const int k = k0 + threadIdx.x;
-        tile[r][threadIdx.x] = (i < N && k < d) ? X[(size_t)i * ld + k] : 0.f;
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int k = k0 + r; const int64_t i = i0 + threadIdx.x;
-        if (k < d && i < N) Xt[(size_t)k * pitch + i] = tile[threadIdx.x][r];
-    }
 }
 
 }  // namespace sgm
