@@ -88,7 +88,9 @@ typedef struct sgm_config {
     int32_t algo;        /* sgm_algo  */
     int32_t cv;          /* 0: sgld/sghmc/sgnht, 1: *cv */
     int32_t n_data;
-    const sgm_array* data; /* model's dataset entries, in the order the family documents */
+    const sgm_array* data; /* model's dataset entries, in the order the family documents.  Row limits (row numbers are 32-bit on the device):
+                            * < 2^31 rows per handle; with the dataset sharded over ranks (sgm_attach_peer_shards) <= 2^32 rows in the whole job
+                            * (the scale-out config's 1e8 is far below both); sgm_create / sgm_attach_peer_shards return SGM_EINVAL beyond them */
     int32_t n_params;
     const sgm_param* params; /* names(params) order = update order (Gauss-Seidel, R/update.R:43-45) */
     double minibatch_size;   /* < 1: proportion of N (convertProp, R/setup.R:128-140) */
