@@ -178,6 +178,14 @@ int sgm_get_state(sgm_handle* h, double* momentum, double* thermostat);
 /* *cv: mode estimate and full-data gradient at it, each [n_chains][P]. */
 int sgm_get_mode(sgm_handle* h, double* theta_hat, double* grad_hat);
 
+/* State dump / restore (the reference leaves persistence to the user of the step-by-step API -- NEWS.md:19, vignettes/nn.Rmd:11 --
+ * who can only save getParams output; a device-resident sampler also carries momenta, thermostats, the mode and its gradient, and
+ * its position in the random streams).  sgm_save_state writes an opaque blob: call it with buf = NULL to learn the size (*need).
+ * sgm_load_state restores it into a handle created with the same configuration and dataset (checked: model, algorithm, chains,
+ * parameter count, rows, minibatch) -- without sgm_init, i.e. without repeating the mode search -- after which sgm_step / sgm_run /
+ * sgm_sample continue the run bit for bit (the streams are keyed by seed, chain and iteration; the seed travels in the blob). */
+int sgm_save_state(sgm_handle* h, void* buf, size_t cap, size_t* need);
+int sgm_load_state(sgm_handle* h, const void* buf, size_t bytes);
 int64_t sgm_chain_length(const sgm_handle* h);
 /* One copy-out of the stored chain (replaces initStorage/updateStorage,
  * R/storage.R:42-80).  Layout: for chain c, for parameter p: a column-major

@@ -4,7 +4,7 @@ Only the hot path is here: the C-ABI library (csrc/, include/sgmcmc_b200.h) and 
 host-side mirror of the reference's R API for that path (api.py).  Importing the API
 needs the built library; there is no CPU fallback.
 """
-from .api import (getChains, getParams, heldoutLogLik, initSess, sghmc, sghmccv, sghmccvSetup, sghmcSetup, sgld,  # noqa: F401
+from .api import (getChains, getParams, heldoutLogLik, initSess, loadState, saveState, sghmc, sghmccv, sghmccvSetup, sghmcSetup, sgld,  # noqa: F401
                   sgldcv, sgldcvSetup, sgldSetup, sgmcmcStep, sgnht, sgnhtcv, sgnhtcvSetup, sgnhtSetup)
 from .models import (gammaPrecisionPrior, gaussMeanLogLik, laplacePrior, logisticLogLik,  # noqa: F401
                      mixture2LogLik, normalPrior, softmaxNetLogLik)

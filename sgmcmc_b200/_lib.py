@@ -65,6 +65,8 @@ SYMBOLS = {
     "sgm_get_params": (C.c_int, [_H, _PD]),
     "sgm_get_state": (C.c_int, [_H, _PD, _PD]),
     "sgm_get_mode": (C.c_int, [_H, _PD, _PD]),
+    "sgm_save_state": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sgm_load_state": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
     "sgm_chain_length": (C.c_int64, [_H]),
     "sgm_copy_chain": (C.c_int, [_H, _PD]),
     "sgm_reset_chain": (C.c_int, [_H]),

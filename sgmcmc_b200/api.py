@@ -239,6 +239,26 @@ def initSess(sgmcmc: Sgmcmc, verbose=True) -> Session:
     return Session(sgmcmc)
 
 
+def saveState(sgmcmc: Sgmcmc, sess: Session) -> bytes:
+    """The whole sampler state as an opaque blob (sgm_save_state): parameters, momenta, thermostats, the control-variate mode and its
+    gradient, seed and position in the random streams.  The reference leaves persistence to the user of the step-by-step API
+    (NEWS.md:19), who can save getParams() only."""
+    lib = _lib.load()
+    need = C.c_size_t()
+    _lib.check(lib.sgm_save_state(sgmcmc.handle, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _lib.check(lib.sgm_save_state(sgmcmc.handle, buf, need.value, C.byref(need)))
+    return buf.raw
+
+
+def loadState(sgmcmc: Sgmcmc, blob: bytes) -> Session:
+    """Restores saveState()'s blob into a sampler made by the same *Setup call (same dataset): takes the place of initSess -- the mode
+    search is not repeated -- and sgmcmcStep / runs continue the saved run bit for bit."""
+    buf = C.create_string_buffer(bytes(blob), len(blob))
+    _lib.check(_lib.load().sgm_load_state(sgmcmc.handle, buf, len(blob)))
+    return Session(sgmcmc)
+
+
 def sgmcmcStep(sgmcmc: Sgmcmc, sess: Session):
     _lib.check(_lib.load().sgm_step(sgmcmc.handle))
 

@@ -1448,6 +1448,24 @@ static int mode_finder_sharded(sgm_handle* h, const ChainArgs& tmpl, bool det, c
     return check_diverged(h, "Chain diverged");
 }
 
+// What follows a known mode (found by initSess, or restored by sgm_load_state): the stride of the mode arrays and, for the logistic
+// family with ONE mode for every chain, the per-datum residual at the mode cached next to y in the rows (logistic_staged.cuh)
+static int after_mode_setup(sgm_handle* h, int M) {
+    h->base.hat_stride = (M == 1 && h->C > 1) ? 0 : h->Pst;
+    h->rhat_cached = false;
+    // Peers that map this rank's rows (sgm_attach_peer_shards) read the cached residual too, so with a sharded dataset the
+    // cache is only valid when every rank holds the SAME mode (SGM_FLAG_SHARED_MODE); one chain per rank without the flag
+    // means one mode per rank, and the kernels then recompute x . beta_hat per gathered row.
+    const bool same_mode_everywhere = (h->flags & SGM_FLAG_SHARED_MODE) || h->n_shards <= 1;
+    if (h->model == SGM_MODEL_LOGISTIC && M == 1 && same_mode_everywhere && (h->d & 3) != 3) {
+        SGM_LAUNCH(logistic_cache_rhat_kernel, (unsigned)cdiv(h->N * 32, 256), 256, 0, h->stream, h->X, h->N, h->ld, h->d, h->theta_hat);
+        CU(cudaGetLastError());
+        h->rhat_cached = true;
+        h->last_launches += 1;
+    }
+    return SGM_OK;
+}
+
 static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t* opt_idx, bool det) {
     if (!h) return fail(SGM_EINVAL, "null handle");
     if (int rc = set_device(h)) return rc;
@@ -1518,19 +1536,7 @@ static int init_common(sgm_handle* h, const float* momentum_noise, const int32_t
             }
         }
         if (int rc = full_gradient(h)) return rc;
-        h->base.hat_stride = (M == 1 && h->C > 1) ? 0 : h->Pst;
-        // one mode for every chain: cache the per-datum residual at the mode next to y (logistic_staged.cuh)
-        h->rhat_cached = false;
-        // Peers that map this rank's rows (sgm_attach_peer_shards) read the cached residual too, so with a sharded dataset the
-        // cache is only valid when every rank holds the SAME mode (SGM_FLAG_SHARED_MODE); one chain per rank without the flag
-        // means one mode per rank, and the kernels then recompute x . beta_hat per gathered row.
-        const bool same_mode_everywhere = (h->flags & SGM_FLAG_SHARED_MODE) || h->n_shards <= 1;
-        if (h->model == SGM_MODEL_LOGISTIC && M == 1 && same_mode_everywhere && (h->d & 3) != 3) {
-            SGM_LAUNCH(logistic_cache_rhat_kernel, (unsigned)cdiv(h->N * 32, 256), 256, 0, h->stream, h->X, h->N, h->ld, h->d, h->theta_hat);
-            CU(cudaGetLastError());
-            h->rhat_cached = true;
-            h->last_launches += 1;
-        }
+        if (int rc = after_mode_setup(h, M)) return rc;
         if (h->n_shards > 1) {
             // peers read the residuals cached in OUR rows: nobody may sample before every rank has written its shard.  A one-double
             // all-reduce enqueued after the cache kernel completes only when all ranks have reached it (stream-ordered rendezvous).
@@ -1758,6 +1764,81 @@ extern "C" int sgm_debug_phase_cycles(sgm_handle* h, int enable, unsigned long l
     if (h->base.prof && out) { CU(cudaMemcpy(out, h->base.prof, (n > 64 ? 64 : n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost)); }
     if (h->base.prof) CU(cudaMemset(h->base.prof, 0, 64 * sizeof(unsigned long long)));
     if (!enable && h->base.prof) { cudaFree(h->base.prof); h->base.prof = nullptr; }
+    return SGM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------
+// state dump / restore (the reference leaves persistence to the user of the step-by-step API, NEWS.md:19)
+// ------------------------------------------------------------------------------------
+namespace {
+struct StateHeader {
+    uint64_t magic;          // "SGMSTAT1"
+    int32_t model, algo, cv, C, P, Pst, T, M;
+    int64_t N; int32_t n, d;
+    uint64_t seed, step, check_ctr;
+    uint64_t payload_floats;
+};
+constexpr uint64_t STATE_MAGIC = 0x31544154534d4753ull;
+}  // namespace
+
+static size_t state_floats(const sgm_handle* h, int M) {
+    return (size_t)2 * h->C * h->Pst + (size_t)h->C * MAX_TENSORS + (h->cv ? (size_t)2 * M * h->Pst : 0);
+}
+
+extern "C" int sgm_save_state(sgm_handle* h, void* buf, size_t cap, size_t* need) {
+    if (!h || !need) return fail(SGM_EINVAL, "null argument");
+    if (!h->inited) return fail(SGM_ESTATE, "sgm_init has not been called");
+    const int M = h->cv ? hat_count(h) : 0;
+    const size_t nf = state_floats(h, M), bytes = sizeof(StateHeader) + nf * sizeof(float);
+    *need = bytes;
+    if (!buf) return SGM_OK;                       // size query
+    if (cap < bytes) return fail(SGM_EINVAL, "state buffer of %zu bytes, %zu needed", cap, bytes);
+    if (int rc = set_device(h)) return rc;
+    StateHeader hd{};
+    hd.magic = STATE_MAGIC; hd.model = h->model; hd.algo = h->algo; hd.cv = h->cv; hd.C = h->C; hd.P = h->P; hd.Pst = h->Pst; hd.T = h->T; hd.M = M;
+    hd.N = h->N; hd.n = h->n; hd.d = h->d; hd.seed = h->seed; hd.step = h->step; hd.check_ctr = h->check_ctr; hd.payload_floats = nf;
+    std::memcpy(buf, &hd, sizeof hd);
+    float* out = reinterpret_cast<float*>(static_cast<char*>(buf) + sizeof hd);
+    const size_t sb = (size_t)h->C * h->Pst, tb = (size_t)h->C * MAX_TENSORS, mb = (size_t)M * h->Pst;
+    CU(cudaMemcpyAsync(out, h->theta, sb * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); out += sb;
+    CU(cudaMemcpyAsync(out, h->mom, sb * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); out += sb;
+    CU(cudaMemcpyAsync(out, h->thermo, tb * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); out += tb;
+    if (h->cv) {
+        CU(cudaMemcpyAsync(out, h->theta_hat, mb * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); out += mb;
+        CU(cudaMemcpyAsync(out, h->g_hat, mb * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return SGM_OK;
+}
+
+extern "C" int sgm_load_state(sgm_handle* h, const void* buf, size_t bytes) {
+    if (!h || !buf) return fail(SGM_EINVAL, "null argument");
+    if (bytes < sizeof(StateHeader)) return fail(SGM_EINVAL, "state blob too short");
+    StateHeader hd;
+    std::memcpy(&hd, buf, sizeof hd);
+    const int M = h->cv ? hat_count(h) : 0;
+    if (hd.magic != STATE_MAGIC) return fail(SGM_EINVAL, "not a sampler state written by sgm_save_state");
+    if (hd.model != h->model || hd.algo != h->algo || hd.cv != h->cv || hd.C != h->C || hd.P != h->P || hd.Pst != h->Pst || hd.T != h->T || hd.M != M ||
+        hd.N != h->N || hd.n != h->n || hd.d != h->d)
+        return fail(SGM_EINVAL, "the state was saved by a sampler of another shape (model / algorithm / chains / parameters / dataset size / minibatch differ)");
+    if (hd.payload_floats != state_floats(h, M) || bytes < sizeof hd + hd.payload_floats * sizeof(float)) return fail(SGM_EINVAL, "state blob truncated");
+    if (int rc = set_device(h)) return rc;
+    const float* in = reinterpret_cast<const float*>(static_cast<const char*>(buf) + sizeof hd);
+    const size_t sb = (size_t)h->C * h->Pst, tb = (size_t)h->C * MAX_TENSORS, mb = (size_t)M * h->Pst;
+    CU(cudaMemcpyAsync(h->theta, in, sb * sizeof(float), cudaMemcpyHostToDevice, h->stream)); in += sb;
+    CU(cudaMemcpyAsync(h->mom, in, sb * sizeof(float), cudaMemcpyHostToDevice, h->stream)); in += sb;
+    CU(cudaMemcpyAsync(h->thermo, in, tb * sizeof(float), cudaMemcpyHostToDevice, h->stream)); in += tb;
+    if (h->cv) {
+        CU(cudaMemcpyAsync(h->theta_hat, in, mb * sizeof(float), cudaMemcpyHostToDevice, h->stream)); in += mb;
+        CU(cudaMemcpyAsync(h->g_hat, in, mb * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    // the random streams are keyed by (seed, chain, iteration): restoring the seed and the counters continues them exactly
+    h->seed = hd.seed; h->base.k0 = (uint32_t)(hd.seed & 0xffffffffu); h->base.k1 = (uint32_t)(hd.seed >> 32);
+    h->step = hd.step; h->check_ctr = hd.check_ctr;
+    if (h->cv) { if (int rc = after_mode_setup(h, M)) return rc; CU(cudaStreamSynchronize(h->stream)); }
+    h->inited = true;
     return SGM_OK;
 }
 

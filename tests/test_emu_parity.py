@@ -99,6 +99,12 @@ def test_posterior_moments_match_the_oracle(case_name, algo, cv, shared):
     ST.test_posterior_moments_match_the_oracle(None, case_name, algo, cv, shared, n_dev=48, n_orc=8, burn=200, keep=600)
 
 
+@pytest.mark.parametrize("case_name,algo,cv,shared", [("gauss2d", "sgld", False, False), ("mixture", "sghmc", True, False), ("logistic54", "sgnht", True, True),
+                                                      ("logistic130", "sghmc", True, False), ("softmaxnet_small", "sgnht", False, False)])
+def test_saved_state_resumes_the_run(case_name, algo, cv, shared):
+    T.test_saved_state_resumes_the_run_bit_for_bit(None, case_name, algo, cv, shared)
+
+
 def test_mode_finder_cadence(capsys):
     T.test_mode_finder_reports_and_checks_every_100_iterations(None, capsys)
 

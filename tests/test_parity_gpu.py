@@ -495,3 +495,36 @@ def test_last_stored_state_is_the_sampler_state(lib, case_name, algo):
     ch, last = S.getChains(dev), S.getParams(dev, sess)
     for k in ch:
         np.testing.assert_array_equal(np.asarray(ch[k])[:, -1].reshape(2, -1), np.asarray(last[k]).reshape(2, -1), err_msg=k)
+
+
+@pytest.mark.parametrize("case_name,algo,cv,shared", [("gauss2d", "sgld", False, False), ("mixture", "sghmc", True, False), ("logistic54", "sgnht", True, True),
+                                                      ("logistic130", "sghmc", True, False), ("softmaxnet_small", "sgnht", False, False)])
+def test_saved_state_resumes_the_run_bit_for_bit(lib, case_name, algo, cv, shared):
+    """sgm_save_state / sgm_load_state: a sampler restored into a fresh handle (no initSess, no second mode search) continues the saved
+    run exactly -- parameters, momenta, thermostats, the mode, the cached residuals and the (seed, chain, iteration)-keyed streams."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import validation as V
+    from sgmcmc_b200._lib import SgmcmcError
+    case = make_case(case_name)
+    a = device_setup(case, algo, cv, n_chains=3, seed=11, n_iters_opt=30, **({"sharedMode": True} if shared else {}))
+    sess = S.initSess(a, verbose=False)
+    for _ in range(7):
+        S.sgmcmcStep(a, sess)
+    blob = S.saveState(a, sess)
+    for _ in range(5):
+        S.sgmcmcStep(a, sess)
+    b = device_setup(case, algo, cv, n_chains=3, seed=99, n_iters_opt=30, **({"sharedMode": True} if shared else {}))   # another seed: the blob carries the run's
+    sess_b = S.loadState(b, blob)
+    for _ in range(5):
+        S.sgmcmcStep(b, sess_b)
+    assert np.array_equal(V.flatParams(a), V.flatParams(b))
+    (ma, ta), (mb, tb) = V.getState(a), V.getState(b)
+    assert np.array_equal(ma, mb) and np.array_equal(ta, tb)
+    if cv:
+        assert all(np.array_equal(x, y) for x, y in zip(V.getMode(a), V.getMode(b)))
+    # a sampler of another shape refuses the blob
+    other = device_setup(case, algo, cv, n_chains=2, seed=11, n_iters_opt=30, **({"sharedMode": True} if shared else {}))
+    with pytest.raises(SgmcmcError):
+        S.loadState(other, blob)
+    with pytest.raises(SgmcmcError):
+        S.loadState(b, blob[:40])
