@@ -21,11 +21,12 @@ def _rows(rs, n):
 
 
 def random_case(rs):
-    """(kind, case name, sampler, mode).  kind: steps = deterministic-step parity; stream = sgm_sample against sgm_run + sgm_copy_chain
+    """(kind, case name, sampler, mode).  kind: steps = deterministic-step parity; finder = the same with the mode finder on a thread-block
+    cluster of `sampler` CTAs per mode; stream = sgm_sample against sgm_run + sgm_copy_chain
     with the device RNG; cvg = the tensor-core many-mode full gradient."""
     algo = str(rs.choice(["sgld", "sghmc", "sgnht"]))
     mode = str(rs.choice(["plain", "cv", "cv_shared"]))
-    fam = rs.choice(["logistic"] * 5 + ["gauss", "mixture", "net", "cvg", "stream"])
+    fam = rs.choice(["logistic"] * 5 + ["gauss", "mixture", "net", "cvg", "stream", "finder", "finder"])
     if fam == "gauss":
         d, n = int(rs.randint(1, 9)), int(rs.choice([1, 2, 7, 32, 33, 100, 257]))
         return "steps", f"gauss{d}d{'_full' if rs.rand() < 0.5 else ''}_n{n}_N{_rows(rs, n)}", algo, mode
@@ -53,6 +54,8 @@ def random_case(rs):
         d = int(rs.choice([1, 2, 3, 4, 5, 7, 123, 124, 127, 128]))
         n = int(rs.choice([1, 2, 3, 31, 32, 33, 255, 256, 257]))
     name = f"logistic{d}_n{n}_N{_rows(rs, n)}"
+    if fam == "finder":      # the cluster mode finder at a pinned cluster size (csrc/logistic_opt_split.cuh)
+        return "finder", name, str(int(rs.choice([2, 4, 8]))), str(rs.choice(["cv", "cv_shared"]))
     if fam == "stream":
         return "stream", name, algo, mode
     return "steps", name, algo, mode
@@ -62,6 +65,8 @@ def run_case(kind, name, algo, mode):
     from tests import test_parity_gpu as T
     if kind == "steps":
         T._deterministic_steps(name, algo, mode != "plain", shared=(mode == "cv_shared"), mass_scaled=True)
+    elif kind == "finder":
+        T._deterministic_steps(name, "sgld", True, shared=(mode == "cv_shared"), mass_scaled=True, options={"mode_finder_split": int(algo)}, n_opt=9)
     elif kind == "cvg":
         from tests import test_fullgrad_tc_gpu as F
         from tests.cases import make_case
