@@ -732,10 +732,11 @@ static CvgPlan cvg_plan(int64_t N, int d, int ld, int Pst, int M, int64_t row0, 
         a.tiles_a = (int)cdiv(rows, CVG_TILE);
         a.n_items = a.tiles_a * P.tiles_m;
         B.grid1 = a.n_items < sms ? a.n_items : sms;
-        B.rowsum_warps = (int64_t)M * cdiv(rows + P.shift, 4096);
+        B.rowsum_warps = (d % CVG_TILE) != 0 ? 0 : (int64_t)M * cdiv(rows + P.shift, 4096);   // 0: pass 2 sums the bias component itself
         B.p1 = a;
         // pass 2: gsum[m][k] += sum_i R^T[m][i] X^T[k][i], K (= rows) split over CTAs
         a.epi = 1; a.a_row0 = 0; a.a_box_w = P.a_box_w;
+        a.bias_row = (d % CVG_TILE) != 0 ? d : -1;   // a free row of the last feature tile carries the bias sums; a full tile would cost a whole extra one
         const int tiles_k = (int)cdiv(d, CVG_TILE);
         // ~8 work items per CTA (static round-robin: the tail is at most one item), each at least 2 K segments long
         int64_t splits = cdiv((int64_t)sms * 8, (int64_t)tiles_k * P.tiles_m);
@@ -831,13 +832,15 @@ static int launch_logistic_fullgrad_tc(sgm_handle* h, int64_t row0, int64_t row1
         a.X = h->X; a.theta_hat = theta_hat; a.Rt = h->Rt; a.gsum = h->gsum;
         SGM_LAUNCH(cvg_kernel, B.grid1, CVG_THREADS, CVG_SMEM, h->stream, a, mX, mTh);
         CU(cudaGetLastError());
-        SGM_LAUNCH(cvg_rowsum_kernel, (unsigned)cdiv(B.rowsum_warps * 32, 256), 256, 0, h->stream, h->Rt, P.pitch, rows + P.shift, M, h->Pst, d, h->gsum);
-        CU(cudaGetLastError());
+        if (B.rowsum_warps > 0) {
+            SGM_LAUNCH(cvg_rowsum_kernel, (unsigned)cdiv(B.rowsum_warps * 32, 256), 256, 0, h->stream, h->Rt, P.pitch, rows + P.shift, M, h->Pst, d, h->gsum);
+            CU(cudaGetLastError());
+        }
         a = B.p2;
         a.X = h->X; a.theta_hat = theta_hat; a.Rt = h->Rt; a.gsum = h->gsum;
         SGM_LAUNCH(cvg_kernel, B.grid2, CVG_THREADS, CVG_SMEM, h->stream, a, mX2, mRt);
         CU(cudaGetLastError());
-        h->last_launches += 3;
+        h->last_launches += B.rowsum_warps > 0 ? 3 : 2;
     }
     h->fullgrad_flops = 4.0 * (double)rows_all * (double)d * (double)M;
     return SGM_OK;
@@ -2202,7 +2205,7 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
                         po.map(B.mRt, CVG_KC, CVG_TILE, "128B");
                         snprintf(note, sizeof note, "pass 1, rows [%lld, %lld): %d items x %d K stages", (long long)B.b0, (long long)B.b1, B.p1.n_items, B.p1.k_chunks);
                         po.launch("cvg_kernel", B.grid1, 1, 1, CVG_THREADS, CVG_SMEM, 512, note);
-                        po.launch("cvg_rowsum_kernel", cdiv(B.rowsum_warps * 32, 256), 1, 1, 256, 0, 0);
+                        if (B.rowsum_warps > 0) po.launch("cvg_rowsum_kernel", cdiv(B.rowsum_warps * 32, 256), 1, 1, 256, 0, 0);
                         snprintf(note, sizeof note, "pass 2: %d items, K per split %d (from global row %d); A = %d features x 32 rows of X as stored (no transposed copy); %zu block(s), R^T %zu B",
                                  B.p2.n_items, B.p2.k_per_split, B.p2.a_k0, P.a_box_w, P.blocks.size(), P.rt_bytes);
                         po.launch("cvg_kernel", B.grid2, 1, 1, CVG_THREADS, CVG_SMEM, 512, note);

@@ -53,6 +53,8 @@ struct CvgArgs {
     int k_per_split;       // K elements per split (multiple of 32 x 8)
     int k_end_a;           // exclusive K bound of the A tensor coordinates (pass 2: row1)
     int a_box_w;           // pass 2: features per row of the A tile in shared memory (the TMA box is a_box_w features x 32 data rows, no swizzle)
+    int bias_row;          // pass 2: A row (feature index) that is the constant 1 -- its sums are the bias component of the gradient, sum_i R[i][m]
+                           // (d when d % 128 != 0: the row is free, the tile is not full; -1: the sums come from cvg_rowsum_kernel instead)
     // pass 1 epilogue
     const float* X; int ld; int d;
     int64_t row_base;      // global row of A-tile 0 (this launch's row block)
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                 } else {
                     // pass 2: the tile is [32 data rows][a_box_w features]; this thread's A row is feature r, its K elements one per data row
                     const bool have = r < a.a_box_w;
+                    const bool ones = (w.tile_a * CVG_TILE + r) == a.bias_row;   // the bias "feature": 1 for every data row (rows past the range meet R = 0)
                     const uint32_t colp = raw + 4u * (uint32_t)r, pitch = 4u * (uint32_t)a.a_box_w;
 #pragma unroll
                     for (int cc = 0; cc < 8; ++cc)
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
                             const uint32_t k0 = (uint32_t)(4 * (4 * hb0 + cc));
                             xa[cc].x = have ? lds32(colp + (k0 + 0u) * pitch) : 0.f; xa[cc].y = have ? lds32(colp + (k0 + 1u) * pitch) : 0.f;
                             xa[cc].z = have ? lds32(colp + (k0 + 2u) * pitch) : 0.f; xa[cc].w = have ? lds32(colp + (k0 + 3u) * pitch) : 0.f;
+                            if (ones) xa[cc] = make_float4(1.f, 1.f, 1.f, 1.f);
                         }
                 }
 #pragma unroll
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
 #pragma unroll
                 for (int j = 0; j < 64; ++j) {
                     const int m = bcol0 + j;
-                    if (arow < a.d && m < a.M) atomicAdd(a.gsum + (size_t)m * a.Pst + arow, (double)acc[j]);
+                    if ((arow < a.d || arow == a.bias_row) && m < a.M) atomicAdd(a.gsum + (size_t)m * a.Pst + arow, (double)acc[j]);
                     acc[j] = 0.f;
                 }
             }
@@ -304,7 +308,8 @@ __global__ void __launch_bounds__(CVG_THREADS, 1) cvg_kernel(const CvgArgs a, co
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// bias component of the gradient: gsum[m][d] += sum_i R^T[m][i]   (one warp per 4096-column slice of a row of R^T)
+// bias component of the gradient: gsum[m][d] += sum_i R^T[m][i]   (one warp per 4096-column slice of a row of R^T).  Only when d is a
+// multiple of 128: otherwise pass 2 carries a constant-1 row in its last, partly empty feature tile and this read of R^T is saved.
 __global__ void cvg_rowsum_kernel(const float* __restrict__ Rt, int64_t pitch, int64_t rows, int M, int Pst, int d, double* __restrict__ gsum) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

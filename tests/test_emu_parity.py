@@ -235,6 +235,11 @@ def test_many_mode_full_gradient(emulated_library, case_name, chains):
     assert ran(emulated_library, "cvg:pass1") > before[0] and ran(emulated_library, "cvg:pass2") > before[1]
 
 
+@pytest.mark.parametrize("case_name,chains", [("logistic128_n20_N300", 17), ("logistic127_n20_N333", 33), ("logistic129_n20_N259", 130), ("logistic3_n5_N100", 16)])
+def test_many_mode_bias_component_either_way(case_name, chains):
+    F.test_many_mode_bias_component_either_way(None, case_name, chains)
+
+
 def test_many_mode_full_gradient_row_tail():
     F.test_many_mode_full_gradient_row_tail_and_blocks(None)
 

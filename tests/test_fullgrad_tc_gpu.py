@@ -92,6 +92,14 @@ def many_mode_check(case, chains, n_opt=4):
 ROW_RANGES = [(1, 700), (37, 37 + 1153), (2001, 4000), (333, 334), (3, 131), (1939, 3878)]
 
 
+@pytest.mark.parametrize("case_name,chains", [("logistic128_n20_N300", 17), ("logistic256_n20_N300", 16), ("logistic127_n20_N333", 33), ("logistic129_n20_N259", 130),
+                                              ("logistic3_n5_N100", 16), ("logistic124_n9_N131", 20)])
+def test_many_mode_bias_component_either_way(lib, case_name, chains):
+    """The bias component of the gradient, sum_i R[i][m]: carried by pass 2 as a constant-1 row of its last feature tile when that tile has a
+    free row (d % 128 != 0: d = 3, 124, 127, 129), summed from R^T by cvg_rowsum_kernel when the tiles are full (d = 128, 256)."""
+    assert many_mode_check(make_case(case_name), chains, n_opt=3) < 1e-5
+
+
 @pytest.mark.parametrize("path", ["tc", "generic", "stream"])
 def test_full_gradient_over_a_row_range_that_starts_anywhere(lib, path):
     """What rank r of a row-sharded job computes: the sum over rows [row0, row1) only, row0 odd / not a multiple of 4 or 32 (the
