@@ -242,6 +242,8 @@ int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops);
  *   "mode_finder_split"  logistic *cv mode finder: 1 = one CTA per mode always; 2, 4, 8 = a thread-block cluster of that many CTAs per
  *                      mode, each summing its part of every minibatch, partial sums exchanged through distributed shared memory
  *                      (default: the largest of these that fits modes x CTAs on the device and leaves every CTA >= 16 rows)
+ *   "sample_out"       sgm_sample: 1 = stage the chain as float32 and widen it on the host even when the caller's array is page-locked
+ *                      (default: a page-locked array is written by the GPU directly, as doubles)
  *   "nn_update"        softmax net: 1 = register-staged update of every tensor (default: streamed through shared memory)
  *   "nn_stage1"        softmax net: 1 = register-staged forward GEMM operands (default: TMA-fed)
  * The library never reads environment variables on the dispatch path. */

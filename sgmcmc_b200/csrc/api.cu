@@ -174,6 +174,7 @@ struct sgm_handle {
     int opt_gather = 0;            // short-row kernel: 1 cp.async, 2 TMA bulk copy per row, 3 mixed, 4 TMA tile::gather4
     int opt_fullgrad = 0;          // logistic full-data gradient: 1 tensor-core contractions, 2 SIMT row-chunk x mode grid
     int opt_small_kernel = 0;      // Gaussian families: 1 = rows from global memory even when the dataset fits in shared memory
+    int opt_sample_out = 0;        // sgm_sample: 1 = staged float32 copy + host widening even into a page-locked caller array
     int opt_mode_finder_split = 0; // logistic mode finder: 1 = always one CTA per mode; 2, 4, 8 = a cluster of that many CTAs per mode (default: by occupancy)
     int opt_sharded_finder = 0;    // 1: mode finder sharded by data rows (each rank draws its part of every minibatch from its own rows, the
                                    // P-vector is all-reduced every SGD step); needs sgm_comm_init + SGM_FLAG_SHARED_MODE
@@ -270,6 +271,25 @@ __global__ void chain_transpose_kernel(const float* __restrict__ store, int64_t 
         if (f < P && it < iters) out[((size_t)blockIdx.z * P + f) * iters + it] = (OutT)tile[threadIdx.x][r];
     }
     (void)cn;
+}
+
+// sgm_sample into a PAGE-LOCKED caller array: block [cnt][C][P] float -> out[(c * P + f) * n_iters + it0 + i] as doubles, written by the
+// GPU straight into host memory (coalesced 256-byte runs along the iterations): no staging copy, no host thread touches the chain
+__global__ void chain_block_to_host_kernel(const float* __restrict__ store, int64_t cnt, int C, int P, int c0, int64_t n_iters, int64_t it0,
+                                           double* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int c = c0 + blockIdx.z;
+    if (threadIdx.y == 0) SGM_EMU_NOTE("sample:direct_to_host");
+    const int64_t i0 = (int64_t)blockIdx.x * 32; const int f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t i = i0 + r; const int f = f0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < cnt && f < P) ? store[((size_t)i * C + c) * P + f] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int f = f0 + r; const int64_t i = i0 + threadIdx.x;
+        if (f < P && i < cnt) out[((size_t)c * P + f) * n_iters + it0 + i] = (double)tile[threadIdx.x][r];
+    }
 }
 
 __global__ void state_to_double_kernel(const float* __restrict__ src, int C, int Pst, int P, const int* __restrict__ flat_of, double* __restrict__ out) {
@@ -1700,6 +1720,15 @@ extern "C" int sgm_sample(sgm_handle* h, int64_t n_iters, int32_t check_every, d
     if (check_every > 0) while (check_every % blk) --blk;     // checks fall on block boundaries
     if (int rc = pipe_setup(h, blk)) return rc;
     sgm_handle::Pipe& p = h->pipe;
+    // A page-locked caller array (sgm_host_alloc, cudaHostAlloc, cudaHostRegister) is written by the GPU directly, as doubles, block by
+    // block on the copy stream: no staging buffer and no host-side widening.  A pageable array (what R allocates) takes the staged path:
+    // float32 over PCIe into page-locked staging, widened into the caller's array by host threads.
+    double* out_dev = nullptr;
+    if (h->opt_sample_out != 1) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) out_dev = static_cast<double*>(pa.devicePointer);
+        else cudaGetLastError();
+    }
     Timer tm(h);
     const int64_t n_blocks = cdiv(n_iters, blk);
     int status = SGM_OK;
@@ -1712,7 +1741,7 @@ extern "C" int sgm_sample(sgm_handle* h, int64_t n_iters, int32_t check_every, d
             for (int c = 0; c < h->C; ++c) if (std::isnan(p.h_lp[b][c])) return fail(SGM_EDIVERGED, "Chain diverged, try decreasing stepsize");
             if (h->progress) h->progress(h->progress_user, 2, it0 + cnt, p.h_lp[b], h->C);
         }
-        widen_block(p.h_T[b], out, h->C, h->P, cnt, n_iters, it0, h->world);
+        if (!out_dev) widen_block(p.h_T[b], out, h->C, h->P, cnt, n_iters, it0, h->world);
         return SGM_OK;
     };
     for (int64_t k = 0; k < n_blocks && status == SGM_OK; ++k) {
@@ -1739,12 +1768,14 @@ extern "C" int sgm_sample(sgm_handle* h, int64_t n_iters, int32_t check_every, d
             for (int c0 = 0; c0 < h->C; c0 += 65535) {
                 const int cn = std::min(65535, h->C - c0);
                 grid.z = (unsigned)cn;
-                SGM_LAUNCH(chain_transpose_kernel<float>, grid, block, 0, p.copy, (const float*)p.d_store[b], cnt, h->C, h->P, c0, cn, p.d_T[b] + (size_t)c0 * h->P * cnt);
+                if (out_dev) SGM_LAUNCH(chain_block_to_host_kernel, grid, block, 0, p.copy, (const float*)p.d_store[b], cnt, h->C, h->P, c0, n_iters, it0, out_dev);
+                else SGM_LAUNCH(chain_transpose_kernel<float>, grid, block, 0, p.copy, (const float*)p.d_store[b], cnt, h->C, h->P, c0, cn, p.d_T[b] + (size_t)c0 * h->P * cnt);
             }
             CU(cudaGetLastError());
+            h->last_launches += (h->C + 65534) / 65535;
         }
         CU(cudaEventRecord(p.transposed[b], p.copy));
-        CU(cudaMemcpyAsync(p.h_T[b], p.d_T[b], (size_t)cnt * per_iter, cudaMemcpyDeviceToHost, p.copy));
+        if (!out_dev) CU(cudaMemcpyAsync(p.h_T[b], p.d_T[b], (size_t)cnt * per_iter, cudaMemcpyDeviceToHost, p.copy));
         CU(cudaMemcpyAsync(p.h_flag[b], h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, p.copy));
         if (check) CU(cudaMemcpyAsync(p.h_lp[b], p.d_lp[b], (size_t)h->C * sizeof(double), cudaMemcpyDeviceToHost, p.copy));
         CU(cudaEventRecord(p.copied[b], p.copy));
@@ -2068,7 +2099,7 @@ extern "C" int sgm_set_option(sgm_handle* h, const char* key, int32_t value) {
     const Opt opts[] = {{"logistic_kernel", &h->opt_logistic_kernel, 1}, {"gather", &h->opt_gather, 4}, {"fullgrad", &h->opt_fullgrad, 2},
                         {"fullgrad_row0", &h->opt_row0, INT32_MAX}, {"fullgrad_row1", &h->opt_row1, INT32_MAX},
                         {"sharded_mode_finder", &h->opt_sharded_finder, 1}, {"small_kernel", &h->opt_small_kernel, 2},
-                        {"mode_finder_split", &h->opt_mode_finder_split, OS_MAX_SPLIT}};
+                        {"mode_finder_split", &h->opt_mode_finder_split, OS_MAX_SPLIT}, {"sample_out", &h->opt_sample_out, 1}};
     for (const Opt& o : opts)
         if (!strcmp(key, o.key)) {
             if (value < 0 || value > o.max) return fail(SGM_EINVAL, "option %s: value %d outside [0, %d]", key, value, o.max);

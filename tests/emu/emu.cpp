@@ -601,8 +601,28 @@ cudaError_t cudaFree(void* p) {
     g_allocs.erase(it);
     return cudaSuccess;
 }
-cudaError_t cudaHostAllocImpl(void** p, size_t bytes, unsigned) { EMU_STICKY(); *p = aligned_alloc(64, (bytes + 63) & ~(size_t)63); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+// page-locked host allocations are remembered: cudaPointerGetAttributes tells them from pageable memory
+static std::map<const unsigned char*, size_t> g_pinned;
+cudaError_t cudaHostAllocImpl(void** p, size_t bytes, unsigned) {
+    EMU_STICKY();
+    const size_t sz = (bytes + 63) & ~(size_t)63;
+    *p = aligned_alloc(64, sz ? sz : 64);
+    if (*p) g_pinned[(const unsigned char*)*p] = sz;
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFreeHost(void* p) { g_pinned.erase((const unsigned char*)p); free(p); return cudaSuccess; }
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+    EMU_STICKY();
+    a->device = 0; a->devicePointer = nullptr; a->hostPointer = nullptr; a->type = cudaMemoryTypeUnregistered;
+    auto it = g_pinned.upper_bound((const unsigned char*)p);
+    if (it != g_pinned.begin()) {
+        --it;
+        if ((const unsigned char*)p < it->first + it->second) { a->type = cudaMemoryTypeHost; a->devicePointer = const_cast<void*>(p); a->hostPointer = const_cast<void*>(p); return cudaSuccess; }
+    }
+    const unsigned char* base = nullptr;
+    if (find_alloc(p, &base)) { a->type = cudaMemoryTypeDevice; a->devicePointer = const_cast<void*>(p); }
+    return cudaSuccess;
+}
 
 static cudaError_t checked_copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind k) {
     EMU_STICKY();

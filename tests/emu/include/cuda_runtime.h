@@ -184,6 +184,9 @@ cudaError_t cudaFree(void* p);
 cudaError_t cudaHostAllocImpl(void** p, size_t bytes, unsigned flags);
 template <class T> static inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned flags) { return cudaHostAllocImpl((void**)p, bytes, flags); }
 cudaError_t cudaFreeHost(void* p);
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t s = nullptr);
 cudaError_t cudaMemset(void* dst, int v, size_t bytes);

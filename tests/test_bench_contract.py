@@ -81,6 +81,7 @@ def test_bench_prints_one_contract_line(monkeypatch, main):
     assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
     assert line["gpu_launches"] >= 2 and "errors" not in line, line.get("errors")
     assert line["e2e"]["last_draw_finite"] is True
+    assert "error" not in line["e2e"]["page_locked_output"] and line["e2e"]["page_locked_output"]["last_draw_finite"] is True, line["e2e"]["page_locked_output"]
     assert set(line["other_workloads"]) == {"c1", "c2", "c4"} - {main}
     assert all("error" not in v for v in line["other_workloads"].values()), line["other_workloads"]
     if main == "c3":

@@ -105,6 +105,13 @@ def test_saved_state_resumes_the_run(case_name, algo, cv, shared):
     T.test_saved_state_resumes_the_run_bit_for_bit(None, case_name, algo, cv, shared)
 
 
+@pytest.mark.parametrize("case_name,algo,cv,n_iters,n_chains", [("logistic54", "sgld", True, 230, 3), ("gauss2d", "sghmc", False, 233, 340), ("softmaxnet_small", "sgnht", False, 120, 2)])
+def test_sampling_into_a_page_locked_array(emulated_library, case_name, algo, cv, n_iters, n_chains):
+    before = ran(emulated_library, "sample:direct_to_host")
+    T.test_sampling_into_a_page_locked_array_equals_the_staged_copy(None, case_name, algo, cv, n_iters, n_chains)
+    assert ran(emulated_library, "sample:direct_to_host") > before, "the page-locked array was not written by the device directly"
+
+
 def test_mode_finder_cadence(capsys):
     T.test_mode_finder_reports_and_checks_every_100_iterations(None, capsys)
 

@@ -528,3 +528,28 @@ def test_saved_state_resumes_the_run_bit_for_bit(lib, case_name, algo, cv, share
         S.loadState(other, blob)
     with pytest.raises(SgmcmcError):
         S.loadState(b, blob[:40])
+
+
+@pytest.mark.parametrize("case_name,algo,cv,n_iters,n_chains", [("logistic54", "sgld", True, 230, 3), ("gauss2d", "sghmc", False, 233, 340), ("softmaxnet_small", "sgnht", False, 120, 2)])
+def test_sampling_into_a_page_locked_array_equals_the_staged_copy(lib, case_name, algo, cv, n_iters, n_chains):
+    """sgm_sample writes a page-locked caller array from the GPU directly (doubles, no staging, no host widening); a pageable array --
+    what R hands over -- goes through float32 staging and host threads.  Same chain either way, and "sample_out" = 1 pins the staged way."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib, api as A
+    from sgmcmc_b200 import validation as V
+    L = _lib.load()
+    case = make_case(case_name)
+    outs = []
+    for kind in ("pageable", "pinned", "pinned_but_staged"):
+        dev = device_setup(case, algo, cv, n_chains=n_chains, seed=5, n_iters_opt=20)
+        if kind == "pinned_but_staged":
+            V.setOption(dev, "sample_out", 1)
+        S.initSess(dev, verbose=False)
+        count = n_chains * dev.P * n_iters
+        buf = np.empty(count, dtype=np.float64) if kind == "pageable" else A._pinned_doubles(count)
+        buf[:] = np.nan
+        _lib.check(L.sgm_sample(dev.handle, n_iters, 100, A._dptr(buf)))
+        outs.append(np.array(buf))
+        del dev
+    assert np.isfinite(outs[0]).all()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
