@@ -29,6 +29,18 @@ runSGMCMC = function( sgmcmc, paramsRaw, options ) {
 # sess$run( sgmcmc$estLogPost, fresh minibatch ) of the reference (R/update.R:198-199), one value per chain
 estLogPost = function( sgmcmc, sess ) .Call( C_sgm_est_logpost, sess, sgmcmc$nChains )
 
+# The whole sampler state as a raw vector (parameters, momenta, thermostats, the control-variate mode and its gradient, seed and
+# position in the random streams): saveRDS( saveState( sgmcmc, sess ), file ) ... loadState( sgmcmc, readRDS( file ) ) on an object
+# made by the same *Setup call takes the place of initSess -- no second mode search -- and the run continues bit for bit.
+# (The reference leaves persistence to the user of the step-by-step API, who can keep getParams() output only: NEWS.md:19.)
+saveState = function( sgmcmc, sess ) {
+    .Call( C_sgm_save_state, sess )
+}
+loadState = function( sgmcmc, blob ) {
+    .Call( C_sgm_load_state, sgmcmc$handle, blob )
+    sgmcmc$handle
+}
+
 # logLik( current params, testset ) per chain, on the device: replaces the TensorFlow tensors a user of the reference builds from
 # sgld$params to monitor a test-set log loss (vignettes/nn.Rmd:113-123, logisticRegression.Rmd:89-115)
 heldoutLogLik = function( sgmcmc, sess, testset ) {

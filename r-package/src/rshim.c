@@ -177,6 +177,22 @@ SEXP C_sgm_est_logpost(SEXP ptr, SEXP n_chains) {
     return out;
 }
 
+/* The whole device state as a raw vector / restored from one (sgm_save_state, sgm_load_state): what saveRDS can persist between R
+ * sessions.  The reference leaves this to the user of the step-by-step API, who can save getParams() only (NEWS.md:19). */
+SEXP C_sgm_save_state(SEXP ptr) {
+    sgm_handle* h = handle_of(ptr);
+    size_t need = 0;
+    check(sgm_save_state(h, NULL, 0, &need));
+    SEXP out = PROTECT(Rf_allocVector(RAWSXP, (R_xlen_t)need));
+    check(sgm_save_state(h, RAW(out), need, &need));
+    UNPROTECT(1);
+    return out;
+}
+SEXP C_sgm_load_state(SEXP ptr, SEXP blob) {
+    check(sgm_load_state(handle_of(ptr), RAW(blob), (size_t)XLENGTH(blob)));
+    return R_NilValue;
+}
+
 SEXP C_sgm_info(SEXP ptr) {
     sgm_handle* h = handle_of(ptr);
     SEXP out = PROTECT(Rf_allocVector(REALSXP, 3));
@@ -192,6 +208,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_sgm_reserve_chain", (DL_FUNC)&C_sgm_reserve_chain, 2}, {"C_sgm_reset_chain", (DL_FUNC)&C_sgm_reset_chain, 1},
     {"C_sgm_get_params", (DL_FUNC)&C_sgm_get_params, 2}, {"C_sgm_copy_chain", (DL_FUNC)&C_sgm_copy_chain, 2},
     {"C_sgm_est_logpost", (DL_FUNC)&C_sgm_est_logpost, 2}, {"C_sgm_info", (DL_FUNC)&C_sgm_info, 1},
+    {"C_sgm_save_state", (DL_FUNC)&C_sgm_save_state, 1}, {"C_sgm_load_state", (DL_FUNC)&C_sgm_load_state, 2},
     {NULL, NULL, 0}};
 
 void R_init_sgmcmc(DllInfo* dll) {

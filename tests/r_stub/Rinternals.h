@@ -9,7 +9,7 @@
 
 typedef ptrdiff_t R_xlen_t;
 typedef enum { FALSE = 0, TRUE = 1 } Rboolean;
-enum { NILSXP = 0, INTSXP = 13, REALSXP = 14, STRSXP = 16, VECSXP = 19, EXTPTRSXP = 22, CHARSXP = 9, SYMSXP = 1 };
+enum { NILSXP = 0, INTSXP = 13, REALSXP = 14, STRSXP = 16, VECSXP = 19, EXTPTRSXP = 22, RAWSXP = 24, CHARSXP = 9, SYMSXP = 1 };
 
 typedef struct SEXPREC {
     int type;
@@ -39,6 +39,7 @@ void R_ClearExternalPtr(SEXP s);
 void R_RegisterCFinalizerEx(SEXP s, void (*fun)(SEXP), Rboolean onexit);
 
 #define REAL(x) ((double*)(x)->data)
+#define RAW(x) ((unsigned char*)(x)->data)
 #define INTEGER(x) ((int*)(x)->data)
 #define XLENGTH(x) ((x)->length)
 #define LENGTH(x) ((int)(x)->length)

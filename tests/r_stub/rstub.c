@@ -12,7 +12,7 @@ const R_CallMethodDef* rstub_registered = NULL;
 static SEXP ext_ptrs[64];
 static int n_ext = 0;
 
-static size_t elem_size(int type) { return type == REALSXP ? sizeof(double) : type == INTSXP ? sizeof(int) : sizeof(SEXP); }
+static size_t elem_size(int type) { return type == REALSXP ? sizeof(double) : type == INTSXP ? sizeof(int) : type == RAWSXP ? 1 : sizeof(SEXP); }
 
 SEXP Rf_allocVector(int type, R_xlen_t n) {
     SEXP s = (SEXP)calloc(1, sizeof(SEXPREC));

@@ -23,6 +23,8 @@ SEXP C_sgm_get_params(SEXP, SEXP);
 SEXP C_sgm_copy_chain(SEXP, SEXP);
 SEXP C_sgm_est_logpost(SEXP, SEXP);
 SEXP C_sgm_info(SEXP);
+SEXP C_sgm_save_state(SEXP);
+SEXP C_sgm_load_state(SEXP, SEXP);
 void R_init_sgmcmc(DllInfo*);
 
 static SEXP num(double v) { SEXP s = Rf_allocVector(REALSXP, 1); REAL(s)[0] = v; return s; }
@@ -39,7 +41,7 @@ int main(int argc, char** argv) {
     int n_reg = 0;
     for (const R_CallMethodDef* m = rstub_registered; m && m->name; ++m) ++n_reg;
     printf("registered %d .Call routines\n", n_reg);
-    if (argc < 2 || strcmp(argv[1], "run") != 0) return n_reg == 12 ? 0 : 1;
+    if (argc < 2 || strcmp(argv[1], "run") != 0) return n_reg == 14 ? 0 : 1;
 
     const int N = 2000, d = 6, chains = 3;
     SEXP X = Rf_allocMatrix(REALSXP, N, d), y = Rf_allocVector(REALSXP, N);
@@ -104,6 +106,16 @@ int main(int argc, char** argv) {
         printf("\nheldout");
         for (int c = 0; c < chains; ++c) printf(" %.17g", REAL(ho)[c]);
         printf("\n");
+        /* saveState / loadState: a third sampler restored from h2's blob continues h2's run exactly */
+        SEXP blob = C_sgm_save_state(h2);
+        for (int k = 0; k < 3; ++k) C_sgm_step(h2);
+        SEXP h3 = C_sgm_create(spec, dataset, params, step, alpha, a);
+        C_sgm_load_state(h3, blob);
+        for (int k = 0; k < 3; ++k) C_sgm_step(h3);
+        SEXP ta = C_sgm_get_params(h2, num(chains)), tb = C_sgm_get_params(h3, num(chains));
+        int same = XLENGTH(ta) == XLENGTH(tb);
+        for (R_xlen_t i = 0; same && i < XLENGTH(ta); ++i) same = REAL(ta)[i] == REAL(tb)[i];
+        printf("state_blob_bytes %ld\nresume_equal %d\n", (long)XLENGTH(blob), same);
     }
     rstub_run_finalizers();   /* what R's garbage collector does with the external pointer */
     return 0;

@@ -1,7 +1,7 @@
 """The `.Call` shim of the R package (r-package/src/rshim.c) on top of a stand-in R C API (tests/r_stub/): R itself is absent
 from the build image, so this is as far as the R-side binding can be exercised here.
 
-  * CPU: the shim compiles against the stub headers, links against libsgmcmc_b200.so and registers its 12 .Call routines;
+  * CPU: the shim compiles against the stub headers, links against libsgmcmc_b200.so and registers its 14 .Call routines;
   * GPU: the driver makes the calls the R files make (create / init / step / run / get_params / copy_chain / est_logpost) and
     must return bit-identical doubles to the same calls through the Python mirror (same library, same seed).
 """
@@ -35,7 +35,7 @@ def test_shim_compiles_links_and_registers(tmp_path):
     exe = _build(tmp_path)
     out = subprocess.run([exe, "check"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "registered 12 .Call routines" in out.stdout
+    assert "registered 14 .Call routines" in out.stdout
 
 
 def _hash01(i, j):
@@ -90,6 +90,9 @@ def _shim_vs_mirror(exe):
     np.testing.assert_array_equal(np.array(lines["sampled_state"], dtype=np.float64), last)
     ho = S.heldoutLogLik(sg2, None, {"X": X[:300], "y": y[:300]})
     np.testing.assert_array_equal(np.array(lines["heldout"], dtype=np.float64), ho)
+    # saveState / loadState through the shim: the restored sampler continued the run bit for bit; the blob is the mirror's size
+    assert lines["resume_equal"] == ["1"]
+    assert int(lines["state_blob_bytes"][0]) == len(S.saveState(sg2, None))
 
 
 @pytest.mark.gpu
