@@ -16,8 +16,8 @@ constexpr int NN_MAXO = 16;     // output width limit
 
 // optional phase timing (debug, ChainArgs::prof): thread 0 of every CTA adds clock64() deltas per stage
 __device__ unsigned long long* nn_prof = nullptr;
-__device__ int nn_stream_updates = 1;   // 0: register-staged update of every tensor (SGM_NN_UPDATE=regs)
-__device__ int nn_s5_tmem = 0;          // 1: S5 with the X tile on the tensor-memory side (SGM_NN_S5=tmem; NOT YET RUN ON A GPU)
+__device__ int nn_stream_updates = 1;   // 0: register-staged update of every tensor (sgm_set_option "nn_update" = 1)
+__device__ int nn_s5_tmem = 0;          // 1: S5 with the X tile on the tensor-memory side (sgm_set_option "nn_stage5" = 1 in builds with -DNN_ENABLE_S5_TMEM; NOT YET RUN ON A GPU)
 __device__ long long nn_t_prev[1024];
 #define NN_TICK(slot)                                                                                   \
     if (nn_prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(nn_prof + (slot), (unsigned long long)(t_ - nn_t_prev[blockIdx.x & 1023])); nn_t_prev[blockIdx.x & 1023] = t_; }

@@ -585,7 +585,7 @@ __device__ void nn_stage5_tc(const NNDims& dm, const NNSmem& sm, const float* __
 #ifdef NN_ENABLE_S5_TMEM
 // ---------------------------------------------------------------------------------------------------------
 // S5, TMA-fed, X on the tensor-memory side -- written at the end of round 1, NOT YET RUN ON A GPU.  Compiled only with
-// -DNN_ENABLE_S5_TMEM (SGM_BUILD_DEFS=-DNN_ENABLE_S5_TMEM python __graft_entry__.py --force), then selected by SGM_NN_S5=tmem.
+// -DNN_ENABLE_S5_TMEM (SGM_BUILD_DEFS=-DNN_ENABLE_S5_TMEM python __graft_entry__.py --force), then selected by sgm_set_option "nn_stage5" = 1.
 //   GB^T[j][n] = sum_r X[row_r][j] dZ1[r][n]      M = 128 inputs j per tile, N = Npad hidden units, K = Kp = round8(nb) rows
 //   * B operand: dZ1^T staged ONCE per call, K-major no-swizzle core matrices, hi / lo (same layout the register-staged S5 uses for A);
 //   * A operand: the X tile arrives as four gather4 blocks [Kp rows][32 inputs] (the SW128 tiles S1 loads); block q belongs to the
