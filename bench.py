@@ -108,9 +108,10 @@ PIN_ONE_CTA_FINDER = False   # set when the cluster mode finder failed its probe
 
 def make_sampler(w, rank, world, chains_local, seed=13, shared=True, synth=None, n_iters_opt=None):
     sg = _make_sampler(w, rank, world, chains_local, seed, shared, synth, n_iters_opt)
-    if PIN_ONE_CTA_FINDER and w["cv"] and w["family"] == "logistic":
+    if PIN_ONE_CTA_FINDER and w["family"] == "logistic":
         from sgmcmc_b200 import validation as V
         V.setOption(sg, "mode_finder_split", 1)
+        V.setOption(sg, "chain_split", 1)
     return sg
 
 
@@ -434,11 +435,15 @@ def quick_workload(name, steps=5, iters=None):
 
 
 def mode_finder_ab(w, n_iters_opt=None):
-    """The *cv mode finder (getMode: nItersOpt sequential SGD steps) with one CTA per mode and with the default dispatch (a thread-block
-    cluster per mode when there are few modes), each on a fresh sampler: device time of initSess, which is the finder plus one full-data
-    gradient and a log-posterior check every 100 steps -- an upper bound on the time per SGD step."""
+    """Few chains / one shared mode: the thread-block cluster per chain (csrc/logistic_split.cuh, the default dispatch there) against one
+    CTA per chain, each on a fresh sampler.
+    mode finder (getMode: nItersOpt sequential SGD steps): device time of initSess, which is the finder plus one full-data gradient and
+    a log-posterior check every 100 steps -- an upper bound on the time per SGD step;
+    one chain (the reference's own way of running): device time of 2000 sgmcmcSteps of ONE chain in one launch."""
     import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib
     from sgmcmc_b200 import validation as V
+    lib = _lib.load()
     n_opt = n_iters_opt or min(int(w.get("n_iters_opt", 2000)), 2000)
     out = {"n_iters_opt": n_opt, "modes": 1}
     for name, split in (("one_cta_per_mode", 1), ("default_dispatch", 0)):
@@ -449,6 +454,18 @@ def mode_finder_ab(w, n_iters_opt=None):
         ms, launches = V.lastTiming(sg)
         out[name] = {"init_ms": ms, "us_per_sgd_step_upper_bound": ms * 1e3 / n_opt, "launches": launches}
         del sg
+    iters = 2000
+    one = {"iters": iters, "chains": 1}
+    for name, split in (("one_cta_per_chain", 1), ("default_dispatch", 0)):
+        sg = make_sampler(w, 0, 1, 1, n_iters_opt=min(n_opt, 200))
+        V.setOption(sg, "chain_split", split)
+        S.initSess(sg, verbose=False)
+        _lib.check(lib.sgm_run(sg.handle, iters, 0))
+        _lib.check(lib.sgm_run(sg.handle, iters, 0))
+        ms, _ = V.lastTiming(sg)
+        one[name] = {"ms": ms, "us_per_step": ms * 1e3 / iters, "chain_iterations_per_s": iters / (ms * 1e-3)}
+        del sg
+    out["one_chain"] = one
     return out
 
 
@@ -529,7 +546,7 @@ def run_ours(args, w):
     # ---- the cluster mode finder, tried in a child process before this process depends on it (rank 0 asks, every rank follows)
     global PIN_ONE_CTA_FINDER
     finder_probe = None
-    if w["cv"] and w["family"] == "logistic":
+    if w["family"] == "logistic":
         if rank == 0:
             finder_probe = probe_cluster_finder()
         bad = 0.0 if (finder_probe is None or finder_probe.get("ok")) else 1.0

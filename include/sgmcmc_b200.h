@@ -242,6 +242,10 @@ int sgm_last_fullgrad_flops(const sgm_handle* h, double* flops);
  *   "mode_finder_split"  logistic *cv mode finder: 1 = one CTA per mode always; 2, 4, 8 = a thread-block cluster of that many CTAs per
  *                      mode, each summing its part of every minibatch, partial sums exchanged through distributed shared memory
  *                      (default: the largest of these that fits modes x CTAs on the device and leaves every CTA >= 16 rows)
+ *   "chain_split"      logistic sampling kernels, same values: with few chains each chain gets a thread-block cluster (its CTAs split every
+ *                      minibatch, exchange partial sums through distributed shared memory and keep identical replicas of the state), which
+ *                      shortens the latency of a step -- the regime of the reference's own usage, ONE chain; with many chains every SM has
+ *                      a chain of its own and the one-CTA kernels run
  *   "sample_out"       sgm_sample: 1 = stage the chain as float32 and widen it on the host even when the caller's array is page-locked
  *                      (default: a page-locked array is written by the GPU directly, as doubles)
  *   "nn_update"        softmax net: 1 = register-staged update of every tensor (default: streamed through shared memory)

@@ -26,7 +26,7 @@
 #include "small_models.cuh"
 #include "logistic.cuh"
 #include "logistic_staged.cuh"
-#include "logistic_opt_split.cuh"
+#include "logistic_split.cuh"
 #include "logistic_fullgrad_stream.cuh"
 #include "logistic_cv_gemm.cuh"
 #include "softmax_net.cuh"
@@ -176,6 +176,7 @@ struct sgm_handle {
     int opt_small_kernel = 0;      // Gaussian families: 1 = rows from global memory even when the dataset fits in shared memory
     int opt_sample_out = 0;        // sgm_sample: 1 = staged float32 copy + host widening even into a page-locked caller array
     int opt_mode_finder_split = 0; // logistic mode finder: 1 = always one CTA per mode; 2, 4, 8 = a cluster of that many CTAs per mode (default: by occupancy)
+    int opt_chain_split = 0;       // logistic sampling kernels: 1 = always one CTA per chain; 2, 4, 8 = a cluster of that many CTAs per chain (default: by occupancy)
     int opt_sharded_finder = 0;    // 1: mode finder sharded by data rows (each rank draws its part of every minibatch from its own rows, the
                                    // P-vector is all-reduced every SGD step); needs sgm_comm_init + SGM_FLAG_SHARED_MODE
     int opt_row0 = 0, opt_row1 = 0;   // row1 > 0: the full-data pass sums rows [row0, row1) only -- what rank r of a row-sharded job does,
@@ -584,60 +585,71 @@ static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
     return fail(SGM_EINVAL, "logistic staged kernel: minibatch %d too large", a.n);
 }
 
-// ---- mode finder with fewer modes than SMs: a thread-block cluster per mode (logistic_opt_split.cuh)
-// CTAs per mode: the largest power of two <= 8 that still leaves every CTA OS_MIN_ROWS minibatch rows and fits modes x CTAs on the
-// device; 1 = keep one CTA per mode (many modes: the SMs are busy anyway)
-constexpr int OS_MIN_ROWS = 16;
-static int opt_split_of(int opt, int modes, int n, int sms) {
+// ---- fewer chains (or modes) than SMs: a thread-block cluster per chain (logistic_split.cuh)
+// CTAs per chain: the largest power of two <= 8 that still leaves every CTA LSP_MIN_ROWS minibatch rows and fits chains x CTAs on the
+// device; 1 = keep one CTA per chain (many chains: the SMs are busy anyway).  opt: 0 = that rule, 1 = never, 2 / 4 / 8 = that cluster size
+constexpr int LSP_MIN_ROWS = 16;
+static int split_of(int opt, int chains, int n, int sms) {
     if (opt == 1) return 1;
     int split = 1;
-    for (int s = 2; s <= OS_MAX_SPLIT; s *= 2)
-        if ((int64_t)modes * s <= sms && n / s >= OS_MIN_ROWS) split = s;
+    for (int s = 2; s <= LSP_MAX_SPLIT; s *= 2)
+        if ((int64_t)chains * s <= sms && n / s >= LSP_MIN_ROWS) split = s;
     if (opt >= 2) { split = 1; while (split * 2 <= opt) split *= 2; if (n / split < 1) split = 1; }
     return split;
 }
+// the cluster size a launch of this handle would use (1: one CTA per chain).  Same rule for the mode finder ("mode_finder_split") and
+// the sampling kernels ("chain_split"): a few chains are the reference's way of running -- they get a cluster each --, many chains
+// are this library's, and then every SM already has a chain of its own
+static int logistic_split_for(const sgm_handle* h, const ChainArgs& a, int sms) {
+    if (a.X != h->X) return 1;
+    const bool finder = a.algo == ALGO_OPT && !a.cv && a.L == 1;
+    const int opt = finder ? h->opt_mode_finder_split : h->opt_chain_split;
+    if (opt == 0 && (h->opt_logistic_kernel || h->opt_gather)) return 1;   // a pinned one-CTA kernel path is what the caller wants to run
+    return split_of(opt, a.C, a.n, sms);
+}
 
 // *launched = false: the device cannot co-schedule such a cluster (or refuses the launch configuration) -- the caller falls back to
-// one CTA per mode; nothing has run in that case
+// one CTA per chain; nothing has run in that case
 template <int G, int V>
-static int launch_logistic_opt_split_gv(sgm_handle* h, const ChainArgs& a, int split, int sms, bool* launched) {
+static int launch_logistic_split_gv(sgm_handle* h, const ChainArgs& a, int split, int sms, bool* launched) {
     *launched = false;
-    const size_t smem = os_smem_bytes(G, V, h->ld);
-    if (smem > 227 * 1024) return SGM_OK;
-    CU(cudaFuncSetAttribute((logistic_opt_split_kernel<G, V>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (; split > 1; split /= 2) {   // the largest cluster the device can hold
+        const size_t smem = lsp_smem_bytes(G, V, h->ld, a.n, split);
+        if (smem > 227 * 1024) continue;
+        CU(cudaFuncSetAttribute((logistic_split_kernel<G, V>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int fit = 0;
         cudaError_t qe;
-        SGM_CLUSTER_OCCUPANCY(qe, &fit, (logistic_opt_split_kernel<G, V>), (unsigned)split, OS_THREADS, smem, split);
+        SGM_CLUSTER_OCCUPANCY(qe, &fit, (logistic_split_kernel<G, V>), (unsigned)split, LSP_THREADS, smem, split);
         if (qe == cudaSuccess && fit > 0) break;
         cudaGetLastError();
     }
     if (split <= 1) return SGM_OK;
+    const size_t smem = lsp_smem_bytes(G, V, h->ld, a.n, split);
     int clusters = sms / split;
     if (clusters > a.C) clusters = a.C;
     if (clusters < 1) clusters = 1;
     cudaError_t err;
-    SGM_LAUNCH_CLUSTER(err, (logistic_opt_split_kernel<G, V>), (unsigned)(clusters * split), OS_THREADS, smem, h->stream, split, a);
+    SGM_LAUNCH_CLUSTER(err, (logistic_split_kernel<G, V>), (unsigned)(clusters * split), LSP_THREADS, smem, h->stream, split, a);
     if (err != cudaSuccess) { cudaGetLastError(); return SGM_OK; }   // a refused configuration is not a fault: nothing was launched
     CU(cudaGetLastError());
     *launched = true;
     return SGM_OK;
 }
 
-static int launch_logistic_opt_split(sgm_handle* h, const ChainArgs& a, int split, int sms, bool* launched) {
-    LOGI_DISPATCH(launch_logistic_opt_split_gv, h, a, split, sms, launched);
+static int launch_logistic_split(sgm_handle* h, const ChainArgs& a, int split, int sms, bool* launched) {
+    LOGI_DISPATCH(launch_logistic_split_gv, h, a, split, sms, launched);
 }
 
 static int launch_logistic(sgm_handle* h, const ChainArgs& a) {
     const_cast<ChainArgs&>(a).rhat_cached = h->rhat_cached ? 1 : 0;
-    if (a.algo == ALGO_OPT && !a.cv && a.L == 1 && a.X == h->X) {   // (a dataset sharded over ranks too: rows resolve through the shard table, the bulk copies then cross NVLink)
+    {
         int sms = 0;
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        const int split = logistic_split_for(h, a, sms);
         LogiShape s;
-        const int split = opt_split_of(h->opt_mode_finder_split, a.C, a.n, sms);
-        if (split > 1 && logi_shape(h->ld, &s) && os_smem_bytes(s.G, s.V, h->ld) <= 227 * 1024) {
+        if (split > 1 && logi_shape(h->ld, &s)) {
             bool launched = false;
-            const int rc = launch_logistic_opt_split(h, a, split, sms, &launched);
+            const int rc = launch_logistic_split(h, a, split, sms, &launched);
             if (rc != SGM_OK || launched) return rc;
         }
     }
@@ -2099,7 +2111,7 @@ extern "C" int sgm_set_option(sgm_handle* h, const char* key, int32_t value) {
     const Opt opts[] = {{"logistic_kernel", &h->opt_logistic_kernel, 1}, {"gather", &h->opt_gather, 4}, {"fullgrad", &h->opt_fullgrad, 2},
                         {"fullgrad_row0", &h->opt_row0, INT32_MAX}, {"fullgrad_row1", &h->opt_row1, INT32_MAX},
                         {"sharded_mode_finder", &h->opt_sharded_finder, 1}, {"small_kernel", &h->opt_small_kernel, 2},
-                        {"mode_finder_split", &h->opt_mode_finder_split, OS_MAX_SPLIT}, {"sample_out", &h->opt_sample_out, 1}};
+                        {"mode_finder_split", &h->opt_mode_finder_split, LSP_MAX_SPLIT}, {"chain_split", &h->opt_chain_split, LSP_MAX_SPLIT}, {"sample_out", &h->opt_sample_out, 1}};
     for (const Opt& o : opts)
         if (!strcmp(key, o.key)) {
             if (value < 0 || value > o.max) return fail(SGM_EINVAL, "option %s: value %d outside [0, %d]", key, value, o.max);
@@ -2213,12 +2225,12 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
             };
             chain(h->C, "sampling");
             if (h->cv) {
-                const int split = opt_split_of(h->opt_mode_finder_split, M, h->n, sms);
-                if (split > 1 && os_smem_bytes(s.G, s.V, h->ld) <= 227 * 1024) {
+                const int split = split_of(h->opt_mode_finder_split, M, h->n, sms);
+                if (split > 1 && lsp_smem_bytes(s.G, s.V, h->ld, h->n, split) <= 227 * 1024) {
                     char note[160];
                     int clusters = sms / split; if (clusters > M) clusters = M;
                     snprintf(note, sizeof note, "mode finder; thread-block clusters of %d CTAs per mode (DSMEM reduction), %d minibatch rows per CTA; <G, V> = <%d, %d>", split, (h->n + split - 1) / split, s.G, s.V);
-                    po.launch("logistic_opt_split_kernel", (int64_t)clusters * split, 1, 1, OS_THREADS, os_smem_bytes(s.G, s.V, h->ld), 0, note);
+                    po.launch("logistic_split_kernel", (int64_t)clusters * split, 1, 1, LSP_THREADS, lsp_smem_bytes(s.G, s.V, h->ld, h->n, split), 0, note);
                 } else {
                     chain(M, "mode finder");
                 }

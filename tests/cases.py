@@ -96,18 +96,19 @@ def make_case(name: str, seed: int = 13):
 
 ALGOS = ("sgld", "sghmc", "sgnht")
 
-# GPU sessions (tests/conftest.py): set when tools/probe_cluster_finder.py did not exit 0 in its own process.  Every logistic *cv
-# sampler made here then keeps the mode finder on one CTA per mode (the kernels with a record on hardware), so a fault of the
-# never-run cluster finder costs its own test and nothing else.  A test that pins "mode_finder_split" itself overrides this.
+# GPU sessions (tests/conftest.py): set when tools/probe_cluster_finder.py did not exit 0 in its own process.  Every logistic
+# sampler made here then keeps to one CTA per chain and per mode (the kernels with a record on hardware), so a fault of the
+# never-run cluster kernel costs its own tests and nothing else.  A test that pins "mode_finder_split" / "chain_split" itself overrides this.
 CLUSTER_PROBE_ERROR = None
 
 
 def device_setup(case, algo, cv, n_chains=1, seed=7, L=3, n_iters_opt=25, pin_finder=True, **kw):
     import sgmcmc_b200 as S
-    if cv and pin_finder and CLUSTER_PROBE_ERROR and "bias" in case["params"]:
+    if pin_finder and CLUSTER_PROBE_ERROR and "bias" in case["params"]:
         from sgmcmc_b200 import validation as V
         dev = device_setup(case, algo, cv, n_chains=n_chains, seed=seed, L=L, n_iters_opt=n_iters_opt, pin_finder=False, **kw)
         V.setOption(dev, "mode_finder_split", 1)
+        V.setOption(dev, "chain_split", 1)
         return dev
     fn = {("sgld", False): S.sgldSetup, ("sghmc", False): S.sghmcSetup, ("sgnht", False): S.sgnhtSetup,
           ("sgld", True): S.sgldcvSetup, ("sghmc", True): S.sghmccvSetup, ("sgnht", True): S.sgnhtcvSetup}[(algo, cv)]

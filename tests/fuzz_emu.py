@@ -54,7 +54,7 @@ def random_case(rs):
         d = int(rs.choice([1, 2, 3, 4, 5, 7, 123, 124, 127, 128]))
         n = int(rs.choice([1, 2, 3, 31, 32, 33, 255, 256, 257]))
     name = f"logistic{d}_n{n}_N{_rows(rs, n)}"
-    if fam == "finder":      # the cluster mode finder at a pinned cluster size (csrc/logistic_opt_split.cuh)
+    if fam == "finder":      # mode finder and sampling steps on a thread-block cluster of a pinned size (csrc/logistic_split.cuh)
         return "finder", name, str(int(rs.choice([2, 4, 8]))), str(rs.choice(["cv", "cv_shared"]))
     if fam == "stream":
         return "stream", name, algo, mode
@@ -66,7 +66,9 @@ def run_case(kind, name, algo, mode):
     if kind == "steps":
         T._deterministic_steps(name, algo, mode != "plain", shared=(mode == "cv_shared"), mass_scaled=True)
     elif kind == "finder":
-        T._deterministic_steps(name, "sgld", True, shared=(mode == "cv_shared"), mass_scaled=True, options={"mode_finder_split": int(algo)}, n_opt=9)
+        k = int(algo)
+        T._deterministic_steps(name, ("sgld", "sghmc", "sgnht")[k % 3], True, shared=(mode == "cv_shared"), mass_scaled=True,
+                               options={"mode_finder_split": k, "chain_split": k}, n_opt=9)
     elif kind == "cvg":
         from tests import test_fullgrad_tc_gpu as F
         from tests.cases import make_case

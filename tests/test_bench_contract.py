@@ -87,6 +87,7 @@ def test_bench_prints_one_contract_line(monkeypatch, main):
     if main == "c3":
         f = line["mode_finder"]
         assert "error" not in f and f["one_cta_per_mode"]["init_ms"] > 0 and f["default_dispatch"]["us_per_sgd_step_upper_bound"] > 0, f
+        assert f["one_chain"]["one_cta_per_chain"]["us_per_step"] > 0 and f["one_chain"]["default_dispatch"]["chain_iterations_per_s"] > 0, f
         assert line["cv_full_gradient"]["GBps"] > 0
         m = line["cv_full_gradient_modes"]
         assert m["TFLOPs"] > 0 and m["peak"] == 800.0 and abs(m["frac_of_3xtf32_ceiling"] - 3 * m["frac"]) < 1e-12

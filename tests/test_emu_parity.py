@@ -207,7 +207,7 @@ def test_logistic_kernel_variants(emulated_library, case_name, option, value, pa
     del rs
 
 
-# ---- mode finder on a thread-block cluster per mode (logistic_opt_split.cuh): cluster launch, barrier.cluster, DSMEM loads ------
+# ---- mode finder on a thread-block cluster per mode (logistic_split.cuh): cluster launch, barrier.cluster, DSMEM loads ------
 @pytest.mark.parametrize("case_name,split,shared", [("logistic54", 8, True), ("logistic54_n500", 4, True), ("logistic5", 2, True), ("logistic130", 8, True),
                                                     ("logistic54_n101", 4, True), ("logistic1024_n1024_N3000", 8, True), ("logistic54", 2, False), ("logistic130", 4, False),
                                                     ("logistic54_n20", 8, True)])
@@ -215,6 +215,24 @@ def test_mode_finder_cluster_split(emulated_library, case_name, split, shared):
     before = ran(emulated_library, "logistic_opt_split")
     T._deterministic_steps(case_name, "sgld", True, shared=shared, options={"mode_finder_split": split}, n_opt=6 if "1024" in case_name else 25)
     assert ran(emulated_library, "logistic_opt_split") > before, "the cluster mode finder did not run"
+
+
+@pytest.mark.parametrize("case_name", ["logistic54", "logistic54_n101", "logistic5", "logistic130", "logistic1024_n1024_N3000"])
+@pytest.mark.parametrize("algo", T.ALGOS)
+@pytest.mark.parametrize("mode", ["plain", "cv", "cv_shared"])
+def test_cluster_per_chain_steps_match_oracle(emulated_library, case_name, algo, mode):
+    before = ran(emulated_library, "logistic_split:sample")
+    for split in ((8,) if "1024" in case_name or case_name == "logistic130" else (2, 8)):
+        if case_name.startswith("logistic1024") and algo == "sghmc":
+            pytest.skip("the long-row shape is covered with two samplers")
+        T.test_cluster_per_chain_steps_match_oracle(None, case_name, algo, mode, split)
+    assert ran(emulated_library, "logistic_split:sample") > before, "the cluster kernel did not run the sampling steps"
+
+
+@pytest.mark.parametrize("case_name,algo,cv,shared", [("logistic54", "sgld", True, True), ("logistic54", "sghmc", False, False), ("logistic130", "sgnht", True, False),
+                                                      ("logistic5", "sgld", False, False)])
+def test_cluster_per_chain_walks_the_same_chain(case_name, algo, cv, shared):
+    T.test_cluster_per_chain_walks_the_same_chain(None, case_name, algo, cv, shared)
 
 
 def test_mode_finder_cluster_split_equals_one_cta_per_mode(emulated_library):

@@ -47,7 +47,7 @@ def test_unaligned_tma_coordinate_is_an_illegal_instruction(emu):
 
 
 def test_cluster_protocol_errors_are_reported(emu):
-    """Thread-block clusters (the cluster mode finder, csrc/logistic_opt_split.cuh): the CTAs of a cluster run one after another as far
+    """Thread-block clusters (the cluster mode finder, csrc/logistic_split.cuh): the CTAs of a cluster run one after another as far
     as each can get, so a CTA that should have waited for its peers reads their shared memory before it is written, and a CTA that
     leaves without the final barrier is gone when a peer comes to read it."""
     v = C.c_float()

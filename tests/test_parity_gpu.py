@@ -57,7 +57,7 @@ def tensor_close_ref(ours_flat, ref32, ref64, what, lenient):
         o += sz
 
 
-ONE_CTA_FINDER = {"mode_finder_split": 1}
+ONE_CTA_FINDER = {"mode_finder_split": 1, "chain_split": 1}   # one CTA per mode and per chain: the kernels with a record on hardware
 
 
 def draw_inputs(rs, chain: OS.Chain, N, n, C):
@@ -70,8 +70,8 @@ def draw_inputs(rs, chain: OS.Chain, N, n, C):
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("cv", [False, True])
 def test_deterministic_steps_match_oracle(lib, case_name, algo, cv):
-    # the mode finder pinned to one CTA per mode: these tests run first on a GPU (tests/conftest.py) and keep to the kernels with the
-    # longest record on hardware; the cluster finder (the default for few modes) has its own test further down the order
+    # pinned to one CTA per mode and per chain: these tests run first on a GPU (tests/conftest.py) and keep to the kernels with the
+    # longest record on hardware; the cluster kernel (the default for few chains / modes) has its own tests further down the order
     _deterministic_steps(case_name, algo, cv, shared=False, options=ONE_CTA_FINDER if case_name.startswith("logistic") else None)
 
 
@@ -88,13 +88,57 @@ def test_deterministic_steps_shared_mode(lib, case_name, algo):
                                                     ("logistic54", 1, True), ("logistic1024_n1024_N3000", 1, False),   # 1 = one CTA per mode (the default once modes x 2 > SMs)
                                                     ("logistic54", 0, True), ("logistic130", 0, False), ("logistic54_n500", 0, True)])   # 0 = the default dispatch
 def test_mode_finder_cluster_split(lib, case_name, split, shared):
-    """The *cv mode finder with a thread-block cluster per mode (logistic_opt_split.cuh: the minibatch split over the cluster's CTAs,
+    """The *cv mode finder with a thread-block cluster per mode (logistic_split.cuh: the minibatch split over the cluster's CTAs,
     partial sums exchanged through distributed shared memory, rows prefetched across steps) finds the oracle's mode -- cluster sizes
     2 / 4 / 8, one shared mode and one mode per chain, minibatches that do not divide by the cluster size, long rows."""
     from tests import cases
     if lib is not None and cases.CLUSTER_PROBE_ERROR and split != 1:
-        pytest.fail("the cluster mode finder failed its probe in a separate process (tests/conftest.py): " + cases.CLUSTER_PROBE_ERROR)
+        pytest.fail("the cluster kernel failed its probe in a separate process (tests/conftest.py): " + cases.CLUSTER_PROBE_ERROR)
     _deterministic_steps(case_name, "sgld", True, shared=shared, options={"mode_finder_split": split})
+
+
+@pytest.mark.parametrize("case_name", ["logistic54", "logistic54_n101", "logistic5", "logistic130", "logistic1024_n1024_N3000"])
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("mode", ["plain", "cv", "cv_shared"])
+@pytest.mark.parametrize("split", [0, 2, 8])
+def test_cluster_per_chain_steps_match_oracle(lib, case_name, algo, mode, split):
+    """Few chains: every chain on a thread-block cluster (logistic_split.cuh) -- all three samplers, plain / control variates / shared
+    mode, the Gauss-Seidel passes of SGLD and SGHMC, thermostats, the validation gradient -- against the oracle; split = 0 is the default
+    dispatch (3 chains on a B200: clusters of 8)."""
+    from tests import cases
+    if lib is not None and cases.CLUSTER_PROBE_ERROR:
+        pytest.fail("the cluster kernel failed its probe in a separate process (tests/conftest.py): " + cases.CLUSTER_PROBE_ERROR)
+    if case_name.startswith("logistic1024") and (split == 2 or algo == "sghmc"):
+        pytest.skip("the long-row shape is covered at one cluster size and two samplers")
+    _deterministic_steps(case_name, algo, mode != "plain", shared=(mode == "cv_shared"), options={"chain_split": split, "mode_finder_split": split},
+                         n_opt=5 if "1024" in case_name else None)
+
+
+@pytest.mark.parametrize("case_name,algo,cv,shared", [("logistic54", "sgld", True, True), ("logistic54", "sghmc", False, False), ("logistic130", "sgnht", True, False),
+                                                      ("logistic5", "sgld", False, False)])
+def test_cluster_per_chain_walks_the_same_chain(lib, case_name, algo, cv, shared):
+    """Device RNG: a chain on a cluster draws the rows and the noise the one-CTA kernels draw (streams keyed by seed, chain, iteration,
+    element), so 120 stored iterations agree up to the order of the float32 sums."""
+    import sgmcmc_b200 as S
+    from sgmcmc_b200 import _lib
+    from sgmcmc_b200 import validation as V
+    from tests import cases
+    if lib is not None and cases.CLUSTER_PROBE_ERROR:
+        pytest.fail("the cluster kernel failed its probe in a separate process (tests/conftest.py): " + cases.CLUSTER_PROBE_ERROR)
+    case = make_case(case_name)
+    outs = []
+    for split in (1, 4):
+        dev = device_setup(case, algo, cv, n_chains=2, seed=21, n_iters_opt=40, sharedMode=shared, pin_finder=False)
+        V.setOption(dev, "chain_split", split)
+        V.setOption(dev, "mode_finder_split", 1)
+        S.initSess(dev, verbose=False)
+        _lib.check(_lib.load().sgm_run(dev.handle, 120, 1))
+        ch = S.getChains(dev)
+        outs.append((np.concatenate([np.asarray(v).reshape(2, 120, -1) for v in ch.values()], axis=2),) + tuple(V.getState(dev)))
+    scale = np.abs(outs[0][0]).max()
+    assert np.abs(outs[0][0] - outs[1][0]).max() <= 1e-5 * scale
+    assert np.abs(outs[0][1] - outs[1][1]).max() <= 1e-5 * max(np.abs(outs[0][1]).max(), 1e-30) + 1e-7
+    assert np.abs(outs[0][2] - outs[1][2]).max() <= 1e-5
 
 
 def _summand_mass(case, theta, rows):

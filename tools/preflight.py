@@ -49,13 +49,16 @@ S.initSess(dev, verbose=False); S.sgmcmcStep(dev, None); assert np.isfinite(V.fl
     ("logistic short-row kernel: TMA bulk copy per row", """
 case = make_case('logistic54'); dev = device_setup(case, 'sgld', True, n_chains=3, n_iters_opt=5); V.setOption(dev, 'gather', 2)
 S.initSess(dev, verbose=False); S.sgmcmcStep(dev, None); assert np.isfinite(V.flatParams(dev)).all()"""),
-    ("logistic short-row kernel: TMA tile::gather4 (default), R = 1 and R = 2", "T._deterministic_steps('logistic54', 'sgld', True, True); T._deterministic_steps('logistic54_n500', 'sghmc', True, False)"),
-    ("logistic long rows d = 1024: chain kernel <32, 9> + streaming full gradient", "T._deterministic_steps('logistic1024_n1024_N3000', 'sgnht', True, True)"),
+    ("logistic short-row kernel: TMA tile::gather4 (default), R = 1 and R = 2", "T._deterministic_steps('logistic54', 'sgld', True, True, options=T.ONE_CTA_FINDER); T._deterministic_steps('logistic54_n500', 'sghmc', True, False, options=T.ONE_CTA_FINDER)"),
+    ("logistic long rows d = 1024: chain kernel <32, 9> + streaming full gradient", "T._deterministic_steps('logistic1024_n1024_N3000', 'sgnht', True, True, options=T.ONE_CTA_FINDER)"),
     ("mode finder on a thread-block cluster per mode (cluster launch, barrier.cluster, DSMEM loads): short and long rows",
      "T._deterministic_steps('logistic54', 'sgld', True, True, options={'mode_finder_split': 8}); T._deterministic_steps('logistic54_n101', 'sgld', True, False, options={'mode_finder_split': 4}); "
      "T._deterministic_steps('logistic1024_n1024_N3000', 'sgld', True, True, options={'mode_finder_split': 8})"),
+    ("sampling on a thread-block cluster per chain (few chains): all samplers, Gauss-Seidel passes, control variates, long rows",
+     "T._deterministic_steps('logistic54', 'sgld', True, True, options={'chain_split': 8}); T._deterministic_steps('logistic54_n101', 'sghmc', False, False, options={'chain_split': 4}); "
+     "T._deterministic_steps('logistic130', 'sgnht', True, False, options={'chain_split': 2}); T._deterministic_steps('logistic1024_n1024_N3000', 'sgnht', True, True, options={'chain_split': 8}, n_opt=5)"),
     ("mode finder with one CTA per mode (short-row and generic kernels in their SGD mode)",
-     "T._deterministic_steps('logistic54', 'sgld', True, True, options={'mode_finder_split': 1}); T._deterministic_steps('logistic1024_n1024_N3000', 'sgld', True, True, options={'mode_finder_split': 1})"),
+     "T._deterministic_steps('logistic54', 'sgld', True, True, options={'mode_finder_split': 1, 'chain_split': 1}); T._deterministic_steps('logistic1024_n1024_N3000', 'sgld', True, True, options={'mode_finder_split': 1, 'chain_split': 1})"),
     ("full gradient over row ranges that start anywhere: streaming kernel", "F.test_full_gradient_over_a_row_range_that_starts_anywhere(None, 'stream')"),
     ("full gradient over row ranges that start anywhere: SIMT grid", "F.test_full_gradient_over_a_row_range_that_starts_anywhere(None, 'generic')"),
     ("tcgen05 many-mode full gradient (cvg_kernel)", "F.test_many_mode_full_gradient_matches_oracle(None, 'logistic54', 20)"),

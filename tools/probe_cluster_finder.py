@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""Probe of the cluster mode finder (csrc/logistic_opt_split.cuh) in a process of its own.
+"""Probe of the cluster kernel (csrc/logistic_split.cuh: a thread-block cluster per chain / per mode) in a process of its own.
 
-    python tools/probe_cluster_finder.py        # exit 0: the cluster finder runs on this device and agrees with the one-CTA finder
+    python tools/probe_cluster_finder.py        # exit 0: the cluster kernel runs on this device and agrees with the one-CTA kernels
 
-The cluster finder is the default dispatch for few modes and has never executed on hardware (round 2 had no GPU access).  A device
-fault is sticky for the process that raised it, so bench.py and the GPU test session ask THIS script first, in a child process:
-when it does not exit 0 they pin "mode_finder_split" = 1 (the kernels measured in round 1) for everything else they do, and only the
-cluster finder's own test / bench entry reports the failure.  Prints one JSON line.
+The cluster kernel is the default dispatch for few chains and few modes and has never executed on hardware (round 2 had no GPU access).
+A device fault is sticky for the process that raised it, so bench.py and the GPU test session ask THIS script first, in a child
+process: when it does not exit 0 they pin "mode_finder_split" = 1 and "chain_split" = 1 (the kernels measured in round 1) for
+everything else they do, and only the cluster kernel's own tests / bench entries report the failure.  Prints one JSON line.
 """
 from __future__ import annotations
 
@@ -43,6 +43,28 @@ def main() -> int:
             out["ok"] = False
             out["why"] = f"{case_name}: cluster of {split} CTAs differs from one CTA per mode by {err:.2e}"
             break
+    # sampling on a cluster per chain: 60 stored iterations of every sampler against the one-CTA kernels (same rows, same noise streams)
+    from sgmcmc_b200 import _lib
+    for case_name, algo, cv, split in (("logistic54", "sgld", True, 8), ("logistic54_n101", "sghmc", False, 4), ("logistic130", "sgnht", True, 2),
+                                       ("logistic1024_n1024_N3000", "sgld", True, 8)):
+        if not out["ok"]:
+            break
+        case = make_case(case_name)
+        chains = []
+        for s in (1, split):
+            dev = device_setup(case, algo, cv, n_chains=2, n_iters_opt=20, pin_finder=False)
+            V.setOption(dev, "mode_finder_split", 1)
+            V.setOption(dev, "chain_split", s)
+            S.initSess(dev, verbose=False)
+            _lib.check(_lib.load().sgm_run(dev.handle, 60, 1))
+            ch = S.getChains(dev)
+            chains.append(np.concatenate([np.asarray(v).reshape(2, 60, -1) for v in ch.values()], axis=2))
+            del dev
+        err = float(np.abs(chains[0] - chains[1]).max() / max(np.abs(chains[0]).max(), 1e-30))
+        out["checks"].append({"case": case_name, "sampler": algo, "split": split, "rel_err_vs_one_cta": err})
+        if not (err <= 1e-5):
+            out["ok"] = False
+            out["why"] = f"{case_name} {algo}: chains on clusters of {split} CTAs differ from one CTA per chain by {err:.2e}"
     print(json.dumps(out))
     return 0 if out["ok"] else 1
 
