@@ -158,6 +158,7 @@ struct sgm_handle {
     CUtensorMap tmap;           // 2-D map of the dataset (box = one row) for TMA tile::gather4
     bool tmap_ok = false;
     float* Rt = nullptr; size_t rt_cap = 0;         // residuals of one row block, transposed [M][rt_pitch]
+    int* d_flat_of = nullptr; double* d_state_out = nullptr; size_t d_state_out_cap = 0;   // getParams / getState: index table, conversion buffer
     // dataset row-sharded over the ranks, peers mapped through CUDA IPC (sgm_attach_peer_shards): every rank holds N rows, the
     // chains sample from world x N rows and gather remote rows over NVLink; the control-variate pass sums the local shard
     int n_shards = 1;
@@ -1256,7 +1257,7 @@ extern "C" void sgm_destroy(sgm_handle* h) {
     for (int r = 0; r < 16; ++r) if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     if (h->d_shard_ptr) cudaFree((void*)h->d_shard_ptr);
     void* ptrs[] = {h->X, h->theta, h->mom, h->thermo, h->theta_hat, h->g_hat, h->scratch, h->gsum, h->dout,
-                    h->d_flag, h->d_idx, h->d_noise, h->store, h->Rt, h->hat_all, h->gsum_all};
+                    h->d_flag, h->d_idx, h->d_noise, h->store, h->Rt, h->d_flat_of, h->d_state_out, h->hat_all, h->gsum_all};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int b = 0; b < 2; ++b) {
         if (h->pipe.d_store[b]) cudaFree(h->pipe.d_store[b]);
@@ -1891,15 +1892,19 @@ extern "C" int sgm_load_state(sgm_handle* h, const void* buf, size_t bytes) {
 // ------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------
+// getParams is called once per iteration by users of the step-by-step API (vignettes/nn.Rmd:99-102): the index table and the
+// conversion buffer live with the handle (a cudaMalloc / cudaFree pair per call costs more than the sgmcmcStep it follows)
 static int state_out(sgm_handle* h, const float* src, int count, double* out) {
     if (int rc = set_device(h)) return rc;
-    std::vector<int> flat_of, tensor_of;
-    host_tables(h, flat_of, tensor_of);
-    DevBuf<int> flat_buf; DevBuf<double> out_buf;
-    CU(flat_buf.alloc(h->Pst));
-    CU(out_buf.alloc((size_t)count * h->P));
-    int* d_flat = flat_buf.p; double* d_out = out_buf.p;
-    CU(cudaMemcpyAsync(d_flat, flat_of.data(), h->Pst * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (!h->d_flat_of) {
+        std::vector<int> flat_of, tensor_of;
+        host_tables(h, flat_of, tensor_of);
+        CU(cudaMalloc(&h->d_flat_of, (size_t)h->Pst * sizeof(int)));
+        CU(cudaMemcpyAsync(h->d_flat_of, flat_of.data(), h->Pst * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));   // the host vector goes out of scope
+    }
+    if (int rc = ensure_buf((void**)&h->d_state_out, &h->d_state_out_cap, (size_t)count * h->P * sizeof(double))) return rc;
+    int* d_flat = h->d_flat_of; double* d_out = h->d_state_out;
     SGM_LAUNCH(state_to_double_kernel, (unsigned)cdiv((int64_t)count * h->Pst, 256), 256, 0, h->stream, src, count, h->Pst, h->P, d_flat, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, d_out, (size_t)count * h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
