@@ -159,6 +159,7 @@ struct sgm_handle {
     bool tmap_ok = false;
     float* Rt = nullptr; size_t rt_cap = 0;         // residuals of one row block, transposed [M][rt_pitch]
     int* d_flat_of = nullptr; double* d_state_out = nullptr; size_t d_state_out_cap = 0;   // getParams / getState: index table, conversion buffer
+    int lsp_asked = 0, lsp_n = 0, lsp_granted = 0;  // cluster kernel: the cluster size asked for last, at which minibatch size, and what the device granted
     // dataset row-sharded over the ranks, peers mapped through CUDA IPC (sgm_attach_peer_shards): every rank holds N rows, the
     // chains sample from world x N rows and gather remote rows over NVLink; the control-variate pass sums the local shard
     int n_shards = 1;
@@ -614,18 +615,25 @@ static int logistic_split_for(const sgm_handle* h, const ChainArgs& a, int sms) 
 template <int G, int V>
 static int launch_logistic_split_gv(sgm_handle* h, const ChainArgs& a, int split, int sms, bool* launched) {
     *launched = false;
-    for (; split > 1; split /= 2) {   // the largest cluster the device can hold
-        const size_t smem = lsp_smem_bytes(G, V, h->ld, a.n, split);
-        if (smem > 227 * 1024) continue;
-        CU(cudaFuncSetAttribute((logistic_split_kernel<G, V>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int fit = 0;
-        cudaError_t qe;
-        SGM_CLUSTER_OCCUPANCY(qe, &fit, (logistic_split_kernel<G, V>), (unsigned)split, LSP_THREADS, smem, split);
-        if (qe == cudaSuccess && fit > 0) break;
-        cudaGetLastError();
+    if (h->lsp_asked == split && h->lsp_n == a.n) {
+        split = h->lsp_granted;        // asked before (a step-by-step loop launches once per sgmcmcStep: no occupancy query per step)
+    } else {
+        const int asked = split;
+        for (; split > 1; split /= 2) {   // the largest cluster the device can hold
+            const size_t smem = lsp_smem_bytes(G, V, h->ld, a.n, split);
+            if (smem > 227 * 1024) continue;
+            CU(cudaFuncSetAttribute((logistic_split_kernel<G, V>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int fit = 0;
+            cudaError_t qe;
+            SGM_CLUSTER_OCCUPANCY(qe, &fit, (logistic_split_kernel<G, V>), (unsigned)split, LSP_THREADS, smem, split);
+            if (qe == cudaSuccess && fit > 0) break;
+            cudaGetLastError();
+        }
+        h->lsp_asked = asked; h->lsp_n = a.n; h->lsp_granted = split;
     }
     if (split <= 1) return SGM_OK;
     const size_t smem = lsp_smem_bytes(G, V, h->ld, a.n, split);
+    CU(cudaFuncSetAttribute((logistic_split_kernel<G, V>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per function, not per handle: set for THIS launch
     int clusters = sms / split;
     if (clusters > a.C) clusters = a.C;
     if (clusters < 1) clusters = 1;
