@@ -293,8 +293,9 @@ with backend.emulated() as lib:
     for case in ("logistic54", "logistic54_n101", "logistic130"):
         for algo in T.ALGOS:
             T._deterministic_steps(case, algo, True, shared=(algo == "sgld"))
-    for case, split, shared in (("logistic54", 4, False), ("logistic54_n101", 8, True), ("logistic130", 2, False)):   # clusters: CTA order, lockstep / depth-first
-        T._deterministic_steps(case, "sgld", True, shared=shared, options={{"mode_finder_split": split}})
+    for case, algo, split, shared in (("logistic54", "sgld", 4, False), ("logistic54_n101", "sghmc", 8, True), ("logistic130", "sgnht", 2, False)):   # clusters: CTA order, lockstep / depth-first
+        T._deterministic_steps(case, algo, True, shared=shared, options={{"mode_finder_split": split, "chain_split": split}})
+    T.test_cluster_per_chain_walks_the_same_chain(None, "logistic54", "sghmc", False, False)
     T._deterministic_steps("mixture", "sghmc", True, shared=False)
     T._deterministic_steps("softmaxnet_small", "sghmc", True, shared=False)
     T._deterministic_steps("softmaxnet", "sghmc", False, shared=False)
