@@ -166,7 +166,9 @@ int sgm_run(sgm_handle* h, int64_t n_iters, int store);
  * hides behind the kernel.  Every check_every iterations (100 in the reference; 0 = never) checkDivergence (R/update.R:197-207) runs on
  * the device: estLogPost on a fresh minibatch; NaN returns SGM_EDIVERGED ("Chain diverged, try decreasing stepsize"), otherwise the
  * values go to the progress callback (sgm_set_progress, phase = 2, one estimate per chain).  The device-resident chain of sgm_run
- * (sgm_chain_length / sgm_copy_chain) is not touched. */
+ * (sgm_chain_length / sgm_copy_chain) is not touched.
+ * When `out` is page-locked host memory (sgm_host_alloc, cudaHostAlloc, cudaHostRegister) the GPU writes the doubles into it directly,
+ * block by block, and no host thread touches the chain; a pageable array (what R allocates) takes the staged path described above. */
 int sgm_sample(sgm_handle* h, int64_t n_iters, int32_t check_every, double* out);
 
 /* ---- reading results ------------------------------------------------------------- */
