@@ -33,6 +33,8 @@ def test_random_shapes(seed):
     ("steps", "logistic8_n100_N300", "sghmc", "plain"),
     # degenerate minibatch (n = N - 1 = 8): the control-variate gradient cancels to ~1e-3; tolerance scaled by the summand mass
     ("steps", "logistic18_n8_N9", "sghmc", "cv"),
+    # n = 2 of N = 491 rows: N / n = 245 multiplies the float32 rounding of the net's O(1) pre-activations; judged against the summand mass
+    ("steps", "softmaxnet_76_12_8_n2_N491", "sgld", "plain"),
 ])
 def test_shapes_the_fuzz_found(kind, name, algo, mode):
     fuzz_emu.run_case(kind, name, algo, mode)
