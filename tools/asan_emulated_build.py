@@ -25,6 +25,10 @@ from tests import test_parity_gpu as T, test_fullgrad_tc_gpu as F, test_launch_p
 with backend.emulated("asan") as lib:
     T._deterministic_steps("logistic54", "sgld", True, shared=True, options={"mode_finder_split": 8})
     T._deterministic_steps("logistic54_n101", "sghmc", True, shared=False)
+    T._deterministic_steps("logistic54_n101", "sghmc", True, shared=False, options={"chain_split": 4, "mode_finder_split": 4})
+    T._deterministic_steps("logistic130", "sgnht", True, shared=True, options={"chain_split": 8})
+    T.test_cluster_per_chain_walks_the_same_chain(None, "logistic54", "sgld", True, True)
+    T.test_sampling_into_a_page_locked_array_equals_the_staged_copy(None, "logistic54", "sgld", True, 230, 3)
     T._deterministic_steps("logistic1024_n1024_N3000", "sgnht", True, shared=True, options={"mode_finder_split": 8}, n_opt=4)
     T._deterministic_steps("mixture", "sgnht", True, shared=False)
     T._deterministic_steps("gauss3d_fullcov", "sghmc", True, shared=False)
