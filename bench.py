@@ -434,6 +434,9 @@ def quick_workload(name, steps=5, iters=None):
 
 
 
+ONE_CHAIN_ITERS = 2000   # sgmcmcSteps of the one-chain latency measurement (one launch)
+
+
 def mode_finder_ab(w, n_iters_opt=None):
     """Few chains / one shared mode: the thread-block cluster per chain (csrc/logistic_split.cuh, the default dispatch there) against one
     CTA per chain, each on a fresh sampler.
@@ -454,7 +457,7 @@ def mode_finder_ab(w, n_iters_opt=None):
         ms, launches = V.lastTiming(sg)
         out[name] = {"init_ms": ms, "us_per_sgd_step_upper_bound": ms * 1e3 / n_opt, "launches": launches}
         del sg
-    iters = 2000
+    iters = ONE_CHAIN_ITERS
     one = {"iters": iters, "chains": 1}
     for name, split in (("one_cta_per_chain", 1), ("default_dispatch", 0)):
         sg = make_sampler(w, 0, 1, 1, n_iters_opt=min(n_opt, 200))

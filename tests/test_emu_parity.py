@@ -65,7 +65,7 @@ def test_small_models_shared_memory_dataset(emulated_library, case_name, algo):
 
 
 @pytest.mark.parametrize("case_name,algo,cv,n_iters,n_chains", [("gauss2d", "sgld", False, 250, 3), ("mixture", "sghmc", False, 137, 3), ("logistic54", "sgld", True, 230, 3),
-                                                                ("logistic130", "sgnht", True, 101, 3), ("softmaxnet_small", "sghmc", False, 120, 3),
+                                                                ("logistic130", "sgnht", True, 101, 3), ("softmaxnet_small", "sghmc", False, 101, 2),
                                                                 ("gauss2d", "sgld", False, 233, 340)])
 def test_streamed_sampling(case_name, algo, cv, n_iters, n_chains, capsys):
     T.test_streamed_sampling_equals_run_then_copy(None, case_name, algo, cv, n_iters, n_chains, capsys)
@@ -96,7 +96,7 @@ def test_last_stored_state_is_the_sampler_state(case_name, algo):
 def test_posterior_moments_match_the_oracle(case_name, algo, cv, shared):
     """Reduced-size run of tests/test_statistics_gpu.py::test_posterior_moments_match_the_oracle (device RNG vs float64 oracle chains)."""
     from tests import test_statistics_gpu as ST
-    ST.test_posterior_moments_match_the_oracle(None, case_name, algo, cv, shared, n_dev=48, n_orc=8, burn=200, keep=600)
+    ST.test_posterior_moments_match_the_oracle(None, case_name, algo, cv, shared, n_dev=32, n_orc=8, burn=200, keep=400)
 
 
 @pytest.mark.parametrize("case_name,algo,cv,shared", [("gauss2d", "sgld", False, False), ("mixture", "sghmc", True, False), ("logistic54", "sgnht", True, True),
@@ -105,7 +105,7 @@ def test_saved_state_resumes_the_run(case_name, algo, cv, shared):
     T.test_saved_state_resumes_the_run_bit_for_bit(None, case_name, algo, cv, shared)
 
 
-@pytest.mark.parametrize("case_name,algo,cv,n_iters,n_chains", [("logistic54", "sgld", True, 230, 3), ("gauss2d", "sghmc", False, 233, 340), ("softmaxnet_small", "sgnht", False, 120, 2)])
+@pytest.mark.parametrize("case_name,algo,cv,n_iters,n_chains", [("logistic54", "sgld", True, 230, 3), ("gauss2d", "sghmc", False, 133, 40), ("softmaxnet_small", "sgnht", False, 101, 2)])
 def test_sampling_into_a_page_locked_array(emulated_library, case_name, algo, cv, n_iters, n_chains):
     before = ran(emulated_library, "sample:direct_to_host")
     T.test_sampling_into_a_page_locked_array_equals_the_staged_copy(None, case_name, algo, cv, n_iters, n_chains)
@@ -217,14 +217,19 @@ def test_mode_finder_cluster_split(emulated_library, case_name, split, shared):
     assert ran(emulated_library, "logistic_opt_split") > before, "the cluster mode finder did not run"
 
 
-@pytest.mark.parametrize("case_name", ["logistic54", "logistic54_n101", "logistic5", "logistic130", "logistic1024_n1024_N3000"])
-@pytest.mark.parametrize("algo", T.ALGOS)
-@pytest.mark.parametrize("mode", ["plain", "cv", "cv_shared"])
+# every sampler x every mode on the covertype shape; the other shapes (odd minibatch, tiny rows, padded rows, long rows) with the
+# sampler and the mode rotating (the GPU suite runs the full cross: tests/test_parity_gpu.py)
+_CLUSTER_CASES = [("logistic54", a, m) for a in T.ALGOS for m in ("plain", "cv", "cv_shared")] + [
+    ("logistic54_n101", "sgld", "cv"), ("logistic54_n101", "sghmc", "cv_shared"), ("logistic54_n101", "sgnht", "plain"),
+    ("logistic5", "sgld", "cv_shared"), ("logistic5", "sghmc", "plain"), ("logistic5", "sgnht", "cv"),
+    ("logistic130", "sgld", "plain"), ("logistic130", "sghmc", "cv"), ("logistic130", "sgnht", "cv_shared"),
+    ("logistic1024_n1024_N3000", "sgld", "cv"), ("logistic1024_n1024_N3000", "sgnht", "cv_shared")]
+
+
+@pytest.mark.parametrize("case_name,algo,mode", _CLUSTER_CASES)
 def test_cluster_per_chain_steps_match_oracle(emulated_library, case_name, algo, mode):
     before = ran(emulated_library, "logistic_split:sample")
-    for split in ((8,) if "1024" in case_name or case_name == "logistic130" else (2, 8)):
-        if case_name.startswith("logistic1024") and algo == "sghmc":
-            pytest.skip("the long-row shape is covered with two samplers")
+    for split in ((2, 4, 8) if case_name == "logistic54_n101" else (8,)):
         T.test_cluster_per_chain_steps_match_oracle(None, case_name, algo, mode, split)
     assert ran(emulated_library, "logistic_split:sample") > before, "the cluster kernel did not run the sampling steps"
 
@@ -290,9 +295,8 @@ from tests.emu import backend
 from tests import test_parity_gpu as T, test_fullgrad_tc_gpu as F
 with backend.emulated() as lib:
     assert lib.emu_async_is_lazy() == {lazy}
-    for case in ("logistic54", "logistic54_n101", "logistic130"):
-        for algo in T.ALGOS:
-            T._deterministic_steps(case, algo, True, shared=(algo == "sgld"))
+    for case, algo in (("logistic54", "sgld"), ("logistic54", "sghmc"), ("logistic54_n101", "sgnht"), ("logistic130", "sghmc"), ("logistic130", "sgld")):
+        T._deterministic_steps(case, algo, True, shared=(algo == "sgld"))
     for case, algo, split, shared in (("logistic54", "sgld", 4, False), ("logistic54_n101", "sghmc", 8, True), ("logistic130", "sgnht", 2, False)):   # clusters: CTA order, lockstep / depth-first
         T._deterministic_steps(case, algo, True, shared=shared, options={{"mode_finder_split": split, "chain_split": split}})
     T.test_cluster_per_chain_walks_the_same_chain(None, "logistic54", "sghmc", False, False)

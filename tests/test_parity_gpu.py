@@ -119,7 +119,7 @@ def test_mode_finder_cluster_split(lib, case_name, split, shared):
 @pytest.mark.parametrize("case_name", ["logistic54", "logistic54_n101", "logistic5", "logistic130", "logistic1024_n1024_N3000"])
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("mode", ["plain", "cv", "cv_shared"])
-@pytest.mark.parametrize("split", [0, 2, 8])
+@pytest.mark.parametrize("split", [0, 8])
 def test_cluster_per_chain_steps_match_oracle(lib, case_name, algo, mode, split):
     """Few chains: every chain on a thread-block cluster (logistic_split.cuh) -- all three samplers, plain / control variates / shared
     mode, the Gauss-Seidel passes of SGLD and SGHMC, thermostats, the validation gradient -- against the oracle; split = 0 is the default
@@ -127,10 +127,17 @@ def test_cluster_per_chain_steps_match_oracle(lib, case_name, algo, mode, split)
     from tests import cases
     if lib is not None and cases.CLUSTER_PROBE_ERROR:
         pytest.fail("the cluster kernel failed its probe in a separate process (tests/conftest.py): " + cases.CLUSTER_PROBE_ERROR)
-    if case_name.startswith("logistic1024") and (split == 2 or algo == "sghmc"):
+    if case_name.startswith("logistic1024") and (split in (2, 4) or algo == "sghmc"):
         pytest.skip("the long-row shape is covered at one cluster size and two samplers")
     _deterministic_steps(case_name, algo, mode != "plain", shared=(mode == "cv_shared"), options={"chain_split": split, "mode_finder_split": split},
                          n_opt=5 if "1024" in case_name else None)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("split", [2, 4])
+def test_cluster_per_chain_small_clusters(lib, algo, split):
+    """Clusters of 2 and 4 CTAs on a minibatch that divides by neither (n = 101)."""
+    test_cluster_per_chain_steps_match_oracle(lib, "logistic54_n101", algo, "cv", split)
 
 
 @pytest.mark.parametrize("case_name,algo,cv,shared", [("logistic54", "sgld", True, True), ("logistic54", "sghmc", False, False), ("logistic130", "sgnht", True, False),
