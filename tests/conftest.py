@@ -52,6 +52,9 @@ _GPU_ORDER = [
     ("test_statistics_gpu.py", "test_3d_gauss"), ("test_statistics_gpu.py", "test_step_by_step"), ("test_statistics_gpu.py", "test_optional_arguments"),
     ("test_statistics_gpu.py", "test_stationary_moments"), ("test_statistics_gpu.py", "test_divergence"), ("test_parity_gpu.py", "test_call_sequences"), ("test_parity_gpu.py", ""),
     ("test_statistics_gpu.py", ""), ("test_r_shim.py", ""), ("test_multi_gpu.py", ""),
+    # first executions on hardware (round 2 had no GPU): the paths probed in a child process come last
+    ("test_parity_gpu.py", "test_sampling_into_a_page_locked_array"), ("test_parity_gpu.py", "test_mode_finder_cluster_split"),
+    ("test_parity_gpu.py", "test_cluster_per_chain"),
 ]
 
 
@@ -59,10 +62,11 @@ def _gpu_rank(item):
     if item.get_closest_marker("gpu") is None:
         return -1
     fname, name = os.path.basename(str(item.fspath)), item.name
-    for k, (f, prefix) in enumerate(_GPU_ORDER):
-        if fname == f and name.startswith(prefix):
-            return k
-    return len(_GPU_ORDER)
+    best, best_len = len(_GPU_ORDER), -1
+    for k, (f, prefix) in enumerate(_GPU_ORDER):      # the longest matching prefix decides
+        if fname == f and name.startswith(prefix) and len(prefix) > best_len:
+            best, best_len = k, len(prefix)
+    return best
 
 
 def pytest_collection_modifyitems(config, items):
