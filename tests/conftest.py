@@ -48,9 +48,10 @@ _GPU_ORDER = [
     ("test_parity_gpu.py", "test_deterministic_steps_match_oracle"), ("test_parity_gpu.py", "test_deterministic_steps_shared_mode"),
     ("test_parity_gpu.py", "test_est_logpost_matches_oracle"), ("test_parity_gpu.py", "test_device_rng_streams_match_oracle"),
     ("test_parity_gpu.py", "test_chain_storage_layout_and_shapes"), ("test_parity_gpu.py", "test_same_seed_reproduces"),
-    ("test_parity_gpu.py", "test_heldout_loglik_matches_oracle"), ("test_fullgrad_tc_gpu.py", ""), ("test_statistics_gpu.py", "test_1d_gauss"),
+    ("test_parity_gpu.py", "test_heldout_loglik_matches_oracle"), ("test_statistics_gpu.py", "test_1d_gauss"),
     ("test_statistics_gpu.py", "test_3d_gauss"), ("test_statistics_gpu.py", "test_step_by_step"), ("test_statistics_gpu.py", "test_optional_arguments"),
     ("test_statistics_gpu.py", "test_stationary_moments"), ("test_statistics_gpu.py", "test_divergence"), ("test_parity_gpu.py", "test_call_sequences"), ("test_parity_gpu.py", ""),
+    ("test_fullgrad_tc_gpu.py", ""),      # (cvg_kernel: pass 2 was rewritten in round 2 -- no longer the binary round 1 measured)
     ("test_statistics_gpu.py", ""), ("test_r_shim.py", ""), ("test_multi_gpu.py", ""),
     # first executions on hardware (round 2 had no GPU): the paths probed in a child process come last
     ("test_parity_gpu.py", "test_sampling_into_a_page_locked_array"), ("test_parity_gpu.py", "test_mode_finder_cluster_split"),
