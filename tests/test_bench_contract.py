@@ -170,13 +170,15 @@ def test_optional_leg_failure_costs_only_its_own_entry():
 
 
 def test_smoke_runs_on_the_emulated_build(monkeypatch, capsys):
-    """__graft_entry__.smoke(): the SIMT / TMA logistic step and the tcgen05 many-mode full gradient, each checked against the oracle."""
+    """__graft_entry__.smoke(): the TMA-gather logistic step, the tcgen05 softmax-net steps and the tcgen05 many-mode full gradient, each
+    checked against the oracle."""
     import __graft_entry__
     monkeypatch.setattr(__graft_entry__, "build", lambda *a, **k: None)
+    monkeypatch.setattr(__graft_entry__, "SMOKE_CHILD_PROBE", False)   # (the child process would load the product library: no GPU here)
     with backend.emulated() as lib:
         lib.emu_note_count.restype = __import__("ctypes").c_longlong
         lib.emu_note_count.argtypes = [__import__("ctypes").c_char_p]
         before = lib.emu_note_count(b"cvg:pass1"), lib.emu_note_count(b"logistic_staged:gather4")
         __graft_entry__.smoke()
         assert lib.emu_note_count(b"cvg:pass1") > before[0] and lib.emu_note_count(b"logistic_staged:gather4") > before[1]
-    assert capsys.readouterr().out.count("smoke ok") == 2
+    assert capsys.readouterr().out.count("smoke ok") == 3
