@@ -115,13 +115,14 @@ def make_sampler(w, rank, world, chains_local, seed=13, shared=True, synth=None,
     return sg
 
 
-def probe_cluster_finder(timeout_s=600):
+def probe_cluster_finder(timeout_s=600, part=None):
     """tools/probe_cluster_finder.py in a process of its own: the cluster mode finder (default dispatch for a shared mode) had never run
     on hardware when this round ended.  Returns the probe's JSON object; {"ok": False, ...} makes this run keep the finder on one CTA
     per mode, so a fault in the new kernel costs the `mode_finder` entry of the line and not the line."""
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
     try:
-        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_cluster_finder.py")], capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_cluster_finder.py")] + (["--part", part] if part else []),
+                           capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
     except subprocess.TimeoutExpired:
         return {"ok": False, "why": f"no answer within {timeout_s} s (killed)"}
     for ln in reversed(p.stdout.strip().splitlines()):
@@ -549,13 +550,20 @@ def run_ours(args, w):
     # ---- the cluster mode finder, tried in a child process before this process depends on it (rank 0 asks, every rank follows)
     global PIN_ONE_CTA_FINDER
     finder_probe = None
+    finder_probe_all_ranks_say_many_mode_bad = False
     if w["family"] == "logistic":
+        mm_probe = None
         if rank == 0:
             finder_probe = probe_cluster_finder()
+            if world > 1 and w["cv"] and not args.no_modes:      # (at N = 1 the many-mode leg runs in a child of its own anyway)
+                mm_probe = probe_cluster_finder(part="many_mode")
+                finder_probe["many_mode"] = mm_probe
         bad = 0.0 if (finder_probe is None or finder_probe.get("ok")) else 1.0
+        mm_bad = 0.0 if (mm_probe is None or mm_probe.get("ok")) else 1.0
         if world > 1:
-            bad = max_over_ranks([bad])[0]
+            bad, mm_bad = max_over_ranks([bad, mm_bad])
         PIN_ONE_CTA_FINDER = bad > 0
+        finder_probe_all_ranks_say_many_mode_bad = mm_bad > 0
 
     def barrier():
         if world > 1:
@@ -715,7 +723,10 @@ def run_ours(args, w):
     # ---- optional legs.  N = 1: each in its own process (a device fault there cannot take the main line with it)
     if w["cv"] and w["family"] == "logistic" and not args.no_modes:
         try:
-            line["cv_full_gradient_modes"] = (run_leg_in_child("modes", args) if world == 1 else many_mode_full_gradient(w, rank, world, args.modes))
+            if world > 1 and finder_probe_all_ranks_say_many_mode_bad:
+                line["cv_full_gradient_modes"] = {"error": "the many-mode full gradient failed in the probe process (mode_finder_probe): not run in process"}
+            else:
+                line["cv_full_gradient_modes"] = (run_leg_in_child("modes", args) if world == 1 else many_mode_full_gradient(w, rank, world, args.modes))
         except Exception as e:   # noqa: BLE001
             errors["cv_full_gradient_modes"] = f"{type(e).__name__}: {str(e)[:300]}"
     if finder_probe is not None:

@@ -110,7 +110,8 @@ def _bench_worker(rank, world, port, peer_shards, out):
     torch.cuda.synchronize = lambda *_: None
     __graft_entry__.build = lambda *a, **k: None
     bench.measure_tf32_peak = lambda *a, **k: (900.0, 800.0)
-    bench.probe_cluster_finder = lambda *a, **k: {"ok": rank != 0 or not peer_shards, "why": "test: rank 0 reports a failed probe"}   # both ranks must then pin
+    # rank 0 reports a failed cluster probe in the --peer-shards run (both ranks must then pin one CTA per chain); the many-mode part passes
+    bench.probe_cluster_finder = lambda *a, part=None, **k: {"ok": part == "many_mode" or rank != 0 or not peer_shards, "why": "test: rank 0 reports a failed probe"}
     rs = np.random.RandomState(13)
     N, d = (1200, 130) if peer_shards else (1500, 54)   # a sharded dataset takes the long-row kernel (rows resolved through the shard table)
     w = dict(desc="toy", algo="sgnht" if peer_shards else "sgld", cv=True, family="logistic", data={"X": rs.randn(N, d), "y": (rs.rand(N) < 0.5).astype(np.float64)},

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Probe of the cluster kernel (csrc/logistic_split.cuh: a thread-block cluster per chain / per mode) in a process of its own.
 
-    python tools/probe_cluster_finder.py        # exit 0: the cluster kernel runs on this device and agrees with the one-CTA kernels
+    python tools/probe_cluster_finder.py                    # exit 0: the cluster kernel runs on this device and agrees with the one-CTA kernels
+    python tools/probe_cluster_finder.py --part many_mode   # exit 0: the tensor-core many-mode full gradient (second pass rewritten in round 2)
 
 The cluster kernel is the default dispatch for few chains and few modes and has never executed on hardware (round 2 had no GPU access).
 A device fault is sticky for the process that raised it, so bench.py and the GPU test session ask THIS script first, in a child
@@ -18,16 +19,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def many_mode() -> int:
+    from tests import test_fullgrad_tc_gpu as F
+    from tests.cases import make_case
+    worst = max(F.many_mode_check(make_case("logistic54"), 20, n_opt=3), F.many_mode_check(make_case("logistic1024_n200_N515"), 128, n_opt=3))
+    ok = bool(worst < 1e-5)
+    print(json.dumps({"ok": ok, "part": "many_mode", "worst_scaled_err": float(worst)}))
+    return 0 if ok else 1
+
+
 def main() -> int:
     import numpy as np
     import torch
     if not torch.cuda.is_available():
         print(json.dumps({"ok": False, "why": "no CUDA device"}))
         return 2
+    if "--part" in sys.argv and sys.argv[sys.argv.index("--part") + 1] == "many_mode":
+        return many_mode()
     import sgmcmc_b200 as S
     from sgmcmc_b200 import validation as V
     from tests.cases import device_setup, make_case
-    out = {"ok": True, "checks": []}
+    out = {"ok": True, "part": "cluster", "checks": []}
     for case_name, split in (("logistic54", 8), ("logistic54_n101", 4), ("logistic130", 2), ("logistic1024_n1024_N3000", 8)):
         case = make_case(case_name)
         modes = []
