@@ -11,6 +11,7 @@ timeout 1500 python tools/preflight.py > gpurun_out/r02_preflight.log 2>&1; rc=$
 [ $rc -eq 0 ] || { echo "preflight failed (rc=$rc)"; exit 1; }
 step "1b cluster mode finder probe (its own process; bench.py and the GPU tests repeat it and fall back to one CTA per mode if it fails)"
 timeout 600 python tools/probe_cluster_finder.py > gpurun_out/r02_cluster_probe.json 2> gpurun_out/r02_cluster_probe.err; echo "probe rc=$?"; tail -c 600 gpurun_out/r02_cluster_probe.json
+timeout 600 python tools/probe_cluster_finder.py --part many_mode > gpurun_out/r02_many_mode_probe.json 2> gpurun_out/r02_many_mode_probe.err; echo "many-mode probe rc=$?"; tail -c 300 gpurun_out/r02_many_mode_probe.json
 step "2 pytest -m gpu"
 timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gpu_tests.log 2>&1; rc=$?; tail -15 gpurun_out/r02_gpu_tests.log
 [ $rc -eq 0 ] || { echo "gpu tests failed (rc=$rc)"; exit 2; }
