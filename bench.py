@@ -334,54 +334,62 @@ def cpu_proxy(w, budget_s, threads):
         s.find_mode(50)  # enough to exercise the path; the timed part is the sampling loop + the full gradient
         fg = time_full_gradient(oracle_model(w), data, w["params"])
     ips, iters, dt = time_iterations(s, budget_s)
+    cpu_proxy.last_sampler = s
     return ips, f"{sample_note}1 chain, {iters} sgmcmcSteps in {dt:.1f} s, torch CPU float32 graph replica, {threads} thread(s)", fg, data
 
 
-def cpu_chain_leg(w, budget_s):
-    """Child of run_reference: ONE chain of the reference-structured proxy on one thread; prints its rate."""
-    ips, note, fg, _ = cpu_proxy(w, budget_s, 1)
-    return {"ips": ips, "note": note, "full_gradient_s": fg}
+def cpu_chain_leg(w, budget_s, steps, warmup):
+    """Child of run_reference: ONE chain of the reference-structured proxy on one thread; W short warm-up samples, then K bounded samples
+    (one per step of the arm); prints the K rates."""
+    import torch
+    from oracle.cpu_baseline import time_iterations
+    torch.set_num_threads(1)
+    ips, note, fg, _ = cpu_proxy(w, 1.0, 1)              # builds the sampler, finds a mode, times the full gradient; first (warm-up) sample
+    s = cpu_proxy.last_sampler
+    for _ in range(max(0, warmup - 1)):
+        time_iterations(s, 1.0)
+    rates, iters_tot, dt_tot = [], 0, 0.0
+    for _ in range(steps):
+        r, iters, dt = time_iterations(s, budget_s)
+        rates.append(r); iters_tot += iters; dt_tot += dt
+    return {"rates": rates, "note": f"1 chain, {iters_tot} sgmcmcSteps in {dt_tot:.1f} s over {steps} samples, torch CPU float32 graph replica, 1 thread", "full_gradient_s": fg}
 
 
 def run_reference(args, w):
     """--impl reference: the reference's own structure on the host cores (the real R+TF stack is absent).  A chain of the reference is
     sequential and its per-op work is far too small for intra-op threads to help (torch with 8 threads: 27 iterations/s against 634 on one
     thread for c3, measured on the development host), so "all the host threads it can use" means what a user of the reference would do
-    with a many-core host: one independent chain per core (one R process each).  Each step of the arm = P single-thread chain processes
-    running concurrently for a bounded time; value = the sum of their rates, mean over the K timed steps."""
+    with a many-core host: one independent chain per core (one R process each).  P single-thread chain processes run side by side; each
+    step of the arm is one bounded sample in every process at the same time; value = the sum of their rates, mean over the K timed steps."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))        # <= 32 processes: each holds its own copy of the dataset (0.7 GB for c3)
-    budget = max(2.0, min(15.0, 100.0 / max(1, args.steps + args.warmup)))
+    budget = max(2.0, min(15.0, 100.0 / max(1, args.steps)))
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
     env.update(OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
-    cmd = [sys.executable, os.path.abspath(__file__), "--leg", "cpu_chain", "--workload", args.workload, "--gpus", "1"]
-    vals, note, failed = [], "", 0
-    for i in range(args.warmup + args.steps):
-        b = budget if i >= args.warmup else 1.0
-        children = [subprocess.Popen(cmd + ["--cpu-budget", str(b)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env, cwd=ROOT) for _ in range(procs)]
-        rates = []
-        for ch in children:
-            try:
-                out, _ = ch.communicate(timeout=b * 4 + 240)
-                r = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
-                rates.append(r["ips"]); note = r["note"]
-            except Exception:   # noqa: BLE001
-                ch.kill(); failed += 1
-        if i >= args.warmup and rates:
-            vals.append(float(np.sum(rates)))
-    if not vals:
+    cmd = [sys.executable, os.path.abspath(__file__), "--leg", "cpu_chain", "--workload", args.workload, "--gpus", "1", "--cpu-budget", str(budget),
+           "--steps", str(args.steps), "--warmup", str(args.warmup)]
+    children = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env, cwd=ROOT) for _ in range(procs)]
+    per_step, note, failed = np.zeros(args.steps), "", 0
+    for ch in children:
+        try:
+            out, _ = ch.communicate(timeout=budget * args.steps * 3 + 600)
+            r = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+            per_step += np.asarray(r["rates"], dtype=np.float64); note = r["note"]
+        except Exception:   # noqa: BLE001
+            ch.kill(); failed += 1
+    if failed == procs:
         print(json.dumps({"impl": "reference", "unavailable": "no CPU chain process produced a rate"}))
         return
-    val = float(np.mean(vals))
-    sample = f"{procs} independent single-thread chains at once, each: {note}" + (f"; {failed} process(es) failed" if failed else "")
+    val = float(np.mean(per_step))
+    sample = f"{procs - failed} independent single-thread chains at once, each: {note}" + (f"; {failed} process(es) failed" if failed else "")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * budget, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": w["desc"], "chains": procs},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "config": {"workload": args.workload, "desc": w["desc"], "chains": procs - failed},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs - failed, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "TF-proxy (torch CPU) -- not the reference binary: R and TensorFlow are absent from this image"}
     print(json.dumps(line))
@@ -511,7 +519,7 @@ def leg_result(leg, w, args):
 def run_leg(args, w):
     """Child side of run_leg_in_child: one JSON object on stdout."""
     if args.leg == "cpu_chain":     # the reference arm's worker: CPU only
-        print(json.dumps(cpu_chain_leg(w, args.cpu_budget)))
+        print(json.dumps(cpu_chain_leg(w, args.cpu_budget, args.steps, args.warmup)))
         return
     import torch
     if not torch.cuda.is_available():
