@@ -240,6 +240,38 @@ def test_cluster_per_chain_walks_the_same_chain(case_name, algo, cv, shared):
     T.test_cluster_per_chain_walks_the_same_chain(None, case_name, algo, cv, shared)
 
 
+def test_default_dispatch_on_a_device_with_many_sms():
+    """The emulated device reports 2 SMs by default, so the library's default dispatch keeps one CTA per chain in most tests here; on a
+    B200 (148 SMs) a handful of chains get a cluster each.  A fresh interpreter with a 64-SM emulated device and the samplers left on
+    the default dispatch: call sequences, save / restore, page-locked output, seeds, device RNG streams against the oracle."""
+    code = """
+from tests.emu import backend
+from tests import cases
+orig = cases.device_setup
+def unpinned(*a, **k):
+    k.setdefault("pin_finder", False)
+    return orig(*a, **k)
+cases.device_setup = unpinned
+from tests import test_parity_gpu as T
+T.device_setup = unpinned
+import ctypes as C
+with backend.emulated() as lib:
+    lib.emu_note_count.restype = C.c_longlong; lib.emu_note_count.argtypes = [C.c_char_p]
+    T.test_call_sequences_walk_one_rng_stream(None, "logistic54", "sgnht", True)
+    T.test_saved_state_resumes_the_run_bit_for_bit(None, "logistic130", "sghmc", True, False)
+    T.test_sampling_into_a_page_locked_array_equals_the_staged_copy(None, "logistic54", "sgld", True, 230, 3)
+    T.test_last_stored_state_is_the_sampler_state(None, "logistic54", "sghmc")
+    T.test_same_seed_reproduces(None)
+    T.test_device_rng_streams_match_oracle(None, "logistic54", "sgld", True)
+    T.test_device_rng_streams_match_oracle(None, "logistic130", "sgnht", True)
+    assert lib.emu_note_count(b"logistic_split:sample") > 500 and lib.emu_note_count(b"logistic_opt_split") > 5
+    assert not lib.emu_last_message()
+print("default dispatch ok")
+"""
+    out = backend.run_isolated(code, env={"SGM_EMU_SMS": "64"})
+    assert out.returncode == 0 and "default dispatch ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 def test_mode_finder_cluster_split_equals_one_cta_per_mode(emulated_library):
     """Device-drawn minibatches: the cluster of CTAs draws exactly the rows the one-CTA finder draws (same keyed permutation, positions
     split over the ranks), so both arrive at the same mode up to the order of the float32 sums; 137 steps cross the 100-iteration
