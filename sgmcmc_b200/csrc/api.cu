@@ -591,12 +591,15 @@ static int launch_logistic_staged(sgm_handle* h, const ChainArgs& a) {
 // CTAs per chain: the largest power of two <= 8 that still leaves every CTA LSP_MIN_ROWS minibatch rows and fits chains x CTAs on the
 // device; 1 = keep one CTA per chain (many chains: the SMs are busy anyway).  opt: 0 = that rule, 1 = never, 2 / 4 / 8 = that cluster size
 constexpr int LSP_MIN_ROWS = 16;
-static int split_of(int opt, int chains, int n, int sms) {
+static int split_of(int opt, int chains, int n, int sms, int ld) {
     if (opt == 1) return 1;
+    if (opt >= 2) { int split = 1; while (split * 2 <= opt) split *= 2; if (n / split < 1) split = 1; return split; }
     int split = 1;
     for (int s = 2; s <= LSP_MAX_SPLIT; s *= 2)
         if ((int64_t)chains * s <= sms && n / s >= LSP_MIN_ROWS) split = s;
-    if (opt >= 2) { split = 1; while (split * 2 <= opt) split *= 2; if (n / split < 1) split = 1; }
+    // short rows: a cluster of 2 spends about as many issue slots per step as the short-row kernel does on one SM (G lanes per row
+    // against a lane per row); the split pays from 4 CTAs on.  Long rows are bound by one SM's load path: 2 CTAs already halve it
+    if (split == 2 && ld <= 128) split = 1;
     return split;
 }
 // the cluster size a launch of this handle would use (1: one CTA per chain).  Same rule for the mode finder ("mode_finder_split") and
@@ -607,7 +610,7 @@ static int logistic_split_for(const sgm_handle* h, const ChainArgs& a, int sms) 
     const bool finder = a.algo == ALGO_OPT && !a.cv && a.L == 1;
     const int opt = finder ? h->opt_mode_finder_split : h->opt_chain_split;
     if (opt == 0 && (h->opt_logistic_kernel || h->opt_gather)) return 1;   // a pinned one-CTA kernel path is what the caller wants to run
-    return split_of(opt, a.C, a.n, sms);
+    return split_of(opt, a.C, a.n, sms, h->ld);
 }
 
 // *launched = false: the device cannot co-schedule such a cluster (or refuses the launch configuration) -- the caller falls back to
@@ -2238,7 +2241,7 @@ extern "C" int sgm_debug_plan(const sgm_plan_query* q, char* out, size_t cap) {
             };
             chain(h->C, "sampling");
             if (h->cv) {
-                const int split = split_of(h->opt_mode_finder_split, M, h->n, sms);
+                const int split = split_of(h->opt_mode_finder_split, M, h->n, sms, h->ld);
                 if (split > 1 && lsp_smem_bytes(s.G, s.V, h->ld, h->n, split) <= 227 * 1024) {
                     char note[160];
                     int clusters = sms / split; if (clusters > M) clusters = M;
