@@ -42,7 +42,8 @@ BENCHED = ["logistic54_n500", "logistic1024_n1024_N3000",   # the template insta
 def test_deterministic_steps_match_oracle(case_name, algo, mode):
     if mode == "cv_shared" and case_name in ("gauss1d", "gauss3d_fullcov", "gauss2d_flat"):
         pytest.skip("shared-mode variant is covered by gauss2d")
-    T._deterministic_steps(case_name, algo, mode != "plain", shared=(mode == "cv_shared"))
+    # (12 mode-finder steps instead of the GPU suite's 25: the float32 autograd replica of the oracle is what takes the time here)
+    T._deterministic_steps(case_name, algo, mode != "plain", shared=(mode == "cv_shared"), n_opt=None if case_name.startswith("logistic1024") else 12)
 
 
 @pytest.mark.parametrize("case_name,algo,cv", [("gauss2d", "sgld", False), ("mixture", "sghmc", False), ("logistic54", "sgld", True),
