@@ -416,6 +416,9 @@ def device_leg(sg, lib, V, _lib, I, steps, warmup, barrier):
     return time.perf_counter() - t0, kernel_ms, launches
 
 
+QUICK_ITERS = 550   # sgmcmcSteps per launch of the compact c1 / c2 measurements
+
+
 def quick_workload(name, steps=5, iters=None):
     """A compact device-resident measurement of another BASELINE config (N = 1 only), for the same JSON line."""
     import sgmcmc_b200 as S
@@ -423,7 +426,7 @@ def quick_workload(name, steps=5, iters=None):
     from sgmcmc_b200 import validation as V
     import torch
     w = workload(name, None)
-    I = iters or (550 if name in ("c1", "c2") else 20)
+    I = iters or (QUICK_ITERS if name in ("c1", "c2") else 20)
     lib = _lib.load()
     sg = make_sampler(w, 0, 1, w["chains"])
     S.initSess(sg, verbose=False)

@@ -52,6 +52,7 @@ def test_bench_prints_one_contract_line(monkeypatch, main):
     monkeypatch.setattr(__graft_entry__, "build", lambda *a, **k: None)
     monkeypatch.setattr(bench, "measure_tf32_peak", lambda *a, **k: (900.0, 800.0))
     monkeypatch.setattr(bench, "ONE_CHAIN_ITERS", 150)   # (emulated kernels: keep the one-chain latency leg short)
+    monkeypatch.setattr(bench, "QUICK_ITERS", 60)
     monkeypatch.setattr(bench, "probe_cluster_finder", lambda *a, **k: {"ok": True, "checks": []})   # (a child process of the real probe finds no GPU here)
     # the optional legs run in child processes on a GPU box; here (emulated build, loaded into THIS process) they run in place
     monkeypatch.setattr(bench, "run_leg_in_child", lambda leg, args, timeout_s=0: bench.leg_result(leg, bench.workload(args.workload, None), args))
