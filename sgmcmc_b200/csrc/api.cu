@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <algorithm>
@@ -201,6 +202,15 @@ __global__ void pack_rows_kernel(const double* __restrict__ src, int64_t N, int 
     if (i >= N * cols) return;
     const int64_t r = row_major ? i / cols : i % N; const int c = (int)(row_major ? i % cols : i / N);
     dst[r * ld + col0 + c] = (float)src[i];
+}
+
+// float rows of one dataset entry, [rows][cols] row-major (a slab converted on the host) -> rows [row0, row0 + rows) of the dataset at
+// column offset col0
+__global__ void pack_slab_kernel(const float* __restrict__ src, int64_t rows, int cols, float* __restrict__ dst, int64_t row0, int ld, int col0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols; const int c = (int)(i - r * cols);
+    dst[(row0 + r) * ld + col0 + c] = src[i];
 }
 
 __global__ void unpack_rows_kernel(const float* __restrict__ src, int64_t row0, int64_t rows, int cols, int ld, int col0, double* __restrict__ dst) {
@@ -1007,6 +1017,103 @@ struct Timer {
     }
 };
 
+
+// ------------------------------------------------------------------------------------
+// dataset upload: the caller's double matrix (column-major as R holds it, or row-major) -> float rows on the device
+// ------------------------------------------------------------------------------------
+// A cudaMemcpy from pageable memory is staged by the driver on one thread, and it would ship doubles.  Instead host threads convert
+// slabs of rows to float32 straight into page-locked staging (half the PCIe bytes; (float)x on the host is the device's
+// __double2float_rn), two slabs in flight: slab k + 1 is converted while slab k crosses the bus and is packed into the padded rows.
+// The staging is process-level (2 x 32 MB, page-locked once: like the CUDA context it is paid for by the first sampler of a process).
+namespace {
+constexpr size_t UP_SLAB_BYTES = 32u << 20;
+struct UploadStaging {
+    std::mutex mu;
+    float* host[2] = {nullptr, nullptr};
+    bool tried = false;
+};
+UploadStaging g_upload;
+
+void convert_rows(const double* A, int64_t N, int cols, int row_major, int64_t r0, int64_t r1, int64_t slab_r0, float* out) {
+    if (row_major) {
+        const double* s_ = A + r0 * cols;
+        float* d_ = out + (r0 - slab_r0) * cols;
+        const int64_t cnt = (r1 - r0) * cols;
+        for (int64_t i = 0; i < cnt; ++i) d_[i] = (float)s_[i];
+        return;
+    }
+    // column-major source: tiles of 256 rows keep the strided writes inside the cache while every column is read contiguously
+    for (int64_t t0 = r0; t0 < r1; t0 += 256) {
+        const int64_t t1 = t0 + 256 < r1 ? t0 + 256 : r1;
+        for (int c = 0; c < cols; ++c) {
+            const double* col = A + (size_t)c * N;
+            float* d_ = out + (t0 - slab_r0) * cols + c;
+            for (int64_t r = t0; r < t1; ++r, d_ += cols) *d_ = (float)col[r];
+        }
+    }
+}
+}  // namespace
+
+// entry A ([N][cols] doubles on the host) -> dst rows [0, N) at column col0 (row stride ld floats), on `stream`; returns a cudaError_t
+static cudaError_t upload_entry(const double* A, int64_t N, int cols, int row_major, float* dst, int ld, int col0, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_upload.mu);
+    if (!g_upload.tried) {
+        g_upload.tried = true;
+        for (int b = 0; b < 2; ++b)
+            if (cudaHostAlloc(&g_upload.host[b], UP_SLAB_BYTES, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g_upload.host[b] = nullptr; }
+    }
+    float* dev[2] = {nullptr, nullptr};
+    cudaEvent_t packed[2] = {nullptr, nullptr};
+    const bool staged = g_upload.host[0] && g_upload.host[1];
+    cudaError_t e = cudaSuccess;
+    const size_t dev_slab = std::min<size_t>(UP_SLAB_BYTES, (size_t)N * cols * sizeof(float));   // a small entry needs a small slab
+    if (staged) {
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) { e = cudaMalloc(&dev[b], dev_slab); if (e == cudaSuccess) e = cudaEventCreate(&packed[b]); }
+    }
+    if (!staged || e != cudaSuccess) {
+        // no page-locked staging (or no room for the two device slabs): the whole entry as doubles, converted by a kernel
+        cudaGetLastError();
+        for (int b = 0; b < 2; ++b) { if (dev[b]) cudaFree(dev[b]); if (packed[b]) cudaEventDestroy(packed[b]); }
+        double* stage = nullptr;
+        const size_t bytes = (size_t)N * cols * sizeof(double);
+        if ((e = cudaMalloc(&stage, bytes)) != cudaSuccess) return e;
+        e = cudaMemcpyAsync(stage, A, bytes, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) { SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(N * cols, 256), 256, 0, stream, stage, N, cols, dst, ld, col0, row_major); e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(stage);
+        return e;
+    }
+    size_t slab_bytes = UP_SLAB_BYTES;
+#ifdef SGM_EMU   // the CPU-emulated test build shrinks the slabs so that toy datasets take several (double buffering, threads, tails)
+    if (const char* sb = getenv("SGM_EMU_UPLOAD_SLAB")) { const size_t v = (size_t)atoll(sb); if (v >= 64 && v <= UP_SLAB_BYTES) slab_bytes = v; }
+#endif
+    const int64_t slab_rows = std::max<int64_t>(1, (int64_t)(slab_bytes / sizeof(float)) / cols);
+    unsigned hw = std::thread::hardware_concurrency();
+    const int T = (int)(hw ? (hw > 8 ? 8 : hw) : 1);
+    int k = 0;
+    for (int64_t r0 = 0; r0 < N && e == cudaSuccess; r0 += slab_rows, ++k) {
+        const int b = k & 1;
+        const int64_t r1 = r0 + slab_rows < N ? r0 + slab_rows : N, rows = r1 - r0;
+        if (k >= 2) e = cudaEventSynchronize(packed[b]);          // the slab that used these buffers two rounds ago has left them
+        if (e != cudaSuccess) break;
+        if ((rows * cols < (1 << 16) && slab_bytes == UP_SLAB_BYTES) || T == 1 || rows < T) convert_rows(A, N, cols, row_major, r0, r1, r0, g_upload.host[b]);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; ++t) th.emplace_back(convert_rows, A, N, cols, row_major, r0 + rows * t / T, r0 + rows * (t + 1) / T, r0, g_upload.host[b]);
+            for (auto& x : th) x.join();
+        }
+        e = cudaMemcpyAsync(dev[b], g_upload.host[b], (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) break;
+        SGM_LAUNCH(pack_slab_kernel, (unsigned)cdiv(rows * cols, 256), 256, 0, stream, (const float*)dev[b], rows, cols, dst, r0, ld, col0);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(packed[b], stream);
+    }
+    const cudaError_t es = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = es;
+    for (int b = 0; b < 2; ++b) { cudaFree(dev[b]); cudaEventDestroy(packed[b]); }
+    return e;
+}
+
 // ------------------------------------------------------------------------------------
 // create
 // ------------------------------------------------------------------------------------
@@ -1161,20 +1268,11 @@ extern "C" int sgm_create(const sgm_config* cfg, sgm_handle** out) {
         CUB(cudaMemsetAsync(h->X, 0, xbytes, h->stream));
         int col0 = 0;
         const int entries = (h->model == SGM_MODEL_GAUSS_MEAN || h->model == SGM_MODEL_MIXTURE2) ? 1 : 2;
-        // one double staging buffer per dataset entry, in the caller's layout (freed before the next entry is staged)
         for (int k = 0; k < entries; ++k) {
             const sgm_array& A = cfg->data[k];
             const int cols = A.ndim >= 2 ? (int)A.dims[1] : 1;
-            double* stage = nullptr;
-            const size_t bytes = (size_t)h->N * cols * sizeof(double);
-            if (cudaMalloc(&stage, bytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(SGM_ENOMEM, "cannot allocate %zu staging bytes", bytes)); }
-            cudaError_t se = cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream);
-            if (se == cudaSuccess) {
-                SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(h->N * cols, 256), 256, 0, h->stream, stage, h->N, cols, h->X, h->ld, col0, (int)(A.row_major != 0));
-                se = cudaGetLastError();
-            }
-            if (se == cudaSuccess) se = cudaStreamSynchronize(h->stream);
-            cudaFree(stage);
+            const cudaError_t se = upload_entry(A.data, h->N, cols, (int)(A.row_major != 0), h->X, h->ld, col0, h->stream);
+            if (se == cudaErrorMemoryAllocation) { cudaGetLastError(); return bail(fail(SGM_ENOMEM, "cannot allocate staging for the dataset upload")); }
             if (se != cudaSuccess) return bail(fail(SGM_ECUDA, "dataset upload failed: %s", cudaGetErrorString(se)));
             col0 += cols;
         }
@@ -2085,14 +2183,7 @@ extern "C" int sgm_heldout_loglik(sgm_handle* h, const sgm_array* data, int32_t 
         const int cols = A.ndim >= 2 ? (int)A.dims[1] : 1;
         const int want = (k == 0) ? h->d : (h->ld >= h->d + cols ? cols : -1);
         if (!A.data || A.dims[0] != Nh || (k == 0 && cols != want) || want < 0) return fail(SGM_EINVAL, "held-out entry %d has the wrong shape", k);
-        DevBuf<double> stage_buf;
-        const size_t bytes = (size_t)Nh * cols * sizeof(double);
-        if (cudaMalloc(&stage_buf.p, bytes) != cudaSuccess) { cudaGetLastError(); return fail(SGM_ENOMEM, "cannot allocate staging"); }
-        double* stage = stage_buf.p;
-        CU(cudaMemcpyAsync(stage, A.data, bytes, cudaMemcpyHostToDevice, h->stream));
-        SGM_LAUNCH(pack_rows_kernel, (unsigned)cdiv(Nh * cols, 256), 256, 0, h->stream, stage, Nh, cols, Xh, h->ld, col0, (int)(A.row_major != 0));
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(h->stream));
+        CU(upload_entry(A.data, Nh, cols, (int)(A.row_major != 0), Xh, h->ld, col0, h->stream));
         col0 += cols;
     }
     ChainArgs a = h->base;

@@ -241,6 +241,26 @@ def test_cluster_per_chain_walks_the_same_chain(case_name, algo, cv, shared):
     T.test_cluster_per_chain_walks_the_same_chain(None, case_name, algo, cv, shared)
 
 
+def test_dataset_upload_in_many_slabs():
+    """The upload converts slabs of rows to float32 on host threads into page-locked staging, two slabs in flight (32 MB each on a
+    device: the toy datasets here are one slab).  A fresh interpreter with 4 KB slabs: C-order / column-major / strided inputs of every
+    family upload identically over dozens of slabs with ragged tails, the held-out set included."""
+    code = """
+from tests.emu import backend
+from tests import test_parity_gpu as T
+with backend.emulated() as lib:
+    for case in ("gauss2d", "logistic54", "softmaxnet_small", "logistic130"):
+        T.test_dataset_layouts_upload_identically(None, case)
+    T.test_heldout_loglik_matches_oracle(None, "logistic54")
+    T.test_heldout_loglik_matches_oracle(None, "mixture")
+    T._deterministic_steps("logistic54_n101", "sgld", True, shared=True)
+    assert not lib.emu_last_message()
+print("slab upload ok")
+"""
+    out = backend.run_isolated(code, env={"SGM_EMU_UPLOAD_SLAB": "4096"})
+    assert out.returncode == 0 and "slab upload ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 def test_default_dispatch_on_a_device_with_many_sms():
     """The emulated device reports 2 SMs by default, so the library's default dispatch keeps one CTA per chain in most tests here; on a
     B200 (148 SMs) a handful of chains get a cluster each.  A fresh interpreter with a 64-SM emulated device and the samplers left on
