@@ -624,6 +624,8 @@ def run_ours(args, w):
     k_ms = float(np.mean(kernel_ms))
     achieved = chains_local * I * w["bytes_per_chain_iter"] / (k_ms * 1e-3) / 1e9
     dataset_mb = {"c1": 0.08, "c2": 0.08, "c3": 130.1, "c4": 191.0, "c5": 51400.0}.get(args.workload)
+    if w.get("synth"):   # generated on the device: rows x padded row (d + y, a multiple of 4 floats) x 4 bytes
+        dataset_mb = w["synth"]["rows"] * 4 * (w["synth"]["dim"] // 4 + 1) * 4 / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
